@@ -1,0 +1,295 @@
+"""Pin ``oracle/`` against the golden vectors produced by the live reference
+(``tests/golden/make_golden.py``).  CPU only.
+
+Bars: bit-exact for indices / masks / schedules tables / interpolation / DDIM arithmetic
+(fp32 op-for-op), <= 2 ulp where a libm transcendental is involved (sigmoid / logit),
+1e-5 max-abs for the dense model forwards (different BLAS summation order only).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser_torch as dn
+from oracle import diffusion_np as df
+from oracle import generate as og
+from oracle import keyframes_np as kf
+from oracle import sampling_np as sp
+
+SCHED = {0: "doubling", 1: "linear", 2: "geom"}
+
+
+def eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(a, b), f"max diff {np.abs(a.astype(np.float64) - b.astype(np.float64)).max()}"
+
+
+def ulp_close(a, b, ulps=2):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    assert a.shape == b.shape
+    tol = ulps * np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32))
+    assert np.all(np.abs(a - b) <= tol), f"max diff {np.abs(a - b).max()}"
+
+
+# ------------------------------------------------------------------ keyframes
+def test_k_schedule(golden):
+    g = golden("keyframes")
+    for row in g["ksched"]:
+        T, K, S, sc = [int(v) for v in row[:4]]
+        want = [int(v) for v in row[4:4 + S + 1]]
+        assert kf.compute_k_schedule(T, K, S, SCHED[sc]) == want
+    # SURVEY 8c known answers
+    assert kf.compute_k_schedule(64, 8, 3) == [64, 32, 16, 8]
+    assert kf.compute_k_schedule(256, 32, 4) == [256, 256, 128, 64, 32]
+    assert kf.compute_k_schedule(64, 8, 3, "linear") == [64, 45, 27, 8]
+    assert kf.compute_k_schedule(256, 32, 4, "geom") == [256, 152, 91, 54, 32]
+    assert kf.compute_k_schedule(128, 8, 3, "geom") == [128, 51, 20, 8]
+
+
+def test_uniform_indices(golden):
+    g = golden("keyframes")
+    for row in g["uniform"]:
+        T, K = int(row[0]), int(row[1])
+        idx, mask = kf.sample_fixed_k_indices_uniform_batch(2, T, K)
+        eq(idx[0], row[2:2 + K])
+        eq(idx[1], row[2:2 + K])
+        assert mask.sum(axis=1).tolist() == [K, K]
+    eq(kf.sample_fixed_k_indices_uniform_batch(1, 64, 8)[0][0], [0, 9, 18, 27, 36, 45, 54, 63])
+    for tag in "ab":
+        B, T, K, jit = g[f"unij_{tag}_cfg"]
+        idx, mask = kf.sample_fixed_k_indices_uniform_batch(int(B), int(T), int(K), jitter=float(jit), u=g[f"unij_{tag}_u"])
+        eq(idx, g[f"unij_{tag}_idx"])
+        eq(mask, g[f"unij_{tag}_mask"])
+
+
+def test_fixed_k_indices(golden):
+    g = golden("keyframes")
+    for tag in "abcde":
+        B, T, K, ee = [int(v) for v in g[f"fixk_{tag}_cfg"]]
+        idx, mask = kf.sample_fixed_k_indices_batch(g[f"fixk_{tag}_scores"], B, T, K, bool(ee))
+        eq(idx, g[f"fixk_{tag}_idx"])
+        eq(mask, g[f"fixk_{tag}_mask"])
+
+
+def test_nested_masks_batch(golden):
+    g = golden("keyframes")
+    for tag in "abcdetfg":
+        B, T, K, S, sc = [int(v) for v in g[f"nest_{tag}_cfg"]]
+        masks, idxs = kf.build_nested_masks_batch(g[f"nest_{tag}_scores"], T, K, S, SCHED[sc])
+        eq(masks, g[f"nest_{tag}_masks"])
+        for s in range(S + 1):
+            eq(idxs[s], g[f"nest_{tag}_idx{s}"])
+        # closed form used by the kernel: rank < K_s - 2
+        rank = kf.stable_rank(g[f"nest_{tag}_scores"])
+        K_list = kf.compute_k_schedule(T, K, S, SCHED[sc])
+        for s in range(S + 1):
+            m = np.zeros((B, T), bool)
+            m[:, 0] = m[:, -1] = True
+            if T > 2:
+                m[:, 1:-1] = rank < K_list[s] - 2
+            eq(m, g[f"nest_{tag}_masks"][:, s])
+
+
+def test_nested_masks_from_base_logits(golden):
+    g = golden("keyframes")
+    for tag in "ab":
+        B, T, K, S = [int(v) for v in g[f"base_{tag}_cfg"]]
+        perms = [g[f"base_{tag}_perm{i}"] for i in range(int(g[f"base_{tag}_nperm"][0]))]
+        masks, idxs = kf.build_nested_masks_from_base(g[f"base_{tag}_idx_base"], T, S, perms)
+        eq(masks, g[f"base_{tag}_masks"])
+        for s in range(S + 1):
+            eq(idxs[s], g[f"base_{tag}_idx{s}"])
+    masks, idxs = kf.build_nested_masks_from_logits(g["logit_logits"], 4, 2)
+    eq(masks, g["logit_masks"])
+    for s in range(3):
+        eq(idxs[s], g[f"logit_idx{s}"])
+    masks, idxs = kf.build_nested_masks_from_level_logits(g["lvl_logits"], 4, 2)
+    eq(masks, g["lvl_masks"])
+    for s in range(3):
+        eq(idxs[s], g[f"lvl_idx{s}"])
+
+
+def test_interpolate_from_indices(golden):
+    g = golden("keyframes")
+    for tag in "abcdefg":
+        B, T, K, D, vel = [int(v) for v in g[f"interp_{tag}_cfg"]]
+        y = kf.interpolate_from_indices(g[f"interp_{tag}_idx"], g[f"interp_{tag}_vals"], T, bool(vel))
+        eq(y, g[f"interp_{tag}_y"])
+    eq(kf.interpolate_from_indices(g["interp_x_idx"], g["interp_x_vals"], 16), g["interp_x_y"])
+    ka = kf.interpolate_from_indices(np.array([[0, 3, 6, 7]]), np.array([[[0.0], [3.0], [12.0], [7.0]]], np.float32), 8)
+    eq(ka, g["interp_ka_y"])
+    eq(ka[0, :, 0], [0, 1, 2, 3, 6, 9, 12, 7])
+
+
+def test_interpolate_from_mask(golden):
+    g = golden("keyframes")
+    # legacy loop (linspace weights) differs from the vectorised contract by <= 1 ulp of the values
+    y = kf.interpolate_from_mask(g["imask_x"], g["imask_m"], False)
+    np.testing.assert_allclose(y, g["imask_y"], rtol=0, atol=2.4e-7)
+    yv = kf.interpolate_from_mask(g["imask_x"], g["imask_m"], True)
+    np.testing.assert_allclose(yv[..., :2], g["imask_yv"][..., :2], rtol=0, atol=2.4e-7)
+    np.testing.assert_allclose(yv[..., 2:], g["imask_yv"][..., 2:], rtol=0, atol=24 * 2.4e-7 * 2)
+    # reference tests/test_corruption.py:9-23
+    x = np.array([[0.0], [2.0], [4.0], [6.0], [8.0]], np.float32)
+    m = np.array([1, 0, 0, 0, 1], bool)
+    np.testing.assert_allclose(kf.interpolate_from_mask(x, m), x)
+
+
+# ------------------------------------------------------------------ diffusion
+def test_schedules(golden):
+    """The tables are a one-off host computation whose last bit is host-libm dependent in the reference
+    itself: torch's AVX512 ``sqrt`` is not correctly rounded (0.6 % of inputs are 1 ulp off IEEE, measured
+    here) and ``cos`` comes from SLEEF.  The oracle restates the formula with IEEE numpy ops and is held to
+    table-level tolerances; the DDIM arithmetic that CONSUMES a given table is bit-exact (next tests)."""
+    g = golden("diffusion")
+    for name in ("linear", "cosine"):
+        for n in (10, 200, 1000):
+            sch = df.make_alpha_bars(df.make_beta_schedule(name, n))
+            for k in ("betas", "alphas", "alpha_bar"):
+                if name == "linear":
+                    eq(sch[k], g[f"sched_{name}_{n}_{k}"])          # linspace + 1-x + cumprod: exact
+                else:
+                    np.testing.assert_allclose(sch[k], g[f"sched_{name}_{n}_{k}"], rtol=2e-6, atol=1e-6)
+            np.testing.assert_allclose(sch["sqrt_alpha_bar"], g[f"sched_{name}_{n}_sqrt_alpha_bar"], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(sch["sqrt_one_minus_alpha_bar"], g[f"sched_{name}_{n}_sqrt_one_minus_alpha_bar"],
+                                       rtol=0, atol=3e-6)
+    sch = df.make_alpha_bars(df.make_beta_schedule("cosine", 1000))
+    assert abs(sch["alpha_bar"][999] - 2.429e-9) < 2e-11
+    assert abs(sch["alpha_bar"][896] - 2.555e-2) < 1e-4
+
+
+def test_timesteps(golden):
+    g = golden("diffusion")
+    for key in g:
+        if not key.startswith("ts_"):
+            continue
+        _, n, steps, sched = key.split("_")
+        eq(df.timesteps(int(n), int(steps), sched), g[key])
+    eq(df.timesteps(1000, 20, "quadratic"),
+       [999, 896, 799, 708, 622, 542, 467, 398, 334, 276, 224, 177, 135, 99, 69, 44, 24, 11, 2, 0])
+
+
+def test_ddim_and_q_sample(golden):
+    g = golden("diffusion")
+    sch = {k: g[f"sched_cosine_1000_{k}"] for k in ("betas", "alphas", "alpha_bar", "sqrt_alpha_bar", "sqrt_one_minus_alpha_bar")}
+    z, eps = g["ddim_z"], g["ddim_eps"]
+    for i, (t, tp) in enumerate(g["ddim_pairs"]):
+        out = df.ddim_step(z, eps, np.full((8,), t), np.full((8,), tp), sch)
+        eq(out, g[f"ddim_{i}_out"])
+        c1, c2, c3, c4 = df.ddim_coefficients(sch["alpha_bar"], int(t), int(tp))
+        eq((c3 * ((z - c1 * eps) / c2) + c4 * eps).astype(np.float32), g[f"ddim_{i}_out"])
+    eq(df.ddim_step(z, eps, g["ddim_v_t"], g["ddim_v_tp"], sch), g["ddim_v_out"])
+    out = df.ddim_step(z, eps, g["ddim_v_t"], g["ddim_v_tp"], sch, eta=0.5, noise=g["ddim_eta_noise"])
+    np.testing.assert_allclose(out, g["ddim_eta_out"], rtol=2e-6, atol=1e-6)
+    eq(df.q_sample(z, g["ddim_v_t"], sch, g["q_noise"])[0], g["q_out"])
+
+
+# ------------------------------------------------------------------ sampling helpers
+def test_clamp_normalize(golden):
+    g = golden("sampling")
+    xh, xr, m, c = g["cl_x_hat"], g["cl_x_ref"], g["cl_mask"], g["cl_conf"]
+    eq(sp.apply_clamp(xh.copy(), xr, m, "pos"), g["cl_hard_pos"])
+    eq(sp.apply_clamp(xh.copy(), xr, m, "all"), g["cl_hard_all"])
+    eq(sp.apply_soft_clamp(xh.copy(), xr, c, 0.7, "pos"), g["cl_soft_pos"])
+    eq(sp.apply_soft_clamp(xh.copy(), xr, c, 0.7, "all"), g["cl_soft_all"])
+    ulp_close(sp.logit_pos(g["nz_p"]), g["nz_logit"], 4)
+    ulp_close(sp.sigmoid_pos(xh * 3), g["nz_sigmoid"], 2)
+
+
+def test_known_conf_anneal(golden):
+    g = golden("sampling")
+    for D in (2, 4):
+        km, kv = sp.build_known_mask_values(g["kn_idx"], g["kn_sg"], D, 16, True)
+        eq(km, g[f"kn_mask_{D}"])
+        eq(kv, g[f"kn_vals_{D}"])
+    m = g["cl_mask"]
+    eq(sp.build_anchor_conf(m, m, True, 0.95, 0.5, 1.0, 0.0, True), g["cf_a"])
+    eq(sp.build_anchor_conf(m, None, False, 0.95, 0.5, 1.0, 0.0, True), g["cf_b"])
+    eq(sp.build_anchor_conf(m, g["cf_student"], True, 0.9, 0.4, 0.8, 0.1, False), g["cf_c"])
+    for mode in ("linear", "cosine", "none"):
+        for s in (1, 2, 3):
+            eq(sp.anneal_conf(g["cf_b"].copy(), s, 3, mode), g[f"an_{mode}_{s}"])
+    eq(sp.anneal_conf(g["cf_b"].copy(), g["an_s_idx"], 3, "linear"), g["anv_linear"])
+    ulp_close(sp.anneal_conf(g["cf_b"].copy(), g["an_s_idx"], 3, "cosine"), g["anv_cosine"], 4)
+    lam = [sp.soft_clamp_lambda(s, 3, sc, 0.8) for sc in ("linear", "cosine", "const") for s in (0, 1, 2, 3)]
+    np.testing.assert_array_equal(np.array(lam), g["lam"])
+    sj = []
+    for K in (8, 16, 32, 64):
+        sj += [sp.compute_sigma_for_level(K, 8, 0.08, 0.012, 0.75), float(sp.compute_jitter_for_level(K, 8, 3, 1.0))]
+    np.testing.assert_array_equal(np.array(sj), g["sigma_jitter"])
+
+
+def test_corrupt_from_anchors(golden):
+    g = golden("sampling")
+    src, idx = g["co_src"], g["co_idx"]
+    eq(sp.distance_alpha(idx, 32), g["co_alpha"])
+    for tag in "abcd":
+        jit, jprob, mode, vel, sigma, asig = g[f"co_{tag}_cfg"]
+        tape = sp.NoiseTape([g[f"co_{tag}_draw{i}"] for i in range(int(g[f"co_{tag}_n"][0]))])
+        out = sp.corrupt_from_anchors(src, idx, 32, tape, float(sigma), float(asig), int(jit), float(jprob),
+                                      "dist" if mode == 0 else "const", True, bool(vel))
+        assert tape.pos == len(tape.draws)
+        eq(out, g[f"co_{tag}_out"])
+
+
+def test_build_interp_batches(golden):
+    g = golden("sampling")
+    idx_levels = [g[f"ad_idx{s}"] for s in range(4)]
+    xs, xp, ms, mp = sp.build_interp_adjacent_batch(g["ad_x0"], 8, 3, g["ad_masks"], idx_levels, g["ad_s_idx"])
+    eq(xs, g["ad_none_xs"]); eq(xp, g["ad_none_xp"]); eq(ms, g["ad_none_ms"]); eq(mp, g["ad_none_mp"])
+    tape = sp.NoiseTape([g[f"ad_dist_draw{i}"] for i in range(int(g["ad_dist_n"][0]))])
+    xs, xp, ms, mp = sp.build_interp_adjacent_batch(
+        g["ad_x0"], 8, 3, g["ad_masks"], idx_levels, g["ad_s_idx"], tape, corrupt_mode="dist",
+        corrupt_sigma_max=0.08, corrupt_sigma_min=0.012, corrupt_sigma_pow=0.75, corrupt_anchor_frac=0.25)
+    assert tape.pos == len(tape.draws)
+    eq(xs, g["ad_dist_xs"]); eq(xp, g["ad_dist_xp"])
+    xs, ms = sp.build_interp_level_batch(g["ad_x0"], 8, 3, g["ad_masks"], idx_levels, g["ad_s_idx"])
+    eq(xs, g["lv_none_xs"]); eq(ms, g["lv_none_ms"])
+
+
+# ------------------------------------------------------------------ dense models (tiny config)
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def test_denoisers_tiny(golden):
+    g = golden("models_tiny")
+    t = lambda k: torch.from_numpy(g[k])
+    cond = {"occ": t("kp2_occ"), "start_goal": t("kp2_sg")}
+    sd = _sd(g, "kp2/")
+    np.testing.assert_allclose(dn.cond_encoder(sd, cond).numpy(), g["kp2_condvec"], atol=1e-5, rtol=0)
+    eps = dn.keypoint_denoiser(sd, 2, t("kp2_z"), t("kp2_t"), t("kp2_idx"), t("kp2_km"), cond, 16)
+    np.testing.assert_allclose(eps.numpy(), g["kp2_eps"], atol=1e-5, rtol=0)
+    cond4 = {"occ": t("kp4_occ"), "start_goal": t("kp4_sg"), "sdf": t("kp4_sdf"), "kp_feat": t("kp4_kpfeat")}
+    eps = dn.keypoint_denoiser(_sd(g, "kp4/"), 2, t("kp4_z"), t("kp2_t"), t("kp2_idx"), t("kp4_km"), cond4, 16)
+    np.testing.assert_allclose(eps.numpy(), g["kp4_eps"], atol=1e-5, rtol=0)
+    for tag, causal in (("il2", False), ("il3", False), ("ic1", True)):
+        out = dn.interp_level_denoiser(_sd(g, tag + "/"), 2, t(f"{tag}_x"), t(f"{tag}_s"), t(f"{tag}_mask"), cond, causal=causal)
+        np.testing.assert_allclose(out.numpy(), g[f"{tag}_out"], atol=1e-5, rtol=0)
+
+
+def test_generate_tiny(golden):
+    g = golden("generate_tiny")
+    cond = {"occ": torch.from_numpy(g["occ"]), "start_goal": torch.from_numpy(g["sg"])}
+    sd_kp, sd_il, sd_il3 = _sd(g, "kp/"), _sd(g, "il/"), _sd(g, "il3/")
+    # teacher-forced per-step check of the Stage-1 loop: feed the reference z_t at every step
+    B, T, K, S, D = 4, 64, 8, 3, 2
+    idx, masks = kf.sample_fixed_k_indices_uniform_batch(B, T, K)
+    km, kv = sp.build_known_mask_values(idx, g["sg"], D, T, True)
+    kv = sp.logit_pos(kv)
+    sched = df.make_alpha_bars(df.make_beta_schedule("cosine", 1000))
+    inter_ref = g["z_inter"]
+    z, inter, _ = og.sample_keypoints_ddim(sd_kp, 2, sched, idx, km, kv, cond, 20, T, g["z_T"], "quadratic",
+                                           return_intermediates=True, teacher_forced=list(inter_ref[:-1]))
+    for i in range(1, inter_ref.shape[0]):
+        scale = max(1.0, np.abs(inter_ref[i]).max())
+        assert np.abs(inter[i] - inter_ref[i]).max() / scale < 2e-4, i
+    # free-running pipeline agrees after sigmoid / interpolation at this (tiny, well-behaved) size
+    for pol in ("none", "endpoints", "all_anchors"):
+        for dims in ("pos", "all"):
+            out = og.generate(sd_kp, sd_il, 2, cond, g["z_T"], T=T, K_min=K, levels=S, D=D, clamp_policy=pol, clamp_dims=dims)
+            np.testing.assert_allclose(out["x_pred"], g["x_pred"], atol=2e-3, rtol=0)
+            np.testing.assert_allclose(out["x_hat"], g[f"x_hat_x0_{pol}_{dims}"], atol=2e-3, rtol=0)
+    out = og.generate(sd_kp, sd_il3, 2, cond, g["z_T"], T=T, K_min=K, levels=S, D=D, stage2_mode="adj",
+                      masks_levels=g["adj_masks_levels"])
+    np.testing.assert_allclose(out["x_hat"], g["x_hat_adj"], atol=2e-3, rtol=0)
