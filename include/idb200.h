@@ -1,0 +1,162 @@
+/*
+ * idb200.h -- C ABI of libidb200.so: the B200 (sm_100a) implementation of the batched
+ * generation-and-corruption hot path of EquilibriaW/Interpolated_Diffusion.
+ *
+ * The reference has no FFI layer (it is pure PyTorch); every entry point below
+ * names the reference Python function (file:line under the reference root) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless marked "host";
+ *   - the caller owns and allocates every buffer; the library never allocates device memory,
+ *     never synchronises the device and only enqueues work on `stream` (so every call is
+ *     CUDA-graph capturable);
+ *   - tensors are dense, row-major, in the reference's own layouts ([B,T,D] trajectories,
+ *     [B,K] int64 indices, uint8 0/1 for torch.bool);
+ *   - return value: 0 on success, a negative IDB200_E* code otherwise; idb200_last_error()
+ *     returns a thread-local human readable message for the last failure.
+ */
+#ifndef IDB200_H
+#define IDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* idb200_stream_t; /* a cudaStream_t */
+
+#define IDB200_OK 0
+#define IDB200_EINVAL (-1)      /* bad shape / size / flag */
+#define IDB200_EALIGN (-2)      /* pointer not aligned as documented */
+#define IDB200_EUNSUPPORTED (-3)/* valid but outside what the kernels cover (e.g. T > 256) */
+#define IDB200_ECUDA (-4)       /* cudaGetLastError() after launch */
+
+int idb200_version(void);
+const char* idb200_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  nested anchor masks + Interp(x0 | M_s)
+ *     replaces src/corruptions/keyframes.py:172-209 (build_nested_masks_batch: argsort of the
+ *     rand scores, per-level cat/sort/scatter_) fused with :348-380 (interpolate_from_indices) as
+ *     used by src/train/train_interp_levels.py:227-383.  Also serves :42-81
+ *     (sample_fixed_k_indices_batch; n_levels = 1) and :260-294 (build_nested_masks_from_logits;
+ *     IDB200_F_DESCENDING with scores = logits + 1, score_stride = T).
+ *
+ *   scores   [B, n] fp32 with row stride `score_stride` elements; n = T-2 (interior positions
+ *            1..T-2) or n = T with IDB200_F_NO_ENDPOINTS.  Finite values only.
+ *   K_list   host, n_levels ints: anchors per level (level 0 finest).  Level s marks t in {0,T-1}
+ *            plus the K_s-2 interior positions of lowest stable rank
+ *            rank(j) = #{u : s_u < s_j or (s_u == s_j and u < j)}   (ties: lower index first).
+ *   masks    [B, n_levels, T] uint8 (0/1) or NULL.
+ *   idx_out  NULL, or int64 buffer holding for level s a dense [B, W_s] block at element offset
+ *            B * (W_0 + ... + W_{s-1}), W_s = (K_s <= 2 || T <= 2) ? 2 : K_s  (endpoint mode),
+ *            W_s = K_s (IDB200_F_NO_ENDPOINTS): ascending anchor positions.
+ *   x0       [B, T, D] fp32, 16-byte aligned, D in {2, 4}; NULL = masks / idx only.
+ *   x_levels output for levels s_lo..s_hi: level s is a dense [B, T, D] block at element offset
+ *            (s - s_lo) * level_stride.  Interp(x0 | M_s): anchors copied exactly, interior
+ *            y = v_l + ((t - i_l) / max(i_r - i_l, 1)) * (v_r - v_l), every fp32 op rounded
+ *            separately (bit-identical to the reference's eager ops).
+ *   IDB200_F_RECOMPUTE_VELOCITY (D == 4): v[t] = (p[t+1] - p[t]) / (1/T), v[T-1] = 0
+ *            (keyframes.py:373-379).
+ * ---------------------------------------------------------------------------------------------- */
+#define IDB200_F_DESCENDING 1
+#define IDB200_F_RECOMPUTE_VELOCITY 2
+#define IDB200_F_NO_ENDPOINTS 4
+
+int idb200_nested_masks_interp(const float* x0, const float* scores, int64_t score_stride, int64_t B, int T,
+                               int D, int n_levels, const int* K_list, uint8_t* masks, int64_t* idx_out,
+                               float* x_levels, int64_t level_stride, int s_lo, int s_hi, int flags,
+                               idb200_stream_t stream);
+
+/* interpolate_from_indices, src/corruptions/keyframes.py:348-380, general form:
+ *   idx [B,K] int64 ascending (duplicates allowed, endpoints not required: linear extrapolation
+ *   outside [idx[0], idx[K-1]] exactly as the reference's clamp of `seg` to [0, K-2] does),
+ *   vals [B,K,D] fp32, y [B,T,D] fp32.  Any D >= 1, T <= 4096, 2 <= K <= T.  */
+int idb200_interpolate_from_indices(const int64_t* idx, const float* vals, int64_t B, int K, int T, int D,
+                                    int recompute_velocity, float* y, idb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1c  training corruption, src/train/train_interp_levels.py:458-510 (_corrupt_from_anchors) with
+ *      :444-455 (_distance_alpha): gather anchors (optionally index-jittered), add anchor noise on
+ *      the position dims (not on endpoints), interpolate, add tent-weighted noise, optionally
+ *      recompute velocity.  Noise tensors are INPUTS (drawn by the caller with the reference's
+ *      generator calls) so results are bit-identical.
+ *   source [B,T,D]; idx [B,K] int64; idx_gather [B,K] int64 or NULL (= idx);
+ *   anchor_noise [B,K,2] or NULL; path_noise [B,T,2] or NULL; mode_dist: 1 = "dist" tent weight.
+ *   row_index  NULL, or int64 [n]: row r of idx/noise corresponds to source / out row row_index[r]
+ *              (the boolean-mask gather/scatter of :328-382 without materialising it); then B = n.
+ * ---------------------------------------------------------------------------------------------- */
+int idb200_corrupt_from_anchors(const float* source, const int64_t* idx, const int64_t* idx_gather,
+                                const float* anchor_noise, const float* path_noise, const int64_t* row_index,
+                                int64_t B, int K, int T, int D, float sigma, float anchor_sigma, int mode_dist,
+                                int clamp_endpoints, int recompute_velocity, float* out,
+                                idb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  DDIM update (+ known-value clamp), src/diffusion/ddpm.py:37-48 (eta = 0) fused with the
+ *     torch.where at src/sample/sample_generate.py:397-399:
+ *       x0 = (z - sqrt(1-ab_t)*eps) / sqrt(ab_t);  z' = sqrt(ab_p)*x0 + sqrt(1-ab_p)*eps
+ *       z' = known_mask ? known_values : z' ;  optional clip of dims 0:2 (:382-386)
+ *     every op rounded separately, IEEE sqrt/div.  n_rows rows of `row_len` elements; the
+ *     timestep of row i is t[i] / t_prev[i] (int64, gathered from alpha_bar[n_train]) or, when
+ *     t == NULL, the two scalars ab_t / ab_prev.  known_mask (uint8) / known_values may be NULL.
+ *     D is the innermost (feature) size used by pos_clip.  z_out may alias z.
+ * ---------------------------------------------------------------------------------------------- */
+int idb200_ddim_step(const float* z, const float* eps, const int64_t* t, const int64_t* t_prev,
+                     const float* alpha_bar, int n_train, float ab_t, float ab_prev, int64_t n_rows,
+                     int64_t row_len, int D, const uint8_t* known_mask, const float* known_values,
+                     int pos_clip, float clip_min, float clip_max, float* z_out, idb200_stream_t stream);
+
+/* q_sample, src/diffusion/ddpm.py:15-24: out = sqrt_ab[t]*r0 + sqrt_1m_ab[t]*noise (per-row t). */
+int idb200_q_sample(const float* r0, const float* noise, const int64_t* t, const float* sqrt_ab,
+                    const float* sqrt_1m_ab, int n_train, int64_t n_rows, int64_t row_len, float* out,
+                    idb200_stream_t stream);
+
+/* _build_known_mask_values, src/sample/sample_generate.py:260-280 (+ logit_pos of
+ * src/utils/normalize.py:4-11 when logit_space != 0, as at sample_generate.py:1021-1022).
+ *   idx [B,K] int64, start_goal [B,4]; known_mask [B,K,D] uint8, known_values [B,K,D] fp32. */
+int idb200_known_mask_values(const int64_t* idx, const float* start_goal, int64_t B, int K, int D, int T,
+                             int clamp_endpoints, int logit_space, float logit_eps, uint8_t* known_mask,
+                             float* known_values, idb200_stream_t stream);
+
+/* logit_pos / sigmoid_pos, src/utils/normalize.py:4-20: dims 0:2 of the innermost axis. */
+int idb200_logit_pos(const float* x, int64_t n_rows, int D, float eps, float* out, idb200_stream_t stream);
+int idb200_sigmoid_pos(const float* x, int64_t n_rows, int D, float* out, idb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2b Stage-2 epilogue, src/sample/sample_generate.py:1252-1285 / :1160-1204 with
+ *     src/utils/clamp.py:4-32:
+ *       x = x_in (+ delta if delta != NULL)
+ *       soft:  x[dims] += (conf*lam) * (x_ref[dims] - x[dims])      (conf != NULL and lam > 0)
+ *       hard:  x[dims]  = clamp ? x_ref[dims] : x[dims]             (policy)
+ *       clip:  x[0:2]   = min(max(x, lo), hi)                       (pos_clip)
+ *     dims = 0:2 ("pos", clamp_dims_all == 0) or all D.  policy: 0 none, 1 endpoints (t in
+ *     {0,T-1}), 2 mask (clamp_mask [B,T] uint8).  out may alias x_in.
+ * ---------------------------------------------------------------------------------------------- */
+#define IDB200_CLAMP_NONE 0
+#define IDB200_CLAMP_ENDPOINTS 1
+#define IDB200_CLAMP_MASK 2
+
+int idb200_stage2_epilogue(const float* x_in, const float* delta, const float* x_ref, const float* conf,
+                           float lam, int policy, const uint8_t* clamp_mask, int clamp_dims_all, int pos_clip,
+                           float clip_min, float clip_max, int64_t B, int T, int D, float* out,
+                           idb200_stream_t stream);
+
+/* _build_anchor_conf + _anneal_conf, src/sample/sample_generate.py:319-360 (train twin
+ * src/train/train_interp_levels.py:546-576), and the mask_in stack at :1163-1178 / :1255-1256.
+ *   mask_s [B,T] uint8; student [B,T] uint8 or NULL; s_row int64 [B] or NULL (then scalar s);
+ *   anneal_mode 0 none, 1 linear, 2 cosine.  conf [B,T] fp32 (may be NULL when only mask_in is
+ *   wanted).  mask_in [B,T,C] fp32 or NULL: C == 2 -> [mask_s, conf]; C == 3 -> [mask_s,
+ *   mask_prev, conf] (mask_prev [B,T] uint8 required). */
+int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student, const uint8_t* mask_prev,
+                       const int64_t* s_row, int s_scalar, int levels, int anneal_mode, float conf_teacher,
+                       float conf_student, float conf_endpoints, float conf_missing, int clamp_endpoints,
+                       int64_t B, int T, int C, float* conf, float* mask_in, idb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDB200_H */

@@ -1,0 +1,139 @@
+"""ctypes binding of libidb200.so (C ABI in include/idb200.h).
+
+There is NO fallback: if the shared library is missing or a tensor is not on a CUDA device the
+call raises.  PyTorch is used for device memory, streams and RNG only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libidb200.so")
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_l = ctypes.c_int64
+c_f = ctypes.c_float
+
+# name -> argtypes (restype is always int unless listed in _SPECIAL)
+_SIGS = {
+    "idb200_nested_masks_interp": [c_p, c_p, c_l, c_l, c_i, c_i, c_i, ctypes.POINTER(c_i), c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
+    "idb200_interpolate_from_indices": [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p],
+    "idb200_corrupt_from_anchors": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_f, c_f, c_i, c_i, c_i, c_p, c_p],
+    "idb200_ddim_step": [c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_l, c_l, c_i, c_p, c_p, c_i, c_f, c_f, c_p, c_p],
+    "idb200_q_sample": [c_p, c_p, c_p, c_p, c_p, c_i, c_l, c_l, c_p, c_p],
+    "idb200_known_mask_values": [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p],
+    "idb200_logit_pos": [c_p, c_l, c_i, c_f, c_p, c_p],
+    "idb200_sigmoid_pos": [c_p, c_l, c_i, c_p, c_p],
+    "idb200_stage2_epilogue": [c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_p, c_p],
+    "idb200_anchor_conf": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_l, c_i, c_i, c_p, c_p, c_p],
+}
+
+EINVAL, EALIGN, EUNSUPPORTED, ECUDA = -1, -2, -3, -4
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def declared_symbols():
+    """Every symbol include/idb200.h declares (used by the CPU-side export test)."""
+    return ["idb200_version", "idb200_last_error"] + list(_SIGS)
+
+
+def register(name: str, argtypes) -> None:
+    """Other modules of the package (denoiser kernels) add their entry points here."""
+    _SIGS[name] = argtypes
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_i
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m interpolated_diffusion_b200.csrc.build` "
+                "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.idb200_version.restype = c_i
+        L.idb200_last_error.restype = ctypes.c_char_p
+        for name, argtypes in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = c_i
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().idb200_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        msg = last_error()
+        if rc == EINVAL:
+            raise ValueError(msg)
+        raise RuntimeError(f"{name} failed ({rc}): {msg}")
+
+
+def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("interpolated_diffusion_b200 runs on CUDA (sm_100a) only; got a tensor on "
+                               f"{t.device}.  There is no CPU fallback.")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} and {t.device}")
+    return dev
+
+
+def resolve_device(device) -> torch.device:
+    """Reference default is CPU; this package is CUDA-only, so None means the current CUDA device."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if device is None:
+        raise RuntimeError("interpolated_diffusion_b200 needs a CUDA device (no CPU fallback)")
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"interpolated_diffusion_b200 runs on CUDA only (got device={device}); no CPU fallback")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream(device: Optional[torch.device] = None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def i64c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t.contiguous()
+
+
+def u8c(t: torch.Tensor) -> torch.Tensor:
+    """bool / uint8 tensor as contiguous 1-byte storage (torch.bool is 0/1 bytes)."""
+    if t.dtype not in (torch.bool, torch.uint8):
+        t = t != 0
+    return t.contiguous()

@@ -1,0 +1,251 @@
+// K2 / K2b: the HBM-bound elementwise epilogues around the two denoisers.
+//
+// Reference arithmetic being replaced (paths under the reference root):
+//   src/diffusion/ddpm.py:15-24, 37-48                 q_sample, ddim_step (eta = 0)
+//   src/sample/sample_generate.py:260-280, 319-360     _build_known_mask_values, _build_anchor_conf, _anneal_conf
+//   src/sample/sample_generate.py:397-399, 1252-1285   known clamp, Stage-2 residual / soft / hard clamp
+//   src/utils/clamp.py:4-32, src/utils/normalize.py:4-20
+//
+// Every fp32 op is an explicitly rounded intrinsic in the reference's order (bit-identical to the
+// eager op-by-op evaluation; IEEE sqrt/div).  All kernels are grid-stride with grids sized in
+// multiples of the SM count; traffic is exactly one read of each input and one write of the output.
+#include "common.cuh"
+
+namespace idb200 {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) ddim_step_kernel(
+    const float* __restrict__ z, const float* __restrict__ eps, const long long* __restrict__ t,
+    const long long* __restrict__ t_prev, const float* __restrict__ alpha_bar, float ab_t_s, float ab_p_s, long long n,
+    long long row_len, int D, const unsigned char* __restrict__ known_mask, const float* __restrict__ known_values,
+    int pos_clip, float clip_min, float clip_max, float* __restrict__ out) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float ab_t = ab_t_s, ab_p = ab_p_s;
+        if (t) {
+            const long long row = i / row_len;
+            ab_t = __ldg(alpha_bar + t[row]);
+            ab_p = __ldg(alpha_bar + t_prev[row]);
+        }
+        const float e = eps[i];
+        // x0 = (rt - sqrt(1 - ab_t) * eps) / sqrt(ab_t)                       ddpm.py:45
+        const float x0 = __fdiv_rn(__fsub_rn(z[i], __fmul_rn(__fsqrt_rn(__fsub_rn(1.0f, ab_t)), e)), __fsqrt_rn(ab_t));
+        // rt_prev = sqrt(ab_prev) * x0 + sqrt(1 - ab_prev) * eps               ddpm.py:47
+        float r = __fadd_rn(__fmul_rn(__fsqrt_rn(ab_p), x0), __fmul_rn(__fsqrt_rn(__fsub_rn(1.0f, ab_p)), e));
+        if (known_mask && known_mask[i]) r = known_values[i];                    // sample_generate.py:398
+        if (pos_clip && (i % D) < 2) r = fminf(fmaxf(r, clip_min), clip_max);    // :382-386
+        out[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) q_sample_kernel(const float* __restrict__ r0, const float* __restrict__ noise,
+                                                            const long long* __restrict__ t, const float* __restrict__ sab,
+                                                            const float* __restrict__ s1m, long long n, long long row_len,
+                                                            float* __restrict__ out) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long tt = t[i / row_len];
+        out[i] = __fadd_rn(__fmul_rn(__ldg(sab + tt), r0[i]), __fmul_rn(__ldg(s1m + tt), noise[i]));  // ddpm.py:24
+    }
+}
+
+__device__ __forceinline__ float logit_clamped(float v, float eps) {
+    // normalize.py:9-10: pos.clamp(eps, 1-eps); log(pos / (1 - pos)).  1-eps is the fp32 scalar.
+    const float hi = static_cast<float>(1.0 - static_cast<double>(eps));
+    const float p = fminf(fmaxf(v, eps), hi);
+    return logf(__fdiv_rn(p, __fsub_rn(1.0f, p)));
+}
+
+__device__ __forceinline__ float sigmoid_f(float v) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+}
+
+__global__ void __launch_bounds__(kThreads) known_mask_values_kernel(const long long* __restrict__ idx,
+                                                                     const float* __restrict__ sg, long long B, int K, int D,
+                                                                     int T, int clamp_endpoints, int logit_space,
+                                                                     float logit_eps, unsigned char* __restrict__ km,
+                                                                     float* __restrict__ kv) {
+    const long long n = B * K * D;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int d = static_cast<int>(i % D);
+        const long long bk = i / D;
+        const long long b = bk / K;
+        unsigned char m = 0;
+        float v = 0.0f;
+        if (clamp_endpoints && D >= 2 && d < 2) {
+            const long long ix = idx[bk];
+            if (ix == 0) { m = 1; v = sg[b * 4 + d]; }
+            if (ix == T - 1) { m = 1; v = sg[b * 4 + 2 + d]; }          // goal wins when T == 1 (:278-279)
+        }
+        if (logit_space && D >= 2 && d < 2) v = logit_clamped(v, logit_eps);  // applied to zeros too (harmless, masked)
+        km[i] = m;
+        kv[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) pos_transform_kernel(const float* __restrict__ x, long long n, int D, int mode,
+                                                                 float eps, float* __restrict__ out) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v = x[i];
+        if (D >= 2 && (i % D) < 2) v = mode ? sigmoid_f(v) : logit_clamped(v, eps);
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) stage2_epilogue_kernel(
+    const float* __restrict__ x_in, const float* __restrict__ delta, const float* __restrict__ x_ref,
+    const float* __restrict__ conf, float lam, int policy, const unsigned char* __restrict__ clamp_mask, int dims_all,
+    int pos_clip, float clip_min, float clip_max, long long B, int T, int D, float* __restrict__ out) {
+    const long long n = B * T * D;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int d = static_cast<int>(i % D);
+        const long long bt = i / D;
+        const int t = static_cast<int>(bt % T);
+        float x = x_in[i];
+        if (delta) x = __fadd_rn(x, delta[i]);                                  // x_hat = x_pred + delta_hat
+        const bool in_dims = dims_all || d < 2;
+        if (in_dims) {
+            if (conf && lam > 0.0f) {                                            // clamp.py:26-32
+                const float w = __fmul_rn(conf[bt], lam);
+                x = __fadd_rn(x, __fmul_rn(w, __fsub_rn(x_ref[i], x)));
+            }
+            const bool hard = (policy == IDB200_CLAMP_ENDPOINTS) ? (t == 0 || t == T - 1)
+                              : (policy == IDB200_CLAMP_MASK) ? (clamp_mask[bt] != 0) : false;
+            if (hard) x = x_ref[i];                                              // clamp.py:7-10
+        }
+        if (pos_clip && d < 2) x = fminf(fmaxf(x, clip_min), clip_max);
+        out[i] = x;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) anchor_conf_kernel(
+    const unsigned char* __restrict__ mask_s, const unsigned char* __restrict__ student,
+    const unsigned char* __restrict__ mask_prev, const long long* __restrict__ s_row, int s_scalar, int levels, int anneal,
+    float c_teacher, float c_student, float c_end, float c_missing, int clamp_endpoints, long long B, int T, int C,
+    float* __restrict__ conf, float* __restrict__ mask_in) {
+    const long long n = B * T;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long b = i / T;
+        const int t = static_cast<int>(i - b * T);
+        const bool m = mask_s[i] != 0;
+        float c = m ? c_teacher : c_missing;                                     // sample_generate.py:329-330
+        if (student && m && student[i]) c = c_student;                           // :331-332
+        if (clamp_endpoints && (t == 0 || t == T - 1)) c = c_end;                // :333-335
+        if (anneal && levels > 0) {                                              // :350-360 / train :565-576
+            float lamv;
+            if (s_row) {
+                const float frac = __fdiv_rn(static_cast<float>(s_row[b]), static_cast<float>(levels));
+                lamv = (anneal == 1) ? __fsub_rn(1.0f, frac)
+                                     : __fmul_rn(0.5f, __fadd_rn(1.0f, cosf(__fmul_rn(3.14159274101257324f, frac))));
+            } else {
+                const double frac = static_cast<double>(s_scalar) / static_cast<double>(levels);
+                lamv = static_cast<float>((anneal == 1) ? 1.0 - frac : 0.5 * (1.0 + cos(3.141592653589793 * frac)));
+            }
+            c = __fadd_rn(c, __fmul_rn(__fsub_rn(1.0f, c), lamv));
+        }
+        if (conf) conf[i] = c;
+        if (mask_in) {
+            float* mi = mask_in + i * C;
+            mi[0] = m ? 1.0f : 0.0f;
+            if (C == 3) { mi[1] = mask_prev[i] ? 1.0f : 0.0f; mi[2] = c; }
+            else mi[1] = c;
+        }
+    }
+}
+
+static inline int ew_grid(long long n) { return grid_for(n, kThreads * 4, 8); }
+
+}  // namespace idb200
+
+using namespace idb200;
+
+extern "C" int idb200_ddim_step(const float* z, const float* eps, const int64_t* t, const int64_t* t_prev,
+                                const float* alpha_bar, int n_train, float ab_t, float ab_prev, int64_t n_rows,
+                                int64_t row_len, int D, const uint8_t* known_mask, const float* known_values, int pos_clip,
+                                float clip_min, float clip_max, float* z_out, idb200_stream_t stream) {
+    IDB_REQUIRE(z && eps && z_out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(n_rows >= 0 && row_len >= 1 && D >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE((t == nullptr) == (t_prev == nullptr), IDB200_EINVAL, "t and t_prev must both be given or both NULL");
+    IDB_REQUIRE(t == nullptr || (alpha_bar != nullptr && n_train > 0), IDB200_EINVAL, "alpha_bar table missing");
+    IDB_REQUIRE((known_mask == nullptr) == (known_values == nullptr), IDB200_EINVAL, "known_mask/known_values mismatch");
+    const long long n = n_rows * row_len;
+    if (n == 0) return IDB200_OK;
+    ddim_step_kernel<<<ew_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, eps, reinterpret_cast<const long long*>(t), reinterpret_cast<const long long*>(t_prev), alpha_bar, ab_t, ab_prev,
+        n, row_len, D, known_mask, known_values, pos_clip, clip_min, clip_max, z_out);
+    return check_launch("ddim_step_kernel");
+}
+
+extern "C" int idb200_q_sample(const float* r0, const float* noise, const int64_t* t, const float* sqrt_ab,
+                               const float* sqrt_1m_ab, int n_train, int64_t n_rows, int64_t row_len, float* out,
+                               idb200_stream_t stream) {
+    IDB_REQUIRE(r0 && noise && t && sqrt_ab && sqrt_1m_ab && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(n_rows >= 0 && row_len >= 1 && n_train > 0, IDB200_EINVAL, "bad shape");
+    const long long n = n_rows * row_len;
+    if (n == 0) return IDB200_OK;
+    q_sample_kernel<<<ew_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        r0, noise, reinterpret_cast<const long long*>(t), sqrt_ab, sqrt_1m_ab, n, row_len, out);
+    return check_launch("q_sample_kernel");
+}
+
+extern "C" int idb200_known_mask_values(const int64_t* idx, const float* start_goal, int64_t B, int K, int D, int T,
+                                        int clamp_endpoints, int logit_space, float logit_eps, uint8_t* known_mask,
+                                        float* known_values, idb200_stream_t stream) {
+    IDB_REQUIRE(idx && known_mask && known_values, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(!clamp_endpoints || start_goal, IDB200_EINVAL, "clamp_endpoints=True but start_goal missing from cond");
+    IDB_REQUIRE(B >= 0 && K >= 1 && D >= 1 && T >= 1, IDB200_EINVAL, "bad shape");
+    if (B == 0) return IDB200_OK;
+    known_mask_values_kernel<<<ew_grid(B * K * D), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(idx), start_goal, B, K, D, T, clamp_endpoints, logit_space, logit_eps, known_mask,
+        known_values);
+    return check_launch("known_mask_values_kernel");
+}
+
+extern "C" int idb200_logit_pos(const float* x, int64_t n_rows, int D, float eps, float* out, idb200_stream_t stream) {
+    IDB_REQUIRE(x && out && n_rows >= 0 && D >= 1, IDB200_EINVAL, "bad arguments");
+    if (n_rows == 0) return IDB200_OK;
+    pos_transform_kernel<<<ew_grid(n_rows * D), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n_rows * D, D, 0, eps, out);
+    return check_launch("pos_transform_kernel(logit)");
+}
+
+extern "C" int idb200_sigmoid_pos(const float* x, int64_t n_rows, int D, float* out, idb200_stream_t stream) {
+    IDB_REQUIRE(x && out && n_rows >= 0 && D >= 1, IDB200_EINVAL, "bad arguments");
+    if (n_rows == 0) return IDB200_OK;
+    pos_transform_kernel<<<ew_grid(n_rows * D), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n_rows * D, D, 1, 0.0f, out);
+    return check_launch("pos_transform_kernel(sigmoid)");
+}
+
+extern "C" int idb200_stage2_epilogue(const float* x_in, const float* delta, const float* x_ref, const float* conf,
+                                      float lam, int policy, const uint8_t* clamp_mask, int clamp_dims_all, int pos_clip,
+                                      float clip_min, float clip_max, int64_t B, int T, int D, float* out,
+                                      idb200_stream_t stream) {
+    IDB_REQUIRE(x_in && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && T >= 1 && D >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(policy >= 0 && policy <= 2, IDB200_EINVAL, "unknown clamp policy %d", policy);
+    IDB_REQUIRE(policy != IDB200_CLAMP_MASK || clamp_mask, IDB200_EINVAL, "clamp_mask missing");
+    IDB_REQUIRE((policy == IDB200_CLAMP_NONE && !(conf && lam > 0.0f)) || x_ref, IDB200_EINVAL, "x_ref missing");
+    if (B == 0) return IDB200_OK;
+    stage2_epilogue_kernel<<<ew_grid(B * T * D), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_in, delta, x_ref, conf, lam, policy, clamp_mask, clamp_dims_all, pos_clip, clip_min, clip_max, B, T, D, out);
+    return check_launch("stage2_epilogue_kernel");
+}
+
+extern "C" int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student, const uint8_t* mask_prev,
+                                  const int64_t* s_row, int s_scalar, int levels, int anneal_mode, float conf_teacher,
+                                  float conf_student, float conf_endpoints, float conf_missing, int clamp_endpoints,
+                                  int64_t B, int T, int C, float* conf, float* mask_in, idb200_stream_t stream) {
+    IDB_REQUIRE(mask_s && (conf || mask_in), IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && T >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(!mask_in || C == 2 || (C == 3 && mask_prev), IDB200_EINVAL, "mask_in needs C==2, or C==3 with mask_prev");
+    IDB_REQUIRE(anneal_mode >= 0 && anneal_mode <= 2, IDB200_EINVAL, "unknown anneal mode");
+    if (B == 0) return IDB200_OK;
+    anchor_conf_kernel<<<ew_grid(B * T), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        mask_s, student, mask_prev, reinterpret_cast<const long long*>(s_row), s_scalar, levels, anneal_mode, conf_teacher,
+        conf_student, conf_endpoints, conf_missing, clamp_endpoints, B, T, C, conf, mask_in);
+    return check_launch("anchor_conf_kernel");
+}

@@ -1,0 +1,498 @@
+// K1: nested anchor masks + piecewise-linear Interp(x0 | M_s), and its relatives.
+//
+// Reference arithmetic being replaced (paths under the reference root):
+//   src/corruptions/keyframes.py:172-209  build_nested_masks_batch  (rand -> argsort -> per level cat/sort/scatter_)
+//   src/corruptions/keyframes.py:348-380  interpolate_from_indices  (searchsorted, 5 gathers, lerp, scatter_, velocity)
+//   src/train/train_interp_levels.py:444-510  _distance_alpha / _corrupt_from_anchors
+//
+// Design (HBM-bound, SURVEY.md 8d: 4600 algorithmic bytes per T=64,D=4,S=3 trajectory):
+//   one warp per trajectory, grid-stride over B.  The [T,D] row is read once with 8/16-byte
+//   vector loads (lane <-> timestep), the T-2 scores are staged in shared memory and ranked by an
+//   all-pairs count, level masks are warp ballots, anchor indices are popc prefix sums, the
+//   segment endpoints are fetched from a shared-memory copy of the row, and every level is
+//   written with one coalesced vector store per lane.  No temporaries ever reach HBM.
+//   All fp32 arithmetic uses the explicitly rounded intrinsics in the reference's operation
+//   order, so results are bit-identical to the eager PyTorch ops (no FMA contraction).
+#include "common.cuh"
+
+namespace idb200 {
+
+constexpr int kMaxLevels = 8;
+constexpr int kWarpsPerCta = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct NestedParams {
+    const float* x0;
+    const float* scores;
+    long long score_stride;
+    unsigned char* masks;
+    long long* idx_out;
+    float* x_levels;
+    long long level_stride;
+    long long B;
+    int T, n, n_levels, s_lo, s_hi, flags;
+    float dt;
+    int thr[kMaxLevels];          // interior positions taken at level s
+    int width[kMaxLevels];        // idx row width W_s
+    long long idx_off[kMaxLevels];// sum of W_j, j < s
+};
+
+template <int D> struct VecOf;
+template <> struct VecOf<2> { using type = float2; };
+template <> struct VecOf<4> { using type = float4; };
+
+__device__ __forceinline__ float lerp_rn(float vl, float vr, float w) {
+    // left + w * (right - left), each op rounded (keyframes.py:371)
+    return __fadd_rn(vl, __fmul_rn(w, __fsub_rn(vr, vl)));
+}
+__device__ __forceinline__ float2 lerp_rn(float2 a, float2 b, float w) {
+    return make_float2(lerp_rn(a.x, b.x, w), lerp_rn(a.y, b.y, w));
+}
+__device__ __forceinline__ float4 lerp_rn(float4 a, float4 b, float w) {
+    return make_float4(lerp_rn(a.x, b.x, w), lerp_rn(a.y, b.y, w), lerp_rn(a.z, b.z, w), lerp_rn(a.w, b.w, w));
+}
+
+template <int E, int D>
+struct WarpScratch {
+    float sc[32 * E + 4];                 // staged scores (padded to a multiple of 4 with +inf)
+    unsigned mw[kMaxLevels * E];          // level mask words: bit (t & 31) of word (t >> 5)
+    unsigned seen[(E < 4) ? 4 : E];       // rank-uniqueness bitmap (tie detector)
+    alignas(16) float xs[(D ? D : 1) * 32 * E];  // the row, for endpoint fetches
+};
+
+// E = ceil(T / 32) mask words per level; D in {0 (masks only), 2, 4}.
+template <int E, int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(const NestedParams p) {
+    __shared__ WarpScratch<E, D> scratch[kWarpsPerCta];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WarpScratch<E, D>& ws = scratch[warp];
+    const long long warps_total = static_cast<long long>(gridDim.x) * kWarpsPerCta;
+    const int T = p.T, n = p.n;
+    const bool noend = (p.flags & IDB200_F_NO_ENDPOINTS) != 0;
+    const bool desc = (p.flags & IDB200_F_DESCENDING) != 0;
+    const int n4 = (n + 3) & ~3;
+    const float kInf = __int_as_float(0x7f800000);
+    using V = typename VecOf<(D ? D : 2)>::type;
+
+    for (long long b = static_cast<long long>(blockIdx.x) * kWarpsPerCta + warp; b < p.B; b += warps_total) {
+        // ---- load scores (lane <-> timestep) and the row ----------------------------------------
+        const float* srow = p.scores + b * p.score_stride;
+        float me[E];
+        int jj[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int t = lane + 32 * e;
+            const int j = noend ? t : t - 1;
+            const bool vj = (j >= 0) && (j < n);
+            jj[e] = vj ? j : -1;
+            float s = vj ? __ldg(srow + j) : kInf;
+            if (desc && vj) s = -s;
+            me[e] = s + 0.0f;             // canonicalise -0 -> +0 so the sign trick below is exact
+        }
+        V xv[E];
+        if (D) {
+            const V* xrow = reinterpret_cast<const V*>(p.x0) + b * T;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int t = lane + 32 * e;
+                if (t < T) xv[e] = __ldg(xrow + t);
+            }
+        }
+        __syncwarp();                      // previous iteration's readers are done with ws
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (jj[e] >= 0) ws.sc[jj[e]] = me[e];
+        if (lane < n4 - n) ws.sc[n + lane] = kInf;
+        if (lane < ((E < 4) ? 4 : E)) ws.seen[lane] = 0u;
+        if (D) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int t = lane + 32 * e;
+                if (t < T) reinterpret_cast<V*>(ws.xs)[t] = xv[e];
+            }
+        }
+        __syncwarp();
+
+        // ---- stable rank by all-pairs count -----------------------------------------------------
+        // fast path counts s_u < s_t through the sign bit of (s_u - s_t): one FADD + one shift-add.
+        int cnt[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) cnt[e] = 0;
+        for (int u = 0; u < n4; u += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(&ws.sc[u]);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                cnt[e] += __float_as_uint(v.x - me[e]) >> 31;
+                cnt[e] += __float_as_uint(v.y - me[e]) >> 31;
+                cnt[e] += __float_as_uint(v.z - me[e]) >> 31;
+                cnt[e] += __float_as_uint(v.w - me[e]) >> 31;
+            }
+        }
+        // ties leave two elements with the same count: detect through a rank bitmap
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (jj[e] >= 0) atomicOr(&ws.seen[cnt[e] >> 5], 1u << (cnt[e] & 31));
+        __syncwarp();
+        int distinct = (lane < E) ? __popc(ws.seen[lane]) : 0;
+        distinct = __reduce_add_sync(kFull, distinct);
+        if (distinct != n) {               // warp-uniform: exact stable order (lower index first)
+#pragma unroll
+            for (int e = 0; e < E; ++e) cnt[e] = 0;
+            for (int u = 0; u < n; ++u) {
+                const float su = ws.sc[u];
+#pragma unroll
+                for (int e = 0; e < E; ++e) cnt[e] += ((su < me[e]) || (su == me[e] && u < jj[e])) ? 1 : 0;
+            }
+        }
+
+        // ---- level masks (ballots) --------------------------------------------------------------
+        for (int s = 0; s < p.n_levels; ++s) {
+            const int thr = p.thr[s];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int t = lane + 32 * e;
+                const bool a = (t < T) && ((!noend && (t == 0 || t == T - 1)) || (jj[e] >= 0 && cnt[e] < thr));
+                const unsigned w = __ballot_sync(kFull, a);
+                if (lane == 0) ws.mw[s * E + e] = w;
+            }
+        }
+        __syncwarp();
+
+        // ---- bool masks [B, n_levels, T] --------------------------------------------------------
+        if (p.masks) {
+            unsigned char* mrow = p.masks + b * static_cast<long long>(p.n_levels) * T;
+            if ((T & 7) == 0) {
+                const int per = T >> 3, chunks = p.n_levels * per;
+                for (int c = lane; c < chunks; c += 32) {
+                    const int s = c / per, t0 = (c - s * per) << 3;
+                    const unsigned bits = (ws.mw[s * E + (t0 >> 5)] >> (t0 & 31)) & 0xffu;
+                    // spread 4 bits to 4 bytes: copies at shifts 0,7,14,21 do not overlap
+                    const unsigned lo = ((bits & 0xfu) * 0x204081u) & 0x01010101u;
+                    const unsigned hi = ((bits >> 4) * 0x204081u) & 0x01010101u;
+                    *reinterpret_cast<uint2*>(mrow + (static_cast<long long>(c) << 3)) = make_uint2(lo, hi);
+                }
+            } else {
+                const int total = p.n_levels * T;
+                for (int i = lane; i < total; i += 32) {
+                    const int s = i / T, t = i - s * T;
+                    mrow[i] = (ws.mw[s * E + (t >> 5)] >> (t & 31)) & 1u;
+                }
+            }
+        }
+
+        // ---- ascending anchor indices per level (popc prefix) -----------------------------------
+        if (p.idx_out) {
+            for (int s = 0; s < p.n_levels; ++s) {
+                const int W = p.width[s];
+                long long* irow = p.idx_out + p.idx_off[s] * p.B + b * W;
+                int base = 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned w = ws.mw[s * E + e];
+                    if ((w >> lane) & 1u) {
+                        const int k = base + __popc(w & ((1u << lane) - 1u));
+                        if (k < W) irow[k] = lane + 32 * e;
+                    }
+                    base += __popc(w);
+                }
+            }
+        }
+
+        // ---- Interp(x0 | M_s) for the requested levels ------------------------------------------
+        if (D) {
+            for (int s = p.s_lo; s <= p.s_hi; ++s) {
+                V yv[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int t = lane + 32 * e;
+                    if (t >= T) continue;
+                    const unsigned w = ws.mw[s * E + e];
+                    if ((w >> lane) & 1u) {            // anchor: exact copy (scatter_ at keyframes.py:372)
+                        yv[e] = xv[e];
+                        continue;
+                    }
+                    int l = 0, r = T - 1;
+                    const unsigned below = w & (kFull >> (31 - lane));
+                    if (below) {
+                        l = 32 * e + 31 - __clz(below);
+                    } else {
+#pragma unroll
+                        for (int e2 = E - 1; e2 >= 0; --e2) {
+                            if (e2 < e) {
+                                const unsigned w2 = ws.mw[s * E + e2];
+                                if (w2) { l = 32 * e2 + 31 - __clz(w2); break; }
+                            }
+                        }
+                    }
+                    const unsigned above = w & (kFull << lane);
+                    if (above) {
+                        r = 32 * e + __ffs(above) - 1;
+                    } else {
+#pragma unroll
+                        for (int e2 = 0; e2 < E; ++e2) {
+                            if (e2 > e) {
+                                const unsigned w2 = ws.mw[s * E + e2];
+                                if (w2) { r = 32 * e2 + __ffs(w2) - 1; break; }
+                            }
+                        }
+                    }
+                    const int den = max(r - l, 1);
+                    const float wt = __fdiv_rn(static_cast<float>(t - l), static_cast<float>(den));
+                    const V vl = reinterpret_cast<const V*>(ws.xs)[l];
+                    const V vr = reinterpret_cast<const V*>(ws.xs)[r];
+                    yv[e] = lerp_rn(vl, vr, wt);
+                }
+                V* orow = reinterpret_cast<V*>(p.x_levels + static_cast<long long>(s - p.s_lo) * p.level_stride) + b * T;
+                if (D == 4 && (p.flags & IDB200_F_RECOMPUTE_VELOCITY)) {
+                    // v[t] = (pos[t+1] - pos[t]) / dt, v[T-1] = 0   (keyframes.py:373-379)
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int t = lane + 32 * e;
+                        float nx = __shfl_down_sync(kFull, yv[e].x, 1);
+                        float ny = __shfl_down_sync(kFull, yv[e].y, 1);
+                        if (e + 1 < E) {
+                            const float fx = __shfl_sync(kFull, yv[(e + 1 < E) ? e + 1 : e].x, 0);
+                            const float fy = __shfl_sync(kFull, yv[(e + 1 < E) ? e + 1 : e].y, 0);
+                            if (lane == 31) { nx = fx; ny = fy; }
+                        }
+                        if (t < T) {
+                            float4 o;
+                            o.x = yv[e].x;
+                            o.y = yv[e].y;
+                            o.z = (t == T - 1) ? 0.0f : __fdiv_rn(__fsub_rn(nx, yv[e].x), p.dt);
+                            o.w = (t == T - 1) ? 0.0f : __fdiv_rn(__fsub_rn(ny, yv[e].y), p.dt);
+                            *reinterpret_cast<float4*>(&orow[t]) = o;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int t = lane + 32 * e;
+                        if (t < T) orow[t] = yv[e];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int E, int D>
+static int launch_nested(const NestedParams& p, cudaStream_t st) {
+    const int grid = grid_for(p.B, kWarpsPerCta, 8);
+    nested_masks_interp_kernel<E, D><<<grid, kWarpsPerCta * 32, 0, st>>>(p);
+    return check_launch("nested_masks_interp_kernel");
+}
+
+template <int D>
+static int dispatch_nested_E(const NestedParams& p, cudaStream_t st) {
+    if (p.T <= 32) return launch_nested<1, D>(p, st);
+    if (p.T <= 64) return launch_nested<2, D>(p, st);
+    if (p.T <= 128) return launch_nested<4, D>(p, st);
+    return launch_nested<8, D>(p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// general interpolate_from_indices: one CTA per trajectory, idx staged in shared memory,
+// (t, d) flattened over the threads; searchsorted(right=True) is an upper-bound binary search.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int upper_bound_smem(const int* a, int K, int t) {
+    int lo = 0, hi = K;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] <= t) lo = mid + 1; else hi = mid;
+    }
+    return lo;            // number of idx <= t
+}
+
+__device__ __forceinline__ float interp_eval(const int* sidx, const float* v, int K, int D, int t, int d) {
+    const int cnt = upper_bound_smem(sidx, K, t);
+    if (cnt > 0 && sidx[cnt - 1] == t) return v[static_cast<long long>(cnt - 1) * D + d];  // scatter_: last duplicate wins
+    const int seg = min(max(cnt - 1, 0), K - 2);
+    const int l = sidx[seg], r = sidx[seg + 1];
+    const float w = __fdiv_rn(static_cast<float>(t - l), static_cast<float>(max(r - l, 1)));
+    return lerp_rn(v[static_cast<long long>(seg) * D + d], v[static_cast<long long>(seg + 1) * D + d], w);
+}
+
+__global__ void __launch_bounds__(128) interp_indices_kernel(const long long* __restrict__ idx, const float* __restrict__ vals,
+                                                             long long B, int K, int T, int D, int vel, float dt,
+                                                             float* __restrict__ y) {
+    extern __shared__ int sidx[];
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) sidx[k] = static_cast<int>(idx[b * K + k]);
+        __syncthreads();
+        const float* v = vals + b * K * D;
+        float* yo = y + b * T * D;
+        const int total = T * D;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int t = i / D, d = i - t * D;
+            float out;
+            if (vel && d >= 2) {
+                if (t == T - 1) out = 0.0f;
+                else out = __fdiv_rn(__fsub_rn(interp_eval(sidx, v, K, D, t + 1, d - 2), interp_eval(sidx, v, K, D, t, d - 2)), dt);
+            } else {
+                out = interp_eval(sidx, v, K, D, t, d);
+            }
+            yo[i] = out;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1c: _corrupt_from_anchors (train_interp_levels.py:458-510), one CTA per row.
+// shared: idx (int) [K], noisy anchor values [K*D], final positions [T*2] (for the velocity pass)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) corrupt_from_anchors_kernel(
+    const float* __restrict__ source, const long long* __restrict__ idx, const long long* __restrict__ idx_gather,
+    const float* __restrict__ anchor_noise, const float* __restrict__ path_noise, const long long* __restrict__ row_index,
+    long long B, int K, int T, int D, float sigma, float anchor_sigma, int mode_dist, int clamp_endpoints, int vel,
+    float dt, float* __restrict__ out) {
+    extern __shared__ int smem_i[];
+    int* sidx = smem_i;
+    float* svals = reinterpret_cast<float*>(smem_i + K);
+    float* spos = svals + K * D;
+    for (long long r = blockIdx.x; r < B; r += gridDim.x) {
+        const long long row = row_index ? row_index[r] : r;
+        const float* src = source + row * T * D;
+        float* orow = out + row * T * D;
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) sidx[k] = static_cast<int>(idx[r * K + k]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+            const int k = i / D, d = i - k * D;
+            const int g = idx_gather ? static_cast<int>(idx_gather[r * K + k]) : sidx[k];
+            float v = src[static_cast<long long>(g) * D + d];
+            if (anchor_noise && d < 2) {               // :486-494
+                float nv = __fmul_rn(anchor_noise[(r * K + k) * 2 + d], anchor_sigma);
+                if (clamp_endpoints && (sidx[k] == 0 || sidx[k] == T - 1)) nv = 0.0f;
+                v = __fadd_rn(v, nv);
+            }
+            svals[i] = v;
+        }
+        __syncthreads();
+        const int total = T * D;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int t = i / D, d = i - t * D;
+            if (vel && d >= 2) continue;
+            float x = interp_eval(sidx, svals, K, D, t, d);
+            if (path_noise && d < 2) {                 // :496-504
+                float alpha = 1.0f;
+                if (mode_dist) {                       // _distance_alpha :444-455
+                    const int cnt = upper_bound_smem(sidx, K, t);
+                    const int seg = min(max(cnt - 1, 0), K - 2);
+                    const int l = sidx[seg], rr = sidx[seg + 1];
+                    const int gap = max(rr - l, 1);
+                    const int dist = min(t - l, rr - t);
+                    alpha = __fdiv_rn(__fmul_rn(2.0f, static_cast<float>(dist)), static_cast<float>(gap));
+                    alpha = fminf(fmaxf(alpha, 0.0f), 1.0f);
+                }
+                const float nz = __fmul_rn(path_noise[(r * T + t) * 2 + d], sigma);
+                x = __fadd_rn(x, __fmul_rn(nz, alpha));
+            }
+            if (vel && d < 2) spos[t * 2 + d] = x;
+            orow[i] = x;
+        }
+        if (vel) {                                     // :505-509
+            __syncthreads();
+            for (int i = threadIdx.x; i < T * 2; i += blockDim.x) {
+                const int t = i >> 1, d = i & 1;
+                const float v = (t == T - 1) ? 0.0f : __fdiv_rn(__fsub_rn(spos[(t + 1) * 2 + d], spos[t * 2 + d]), dt);
+                orow[t * D + 2 + d] = v;
+            }
+        }
+    }
+}
+
+}  // namespace idb200
+
+using namespace idb200;
+
+extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, int64_t score_stride, int64_t B, int T,
+                                          int D, int n_levels, const int* K_list, uint8_t* masks, int64_t* idx_out,
+                                          float* x_levels, int64_t level_stride, int s_lo, int s_hi, int flags,
+                                          idb200_stream_t stream) {
+    IDB_REQUIRE(B >= 0, IDB200_EINVAL, "B must be >= 0");
+    IDB_REQUIRE(T >= 1, IDB200_EINVAL, "T must be positive");
+    IDB_REQUIRE(T <= 256, IDB200_EUNSUPPORTED, "nested_masks_interp supports T <= 256 (got %d)", T);
+    IDB_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, IDB200_EUNSUPPORTED, "n_levels must be in [1,%d]", kMaxLevels);
+    IDB_REQUIRE(K_list != nullptr, IDB200_EINVAL, "K_list is NULL");
+    const bool noend = (flags & IDB200_F_NO_ENDPOINTS) != 0;
+    IDB_REQUIRE(noend || T >= 2, IDB200_EINVAL, "T must be >= 2 when using endpoints");
+    NestedParams p{};
+    p.n = noend ? T : T - 2;
+    IDB_REQUIRE(p.n == 0 || scores != nullptr, IDB200_EINVAL, "scores is NULL");
+    IDB_REQUIRE(score_stride >= p.n, IDB200_EINVAL, "score_stride smaller than the row length");
+    if (x0 != nullptr) {
+        IDB_REQUIRE(!noend, IDB200_EINVAL, "interpolation needs endpoint anchors");
+        IDB_REQUIRE(D == 2 || D == 4, IDB200_EUNSUPPORTED, "fused interpolation supports D in {2,4} (got %d)", D);
+        IDB_REQUIRE(x_levels != nullptr, IDB200_EINVAL, "x_levels is NULL");
+        IDB_REQUIRE(s_lo >= 0 && s_hi < n_levels && s_lo <= s_hi, IDB200_EINVAL, "bad level range [%d,%d]", s_lo, s_hi);
+        IDB_REQUIRE(aligned(x0, 16) && aligned(x_levels, 16) && (level_stride * 4) % 16 == 0, IDB200_EALIGN,
+                    "x0 / x_levels must be 16-byte aligned");
+    }
+    IDB_REQUIRE(masks == nullptr || aligned(masks, 8), IDB200_EALIGN, "masks must be 8-byte aligned");
+    long long off = 0;
+    for (int s = 0; s < n_levels; ++s) {
+        const int Ks = K_list[s];
+        IDB_REQUIRE(Ks >= 1, IDB200_EINVAL, "K_list[%d] must be positive", s);
+        if (noend) {
+            p.thr[s] = Ks < T ? Ks : T;
+            p.width[s] = p.thr[s];
+        } else {
+            int thr = Ks - 2;
+            if (thr < 0) thr = 0;
+            if (thr > p.n) thr = p.n;
+            p.thr[s] = thr;
+            p.width[s] = (Ks <= 2 || T <= 2) ? 2 : (Ks < T ? Ks : T);
+        }
+        p.idx_off[s] = off;
+        off += p.width[s];
+    }
+    if (B == 0) return IDB200_OK;
+    p.x0 = x0; p.scores = scores; p.score_stride = score_stride; p.masks = masks;
+    p.idx_out = reinterpret_cast<long long*>(idx_out);
+    p.x_levels = x_levels; p.level_stride = level_stride; p.B = B; p.T = T; p.n_levels = n_levels;
+    p.s_lo = s_lo; p.s_hi = s_hi; p.flags = flags;
+    p.dt = static_cast<float>(1.0 / static_cast<double>(T));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (x0 == nullptr) return dispatch_nested_E<0>(p, st);
+    if (D == 2) return dispatch_nested_E<2>(p, st);
+    return dispatch_nested_E<4>(p, st);
+}
+
+extern "C" int idb200_interpolate_from_indices(const int64_t* idx, const float* vals, int64_t B, int K, int T, int D,
+                                               int recompute_velocity, float* y, idb200_stream_t stream) {
+    IDB_REQUIRE(idx && vals && y, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && D >= 1 && T >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(K >= 2, IDB200_EINVAL, "K must be >= 2");
+    IDB_REQUIRE(K <= 8192 && T <= 65536, IDB200_EUNSUPPORTED, "K <= 8192 and T <= 65536 supported");
+    if (B == 0) return IDB200_OK;
+    const int vel = (recompute_velocity && D == 4) ? 1 : 0;
+    const int grid = grid_for(B, 1, 16);
+    interp_indices_kernel<<<grid, 128, K * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(idx), vals, B, K, T, D, vel, static_cast<float>(1.0 / static_cast<double>(T)), y);
+    return check_launch("interp_indices_kernel");
+}
+
+extern "C" int idb200_corrupt_from_anchors(const float* source, const int64_t* idx, const int64_t* idx_gather,
+                                           const float* anchor_noise, const float* path_noise, const int64_t* row_index,
+                                           int64_t B, int K, int T, int D, float sigma, float anchor_sigma, int mode_dist,
+                                           int clamp_endpoints, int recompute_velocity, float* out,
+                                           idb200_stream_t stream) {
+    IDB_REQUIRE(source && idx && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && D >= 1 && T >= 1 && K >= 2, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE((!anchor_noise && !path_noise) || D >= 2, IDB200_EINVAL, "noise needs D >= 2");
+    const size_t smem = sizeof(int) * K + sizeof(float) * (static_cast<size_t>(K) * D + 2 * static_cast<size_t>(T));
+    IDB_REQUIRE(smem <= 48 * 1024, IDB200_EUNSUPPORTED, "K*D + 2T too large for one CTA (%zu bytes)", smem);
+    if (B == 0) return IDB200_OK;
+    const int vel = (recompute_velocity && D == 4) ? 1 : 0;
+    const float* an = (anchor_sigma > 0.0f) ? anchor_noise : nullptr;   // :486 `if anchor_sigma > 0.0`
+    const float* pn = (sigma > 0.0f) ? path_noise : nullptr;            // :496 `if sigma > 0.0`
+    const int grid = grid_for(B, 1, 16);
+    corrupt_from_anchors_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        source, reinterpret_cast<const long long*>(idx), reinterpret_cast<const long long*>(idx_gather), an, pn,
+        reinterpret_cast<const long long*>(row_index), B, K, T, D, sigma, anchor_sigma, mode_dist, clamp_endpoints, vel,
+        static_cast<float>(1.0 / static_cast<double>(T)), out);
+    return check_launch("corrupt_from_anchors_kernel");
+}
