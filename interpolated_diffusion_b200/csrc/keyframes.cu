@@ -18,7 +18,6 @@
 namespace idb200 {
 
 constexpr int kMaxLevels = 8;
-constexpr int kWarpsPerCta = 8;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct NestedParams {
@@ -32,6 +31,7 @@ struct NestedParams {
     long long B;
     int T, n, n_levels, s_lo, s_hi, flags;
     float dt;
+    float bucket_lo, bucket_scale;   // score -> bucket = clamp(int((s - lo) * scale), 0, NB-1): any monotone map is correct
     int thr[kMaxLevels];          // interior positions taken at level s
     int width[kMaxLevels];        // idx row width W_s
     long long idx_off[kMaxLevels];// sum of W_j, j < s
@@ -45,37 +45,96 @@ __device__ __forceinline__ float lerp_rn(float vl, float vr, float w) {
     // left + w * (right - left), each op rounded (keyframes.py:371)
     return __fadd_rn(vl, __fmul_rn(w, __fsub_rn(vr, vl)));
 }
+
+// Packed fp32x2 add / sub (FADD2 on sm_100a): two independent round-to-nearest results per
+// instruction.  The multiply stays scalar: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even
+// with explicit .rn, which would break bit parity with the reference's separately rounded ops.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ float2 lerp_rn(float2 a, float2 b, float w) {
-    return make_float2(lerp_rn(a.x, b.x, w), lerp_rn(a.y, b.y, w));
+    float dx, dy;
+    const unsigned long long l = pack2(a.x, a.y);
+    unpack2(sub2_rn(pack2(b.x, b.y), l), dx, dy);
+    float2 o;
+    unpack2(add2_rn(l, pack2(__fmul_rn(w, dx), __fmul_rn(w, dy))), o.x, o.y);
+    return o;
 }
 __device__ __forceinline__ float4 lerp_rn(float4 a, float4 b, float w) {
-    return make_float4(lerp_rn(a.x, b.x, w), lerp_rn(a.y, b.y, w), lerp_rn(a.z, b.z, w), lerp_rn(a.w, b.w, w));
+    const float2 lo = lerp_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), w);
+    const float2 hi = lerp_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), w);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+
+// count += [a < m] for two candidates at once: sign bits of the packed difference (a - m)
+__device__ __forceinline__ void count_lt2(int& cnt, float a0, float a1, unsigned long long m2) {
+    float d0, d1;
+    unpack2(sub2_rn(pack2(a0, a1), m2), d0, d1);
+    cnt += __float_as_uint(d0) >> 31;
+    cnt += __float_as_uint(d1) >> 31;
+}
+
+constexpr int kBucketCap = 32;            // slots per score bucket (overflow -> all-pairs fallback)
+
+template <int E> struct K1Cfg {
+    static constexpr int kWarps = (E <= 4) ? 8 : 4;
+    static constexpr int kBuckets = 4 * E;            // ~16 scores per bucket for uniform scores
+    static constexpr bool kWTable = (E <= 2);         // exact (t-l)/(r-l) quotients from shared memory
+};
 
 template <int E, int D>
 struct WarpScratch {
-    float sc[32 * E + 4];                 // staged scores (padded to a multiple of 4 with +inf)
-    unsigned mw[kMaxLevels * E];          // level mask words: bit (t & 31) of word (t >> 5)
-    unsigned seen[(E < 4) ? 4 : E];       // rank-uniqueness bitmap (tie detector)
-    alignas(16) float xs[(D ? D : 1) * 32 * E];  // the row, for endpoint fetches
+    alignas(16) float sc[32 * E + 4];                      // staged scores (padded with +inf)
+    alignas(16) float blist[K1Cfg<E>::kBuckets * kBucketCap];  // scores grouped by bucket (+inf padded)
+    alignas(16) float cv[(D ? D : 1) * 32 * E];            // anchor values of the current level, compacted
+    int ci[32 * E];                                        // anchor positions of the current level, compacted
+    int bcnt[K1Cfg<E>::kBuckets];                          // bucket sizes, then exclusive starts
+    unsigned mw[kMaxLevels * E];                           // level mask words: bit (t & 31) of word (t >> 5)
+    unsigned seen[(E < 4) ? 4 : E];                        // rank-uniqueness bitmap (tie detector)
 };
 
 // E = ceil(T / 32) mask words per level; D in {0 (masks only), 2, 4}.
 template <int E, int D>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(const NestedParams p) {
-    __shared__ WarpScratch<E, D> scratch[kWarpsPerCta];
+__global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_kernel(const NestedParams p) {
+    constexpr int kWarps = K1Cfg<E>::kWarps;
+    constexpr int NB = K1Cfg<E>::kBuckets;
+    __shared__ WarpScratch<E, D> scratch[kWarps];
+    __shared__ float wtab[K1Cfg<E>::kWTable && D ? 64 * 64 : 1];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpScratch<E, D>& ws = scratch[warp];
-    const long long warps_total = static_cast<long long>(gridDim.x) * kWarpsPerCta;
+    const long long warps_total = static_cast<long long>(gridDim.x) * kWarps;
     const int T = p.T, n = p.n;
     const bool noend = (p.flags & IDB200_F_NO_ENDPOINTS) != 0;
     const bool desc = (p.flags & IDB200_F_DESCENDING) != 0;
     const int n4 = (n + 3) & ~3;
     const float kInf = __int_as_float(0x7f800000);
+    const unsigned lane_le = kFull >> (31 - lane);
     using V = typename VecOf<(D ? D : 2)>::type;
 
-    for (long long b = static_cast<long long>(blockIdx.x) * kWarpsPerCta + warp; b < p.B; b += warps_total) {
+    if (K1Cfg<E>::kWTable && D) {
+        // wtab[gap][off] = off / max(gap, 1), IEEE-rounded once per CTA (keyframes.py:369-370)
+        for (int i = threadIdx.x; i < 64 * 64; i += kWarps * 32)
+            wtab[i] = __fdiv_rn(static_cast<float>(i & 63), static_cast<float>(max(i >> 6, 1)));
+        __syncthreads();
+    }
+
+    for (long long b = static_cast<long long>(blockIdx.x) * kWarps + warp; b < p.B; b += warps_total) {
         // ---- load scores (lane <-> timestep) and the row ----------------------------------------
         const float* srow = p.scores + b * p.score_stride;
         float me[E];
@@ -88,7 +147,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(
             jj[e] = vj ? j : -1;
             float s = vj ? __ldg(srow + j) : kInf;
             if (desc && vj) s = -s;
-            me[e] = s + 0.0f;             // canonicalise -0 -> +0 so the sign trick below is exact
+            me[e] = s + 0.0f;             // canonicalise -0 -> +0 so the sign-bit count is exact
         }
         V xv[E];
         if (D) {
@@ -105,28 +164,65 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(
             if (jj[e] >= 0) ws.sc[jj[e]] = me[e];
         if (lane < n4 - n) ws.sc[n + lane] = kInf;
         if (lane < ((E < 4) ? 4 : E)) ws.seen[lane] = 0u;
-        if (D) {
+        if (lane < NB) ws.bcnt[lane] = 0;
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int t = lane + 32 * e;
-                if (t < T) reinterpret_cast<V*>(ws.xs)[t] = xv[e];
-            }
-        }
+        for (int i = 0; i < NB * kBucketCap / 128; ++i)
+            reinterpret_cast<float4*>(ws.blist)[lane + 32 * i] = make_float4(kInf, kInf, kInf, kInf);
         __syncwarp();
 
-        // ---- stable rank by all-pairs count -----------------------------------------------------
-        // fast path counts s_u < s_t through the sign bit of (s_u - s_t): one FADD + one shift-add.
-        int cnt[E];
+        // ---- stable rank ------------------------------------------------------------------------
+        // rank(j) = #{u : s_u < s_j} (+ index tie-break).  Scores are grouped into NB monotone value
+        // buckets: rank = (sizes of lower buckets) + (count inside the own bucket), so each element is
+        // compared with ~n/NB candidates instead of n.  Any bucket function that is non-decreasing
+        // in the score is correct; a bucket that overflows its slots falls back to the all-pairs count.
+        int cnt[E], bk[E], slot[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) cnt[e] = 0;
-        for (int u = 0; u < n4; u += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(&ws.sc[u]);
+        for (int e = 0; e < E; ++e) {
+            const float f = (me[e] - p.bucket_lo) * p.bucket_scale;
+            int bb = (f >= static_cast<float>(NB - 1)) ? NB - 1 : ((f > 0.0f) ? static_cast<int>(f) : 0);
+            bk[e] = bb;
+            slot[e] = (jj[e] >= 0) ? atomicAdd(&ws.bcnt[bb], 1) : kBucketCap;
+            if (slot[e] < kBucketCap) ws.blist[bb * kBucketCap + slot[e]] = me[e];
+            cnt[e] = 0;
+        }
+        __syncwarp();
+        int bsize = (lane < NB) ? ws.bcnt[lane] : 0;
+        const int bmax = __reduce_max_sync(kFull, bsize);
+        int bstart = bsize;                // inclusive scan over the NB bucket sizes
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                cnt[e] += __float_as_uint(v.x - me[e]) >> 31;
-                cnt[e] += __float_as_uint(v.y - me[e]) >> 31;
-                cnt[e] += __float_as_uint(v.z - me[e]) >> 31;
-                cnt[e] += __float_as_uint(v.w - me[e]) >> 31;
+        for (int o = 1; o < NB; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, bstart, o);
+            if (lane >= o) bstart += v;
+        }
+        __syncwarp();
+        if (lane < NB) ws.bcnt[lane] = bstart - bsize;    // exclusive start
+        __syncwarp();
+        bool exact_needed = false;
+        if (bmax <= kBucketCap) {
+            unsigned long long m2[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) m2[e] = pack2(me[e], me[e]);
+            for (int u = 0; u < bmax; u += 4) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const float4 v = *reinterpret_cast<const float4*>(&ws.blist[bk[e] * kBucketCap + u]);
+                    count_lt2(cnt[e], v.x, v.y, m2[e]);
+                    count_lt2(cnt[e], v.z, v.w, m2[e]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) cnt[e] += ws.bcnt[bk[e]];
+        } else {                           // pathological score distribution: all-pairs sign-bit count
+            unsigned long long m2[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) m2[e] = pack2(me[e], me[e]);
+            for (int u = 0; u < n4; u += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(&ws.sc[u]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    count_lt2(cnt[e], v.x, v.y, m2[e]);
+                    count_lt2(cnt[e], v.z, v.w, m2[e]);
+                }
             }
         }
         // ties leave two elements with the same count: detect through a rank bitmap
@@ -136,7 +232,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(
         __syncwarp();
         int distinct = (lane < E) ? __popc(ws.seen[lane]) : 0;
         distinct = __reduce_add_sync(kFull, distinct);
-        if (distinct != n) {               // warp-uniform: exact stable order (lower index first)
+        exact_needed = (distinct != n);
+        if (exact_needed) {                // warp-uniform: exact stable order (lower index first)
 #pragma unroll
             for (int e = 0; e < E; ++e) cnt[e] = 0;
             for (int u = 0; u < n; ++u) {
@@ -191,7 +288,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(
                 for (int e = 0; e < E; ++e) {
                     const unsigned w = ws.mw[s * E + e];
                     if ((w >> lane) & 1u) {
-                        const int k = base + __popc(w & ((1u << lane) - 1u));
+                        const int k = base + __popc(w & lane_le) - 1;
                         if (k < W) irow[k] = lane + 32 * e;
                     }
                     base += __popc(w);
@@ -200,48 +297,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(
         }
 
         // ---- Interp(x0 | M_s) for the requested levels ------------------------------------------
+        // Anchors compact their (position, value) into shared lists; every timestep finds its
+        // segment as popc(mask bits <= t) - 1 and reads both endpoints with independent loads.
         if (D) {
             for (int s = p.s_lo; s <= p.s_hi; ++s) {
+                int seg[E];
+                bool anchor[E];
+                int base = 0;
+                __syncwarp();              // readers of the previous level's lists are done
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned w = ws.mw[s * E + e];
+                    const int t = lane + 32 * e;
+                    seg[e] = base + __popc(w & lane_le) - 1;
+                    anchor[e] = ((w >> lane) & 1u) != 0;
+                    if (anchor[e]) {
+                        reinterpret_cast<V*>(ws.cv)[seg[e]] = xv[e];
+                        ws.ci[seg[e]] = t;
+                    }
+                    base += __popc(w);
+                }
+                __syncwarp();
+                const int klast = base - 1;
                 V yv[E];
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int t = lane + 32 * e;
                     if (t >= T) continue;
-                    const unsigned w = ws.mw[s * E + e];
-                    if ((w >> lane) & 1u) {            // anchor: exact copy (scatter_ at keyframes.py:372)
-                        yv[e] = xv[e];
-                        continue;
-                    }
-                    int l = 0, r = T - 1;
-                    const unsigned below = w & (kFull >> (31 - lane));
-                    if (below) {
-                        l = 32 * e + 31 - __clz(below);
-                    } else {
-#pragma unroll
-                        for (int e2 = E - 1; e2 >= 0; --e2) {
-                            if (e2 < e) {
-                                const unsigned w2 = ws.mw[s * E + e2];
-                                if (w2) { l = 32 * e2 + 31 - __clz(w2); break; }
-                            }
-                        }
-                    }
-                    const unsigned above = w & (kFull << lane);
-                    if (above) {
-                        r = 32 * e + __ffs(above) - 1;
-                    } else {
-#pragma unroll
-                        for (int e2 = 0; e2 < E; ++e2) {
-                            if (e2 > e) {
-                                const unsigned w2 = ws.mw[s * E + e2];
-                                if (w2) { r = 32 * e2 + __ffs(w2) - 1; break; }
-                            }
-                        }
-                    }
-                    const int den = max(r - l, 1);
-                    const float wt = __fdiv_rn(static_cast<float>(t - l), static_cast<float>(den));
-                    const V vl = reinterpret_cast<const V*>(ws.xs)[l];
-                    const V vr = reinterpret_cast<const V*>(ws.xs)[r];
-                    yv[e] = lerp_rn(vl, vr, wt);
+                    const int k1 = min(seg[e] + 1, klast);
+                    const int l = ws.ci[seg[e]], r = ws.ci[k1];
+                    const V vl = reinterpret_cast<const V*>(ws.cv)[seg[e]];
+                    const V vr = reinterpret_cast<const V*>(ws.cv)[k1];
+                    float wt;
+                    if (K1Cfg<E>::kWTable) wt = wtab[((r - l) << 6) + (t - l)];
+                    else wt = __fdiv_rn(static_cast<float>(t - l), static_cast<float>(max(r - l, 1)));
+                    const V y = lerp_rn(vl, vr, wt);
+                    yv[e] = anchor[e] ? xv[e] : y;      // anchors: exact copy (scatter_ at keyframes.py:372)
                 }
                 V* orow = reinterpret_cast<V*>(p.x_levels + static_cast<long long>(s - p.s_lo) * p.level_stride) + b * T;
                 if (D == 4 && (p.flags & IDB200_F_RECOMPUTE_VELOCITY)) {
@@ -279,8 +370,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) nested_masks_interp_kernel(
 
 template <int E, int D>
 static int launch_nested(const NestedParams& p, cudaStream_t st) {
-    const int grid = grid_for(p.B, kWarpsPerCta, 8);
-    nested_masks_interp_kernel<E, D><<<grid, kWarpsPerCta * 32, 0, st>>>(p);
+    constexpr int kWarps = K1Cfg<E>::kWarps;
+    const int grid = grid_for(p.B, kWarps, 8);
+    nested_masks_interp_kernel<E, D><<<grid, kWarps * 32, 0, st>>>(p);
     return check_launch("nested_masks_interp_kernel");
 }
 
@@ -428,8 +520,9 @@ extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, 
         IDB_REQUIRE(D == 2 || D == 4, IDB200_EUNSUPPORTED, "fused interpolation supports D in {2,4} (got %d)", D);
         IDB_REQUIRE(x_levels != nullptr, IDB200_EINVAL, "x_levels is NULL");
         IDB_REQUIRE(s_lo >= 0 && s_hi < n_levels && s_lo <= s_hi, IDB200_EINVAL, "bad level range [%d,%d]", s_lo, s_hi);
-        IDB_REQUIRE(aligned(x0, 16) && aligned(x_levels, 16) && (level_stride * 4) % 16 == 0, IDB200_EALIGN,
-                    "x0 / x_levels must be 16-byte aligned");
+        const size_t va = static_cast<size_t>(D) * 4;      // one float2 / float4 per timestep
+        IDB_REQUIRE(aligned(x0, va) && aligned(x_levels, va) && (level_stride * 4) % va == 0, IDB200_EALIGN,
+                    "x0 / x_levels must be %zu-byte aligned", va);
     }
     IDB_REQUIRE(masks == nullptr || aligned(masks, 8), IDB200_EALIGN, "masks must be 8-byte aligned");
     long long off = 0;
@@ -455,6 +548,12 @@ extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, 
     p.x_levels = x_levels; p.level_stride = level_stride; p.B = B; p.T = T; p.n_levels = n_levels;
     p.s_lo = s_lo; p.s_hi = s_hi; p.flags = flags;
     p.dt = static_cast<float>(1.0 / static_cast<double>(T));
+    {   // bucket map: scores are torch.rand in [0,1) (keys in (-1,0] when descending).  For other inputs
+        // (selector logits) the map is still monotone, hence correct, just less balanced.
+        const int nb = 4 * ((T <= 32) ? 1 : (T <= 64) ? 2 : (T <= 128) ? 4 : 8);
+        p.bucket_lo = (flags & IDB200_F_DESCENDING) ? -1.0f : 0.0f;
+        p.bucket_scale = static_cast<float>(nb);
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (x0 == nullptr) return dispatch_nested_E<0>(p, st);
     if (D == 2) return dispatch_nested_E<2>(p, st);
