@@ -31,7 +31,6 @@ struct NestedParams {
     long long B;
     int T, n, n_levels, s_lo, s_hi, flags;
     float dt;
-    float bucket_lo, bucket_scale;   // score -> bucket = clamp(int((s - lo) * scale), 0, NB-1): any monotone map is correct
     int thr[kMaxLevels];          // interior positions taken at level s
     int width[kMaxLevels];        // idx row width W_s
     long long idx_off[kMaxLevels];// sum of W_j, j < s
@@ -89,32 +88,24 @@ __device__ __forceinline__ void count_lt2(int& cnt, float a0, float a1, unsigned
     cnt += __float_as_uint(d1) >> 31;
 }
 
-constexpr int kBucketCap = 32;            // slots per score bucket (overflow -> all-pairs fallback)
-
 template <int E> struct K1Cfg {
     static constexpr int kWarps = (E <= 4) ? 8 : 4;
-    static constexpr int kBuckets = 4 * E;            // ~16 scores per bucket for uniform scores
-    static constexpr bool kWTable = (E <= 2);         // exact (t-l)/(r-l) quotients from shared memory
 };
 
 template <int E, int D>
 struct WarpScratch {
     alignas(16) float sc[32 * E + 4];                      // staged scores (padded with +inf)
-    alignas(16) float blist[K1Cfg<E>::kBuckets * kBucketCap];  // scores grouped by bucket (+inf padded)
     alignas(16) float cv[(D ? D : 1) * 32 * E];            // anchor values of the current level, compacted
-    int ci[32 * E];                                        // anchor positions of the current level, compacted
-    int bcnt[K1Cfg<E>::kBuckets];                          // bucket sizes, then exclusive starts
+    alignas(8) int2 seg_lr[32 * E];                        // (left, right) anchor position of segment k
     unsigned mw[kMaxLevels * E];                           // level mask words: bit (t & 31) of word (t >> 5)
-    unsigned seen[(E < 4) ? 4 : E];                        // rank-uniqueness bitmap (tie detector)
 };
 
 // E = ceil(T / 32) mask words per level; D in {0 (masks only), 2, 4}.
 template <int E, int D>
 __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_kernel(const NestedParams p) {
     constexpr int kWarps = K1Cfg<E>::kWarps;
-    constexpr int NB = K1Cfg<E>::kBuckets;
     __shared__ WarpScratch<E, D> scratch[kWarps];
-    __shared__ float wtab[K1Cfg<E>::kWTable && D ? 64 * 64 : 1];
+    __shared__ float rtab[256];            // rtab[g] = RN(1 / max(g, 1))
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpScratch<E, D>& ws = scratch[warp];
@@ -127,10 +118,8 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
     const unsigned lane_le = kFull >> (31 - lane);
     using V = typename VecOf<(D ? D : 2)>::type;
 
-    if (K1Cfg<E>::kWTable && D) {
-        // wtab[gap][off] = off / max(gap, 1), IEEE-rounded once per CTA (keyframes.py:369-370)
-        for (int i = threadIdx.x; i < 64 * 64; i += kWarps * 32)
-            wtab[i] = __fdiv_rn(static_cast<float>(i & 63), static_cast<float>(max(i >> 6, 1)));
+    if (D) {
+        for (int i = threadIdx.x; i < 256; i += kWarps * 32) rtab[i] = __frcp_rn(static_cast<float>(max(i, 1)));
         __syncthreads();
     }
 
@@ -163,59 +152,18 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
         for (int e = 0; e < E; ++e)
             if (jj[e] >= 0) ws.sc[jj[e]] = me[e];
         if (lane < n4 - n) ws.sc[n + lane] = kInf;
-        if (lane < ((E < 4) ? 4 : E)) ws.seen[lane] = 0u;
-        if (lane < NB) ws.bcnt[lane] = 0;
-#pragma unroll
-        for (int i = 0; i < NB * kBucketCap / 128; ++i)
-            reinterpret_cast<float4*>(ws.blist)[lane + 32 * i] = make_float4(kInf, kInf, kInf, kInf);
         __syncwarp();
 
-        // ---- stable rank ------------------------------------------------------------------------
-        // rank(j) = #{u : s_u < s_j} (+ index tie-break).  Scores are grouped into NB monotone value
-        // buckets: rank = (sizes of lower buckets) + (count inside the own bucket), so each element is
-        // compared with ~n/NB candidates instead of n.  Any bucket function that is non-decreasing
-        // in the score is correct; a bucket that overflows its slots falls back to the all-pairs count.
-        int cnt[E], bk[E], slot[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const float f = (me[e] - p.bucket_lo) * p.bucket_scale;
-            int bb = (f >= static_cast<float>(NB - 1)) ? NB - 1 : ((f > 0.0f) ? static_cast<int>(f) : 0);
-            bk[e] = bb;
-            slot[e] = (jj[e] >= 0) ? atomicAdd(&ws.bcnt[bb], 1) : kBucketCap;
-            if (slot[e] < kBucketCap) ws.blist[bb * kBucketCap + slot[e]] = me[e];
-            cnt[e] = 0;
-        }
-        __syncwarp();
-        int bsize = (lane < NB) ? ws.bcnt[lane] : 0;
-        const int bmax = __reduce_max_sync(kFull, bsize);
-        int bstart = bsize;                // inclusive scan over the NB bucket sizes
-#pragma unroll
-        for (int o = 1; o < NB; o <<= 1) {
-            const int v = __shfl_up_sync(kFull, bstart, o);
-            if (lane >= o) bstart += v;
-        }
-        __syncwarp();
-        if (lane < NB) ws.bcnt[lane] = bstart - bsize;    // exclusive start
-        __syncwarp();
-        bool exact_needed = false;
-        if (bmax <= kBucketCap) {
+        // ---- stable rank by all-pairs count -----------------------------------------------------
+        // rank(j) = #{u : s_u < s_j}: every lane streams the staged scores with broadcast 16-byte
+        // loads and counts sign bits of the packed differences (one FADD2 + two shift-adds per pair
+        // of candidates).  A tie makes both partners miss a count, so sum(rank) < n(n-1)/2 detects
+        // ties exactly; those rows (~1e-4 of torch.rand rows) take the index-tie-break path.
+        int cnt[E];
+        {
             unsigned long long m2[E];
 #pragma unroll
-            for (int e = 0; e < E; ++e) m2[e] = pack2(me[e], me[e]);
-            for (int u = 0; u < bmax; u += 4) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const float4 v = *reinterpret_cast<const float4*>(&ws.blist[bk[e] * kBucketCap + u]);
-                    count_lt2(cnt[e], v.x, v.y, m2[e]);
-                    count_lt2(cnt[e], v.z, v.w, m2[e]);
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < E; ++e) cnt[e] += ws.bcnt[bk[e]];
-        } else {                           // pathological score distribution: all-pairs sign-bit count
-            unsigned long long m2[E];
-#pragma unroll
-            for (int e = 0; e < E; ++e) m2[e] = pack2(me[e], me[e]);
+            for (int e = 0; e < E; ++e) { cnt[e] = 0; m2[e] = pack2(me[e], me[e]); }
             for (int u = 0; u < n4; u += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(&ws.sc[u]);
 #pragma unroll
@@ -225,15 +173,11 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
                 }
             }
         }
-        // ties leave two elements with the same count: detect through a rank bitmap
+        int rsum = 0;
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-            if (jj[e] >= 0) atomicOr(&ws.seen[cnt[e] >> 5], 1u << (cnt[e] & 31));
-        __syncwarp();
-        int distinct = (lane < E) ? __popc(ws.seen[lane]) : 0;
-        distinct = __reduce_add_sync(kFull, distinct);
-        exact_needed = (distinct != n);
-        if (exact_needed) {                // warp-uniform: exact stable order (lower index first)
+        for (int e = 0; e < E; ++e) rsum += (jj[e] >= 0) ? cnt[e] : 0;
+        rsum = __reduce_add_sync(kFull, rsum);
+        if (rsum != (n * (n - 1)) / 2) {   // warp-uniform: exact stable order (lower index first)
 #pragma unroll
             for (int e = 0; e < E; ++e) cnt[e] = 0;
             for (int u = 0; u < n; ++u) {
@@ -297,8 +241,11 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
         }
 
         // ---- Interp(x0 | M_s) for the requested levels ------------------------------------------
-        // Anchors compact their (position, value) into shared lists; every timestep finds its
-        // segment as popc(mask bits <= t) - 1 and reads both endpoints with independent loads.
+        // Anchor k publishes its value and position into compacted shared lists (segment k spans
+        // [pos_k, pos_{k+1}]); timestep t finds its segment as popc(mask bits <= t) - 1 and fetches
+        // both endpoints with independent loads.  w = (t-l)/(r-l) is the correctly rounded quotient:
+        // q = off*RN(1/gap), one FMA residual and one FMA correction (exhaustively equal to IEEE
+        // division for 0 <= off, gap <= 255).
         if (D) {
             for (int s = p.s_lo; s <= p.s_hi; ++s) {
                 int seg[E];
@@ -313,10 +260,12 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
                     anchor[e] = ((w >> lane) & 1u) != 0;
                     if (anchor[e]) {
                         reinterpret_cast<V*>(ws.cv)[seg[e]] = xv[e];
-                        ws.ci[seg[e]] = t;
+                        ws.seg_lr[seg[e]].x = t;
+                        if (seg[e] > 0) ws.seg_lr[seg[e] - 1].y = t;
                     }
                     base += __popc(w);
                 }
+                if (lane == 0) ws.seg_lr[base - 1].y = T - 1;      // last anchor closes on itself
                 __syncwarp();
                 const int klast = base - 1;
                 V yv[E];
@@ -325,12 +274,15 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
                     const int t = lane + 32 * e;
                     if (t >= T) continue;
                     const int k1 = min(seg[e] + 1, klast);
-                    const int l = ws.ci[seg[e]], r = ws.ci[k1];
+                    const int2 lr = ws.seg_lr[seg[e]];
                     const V vl = reinterpret_cast<const V*>(ws.cv)[seg[e]];
                     const V vr = reinterpret_cast<const V*>(ws.cv)[k1];
-                    float wt;
-                    if (K1Cfg<E>::kWTable) wt = wtab[((r - l) << 6) + (t - l)];
-                    else wt = __fdiv_rn(static_cast<float>(t - l), static_cast<float>(max(r - l, 1)));
+                    const int gap = lr.y - lr.x;
+                    const float off = static_cast<float>(t - lr.x);
+                    const float rg = rtab[gap];
+                    const float q = __fmul_rn(off, rg);
+                    const float rem = __fmaf_rn(-static_cast<float>(max(gap, 1)), q, off);
+                    const float wt = __fmaf_rn(rem, rg, q);
                     const V y = lerp_rn(vl, vr, wt);
                     yv[e] = anchor[e] ? xv[e] : y;      // anchors: exact copy (scatter_ at keyframes.py:372)
                 }
@@ -513,7 +465,7 @@ extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, 
     IDB_REQUIRE(noend || T >= 2, IDB200_EINVAL, "T must be >= 2 when using endpoints");
     NestedParams p{};
     p.n = noend ? T : T - 2;
-    IDB_REQUIRE(p.n == 0 || scores != nullptr, IDB200_EINVAL, "scores is NULL");
+    IDB_REQUIRE(B == 0 || p.n == 0 || scores != nullptr, IDB200_EINVAL, "scores is NULL");
     IDB_REQUIRE(score_stride >= p.n, IDB200_EINVAL, "score_stride smaller than the row length");
     if (x0 != nullptr) {
         IDB_REQUIRE(!noend, IDB200_EINVAL, "interpolation needs endpoint anchors");
@@ -548,12 +500,6 @@ extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, 
     p.x_levels = x_levels; p.level_stride = level_stride; p.B = B; p.T = T; p.n_levels = n_levels;
     p.s_lo = s_lo; p.s_hi = s_hi; p.flags = flags;
     p.dt = static_cast<float>(1.0 / static_cast<double>(T));
-    {   // bucket map: scores are torch.rand in [0,1) (keys in (-1,0] when descending).  For other inputs
-        // (selector logits) the map is still monotone, hence correct, just less balanced.
-        const int nb = 4 * ((T <= 32) ? 1 : (T <= 64) ? 2 : (T <= 128) ? 4 : 8);
-        p.bucket_lo = (flags & IDB200_F_DESCENDING) ? -1.0f : 0.0f;
-        p.bucket_scale = static_cast<float>(nb);
-    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (x0 == nullptr) return dispatch_nested_E<0>(p, st);
     if (D == 2) return dispatch_nested_E<2>(p, st);
