@@ -156,6 +156,22 @@ int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student, const uint
                        float conf_student, float conf_endpoints, float conf_missing, int clamp_endpoints,
                        int64_t B, int T, int C, float* conf, float* mask_in, idb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K3a  token GEMM on tcgen05 / TMEM fed by TMA:  out[M,N] = epi(A[M,K] * W[N,K]^T + bias[N])
+ *      The dense contractions of src/models/transformer.py:35-46 (packed QKV, out_proj, ff.0, ff.2)
+ *      and the in/out projections of the two denoisers (nn.Linear weight layout [out, in] = [N, K]).
+ *   A, W: bf16 row-major, 16-byte aligned; K % 64 == 0, N % 32 == 0; M arbitrary.
+ *   epilogue: 0 bf16 store, 1 SiLU then bf16 store (ff.0), 2 fp32 residual accumulate
+ *             out[M,N] += acc + bias (out_proj / ff.2 into the residual stream), 3 fp32 store.
+ * ---------------------------------------------------------------------------------------------- */
+#define IDB200_EPI_BF16 0
+#define IDB200_EPI_SILU_BF16 1
+#define IDB200_EPI_RESID_F32 2
+#define IDB200_EPI_F32 3
+
+int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K, int epilogue,
+                     idb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ _SIGS = {
     "idb200_logit_pos": [c_p, c_l, c_i, c_f, c_p, c_p],
     "idb200_sigmoid_pos": [c_p, c_l, c_i, c_p, c_p],
     "idb200_stage2_epilogue": [c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_p, c_p],
+    "idb200_gemm_bf16": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
     "idb200_anchor_conf": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_l, c_i, c_i, c_p, c_p, c_p],
 }
 

@@ -1,0 +1,283 @@
+// K3a: token GEMM  out[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)  on tcgen05 / TMEM fed by TMA.
+//
+// This is the dense building block of the two denoisers (reference: the nn.Linear / packed-QKV /
+// out_proj / ff GEMMs inside src/models/transformer.py:35-46, src/models/denoiser_keypoints.py:82-113,
+// src/models/denoiser_interp_levels.py:64-84, which today run as cuBLAS calls from PyTorch eager).
+//
+// Structure (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0      TMA producer: A tile [128 x 64] and W tile [BN x 64] bf16 per k-block, SWIZZLE_128B,
+//               kStages-deep mbarrier ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block,
+//               accumulating in TMEM; tcgen05.commit frees the smem slot / publishes the accumulator
+//   warp 2      TMEM allocator (512 columns = two BN-wide accumulator stages)
+//   warps 4..7  epilogue: tcgen05.ld (thread <-> output row), bias / SiLU / residual, global stores;
+//               overlaps the next tile's MMAs through the second accumulator stage
+// M is arbitrary (TMA zero-fills out-of-range rows, stores are row-guarded); N % BN == 0; K % 64 == 0.
+#include "tc_common.cuh"
+
+namespace idb200 {
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+}  // namespace
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(IDB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if (!aligned(base, 16) || (cols * 2) % 16 != 0) return fail(IDB200_EALIGN, "TMA needs 16-byte aligned base and row pitch");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IDB200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    return IDB200_OK;
+}
+
+using namespace tc;
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+
+enum { EPI_BF16 = 0, EPI_SILU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3 };
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
+    static constexpr int kStages = (BN <= 128) ? 6 : 4;
+    static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+    const float* bias;      // [N] or nullptr
+    void* out;              // bf16 [M,N] (EPI_BF16 / EPI_SILU_BF16), fp32 [M,N] (EPI_F32), fp32 residual in/out (EPI_RESID_F32)
+    long long M;
+    int N, K, epilogue;
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                              // [kStages]  TMA -> MMA
+    uint64_t* empty_bar = bars + Cfg::kStages;              // [kStages]  MMA -> TMA
+    uint64_t* acc_full = bars + 2 * Cfg::kStages;           // [kAccStages] MMA -> epilogue
+    uint64_t* acc_empty = acc_full + Cfg::kAccStages;       // [kAccStages] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = p.N / BN;
+    const long long m_tiles = (p.M + kBM - 1) / kBM;
+    const long long tiles = m_tiles * n_tiles;
+    const int k_blocks = p.K / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = static_cast<int>(tile / n_tiles) * kBM;
+                const int n0 = static_cast<int>(tile % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t* sb = sa + kBM * kBK * 2;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+                    tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBK, n0);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1, 2);      // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);         // TMA bytes landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + kBM * kBK * 2);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);                // smem slot free once these MMAs retire
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[acc]);                       // accumulator complete
+                if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: warp (4 + q) owns TMEM lanes [32q, 32q+32) =====
+        const int q = warp - 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const long long m0 = (tile / n_tiles) * kBM;
+            const int n0 = static_cast<int>(tile % n_tiles) * BN;
+            mbar_wait(&acc_full[acc], acc_phase, 4);
+            tc_fence_after();
+            const long long row = m0 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c, r);
+                tmem_ld_wait();
+                if (row < p.M) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __uint_as_float(r[j]);
+                        if (p.bias) v[j] += __ldg(p.bias + n0 + c + j);
+                    }
+                    const long long o = row * p.N + n0 + c;
+                    if (p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16) {
+                        if (p.epilogue == EPI_SILU_BF16) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            dst[j] = pk;
+                        }
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 w = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (p.epilogue == EPI_RESID_F32) {
+                                const float4 h = dst[j];
+                                w.x += h.x; w.y += h.y; w.z += h.z; w.w += h.w;
+                            }
+                            dst[j] = w;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const long long tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, p);
+    return check_launch("gemm_bf16_tn_kernel");
+}
+
+int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, long long M, int N, int K, int epilogue,
+                 cudaStream_t st) {
+    IDB_REQUIRE(A && W && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(M >= 0 && N > 0 && K > 0, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(K % kBK == 0, IDB200_EUNSUPPORTED, "K must be a multiple of %d (got %d)", kBK, K);
+    IDB_REQUIRE(N % 32 == 0, IDB200_EUNSUPPORTED, "N must be a multiple of 32 (got %d)", N);
+    IDB_REQUIRE(epilogue >= 0 && epilogue <= 3, IDB200_EINVAL, "unknown epilogue %d", epilogue);
+    IDB_REQUIRE(aligned(out, 16), IDB200_EALIGN, "out must be 16-byte aligned");
+    if (M == 0) return IDB200_OK;
+    int BN = 0;
+    for (int cand : {256, 192, 128, 96, 64, 32})
+        if (N % cand == 0) { BN = cand; break; }
+    CUtensorMap ta, tw;
+    int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), kBM, kBK);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint32_t>(BN), kBK);
+    if (rc) return rc;
+    GemmParams p{bias, out, M, N, K, epilogue};
+    switch (BN) {
+        case 256: return launch_gemm<256>(ta, tw, p, st);
+        case 192: return launch_gemm<192>(ta, tw, p, st);
+        case 128: return launch_gemm<128>(ta, tw, p, st);
+        case 96: return launch_gemm<96>(ta, tw, p, st);
+        case 64: return launch_gemm<64>(ta, tw, p, st);
+        default: return launch_gemm<32>(ta, tw, p, st);
+    }
+}
+
+}  // namespace idb200
+
+extern "C" int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K,
+                                int epilogue, idb200_stream_t stream) {
+    return idb200::gemm_bf16_tn(A, W, bias, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream));
+}

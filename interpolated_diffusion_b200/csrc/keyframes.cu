@@ -320,6 +320,205 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path of K1 for the headline shape: T == 64 (two timesteps per lane), NL <= 4 levels,
+// endpoint mode.  Same algorithm as the generic kernel above with every shape decision made at
+// compile time: level masks live in registers, the level loop is unrolled, no runtime divisions.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+struct FastScratch {
+    alignas(16) float sc[64 + 4];
+    alignas(16) float cv[(D ? D : 1) * 64];
+    alignas(8) int2 seg_lr[64];
+    alignas(16) unsigned mw[8];
+};
+
+template <int D, int NL>
+__global__ void __launch_bounds__(256) nested_masks_interp_t64_kernel(const NestedParams p) {
+    constexpr int kWarps = 8;
+    constexpr int T = 64, n = 62;
+    __shared__ FastScratch<D> scratch[kWarps];
+    __shared__ float rtab[64];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    FastScratch<D>& ws = scratch[warp];
+    const long long warps_total = static_cast<long long>(gridDim.x) * kWarps;
+    const bool desc = (p.flags & IDB200_F_DESCENDING) != 0;
+    const float kInf = __int_as_float(0x7f800000);
+    const unsigned lane_le = kFull >> (31 - lane);
+    using V = typename VecOf<(D ? D : 2)>::type;
+
+    if (D) {
+        if (threadIdx.x < 64) rtab[threadIdx.x] = __frcp_rn(static_cast<float>(max(static_cast<int>(threadIdx.x), 1)));
+        __syncthreads();
+    }
+    if (lane < 2) ws.sc[62 + lane] = kInf;          // padding never changes
+
+    for (long long b = static_cast<long long>(blockIdx.x) * kWarps + warp; b < p.B; b += warps_total) {
+        // lane <-> timesteps t0 = lane, t1 = lane + 32; interior score index j = t - 1
+        const float* srow = p.scores + b * p.score_stride;
+        float s0 = (lane >= 1) ? __ldg(srow + lane - 1) : kInf;
+        float s1 = (lane < 31) ? __ldg(srow + lane + 31) : kInf;
+        V x0v, x1v;
+        if (D) {
+            const V* xrow = reinterpret_cast<const V*>(p.x0) + b * T;
+            x0v = __ldg(xrow + lane);
+            x1v = __ldg(xrow + lane + 32);
+        }
+        if (desc) { s0 = -s0; s1 = -s1; }           // (+inf sentinels become -inf but are never staged)
+        const float me0 = s0 + 0.0f, me1 = s1 + 0.0f;
+        __syncwarp();
+        if (lane >= 1) ws.sc[lane - 1] = me0;
+        if (lane < 31) ws.sc[lane + 31] = me1;
+        __syncwarp();
+
+        int c0 = 0, c1 = 0;
+        {
+            const unsigned long long m0 = pack2(me0, me0), m1 = pack2(me1, me1);
+#pragma unroll
+            for (int u = 0; u < 64; u += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(&ws.sc[u]);
+                count_lt2(c0, v.x, v.y, m0);
+                count_lt2(c0, v.z, v.w, m0);
+                count_lt2(c1, v.x, v.y, m1);
+                count_lt2(c1, v.z, v.w, m1);
+            }
+        }
+        const bool v0 = lane >= 1, v1 = lane < 31;  // element holds an interior score
+        int rsum = (v0 ? c0 : 0) + (v1 ? c1 : 0);
+        rsum = __reduce_add_sync(kFull, rsum);
+        if (rsum != (n * (n - 1)) / 2) {            // ties: exact stable order (lower index first)
+            c0 = 0; c1 = 0;
+            for (int u = 0; u < n; ++u) {
+                const float su = ws.sc[u];
+                c0 += ((su < me0) || (su == me0 && u < lane - 1)) ? 1 : 0;
+                c1 += ((su < me1) || (su == me1 && u < lane + 31)) ? 1 : 0;
+            }
+        }
+
+        unsigned w0[NL], w1[NL];
+#pragma unroll
+        for (int s = 0; s < NL; ++s) {
+            const int thr = p.thr[s];
+            w0[s] = __ballot_sync(kFull, lane == 0 || c0 < thr);          // t = 0 is always an anchor
+            w1[s] = __ballot_sync(kFull, lane == 31 || c1 < thr);         // t = 63 is always an anchor
+        }
+
+        if (p.masks) {
+            // [NL, 64] bytes per trajectory = NL * 8 chunks of 8 bytes, one per lane
+            if (lane == 0) {
+#pragma unroll
+                for (int s = 0; s < NL; ++s) { ws.mw[2 * s] = w0[s]; ws.mw[2 * s + 1] = w1[s]; }
+            }
+            __syncwarp();
+            if (lane < NL * 8) {
+                const unsigned word = ws.mw[lane >> 2];
+                const unsigned bits = (word >> ((lane & 3) << 3)) & 0xffu;
+                const unsigned lo = ((bits & 0xfu) * 0x204081u) & 0x01010101u;
+                const unsigned hi = ((bits >> 4) * 0x204081u) & 0x01010101u;
+                reinterpret_cast<uint2*>(p.masks + b * (NL * 64))[lane] = make_uint2(lo, hi);
+            }
+        }
+
+        if (p.idx_out) {
+#pragma unroll
+            for (int s = 0; s < NL; ++s) {
+                const int W = p.width[s];
+                long long* irow = p.idx_out + p.idx_off[s] * p.B + b * W;
+                const int k0 = __popc(w0[s] & lane_le) - 1;
+                const int k1 = __popc(w0[s]) + __popc(w1[s] & lane_le) - 1;
+                if (((w0[s] >> lane) & 1u) && k0 < W) irow[k0] = lane;
+                if (((w1[s] >> lane) & 1u) && k1 < W) irow[k1] = lane + 32;
+            }
+        }
+
+        if (D) {
+#pragma unroll
+            for (int s = 0; s < NL; ++s) {
+                if (s < p.s_lo || s > p.s_hi) continue;               // warp-uniform
+                const int n0 = __popc(w0[s]);
+                const int seg0 = __popc(w0[s] & lane_le) - 1;
+                const int seg1 = n0 + __popc(w1[s] & lane_le) - 1;
+                const bool a0 = (w0[s] >> lane) & 1u, a1 = (w1[s] >> lane) & 1u;
+                const int klast = n0 + __popc(w1[s]) - 1;
+                __syncwarp();                                          // previous level's readers are done
+                if (a0) {
+                    reinterpret_cast<V*>(ws.cv)[seg0] = x0v;
+                    ws.seg_lr[seg0].x = lane;
+                    if (seg0 > 0) ws.seg_lr[seg0 - 1].y = lane;
+                }
+                if (a1) {
+                    reinterpret_cast<V*>(ws.cv)[seg1] = x1v;
+                    ws.seg_lr[seg1].x = lane + 32;
+                    ws.seg_lr[seg1 - 1].y = lane + 32;                 // seg1 >= 1: t = 0 is an anchor
+                    if (lane == 31) ws.seg_lr[seg1].y = 63;            // last anchor closes on itself
+                }
+                __syncwarp();
+                V* orow = reinterpret_cast<V*>(p.x_levels + static_cast<long long>(s - p.s_lo) * p.level_stride) + b * T;
+                V y0 = x0v, y1 = x1v;
+                if (!a0) {
+                    const int2 lr = ws.seg_lr[seg0];
+                    const V vl = reinterpret_cast<const V*>(ws.cv)[seg0];
+                    const V vr = reinterpret_cast<const V*>(ws.cv)[seg0 + 1];
+                    const int gap = lr.y - lr.x;                       // >= 2 for a non-anchor
+                    const float off = static_cast<float>(lane - lr.x);
+                    const float rg = rtab[gap];
+                    const float q = __fmul_rn(off, rg);
+                    const float wt = __fmaf_rn(__fmaf_rn(-static_cast<float>(gap), q, off), rg, q);
+                    y0 = lerp_rn(vl, vr, wt);
+                }
+                if (!a1) {
+                    const int2 lr = ws.seg_lr[seg1];
+                    const V vl = reinterpret_cast<const V*>(ws.cv)[seg1];
+                    const V vr = reinterpret_cast<const V*>(ws.cv)[min(seg1 + 1, klast)];
+                    const int gap = lr.y - lr.x;
+                    const float off = static_cast<float>(lane + 32 - lr.x);
+                    const float rg = rtab[gap];
+                    const float q = __fmul_rn(off, rg);
+                    const float wt = __fmaf_rn(__fmaf_rn(-static_cast<float>(gap), q, off), rg, q);
+                    y1 = lerp_rn(vl, vr, wt);
+                }
+                if (D == 4 && (p.flags & IDB200_F_RECOMPUTE_VELOCITY)) {
+                    // v[t] = (pos[t+1] - pos[t]) / dt, v[T-1] = 0   (keyframes.py:373-379)
+                    float nx0 = __shfl_down_sync(kFull, y0.x, 1), ny0 = __shfl_down_sync(kFull, y0.y, 1);
+                    const float nx1 = __shfl_down_sync(kFull, y1.x, 1), ny1 = __shfl_down_sync(kFull, y1.y, 1);
+                    const float fx = __shfl_sync(kFull, y1.x, 0), fy = __shfl_sync(kFull, y1.y, 0);
+                    if (lane == 31) { nx0 = fx; ny0 = fy; }
+                    float4 o0, o1;
+                    o0.x = y0.x; o0.y = y0.y;
+                    o0.z = __fdiv_rn(__fsub_rn(nx0, y0.x), p.dt);
+                    o0.w = __fdiv_rn(__fsub_rn(ny0, y0.y), p.dt);
+                    o1.x = y1.x; o1.y = y1.y;
+                    o1.z = (lane == 31) ? 0.0f : __fdiv_rn(__fsub_rn(nx1, y1.x), p.dt);
+                    o1.w = (lane == 31) ? 0.0f : __fdiv_rn(__fsub_rn(ny1, y1.y), p.dt);
+                    *reinterpret_cast<float4*>(&orow[lane]) = o0;
+                    *reinterpret_cast<float4*>(&orow[lane + 32]) = o1;
+                } else {
+                    orow[lane] = y0;
+                    orow[lane + 32] = y1;
+                }
+            }
+        }
+    }
+}
+
+template <int D, int NL>
+static int launch_nested_t64(const NestedParams& p, cudaStream_t st) {
+    const int grid = grid_for(p.B, 8, 8);
+    nested_masks_interp_t64_kernel<D, NL><<<grid, 256, 0, st>>>(p);
+    return check_launch("nested_masks_interp_t64_kernel");
+}
+
+template <int D>
+static int dispatch_nested_t64(const NestedParams& p, cudaStream_t st) {
+    switch (p.n_levels) {
+        case 1: return launch_nested_t64<D, 1>(p, st);
+        case 2: return launch_nested_t64<D, 2>(p, st);
+        case 3: return launch_nested_t64<D, 3>(p, st);
+        default: return launch_nested_t64<D, 4>(p, st);
+    }
+}
+
 template <int E, int D>
 static int launch_nested(const NestedParams& p, cudaStream_t st) {
     constexpr int kWarps = K1Cfg<E>::kWarps;
@@ -501,6 +700,11 @@ extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, 
     p.s_lo = s_lo; p.s_hi = s_hi; p.flags = flags;
     p.dt = static_cast<float>(1.0 / static_cast<double>(T));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (T == 64 && n_levels <= 4 && !noend) {      // compile-time specialised headline shape
+        if (x0 == nullptr) return dispatch_nested_t64<0>(p, st);
+        if (D == 2) return dispatch_nested_t64<2>(p, st);
+        return dispatch_nested_t64<4>(p, st);
+    }
     if (x0 == nullptr) return dispatch_nested_E<0>(p, st);
     if (D == 2) return dispatch_nested_E<2>(p, st);
     return dispatch_nested_E<4>(p, st);
@@ -508,8 +712,8 @@ extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, 
 
 extern "C" int idb200_interpolate_from_indices(const int64_t* idx, const float* vals, int64_t B, int K, int T, int D,
                                                int recompute_velocity, float* y, idb200_stream_t stream) {
-    IDB_REQUIRE(idx && vals && y, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(B >= 0 && D >= 1 && T >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(B == 0 || (idx && vals && y), IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(K >= 2, IDB200_EINVAL, "K must be >= 2");
     IDB_REQUIRE(K <= 8192 && T <= 65536, IDB200_EUNSUPPORTED, "K <= 8192 and T <= 65536 supported");
     if (B == 0) return IDB200_OK;
@@ -525,8 +729,8 @@ extern "C" int idb200_corrupt_from_anchors(const float* source, const int64_t* i
                                            int64_t B, int K, int T, int D, float sigma, float anchor_sigma, int mode_dist,
                                            int clamp_endpoints, int recompute_velocity, float* out,
                                            idb200_stream_t stream) {
-    IDB_REQUIRE(source && idx && out, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(B >= 0 && D >= 1 && T >= 1 && K >= 2, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(B == 0 || (source && idx && out), IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE((!anchor_noise && !path_noise) || D >= 2, IDB200_EINVAL, "noise needs D >= 2");
     const size_t smem = sizeof(int) * K + sizeof(float) * (static_cast<size_t>(K) * D + 2 * static_cast<size_t>(T));
     IDB_REQUIRE(smem <= 48 * 1024, IDB200_EUNSUPPORTED, "K*D + 2T too large for one CTA (%zu bytes)", smem);
