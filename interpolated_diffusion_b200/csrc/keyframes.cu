@@ -327,11 +327,25 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
 // ------------------------------------------------------------------------------------------------
 template <int D>
 struct FastScratch {
+    alignas(16) float xin[2][(D ? D : 1) * 64];   // cp.async landing buffers for the row (double-buffered)
+    alignas(16) float sin_[2][64];                // ... and for the 62 scores
     alignas(16) float sc[64 + 4];
     alignas(16) float cv[(D ? D : 1) * 64];
     alignas(8) int2 seg_lr[64];
     alignas(16) unsigned mw[8];
 };
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int D, int NL>
 __global__ void __launch_bounds__(256) nested_masks_interp_t64_kernel(const NestedParams p) {
@@ -346,6 +360,7 @@ __global__ void __launch_bounds__(256) nested_masks_interp_t64_kernel(const Nest
     const bool desc = (p.flags & IDB200_F_DESCENDING) != 0;
     const float kInf = __int_as_float(0x7f800000);
     const unsigned lane_le = kFull >> (31 - lane);
+    const bool s8 = ((p.score_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.scores) & 7) == 0);  // 8-byte score rows
     using V = typename VecOf<(D ? D : 2)>::type;
 
     if (D) {
@@ -354,17 +369,43 @@ __global__ void __launch_bounds__(256) nested_masks_interp_t64_kernel(const Nest
     }
     if (lane < 2) ws.sc[62 + lane] = kInf;          // padding never changes
 
-    for (long long b = static_cast<long long>(blockIdx.x) * kWarps + warp; b < p.B; b += warps_total) {
-        // lane <-> timesteps t0 = lane, t1 = lane + 32; interior score index j = t - 1
+    // Software pipeline: the next trajectory's row and scores stream into shared memory with cp.async
+    // (no registers held) while the current one is ranked and interpolated.
+    auto prefetch = [&](long long b, int buf) {
         const float* srow = p.scores + b * p.score_stride;
-        float s0 = (lane >= 1) ? __ldg(srow + lane - 1) : kInf;
-        float s1 = (lane < 31) ? __ldg(srow + lane + 31) : kInf;
-        V x0v, x1v;
+        if (s8) {
+            if (lane < 31) cp_async_8(&ws.sin_[buf][2 * lane], srow + 2 * lane);
+        } else {
+            cp_async_4(&ws.sin_[buf][lane], srow + lane);
+            if (lane < 30) cp_async_4(&ws.sin_[buf][lane + 32], srow + lane + 32);
+        }
         if (D) {
             const V* xrow = reinterpret_cast<const V*>(p.x0) + b * T;
-            x0v = __ldg(xrow + lane);
-            x1v = __ldg(xrow + lane + 32);
+            if (D == 4) {
+                cp_async_16(&reinterpret_cast<V*>(ws.xin[buf])[lane], xrow + lane);
+                cp_async_16(&reinterpret_cast<V*>(ws.xin[buf])[lane + 32], xrow + lane + 32);
+            } else {
+                cp_async_16(&reinterpret_cast<float4*>(ws.xin[buf])[lane], reinterpret_cast<const float4*>(xrow) + lane);
+            }
         }
+        cp_async_commit();
+    };
+
+    long long b = static_cast<long long>(blockIdx.x) * kWarps + warp;
+    int buf = 0;
+    if (b < p.B) prefetch(b, 0);
+    for (; b < p.B; b += warps_total, buf ^= 1) {
+        cp_async_wait_all();
+        __syncwarp();
+        // lane <-> timesteps t0 = lane, t1 = lane + 32; interior score index j = t - 1
+        float s0 = (lane >= 1) ? ws.sin_[buf][lane - 1] : kInf;
+        float s1 = (lane < 31) ? ws.sin_[buf][lane + 31] : kInf;
+        V x0v, x1v;
+        if (D) {
+            x0v = reinterpret_cast<const V*>(ws.xin[buf])[lane];
+            x1v = reinterpret_cast<const V*>(ws.xin[buf])[lane + 32];
+        }
+        if (b + warps_total < p.B) prefetch(b + warps_total, buf ^ 1);   // buffer buf^1 was consumed last iteration
         if (desc) { s0 = -s0; s1 = -s1; }           // (+inf sentinels become -inf but are never staged)
         const float me0 = s0 + 0.0f, me1 = s1 + 0.0f;
         __syncwarp();
@@ -700,7 +741,7 @@ extern "C" int idb200_nested_masks_interp(const float* x0, const float* scores, 
     p.s_lo = s_lo; p.s_hi = s_hi; p.flags = flags;
     p.dt = static_cast<float>(1.0 / static_cast<double>(T));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (T == 64 && n_levels <= 4 && !noend) {      // compile-time specialised headline shape
+    if (T == 64 && n_levels <= 4 && !noend && (x0 == nullptr || aligned(x0, 16))) {   // compile-time specialised headline shape
         if (x0 == nullptr) return dispatch_nested_t64<0>(p, st);
         if (D == 2) return dispatch_nested_t64<2>(p, st);
         return dispatch_nested_t64<4>(p, st);
