@@ -172,6 +172,54 @@ int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student, const uint
 int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K, int epilogue,
                      idb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Denoiser building blocks (KeypointDenoiser / InterpLevelDenoiser forwards,
+ * src/models/denoiser_keypoints.py:82-113, src/models/denoiser_interp_levels.py:64-84,
+ * src/models/transformer.py:35-46, src/models/encoders.py:8-71).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* fp32 SIMT GEMM out[M,N](ldo) = act(A[M,K](lda) * W[N,K]^T + bias) (+ out when accumulate != 0):
+ * the per-trajectory linears (cond_proj, FiLM, t_embed, level_proj, maze.fc, sg.mlp; M = B, K <= 256) and
+ * the fp32 check mode of the token GEMMs.  A fp32 or bf16 (a_is_bf16); act: 0 none, 1 SiLU. */
+int idb200_sgemm(const void* A, int a_is_bf16, int64_t lda, const float* W, const float* bias, float* out,
+                 int64_t ldo, int64_t M, int N, int K, int act, int accumulate, idb200_stream_t stream);
+
+/* MazeEncoder conv stack, src/models/encoders.py:15-24: [conv3x3 pad 1 + SiLU] x n_layers then the mean
+ * over H x W.  occ / sdf [B,1,H,W] fp32 (sdf iff channels[0] == 2); channels host [n_layers+1];
+ * weights / biases host arrays of device pointers ([C_out,C_in,3,3], [C_out]); pooled [B, C_last]. */
+int idb200_conv_encoder(const float* occ, const float* sdf, int64_t B, int H, int W, int n_layers, const int* channels,
+                        const float* const* weights, const float* const* biases, float* pooled,
+                        idb200_stream_t stream);
+
+/* sinusoid table out[rows, dim] = [sin(a f_i) | cos(a f_i)], f_i = exp(-ln(1e4) i / (dim/2)):
+ * mode 0: a = r / max(1, rows-1) (continuous_time_embedding of idx/(T-1), denoiser_keypoints.py:24-34);
+ * mode 1: a = args[r] (timestep_embedding :11-21; _positional_embedding of denoiser_interp_levels.py:54-62). */
+int idb200_sinusoid(const float* args, int rows, int dim, int mode, float* out, idb200_stream_t stream);
+
+/* token assembly + in_proj (denoiser_keypoints.py:102-111, denoiser_interp_levels.py:71-82):
+ *   h[m,:] = [src0 | src1 | src2][m,:] . Wf + tab[tab_idx ? tab_idx[m] : m % L] + row_a[(m/L) * row_a_stride]
+ *            + row_b[(m/L) * d]
+ * src0 fp32 [M,n0], src1 fp32 [M,n1] or NULL, src2 uint8 [M,n2] or NULL (n0+n1+n2 <= 16), Wf [n0+n1+n2, d]. */
+int idb200_embed_tokens(const float* src0, int n0, const float* src1, int n1, const uint8_t* src2, int n2,
+                        const float* Wf, const float* tab, const int64_t* tab_idx, const float* row_a,
+                        int64_t row_a_stride, const float* row_b, float* h, int64_t M, int L, int d,
+                        idb200_stream_t stream);
+
+/* LayerNorm(eps 1e-5) + FiLM, src/models/transformer.py:28-41: out = LN(h) * (1 + gamma[b]) + beta[b];
+ * gamma_beta row b = [gamma (d) | beta (d)] at stride gb_stride (NULL: no FiLM); out bf16 or fp32 [M,d]. */
+int idb200_ln_film(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                   void* out, int out_is_bf16, int64_t M, int L, int d, idb200_stream_t stream);
+
+/* output head y[M,D] = h[M,d] . W[D,d]^T + bias (D <= 4; the `out` Linear of both denoisers). */
+int idb200_out_head(const float* h, const float* W, const float* bias, float* y, int64_t M, int d, int D,
+                    idb200_stream_t stream);
+
+/* multi-head self-attention of nn.MultiheadAttention (transformer.py:11,39) on a packed qkv [B*L, 3*H*32]:
+ * out[B*L, H*32] = softmax(q k^T / sqrt(32) [+ causal mask]) v per trajectory and head.  bf16 (mma.sync
+ * path when L % 16 == 0, else / force_simt: fp32 CUDA-core math) or fp32 in/out.  L <= 256. */
+int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t B, int L, int H, int causal, int force_simt,
+                     idb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,307 @@
+// K3b: small-sequence multi-head attention (bidirectional or causal), head_dim = 32.
+//
+// Reference: nn.MultiheadAttention inside src/models/transformer.py:11,39 (packed QKV already projected by
+// the token GEMM; this file is softmax(Q K^T / sqrt(32) [+ causal mask]) V per trajectory and head; the
+// -inf upper-triangular mask of transformer.py:68-71 is the `causal` flag).
+//
+//   attn_simt   fp32 CUDA-core path: L = 8 (Stage 1, 0.5 % of the FLOPs) and the fp32 check mode.
+//               Lanes map to (problem, query); several (trajectory, head) problems share a warp when L < 32.
+//   attn_mma    bf16 mma.sync m16n8k16 path with ldmatrix fragments and an online softmax over 64-key
+//               blocks: L = 16..256 (Stage 2, L = 64; long-horizon causal L = 256).  One warp per
+//               (head, 16-query block); Q/K/V of the CTA's (trajectory, head group) are staged in shared
+//               memory with cp.async.  Attention is <= 14 % of the FLOPs, the tcgen05
+//               pipeline is reserved for the projections.
+// qkv: [M, 3d] rows = tokens, columns [q | k | v], head h at columns h*32 inside each third.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace idb200 {
+
+constexpr int kHD = 32;
+
+template <typename T> __device__ __forceinline__ float ld_f32(const T* p);
+template <> __device__ __forceinline__ float ld_f32<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_f32<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st_f32(T* p, float v);
+template <> __device__ __forceinline__ void st_f32<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_f32<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------
+// SIMT path
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, long long B, int L, int H,
+                                                        int causal) {
+    extern __shared__ float smem_kv[];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = (L < 32) ? 32 / L : 1;          // problems per warp
+    const int d = H * kHD;
+    const long long problems = B * H;
+    const long long groups = (problems + G - 1) / G;
+    float* Ks = smem_kv + static_cast<size_t>(warp) * 2 * G * L * (kHD + 1);
+    float* Vs = Ks + static_cast<size_t>(G) * L * (kHD + 1);
+    const float scale = rsqrtf(static_cast<float>(kHD));
+    for (long long grp = static_cast<long long>(blockIdx.x) * warps + warp; grp < groups; grp += static_cast<long long>(gridDim.x) * warps) {
+        __syncwarp();
+        // stage K and V of the G problems: element e -> (g, j, c)
+        for (int e = lane; e < G * L * kHD; e += 32) {
+            const int c = e % kHD, j = (e / kHD) % L, g = e / (kHD * L);
+            const long long pr = grp * G + g;
+            float kv = 0.0f, vv = 0.0f;
+            if (pr < problems) {
+                const long long b = pr / H;
+                const int h = static_cast<int>(pr - b * H);
+                const T* row = qkv + (b * L + j) * 3 * d;
+                kv = ld_f32<T>(row + d + h * kHD + c);
+                vv = ld_f32<T>(row + 2 * d + h * kHD + c);
+            }
+            Ks[(g * L + j) * (kHD + 1) + c] = kv;
+            Vs[(g * L + j) * (kHD + 1) + c] = vv;
+        }
+        __syncwarp();
+        const int reps = (L + 31) / 32;
+        for (int r = 0; r < reps; ++r) {
+            const int g = (L < 32) ? lane / L : 0;
+            const int i = (L < 32) ? lane % L : lane + 32 * r;
+            const long long pr = grp * G + g;
+            if (g >= G || i >= L || pr >= problems) continue;
+            const long long b = pr / H;
+            const int h = static_cast<int>(pr - b * H);
+            const T* qrow = qkv + (b * L + i) * 3 * d + h * kHD;
+            float q[kHD], o[kHD];
+#pragma unroll
+            for (int c = 0; c < kHD; ++c) { q[c] = ld_f32<T>(qrow + c) * scale; o[c] = 0.0f; }
+            float mx = -INFINITY, den = 0.0f;
+            const int jend = causal ? i + 1 : L;
+            for (int j = 0; j < jend; ++j) {
+                const float* kr = Ks + (g * L + j) * (kHD + 1);
+                const float* vr = Vs + (g * L + j) * (kHD + 1);
+                float s = 0.0f;
+#pragma unroll
+                for (int c = 0; c < kHD; ++c) s = fmaf(q[c], kr[c], s);
+                const float mn = fmaxf(mx, s);
+                const float corr = expf(mx - mn);
+                const float pj = expf(s - mn);
+                den = den * corr + pj;
+#pragma unroll
+                for (int c = 0; c < kHD; ++c) o[c] = fmaf(pj, vr[c], o[c] * corr);
+                mx = mn;
+            }
+            const float inv = 1.0f / den;
+            T* orow = out + (b * L + i) * d + h * kHD;
+#pragma unroll
+            for (int c = 0; c < kHD; ++c) st_f32<T>(orow + c, o[c] * inv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mma.sync path (bf16)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(unsigned (&r)[4], const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_ptr))));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned (&r)[4], const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_ptr))));
+}
+// D(16x8 f32) += A(16x16 bf16, row) * B(16x8 bf16, col)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned*>(&v);
+}
+
+constexpr int kPitch = 40;      // bf16 elements per staged row (80 bytes): conflict-free ldmatrix rows
+
+// grid.x = B * (H / HG); CTA stages Q, K, V of HG heads of one trajectory: [3][HG][L][kPitch] bf16
+__global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                       long long B, int L, int H, int HG, int causal) {
+    extern __shared__ __align__(16) unsigned char smem_attn[];
+    __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+    const int d = H * kHD;
+    const int groups_per_b = H / HG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const size_t part = static_cast<size_t>(HG) * L * kPitch;       // elements per Q / K / V region
+    const float scale_log2 = rsqrtf(static_cast<float>(kHD)) * 1.4426950408889634f;
+    for (long long cta = blockIdx.x; cta < B * groups_per_b; cta += gridDim.x) {
+        const long long b = cta / groups_per_b;
+        const int h0 = static_cast<int>(cta - b * groups_per_b) * HG;
+        __syncthreads();
+        // stage: 16-byte chunks; per token row, per third (q/k/v), HG*32 contiguous bf16 = HG*4 chunks
+        const int chunks_per_tok = 3 * HG * 4;
+        for (int e = threadIdx.x; e < L * chunks_per_tok; e += blockDim.x) {
+            const int tok = e / chunks_per_tok, r = e - tok * chunks_per_tok;
+            const int third = r / (HG * 4), rr = r - third * (HG * 4);
+            const int hh = rr >> 2, ck = rr & 3;
+            const __nv_bfloat16* src = qkv + (b * L + tok) * 3 * d + third * d + (h0 + hh) * kHD + ck * 8;
+            __nv_bfloat16* dst = sm + third * part + (static_cast<size_t>(hh) * L + tok) * kPitch + ck * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        const int qblocks = L / 16;
+        for (int task = warp; task < HG * qblocks; task += nwarps) {
+            const int hh = task / qblocks, qb = task - hh * qblocks;
+            const __nv_bfloat16* Qs = sm + (static_cast<size_t>(hh) * L + qb * 16) * kPitch;
+            const __nv_bfloat16* Ks = sm + part + static_cast<size_t>(hh) * L * kPitch;
+            const __nv_bfloat16* Vs = sm + 2 * part + static_cast<size_t>(hh) * L * kPitch;
+            // Q fragments: two k-steps (dims 0-15, 16-31); ldmatrix x4: matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7),
+            // (rows 0-7, k 8-15), (rows 8-15, k 8-15) -> a0..a3
+            unsigned qa[2][4];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int col = ks * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(qa[ks], Qs + row * kPitch + col);
+            }
+            float o[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[nt][c] = 0.0f;
+            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;   // rows g and g+8 of the 16-row block
+            const int g = lane >> 2, tq = lane & 3;
+            const int qrow0 = qb * 16 + g, qrow1 = qrow0 + 8;
+            const int kend = causal ? (qb + 1) * 16 : L;                   // keys needed by this query block
+            for (int k0 = 0; k0 < kend; k0 += 64) {
+                const int kw = min(64, kend - k0);                         // multiple of 16
+                float s[8][4];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[nt][c] = 0.0f;
+                    if (nt * 8 < kw) {
+                        // B fragments of K for keys k0 + nt*8 .. +7: matrices (dims 0-7), (8-15), (16-23), (24-31)
+                        unsigned kb[4];
+                        ldmatrix_x4(kb, Ks + (k0 + nt * 8 + (lane & 7)) * kPitch + (lane >> 3) * 8);
+                        mma_bf16_16816(s[nt], qa[0], kb[0], kb[1]);
+                        mma_bf16_16816(s[nt], qa[1], kb[2], kb[3]);
+                    }
+                }
+                // scale, mask, block max
+                float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int key = k0 + nt * 8 + tq * 2 + (c & 1);
+                        const int qr = (c < 2) ? qrow0 : qrow1;
+                        const bool ok = (nt * 8 < kw) && (!causal || key <= qr);
+                        s[nt][c] = ok ? s[nt][c] * scale_log2 : -INFINITY;
+                    }
+                    bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+                    bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+                }
+                bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+                bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+                bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+                bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+                const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);     // finite: key 0 is always visible
+                const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+                m0 = mn0; m1 = mn1;
+                float rs0 = 0.0f, rs1 = 0.0f;
+                unsigned pa[4][4];                                          // P as A fragments, one per 16-key step
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const float p0 = exp2f(s[nt][0] - mn0), p1 = exp2f(s[nt][1] - mn0);
+                    const float p2 = exp2f(s[nt][2] - mn1), p3 = exp2f(s[nt][3] - mn1);
+                    rs0 += p0 + p1;
+                    rs1 += p2 + p3;
+                    // C layout of key tiles (2j, 2j+1) -> A fragment of k-step j: a0 = rows g keys 0-7, a1 = rows g+8 keys 0-7,
+                    // a2 = rows g keys 8-15, a3 = rows g+8 keys 8-15
+                    pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+                    pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+                }
+                l0 = l0 * c0 + rs0;
+                l1 = l1 * c1 + rs1;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+                // O += P V: k-steps of 16 keys; B fragments of V via transposed ldmatrix:
+                // matrices (keys 0-7, dims n0..n0+7), (keys 8-15, same dims), (keys 0-7, dims n0+8..), (keys 8-15, ...)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks * 16 < kw) {
+#pragma unroll
+                        for (int np = 0; np < 2; ++np) {
+                            unsigned vb[4];
+                            const int key = k0 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                            const int col = np * 16 + (lane >> 4) * 8;
+                            ldmatrix_x4_trans(vb, Vs + key * kPitch + col);
+                            mma_bf16_16816(o[np * 2 + 0], pa[ks], vb[0], vb[1]);
+                            mma_bf16_16816(o[np * 2 + 1], pa[ks], vb[2], vb[3]);
+                        }
+                    }
+                }
+            }
+            // the row sums live in the 4 lanes of a quad
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+            __nv_bfloat16* o0 = out + (b * L + qrow0) * d + (h0 + hh) * kHD;
+            __nv_bfloat16* o1 = out + (b * L + qrow1) * d + (h0 + hh) * kHD;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                *reinterpret_cast<unsigned*>(o0 + nt * 8 + tq * 2) = pack_bf16(o[nt][0] * i0, o[nt][1] * i0);
+                *reinterpret_cast<unsigned*>(o1 + nt * 8 + tq * 2) = pack_bf16(o[nt][2] * i1, o[nt][3] * i1);
+            }
+        }
+    }
+}
+
+}  // namespace idb200
+
+using namespace idb200;
+
+extern "C" int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t B, int L, int H, int causal, int force_simt,
+                                idb200_stream_t stream) {
+    IDB_REQUIRE(B >= 0 && L >= 1 && H >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(L <= 256, IDB200_EUNSUPPORTED, "attention supports L <= 256 (got %d)", L);
+    if (B == 0) return IDB200_OK;
+    IDB_REQUIRE(qkv && out, IDB200_EINVAL, "NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool use_mma = is_bf16 && !force_simt && (L % 16 == 0) && aligned(qkv, 16) && aligned(out, 4);
+    if (use_mma) {
+        int HG = H;
+        while (HG > 1 && (3 * static_cast<size_t>(HG) * L * kPitch * 2 > 100 * 1024 || H % HG != 0)) --HG;
+        const size_t smem = 3 * static_cast<size_t>(HG) * L * kPitch * 2;
+        static size_t smem_set = 0;
+        if (smem > smem_set) {
+            cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            smem_set = smem;
+        }
+        const int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+        const int grid = grid_for(B * (H / HG), 1, per_sm > 0 ? per_sm : 1);
+        attn_mma_kernel<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), B, L, H, HG, causal);
+        return check_launch("attn_mma_kernel");
+    }
+    const int G = (L < 32) ? 32 / L : 1;
+    const int warps = (L <= 64) ? 4 : 1;
+    const size_t smem = static_cast<size_t>(warps) * 2 * G * L * (kHD + 1) * sizeof(float);
+    const long long groups = (B * H + G - 1) / G;
+    const int grid = grid_for(groups, warps, 8);
+    if (is_bf16) {
+        static size_t set_b = 0;
+        if (smem > set_b) { cudaFuncSetAttribute(attn_simt_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); set_b = smem; }
+        attn_simt_kernel<__nv_bfloat16><<<grid, warps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), B, L, H, causal);
+    } else {
+        static size_t set_f = 0;
+        if (smem > set_f) { cudaFuncSetAttribute(attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); set_f = smem; }
+        attn_simt_kernel<float><<<grid, warps * 32, smem, st>>>(static_cast<const float*>(qkv), static_cast<float*>(out), B, L, H, causal);
+    }
+    return check_launch("attn_simt_kernel");
+}

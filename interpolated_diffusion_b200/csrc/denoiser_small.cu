@@ -1,0 +1,439 @@
+// Small (non-GEMM-dominant) kernels of the two denoisers.
+//
+// Reference modules being replaced (paths under the reference root):
+//   src/models/encoders.py:8-71                       MazeEncoder / StartGoalEncoder / MazeConditionEncoder
+//   src/models/denoiser_keypoints.py:11-34, 91-111    sinusoid embeddings, token assembly, in_proj, t_embed
+//   src/models/denoiser_interp_levels.py:54-82        positional embedding, token assembly, in_proj, level_proj
+//   src/models/transformer.py:28-46                   LayerNorm + FiLM (the GEMMs are in gemm.cu)
+//
+//   sgemm_tn      fp32 SIMT GEMM for the per-trajectory linears (cond_proj, FiLM gamma/beta, t_embed,
+//                 level_proj, fc) -- M = B rows, tiny K -- and for the fp32 check mode of the token GEMMs
+//   conv_encoder  3x3 pad-1 conv stack + SiLU, global mean pool (fp32, planes resident in shared memory)
+//   embed_*       token assembly + in_proj as a gathered small-K product (the sinusoid part of in_proj is
+//                 a [T, d] table because idx takes T values; timestep / level / cond terms are per-row adds)
+//   ln_film       LayerNorm(eps 1e-5) * (1 + gamma) + beta -> bf16 (or fp32) GEMM operand
+//   out_head      h[M,d] . W_out[D,d]^T + b  (D = 2 or 4: memory-bound dot products)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace idb200 {
+
+__device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// fp32 SIMT GEMM: out[M,N] (ldo) = act(A[M,K] (lda) * W[N,K]^T + bias[N]) (+ out if accumulate)
+// 64x64 tile, 16-deep k-blocks, 256 threads, 4x4 register tile.
+// ------------------------------------------------------------------------------------------------
+template <typename TA>
+__device__ __forceinline__ float to_f32(TA v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename TA>
+__global__ void __launch_bounds__(256) sgemm_tn_kernel(const TA* __restrict__ A, long long lda, const float* __restrict__ W,
+                                                       const float* __restrict__ bias, float* __restrict__ out, long long ldo,
+                                                       long long M, int N, int K, int act, int accumulate) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long m0 = static_cast<long long>(blockIdx.y) * 64;
+    const int n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, c = i & 15;
+            const long long m = m0 + r;
+            const int k = k0 + c;
+            As[c][r] = (m < M && k < K) ? to_f32<TA>(A[m * lda + k]) : 0.0f;
+            const int nn = n0 + r;
+            Ws[c][r] = (nn < N && k < K) ? W[static_cast<long long>(nn) * K + k] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[c][ty * 4 + i]; w[i] = Ws[c][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nn = n0 + tx * 4 + j;
+            if (nn >= N) continue;
+            float v = acc[i][j] + (bias ? bias[nn] : 0.0f);
+            if (act == 1) v = silu_exact(v);
+            if (accumulate) v += out[m * ldo + nn];
+            out[m * ldo + nn] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv encoder: one CTA per trajectory; activation planes [C][H+2][W+2] fp32 in shared memory (zero
+// border = padding 1), layers ping-pong between two plane buffers; SiLU after each conv; the last
+// layer is reduced to the spatial mean [C_last] and written to pooled[b, :].
+// ------------------------------------------------------------------------------------------------
+struct ConvParams {
+    const float* occ;        // [B, 1, H, W]
+    const float* sdf;        // [B, 1, H, W] or nullptr
+    const float* w[6];       // layer weights [C_out, C_in, 3, 3]
+    const float* bias[6];    // [C_out]
+    int ch[7];               // ch[0] = input channels, ch[l+1] = C_out of layer l
+    int n_layers;
+    int H, W;
+    long long B;
+    float* pooled;           // [B, ch[n_layers]]
+};
+
+__global__ void __launch_bounds__(256) conv_encoder_kernel(const ConvParams p) {
+    extern __shared__ float smem_f[];
+    const int PH = p.H + 2, PW = p.W + 2, plane = PH * PW, HW = p.H * p.W;
+    int cmax = 0;
+    for (int l = 0; l <= p.n_layers; ++l) cmax = max(cmax, p.ch[l]);
+    float* buf0 = smem_f;
+    float* buf1 = smem_f + static_cast<size_t>(cmax) * plane;
+    for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * cmax * plane; i += blockDim.x) smem_f[i] = 0.0f;   // borders stay zero
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.ch[0] * HW; i += blockDim.x) {
+            const int c = i / HW, r = i - c * HW, y = r / p.W, x = r - y * p.W;
+            const float* src = (c == 0) ? p.occ : p.sdf;
+            buf0[c * plane + (y + 1) * PW + x + 1] = src[b * HW + r];
+        }
+        float* in = buf0;
+        float* outp = buf1;
+        for (int l = 0; l < p.n_layers; ++l) {
+            __syncthreads();
+            const int ci = p.ch[l], co = p.ch[l + 1];
+            __syncthreads();
+            // each thread: one output channel x a strip of 4 horizontally adjacent pixels
+            const int strips_per_row = (p.W + 3) / 4;
+            const int strips = p.H * strips_per_row;
+            for (int item = threadIdx.x; item < co * strips; item += blockDim.x) {
+                const int c = item / strips, s = item - c * strips;
+                const int y = s / strips_per_row, x0 = (s - y * strips_per_row) * 4;
+                float a0 = p.bias[l][c], a1 = a0, a2 = a0, a3 = a0;
+                const float* wc = p.w[l] + static_cast<long long>(c) * ci * 9;
+                for (int k = 0; k < ci; ++k) {
+                    const float* ip = in + k * plane + y * PW + x0;       // top-left of the 3 x 6 window
+                    const float* wk = wc + k * 9;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const float i0 = ip[ky * PW + 0], i1 = ip[ky * PW + 1], i2 = ip[ky * PW + 2];
+                        const float i3 = (x0 + 3 < PW) ? ip[ky * PW + 3] : 0.0f;
+                        const float i4 = (x0 + 4 < PW) ? ip[ky * PW + 4] : 0.0f;
+                        const float i5 = (x0 + 5 < PW) ? ip[ky * PW + 5] : 0.0f;
+                        const float w0 = __ldg(wk + ky * 3), w1 = __ldg(wk + ky * 3 + 1), w2 = __ldg(wk + ky * 3 + 2);
+                        a0 = fmaf(i0, w0, fmaf(i1, w1, fmaf(i2, w2, a0)));
+                        a1 = fmaf(i1, w0, fmaf(i2, w1, fmaf(i3, w2, a1)));
+                        a2 = fmaf(i2, w0, fmaf(i3, w1, fmaf(i4, w2, a2)));
+                        a3 = fmaf(i3, w0, fmaf(i4, w1, fmaf(i5, w2, a3)));
+                    }
+                }
+                const float v[4] = {silu_exact(a0), silu_exact(a1), silu_exact(a2), silu_exact(a3)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x0 + j < p.W) outp[c * plane + (y + 1) * PW + x0 + j + 1] = v[j];
+            }
+            float* t = in; in = outp; outp = t;
+        }
+        __syncthreads();
+        // spatial mean of the last layer: one warp per channel, fixed summation order (deterministic)
+        const int cl = p.ch[p.n_layers];
+        for (int c = threadIdx.x >> 5; c < cl; c += blockDim.x >> 5) {
+            float acc = 0.0f;
+            for (int i = threadIdx.x & 31; i < HW; i += 32) {
+                const int y = i / p.W, x = i - y * p.W;
+                acc += in[c * plane + (y + 1) * PW + x + 1];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((threadIdx.x & 31) == 0) p.pooled[b * cl + c] = acc / static_cast<float>(HW);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sinusoid tables: out[r, :dim] = [sin(a_r * f_i), cos(a_r * f_i)], f_i = exp(-ln(1e4) * i / half)
+//   mode 0: a_r = r / max(1, rows - 1)   (continuous_time_embedding of idx/(T-1); _positional_embedding)
+//   mode 1: a_r = args[r]                (timestep_embedding of t)
+// ------------------------------------------------------------------------------------------------
+__global__ void sinusoid_kernel(const float* __restrict__ args, int rows, int dim, int mode, float* __restrict__ out) {
+    const int half = dim / 2;
+    const long long n = static_cast<long long>(rows) * dim;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / dim), c = static_cast<int>(i - static_cast<long long>(r) * dim);
+        float v = 0.0f;
+        if (c < 2 * half) {
+            const int fi = (c < half) ? c : c - half;
+            // freqs = exp(-log(10000) * arange(half) / half): fp32 ops in the reference's order
+            const float freq = expf(__fdiv_rn(__fmul_rn(-logf(10000.0f), static_cast<float>(fi)), static_cast<float>(half)));
+            const float a = (mode == 0) ? __fdiv_rn(static_cast<float>(r), fmaxf(1.0f, static_cast<float>(rows - 1))) : args[r];
+            const float x = __fmul_rn(a, freq);
+            v = (c < half) ? sinf(x) : cosf(x);
+        }
+        out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// token embedding.  h[m, :] = sum_j feat[m, j] * Wf[j, :] + tab[tab_row(m), :] + row_a[b or 0, :] + row_b[b, :]
+//   feat: F small features per token (z_t | known_mask | kp_feat  or  x_s | mask channels), gathered
+//   from up to 3 sources; Wf is the matching column slice of in_proj.weight, transposed to [F, d].
+//   tab: [T, d] table (Stage 1: in_proj(pos sinusoid)[idx]; Stage 2: fixed positional sinusoid[t]).
+//   row_a: timestep / level embedding (row stride 0 when batch-constant), row_b: cond_proj(cond_vec)+bias.
+// ------------------------------------------------------------------------------------------------
+struct EmbedParams {
+    const float* src0; int n0;            // fp32 [M, n0]
+    const float* src1; int n1;            // fp32 [M, n1] or nullptr
+    const unsigned char* src2; int n2;    // uint8 [M, n2] (bool mask) or nullptr
+    const float* Wf;                      // [n0 + n1 + n2, d]
+    const float* tab;                     // [T, d]
+    const long long* tab_idx;             // int64 [M] (Stage 1 idx) or nullptr -> row = m % L
+    const float* row_a; long long row_a_stride;
+    const float* row_b;                   // [B, d]
+    float* h;                             // [M, d]
+    long long M; int L, d;
+};
+
+__global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
+    // one warp per token; lanes stride over d
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int F = p.n0 + p.n1 + p.n2;
+    for (long long m = warp; m < p.M; m += nwarps) {
+        const long long b = m / p.L;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float v = 0.0f;
+            if (j < p.n0) v = p.src0[m * p.n0 + j];
+            else if (j < p.n0 + p.n1) v = p.src1[m * p.n1 + (j - p.n0)];
+            else if (j < F) v = p.src2[m * p.n2 + (j - p.n0 - p.n1)] ? 1.0f : 0.0f;
+            f[j] = v;
+        }
+        const long long trow = p.tab_idx ? p.tab_idx[m] : (m - b * p.L);
+        const float* tab = p.tab + trow * p.d;
+        const float* ra = p.row_a + b * p.row_a_stride;
+        const float* rb = p.row_b + b * p.d;
+        for (int c = lane; c < p.d; c += 32) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < F) acc = fmaf(f[j], __ldg(p.Wf + j * p.d + c), acc);
+            p.h[m * p.d + c] = acc + tab[c] + ra[c] + rb[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (eps = 1e-5, affine) + FiLM: a = LN(h) * (1 + gamma[b]) + beta[b]   (transformer.py:28-41)
+//   one warp per token, row held in registers (d <= 512), two-pass variance like ATen.
+//   gb: [B, gb_stride] fp32 with gamma at [0, d) and beta at [d, 2d) of the layer's slice; nullptr = no FiLM.
+// ------------------------------------------------------------------------------------------------
+template <typename TO, int VPL>
+__global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ h, const float* __restrict__ lnw,
+                                                      const float* __restrict__ lnb, const float* __restrict__ gb,
+                                                      long long gb_stride, TO* __restrict__ out, long long M, int L, int d) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long m = warp; m < M; m += nwarps) {
+        const float4* row = reinterpret_cast<const float4*>(h + m * d);
+        float4 v[VPL];
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 * 4 < d) {
+                v[i] = row[c4];
+                sum += v[i].x + v[i].y + v[i].z + v[i].w;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / static_cast<float>(d);
+        float sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 * 4 < d) {
+                const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                sq += a * a + b2 * b2 + c * c + e * e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq / static_cast<float>(d) + 1e-5f);
+        const float* g = gb ? gb + (m / L) * gb_stride : nullptr;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 * 4 < d) {
+                const float4 w4 = reinterpret_cast<const float4*>(lnw)[c4];
+                const float4 b4 = reinterpret_cast<const float4*>(lnb)[c4];
+                float o0 = (v[i].x - mean) * rstd * w4.x + b4.x;
+                float o1 = (v[i].y - mean) * rstd * w4.y + b4.y;
+                float o2 = (v[i].z - mean) * rstd * w4.z + b4.z;
+                float o3 = (v[i].w - mean) * rstd * w4.w + b4.w;
+                if (g) {
+                    const float4 ga = reinterpret_cast<const float4*>(g)[c4];
+                    const float4 be = reinterpret_cast<const float4*>(g + d)[c4];
+                    o0 = o0 * (1.0f + ga.x) + be.x;
+                    o1 = o1 * (1.0f + ga.y) + be.y;
+                    o2 = o2 * (1.0f + ga.z) + be.z;
+                    o3 = o3 * (1.0f + ga.w) + be.w;
+                }
+                if constexpr (sizeof(TO) == 2) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<unsigned*>(&p0);
+                    pk.y = *reinterpret_cast<unsigned*>(&p1);
+                    reinterpret_cast<uint2*>(out + m * d)[c4] = pk;
+                } else {
+                    reinterpret_cast<float4*>(out + m * d)[c4] = make_float4(o0, o1, o2, o3);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// output head: y[m, j] = h[m, :] . W[j, :] + b[j], j < D (D <= 4): one warp per token
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) out_head_kernel(const float* __restrict__ h, const float* __restrict__ W,
+                                                       const float* __restrict__ bias, float* __restrict__ y, long long M, int d,
+                                                       int D) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long m = warp; m < M; m += nwarps) {
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int c4 = lane; c4 * 4 < d; c4 += 32) {
+            const float4 hv = reinterpret_cast<const float4*>(h + m * d)[c4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < D) {
+                    const float4 wv = reinterpret_cast<const float4*>(W + static_cast<long long>(j) * d)[c4];
+                    acc[j] = fmaf(hv.x, wv.x, fmaf(hv.y, wv.y, fmaf(hv.z, wv.z, fmaf(hv.w, wv.w, acc[j]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        if (lane < D) y[m * D + lane] = acc[lane] + bias[lane];
+    }
+}
+
+static inline int warp_grid(long long rows) { return grid_for(rows, 8, 8); }
+
+}  // namespace idb200
+
+using namespace idb200;
+
+extern "C" int idb200_sgemm(const void* A, int a_is_bf16, int64_t lda, const float* W, const float* bias, float* out,
+                            int64_t ldo, int64_t M, int N, int K, int act, int accumulate, idb200_stream_t stream) {
+    IDB_REQUIRE(M >= 0 && N > 0 && K > 0, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(M == 0 || (A && W && out), IDB200_EINVAL, "NULL pointer");
+    if (M == 0) return IDB200_OK;
+    IDB_REQUIRE((M + 63) / 64 <= 65535 * 32LL, IDB200_EUNSUPPORTED, "M too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // grid.y is limited to 65535: loop over row chunks
+    const long long chunk = 65535LL * 64;
+    for (long long m0 = 0; m0 < M; m0 += chunk) {
+        const long long mm = (M - m0 < chunk) ? M - m0 : chunk;
+        dim3 grid((N + 63) / 64, static_cast<unsigned>((mm + 63) / 64));
+        if (a_is_bf16)
+            sgemm_tn_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(A) + m0 * lda, lda, W, bias,
+                                                                 out + m0 * ldo, ldo, mm, N, K, act, accumulate);
+        else
+            sgemm_tn_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(A) + m0 * lda, lda, W, bias, out + m0 * ldo,
+                                                         ldo, mm, N, K, act, accumulate);
+    }
+    return check_launch("sgemm_tn_kernel");
+}
+
+extern "C" int idb200_conv_encoder(const float* occ, const float* sdf, int64_t B, int H, int W, int n_layers,
+                                   const int* channels /*host [n_layers+1]*/, const float* const* weights /*host*/,
+                                   const float* const* biases /*host*/, float* pooled, idb200_stream_t stream) {
+    IDB_REQUIRE(n_layers >= 1 && n_layers <= 6, IDB200_EUNSUPPORTED, "1..6 conv layers supported");
+    IDB_REQUIRE(B >= 0 && H >= 1 && W >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(channels[0] == 1 || (channels[0] == 2 && sdf), IDB200_EINVAL, "use_sdf is True but sdf missing from cond");
+    if (B == 0) return IDB200_OK;
+    IDB_REQUIRE(occ && pooled, IDB200_EINVAL, "NULL pointer");
+    ConvParams p{};
+    p.occ = occ; p.sdf = sdf; p.n_layers = n_layers; p.H = H; p.W = W; p.B = B; p.pooled = pooled;
+    int cmax = 0;
+    for (int l = 0; l <= n_layers; ++l) { p.ch[l] = channels[l]; cmax = cmax > channels[l] ? cmax : channels[l]; }
+    for (int l = 0; l < n_layers; ++l) { p.w[l] = weights[l]; p.bias[l] = biases[l]; }
+    const size_t smem = 2 * static_cast<size_t>(cmax) * (H + 2) * (W + 2) * sizeof(float);
+    IDB_REQUIRE(smem <= 227 * 1024, IDB200_EUNSUPPORTED, "conv planes need %zu bytes of shared memory (> 227 KB)", smem);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        smem_set = smem;
+    }
+    const int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+    const int grid = grid_for(B, 1, per_sm > 0 ? per_sm : 1);
+    conv_encoder_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("conv_encoder_kernel");
+}
+
+extern "C" int idb200_sinusoid(const float* args, int rows, int dim, int mode, float* out, idb200_stream_t stream) {
+    IDB_REQUIRE(rows >= 0 && dim >= 1 && out, IDB200_EINVAL, "bad arguments");
+    IDB_REQUIRE(mode == 0 || args, IDB200_EINVAL, "args missing");
+    if (rows == 0) return IDB200_OK;
+    sinusoid_kernel<<<grid_for(static_cast<long long>(rows) * dim, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(args, rows, dim, mode, out);
+    return check_launch("sinusoid_kernel");
+}
+
+extern "C" int idb200_embed_tokens(const float* src0, int n0, const float* src1, int n1, const uint8_t* src2, int n2,
+                                   const float* Wf, const float* tab, const int64_t* tab_idx, const float* row_a,
+                                   int64_t row_a_stride, const float* row_b, float* h, int64_t M, int L, int d,
+                                   idb200_stream_t stream) {
+    IDB_REQUIRE(M >= 0 && L >= 1 && d >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(n0 + n1 + n2 <= 16 && n0 >= 0 && n1 >= 0 && n2 >= 0, IDB200_EUNSUPPORTED, "at most 16 token features");
+    if (M == 0) return IDB200_OK;
+    IDB_REQUIRE(src0 && Wf && tab && row_a && row_b && h, IDB200_EINVAL, "NULL pointer");
+    EmbedParams p{src0, n0, src1, n1, src2, n2, Wf, tab, reinterpret_cast<const long long*>(tab_idx), row_a, row_a_stride, row_b, h, M, L, d};
+    embed_kernel<<<warp_grid(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("embed_kernel");
+}
+
+extern "C" int idb200_ln_film(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
+                              int64_t gb_stride, void* out, int out_is_bf16, int64_t M, int L, int d, idb200_stream_t stream) {
+    IDB_REQUIRE(M >= 0 && L >= 1 && d >= 4 && d % 4 == 0 && d <= 512, IDB200_EUNSUPPORTED, "d must be a multiple of 4, <= 512");
+    if (M == 0) return IDB200_OK;
+    IDB_REQUIRE(h && ln_w && ln_b && out, IDB200_EINVAL, "NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = warp_grid(M);
+    if (out_is_bf16) ln_film_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<__nv_bfloat16*>(out), M, L, d);
+    else ln_film_kernel<float, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<float*>(out), M, L, d);
+    return check_launch("ln_film_kernel");
+}
+
+extern "C" int idb200_out_head(const float* h, const float* W, const float* bias, float* y, int64_t M, int d, int D,
+                               idb200_stream_t stream) {
+    IDB_REQUIRE(M >= 0 && d % 4 == 0 && D >= 1 && D <= 4, IDB200_EUNSUPPORTED, "D <= 4 and d % 4 == 0 supported");
+    if (M == 0) return IDB200_OK;
+    IDB_REQUIRE(h && W && bias && y, IDB200_EINVAL, "NULL pointer");
+    out_head_kernel<<<warp_grid(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, W, bias, y, M, d, D);
+    return check_launch("out_head_kernel");
+}

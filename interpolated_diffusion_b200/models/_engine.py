@@ -1,0 +1,192 @@
+"""Host-side orchestration of the denoiser kernels: weight packing (once per parameter version), workspaces
+and the per-layer launch sequence.  All arithmetic happens in libidb200 (tcgen05 token GEMMs, mma.sync /
+SIMT attention, fused LN+FiLM, fp32 SIMT linears for the per-trajectory terms); PyTorch only owns memory."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import _lib as L
+
+EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2, 3
+
+
+def _sig(params) -> Tuple:
+    return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
+
+
+def sgemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None, *, act: int = 0,
+          accumulate: bool = False) -> torch.Tensor:
+    """out[M,N] = act(A[M,K] @ W[N,K]^T + bias) in fp32 (idb200_sgemm).  A may be fp32 or bf16, row-strided."""
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and A.stride(1) == 1 and W.is_contiguous()
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    L.call("idb200_sgemm", A.data_ptr(), int(A.dtype == torch.bfloat16), A.stride(0), W.data_ptr(), L.ptr(bias), out.data_ptr(),
+           out.stride(0), M, N, K, act, int(accumulate), L.stream(A.device))
+    return out
+
+
+def gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, epilogue: int) -> torch.Tensor:
+    M, K = A.shape
+    L.call("idb200_gemm_bf16", A.data_ptr(), W.data_ptr(), L.ptr(bias), out.data_ptr(), M, W.shape[0], K, epilogue,
+           L.stream(A.device))
+    return out
+
+
+def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out = torch.empty((rows, dim), device=device, dtype=torch.float32)
+    L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))
+    return out
+
+
+def ln_film(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], out: torch.Tensor, Lseq: int) -> torch.Tensor:
+    M, d = h.shape
+    L.call("idb200_ln_film", h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), L.ptr(gb), 0 if gb is None else gb.stride(0),
+           out.data_ptr(), int(out.dtype == torch.bfloat16), M, Lseq, d, L.stream(h.device))
+    return out
+
+
+def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, Lseq: int, H: int, causal: bool, force_simt: bool = False):
+    L.call("idb200_attention", qkv.data_ptr(), out.data_ptr(), int(qkv.dtype == torch.bfloat16), B, Lseq, H, int(causal),
+           int(force_simt), L.stream(qkv.device))
+    return out
+
+
+class Workspace:
+    """Grow-only device buffers keyed by name (stable addresses once sized: CUDA-graph friendly)."""
+
+    def __init__(self):
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype, device) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        buf = self.bufs.get(name)
+        if buf is None or buf.numel() < n or buf.dtype != dtype or buf.device != device:
+            buf = torch.empty((max(n, 1),), dtype=dtype, device=device)
+            self.bufs[name] = buf
+        return buf[:n].view(*shape)
+
+
+class PackedEncoder:
+    """bf16 (tensor-core) and fp32 (check-mode) views of a TransformerEncoder's weights + the launch sequence of
+    transformer.py:35-46 / 73-82."""
+
+    def __init__(self, encoder):
+        self.enc = encoder
+        self._key = None
+        self.ws = Workspace()
+
+    def _pack(self):
+        layers = self.enc.layers
+        params = [p for l in layers for p in l.parameters()]
+        key = _sig(params)
+        if key == self._key:
+            return
+        self.layers = []
+        film_w, film_b = [], []
+        for l in layers:
+            d = l.norm1.weight.shape[0]
+            e = {
+                "wqkv32": l.attn.in_proj_weight.detach().float().contiguous(), "bqkv": l.attn.in_proj_bias.detach().float().contiguous(),
+                "wo32": l.attn.out_proj.weight.detach().float().contiguous(), "bo": l.attn.out_proj.bias.detach().float().contiguous(),
+                "w132": l.ff[0].weight.detach().float().contiguous(), "b1": l.ff[0].bias.detach().float().contiguous(),
+                "w232": l.ff[2].weight.detach().float().contiguous(), "b2": l.ff[2].bias.detach().float().contiguous(),
+                "n1w": l.norm1.weight.detach().float().contiguous(), "n1b": l.norm1.bias.detach().float().contiguous(),
+                "n2w": l.norm2.weight.detach().float().contiguous(), "n2b": l.norm2.bias.detach().float().contiguous(),
+            }
+            for k in ("wqkv", "wo", "w1", "w2"):
+                e[k] = e[k + "32"].to(torch.bfloat16).contiguous()
+            self.layers.append(e)
+            if l.film1 is not None:
+                film_w += [l.film1.weight.detach().float(), l.film2.weight.detach().float()]
+                film_b += [l.film1.bias.detach().float(), l.film2.bias.detach().float()]
+        self.has_film = len(film_w) > 0
+        if self.has_film:
+            self.film_w = torch.cat(film_w, dim=0).contiguous()      # [n_layers * 2 * 2d, d_cond]
+            self.film_b = torch.cat(film_b, dim=0).contiguous()
+        self.d = layers[0].norm1.weight.shape[0]
+        self.ff = layers[0].ff[0].weight.shape[0]
+        self.n_heads = layers[0].attn.num_heads
+        self._key = key
+
+    def film_params(self, cond_vec: torch.Tensor) -> Optional[torch.Tensor]:
+        """All layers' FiLM [gamma|beta] in one fp32 GEMM: [B, n_layers*2, 2d] (loop-invariant across DDIM steps)."""
+        self._pack()
+        if not self.has_film or cond_vec is None:
+            return None
+        out = sgemm(cond_vec, self.film_w, self.film_b)
+        return out.view(cond_vec.shape[0], len(self.layers) * 2, 2 * self.d)
+
+    def forward(self, h: torch.Tensor, B: int, Lseq: int, film: Optional[torch.Tensor], precision: str = "bf16") -> torch.Tensor:
+        """In-place on the fp32 residual stream h [B*L, d]."""
+        self._pack()
+        M, d = h.shape
+        dev = h.device
+        H, ff = self.n_heads, self.ff
+        causal = bool(self.enc.causal)
+        if precision == "bf16":
+            a = self.ws.get("a", (M, d), torch.bfloat16, dev)
+            qkv = self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
+            f = self.ws.get("f", (M, ff), torch.bfloat16, dev)
+            for i, e in enumerate(self.layers):
+                g1 = film[:, 2 * i] if film is not None else None
+                g2 = film[:, 2 * i + 1] if film is not None else None
+                ln_film(h, e["n1w"], e["n1b"], g1, a, Lseq)
+                gemm_bf16(a, e["wqkv"], e["bqkv"], qkv, EPI_BF16)
+                attention(qkv, a, B, Lseq, H, causal)                    # `a` is free again: reuse as attention output
+                gemm_bf16(a, e["wo"], e["bo"], h, EPI_RESID_F32)
+                ln_film(h, e["n2w"], e["n2b"], g2, a, Lseq)
+                gemm_bf16(a, e["w1"], e["b1"], f, EPI_SILU_BF16)
+                gemm_bf16(f, e["w2"], e["b2"], h, EPI_RESID_F32)
+        elif precision == "fp32":
+            a = self.ws.get("a32", (M, d), torch.float32, dev)
+            o = self.ws.get("o32", (M, d), torch.float32, dev)
+            qkv = self.ws.get("qkv32", (M, 3 * d), torch.float32, dev)
+            f = self.ws.get("f32", (M, ff), torch.float32, dev)
+            for i, e in enumerate(self.layers):
+                g1 = film[:, 2 * i] if film is not None else None
+                g2 = film[:, 2 * i + 1] if film is not None else None
+                ln_film(h, e["n1w"], e["n1b"], g1, a, Lseq)
+                sgemm(a, e["wqkv32"], e["bqkv"], qkv)
+                attention(qkv, o, B, Lseq, H, causal)
+                sgemm(o, e["wo32"], e["bo"], h, accumulate=True)
+                ln_film(h, e["n2w"], e["n2b"], g2, a, Lseq)
+                sgemm(a, e["w132"], e["b1"], f, act=1)
+                sgemm(f, e["w232"], e["b2"], h, accumulate=True)
+        else:
+            raise ValueError(f"unknown precision {precision!r} (use 'bf16' or 'fp32')")
+        return h
+
+
+def conv_encoder(occ: torch.Tensor, sdf: Optional[torch.Tensor], weights: List[torch.Tensor], biases: List[torch.Tensor]) -> torch.Tensor:
+    B, _, Hh, Ww = occ.shape
+    n = len(weights)
+    chans = [weights[0].shape[1]] + [w.shape[0] for w in weights]
+    ch = (ctypes.c_int * (n + 1))(*chans)
+    wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in weights])
+    bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in biases])
+    pooled = torch.empty((B, chans[-1]), device=occ.device, dtype=torch.float32)
+    L.call("idb200_conv_encoder", occ.data_ptr(), L.ptr(sdf), B, Hh, Ww, n, ch, wp, bp, pooled.data_ptr(), L.stream(occ.device))
+    return pooled
+
+
+def embed_tokens(src0, src1, src2, Wf, tab, tab_idx, row_a, row_b, h, M, Lseq, d):
+    n0 = src0.shape[-1]
+    n1 = 0 if src1 is None else src1.shape[-1]
+    n2 = 0 if src2 is None else src2.shape[-1]
+    stride = 0 if row_a.shape[0] == 1 else row_a.stride(0)
+    L.call("idb200_embed_tokens", src0.data_ptr(), n0, L.ptr(src1), n1, L.ptr(src2), n2, Wf.data_ptr(), tab.data_ptr(),
+           L.ptr(tab_idx), row_a.data_ptr(), stride, row_b.data_ptr(), h.data_ptr(), M, Lseq, d, L.stream(h.device))
+    return h
+
+
+def out_head(h: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    M, d = h.shape
+    L.call("idb200_out_head", h.data_ptr(), W.data_ptr(), bias.data_ptr(), y.data_ptr(), M, d, W.shape[0], L.stream(h.device))
+    return y

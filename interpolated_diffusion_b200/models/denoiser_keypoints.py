@@ -1,0 +1,134 @@
+"""Mirror of the reference's ``src/models/denoiser_keypoints.py``: same constructor, parameter tree and
+``forward(z_t, t, idx, known_mask, cond, T)``; executed by libidb200 (CUDA only, inference / no autograd)."""
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib as L
+from . import _engine as E
+from .encoders import MazeConditionEncoder
+from .transformer import TransformerEncoder
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int) -> torch.Tensor:
+    """denoiser_keypoints.py:11-21 (sinusoid of the integer timestep)."""
+    L.require_cuda(timesteps)
+    emb = E.sinusoid(timesteps.numel(), dim - (dim % 2), timesteps.device, args=timesteps.reshape(-1).float().contiguous())
+    if dim % 2 == 1:
+        emb = F.pad(emb, (0, 1))
+    return emb
+
+
+def continuous_time_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """denoiser_keypoints.py:24-34 (sinusoid of a continuous position in [0,1])."""
+    L.require_cuda(t)
+    emb = E.sinusoid(t.numel(), dim - (dim % 2), t.device, args=t.reshape(-1).float().contiguous()).view(*t.shape, -1)
+    if dim % 2 == 1:
+        emb = F.pad(emb, (0, 1))
+    return emb
+
+
+class KeypointDenoiser(nn.Module):
+    def __init__(self, d_model: int = 256, n_layers: int = 8, n_heads: int = 8, d_ff: int = 1024, dropout: float = 0.0,
+                 d_cond: int = 128, use_sdf: bool = False, use_start_goal: bool = True, data_dim: int = 2,
+                 pos_dim: Optional[int] = None, cond_encoder: Optional[nn.Module] = None, use_checkpoint: bool = False,
+                 kp_feat_dim: int = 0, maze_channels: tuple = (32, 64)):
+        super().__init__()
+        self.data_dim = data_dim
+        self.d_cond = d_cond
+        self.kp_feat_dim = kp_feat_dim
+        if pos_dim is None:
+            pos_dim = d_model // 2
+        self.pos_dim = pos_dim
+        self.in_proj = nn.Linear(data_dim + pos_dim + data_dim + kp_feat_dim, d_model)
+        self.t_embed = nn.Sequential(nn.Linear(d_model, d_model), nn.SiLU(), nn.Linear(d_model, d_model))
+        if cond_encoder is None:
+            cond_encoder = MazeConditionEncoder(use_sdf=use_sdf, d_cond=d_cond, use_start_goal=use_start_goal,
+                                                maze_channels=maze_channels)
+        self.cond_enc = cond_encoder
+        self.cond_proj = nn.Linear(d_cond, d_model)
+        self.transformer = TransformerEncoder(d_model=d_model, n_layers=n_layers, n_heads=n_heads, d_ff=d_ff, dropout=dropout,
+                                              cond_dim=d_cond, causal=False, use_checkpoint=use_checkpoint)
+        self.out = nn.Linear(d_model, data_dim)
+        self.precision = "bf16"          # "fp32" = check mode (SIMT fp32 GEMMs / attention)
+        self._cache = {}
+        self._ws = E.Workspace()
+
+    # ---- packed / derived tensors -------------------------------------------------------------
+    def _derived(self, T: int, device):
+        """in_proj split by feature group + the [T, d] table in_proj(pos sinusoid(t/(T-1))) (idx takes T values)."""
+        key = (T, E._sig([self.in_proj.weight, self.in_proj.bias, self.cond_proj.bias]))
+        hit = self._cache.get("derived")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        D, P, Fk = self.data_dim, self.pos_dim, self.kp_feat_dim
+        W = self.in_proj.weight.detach().float()
+        # kernel feature order: [z_t | kp_feat | known_mask]
+        Wf = torch.cat([W[:, :D], W[:, 2 * D + P:], W[:, D + P: 2 * D + P]], dim=1).t().contiguous()
+        pos_tab = E.sinusoid(T, P - (P % 2), device)                         # a = r / max(1, T-1)
+        W_pos = W[:, D: D + P - (P % 2)].contiguous()
+        tab = E.sgemm(pos_tab, W_pos, None)                                  # [T, d]
+        bias_b = (self.cond_proj.bias.detach().float() + self.in_proj.bias.detach().float()).contiguous()
+        val = {"Wf": Wf, "tab": tab, "bias_b": bias_b}
+        self._cache["derived"] = (key, val)
+        return val
+
+    @torch.no_grad()
+    def encode_cond(self, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """cond_vec [B, d_cond]: loop-invariant across DDIM steps (the reference recomputes it per step, :107)."""
+        return self.cond_enc(cond)
+
+    @torch.no_grad()
+    def timestep_vector(self, t: torch.Tensor) -> torch.Tensor:
+        """t_embed(timestep_embedding(t, d)) -> [len(t), d] (denoiser_keypoints.py:104-105)."""
+        d = self.in_proj.weight.shape[0]
+        emb = timestep_embedding(t, d)
+        hdn = E.sgemm(emb, self.t_embed[0].weight.detach().float().contiguous(), self.t_embed[0].bias.detach().float().contiguous(), act=1)
+        return E.sgemm(hdn, self.t_embed[2].weight.detach().float().contiguous(), self.t_embed[2].bias.detach().float().contiguous())
+
+    @torch.no_grad()
+    def forward(self, z_t: torch.Tensor, t: torch.Tensor, idx: torch.Tensor, known_mask: torch.Tensor,
+                cond: Dict[str, torch.Tensor], T: int, *, cond_vec: Optional[torch.Tensor] = None,
+                film: Optional[torch.Tensor] = None, t_vec: Optional[torch.Tensor] = None,
+                row_b: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """denoiser_keypoints.py:82-113 -> eps [B, K, D].  Keyword extras let a sampler hoist the loop-invariant
+        pieces (cond_vec, FiLM parameters, cond_proj row, per-step timestep vector) out of the DDIM loop."""
+        dev = L.require_cuda(z_t, t, idx, known_mask)
+        B, K, D = z_t.shape
+        d = self.in_proj.weight.shape[0]
+        der = self._derived(T, dev)
+        z = L.f32c(z_t)
+        km = L.u8c(known_mask)
+        kp_feat = None
+        if self.kp_feat_dim > 0:
+            if cond is not None and "kp_feat" in cond:
+                kp_feat = L.f32c(cond["kp_feat"])
+                if kp_feat.shape[:2] != (B, K):
+                    raise ValueError("kp_feat must have shape [B,K,F]")
+                if kp_feat.shape[-1] != self.kp_feat_dim:
+                    raise ValueError("kp_feat_dim mismatch")
+            else:
+                kp_feat = torch.zeros((B, K, self.kp_feat_dim), device=dev, dtype=torch.float32)
+        if cond_vec is None:
+            if cond and self.cond_enc is not None:
+                cond_vec = self.cond_enc(cond)
+            else:
+                cond_vec = torch.zeros((B, self.d_cond), device=dev, dtype=torch.float32)
+        if row_b is None:
+            row_b = E.sgemm(cond_vec, self.cond_proj.weight.detach().float().contiguous(), der["bias_b"])
+        if t_vec is None:
+            t_vec = self.timestep_vector(L.i64c(t))
+        pk = self.transformer.packed()
+        if film is None:
+            film = pk.film_params(cond_vec)
+        M = B * K
+        h = self._ws.get("h", (M, d), torch.float32, dev)
+        E.embed_tokens(z.view(M, D), None if kp_feat is None else kp_feat.view(M, -1), km.view(M, D), der["Wf"], der["tab"],
+                       L.i64c(idx).view(M), t_vec, row_b, h, M, K, d)
+        pk.forward(h, B, K, film, self.precision)
+        if out is None:
+            out = torch.empty((B, K, D), device=dev, dtype=torch.float32)
+        E.out_head(h, self.out.weight.detach().float().contiguous(), self.out.bias.detach().float().contiguous(), out.view(M, D))
+        return out

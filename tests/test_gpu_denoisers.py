@@ -1,0 +1,174 @@
+"""GPU parity of the denoiser path (conv encoder, embeddings, LN+FiLM, tcgen05 GEMMs, attention, output head)
+against the CPU oracle on identical weights and inputs, and against the golden outputs of the live reference.
+
+Tolerances (BASELINE.json north_star): bf16 path <= 2e-2 max-abs on eps / delta (O(1) outputs), fp32 check
+mode <= 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser_torch as odn
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(d_model=64, n_layers=2, n_heads=2, d_ff=128, d_cond=32, maze_channels=(8, 16))
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def _maxabs(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item()
+
+
+def test_attention_kernels_vs_torch():
+    from interpolated_diffusion_b200.models import _engine as E
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (B, L, H, causal) in [(5, 8, 8, False), (3, 64, 8, False), (2, 64, 8, True), (2, 256, 4, True), (3, 16, 2, False),
+                              (2, 32, 4, True), (7, 8, 2, True), (1, 256, 8, False), (2, 128, 2, False), (3, 5, 2, False)]:
+        d = H * 32
+        qkv = torch.randn((B * L, 3 * d), generator=g, device="cuda")
+        q, k, v = [t.view(B, L, H, 32).transpose(1, 2) for t in qkv.split(d, dim=-1)]
+        ref32 = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B * L, d)
+        out32 = E.attention(qkv, torch.empty((B * L, d), device="cuda"), B, L, H, causal)
+        assert _maxabs(out32, ref32) < 2e-5, (B, L, H, causal)
+        qb = qkv.bfloat16()
+        qf, kf, vf = [t.float().view(B, L, H, 32).transpose(1, 2) for t in qb.split(d, dim=-1)]
+        refb = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, is_causal=causal).transpose(1, 2).reshape(B * L, d)
+        outb = E.attention(qb, torch.empty((B * L, d), device="cuda", dtype=torch.bfloat16), B, L, H, causal)
+        assert _maxabs(outb, refb) < 2.5e-2, (B, L, H, causal, "mma" if L % 16 == 0 else "simt")
+        outs = E.attention(qb, torch.empty((B * L, d), device="cuda", dtype=torch.bfloat16), B, L, H, causal, force_simt=True)
+        assert _maxabs(outs, refb) < 1e-2, (B, L, H, causal, "simt-bf16")
+
+
+def test_small_kernels_vs_torch():
+    from interpolated_diffusion_b200.models import _engine as E
+    g = torch.Generator(device="cuda").manual_seed(1)
+    # sgemm
+    for (M, N, K) in [(100, 70, 33), (1, 256, 128), (513, 512, 4), (64, 64, 256)]:
+        A = torch.randn((M, K), generator=g, device="cuda")
+        W = torch.randn((N, K), generator=g, device="cuda")
+        b = torch.randn((N,), generator=g, device="cuda")
+        ref = A.double() @ W.double().t() + b.double()
+        assert _maxabs(E.sgemm(A, W, b), ref.float()) < 1e-4
+        assert _maxabs(E.sgemm(A, W, b, act=1), torch.nn.functional.silu(ref).float()) < 1e-4
+        o = torch.ones((M, N), device="cuda")
+        assert _maxabs(E.sgemm(A, W, None, o, accumulate=True), (A.double() @ W.double().t() + 1).float()) < 1e-4
+    # LN + FiLM
+    for d in (64, 256, 384):
+        M, Lq = 77 * 8, 8
+        h = torch.randn((M, d), generator=g, device="cuda") * 3 + 1
+        w, b = torch.randn((d,), generator=g, device="cuda"), torch.randn((d,), generator=g, device="cuda")
+        gb = torch.randn((M // Lq, 2 * d), generator=g, device="cuda")
+        ref = torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)
+        ref = (ref.view(-1, Lq, d) * (1 + gb[:, None, :d]) + gb[:, None, d:]).view(M, d)
+        assert _maxabs(E.ln_film(h, w, b, gb, torch.empty_like(h), Lq), ref) < 2e-5
+        ob = E.ln_film(h, w, b, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq)
+        assert _maxabs(ob, ref) < 0.05 and _maxabs(ob, ref.bfloat16()) < 0.07
+        assert _maxabs(E.ln_film(h, w, b, None, torch.empty_like(h), Lq), torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)) < 2e-5
+    # conv encoder
+    for (chans, H, W) in [((1, 32, 64), 21, 21), ((2, 8, 16), 9, 12), ((1, 32, 64, 128, 128), 21, 21)]:
+        B = 5
+        x = (torch.rand((B, chans[0], H, W), generator=g, device="cuda") < 0.3).float()
+        ws = [torch.randn((chans[i + 1], chans[i], 3, 3), generator=g, device="cuda") * (chans[i] * 9) ** -0.5 for i in range(len(chans) - 1)]
+        bs = [torch.randn((c,), generator=g, device="cuda") * 0.1 for c in chans[1:]]
+        ref = x
+        for w_, b_ in zip(ws, bs):
+            ref = torch.nn.functional.silu(torch.nn.functional.conv2d(ref, w_, b_, padding=1))
+        ref = ref.mean(dim=[2, 3])
+        got = E.conv_encoder(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if chans[0] == 2 else None, ws, bs)
+        assert _maxabs(got, ref) < 2e-5, chans
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_denoisers_tiny_golden(golden, precision, tol):
+    """Outputs of the LIVE reference on the tiny random-init models (tests/golden/models_tiny.npz)."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_interp_levels_causal import InterpLevelCausalDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    g = golden("models_tiny")
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    cond = {"occ": t("kp2_occ"), "start_goal": t("kp2_sg")}
+    m = KeypointDenoiser(data_dim=2, **TINY).cuda()
+    m.load_state_dict(_sd(g, "kp2/"))
+    m.precision = precision
+    assert _maxabs(m.cond_enc(cond), torch.from_numpy(g["kp2_condvec"])) < 1e-5
+    eps = m(t("kp2_z"), t("kp2_t"), t("kp2_idx"), t("kp2_km"), cond, 16)
+    assert _maxabs(eps, torch.from_numpy(g["kp2_eps"])) < tol
+    m4 = KeypointDenoiser(data_dim=4, kp_feat_dim=3, use_sdf=True, **TINY).cuda()
+    m4.load_state_dict(_sd(g, "kp4/"))
+    m4.precision = precision
+    cond4 = {"occ": t("kp4_occ"), "start_goal": t("kp4_sg"), "sdf": t("kp4_sdf"), "kp_feat": t("kp4_kpfeat")}
+    eps = m4(t("kp4_z"), t("kp2_t"), t("kp2_idx"), t("kp4_km"), cond4, 16)
+    assert _maxabs(eps, torch.from_numpy(g["kp4_eps"])) < tol
+    for tag, cls, C, D in (("il2", InterpLevelDenoiser, 2, 2), ("il3", InterpLevelDenoiser, 3, 4), ("ic1", InterpLevelCausalDenoiser, 1, 2)):
+        mi = cls(data_dim=D, max_levels=3, mask_channels=C, **TINY).cuda()
+        mi.load_state_dict(_sd(g, tag + "/"))
+        mi.precision = precision
+        out = mi(t(f"{tag}_x"), t(f"{tag}_s"), t(f"{tag}_mask"), cond)
+        assert _maxabs(out, torch.from_numpy(g[f"{tag}_out"])) < tol, tag
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_denoisers_full_size_vs_oracle(precision, tol):
+    """BASELINE small model (d=256, 8 layers, 8 heads, ff 1024, maze 32-64), random init: Stage-1 (K=8) and
+    Stage-2 (T=64) single evaluations on identical inputs (ladder L2 of SURVEY 7.3-1)."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    B, T, K, D = 24, 64, 8, 2
+    gen = torch.Generator().manual_seed(5)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=D)
+    il = InterpLevelDenoiser(data_dim=D, max_levels=3, mask_channels=2)
+    sd_kp = {k: v.clone() for k, v in kp.state_dict().items()}
+    sd_il = {k: v.clone() for k, v in il.state_dict().items()}
+    kp, il = kp.cuda(), il.cuda()
+    kp.precision = il.precision = precision
+    idx = torch.tensor([0, 9, 18, 27, 36, 45, 54, 63]).repeat(B, 1)
+    z = torch.randn((B, K, D), generator=gen)
+    km = torch.zeros((B, K, D), dtype=torch.bool)
+    km[:, 0] = km[:, -1] = True
+    for tval in (999, 500, 2):
+        t = torch.full((B,), tval, dtype=torch.long)
+        ref = odn.keypoint_denoiser(sd_kp, 8, z, t, idx, km, cond, T)
+        got = kp(z.cuda(), t.cuda(), idx.cuda(), km.cuda(), _cuda(cond), T)
+        assert _maxabs(got, ref) < tol, (tval, _maxabs(got, ref))
+    x = torch.rand((B, T, D), generator=gen)
+    mask_in = torch.rand((B, T, 2), generator=gen)
+    s = torch.full((B,), 3, dtype=torch.long)
+    ref = odn.interp_level_denoiser(sd_il, 8, x, s, mask_in, cond)
+    got = il(x.cuda(), s.cuda(), mask_in.cuda(), _cuda(cond))
+    assert _maxabs(got, ref) < tol, _maxabs(got, ref)
+    # hoisted loop-invariants give the same result as the plain call
+    cv = il.encode_cond(_cuda(cond))
+    got2 = il(x.cuda(), s.cuda(), mask_in.cuda(), None, cond_vec=cv, film=il.transformer.packed().film_params(cv),
+              level_vec=il.level_vector(torch.tensor([3]).cuda()))
+    assert _maxabs(got2, got) < 1e-6
+
+
+def test_causal_long_horizon_vs_oracle():
+    """BASELINE config 5 shape: T=256 causal Stage-2 denoiser (small model), bf16 path."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels_causal import InterpLevelCausalDenoiser
+    B, T, D = 3, 256, 2
+    gen = torch.Generator().manual_seed(6)
+    cond = {"occ": (torch.rand((B, 1, 9, 12), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    torch.manual_seed(1)
+    m = InterpLevelCausalDenoiser(data_dim=D, max_levels=4, mask_channels=1)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    x = torch.rand((B, T, D), generator=gen)
+    mask = torch.rand((B, T), generator=gen) < 0.2
+    s = torch.tensor([4, 2, 1])
+    ref = odn.interp_level_denoiser(sd, 8, x, s, mask, cond, causal=True)
+    got = m(x.cuda(), s.cuda(), mask.cuda(), _cuda(cond))
+    assert _maxabs(got, ref) < 2e-2, _maxabs(got, ref)
+    m.precision = "fp32"
+    got = m(x.cuda(), s.cuda(), mask.cuda(), _cuda(cond))
+    assert _maxabs(got, ref) < 1e-4, _maxabs(got, ref)
