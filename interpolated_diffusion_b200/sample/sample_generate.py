@@ -152,3 +152,196 @@ def _sample_keypoints_ddim(model, schedule, idx: torch.Tensor, known_mask: torch
     if return_intermediates:
         return z, intermediates
     return z
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The batched generation hot loop (sample_generate.py:974-1285; exact recipe in SURVEY.md 3.5).
+# ------------------------------------------------------------------------------------------------------------
+class GenerationConfig:
+    """The hot-path flags of the reference CLI (sample_generate.py:38-155) with the reference defaults."""
+
+    def __init__(self, T: int = 64, K_min: int = 8, levels: int = 3, data_dim: int = 2, ddim_steps: int = 20,
+                 ddim_schedule: str = "quadratic", n_train: int = 1000, beta_schedule: str = "cosine", stage2_mode: str = "x0",
+                 clamp_policy: str = "endpoints", clamp_dims: str = "pos", logit_space: bool = True, logit_eps: float = 1e-5,
+                 anchor_conf: bool = True, anchor_conf_teacher: float = 0.95, anchor_conf_student: float = 0.5,
+                 anchor_conf_endpoints: float = 1.0, anchor_conf_missing: float = 0.0, anchor_conf_anneal_mode: str = "linear",
+                 soft_anchor_clamp: bool = True, soft_clamp_schedule: str = "linear", soft_clamp_max: float = 1.0,
+                 recompute_vel: bool = True, clamp_endpoints: bool = True, pos_clip: bool = False, pos_clip_min: float = 0.0,
+                 pos_clip_max: float = 1.0, kp_index_mode: str = "uniform", k_schedule: str = "doubling"):
+        if clamp_policy not in ("none", "endpoints", "all_anchors"):
+            raise ValueError(f"Unknown clamp_policy: {clamp_policy}")
+        if clamp_dims not in ("pos", "all"):
+            raise ValueError(f"Unknown clamp_dims: {clamp_dims}")
+        if stage2_mode not in ("x0", "adj"):
+            raise ValueError(f"Unknown stage2_mode: {stage2_mode}")
+        self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
+
+
+def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optional[GenerationConfig] = None, *,
+             z_T: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None, masks_levels: Optional[torch.Tensor] = None,
+             generator: Optional[torch.Generator] = None, return_all: bool = False, out: Optional[torch.Tensor] = None):
+    """Stage-1 DDIM over K keypoints -> sigmoid -> Interp to T -> Stage-2 (one-step ``x0`` jump or ``adj`` chain)
+    -> soft / hard clamp by ``clamp_policy``.  Everything runs on the current CUDA stream without host syncs, so
+    the whole call is CUDA-graph capturable (see :class:`GenerationGraph`).
+
+    Loop-invariant work the reference repeats every step is hoisted: the conv conditioning encoder, FiLM
+    parameters and cond_proj run once per model, and the per-step timestep vectors are one batched product."""
+    from ..corruptions import keyframes as kf
+    from ..utils.clamp import stage2_epilogue
+    from ..utils.normalize import sigmoid_pos
+
+    cfg = cfg or GenerationConfig()
+    sg = cond["start_goal"]
+    dev = L.require_cuda(sg, cond["occ"])
+    B = sg.shape[0]
+    T, K, S, D = cfg.T, cfg.K_min, cfg.levels, cfg.data_dim
+    # 1. anchors
+    if idx is None:
+        if cfg.kp_index_mode == "uniform":
+            idx, masks = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device=dev)
+        elif cfg.kp_index_mode == "random":
+            idx, masks = kf.sample_fixed_k_indices_batch(B, T, K, generator=generator, device=dev)
+        else:
+            raise ValueError(f"kp_index_mode={cfg.kp_index_mode!r} needs explicit idx= (selector models are out of scope)")
+    else:
+        masks = torch.zeros((B, T), device=dev, dtype=torch.bool)
+        masks.scatter_(1, idx, True)
+    K = idx.shape[1]
+    # 2. known endpoints (logit space)
+    known_mask, known_values = _build_known_mask_values(idx, cond, D, T, cfg.clamp_endpoints, logit_space=cfg.logit_space,
+                                                        logit_eps=cfg.logit_eps)
+    # 3. initial noise
+    z = torch.randn((B, K, D), device=dev) if z_T is None else L.f32c(z_T).clone()
+    z = torch.where(known_mask, known_values, z)
+    clip1 = bool(cfg.pos_clip) and not bool(cfg.logit_space)
+    if clip1:
+        z[..., :2] = z[..., :2].clamp(min=cfg.pos_clip_min, max=cfg.pos_clip_max)
+    # 4. Stage-1 DDIM
+    sched = _schedule_cache(cfg.beta_schedule, cfg.n_train)
+    times = _timesteps(cfg.n_train, cfg.ddim_steps, schedule=cfg.ddim_schedule).tolist()
+    ab = sched["alpha_bar_host"]
+    cond_vec = kp_model.encode_cond(cond)
+    pk = kp_model.transformer.packed()
+    film = pk.film_params(cond_vec)
+    row_b = _cond_row(kp_model, cond_vec, T, dev)
+    t_vecs = kp_model.timestep_vector(torch.tensor(times[:-1], device=dev, dtype=torch.long)) if len(times) > 1 else None
+    eps = torch.empty((B, K, D), device=dev, dtype=torch.float32)
+    for i in range(len(times) - 1):
+        kp_model(z, None, idx, known_mask, None, T, cond_vec=cond_vec, film=film, t_vec=t_vecs[i:i + 1], row_b=row_b, out=eps)
+        ddim_step_scalar(z, eps, float(ab[times[i]]), float(ab[times[i + 1]]), known_mask=known_mask, known_values=known_values,
+                         pos_clip=clip1, pos_clip_min=cfg.pos_clip_min, pos_clip_max=cfg.pos_clip_max, out=z)
+    # 5-6. back to position space, interpolate to T
+    z_pred = sigmoid_pos(z) if cfg.logit_space else z
+    x_pred = kf.interpolate_from_indices(idx, z_pred, T, recompute_velocity=bool(cfg.recompute_vel))
+    # 7-10. Stage 2
+    cond_vec2 = interp_model.encode_cond(cond)
+    pk2 = interp_model.transformer.packed()
+    film2 = pk2.film_params(cond_vec2)
+    row_b2 = _cond_row(interp_model, cond_vec2, T, dev)
+    ac = dict(conf_teacher=cfg.anchor_conf_teacher, conf_student=cfg.anchor_conf_student,
+              conf_endpoints=cfg.anchor_conf_endpoints, conf_missing=cfg.anchor_conf_missing,
+              clamp_endpoints=cfg.clamp_endpoints)
+    x_hat = out if out is not None else torch.empty((B, T, D), device=dev, dtype=torch.float32)
+    if cfg.stage2_mode == "x0":
+        level_vec = interp_model.level_vector(torch.tensor([S], device=dev, dtype=torch.long))
+        conf_pred = None
+        if cfg.anchor_conf:
+            # conf_pred (student == mask) and the annealed copy fed to the model; anneal at s == S is the identity
+            conf_pred, _ = anchor_conf_mask_in(masks, masks, None, S, S, "none", **ac)
+            _, mask_in = anchor_conf_mask_in(masks, masks, None, S, S, cfg.anchor_conf_anneal_mode, want_conf=False, channels=2, **ac)
+        else:
+            mask_in = masks
+        delta = interp_model(x_pred, None, mask_in, None, cond_vec=cond_vec2, film=film2, level_vec=level_vec, row_b=row_b2)
+        lam = _soft_clamp_lambda(S, S, cfg.soft_clamp_schedule, cfg.soft_clamp_max) if (cfg.soft_anchor_clamp and conf_pred is not None) else 0.0
+        stage2_epilogue(x_pred, delta, x_pred, conf_pred if lam > 0.0 else None, lam, cfg.clamp_policy, masks, cfg.clamp_dims, out=x_hat)
+    else:
+        if masks_levels is None:
+            masks_levels, _ = kf.build_nested_masks_from_base(idx, T, S, generator=generator, k_schedule=cfg.k_schedule)
+        level_vecs = interp_model.level_vector(torch.arange(0, S + 1, device=dev, dtype=torch.long))
+        x_curr = x_pred
+        for s in range(S, 0, -1):
+            m_s, m_prev = masks_levels[:, s].contiguous(), masks_levels[:, s - 1].contiguous()
+            if cfg.anchor_conf:
+                conf_s, mask_in = anchor_conf_mask_in(m_s, None, m_prev, s, S, cfg.anchor_conf_anneal_mode, channels=3, **ac)
+            else:
+                conf_s, mask_in = None, torch.stack([m_s, m_prev], dim=-1)
+            delta = interp_model(x_curr, None, mask_in, None, cond_vec=cond_vec2, film=film2, level_vec=level_vecs[s:s + 1], row_b=row_b2)
+            lam = _soft_clamp_lambda(s, S, cfg.soft_clamp_schedule, cfg.soft_clamp_max) if (cfg.soft_anchor_clamp and conf_s is not None) else 0.0
+            tgt = x_hat if s == 1 else torch.empty_like(x_pred)
+            x_curr = stage2_epilogue(x_curr, delta, x_pred, conf_s if lam > 0.0 else None, lam, cfg.clamp_policy, m_s, cfg.clamp_dims,
+                                     pos_clip=cfg.pos_clip, pos_clip_min=cfg.pos_clip_min, pos_clip_max=cfg.pos_clip_max, out=tgt)
+    if return_all:
+        return {"x_hat": x_hat, "x_pred": x_pred, "z": z, "z_pred": z_pred, "idx": idx, "masks": masks}
+    return x_hat
+
+
+_SCHEDULES: Dict = {}
+
+
+def _schedule_cache(name: str, n_train: int):
+    from ..diffusion.schedules import make_alpha_bars, make_beta_schedule
+    key = (name, n_train)
+    if key not in _SCHEDULES:
+        sch = make_alpha_bars(make_beta_schedule(name, n_train))
+        sch["alpha_bar_host"] = sch["alpha_bar"].to(torch.float32).numpy()
+        _SCHEDULES[key] = sch
+    return _SCHEDULES[key]
+
+
+def _cond_row(model, cond_vec: torch.Tensor, T: int, dev) -> torch.Tensor:
+    from ..models import _engine as E
+    der = model._derived(T, dev)
+    return E.sgemm(cond_vec, model.cond_proj.weight.detach().float().contiguous(), der["bias_b"])
+
+
+class GenerationGraph:
+    """The whole generation call captured once as a single CUDA graph for a fixed batch shape (19 Stage-1
+    evaluations + DDIM updates, sigmoid, interpolation, Stage-2, clamp: ~600 kernel launches replayed with one
+    host call).  Inputs are copied into static buffers, ``run`` replays the graph and returns the static output."""
+
+    def __init__(self, kp_model, interp_model, B: int, cfg: Optional[GenerationConfig] = None, *, occ_shape=(1, 21, 21),
+                 use_sdf: bool = False, device=None):
+        self.cfg = cfg or GenerationConfig()
+        self.kp, self.il = kp_model, interp_model
+        dev = L.resolve_device(device)
+        self.dev = dev
+        K, D, T = self.cfg.K_min, self.cfg.data_dim, self.cfg.T
+        self.cond = {"occ": torch.zeros((B,) + tuple(occ_shape), device=dev), "start_goal": torch.full((B, 4), 0.5, device=dev)}
+        if use_sdf:
+            self.cond["sdf"] = torch.zeros((B,) + tuple(occ_shape), device=dev)
+        self.z_T = torch.zeros((B, K, D), device=dev)
+        self.x_hat = torch.empty((B, T, D), device=dev)
+        self.masks_levels = None
+        if self.cfg.stage2_mode == "adj":
+            from ..corruptions import keyframes as kf
+            idx, _ = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device=dev)
+            self.masks_levels, _ = kf.build_nested_masks_from_base(idx, T, self.cfg.levels)
+        self.graph = None
+        self.launches = 0
+
+    def _body(self):
+        generate(self.kp, self.il, self.cond, self.cfg, z_T=self.z_T, masks_levels=self.masks_levels, out=self.x_hat)
+
+    def capture(self):
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):                     # warm-up: packs weights, sizes workspaces, sets kernel attributes
+                self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        return self
+
+    def run(self, cond: Optional[Dict[str, torch.Tensor]] = None, z_T: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.graph is None:
+            self.capture()
+        if cond is not None:
+            for k, buf in self.cond.items():
+                buf.copy_(cond[k], non_blocking=True)
+        if z_T is not None:
+            self.z_T.copy_(z_T, non_blocking=True)
+        self.graph.replay()
+        return self.x_hat

@@ -69,7 +69,7 @@ def test_small_kernels_vs_torch():
         ref = (ref.view(-1, Lq, d) * (1 + gb[:, None, :d]) + gb[:, None, d:]).view(M, d)
         assert _maxabs(E.ln_film(h, w, b, gb, torch.empty_like(h), Lq), ref) < 2e-5
         ob = E.ln_film(h, w, b, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq)
-        assert _maxabs(ob, ref) < 0.05 and _maxabs(ob, ref.bfloat16()) < 0.07
+        assert ((ob.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-6).all()      # one bf16 rounding
         assert _maxabs(E.ln_film(h, w, b, None, torch.empty_like(h), Lq), torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)) < 2e-5
     # conv encoder
     for (chans, H, W) in [((1, 32, 64), 21, 21), ((2, 8, 16), 9, 12), ((1, 32, 64, 128, 128), 21, 21)]:
