@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the generation hot path (BASELINE.json: end-to-end trajectories/sec, DDIM-20 + interp + Stage-2).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+One "step" = one batch of synthetic particle-maze conditioning through the whole path: Stage-1 K=8 keypoint DDIM
+(20 timesteps = 19 denoiser evaluations), sigmoid, piecewise-linear interpolation to T=64, Stage-2 one-step jump,
+soft + hard clamp (clamp_policy=endpoints) -- BASELINE.json configs[2], B = 65536 trajectories per GPU, small
+random-init models (d=256, 8 layers, 8 heads, ff 1024, maze 32-64).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "end-to-end trajectories/sec (DDIM20+interp+stage2)"
+UNIT = "trajectories/s"
+T, K_MIN, LEVELS, D = 64, 8, 3, 2
+# algorithmic FLOPs per trajectory (small model): 19 Stage-1 evals + 1 Stage-2 eval + conv encoders
+D_MODEL, N_LAYERS, D_FF, D_COND = 256, 8, 1024, 128
+
+
+def gemm_flops_per_traj() -> float:
+    per_tok_layer = 2 * D_MODEL * 3 * D_MODEL + 2 * D_MODEL * D_MODEL + 4 * D_MODEL * D_FF      # QKV + out + MLP
+    return float(N_LAYERS * per_tok_layer * (19 * K_MIN + T))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p.get("hbm_gbs", 6650.0), "bf16": p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0)), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def synthetic_cond(B: int, seed: int, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    occ = (torch.rand((B, 1, 21, 21), generator=g) < 0.2).float()
+    sg = torch.rand((B, 4), generator=g)
+    if pin:
+        occ, sg = occ.pin_memory(), sg.pin_memory()
+    return {"occ": occ.to(device), "start_goal": sg.to(device)}
+
+
+def build_models(device):
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=D)
+    il = InterpLevelDenoiser(data_dim=D, max_levels=LEVELS, mask_channels=2)
+    return kp.to(device), il.to(device)
+
+
+def cpu_reference_rate(sample_B: int, steps: int = 1, warmup: int = 0):
+    """The reference algorithm (oracle port of sample_generate.py:974-1285) on the host cores."""
+    import numpy as np
+    from oracle import generate as og
+    torch.manual_seed(0)
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    kp = KeypointDenoiser(data_dim=D)
+    il = InterpLevelDenoiser(data_dim=D, max_levels=LEVELS, mask_channels=2)
+    sd_kp = {k: v.detach() for k, v in kp.state_dict().items()}
+    sd_il = {k: v.detach() for k, v in il.state_dict().items()}
+    cond = synthetic_cond(sample_B, 0)
+    rng = np.random.default_rng(0)
+    z_T = rng.standard_normal((sample_B, K_MIN, D)).astype(np.float32)
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            og.generate(sd_kp, sd_il, 8, cond, z_T, T=T, K_min=K_MIN, levels=LEVELS, D=D)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return sample_B / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_B = args.ref_batch
+    rate, dt, cores = cpu_reference_rate(sample_B, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "generation: Stage-1 DDIM-20 K=8 + interp T=64 + Stage-2 one-step, small model, clamp_policy=endpoints",
+                   "sample": f"{sample_B} trajectories per step (bounded CPU sample of the same workload)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{sample_B} trajectories/step x {args.steps} steps"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from interpolated_diffusion_b200 import _lib as L
+    from interpolated_diffusion_b200.models import _engine as E
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph
+
+    B = args.batch
+    cfg = GenerationConfig(T=T, K_min=K_MIN, levels=LEVELS, data_dim=D)
+    kp, il = build_models(dev)
+    graph = GenerationGraph(kp, il, B, cfg, device=dev)
+    # count this library's kernel launches in one step (every L.call enqueues exactly one kernel here)
+    calls = [0]
+    orig_call = L.call
+
+    def counting_call(name, *a):
+        calls[0] += 1
+        return orig_call(name, *a)
+
+    L.call = counting_call
+    graph._body()
+    L.call = orig_call
+    launches_per_step = calls[0]
+    graph.capture()
+
+    host = synthetic_cond(B, 1000 + rank, pin=True)
+    host_out = torch.empty((B, T, D), dtype=torch.float32).pin_memory()
+    dcond = {k: v.to(dev) for k, v in host.items()}
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gathered = torch.empty((world * B, T, D), device=dev) if world > 1 else None
+
+    def step_device():
+        z_T = torch.randn((B, K_MIN, D), generator=gen, device=dev)
+        x = graph.run(dcond, z_T)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x)
+        return x
+
+    def step_e2e():
+        z_T = torch.randn((B, K_MIN, D), generator=gen, device=dev)
+        x = graph.run(host, z_T)                      # H2D of occ + start_goal from pinned memory inside the step
+        host_out.copy_(x, non_blocking=True)          # D2H of the samples
+        return x
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), clocks
+
+    ms_dev, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=(rank == 0))
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup // 2, 1))
+
+    # roofline of the dominant kernel (tcgen05 token GEMM): one instrumented eager step, CUDA events on the launching stream
+    roof = None
+    if rank == 0:
+        evs = []
+        orig = E.gemm_bf16
+
+        def timed_gemm(A, W, bias, out, epi):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig(A, W, bias, out, epi)
+            b.record()
+            evs.append((a, b, 2.0 * A.shape[0] * W.shape[0] * A.shape[1]))
+            return r
+
+        E.gemm_bf16 = timed_gemm
+        graph._body()
+        torch.cuda.synchronize(dev)
+        E.gemm_bf16 = orig
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+        flops = sum(f for _, _, f in evs)
+        pk = peaks()
+        achieved = flops / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all launches of one step)", "achieved": achieved,
+                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " sustained",
+                "launches_per_step": len(evs), "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / (ms_dev / args.steps)}
+
+    if rank == 0:
+        cpu_rate, cpu_dt, cores = cpu_reference_rate(args.cpu_sample, steps=1, warmup=0) if world == 1 and not args.skip_cpu else (None, None, None)
+        per_step = ms_dev / args.steps
+        value = world * B / (per_step * 1e-3)
+        e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "generation: Stage-1 DDIM-20 K=8 + interp T=64 + Stage-2 one-step (x0), small model 256x8 ff1024, "
+                                   "clamp_policy=endpoints, D=2 (BASELINE.json configs[2])",
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"trajectory-sharded x{world}" + (" + NCCL all-gather of samples" if world > 1 else ""),
+                       "cuda_graph": True, "l2": "per-step activation working set (~20 GB) >> 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "roofline": roof,
+            "flops_per_traj_gemm": gemm_flops_per_traj(), "tflops_e2e": value * gemm_flops_per_traj() / 1e12,
+        }
+        if cpu_rate is not None:
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample} trajectories, one pass of the oracle port ({cpu_dt:.1f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="trajectories per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="trajectories of the CPU baseline sample")
+    ap.add_argument("--ref-batch", type=int, default=512, help="trajectories per step of the reference arm")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

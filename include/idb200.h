@@ -186,9 +186,10 @@ int idb200_sgemm(const void* A, int a_is_bf16, int64_t lda, const float* W, cons
 
 /* MazeEncoder conv stack, src/models/encoders.py:15-24: [conv3x3 pad 1 + SiLU] x n_layers then the mean
  * over H x W.  occ / sdf [B,1,H,W] fp32 (sdf iff channels[0] == 2); channels host [n_layers+1];
- * weights / biases host arrays of device pointers ([C_out,C_in,3,3], [C_out]); pooled [B, C_last]. */
+ * weights / biases host arrays of device pointers ([C_out,C_in,3,3], [C_out]); pooled [B, C_last];
+ * scratch: 2 * B * max(channels[1..n_layers-1]) * H * W floats for the intermediate planes (NULL if 1 layer). */
 int idb200_conv_encoder(const float* occ, const float* sdf, int64_t B, int H, int W, int n_layers, const int* channels,
-                        const float* const* weights, const float* const* biases, float* pooled,
+                        const float* const* weights, const float* const* biases, float* scratch, float* pooled,
                         idb200_stream_t stream);
 
 /* sinusoid table out[rows, dim] = [sin(a f_i) | cos(a f_i)], f_i = exp(-ln(1e4) i / (dim/2)):

@@ -32,7 +32,7 @@ _SIGS = {
     "idb200_stage2_epilogue": [c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_p, c_p],
     "idb200_gemm_bf16": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
     "idb200_sgemm": [c_p, c_i, c_l, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_i, c_i, c_p],
-    "idb200_conv_encoder": [c_p, c_p, c_l, c_i, c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_p), ctypes.POINTER(c_p), c_p, c_p],
+    "idb200_conv_encoder": [c_p, c_p, c_l, c_i, c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_p), ctypes.POINTER(c_p), c_p, c_p, c_p],
     "idb200_sinusoid": [c_p, c_i, c_i, c_i, c_p, c_p],
     "idb200_embed_tokens": [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_p],
     "idb200_ln_film": [c_p, c_p, c_p, c_p, c_l, c_p, c_i, c_l, c_i, c_i, c_p],

@@ -81,54 +81,73 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const TA* __restrict__ A,
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv encoder: one CTA per trajectory; activation planes [C][H+2][W+2] fp32 in shared memory (zero
-// border = padding 1), layers ping-pong between two plane buffers; SiLU after each conv; the last
-// layer is reduced to the spatial mean [C_last] and written to pooled[b, :].
+// conv encoder: one launch per 3x3 pad-1 conv layer (+ SiLU).  A CTA owns (trajectory, block of 32 output
+// channels); input planes stream through shared memory in chunks of <= 32 channels ([23 x 23] zero-bordered
+// planes for a 21 x 21 maze), each thread accumulates 4-pixel strips for its output channels in registers.
+// Intermediate layers write [B, C, H, W] fp32 to a caller-provided scratch; the last layer is reduced to the
+// spatial mean [B, C_last] with a fixed summation order (deterministic).
 // ------------------------------------------------------------------------------------------------
-struct ConvParams {
-    const float* occ;        // [B, 1, H, W]
-    const float* sdf;        // [B, 1, H, W] or nullptr
-    const float* w[6];       // layer weights [C_out, C_in, 3, 3]
-    const float* bias[6];    // [C_out]
-    int ch[7];               // ch[0] = input channels, ch[l+1] = C_out of layer l
-    int n_layers;
-    int H, W;
+constexpr int kConvCo = 32;       // output channels per CTA
+constexpr int kConvCi = 32;       // input channels per shared-memory chunk
+constexpr int kConvItems = 16;    // (channel, strip) items per thread: supports up to 32 * 128 strips / 256 threads
+
+struct ConvLayerParams {
+    const float* in0;        // [B, ci0, H, W] (first ci0 input channels)
+    const float* in1;        // [B, ci - ci0, H, W] or nullptr (sdf plane of layer 0)
+    int ci0;
+    const float* w;          // [co, ci, 3, 3]
+    const float* bias;       // [co]
+    float* out;              // [B, co, H, W] or nullptr when pooling
+    float* pooled;           // [B, co] (last layer) or nullptr
+    int ci, co, H, W;
     long long B;
-    float* pooled;           // [B, ch[n_layers]]
 };
 
-__global__ void __launch_bounds__(256) conv_encoder_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(256) conv3x3_silu_kernel(const ConvLayerParams p) {
     extern __shared__ float smem_f[];
-    const int PH = p.H + 2, PW = p.W + 2, plane = PH * PW, HW = p.H * p.W;
-    int cmax = 0;
-    for (int l = 0; l <= p.n_layers; ++l) cmax = max(cmax, p.ch[l]);
-    float* buf0 = smem_f;
-    float* buf1 = smem_f + static_cast<size_t>(cmax) * plane;
-    for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2 * cmax * plane; i += blockDim.x) smem_f[i] = 0.0f;   // borders stay zero
-        __syncthreads();
-        for (int i = threadIdx.x; i < p.ch[0] * HW; i += blockDim.x) {
-            const int c = i / HW, r = i - c * HW, y = r / p.W, x = r - y * p.W;
-            const float* src = (c == 0) ? p.occ : p.sdf;
-            buf0[c * plane + (y + 1) * PW + x + 1] = src[b * HW + r];
+    const int PW = p.W + 2, plane = (p.H + 2) * PW, HW = p.H * p.W;
+    const int strips_per_row = (p.W + 3) / 4;
+    const int strips = p.H * strips_per_row;
+    float* planes = smem_f;                                   // [kConvCi][plane]
+    float* red = smem_f + kConvCi * plane;                    // [kConvCo][strips] (pooling only)
+    const int co_blocks = (p.co + kConvCo - 1) / kConvCo;
+    const long long work = p.B * co_blocks;
+    for (long long wi = blockIdx.x; wi < work; wi += gridDim.x) {
+        const long long b = wi / co_blocks;
+        const int c0 = static_cast<int>(wi - b * co_blocks) * kConvCo;
+        const int nco = min(kConvCo, p.co - c0);
+        const int items = nco * strips;
+        float acc[kConvItems][4];
+#pragma unroll
+        for (int it = 0; it < kConvItems; ++it) {
+            const int item = threadIdx.x + it * 256;
+            const float bv = (item < items) ? p.bias[c0 + item / strips] : 0.0f;
+            acc[it][0] = acc[it][1] = acc[it][2] = acc[it][3] = bv;
         }
-        float* in = buf0;
-        float* outp = buf1;
-        for (int l = 0; l < p.n_layers; ++l) {
+        for (int k0 = 0; k0 < p.ci; k0 += kConvCi) {
+            const int nk = min(kConvCi, p.ci - k0);
             __syncthreads();
-            const int ci = p.ch[l], co = p.ch[l + 1];
+            for (int i = threadIdx.x; i < nk * plane; i += 256) {
+                const int k = i / plane, r = i - k * plane, yy = r / PW, xx = r - yy * PW;
+                float v = 0.0f;
+                if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
+                    const int ch = k0 + k;
+                    const float* src = (ch < p.ci0) ? p.in0 + (b * p.ci0 + ch) * HW : p.in1 + (b * (p.ci - p.ci0) + (ch - p.ci0)) * HW;
+                    v = src[(yy - 1) * p.W + (xx - 1)];
+                }
+                planes[i] = v;
+            }
             __syncthreads();
-            // each thread: one output channel x a strip of 4 horizontally adjacent pixels
-            const int strips_per_row = (p.W + 3) / 4;
-            const int strips = p.H * strips_per_row;
-            for (int item = threadIdx.x; item < co * strips; item += blockDim.x) {
-                const int c = item / strips, s = item - c * strips;
-                const int y = s / strips_per_row, x0 = (s - y * strips_per_row) * 4;
-                float a0 = p.bias[l][c], a1 = a0, a2 = a0, a3 = a0;
-                const float* wc = p.w[l] + static_cast<long long>(c) * ci * 9;
-                for (int k = 0; k < ci; ++k) {
-                    const float* ip = in + k * plane + y * PW + x0;       // top-left of the 3 x 6 window
+#pragma unroll
+            for (int it = 0; it < kConvItems; ++it) {
+                const int item = threadIdx.x + it * 256;
+                if (item >= items) continue;
+                const int c = item / strips, sidx = item - c * strips;
+                const int y = sidx / strips_per_row, x0 = (sidx - y * strips_per_row) * 4;
+                const float* wc = p.w + (static_cast<long long>(c0 + c) * p.ci + k0) * 9;
+                float a0 = acc[it][0], a1 = acc[it][1], a2 = acc[it][2], a3 = acc[it][3];
+                for (int k = 0; k < nk; ++k) {
+                    const float* ip = planes + k * plane + y * PW + x0;   // top-left of the 3 x 6 window
                     const float* wk = wc + k * 9;
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
@@ -143,25 +162,35 @@ __global__ void __launch_bounds__(256) conv_encoder_kernel(const ConvParams p) {
                         a3 = fmaf(i3, w0, fmaf(i4, w1, fmaf(i5, w2, a3)));
                     }
                 }
-                const float v[4] = {silu_exact(a0), silu_exact(a1), silu_exact(a2), silu_exact(a3)};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x0 + j < p.W) outp[c * plane + (y + 1) * PW + x0 + j + 1] = v[j];
+                acc[it][0] = a0; acc[it][1] = a1; acc[it][2] = a2; acc[it][3] = a3;
             }
-            float* t = in; in = outp; outp = t;
         }
-        __syncthreads();
-        // spatial mean of the last layer: one warp per channel, fixed summation order (deterministic)
-        const int cl = p.ch[p.n_layers];
-        for (int c = threadIdx.x >> 5; c < cl; c += blockDim.x >> 5) {
-            float acc = 0.0f;
-            for (int i = threadIdx.x & 31; i < HW; i += 32) {
-                const int y = i / p.W, x = i - y * p.W;
-                acc += in[c * plane + (y + 1) * PW + x + 1];
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if ((threadIdx.x & 31) == 0) p.pooled[b * cl + c] = acc / static_cast<float>(HW);
+        for (int it = 0; it < kConvItems; ++it) {
+            const int item = threadIdx.x + it * 256;
+            if (item >= items) continue;
+            const int c = item / strips, sidx = item - c * strips;
+            const int y = sidx / strips_per_row, x0 = (sidx - y * strips_per_row) * 4;
+            float part = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (x0 + j < p.W) {
+                    const float v = silu_exact(acc[it][j]);
+                    if (p.out) p.out[(b * p.co + c0 + c) * HW + y * p.W + x0 + j] = v;
+                    part += v;
+                }
+            }
+            if (p.pooled) red[c * strips + sidx] = part;
+        }
+        if (p.pooled) {
+            __syncthreads();
+            for (int c = threadIdx.x >> 5; c < nco; c += 8) {       // one warp per channel, fixed order
+                float sum = 0.0f;
+                for (int i = threadIdx.x & 31; i < strips; i += 32) sum += red[c * strips + i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if ((threadIdx.x & 31) == 0) p.pooled[b * p.co + c0 + c] = sum / static_cast<float>(HW);
+            }
         }
     }
 }
@@ -371,29 +400,45 @@ extern "C" int idb200_sgemm(const void* A, int a_is_bf16, int64_t lda, const flo
 
 extern "C" int idb200_conv_encoder(const float* occ, const float* sdf, int64_t B, int H, int W, int n_layers,
                                    const int* channels /*host [n_layers+1]*/, const float* const* weights /*host*/,
-                                   const float* const* biases /*host*/, float* pooled, idb200_stream_t stream) {
-    IDB_REQUIRE(n_layers >= 1 && n_layers <= 6, IDB200_EUNSUPPORTED, "1..6 conv layers supported");
+                                   const float* const* biases /*host*/, float* scratch, float* pooled, idb200_stream_t stream) {
+    IDB_REQUIRE(n_layers >= 1 && n_layers <= 8, IDB200_EUNSUPPORTED, "1..8 conv layers supported");
     IDB_REQUIRE(B >= 0 && H >= 1 && W >= 1, IDB200_EINVAL, "bad shape");
     IDB_REQUIRE(channels[0] == 1 || (channels[0] == 2 && sdf), IDB200_EINVAL, "use_sdf is True but sdf missing from cond");
     if (B == 0) return IDB200_OK;
     IDB_REQUIRE(occ && pooled, IDB200_EINVAL, "NULL pointer");
-    ConvParams p{};
-    p.occ = occ; p.sdf = sdf; p.n_layers = n_layers; p.H = H; p.W = W; p.B = B; p.pooled = pooled;
-    int cmax = 0;
-    for (int l = 0; l <= n_layers; ++l) { p.ch[l] = channels[l]; cmax = cmax > channels[l] ? cmax : channels[l]; }
-    for (int l = 0; l < n_layers; ++l) { p.w[l] = weights[l]; p.bias[l] = biases[l]; }
-    const size_t smem = 2 * static_cast<size_t>(cmax) * (H + 2) * (W + 2) * sizeof(float);
+    const int plane = (H + 2) * (W + 2);
+    const int strips = H * ((W + 3) / 4);
+    IDB_REQUIRE(kConvCo * strips <= kConvItems * 256, IDB200_EUNSUPPORTED, "maze %dx%d too large for the conv kernel", H, W);
+    const size_t smem = (static_cast<size_t>(kConvCi) * plane + static_cast<size_t>(kConvCo) * strips) * sizeof(float);
     IDB_REQUIRE(smem <= 227 * 1024, IDB200_EUNSUPPORTED, "conv planes need %zu bytes of shared memory (> 227 KB)", smem);
+    int cmid = 0;
+    for (int l = 1; l < n_layers; ++l) cmid = cmid > channels[l] ? cmid : channels[l];
+    IDB_REQUIRE(n_layers == 1 || scratch, IDB200_EINVAL, "scratch (2 * B * max mid channels * H * W floats) is NULL");
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_silu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         smem_set = smem;
     }
     const int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
-    const int grid = grid_for(B, 1, per_sm > 0 ? per_sm : 1);
-    conv_encoder_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
-    return check_launch("conv_encoder_kernel");
+    const long long HW = static_cast<long long>(H) * W;
+    float* bufs[2] = {scratch, scratch ? scratch + B * cmid * HW : nullptr};
+    for (int l = 0; l < n_layers; ++l) {
+        ConvLayerParams p{};
+        const bool last = (l == n_layers - 1);
+        if (l == 0) { p.in0 = occ; p.in1 = sdf; p.ci0 = 1; }
+        else { p.in0 = bufs[(l - 1) & 1]; p.in1 = nullptr; p.ci0 = channels[l]; }
+        p.w = weights[l]; p.bias = biases[l];
+        p.out = last ? nullptr : bufs[l & 1];
+        p.pooled = last ? pooled : nullptr;
+        p.ci = channels[l]; p.co = channels[l + 1]; p.H = H; p.W = W; p.B = B;
+        const long long work = B * ((p.co + kConvCo - 1) / kConvCo);
+        const int grid = grid_for(work, 1, per_sm > 0 ? per_sm : 1);
+        conv3x3_silu_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+        int rc = check_launch("conv3x3_silu_kernel");
+        if (rc) return rc;
+    }
+    return IDB200_OK;
 }
 
 extern "C" int idb200_sinusoid(const float* args, int rows, int dim, int mode, float* out, idb200_stream_t stream) {

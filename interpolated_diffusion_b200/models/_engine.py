@@ -164,6 +164,9 @@ class PackedEncoder:
         return h
 
 
+_CONV_WS = Workspace()
+
+
 def conv_encoder(occ: torch.Tensor, sdf: Optional[torch.Tensor], weights: List[torch.Tensor], biases: List[torch.Tensor]) -> torch.Tensor:
     B, _, Hh, Ww = occ.shape
     n = len(weights)
@@ -172,7 +175,10 @@ def conv_encoder(occ: torch.Tensor, sdf: Optional[torch.Tensor], weights: List[t
     wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in weights])
     bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in biases])
     pooled = torch.empty((B, chans[-1]), device=occ.device, dtype=torch.float32)
-    L.call("idb200_conv_encoder", occ.data_ptr(), L.ptr(sdf), B, Hh, Ww, n, ch, wp, bp, pooled.data_ptr(), L.stream(occ.device))
+    cmid = max(chans[1:-1]) if n > 1 else 0
+    scratch = _CONV_WS.get(f"conv{occ.device.index}", (2, B, max(cmid, 1), Hh, Ww), torch.float32, occ.device) if n > 1 else None
+    L.call("idb200_conv_encoder", occ.data_ptr(), L.ptr(sdf), B, Hh, Ww, n, ch, wp, bp, L.ptr(scratch), pooled.data_ptr(),
+           L.stream(occ.device))
     return pooled
 
 

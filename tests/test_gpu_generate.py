@@ -1,0 +1,157 @@
+"""GPU parity of the generation loop (Stage-1 DDIM -> sigmoid -> interp -> Stage-2 -> clamp) against the golden
+outputs of the live reference (tiny random-init models) and the CPU oracle (BASELINE small model).
+
+Protocol: the cosine schedule's first DDIM step multiplies (z - eps) by ~3243, so free-running
+rollouts of non-contractive random-init nets amplify any rounding difference.  The gate is therefore teacher-forced
+per step (identical z_t into both sides, z_{t-1} compared relative to its scale); free-running agreement is checked
+where it is meaningful (fp32 check mode on the tiny models, where the reference itself is stable)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import generate as og
+from oracle import diffusion_np as odf
+from oracle import keyframes_np as okf
+from oracle import sampling_np as osp
+
+pytestmark = pytest.mark.gpu
+TINY = dict(d_model=64, n_layers=2, n_heads=2, d_ff=128, d_cond=32, maze_channels=(8, 16))
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def _models(g, precision):
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    kp = KeypointDenoiser(data_dim=2, **TINY).cuda()
+    kp.load_state_dict(_sd(g, "kp/"))
+    il = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=2, **TINY).cuda()
+    il.load_state_dict(_sd(g, "il/"))
+    il3 = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=3, **TINY).cuda()
+    il3.load_state_dict(_sd(g, "il3/"))
+    for m in (kp, il, il3):
+        m.precision = precision
+    return kp, il, il3
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 3e-2)])
+def test_stage1_teacher_forced_golden(golden, precision, tol):
+    from interpolated_diffusion_b200.diffusion import schedules
+    from interpolated_diffusion_b200.diffusion.ddpm import _timesteps, ddim_step_scalar
+    from interpolated_diffusion_b200.sample import sample_generate as sg
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    g = golden("generate_tiny")
+    kp, _, _ = _models(g, precision)
+    B, T, K, D = 4, 64, 8, 2
+    cond = {"occ": torch.from_numpy(g["occ"]).cuda(), "start_goal": torch.from_numpy(g["sg"]).cuda()}
+    idx, masks = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device="cuda")
+    km, kv = sg._build_known_mask_values(idx, cond, D, T, True, logit_space=True)
+    sch = schedules.make_alpha_bars(schedules.make_beta_schedule("cosine", 1000))
+    ab = sch["alpha_bar"].numpy()
+    times = _timesteps(1000, 20, "quadratic").tolist()
+    inter = g["z_inter"]
+    assert len(times) - 1 == inter.shape[0] - 1 == 19
+    for i in range(19):
+        z = torch.from_numpy(inter[i]).cuda()
+        t = torch.full((B,), times[i], device="cuda", dtype=torch.long)
+        eps = kp(z, t, idx, km, cond, T)
+        z2 = ddim_step_scalar(z, eps, float(ab[times[i]]), float(ab[times[i + 1]]), known_mask=km, known_values=kv)
+        ref = inter[i + 1]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert np.abs(z2.cpu().numpy() - ref).max() / scale < tol, (i, np.abs(z2.cpu().numpy() - ref).max(), scale)
+
+
+def test_generate_free_running_fp32_golden(golden):
+    """fp32 check mode reproduces the reference's own free-running pipeline on the tiny models: x_pred and x_hat for
+    every clamp_policy x clamp_dims, and the adj chain."""
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, generate
+    g = golden("generate_tiny")
+    kp, il, il3 = _models(g, "fp32")
+    cond = {"occ": torch.from_numpy(g["occ"]).cuda(), "start_goal": torch.from_numpy(g["sg"]).cuda()}
+    z_T = torch.from_numpy(g["z_T"]).cuda()
+    for pol in ("none", "endpoints", "all_anchors"):
+        for dims in ("pos", "all"):
+            out = generate(kp, il, cond, GenerationConfig(clamp_policy=pol, clamp_dims=dims), z_T=z_T, return_all=True)
+            np.testing.assert_allclose(out["x_pred"].cpu().numpy(), g["x_pred"], atol=3e-3, rtol=0)
+            np.testing.assert_allclose(out["x_hat"].cpu().numpy(), g[f"x_hat_x0_{pol}_{dims}"], atol=3e-3, rtol=0)
+            if pol == "endpoints":          # hard clamp: endpoints equal x_pred exactly
+                assert torch.equal(out["x_hat"][:, [0, -1], :2], out["x_pred"][:, [0, -1], :2])
+    out = generate(kp, il3, cond, GenerationConfig(stage2_mode="adj"), z_T=z_T,
+                   masks_levels=torch.from_numpy(g["adj_masks_levels"]).cuda(), return_all=True)
+    np.testing.assert_allclose(out["x_hat"].cpu().numpy(), g["x_hat_adj"], atol=3e-3, rtol=0)
+
+
+def test_generate_stage2_given_x_pred_vs_oracle():
+    """BASELINE small model: everything after Stage 1 (interp, conf channel, Stage-2 jump, soft + hard clamp) from the
+    SAME keypoints, bf16 path vs the CPU oracle: <= 2e-2 on x_hat (delta is the only rounded quantity)."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph, generate
+    B, T, K, S, D = 32, 64, 8, 3, 2
+    gen = torch.Generator().manual_seed(11)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=D)
+    il = InterpLevelDenoiser(data_dim=D, max_levels=S, mask_channels=2)
+    sd_kp = {k: v.clone() for k, v in kp.state_dict().items()}
+    sd_il = {k: v.clone() for k, v in il.state_dict().items()}
+    kp, il = kp.cuda(), il.cuda()
+    ccond = {k: v.cuda() for k, v in cond.items()}
+    z_T = torch.randn((B, K, D), generator=gen)
+    cfg = GenerationConfig()
+    out = generate(kp, il, ccond, cfg, z_T=z_T.cuda(), return_all=True)
+    # oracle continuation from the CUDA path's own keypoints z (teacher-forced at the stage boundary)
+    z = out["z"].cpu().numpy()
+    idx, masks = okf.sample_fixed_k_indices_uniform_batch(B, T, K)
+    assert np.array_equal(out["idx"].cpu().numpy(), idx)
+    z_pred = osp.sigmoid_pos(z)
+    x_pred = okf.interpolate_from_indices(idx, z_pred, T, True)
+    np.testing.assert_allclose(out["x_pred"].cpu().numpy(), x_pred, atol=1e-6, rtol=0)
+    conf = osp.build_anchor_conf(masks, masks, True, 0.95, 0.5, 1.0, 0.0, True)
+    mask_in = np.stack([masks.astype(np.float32), osp.anneal_conf(conf, S, S, "linear")], axis=-1)
+    from oracle import denoiser_torch as odn
+    delta = odn.interp_level_denoiser(sd_il, 8, torch.from_numpy(x_pred), torch.full((B,), S), torch.from_numpy(mask_in), cond).numpy()
+    x_hat = (x_pred + delta).astype(np.float32)
+    x_hat = osp.apply_soft_clamp(x_hat, x_pred, conf, 1.0, "pos")
+    cm = np.zeros_like(masks); cm[:, 0] = cm[:, -1] = True
+    x_hat = osp.apply_clamp(x_hat, x_pred, cm, "pos")
+    assert np.abs(out["x_hat"].cpu().numpy() - x_hat).max() < 2e-2
+    # Stage 1, teacher-forced on the first and a late step against the oracle eps
+    sched = odf.make_alpha_bars(odf.make_beta_schedule("cosine", 1000))
+    km, kv = osp.build_known_mask_values(idx, cond["start_goal"].numpy(), D, T, True)
+    for tval in (999, 44):
+        zz = torch.randn((B, K, D), generator=gen)
+        eps_ref = odn.keypoint_denoiser(sd_kp, 8, zz, torch.full((B,), tval), torch.from_numpy(idx), torch.from_numpy(km), cond, T)
+        eps = kp(zz.cuda(), torch.full((B,), tval, device="cuda"), out["idx"], torch.from_numpy(km).cuda(), ccond, T)
+        assert (eps.cpu() - eps_ref).abs().max().item() < 2e-2
+    # the CUDA-graph replay equals the eager call bit for bit
+    gg = GenerationGraph(kp, il, B, cfg).capture()
+    xg = gg.run(ccond, z_T.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(xg, out["x_hat"])
+    xg2 = gg.run(ccond, z_T.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(xg2, out["x_hat"])
+
+
+def test_sample_keypoints_ddim_mirror(golden):
+    """The drop-in `_sample_keypoints_ddim(model, schedule, idx, known_mask, known_values, cond, steps, T, ...)`."""
+    from interpolated_diffusion_b200.diffusion import schedules
+    from interpolated_diffusion_b200.sample import sample_generate as sg
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    g = golden("generate_tiny")
+    kp, _, _ = _models(g, "fp32")
+    B, T, K, D = 4, 64, 8, 2
+    cond = {"occ": torch.from_numpy(g["occ"]).cuda(), "start_goal": torch.from_numpy(g["sg"]).cuda()}
+    idx, _ = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device="cuda")
+    km, kv = sg._build_known_mask_values(idx, cond, D, T, True, logit_space=True)
+    sch = schedules.make_alpha_bars(schedules.make_beta_schedule("cosine", 1000))
+    z, inter = sg._sample_keypoints_ddim(kp, sch, idx, km, kv, cond, 20, T, schedule_name="quadratic", return_intermediates=True,
+                                         z_T=torch.from_numpy(g["z_T"]).cuda())
+    assert len(inter) == 20
+    ref = g["z_inter"]
+    for i in (1, 5, 19):
+        scale = max(1.0, float(np.abs(ref[i]).max()))
+        assert np.abs(inter[i].cpu().numpy() - ref[i]).max() / scale < 5e-3, i
