@@ -198,7 +198,7 @@ def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optiona
     # 1. anchors
     if idx is None:
         if cfg.kp_index_mode == "uniform":
-            idx, masks = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device=dev)
+            idx, masks = _uniform_idx_cache(B, T, K, dev)       # batch-invariant row: built once per shape
         elif cfg.kp_index_mode == "random":
             idx, masks = kf.sample_fixed_k_indices_batch(B, T, K, generator=generator, device=dev)
         else:
@@ -224,7 +224,8 @@ def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optiona
     pk = kp_model.transformer.packed()
     film = pk.film_params(cond_vec)
     row_b = _cond_row(kp_model, cond_vec, T, dev)
-    t_vecs = kp_model.timestep_vector(torch.tensor(times[:-1], device=dev, dtype=torch.long)) if len(times) > 1 else None
+    t_vecs = _cached(kp_model, ("t_vecs", tuple(times), str(dev)), [kp_model.t_embed[0].weight, kp_model.t_embed[0].bias, kp_model.t_embed[2].weight, kp_model.t_embed[2].bias],
+                     lambda: kp_model.timestep_vector(torch.tensor(times[:-1], device=dev, dtype=torch.long)))
     eps = torch.empty((B, K, D), device=dev, dtype=torch.float32)
     for i in range(len(times) - 1):
         kp_model(z, None, idx, known_mask, None, T, cond_vec=cond_vec, film=film, t_vec=t_vecs[i:i + 1], row_b=row_b, out=eps)
@@ -243,7 +244,7 @@ def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optiona
               clamp_endpoints=cfg.clamp_endpoints)
     x_hat = out if out is not None else torch.empty((B, T, D), device=dev, dtype=torch.float32)
     if cfg.stage2_mode == "x0":
-        level_vec = interp_model.level_vector(torch.tensor([S], device=dev, dtype=torch.long))
+        level_vec = _level_vectors(interp_model, S, dev)[S:S + 1]
         conf_pred = None
         if cfg.anchor_conf:
             # conf_pred (student == mask) and the annealed copy fed to the model; anneal at s == S is the identity
@@ -257,7 +258,7 @@ def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optiona
     else:
         if masks_levels is None:
             masks_levels, _ = kf.build_nested_masks_from_base(idx, T, S, generator=generator, k_schedule=cfg.k_schedule)
-        level_vecs = interp_model.level_vector(torch.arange(0, S + 1, device=dev, dtype=torch.long))
+        level_vecs = _level_vectors(interp_model, S, dev)
         x_curr = x_pred
         for s in range(S, 0, -1):
             m_s, m_prev = masks_levels[:, s].contiguous(), masks_levels[:, s - 1].contiguous()
@@ -276,6 +277,35 @@ def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optiona
 
 
 _SCHEDULES: Dict = {}
+_UNIFORM_IDX: Dict = {}
+
+
+def _uniform_idx_cache(B: int, T: int, K: int, dev):
+    from ..corruptions import keyframes as kf
+    key = (B, T, K, str(dev))
+    if key not in _UNIFORM_IDX:
+        _UNIFORM_IDX.clear()                      # keep one shape (static addresses for graph replay)
+        _UNIFORM_IDX[key] = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device=dev)
+    return _UNIFORM_IDX[key]
+
+
+def _cached(model, key, params, fn):
+    """Per-model cache of small derived tensors (timestep / level vectors), invalidated when the weights change.
+    Keeps host->device copies and tiny GEMMs out of the per-call (and graph-captured) path."""
+    from ..models import _engine as E
+    sig = E._sig(params)
+    hit = model._cache.get(key)
+    if hit is None or hit[0] != sig:
+        hit = (sig, fn())
+        model._cache[key] = hit
+    return hit[1]
+
+
+def _level_vectors(interp_model, S: int, dev):
+    params = [interp_model.level_emb.weight, interp_model.level_proj[0].weight, interp_model.level_proj[0].bias,
+              interp_model.level_proj[2].weight, interp_model.level_proj[2].bias]
+    return _cached(interp_model, ("level_vecs", S, str(dev)), params,
+                   lambda: interp_model.level_vector(torch.arange(0, S + 1, device=dev, dtype=torch.long)))
 
 
 def _schedule_cache(name: str, n_train: int):

@@ -77,10 +77,10 @@ def test_small_kernels_vs_torch():
         x = (torch.rand((B, chans[0], H, W), generator=g, device="cuda") < 0.3).float()
         ws = [torch.randn((chans[i + 1], chans[i], 3, 3), generator=g, device="cuda") * (chans[i] * 9) ** -0.5 for i in range(len(chans) - 1)]
         bs = [torch.randn((c,), generator=g, device="cuda") * 0.1 for c in chans[1:]]
-        ref = x
+        ref = x.double()                  # fp64 reference (cuDNN fp32 convolutions default to TF32)
         for w_, b_ in zip(ws, bs):
-            ref = torch.nn.functional.silu(torch.nn.functional.conv2d(ref, w_, b_, padding=1))
-        ref = ref.mean(dim=[2, 3])
+            ref = torch.nn.functional.silu(torch.nn.functional.conv2d(ref, w_.double(), b_.double(), padding=1))
+        ref = ref.mean(dim=[2, 3]).float()
         got = E.conv_encoder(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if chans[0] == 2 else None, ws, bs)
         assert _maxabs(got, ref) < 2e-5, chans
 
