@@ -221,6 +221,12 @@ int idb200_out_head(const float* h, const float* W, const float* bias, float* y,
 int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t B, int L, int H, int causal, int force_simt,
                      idb200_stream_t stream);
 
+/* K3d  fused transformer MLP (d_model = 256): h[M,256] += W2 . SiLU(W1 . a + b1) + b2, the `ff` branch of
+ * src/models/transformer.py:43-45 in one tcgen05 kernel; the [M, d_ff] hidden activation stays in TMEM / shared
+ * memory.  a bf16 [M,256] (LN+FiLM output), W1 bf16 [ff,256], W2 bf16 [256,ff], ff % 128 == 0, ff <= 2048. */
+int idb200_mlp_fused(const void* a, const void* W1, const float* b1, const void* W2, const float* b2, float* h,
+                     int64_t M, int d, int ff, idb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,8 +124,10 @@ __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
 constexpr int kPitch = 40;      // bf16 elements per staged row (80 bytes): conflict-free ldmatrix rows
 
 // grid.x = B * (H / HG); CTA stages Q, K, V of HG heads of one trajectory: [3][HG][L][kPitch] bf16
+// blk > 0: block-diagonal attention -- the L rows of a "sequence" are L / blk independent trajectories of blk tokens
+// (Stage 1: blk = 8 tokens per trajectory, 8 trajectories per 64-row sequence), a query only sees keys of its own block.
 __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                       long long B, int L, int H, int HG, int causal) {
+                                                       long long B, int L, int H, int HG, int causal, int blk) {
     extern __shared__ __align__(16) unsigned char smem_attn[];
     __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_attn);
     const int d = H * kHD;
@@ -174,8 +176,13 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
             float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;   // rows g and g+8 of the 16-row block
             const int g = lane >> 2, tq = lane & 3;
             const int qrow0 = qb * 16 + g, qrow1 = qrow0 + 8;
-            const int kend = causal ? (qb + 1) * 16 : L;                   // keys needed by this query block
-            for (int k0 = 0; k0 < kend; k0 += 64) {
+            int kbeg = 0, kend = causal ? (qb + 1) * 16 : L;               // keys needed by this query block
+            if (blk > 0) {                                                 // only the blocks the 16 query rows belong to
+                kbeg = (((qb * 16) / blk) * blk) & ~15;
+                const int ke = ((qb * 16 + 15) / blk + 1) * blk;
+                kend = min(kend, min(L, (ke + 15) & ~15));
+            }
+            for (int k0 = kbeg; k0 < kend; k0 += 64) {
                 const int kw = min(64, kend - k0);                         // multiple of 16
                 float s[8][4];
 #pragma unroll
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
                     for (int c = 0; c < 4; ++c) {
                         const int key = k0 + nt * 8 + tq * 2 + (c & 1);
                         const int qr = (c < 2) ? qrow0 : qrow1;
-                        const bool ok = (nt * 8 < kw) && (!causal || key <= qr);
+                        const bool ok = (nt * 8 < kw) && (!causal || key <= qr) && (blk <= 0 || key / blk == qr / blk);
                         s[nt][c] = ok ? s[nt][c] * scale_log2 : -INFINITY;
                     }
                     bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
@@ -273,11 +280,19 @@ extern "C" int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t
     if (B == 0) return IDB200_OK;
     IDB_REQUIRE(qkv && out, IDB200_EINVAL, "NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool use_mma = is_bf16 && !force_simt && (L % 16 == 0) && aligned(qkv, 16) && aligned(out, 4);
+    // short sequences (Stage 1, L = 8): pack Lp / L trajectories into one block-diagonal "sequence" for the mma path
+    int Lp = L, blk = 0;
+    long long Bp = B;
+    if (is_bf16 && !force_simt && L < 16 && (L == 8 || L == 4 || L == 2)) {
+        for (int cand : {64, 32, 16}) {
+            if (cand % L == 0 && B % (cand / L) == 0) { Lp = cand; blk = L; Bp = B / (cand / L); break; }
+        }
+    }
+    const bool use_mma = is_bf16 && !force_simt && (Lp % 16 == 0) && aligned(qkv, 16) && aligned(out, 4);
     if (use_mma) {
         int HG = H;
-        while (HG > 1 && (3 * static_cast<size_t>(HG) * L * kPitch * 2 > 100 * 1024 || H % HG != 0)) --HG;
-        const size_t smem = 3 * static_cast<size_t>(HG) * L * kPitch * 2;
+        while (HG > 1 && (3 * static_cast<size_t>(HG) * Lp * kPitch * 2 > 100 * 1024 || H % HG != 0)) --HG;
+        const size_t smem = 3 * static_cast<size_t>(HG) * Lp * kPitch * 2;
         static size_t smem_set = 0;
         if (smem > smem_set) {
             cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -285,8 +300,8 @@ extern "C" int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t
             smem_set = smem;
         }
         const int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
-        const int grid = grid_for(B * (H / HG), 1, per_sm > 0 ? per_sm : 1);
-        attn_mma_kernel<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), B, L, H, HG, causal);
+        const int grid = grid_for(Bp * (H / HG), 1, per_sm > 0 ? per_sm : 1);
+        attn_mma_kernel<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), Bp, Lp, H, HG, causal, blk);
         return check_launch("attn_mma_kernel");
     }
     const int G = (L < 32) ? 32 / L : 1;

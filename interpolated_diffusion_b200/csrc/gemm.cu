@@ -10,7 +10,7 @@
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block,
 //               accumulating in TMEM; tcgen05.commit frees the smem slot / publishes the accumulator
 //   warp 2      TMEM allocator (512 columns = two BN-wide accumulator stages)
-//   warps 4..7  epilogue: tcgen05.ld (thread <-> output row), bias / SiLU / residual, global stores;
+//   warps 4..11 epilogue: tcgen05.ld (thread <-> output row), bias / SiLU / residual, global stores;
 //               overlaps the next tile's MMAs through the second accumulator stage
 // M is arbitrary (TMA zero-fills out-of-range rows, stores are row-guarded); N % BN == 0; K % 64 == 0.
 #include "tc_common.cuh"
@@ -53,7 +53,8 @@ using namespace tc;
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int kBiasFloats = 2048;       // bias vector staged in shared memory (N <= 2048)
 
 enum { EPI_BF16 = 0, EPI_SILU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3 };
 
@@ -62,7 +63,7 @@ struct GemmCfg {
     static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
     static constexpr int kStages = (BN <= 128) ? 6 : 4;
     static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kBiasFloats * 4;
 };
 
 struct GemmParams {
@@ -72,7 +73,14 @@ struct GemmParams {
     int N, K, epilogue;
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU (tanh.approx, rel. error ~2^-11, below the bf16
+// rounding of the stored result) instead of ex2 + rcp.
+__device__ __forceinline__ float silu_f(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -86,6 +94,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* acc_full = bars + 2 * Cfg::kStages;           // [kAccStages] MMA -> epilogue
     uint64_t* acc_empty = acc_full + Cfg::kAccStages;       // [kAccStages] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::kAccStages);
+    float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -100,13 +109,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_mbar_init();
     }
     if (warp == 2) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    const bool bias_smem = p.bias != nullptr && p.N <= kBiasFloats;
+    if (bias_smem)
+        for (int i = threadIdx.x; i < p.N; i += kGemmThreads) sbias[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -160,8 +172,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: warp (4 + q) owns TMEM lanes [32q, 32q+32) =====
-        const int q = warp - 4;
+        // ===== epilogue: 8 warps; warps (4 + q) and (8 + q) share TMEM lanes [32q, 32q+32) and alternate
+        // over the 32-column chunks, so every SM sub-partition has two epilogue warps to hide TMEM / MUFU latency
+        const int ew = warp - 4;
+        const int q = ew & 3, half = ew >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -172,16 +186,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const long long row = m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = half * 32; c < BN; c += 64) {
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
                 if (row < p.M) {
                     float v[32];
+                    if (bias_smem) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(r[j]);
-                        if (p.bias) v[j] += __ldg(p.bias + n0 + c + j);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bv = *reinterpret_cast<const float4*>(&sbias[n0 + c + 4 * j]);
+                            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bv.x;
+                            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bv.y;
+                            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv.z;
+                            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            v[j] = __uint_as_float(r[j]);
+                            if (p.bias) v[j] += __ldg(p.bias + n0 + c + j);
+                        }
                     }
                     const long long o = row * p.N + n0 + c;
                     if (p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16) {
@@ -205,14 +230,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                     } else {
                         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+                        if (p.epilogue == EPI_RESID_F32) {
+                            float4 hv[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 w = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            if (p.epilogue == EPI_RESID_F32) {
-                                const float4 h = dst[j];
-                                w.x += h.x; w.y += h.y; w.z += h.z; w.w += h.w;
-                            }
-                            dst[j] = w;
+                            for (int j = 0; j < 8; ++j) hv[j] = dst[j];            // all loads first (MLP)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                dst[j] = make_float4(v[4 * j] + hv[j].x, v[4 * j + 1] + hv[j].y, v[4 * j + 2] + hv[j].z, v[4 * j + 3] + hv[j].w);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
                     }
                 }

@@ -37,6 +37,14 @@ def gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], ou
     return out
 
 
+def mlp_fused(a: torch.Tensor, W1: torch.Tensor, b1: torch.Tensor, W2: torch.Tensor, b2: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """h += W2 . SiLU(W1 . a + b1) + b2 in one kernel (idb200_mlp_fused, d_model = 256)."""
+    M, d = a.shape
+    L.call("idb200_mlp_fused", a.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), h.data_ptr(), M, d,
+           W1.shape[0], L.stream(a.device))
+    return h
+
+
 def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((rows, dim), device=device, dtype=torch.float32)
     L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))
@@ -81,6 +89,7 @@ class PackedEncoder:
         self.enc = encoder
         self._key = None
         self.ws = Workspace()
+        self.fuse_mlp = True            # d_model == 256: FF1 + SiLU + FF2 + residual in one kernel
 
     def _pack(self):
         layers = self.enc.layers
@@ -133,7 +142,8 @@ class PackedEncoder:
         if precision == "bf16":
             a = self.ws.get("a", (M, d), torch.bfloat16, dev)
             qkv = self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
-            f = self.ws.get("f", (M, ff), torch.bfloat16, dev)
+            fuse_mlp = self.fuse_mlp and d == 256 and ff % 128 == 0 and ff <= 2048
+            f = None if fuse_mlp else self.ws.get("f", (M, ff), torch.bfloat16, dev)
             for i, e in enumerate(self.layers):
                 g1 = film[:, 2 * i] if film is not None else None
                 g2 = film[:, 2 * i + 1] if film is not None else None
@@ -142,8 +152,11 @@ class PackedEncoder:
                 attention(qkv, a, B, Lseq, H, causal)                    # `a` is free again: reuse as attention output
                 gemm_bf16(a, e["wo"], e["bo"], h, EPI_RESID_F32)
                 ln_film(h, e["n2w"], e["n2b"], g2, a, Lseq)
-                gemm_bf16(a, e["w1"], e["b1"], f, EPI_SILU_BF16)
-                gemm_bf16(f, e["w2"], e["b2"], h, EPI_RESID_F32)
+                if fuse_mlp:
+                    mlp_fused(a, e["w1"], e["b1"], e["w2"], e["b2"], h)
+                else:
+                    gemm_bf16(a, e["w1"], e["b1"], f, EPI_SILU_BF16)
+                    gemm_bf16(f, e["w2"], e["b2"], h, EPI_RESID_F32)
         elif precision == "fp32":
             a = self.ws.get("a32", (M, d), torch.float32, dev)
             o = self.ws.get("o32", (M, d), torch.float32, dev)

@@ -57,3 +57,34 @@ def test_gemm_argument_errors():
     W = torch.zeros((32, 48), device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="multiple of 64"):
         gemm(A, W, None, torch.empty((8, 32), device="cuda"), 3)
+
+
+@pytest.mark.parametrize("M,ff", [(128, 128), (1000, 1024), (148 * 128 * 2 + 5, 1024), (4096, 256), (333, 2048), (7, 384)])
+def test_mlp_fused_vs_unfused_reference(M, ff):
+    from interpolated_diffusion_b200.models import _engine as E
+    d = 256
+    g = torch.Generator(device="cuda").manual_seed(M + ff)
+    a = (torch.randn((M, d), generator=g, device="cuda")).bfloat16()
+    W1 = (torch.randn((ff, d), generator=g, device="cuda") * d ** -0.5).bfloat16()
+    W2 = (torch.randn((d, ff), generator=g, device="cuda") * ff ** -0.5).bfloat16()
+    b1 = torch.randn((ff,), generator=g, device="cuda") * 0.1
+    b2 = torch.randn((d,), generator=g, device="cuda") * 0.1
+    h0 = torch.randn((M, d), generator=g, device="cuda")
+    hid = torch.nn.functional.silu(a.float() @ W1.float().t() + b1).bfloat16().float()     # hidden is rounded to bf16
+    ref = h0 + hid @ W2.float().t() + b2
+    h = h0.clone()
+    E.mlp_fused(a, W1, b1, W2, b2, h)
+    torch.cuda.synchronize()
+    assert torch.isfinite(h).all()
+    # differences: tanh.approx SiLU (~5e-4 rel) before the bf16 rounding of the hidden activation
+    assert (h - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item() / 4)
+    # exact-integer variant: every product and partial sum is exact -> bit-exact (catches swizzle / slot-order bugs)
+    ai = torch.randint(-2, 3, (M, d), generator=g, device="cuda").bfloat16()
+    W1i = torch.zeros((ff, d), device="cuda")
+    W1i[torch.arange(ff), torch.randint(0, d, (ff,), generator=g, device="cuda")] = 64.0     # hidden = 64 * a[:, perm]: SiLU saturates to {0, +-128..}
+    W2i = torch.randint(-2, 3, (d, ff), generator=g, device="cuda").bfloat16()
+    hz = torch.zeros((M, d), device="cuda")
+    E.mlp_fused(ai, W1i.bfloat16(), torch.zeros_like(b1), W2i, torch.zeros_like(b2), hz)
+    hid_i = torch.nn.functional.silu(ai.float() @ W1i.t()).bfloat16().float()
+    ref_i = hid_i @ W2i.float().t()
+    assert (hz - ref_i).abs().max().item() < 1e-3 * max(1.0, ref_i.abs().max().item())
