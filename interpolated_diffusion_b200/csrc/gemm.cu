@@ -34,19 +34,25 @@ EncodeTiledFn encode_tiled_fn() {
 }
 }  // namespace
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                 uint32_t box_cols) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(IDB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    if (!aligned(base, 16) || (cols * 2) % 16 != 0) return fail(IDB200_EALIGN, "TMA needs 16-byte aligned base and row pitch");
+    if (!aligned(base, 16) || (cols * elem_bytes) % 16 != 0) return fail(IDB200_EALIGN, "TMA needs 16-byte aligned base and row pitch");
+    if (box_cols * elem_bytes != 128) return fail(IDB200_EINVAL, "SWIZZLE_128B boxes are 128 bytes wide");
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {cols * 2};
+    cuuint64_t gstride[1] = {cols * elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapDataType dt = (elem_bytes == 2) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(IDB200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
     return IDB200_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    return make_tmap_2d(out, base, 2, rows, cols, box_rows, box_cols);
 }
 
 using namespace tc;

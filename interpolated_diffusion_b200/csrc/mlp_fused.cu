@@ -8,7 +8,7 @@
 //   FF1(c): acc1[c&1] (TMEM, 128 cols)  = A[128x256] . W1[c*128.., :]^T          16 x tcgen05.mma N=128
 //   EPI1(c): acc1 -> +b1 -> SiLU -> bf16 -> H[c&1] in shared memory (SWIZZLE_128B K-major, an MMA A operand)
 //   FF2(c): acc2 (TMEM, 256 cols)      += H[c&1][128x128] . W2[:, c*128..]^T     16 x tcgen05.mma N=128
-//   final:  h += acc2 + b2   (fp32 read-modify-write of the residual stream)
+//   final:  h += acc2 + b2   (fp32 tile staged in the idle H buffers, TMA reduce-add into the residual stream)
 // The MMA warp runs FF1(c+2) while the 8 epilogue warps do EPI1(c) (acc1 and H are double-buffered), weights stream
 // through a 5-slot TMA ring of [128 x 64] bf16 tiles in exactly the order the MMA warp consumes them.
 // TMEM: acc2 cols [0,256), acc1 cols [256,384) / [384,512).
@@ -48,7 +48,7 @@ __device__ __forceinline__ float silu_fast(float x) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
-                 const __grid_constant__ CUtensorMap tmap_w2, const Params p) {
+                 const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_h, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -74,6 +74,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w1);
         tma_prefetch_desc(&tmap_w2);
+        tma_prefetch_desc(&tmap_h);
     }
     if (warp == 1 && lane == 0) {
         mbar_init(a_full, 1);
@@ -249,32 +250,44 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ++use1[b];
                 ++useh[b];
             }
-            // final epilogue: h += acc2 + b2 (this warp: 128 of the 256 columns of its 32 rows)
+            // final epilogue: h += acc2 + b2.  No read of h: the fp32 tile is staged in the (now idle) H buffers as four
+            // [128 x 32] SWIZZLE_128B boxes per 128-column round and added to global memory by TMA reduce-add, so the
+            // residual update is asynchronous and fully coalesced (out-of-range rows are clipped by the tensor map).
             mbar_wait(acc2_full, tile_n & 1, 32);
             tc_fence_after();
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                const int col = half * 128 + cc * 32;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + lane_base + col, r);
-                tmem_ld_wait();
-                if (row < p.M) {
-                    float4* dst = reinterpret_cast<float4*>(p.h + row * kD + col);
-                    float4 hv[8];
+            for (int rnd = 0; rnd < 2; ++rnd) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) hv[j] = dst[j];
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int col = rnd * 128 + half * 64 + cc * 32;
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + lane_base + col, r);
+                    tmem_ld_wait();
+                    uint8_t* box = smem + kOffH + (half * 2 + cc) * kTile;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 bv = *reinterpret_cast<const float4*>(sb2 + col + 4 * j);
-                        dst[j] = make_float4(__uint_as_float(r[4 * j + 0]) + bv.x + hv[j].x, __uint_as_float(r[4 * j + 1]) + bv.y + hv[j].y,
-                                             __uint_as_float(r[4 * j + 2]) + bv.z + hv[j].z, __uint_as_float(r[4 * j + 3]) + bv.w + hv[j].w);
+                        const float4 v = make_float4(__uint_as_float(r[4 * j + 0]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
+                                                     __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
+                        *reinterpret_cast<float4*>(box + row_in_tile * 128 + ((j ^ (row_in_tile & 7)) << 4)) = v;
                     }
                 }
+                fence_proxy_async_smem();
+                named_barrier_sync(1, 256);
+                if (ew == 0 && lane == 0) {
+                    const int m0 = static_cast<int>(tile) * 128;
+#pragma unroll
+                    for (int bx = 0; bx < 4; ++bx) tma_reduce_add_2d(&tmap_h, smem + kOffH + bx * kTile, rnd * 128 + bx * 32, m0);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();                            // staging may be overwritten after this
+                }
+                named_barrier_sync(2, 256);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc2_empty);
         }
+        if (ew == 0 && lane == 0) tma_store_wait_all();                  // all residual updates landed before exit
     }
 
     tc_fence_before();
@@ -295,12 +308,14 @@ int mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, co
     if (M == 0) return IDB200_OK;
     IDB_REQUIRE(A && W1 && b1 && W2 && b2 && h, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(aligned(h, 16), IDB200_EALIGN, "h must be 16-byte aligned");
-    CUtensorMap ta, t1, t2;
+    CUtensorMap ta, t1, t2, th;
     int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), d, 128, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&t1, W1, ff, d, 128, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&t2, W2, d, ff, 128, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&th, h, 4, static_cast<uint64_t>(M), d, 128, 32);
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
@@ -311,7 +326,7 @@ int mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, co
     const long long tiles = (M + 127) / 128;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     mlp::Params p{b1, b2, h, M, ff};
-    mlp::mlp_fused_kernel<<<grid, mlp::kThreads, mlp::kSmem, st>>>(ta, t1, t2, p);
+    mlp::mlp_fused_kernel<<<grid, mlp::kThreads, mlp::kSmem, st>>>(ta, t1, t2, th, p);
     return check_launch("mlp_fused_kernel");
 }
 

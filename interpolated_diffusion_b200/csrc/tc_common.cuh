@@ -80,6 +80,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// h[tile] += smem tile: TMA reduce-add (fp32) into global memory, bulk-group completion
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, loads
 // ------------------------------------------------------------------------------------------------
@@ -162,5 +175,7 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
 
 // host: encode a 2-D bf16 row-major [rows, cols] tensor map with a (box_rows x 64) box, 128-byte swizzle
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
+// generic: elem_bytes 2 (bf16) or 4 (fp32); the box must be 128 bytes wide (SWIZZLE_128B)
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
 }  // namespace idb200

@@ -1,0 +1,45 @@
+"""Trajectory-batch sharding across the GPUs of one box (one process per GPU).
+
+The generation path is row-independent (no cross-sample statistic: LayerNorm is per token), so the batch is split into
+contiguous per-rank ranges with no data-path collective; the only exchange is the final all-gather of the samples."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) rows of `rank`; the first (total % world) ranks take one extra row."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_cond(cond: dict, rank: int, world: int) -> dict:
+    B = next(iter(cond.values())).shape[0]
+    lo, hi = shard_range(B, rank, world)
+    return {k: v[lo:hi] for k, v in cond.items()}
+
+
+def gather_samples(x_local: torch.Tensor, total: int | None = None) -> torch.Tensor:
+    """All ranks receive the samples of every rank, concatenated in rank order.  Equal shards use one
+    `all_gather_into_tensor` (NCCL over NVLink on the GPU box); ragged shards fall back to padded gathers."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return x_local
+    world = dist.get_world_size()
+    n_local = torch.tensor([x_local.shape[0]], device=x_local.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local)
+    sizes = [int(s.item()) for s in sizes]
+    if len(set(sizes)) == 1 and dist.get_backend() == "nccl":
+        out = torch.empty((world * sizes[0],) + tuple(x_local.shape[1:]), device=x_local.device, dtype=x_local.dtype)
+        dist.all_gather_into_tensor(out, x_local.contiguous())
+        return out
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(x_local.shape[1:]), device=x_local.device, dtype=x_local.dtype)
+    pad[: x_local.shape[0]] = x_local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
