@@ -227,6 +227,14 @@ int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t B, int L, 
 int idb200_mlp_fused(const void* a, const void* W1, const float* b1, const void* W2, const float* b2, float* h,
                      int64_t M, int d, int ff, idb200_stream_t stream);
 
+/* K4 (tensor-core path)  two-layer MazeEncoder conv stack of src/models/encoders.py:15-24 in one launch:
+ * conv3x3(cin->c1)+SiLU on CUDA cores into a shared-memory bf16 channels-last tile, conv3x3(c1->c2)+SiLU as an
+ * implicit GEMM (mma.sync bf16, fp32 accumulate), spatial mean -> pooled [B, c2].
+ * w0 [c1,cin,3,3] fp32; w1 packed bf16 [c2, 9*c1] with k = (ky*3+kx)*c1 + c.  c1 in {16,32,48,64}, c2 in {32,64}. */
+int idb200_conv_encoder_tc(const float* occ, const float* sdf, int64_t B, int H, int W, int cin, int c1, int c2,
+                           const float* w0, const float* b0, const void* w1_packed_bf16, const float* b1, float* pooled,
+                           idb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

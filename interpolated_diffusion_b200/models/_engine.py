@@ -195,6 +195,28 @@ def conv_encoder(occ: torch.Tensor, sdf: Optional[torch.Tensor], weights: List[t
     return pooled
 
 
+def conv_encoder_tc(occ: torch.Tensor, sdf: Optional[torch.Tensor], w0, b0, w1_packed, b1) -> torch.Tensor:
+    """Two-layer conv stack on tensor cores (idb200_conv_encoder_tc); w1_packed = bf16 [c2, 9*c1], k = tap*c1 + c."""
+    B, _, Hh, Ww = occ.shape
+    c1, cin = w0.shape[0], w0.shape[1]
+    c2 = w1_packed.shape[0]
+    pooled = torch.empty((B, c2), device=occ.device, dtype=torch.float32)
+    L.call("idb200_conv_encoder_tc", occ.data_ptr(), L.ptr(sdf), B, Hh, Ww, cin, c1, c2, w0.data_ptr(), b0.data_ptr(),
+           w1_packed.data_ptr(), b1.data_ptr(), pooled.data_ptr(), L.stream(occ.device))
+    return pooled
+
+
+def conv_tc_supported(convs, Hh: int, Ww: int) -> bool:
+    if len(convs) != 2:
+        return False
+    c1, c2 = convs[0].weight.shape[0], convs[1].weight.shape[0]
+    if c1 % 16 or not (16 <= c1 <= 64) or c2 not in (32, 64):
+        return False
+    pp = (Hh + 2) * (Ww + 2)
+    smem = pp * (c1 + 8) * 2 + c2 * (9 * c1 + 8) * 2 + (convs[0].weight.shape[1] * pp + c1 * 18 + c1 + 5 * c2 + 8) * 4
+    return smem <= 220 * 1024
+
+
 def embed_tokens(src0, src1, src2, Wf, tab, tab_idx, row_a, row_b, h, M, Lseq, d):
     n0 = src0.shape[-1]
     n1 = 0 if src1 is None else src1.shape[-1]

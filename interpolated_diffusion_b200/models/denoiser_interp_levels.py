@@ -60,7 +60,13 @@ class InterpLevelDenoiser(nn.Module):
         return val
 
     @torch.no_grad()
+    def _sync_precision(self):
+        if hasattr(self.cond_enc, "maze"):
+            self.cond_enc.precision = self.precision
+
+    @torch.no_grad()
     def encode_cond(self, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
+        self._sync_precision()
         return self.cond_enc(cond)
 
     @torch.no_grad()
@@ -91,7 +97,7 @@ class InterpLevelDenoiser(nn.Module):
             src1 = L.f32c(mask).view(M, C)
         if cond_vec is None:
             if cond and self.cond_enc is not None:
-                cond_vec = self.cond_enc(cond)
+                cond_vec = self.encode_cond(cond)
             else:
                 cond_vec = torch.zeros((B, self.d_cond), device=dev, dtype=torch.float32)
         if row_b is None:

@@ -76,8 +76,14 @@ class KeypointDenoiser(nn.Module):
         return val
 
     @torch.no_grad()
+    def _sync_precision(self):
+        if hasattr(self.cond_enc, "maze"):
+            self.cond_enc.precision = self.precision
+
+    @torch.no_grad()
     def encode_cond(self, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
         """cond_vec [B, d_cond]: loop-invariant across DDIM steps (the reference recomputes it per step, :107)."""
+        self._sync_precision()
         return self.cond_enc(cond)
 
     @torch.no_grad()
@@ -113,7 +119,7 @@ class KeypointDenoiser(nn.Module):
                 kp_feat = torch.zeros((B, K, self.kp_feat_dim), device=dev, dtype=torch.float32)
         if cond_vec is None:
             if cond and self.cond_enc is not None:
-                cond_vec = self.cond_enc(cond)
+                cond_vec = self.encode_cond(cond)
             else:
                 cond_vec = torch.zeros((B, self.d_cond), device=dev, dtype=torch.float32)
         if row_b is None:

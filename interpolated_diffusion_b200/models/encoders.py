@@ -25,15 +25,27 @@ class MazeEncoder(nn.Module):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """encoders.py:22-25; x [B, C_in, H, W]."""
+        """encoders.py:22-25; x [B, C_in, H, W].  ``self.precision == "bf16"`` (default) runs the two-layer stack as a
+        tensor-core implicit GEMM; "fp32" (check mode) and other depths use the fp32 direct-conv kernels."""
         L.require_cuda(x)
         x = L.f32c(x)
         occ = x[:, 0:1].contiguous()
         sdf = x[:, 1:2].contiguous() if x.shape[1] > 1 else None
         convs = [m for m in self.convs if isinstance(m, nn.Conv2d)]
-        pooled = E.conv_encoder(occ, sdf, [c.weight.detach().float().contiguous() for c in convs],
-                                [c.bias.detach().float().contiguous() for c in convs])
-        return E.sgemm(pooled, self.fc.weight.detach().float().contiguous(), self.fc.bias.detach().float().contiguous())
+        fcw, fcb = self.fc.weight.detach().float().contiguous(), self.fc.bias.detach().float().contiguous()
+        if getattr(self, "precision", "bf16") == "bf16" and E.conv_tc_supported(convs, x.shape[2], x.shape[3]):
+            key = E._sig([convs[1].weight])
+            if getattr(self, "_w1_key", None) != key:
+                w = convs[1].weight.detach().float()
+                self._w1_packed = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+                self._w1_key = key
+            pooled = E.conv_encoder_tc(occ, sdf, convs[0].weight.detach().float().contiguous(),
+                                       convs[0].bias.detach().float().contiguous(), self._w1_packed,
+                                       convs[1].bias.detach().float().contiguous())
+        else:
+            pooled = E.conv_encoder(occ, sdf, [c.weight.detach().float().contiguous() for c in convs],
+                                    [c.bias.detach().float().contiguous() for c in convs])
+        return E.sgemm(pooled, fcw, fcb)
 
 
 class StartGoalEncoder(nn.Module):
@@ -71,6 +83,7 @@ class MazeConditionEncoder(nn.Module):
             x = torch.cat([occ, sdf], dim=1)
         else:
             x = occ
+        self.maze.precision = getattr(self, "precision", "bf16")
         emb = self.maze(x)
         if self.use_start_goal:
             if "start_goal" not in cond:

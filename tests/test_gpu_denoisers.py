@@ -73,7 +73,7 @@ def test_small_kernels_vs_torch():
         assert ((ob.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-6).all()      # one bf16 rounding
         assert _maxabs(E.ln_film(h, w, b, None, torch.empty_like(h), Lq), torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)) < 2e-5
     # conv encoder
-    for (chans, H, W) in [((1, 32, 64), 21, 21), ((2, 8, 16), 9, 12), ((1, 32, 64, 128, 128), 21, 21)]:
+    for (chans, H, W) in [((1, 32, 64), 21, 21), ((2, 8, 16), 9, 12), ((1, 32, 64, 128, 128), 21, 21), ((2, 16, 32), 9, 12), ((1, 64, 64), 12, 9)]:
         B = 5
         x = (torch.rand((B, chans[0], H, W), generator=g, device="cuda") < 0.3).float()
         ws = [torch.randn((chans[i + 1], chans[i], 3, 3), generator=g, device="cuda") * (chans[i] * 9) ** -0.5 for i in range(len(chans) - 1)]
@@ -84,6 +84,11 @@ def test_small_kernels_vs_torch():
         ref = ref.mean(dim=[2, 3]).float()
         got = E.conv_encoder(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if chans[0] == 2 else None, ws, bs)
         assert _maxabs(got, ref) < 2e-5, chans
+        if len(chans) == 3 and chans[1] % 16 == 0 and chans[2] in (32, 64):
+            # tensor-core implicit-GEMM path: bf16 activations / weights of the second conv, fp32 accumulate
+            w1p = ws[1].permute(0, 2, 3, 1).reshape(chans[2], -1).to(torch.bfloat16).contiguous()
+            got_tc = E.conv_encoder_tc(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if chans[0] == 2 else None, ws[0], bs[0], w1p, bs[1])
+            assert _maxabs(got_tc, ref) < 3e-3, (chans, _maxabs(got_tc, ref))
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
