@@ -37,6 +37,20 @@ def gemm_flops_per_traj() -> float:
     return float(N_LAYERS * per_tok_layer * (19 * K_MIN + T))
 
 
+def _attn_block_flops(a):
+    M, Lq = a[9], a[10]
+    return float(M) * (2 * D_MODEL * 3 * D_MODEL + 2 * D_MODEL * D_MODEL + 4 * Lq * D_MODEL)
+
+
+# algorithmic FLOPs of one call of each dense entry point, from its C-ABI arguments (include/idb200.h)
+DENSE_FLOPS = {
+    "idb200_gemm_bf16": lambda a: 2.0 * a[4] * a[5] * a[6],
+    "idb200_mlp_fused": lambda a: 4.0 * a[6] * a[7] * a[8],
+    "idb200_mlp_block": lambda a: 4.0 * a[9] * a[11] * a[12],
+    "idb200_attn_block": _attn_block_flops,
+}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -218,31 +232,46 @@ def run_ours(args):
     ms_dev, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=(rank == 0))
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup // 2, 1))
 
-    # roofline of the dominant kernel (tcgen05 token GEMM): one instrumented eager step, CUDA events on the launching stream
-    roof = None
+    # roofline of the dominant kernel: one instrumented eager step, every library call bracketed by CUDA events on the
+    # launching stream (each L.call enqueues exactly one kernel), grouped by entry point
+    roof, breakdown = None, None
     if rank == 0:
         evs = []
-        orig = E.gemm_bf16
 
-        def timed_gemm(A, W, bias, out, epi):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            r = orig(A, W, bias, out, epi)
-            b.record()
-            evs.append((a, b, 2.0 * A.shape[0] * W.shape[0] * A.shape[1]))
+        def timed_call(name, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig_call(name, *a)
+            e1.record()
+            evs.append((name, e0, e1, DENSE_FLOPS.get(name, lambda a: 0.0)(a)))
             return r
 
-        E.gemm_bf16 = timed_gemm
+        L.call = timed_call
         graph._body()
         torch.cuda.synchronize(dev)
-        E.gemm_bf16 = orig
-        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
-        flops = sum(f for _, _, f in evs)
+        L.call = orig_call
+        agg = {}
+        for name, e0, e1, fl in evs:
+            t = agg.setdefault(name, [0, 0.0, 0.0])
+            t[0] += 1
+            t[1] += e0.elapsed_time(e1)
+            t[2] += fl
+        total_ms = sum(t[1] for t in agg.values())
+        breakdown = {n: {"launches": t[0], "ms": round(t[1], 3), "tflops": (round(t[2] / (t[1] * 1e-3) / 1e12, 1) if t[2] and t[1] > 0 else None)}
+                     for n, t in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        dense = {n: t for n, t in agg.items() if t[2] > 0 and t[1] > 0}
         pk = peaks()
-        achieved = flops / (gemm_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all launches of one step)", "achieved": achieved,
-                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " sustained",
-                "launches_per_step": len(evs), "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / (ms_dev / args.steps)}
+        if dense:
+            top = max(dense, key=lambda n: dense[n][1])
+            cnt, ms, fl = dense[top]
+            achieved = fl / (ms * 1e-3) / 1e12
+            all_ms = sum(t[1] for t in dense.values())
+            all_fl = sum(t[2] for t in dense.values())
+            roof = {"bound": "tensor", "kernel": f"{top} (tcgen05; all {cnt} launches of one step)", "achieved": achieved,
+                    "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " sustained",
+                    "launches_per_step": cnt, "ms_per_step_in_kernel": ms, "share_of_step": ms / total_ms,
+                    "all_dense_kernels": {"achieved": all_fl / (all_ms * 1e-3) / 1e12, "frac": all_fl / (all_ms * 1e-3) / 1e12 / pk["bf16"],
+                                          "share_of_step": all_ms / total_ms}}
 
     if rank == 0:
         cpu_rate, cpu_dt, cores = cpu_reference_rate(args.cpu_sample, steps=1, warmup=0) if world == 1 and not args.skip_cpu else (None, None, None)
@@ -259,7 +288,7 @@ def run_ours(args):
                        "cuda_graph": True, "l2": "per-step activation working set (~20 GB) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "roofline": roof,
+            "clocks": clocks, "roofline": roof, "kernels": breakdown,
             "flops_per_traj_gemm": gemm_flops_per_traj(), "tflops_e2e": value * gemm_flops_per_traj() / 1e12,
         }
         if cpu_rate is not None:

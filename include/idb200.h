@@ -227,6 +227,25 @@ int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t B, int L, 
 int idb200_mlp_fused(const void* a, const void* W1, const float* b1, const void* W2, const float* b2, float* h,
                      int64_t M, int d, int ff, idb200_stream_t stream);
 
+/* K3e  fused attention half of a transformer block (d_model = 256, 8 heads), src/models/transformer.py:35-41:
+ *        h[M,256] += out_proj(MHA(LayerNorm(h) * (1 + gamma) + beta))
+ * in one tcgen05 kernel per 128-token tile (LayerNorm+FiLM prologue, QKV projection, in-tile attention over the
+ * 128 / L trajectories of the tile, out projection, TMA reduce-add residual).  L | 128, M % L == 0.
+ *   gamma_beta: FiLM rows [gamma (256) | beta (256)] of trajectory m / L at stride gb_stride floats, or NULL.
+ *   wqkv_packed bf16 [768,256] / bqkv_packed fp32 [768]: in_proj rows re-ordered head-group-major, group g (heads
+ *   2g, 2g+1) = rows [Wq[64g:64g+64]; Wk[64g:64g+64]; Wv[64g:64g+64]].  wo bf16 [256,256], bo fp32 [256].
+ *   causal != 0: the -inf upper-triangular mask of transformer.py:68-71. */
+int idb200_attn_block(float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                      const void* wqkv_packed, const float* bqkv_packed, const void* wo, const float* bo, int64_t M,
+                      int L, int d, int H, int causal, idb200_stream_t stream);
+
+/* K3d' fused MLP half, src/models/transformer.py:42-45:  h[M,256] += ff.2(SiLU(ff.0(LayerNorm(h) * (1 + gamma) + beta)))
+ * = idb200_mlp_fused with the LayerNorm + FiLM prologue computed in shared memory (no [M,256] operand in HBM).
+ * L | 8 or 8 | L (trajectory length, selects the FiLM row m / L). */
+int idb200_mlp_block(float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                     const void* W1, const float* b1, const void* W2, const float* b2, int64_t M, int L, int d, int ff,
+                     idb200_stream_t stream);
+
 /* K4 (tensor-core path)  two-layer MazeEncoder conv stack of src/models/encoders.py:15-24 in one launch:
  * conv3x3(cin->c1)+SiLU on CUDA cores into a shared-memory bf16 channels-last tile, conv3x3(c1->c2)+SiLU as an
  * implicit GEMM (mma.sync bf16, fp32 accumulate), spatial mean -> pooled [B, c2].

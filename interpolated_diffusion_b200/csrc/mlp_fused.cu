@@ -12,13 +12,13 @@
 // The MMA warp runs FF1(c+2) while the 8 epilogue warps do EPI1(c) (acc1 and H are double-buffered), weights stream
 // through a 5-slot TMA ring of [128 x 64] bf16 tiles in exactly the order the MMA warp consumes them.
 // TMEM: acc2 cols [0,256), acc1 cols [256,384) / [384,512).
-#include "tc_common.cuh"
+#include "fused_common.cuh"
 
 namespace idb200 {
 using namespace tc;
+using fused::kD;
 
 namespace mlp {
-constexpr int kD = 256;                 // d_model
 constexpr int kCH = 128;                // hidden chunk
 constexpr int kThreads = 384;           // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr int kSlots = 5;
@@ -29,7 +29,7 @@ constexpr int kOffRing = kOffH + 4 * kTile;
 constexpr int kOffBar = kOffRing + kSlots * kTile;
 constexpr int kOffBias = kOffBar + 256;
 constexpr int kMaxFF = 2048;
-constexpr int kSmem = kOffBias + (kMaxFF + kD) * 4 + 1024;
+constexpr int kSmem = kOffBias + (kMaxFF + 3 * kD) * 4 + 1024;      // b1 | b2 | ln_w | ln_b
 
 struct Params {
     const float* b1;     // [ff]
@@ -37,6 +37,12 @@ struct Params {
     float* h;            // [M, 256] fp32 residual stream (in/out)
     long long M;
     int ff;
+    // LayerNorm + FiLM prologue (kLN kernels): A = LN(h) * (1 + gamma) + beta is produced in shared memory by the compute warps
+    const float* lnw;
+    const float* lnb;
+    const float* gb;
+    long long gb_stride;
+    int L;
 };
 
 __device__ __forceinline__ float silu_fast(float x) {
@@ -46,6 +52,7 @@ __device__ __forceinline__ float silu_fast(float x) {
     return fmaf(hx, t, hx);
 }
 
+template <bool kLN>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_h, const Params p) {
@@ -77,7 +84,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tma_prefetch_desc(&tmap_h);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(a_full, 1);
+        mbar_init(a_full, kLN ? 8 : 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < kSlots; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
@@ -96,6 +103,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = threadIdx.x; i < p.ff; i += kThreads) sb1[i] = p.b1[i];
     for (int i = threadIdx.x; i < kD; i += kThreads) sb2[i] = p.b2[i];
+    float* slnw = sb2 + kD;
+    float* slnb = slnw + kD;
+    if (kLN)
+        for (int i = threadIdx.x; i < kD; i += kThreads) { slnw[i] = p.lnw[i]; slnb[i] = p.lnb[i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -120,9 +131,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             };
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
                 const int m0 = static_cast<int>(tile) * 128;
-                mbar_wait(a_empty, (tile_n & 1) ^ 1, 11);
-                mbar_arrive_expect_tx(a_full, 4 * kTile);
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + kOffA + kb * kTile, &tmap_a, a_full, kb * 64, m0);
+                if (!kLN) {
+                    mbar_wait(a_empty, (tile_n & 1) ^ 1, 11);
+                    mbar_arrive_expect_tx(a_full, 4 * kTile);
+                    for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + kOffA + kb * kTile, &tmap_a, a_full, kb * 64, m0);
+                }
                 ff1(0);
                 if (nc > 1) ff1(1);
                 for (int c = 0; c < nc; ++c) {
@@ -204,8 +217,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
         uint32_t use1[2] = {0, 0}, useh[2] = {0, 0};
         uint32_t tile_n = 0;
+        if (kLN && static_cast<long long>(blockIdx.x) < tiles) {
+            fused::ln_film_tile(p.h, static_cast<long long>(blockIdx.x) * 128, p.M, p.L, p.gb, p.gb_stride, slnw, slnb, smem + kOffA, ew, lane);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_n) {
-            const long long row = tile * 128 + row_in_tile;
             for (int c = 0; c < nc; ++c) {
                 const int b = c & 1;
                 mbar_wait(&acc1_full[b], use1[b] & 1, 30);
@@ -250,39 +268,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ++use1[b];
                 ++useh[b];
             }
-            // final epilogue: h += acc2 + b2.  No read of h: the fp32 tile is staged in the (now idle) H buffers as four
-            // [128 x 32] SWIZZLE_128B boxes per 128-column round and added to global memory by TMA reduce-add, so the
-            // residual update is asynchronous and fully coalesced (out-of-range rows are clipped by the tensor map).
+            if (kLN) {
+                // LayerNorm of the next tile before this tile's final epilogue (the last FF1 has been consumed by EPI1, so the
+                // A buffer is free): FF1 of the next tile overlaps the epilogue
+                const long long next = tile + gridDim.x;
+                if (next < tiles) {
+                    mbar_wait(a_empty, tile_n & 1, 33);
+                    fused::ln_film_tile(p.h, next * 128, p.M, p.L, p.gb, p.gb_stride, slnw, slnb, smem + kOffA, ew, lane);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full);
+                }
+            }
+            // final epilogue: h += acc2 + b2 (fp32 tile staged in the idle H buffers, TMA reduce-add: fused_common.cuh)
             mbar_wait(acc2_full, tile_n & 1, 32);
             tc_fence_after();
-#pragma unroll 1
-            for (int rnd = 0; rnd < 2; ++rnd) {
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int col = rnd * 128 + half * 64 + cc * 32;
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + lane_base + col, r);
-                    tmem_ld_wait();
-                    uint8_t* box = smem + kOffH + (half * 2 + cc) * kTile;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 bv = *reinterpret_cast<const float4*>(sb2 + col + 4 * j);
-                        const float4 v = make_float4(__uint_as_float(r[4 * j + 0]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
-                                                     __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
-                        *reinterpret_cast<float4*>(box + row_in_tile * 128 + ((j ^ (row_in_tile & 7)) << 4)) = v;
-                    }
-                }
-                fence_proxy_async_smem();
-                named_barrier_sync(1, 256);
-                if (ew == 0 && lane == 0) {
-                    const int m0 = static_cast<int>(tile) * 128;
-#pragma unroll
-                    for (int bx = 0; bx < 4; ++bx) tma_reduce_add_2d(&tmap_h, smem + kOffH + bx * kTile, rnd * 128 + bx * 32, m0);
-                    tma_store_commit();
-                    tma_store_wait_read<0>();                            // staging may be overwritten after this
-                }
-                named_barrier_sync(2, 256);
-            }
+            fused::residual_epilogue(tmem_base, sb2, smem + kOffH, &tmap_h, static_cast<int>(tile) * 128, ew, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc2_empty);
@@ -301,15 +302,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }  // namespace mlp
 
 int mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* h, long long M, int d, int ff,
-              cudaStream_t st) {
-    IDB_REQUIRE(d == mlp::kD, IDB200_EUNSUPPORTED, "fused MLP is specialised for d_model = 256 (got %d)", d);
+              const float* lnw, const float* lnb, const float* gb, long long gb_stride, int L, cudaStream_t st) {
+    const bool ln = (A == nullptr);
+    IDB_REQUIRE(d == kD, IDB200_EUNSUPPORTED, "fused MLP is specialised for d_model = 256 (got %d)", d);
     IDB_REQUIRE(ff % mlp::kCH == 0 && ff >= mlp::kCH && ff <= mlp::kMaxFF, IDB200_EUNSUPPORTED, "d_ff must be a multiple of 128, <= 2048");
     IDB_REQUIRE(M >= 0, IDB200_EINVAL, "bad shape");
     if (M == 0) return IDB200_OK;
-    IDB_REQUIRE(A && W1 && b1 && W2 && b2 && h, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(W1 && b1 && W2 && b2 && h, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(aligned(h, 16), IDB200_EALIGN, "h must be 16-byte aligned");
+    if (ln) {
+        IDB_REQUIRE(lnw && lnb, IDB200_EINVAL, "NULL LayerNorm parameters");
+        IDB_REQUIRE(L >= 1 && M % L == 0, IDB200_EINVAL, "M must be a multiple of L");
+        IDB_REQUIRE(L >= 8 ? (L % 8 == 0) : (8 % L == 0), IDB200_EUNSUPPORTED, "fused MLP block needs L | 8 or 8 | L (got %d)", L);
+        IDB_REQUIRE(!gb || (aligned(gb, 16) && gb_stride % 4 == 0), IDB200_EALIGN, "gamma_beta must be 16-byte aligned");
+    }
     CUtensorMap ta, t1, t2, th;
-    int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), d, 128, 64);
+    int rc = make_tmap_bf16_2d(&ta, ln ? W1 : A, ln ? static_cast<uint64_t>(ff) : static_cast<uint64_t>(M), d, 128, 64);   // unused when ln
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&t1, W1, ff, d, 128, 64);
     if (rc) return rc;
@@ -319,14 +327,16 @@ int mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, co
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(mlp::mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(mlp::mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::kSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp::mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::kSmem);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", mlp::kSmem, cudaGetErrorString(e));
         attr = true;
     }
     const long long tiles = (M + 127) / 128;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    mlp::Params p{b1, b2, h, M, ff};
-    mlp::mlp_fused_kernel<<<grid, mlp::kThreads, mlp::kSmem, st>>>(ta, t1, t2, th, p);
+    mlp::Params p{b1, b2, h, M, ff, lnw, lnb, gb, gb_stride, L};
+    if (ln) mlp::mlp_fused_kernel<true><<<grid, mlp::kThreads, mlp::kSmem, st>>>(ta, t1, t2, th, p);
+    else mlp::mlp_fused_kernel<false><<<grid, mlp::kThreads, mlp::kSmem, st>>>(ta, t1, t2, th, p);
     return check_launch("mlp_fused_kernel");
 }
 
@@ -334,5 +344,12 @@ int mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, co
 
 extern "C" int idb200_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* h,
                                 int64_t M, int d, int ff, idb200_stream_t stream) {
-    return idb200::mlp_fused(A, W1, b1, W2, b2, h, M, d, ff, static_cast<cudaStream_t>(stream));
+    IDB_REQUIRE(A != nullptr, IDB200_EINVAL, "NULL pointer");
+    return idb200::mlp_fused(A, W1, b1, W2, b2, h, M, d, ff, nullptr, nullptr, nullptr, 0, 1, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int idb200_mlp_block(float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                                const void* W1, const float* b1, const void* W2, const float* b2, int64_t M, int L, int d, int ff,
+                                idb200_stream_t stream) {
+    return idb200::mlp_fused(nullptr, W1, b1, W2, b2, h, M, d, ff, ln_w, ln_b, gamma_beta, gb_stride, L, static_cast<cudaStream_t>(stream));
 }

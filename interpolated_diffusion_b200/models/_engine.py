@@ -45,6 +45,22 @@ def mlp_fused(a: torch.Tensor, W1: torch.Tensor, b1: torch.Tensor, W2: torch.Ten
     return h
 
 
+def attn_block(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], wqkv_g, bqkv_g, wo, bo, Lseq: int, H: int, causal: bool):
+    """h += out_proj(MHA(LN(h) * (1 + gamma) + beta)) in one kernel (idb200_attn_block; d_model = 256, L | 128)."""
+    M, d = h.shape
+    L.call("idb200_attn_block", h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), L.ptr(gb), 0 if gb is None else gb.stride(0),
+           wqkv_g.data_ptr(), bqkv_g.data_ptr(), wo.data_ptr(), bo.data_ptr(), M, Lseq, d, H, int(causal), L.stream(h.device))
+    return h
+
+
+def mlp_block(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], W1, b1, W2, b2, Lseq: int):
+    """h += ff.2(SiLU(ff.0(LN(h) * (1 + gamma) + beta))) in one kernel (idb200_mlp_block; d_model = 256)."""
+    M, d = h.shape
+    L.call("idb200_mlp_block", h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), L.ptr(gb), 0 if gb is None else gb.stride(0),
+           W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), M, Lseq, d, W1.shape[0], L.stream(h.device))
+    return h
+
+
 def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((rows, dim), device=device, dtype=torch.float32)
     L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))
@@ -90,6 +106,7 @@ class PackedEncoder:
         self._key = None
         self.ws = Workspace()
         self.fuse_mlp = True            # d_model == 256: FF1 + SiLU + FF2 + residual in one kernel
+        self.fuse_blocks = True         # d_model == 256, 8 heads, L | 128: two kernels per layer (attn_block, mlp_block)
 
     def _pack(self):
         layers = self.enc.layers
@@ -111,6 +128,11 @@ class PackedEncoder:
             }
             for k in ("wqkv", "wo", "w1", "w2"):
                 e[k] = e[k + "32"].to(torch.bfloat16).contiguous()
+            if d % 64 == 0:
+                # head-group-major in_proj for the fused attention block: group g = [Wq[64g:64g+64]; Wk[..]; Wv[..]]
+                order = torch.cat([torch.arange(64) + part * d + g * 64 for g in range(d // 64) for part in range(3)]).to(e["wqkv"].device)
+                e["wqkv_g"] = e["wqkv"][order].contiguous()
+                e["bqkv_g"] = e["bqkv"][order].contiguous()
             self.layers.append(e)
             if l.film1 is not None:
                 film_w += [l.film1.weight.detach().float(), l.film2.weight.detach().float()]
@@ -140,13 +162,21 @@ class PackedEncoder:
         H, ff = self.n_heads, self.ff
         causal = bool(self.enc.causal)
         if precision == "bf16":
-            a = self.ws.get("a", (M, d), torch.bfloat16, dev)
-            qkv = self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
             fuse_mlp = self.fuse_mlp and d == 256 and ff % 128 == 0 and ff <= 2048
+            fuse_attn = self.fuse_blocks and d == 256 and H == 8 and 128 % Lseq == 0 and M % Lseq == 0
+            fuse_ln_mlp = self.fuse_blocks and fuse_mlp and (Lseq % 8 == 0 or 8 % Lseq == 0)
+            fused = fuse_attn and fuse_ln_mlp
+            if not fused:
+                a = self.ws.get("a", (M, d), torch.bfloat16, dev)
+                qkv = self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
             f = None if fuse_mlp else self.ws.get("f", (M, ff), torch.bfloat16, dev)
             for i, e in enumerate(self.layers):
                 g1 = film[:, 2 * i] if film is not None else None
                 g2 = film[:, 2 * i + 1] if film is not None else None
+                if fused:
+                    attn_block(h, e["n1w"], e["n1b"], g1, e["wqkv_g"], e["bqkv_g"], e["wo"], e["bo"], Lseq, H, causal)
+                    mlp_block(h, e["n2w"], e["n2b"], g2, e["w1"], e["b1"], e["w2"], e["b2"], Lseq)
+                    continue
                 ln_film(h, e["n1w"], e["n1b"], g1, a, Lseq)
                 gemm_bf16(a, e["wqkv"], e["bqkv"], qkv, EPI_BF16)
                 attention(qkv, a, B, Lseq, H, causal)                    # `a` is free again: reuse as attention output

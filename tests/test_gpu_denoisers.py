@@ -178,3 +178,41 @@ def test_causal_long_horizon_vs_oracle():
     m.precision = "fp32"
     got = m(x.cuda(), s.cuda(), mask.cuda(), _cuda(cond))
     assert _maxabs(got, ref) < 1e-4, _maxabs(got, ref)
+
+
+@pytest.mark.parametrize("Lseq,B,causal", [(8, 37, False), (64, 5, False), (64, 3, True), (16, 9, False), (32, 4, True),
+                                           (128, 3, False), (4, 70, False), (1, 130, False)])
+def test_fused_transformer_blocks_vs_oracle(Lseq, B, causal):
+    """idb200_attn_block + idb200_mlp_block (two kernels per layer, LN/FiLM/QKV/attention/out-proj and LN/FiLM/MLP fused)
+    against the CPU oracle of transformer.py:35-46 and against the unfused kernel sequence; ragged last tile
+    (B*L not a multiple of 128), FiLM on, bidirectional and causal."""
+    from interpolated_diffusion_b200.models.transformer import TransformerEncoder
+    torch.manual_seed(7 + Lseq)
+    enc = TransformerEncoder(d_model=256, n_layers=2, n_heads=8, d_ff=1024, cond_dim=128, causal=causal)
+    with torch.no_grad():
+        for l in enc.layers:      # non-trivial LayerNorm affine / biases (default init is 1 / 0)
+            for p_ in (l.norm1.weight, l.norm2.weight):
+                p_.add_(0.1 * torch.randn_like(p_))
+            for p_ in (l.norm1.bias, l.norm2.bias, l.attn.in_proj_bias, l.attn.out_proj.bias):
+                p_.add_(0.1 * torch.randn_like(p_))
+    sd = {"transformer.layers." + k[len("layers."):]: v.clone() for k, v in enc.state_dict().items()}
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn((B, Lseq, 256), generator=gen)
+    cv = torch.randn((B, 128), generator=gen)
+    ref = odn.transformer_encoder(x, cv, sd, 8, causal)
+    enc = enc.cuda()
+    pk = enc.packed()
+    assert pk.fuse_blocks
+    got = enc(x.cuda(), cv.cuda())
+    pk.fuse_blocks = False
+    unfused = enc(x.cuda(), cv.cuda())
+    pk.fuse_blocks = True
+    scale = ref.abs().max().item()
+    assert _maxabs(got, ref) < 2e-2 * max(1.0, scale / 4), (_maxabs(got, ref), scale)
+    assert _maxabs(got, unfused) < 2e-2 * max(1.0, scale / 4), _maxabs(got, unfused)
+    # no FiLM
+    enc2 = TransformerEncoder(d_model=256, n_layers=1, n_heads=8, d_ff=1024, cond_dim=None, causal=causal)
+    sd2 = {"transformer.layers." + k[len("layers."):]: v.clone() for k, v in enc2.state_dict().items()}
+    ref2 = odn.transformer_encoder(x, None, sd2, 8, causal)
+    got2 = enc2.cuda()(x.cuda(), None)
+    assert _maxabs(got2, ref2) < 2e-2 * max(1.0, ref2.abs().max().item() / 4), _maxabs(got2, ref2)

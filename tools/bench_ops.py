@@ -39,9 +39,13 @@ for L in (8, 64):
     timeit(f"qkv gemm M={M}", lambda: E.gemm_bf16(a, Wq, bq, qkv, 0))
     Wo = (torch.randn((d, d), device=dev) * 0.06).bfloat16()
     timeit(f"outproj gemm M={M}", lambda: E.gemm_bf16(a, Wo, b2, h, 2))
+    timeit(f"attn_block L={L} M={M}", lambda: E.attn_block(h, w, bb, gb, Wq, bq, Wo, b2, L, H, False))
+    timeit(f"mlp_block L={L} M={M}", lambda: E.mlp_block(h, w, bb, gb, W1, b1, W2, b2, L))
     del a, h, qkv, o
 occ = (torch.rand((B, 1, 21, 21), device=dev) < 0.2).float()
 ws = [torch.randn((32, 1, 3, 3), device=dev) * 0.3, torch.randn((64, 32, 3, 3), device=dev) * 0.06]
 bs = [torch.zeros(32, device=dev), torch.zeros(64, device=dev)]
 timeit("conv_encoder", lambda: E.conv_encoder(occ, None, ws, bs), it=2)
+w1p = ws[1].permute(0, 2, 3, 1).reshape(64, 9 * 32).contiguous().bfloat16()
+timeit("conv_encoder_tc", lambda: E.conv_encoder_tc(occ, None, ws[0], bs[0], w1p, bs[1]), it=2)
 print(json.dumps(res, indent=1))
