@@ -246,6 +246,20 @@ int idb200_mlp_block(float* h, const float* ln_w, const float* ln_b, const float
                      const void* W1, const float* b1, const void* W2, const float* b2, int64_t M, int L, int d, int ff,
                      idb200_stream_t stream);
 
+/* K3f  the whole TransformerEncoder (every layer of src/models/transformer.py:73-82) in ONE persistent tcgen05 kernel,
+ * d_model = 256, 8 heads, d_ff % 128 == 0 (<= 1024), L | 128, M % L == 0.  A CTA carries a 128-token tile through all
+ * layers with the fp32 residual stream resident in tensor memory; h is read and written once.
+ *   layer_params fp32, per layer: [ln1_w 256 | ln1_b 256 | cb1 256 | bqkv_packed 768 | ln2_w 256 | ln2_b 256 | cb2 256 | 0.5 * b1 (ff)]
+ *     cb1 / cb2 = sum of the out_proj / ff.2 biases of everything accumulated into h before that LayerNorm
+ *     (the accumulating GEMMs never add their bias; LayerNorm reads h + cb), bias_total [256] = the final sum.
+ *   gamma_beta: FiLM rows of trajectory m / L at stride gb_stride floats, [2 * n_layers][gamma 256 | beta 256]
+ *     (row 2l = film1 of layer l, 2l+1 = film2), or NULL.
+ *   wqkv_packed bf16 [n_layers*768, 256] (per layer head-group-major, see idb200_attn_block), wo bf16 [n_layers*256, 256],
+ *   w1 bf16 [n_layers*ff, 256], w2 bf16 [n_layers*256, ff]. */
+int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_total, const float* gamma_beta,
+                         int64_t gb_stride, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
+                         int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream);
+
 /* K4 (tensor-core path)  two-layer MazeEncoder conv stack of src/models/encoders.py:15-24 in one launch:
  * conv3x3(cin->c1)+SiLU on CUDA cores into a shared-memory bf16 channels-last tile, conv3x3(c1->c2)+SiLU as an
  * implicit GEMM (mma.sync bf16, fp32 accumulate), spatial mean -> pooled [B, c2].

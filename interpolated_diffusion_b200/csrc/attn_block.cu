@@ -61,6 +61,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __grid_co
                   const __grid_constant__ CUtensorMap tmap_wo_b, const __grid_constant__ CUtensorMap tmap_h, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    __builtin_assume(__isShared(smem));             // keep LDS / STS (the integer round trip hides the address space)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* x_full = bars + 0;
     uint64_t* x_empty = bars + 1;

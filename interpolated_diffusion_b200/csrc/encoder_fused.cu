@@ -1,0 +1,722 @@
+// K3f: the WHOLE TransformerEncoder (all layers) of both denoisers in ONE persistent kernel, d_model = 256, 8 heads.
+//
+//     for each layer:  h += out_proj(MHA(LN1(h) (1+g1) + b1'));   h += ff2(SiLU(ff1(LN2(h) (1+g2) + b2')))
+//
+// Reference: src/models/transformer.py:35-46 (TransformerBlock.forward) iterated by :73-82 (TransformerEncoder).
+//
+// A 128-token tile (128 / L whole trajectories) never interacts with another tile, so a CTA carries its tile
+// through every layer with the fp32 residual stream RESIDENT IN TENSOR MEMORY: h = TMEM columns [0,256).  The
+// out-projection and FF2 MMAs accumulate straight onto h (the residual add is the accumulate flag), LayerNorm reads
+// h back with tcgen05.ld in the accumulator's natural thread-per-row layout (row statistics are in-thread sums, no
+// shuffles), and HBM sees one fp32 read and one write of h per tile for the whole encoder (the two-kernels-per-layer
+// path moved 4 KB per token per layer).  The biases of the accumulating GEMMs (b_o, b_2) are never added to TMEM:
+// the host passes their running sums cb (pending bias before each LayerNorm) and the kernel reads h + cb.
+//
+// One CTA per SM, 640 threads: warp 0 TMA producer (weights, 5-slot ring of [128 x 64] bf16 tiles, in exactly the
+// order the MMA warp consumes them, free-running across phases/layers), warp 1 tcgen05.mma issuer, warp 2 TMEM
+// allocator, warp 3 per-layer parameter loader (cp.async.bulk 1-D), warps 4..19 compute (thread <-> tile row x
+// column quarter: 4 warps per SM sub-partition hide the TMEM / shared-memory / MUFU latencies of each other).
+// Per layer:
+//   LN1   compute: h(+cb1) -> LayerNorm, FiLM -> X (bf16 K-major SWIZZLE_128B A operand, 64 KB)
+//   for head group g = 0..3:
+//     GEMM_g  acc (TMEM cols 256..447) = X . [Wq_g;Wk_g;Wv_g]^T                 16 x (N=128 + N=64) tcgen05.mma
+//     EPI_g   compute: acc + bias -> bf16 q|k|v rows in shared memory
+//     ATT_g   compute: softmax(q k^T / sqrt(32)) v per (16-row block, head), mma.sync + ldmatrix -> O_g (A operand)
+//     OUT_g   h (TMEM cols 0..255) += O_g . Wo[:, 64g..64g+63]^T                2 x 4 tcgen05.mma N=128
+//   LN2   compute: h(+cb2) -> X
+//   for hidden chunk c = 0..ff/128-1:
+//     FF1_c   acc1[c&1] (TMEM cols 256.. / 384..) = X . W1[128c.., :]^T
+//     EPI1_c  compute: acc1 + b1 -> SiLU -> bf16 H[c&1] (A operand)
+//     FF2_c   h += H[c&1] . W2[:, 128c..]^T
+// GEMM_{g+1} overlaps ATT_g, FF1_{c+2} overlaps EPI1_c; the shared-memory scratch (q|k|v staging + O, or H) and the
+// TMEM scratch columns [256,512) are time-shared by the two phases (ordered by the x_full / h_ready barriers).
+#include <cstdlib>
+
+#include "fused_common.cuh"
+
+namespace idb200 {
+using namespace tc;
+using namespace fused;
+
+namespace ef {
+constexpr int kThreads = 640;
+constexpr int kCW = 16;                             // compute warps
+constexpr int kCT = kCW * 32;                       // compute threads (named-barrier width)
+constexpr int kSlots = 5;
+constexpr int kSlotBytes = kTile;                   // [128 x 64] bf16 (the V tile [64 x 64] uses half a slot)
+constexpr int kMaxFF = 1024;
+constexpr int kOffX = 0;                            // 4 x [128 x 64] bf16
+constexpr int kOffS = 4 * kTile;                    // scratch: q|k|v staging (51200) + O (16384)  |  H[2][2] (65536)
+constexpr int kOffQkv = kOffS;
+constexpr int kOffO = kOffS + 128 * kPitch * 2;
+constexpr int kOffH = kOffS;
+constexpr int kOffRing = kOffO + kTile;
+constexpr int kOffBar = kOffRing + kSlots * kSlotBytes;
+constexpr int kOffStat = kOffO + 12288;             // float2 [4][128] LayerNorm partial statistics: the tail of the O tile, idle
+                                                    // while a LayerNorm runs (every MMA reading O / H has completed: h_ready)
+constexpr int kOffPA = kOffBar + 256;             // ln1_w 256 | ln1_b 256 | cb1 256 | bqkv 768
+constexpr int kPAFloats = 1536;
+constexpr int kOffPM = kOffPA + kPAFloats * 4;      // ln2_w 256 | ln2_b 256 | cb2 256 | b1 ff
+constexpr int kPMFloatsMax = 768 + kMaxFF;
+constexpr int kSmem = kOffPM + kPMFloatsMax * 4 + 1024;
+static_assert(kOffO % 1024 == 0 && kOffRing % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
+static_assert(kOffH + 4 * kTile <= kOffRing, "H buffers fit the scratch region");
+static_assert(kSmem <= 232448, "shared memory budget");
+
+constexpr uint32_t kColAcc = 256;                   // TMEM scratch columns
+
+struct Params {
+    float* h;                   // [M, 256] fp32 residual stream (in/out)
+    const float* params;        // per layer: PA (1536 floats) | PM (768 + ff floats)
+    const float* cb_total;      // [256] sum of all accumulate-GEMM biases (added when h is written back)
+    const float* gb;            // FiLM [B, 2 * n_layers, 512] rows = [gamma | beta] per LayerNorm, or nullptr
+    long long gb_stride;        // floats between trajectories
+    long long M;
+    int L;
+    int causal;
+    int ff;
+    int n_layers;
+    unsigned long long* prof;   // dev: [P_N] cycle sums (kProf kernels only)
+};
+
+// SiLU(acc + b) = hx * tanh(hx) + hx with hx = 0.5 * (acc + b); hb = 0.5 * b
+__device__ __forceinline__ float silu_half(float acc, float hb) {
+    const float hx = fmaf(acc, 0.5f, hb);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+    return fmaf(hx, t, hx);
+}
+
+// LayerNorm(eps 1e-5) * (1 + gamma) + beta of the tile's rows, read from the TMEM-resident residual stream.
+// Thread <-> (row, column quarter `part`): statistics are in-thread sums over 64 columns (shifted by the first element)
+// merged with the other three quarters' through shared memory (Chan's formula).  Output: the bf16 SWIZZLE_128B
+// k-block `part` of the A operand X.
+// film: this thread's trajectory FiLM row [gamma 256 | beta 256] -- in shared memory (kFilmSmem: staged by bulk copies,
+// wait on film_full before the first read) or in global memory -- or nullptr (no FiLM / dead row).
+template <bool kFilmSmem>
+__device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const float* sb, const float* scb, const float* film,
+                                     uint64_t* film_full, uint32_t film_parity, float2* stat, uint8_t* X, int row, int part, long long* tt) {
+    __builtin_assume(__isShared(sw));
+    __builtin_assume(__isShared(sb));
+    __builtin_assume(__isShared(scb));
+    __builtin_assume(__isShared(stat));
+    __builtin_assume(__isShared(X));
+    if (kFilmSmem && film != nullptr) __builtin_assume(__isShared(film));
+    const int c0 = part * 64;
+    const uint32_t t0 = tmem_row + c0;
+    // ---- pass 1: statistics (both 32-column loads in flight) ----
+    float xs, s1 = 0.0f, s2 = 0.0f;
+    {
+        uint32_t r[2][32];
+        tmem_ld_32x32(t0, r[0]);
+        tmem_ld_32x32(t0 + 32, r[1]);
+        tmem_ld_wait();
+        const float4* cb4 = reinterpret_cast<const float4*>(scb + c0);
+        xs = __uint_as_float(r[0][0]) + cb4[0].x;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 cb = cb4[u * 8 + j];
+                const float d0 = __uint_as_float(r[u][4 * j + 0]) + (cb.x - xs), d1 = __uint_as_float(r[u][4 * j + 1]) + (cb.y - xs);
+                const float d2 = __uint_as_float(r[u][4 * j + 2]) + (cb.z - xs), d3 = __uint_as_float(r[u][4 * j + 3]) + (cb.w - xs);
+                s1 += (d0 + d1) + (d2 + d3);
+                s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+            }
+    }
+    stat[part * 128 + row] = make_float2(xs + s1 * (1.0f / 64.0f), s2 - s1 * s1 * (1.0f / 64.0f));
+    if (tt) tt[0] = clock64();
+    named_barrier_sync(3, kCT);
+    if (tt) tt[1] = clock64();
+    float mean = 0.0f, m2 = 0.0f;
+    float2 st[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { st[i] = stat[i * 128 + row]; mean += st[i].x; m2 += st[i].y; }
+    mean *= 0.25f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float dm = st[i].x - mean; m2 = fmaf(dm * dm, 64.0f, m2); }
+    const float rstd = rsqrtf(fmaxf(m2 * (1.0f / 256.0f), 0.0f) + 1e-5f);
+    const float shift = -mean * rstd;
+    if (kFilmSmem) mbar_wait(film_full, film_parity, 58);
+    if (tt) tt[2] = clock64();
+    // ---- pass 2: normalise, FiLM, pack (the second 32-column load is in flight while the first is processed) ----
+    uint32_t r[2][32];
+    tmem_ld_32x32(t0, r[0]);
+    tmem_ld_32x32(t0 + 32, r[1]);
+    uint8_t* xt = X + part * kTile;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld_wait();
+        const int col = c0 + cc * 32;
+        const float4* cb4 = reinterpret_cast<const float4*>(scb + col);
+        const float4* w4 = reinterpret_cast<const float4*>(sw + col);
+        const float4* b4 = reinterpret_cast<const float4*>(sb + col);
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {                                 // 8 columns -> one 16-byte swizzle chunk
+            float y[8];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = j2 * 2 + u;
+                const float4 cb = cb4[j], w = w4[j], b = b4[j];
+                // ((x + cb) - mean) * rstd = x * rstd + (cb * rstd + shift)
+                y[4 * u + 0] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 0]), rstd, fmaf(cb.x, rstd, shift)), w.x, b.x);
+                y[4 * u + 1] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 1]), rstd, fmaf(cb.y, rstd, shift)), w.y, b.y);
+                y[4 * u + 2] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 2]), rstd, fmaf(cb.z, rstd, shift)), w.z, b.z);
+                y[4 * u + 3] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 3]), rstd, fmaf(cb.w, rstd, shift)), w.w, b.w);
+                if (film != nullptr) {
+                    const float4* f4 = reinterpret_cast<const float4*>(film + col) + j;
+                    const float4 g = kFilmSmem ? f4[0] : __ldg(f4);
+                    const float4 t = kFilmSmem ? f4[64] : __ldg(f4 + 64);
+                    y[4 * u + 0] = fmaf(y[4 * u + 0], 1.0f + g.x, t.x);
+                    y[4 * u + 1] = fmaf(y[4 * u + 1], 1.0f + g.y, t.y);
+                    y[4 * u + 2] = fmaf(y[4 * u + 2], 1.0f + g.z, t.z);
+                    y[4 * u + 3] = fmaf(y[4 * u + 3], 1.0f + g.w, t.w);
+                }
+            }
+            uint4 pk;
+            pk.x = pack2_bf16(y[0], y[1]);
+            pk.y = pack2_bf16(y[2], y[3]);
+            pk.z = pack2_bf16(y[4], y[5]);
+            pk.w = pack2_bf16(y[6], y[7]);
+            *reinterpret_cast<uint4*>(xt + sw128_offset(row, cc * 32 + 8 * j2)) = pk;
+        }
+    }
+}
+
+// kProf (dev, IDB200_PROF=1): compute warp 0 lane 0 accumulates clock64() spans per phase into p.prof[0..15]
+enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_N };
+
+template <bool kProf>
+__global__ void __launch_bounds__(kThreads, 1)
+encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
+                     const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_w1,
+                     const __grid_constant__ CUtensorMap tm_w2, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    __builtin_assume(__isShared(smem));             // the integer round trip hides the address space: keep LDS / STS, not generic LD / ST
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    uint64_t* x_full = bars + 0;                    // compute -> MMA: X (LayerNorm output) written          (kCW arrivals)
+    uint64_t* h_ready = bars + 1;                   // MMA -> compute: every accumulate into h has completed (commit)
+    uint64_t* slot_full = bars + 2;                 // [kSlots]
+    uint64_t* slot_empty = slot_full + kSlots;      // [kSlots]
+    uint64_t* acc_full = slot_empty + kSlots;
+    uint64_t* acc_empty = acc_full + 1;
+    uint64_t* o_full = acc_empty + 1;
+    uint64_t* o_empty = o_full + 1;
+    uint64_t* acc1_full = o_empty + 1;              // [2]
+    uint64_t* acc1_empty = acc1_full + 2;           // [2]
+    uint64_t* hb_full = acc1_empty + 2;             // [2]
+    uint64_t* hb_empty = hb_full + 2;               // [2]
+    uint64_t* pa_full = hb_empty + 2;
+    uint64_t* pa_empty = pa_full + 1;
+    uint64_t* pm_full = pa_empty + 1;
+    uint64_t* pm_empty = pm_full + 1;
+    uint64_t* film_full = pm_empty + 1;             // FiLM rows of the next LayerNorm staged in the scratch region (tx bytes)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(film_full + 1);
+    float2* stat = reinterpret_cast<float2*>(smem + kOffStat);
+    float* sPA = reinterpret_cast<float*>(smem + kOffPA);
+    float* sPM = reinterpret_cast<float*>(smem + kOffPM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nc = p.ff / 128;
+    const int NL = p.n_layers;
+    const long long tiles = (p.M + 127) / 128;
+    const int pm_floats = 768 + p.ff;
+    const int layer_floats = kPAFloats + pm_floats;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qk);
+        tma_prefetch_desc(&tm_v);
+        tma_prefetch_desc(&tm_wo);
+        tma_prefetch_desc(&tm_w1);
+        tma_prefetch_desc(&tm_w2);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(x_full, kCW);
+        mbar_init(h_ready, 1);
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, kCW);
+        mbar_init(o_full, kCW);
+        mbar_init(o_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc1_full[i], 1);
+            mbar_init(&acc1_empty[i], kCW);
+            mbar_init(&hb_full[i], kCW);
+            mbar_init(&hb_empty[i], 1);
+        }
+        mbar_init(pa_full, 1);
+        mbar_init(pa_empty, kCW);
+        mbar_init(pm_full, 1);
+        mbar_init(pm_empty, kCW);
+        mbar_init(film_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_h = tmem_base;
+    const uint32_t tmem_acc = tmem_base + kColAcc;
+
+    if (warp == 0) {
+        // ===================== TMA producer (weights) =====================
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t sphase = 0;
+            auto load = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
+                mbar_wait(&slot_empty[slot], sphase ^ 1, 10);
+                mbar_arrive_expect_tx(&slot_full[slot], bytes);
+                tma_load_2d(smem + kOffRing + slot * kSlotBytes, m, &slot_full[slot], c0, c1);
+                if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+            };
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int l = 0; l < NL; ++l) {
+                    auto qkv = [&](int g) {
+#pragma unroll 1
+                        for (int kb = 0; kb < 4; ++kb) {
+                            load(&tm_qk, kb * 64, l * 768 + g * 192, kTile);
+                            load(&tm_v, kb * 64, l * 768 + g * 192 + 128, kTile / 2);
+                        }
+                    };
+                    auto wo = [&](int g) {
+                        load(&tm_wo, g * 64, l * 256, kTile);
+                        load(&tm_wo, g * 64, l * 256 + 128, kTile);
+                    };
+                    auto ff1 = [&](int c) {
+#pragma unroll 1
+                        for (int kb = 0; kb < 4; ++kb) load(&tm_w1, kb * 64, l * p.ff + c * 128, kTile);
+                    };
+                    auto ff2 = [&](int c) {
+#pragma unroll 1
+                        for (int i = 0; i < 4; ++i) load(&tm_w2, c * 128 + (i & 1) * 64, l * 256 + (i >> 1) * 128, kTile);
+                    };
+                    // attention half: G0 G1 O0 G2 O1 G3 O2 O3 (rolled: one copy of each body keeps the code small)
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) {
+                        if ((0x2Bu >> i) & 1u) qkv(i < 2 ? i : (i + 1) >> 1);
+                        else wo(i < 7 ? (i >> 1) - 1 : 3);
+                    }
+#pragma unroll 1
+                    for (int c = -2; c < nc; ++c) {
+                        if (c >= 0) ff2(c);
+                        if (c + 2 < nc) ff1(c + 2);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
+            constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
+            int slot = 0;
+            uint32_t sphase = 0, n_x = 0, n_acc = 0, n_o = 0;
+            uint32_t use1[2] = {0, 0}, useh[2] = {0, 0};
+            const uint32_t sX = smem_u32(smem + kOffX), sO = smem_u32(smem + kOffO), sH = smem_u32(smem + kOffH), sR = smem_u32(smem + kOffRing);
+            // 4 x (K = 16) MMAs of one [.. x 64] k-block: A tile at a_addr, B = the current ring slot
+            auto mma_slot = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, bool first_zero, int tag) {
+                mbar_wait(&slot_full[slot], sphase, tag);
+                tc_fence_after();
+                const uint64_t ad = umma_desc_sw128(a_addr);
+                const uint64_t bd = umma_desc_sw128(sR + slot * kSlotBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
+                umma_commit(&slot_empty[slot]);
+                if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+            };
+            auto gemm = [&](int g) {
+                mbar_wait(acc_empty, (n_acc & 1) ^ 1, 20);              // EPI of the previous group drained the accumulator
+                tc_fence_after();
+#pragma unroll 1
+                for (int kb = 0; kb < 4; ++kb) {
+                    mma_slot(tmem_acc, sX + kb * kTile, idesc128, kb == 0, 21);          // q | k  (128 columns)
+                    mma_slot(tmem_acc + 128, sX + kb * kTile, idesc64, kb == 0, 22);     // v      (64 columns)
+                }
+                umma_commit(acc_full);
+                ++n_acc;
+            };
+            auto outp = [&](int g) {
+                mbar_wait(o_full, n_o & 1, 23);                          // ATT_g wrote O_g
+                tc_fence_after();
+                mma_slot(tmem_h, sO, idesc128, false, 24);               // h[:, 0:128]   += O_g . Wo[0:128, 64g..]^T
+                mma_slot(tmem_h + 128, sO, idesc128, false, 25);         // h[:, 128:256] += O_g . Wo[128:256, 64g..]^T
+                umma_commit(o_empty);
+                if (g == 3) umma_commit(h_ready);
+                ++n_o;
+            };
+            auto ff1 = [&](int c) {
+                const int b = c & 1;
+                mbar_wait(&acc1_empty[b], (use1[b] & 1) ^ 1, 26);       // EPI1 drained acc1[b]
+                tc_fence_after();
+#pragma unroll 1
+                for (int kb = 0; kb < 4; ++kb) mma_slot(tmem_acc + b * 128, sX + kb * kTile, idesc128, kb == 0, 27);
+                umma_commit(&acc1_full[b]);
+                ++use1[b];
+            };
+            auto ff2 = [&](int c) {
+                const int b = c & 1;
+                mbar_wait(&hb_full[b], useh[b] & 1, 28);                 // EPI1 wrote H[b]
+                tc_fence_after();
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) mma_slot(tmem_h + (i >> 1) * 128, sH + (b * 2 + (i & 1)) * kTile, idesc128, false, 29);
+                umma_commit(&hb_empty[b]);
+                if (c == nc - 1) umma_commit(h_ready);
+                ++useh[b];
+            };
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int l = 0; l < NL; ++l) {
+                    mbar_wait(x_full, n_x & 1, 30);
+                    ++n_x;
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) {                        // G0 G1 O0 G2 O1 G3 O2 O3
+                        if ((0x2Bu >> i) & 1u) gemm(i < 2 ? i : (i + 1) >> 1);
+                        else outp(i < 7 ? (i >> 1) - 1 : 3);
+                    }
+                    mbar_wait(x_full, n_x & 1, 31);
+                    ++n_x;
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = -2; c < nc; ++c) {
+                        if (c >= 0) ff2(c);
+                        if (c + 2 < nc) ff1(c + 2);
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== per-layer parameter loader =====================
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                for (int l = 0; l < NL; ++l, ++n) {
+                    const float* src = p.params + static_cast<long long>(l) * layer_floats;
+                    mbar_wait<true>(pa_empty, (n & 1) ^ 1, 40);
+                    mbar_arrive_expect_tx(pa_full, kPAFloats * 4);
+                    bulk_load_1d(sPA, src, kPAFloats * 4, pa_full);
+                    mbar_wait<true>(pm_empty, (n & 1) ^ 1, 41);
+                    mbar_arrive_expect_tx(pm_full, pm_floats * 4);
+                    bulk_load_1d(sPM, src + kPAFloats, pm_floats * 4, pm_full);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== compute warps =====================
+        const int ew = warp - 4;
+        const int q = ew & 3, part = ew >> 2;            // TMEM lane quadrant (warp % 4), column quarter
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t tmem_row = tmem_h + lane_base;
+        const __nv_bfloat16* sq = reinterpret_cast<const __nv_bfloat16*>(smem + kOffQkv);
+        uint8_t* sqb = smem + kOffQkv;
+        uint8_t* so = smem + kOffO;
+        const int L = p.L;
+        uint32_t n_acc = 0, n_o = 0, n_h = 0, n_p = 0, n_film = 0;
+        uint32_t use1[2] = {0, 0}, useh[2] = {0, 0};
+        unsigned long long pacc[P_N] = {};
+        long long tprev = kProf ? clock64() : 0;
+        auto stamp = [&](int what) {
+            if (kProf) {
+                const long long t = clock64();
+                pacc[what] += static_cast<unsigned long long>(t - tprev);
+                tprev = t;
+            }
+        };
+        // FiLM staging (L >= 8: at most 16 trajectories per tile): one thread copies the [gamma | beta] rows of the tile's
+        // trajectories for LayerNorm `which` (0/1) of layer l into the first 32 KB of the scratch region, which is idle
+        // between the last attention read and EPI1_0 / between FF2 of the last even chunk and EPI_0.
+        const bool film_smem = (p.gb != nullptr) && L >= 8;
+        auto stage_film = [&](long long tile_, int l_, int which) {
+            if (film_smem && ew == 0 && lane == 0) {
+                const long long t0 = tile_ * 128 / L;
+                const long long left = p.M / L - t0;
+                const int nt = static_cast<int>(left < 128 / L ? left : 128 / L);
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(film_full, static_cast<uint32_t>(nt) * 2048u);
+                for (int t = 0; t < nt; ++t)
+                    bulk_load_1d(smem + kOffS + t * 2048, p.gb + (t0 + t) * p.gb_stride + (2 * l_ + which) * 512, 2048, film_full);
+            }
+        };
+        if (static_cast<long long>(blockIdx.x) < tiles) stage_film(blockIdx.x, 0, 0);
+        // attention work unit of this warp: 16-row block rb, head hh of the group
+        const int rb = ew & 7, hh = ew >> 3;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const long long m0 = tile * 128;
+            const long long m = m0 + row;
+            const bool live = m < p.M;
+            // ---- residual stream tile -> TMEM (this thread: its row, columns part*64 .. +63) ----
+            {
+                const float4* src = reinterpret_cast<const float4*>(p.h + m * kD + part * 64);
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = live ? src[cc * 8 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        r[4 * j + 0] = __float_as_uint(v.x);
+                        r[4 * j + 1] = __float_as_uint(v.y);
+                        r[4 * j + 2] = __float_as_uint(v.z);
+                        r[4 * j + 3] = __float_as_uint(v.w);
+                    }
+                    tmem_st_32x32(tmem_row + part * 64 + cc * 32, r);
+                }
+                tmem_st_wait();
+            }
+            stamp(P_LOAD);
+            // FiLM row of this thread's trajectory: global (L < 8) or staged in the scratch region (L >= 8, slot = row / L)
+            const float* gbtraj = (p.gb != nullptr && live) ? p.gb + (m / L) * p.gb_stride : nullptr;
+            const float* sfilm = (p.gb != nullptr && live) ? reinterpret_cast<const float*>(smem + kOffS) + (row / L) * 512 : nullptr;
+            for (int l = 0; l < NL; ++l, ++n_p) {
+                // ================= attention half =================
+                mbar_wait(pa_full, n_p & 1, 50);
+                stamp(P_WPA);
+                long long tt[3] = {0, 0, 0};
+                if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * 512 : nullptr, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_full);
+                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; }
+                stamp(P_LN1);
+                const float* sbqkv = sPA + 768;
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    mbar_wait(acc_full, n_acc & 1, 51);
+                    tc_fence_after();
+                    named_barrier_sync(1, kCT);                          // every warp is done reading the previous q|k|v
+                    stamp(P_WACC);
+                    // ---- EPI_g: acc + bias -> bf16 q|k|v rows (this thread: its row, 48 of the 192 columns) ----
+                    {
+                        uint32_t ra[32], rc[16];
+                        tmem_ld_32x32(tmem_acc + lane_base + part * 48, ra);
+                        tmem_ld_32x16(tmem_acc + lane_base + part * 48 + 32, rc);
+                        tmem_ld_wait();
+                        const float* bb = sbqkv + g * 192 + part * 48;
+                        uint8_t* dst = sqb + row * (kPitch * 2) + part * 96;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
+                            const uint32_t* v = (j < 4) ? &ra[8 * j] : &rc[8 * (j - 4)];
+                            uint4 pk;
+                            pk.x = pack2_bf16(__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y);
+                            pk.y = pack2_bf16(__uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w);
+                            pk.z = pack2_bf16(__uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y);
+                            pk.w = pack2_bf16(__uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w);
+                            *reinterpret_cast<uint4*>(dst + 16 * j) = pk;
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                    ++n_acc;
+                    named_barrier_sync(2, kCT);                          // q|k|v of the whole tile are in shared memory
+                    stamp(P_EPI);
+                    // ---- ATT_g: this warp's (16-row block, head) ----
+                    float o[4][4];
+                    {
+                        int kbeg, kend, lgblk = -1;
+                        if (L < 16) { kbeg = rb * 16; kend = kbeg + 16; lgblk = 31 - __clz(L); }
+                        else {
+                            kbeg = (rb * 16 / L) * L;
+                            kend = p.causal ? rb * 16 + 16 : kbeg + L;
+                        }
+                        if (L <= 16) attn_unit<2>(sq + hh * 32, sq + 64 + hh * 32, sq + 128 + hh * 32, rb, kbeg, kend, lgblk, p.causal, lane, o);
+                        else attn_unit<4>(sq + hh * 32, sq + 64 + hh * 32, sq + 128 + hh * 32, rb, kbeg, kend, lgblk, p.causal, lane, o);
+                    }
+                    if (g == 3 && film_smem) {                           // the staging rows are dead: stage LN2's FiLM rows over them
+                        named_barrier_sync(1, kCT);
+                        stage_film(tile, l, 1);
+                    }
+                    stamp(P_ATT);
+                    mbar_wait(o_empty, (n_o & 1) ^ 1, 52);               // OUT_{g-1} finished reading O
+                    stamp(P_WO);
+                    {
+                        const int gq = lane >> 2, tq = lane & 3;
+                        const int r0 = rb * 16 + gq;
+                        uint8_t* o0 = so + r0 * 128 + tq * 4;            // sw128_offset(r0, c): chunk (c >> 3) ^ (r0 & 7); r0 + 8: + 1024 bytes
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const int ch = ((hh * 4 + nt) ^ (r0 & 7)) << 4;
+                            *reinterpret_cast<unsigned*>(o0 + ch) = pack2_bf16(o[nt][0], o[nt][1]);
+                            *reinterpret_cast<unsigned*>(o0 + ch + 1024) = pack2_bf16(o[nt][2], o[nt][3]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_full);
+                    ++n_o;
+                    stamp(P_OWR);
+                }
+                if (lane == 0) mbar_arrive(pa_empty);                    // (after the __syncwarp above: the warp is done with PA)
+                // ================= MLP half =================
+                mbar_wait(pm_full, n_p & 1, 53);
+                mbar_wait(h_ready, n_h & 1, 54);                         // OUT_3 has landed in h
+                ++n_h;
+                tc_fence_after();
+                stamp(P_WH1);
+                if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                else ln_tmem<false>(tmem_row, sPM, sPM + 256, sPM + 512, gbtraj ? gbtraj + (2 * l + 1) * 512 : nullptr, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_full);
+                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; }
+                stamp(P_LN2);
+                const float* sb1 = sPM + 768;
+#pragma unroll 1
+                for (int c = 0; c < nc; ++c) {
+                    const int b = c & 1;
+                    mbar_wait(&acc1_full[b], use1[b] & 1, 55);
+                    mbar_wait(&hb_empty[b], (useh[b] & 1) ^ 1, 56);     // FF2 of the previous use finished reading H[b]
+                    tc_fence_after();
+                    stamp(P_WACC1);
+                    {
+                        // this thread: its row, columns part*32 .. +31 of the 128-column chunk (k-block part >> 1 of H[b])
+                        uint8_t* hb = smem + kOffH + (b * 2 + (part >> 1)) * kTile;
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_acc + lane_base + b * 128 + part * 32, r);
+                        tmem_ld_wait();
+                        const float* bb = sb1 + c * 128 + part * 32;    // 0.5 * b1 (pre-halved on the host)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {                    // 8 columns -> one 16-byte swizzle chunk
+                            const float4 b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
+                            const float4 b1v = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
+                            uint4 pk;
+                            pk.x = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 0]), b0.x), silu_half(__uint_as_float(r[8 * j + 1]), b0.y));
+                            pk.y = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 2]), b0.z), silu_half(__uint_as_float(r[8 * j + 3]), b0.w));
+                            pk.z = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 4]), b1v.x), silu_half(__uint_as_float(r[8 * j + 5]), b1v.y));
+                            pk.w = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 6]), b1v.z), silu_half(__uint_as_float(r[8 * j + 7]), b1v.w));
+                            *reinterpret_cast<uint4*>(hb + sw128_offset(row, (part & 1) * 32 + j * 8)) = pk;
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();                            // H writes -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&acc1_empty[b]);
+                        mbar_arrive(&hb_full[b]);
+                    }
+                    ++use1[b];
+                    ++useh[b];
+                    stamp(P_EPI1);
+                }
+                if (lane == 0) mbar_arrive(pm_empty);
+                if (film_smem && ew == 0 && lane == 0) {
+                    // H[0] is dead once FF2 of the last even chunk has completed: stage the next LayerNorm's FiLM rows there
+                    const long long nxt = (l + 1 < NL) ? tile : tile + gridDim.x;
+                    if (nxt < tiles) {
+                        mbar_wait(&hb_empty[0], (useh[0] & 1) ^ 1, 59);
+                        stage_film(nxt, (l + 1 < NL) ? l + 1 : 0, 0);
+                    }
+                }
+                mbar_wait(h_ready, n_h & 1, 57);                         // the last FF2 has landed in h
+                ++n_h;
+                tc_fence_after();
+                stamp(P_WH2);
+            }
+            // ---- TMEM -> residual stream (+ the pending biases) ----
+            {
+                float4* dst = reinterpret_cast<float4*>(p.h + m * kD + part * 64);
+                const float4* cbt = reinterpret_cast<const float4*>(p.cb_total + part * 64);
+                uint32_t r[2][32];
+                tmem_ld_32x32(tmem_row + part * 64, r[0]);
+                tmem_ld_32x32(tmem_row + part * 64 + 32, r[1]);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 cb = __ldg(cbt + cc * 8 + j);
+                            dst[cc * 8 + j] = make_float4(__uint_as_float(r[cc][4 * j + 0]) + cb.x, __uint_as_float(r[cc][4 * j + 1]) + cb.y,
+                                                          __uint_as_float(r[cc][4 * j + 2]) + cb.z, __uint_as_float(r[cc][4 * j + 3]) + cb.w);
+                        }
+                }
+            }
+            stamp(P_STORE);
+        }
+        if (kProf && ew == 0 && lane == 0)
+            for (int i = 0; i < P_N; ++i) atomicAdd(p.prof + i, pacc[i]);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace ef
+
+int encoder_fused(float* h, const float* params, const float* cb_total, const float* gb, long long gb_stride, const void* wqkv,
+                  const void* wo, const void* w1, const void* w2, long long M, int L, int d, int H, int ff, int n_layers, int causal,
+                  cudaStream_t st) {
+    IDB_REQUIRE(d == kD && H == 8, IDB200_EUNSUPPORTED, "fused encoder is specialised for d_model = 256, 8 heads (got %d, %d)", d, H);
+    IDB_REQUIRE(L >= 1 && L <= 128 && (128 % L) == 0, IDB200_EUNSUPPORTED, "fused encoder needs L | 128 (got %d)", L);
+    IDB_REQUIRE(ff % 128 == 0 && ff >= 128 && ff <= ef::kMaxFF, IDB200_EUNSUPPORTED, "fused encoder needs d_ff a multiple of 128, <= 1024 (got %d)", ff);
+    IDB_REQUIRE(n_layers >= 1, IDB200_EINVAL, "n_layers must be >= 1");
+    IDB_REQUIRE(M >= 0 && M % L == 0, IDB200_EINVAL, "M must be a multiple of L");
+    if (M == 0) return IDB200_OK;
+    IDB_REQUIRE(h && params && cb_total && wqkv && wo && w1 && w2, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(aligned(h, 16) && aligned(params, 16) && aligned(cb_total, 16) && (!gb || (aligned(gb, 16) && gb_stride % 4 == 0)),
+                IDB200_EALIGN, "h / params / gamma_beta must be 16-byte aligned");
+    CUtensorMap tqk, tv, two, t1, t2;
+    int rc = make_tmap_bf16_2d(&tqk, wqkv, static_cast<uint64_t>(n_layers) * 768, 256, 128, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tv, wqkv, static_cast<uint64_t>(n_layers) * 768, 256, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&two, wo, static_cast<uint64_t>(n_layers) * 256, 256, 128, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&t1, w1, static_cast<uint64_t>(n_layers) * ff, 256, 128, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&t2, w2, static_cast<uint64_t>(n_layers) * 256, ff, 128, 64);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(ef::encoder_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ef::encoder_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", ef::kSmem, cudaGetErrorString(e));
+        attr = true;
+    }
+    const long long tiles = (M + 127) / 128;
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    ef::Params p{h, params, cb_total, gb, gb_stride, M, L, causal, ff, n_layers, nullptr};
+    static const bool prof = getenv("IDB200_PROF") != nullptr;
+    if (prof) {                                                           // dev only: synchronous, prints the phase breakdown
+        static unsigned long long* dprof = nullptr;
+        if (!dprof) cudaMalloc(&dprof, ef::P_N * sizeof(unsigned long long));
+        cudaMemsetAsync(dprof, 0, ef::P_N * sizeof(unsigned long long), st);
+        p.prof = dprof;
+        ef::encoder_fused_kernel<true><<<grid, ef::kThreads, ef::kSmem, st>>>(tqk, tv, two, t1, t2, p);
+        unsigned long long hp[ef::P_N];
+        cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        static const char* names[ef::P_N] = {"load", "ln1", "wait_acc", "epi", "att", "wait_o", "o_write", "wait_h1", "ln2", "wait_acc1", "epi1",
+                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film)"};
+        const double units = static_cast<double>(tiles) * n_layers;
+        fprintf(stderr, "encoder_fused prof (cycles per tile-layer, L=%d):", L);
+        double tot = 0;
+        for (int i = 0; i < ef::P_N; ++i) { fprintf(stderr, " %s=%.0f", names[i], hp[i] / units); if (i < ef::P_LNP1) tot += hp[i] / units; }
+        fprintf(stderr, " total=%.0f\n", tot);
+        return check_launch("encoder_fused_kernel<prof>");
+    }
+    ef::encoder_fused_kernel<false><<<grid, ef::kThreads, ef::kSmem, st>>>(tqk, tv, two, t1, t2, p);
+    return check_launch("encoder_fused_kernel");
+}
+
+}  // namespace idb200
+
+extern "C" int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_total, const float* gamma_beta,
+                                    int64_t gb_stride, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
+                                    int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream) {
+    return idb200::encoder_fused(h, layer_params, bias_total, gamma_beta, gb_stride, wqkv_packed, wo, w1, w2, M, L, d, H, ff, n_layers,
+                                 causal, static_cast<cudaStream_t>(stream));
+}

@@ -235,6 +235,156 @@ __device__ __forceinline__ void attn_unit(const __nv_bfloat16* Q, const __nv_bfl
     for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= i0; o[nt][1] *= i0; o[nt][2] *= i1; o[nt][3] *= i1; }
 }
 
+// pure-register variants (not volatile: the compiler may interleave independent chains)
+__device__ __forceinline__ void hmma_16816_nv(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Both heads of a head group at once (two independent dependency chains interleaved instruction by instruction):
+// softmax(q k^T / sqrt(32)) v for the 16-row block rb, keys kbeg..kend-1 (tile rows), from the staged bf16 rows
+// sq[row][q 64 | k 64 | v 64] (pitch kPitch, head hh at column offset 32 hh of each part).  NT key tiles of 8 per step.
+template <int NT>
+__device__ __forceinline__ void attn_unit2(const __nv_bfloat16* sq, int rb, int kbeg, int kend, int lgblk, int causal, int lane,
+                                           float (&o)[2][4][4]) {
+    constexpr float kScaleLog2 = 0.17677669529663687f * 1.4426950408889634f;
+    unsigned qa[2][2][4];
+    {
+        const __nv_bfloat16* qp = sq + (rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 8;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[hh][ks], qp + hh * 32 + ks * 16);
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[hh][nt][c] = 0.0f;
+    float mx[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}}, ls[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+    const int g = lane >> 2, tq = lane & 3;
+    const int qrow0 = rb * 16 + g, qrow1 = qrow0 + 8;
+    const __nv_bfloat16* kp = sq + (lane & 7) * kPitch + 64 + (lane >> 3) * 8;
+    const __nv_bfloat16* vp = sq + ((lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + 128 + (lane >> 4) * 8;
+    for (int k0 = kbeg; k0 < kend; k0 += 8 * NT) {
+        const int kw = min(8 * NT, kend - k0);                          // multiple of 16
+        float s[2][NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s[hh][nt][c] = 0.0f;
+            if (nt * 8 < kw) {
+                unsigned kb[2][4];
+                ldsm_x4(kb[0], kp + (k0 + nt * 8) * kPitch);
+                ldsm_x4(kb[1], kp + (k0 + nt * 8) * kPitch + 32);
+                hmma_16816_nv(s[0][nt], qa[0][0], kb[0][0], kb[0][1]);
+                hmma_16816_nv(s[1][nt], qa[1][0], kb[1][0], kb[1][1]);
+                hmma_16816_nv(s[0][nt], qa[0][1], kb[0][2], kb[0][3]);
+                hmma_16816_nv(s[1][nt], qa[1][1], kb[1][2], kb[1][3]);
+            }
+        }
+        float bm[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int key = k0 + nt * 8 + tq * 2 + (c & 1);
+                const int qr = (c < 2) ? qrow0 : qrow1;
+                const bool ok = (nt * 8 < kw) && (!causal || key <= qr) && (lgblk < 0 || ((key ^ qr) >> lgblk) == 0);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) s[hh][nt][c] = ok ? s[hh][nt][c] * kScaleLog2 : -INFINITY;
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                bm[hh][0] = fmaxf(bm[hh][0], fmaxf(s[hh][nt][0], s[hh][nt][1]));
+                bm[hh][1] = fmaxf(bm[hh][1], fmaxf(s[hh][nt][2], s[hh][nt][3]));
+            }
+        }
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) bm[hh][i] = fmaxf(bm[hh][i], __shfl_xor_sync(0xffffffffu, bm[hh][i], off));
+        float corr[2][2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float mn = fmaxf(mx[hh][i], bm[hh][i]);            // finite: a query always sees its own key
+                corr[hh][i] = ex2_fast(mx[hh][i] - mn);
+                mx[hh][i] = mn;
+            }
+        unsigned pa[2][NT / 2][4];
+        float rs[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float p0 = ex2_fast(s[hh][nt][0] - mx[hh][0]), p1 = ex2_fast(s[hh][nt][1] - mx[hh][0]);
+                const float p2 = ex2_fast(s[hh][nt][2] - mx[hh][1]), p3 = ex2_fast(s[hh][nt][3] - mx[hh][1]);
+                rs[hh][0] += p0 + p1;
+                rs[hh][1] += p2 + p3;
+                pa[hh][nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p0, p1);
+                pa[hh][nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);
+            }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            ls[hh][0] = ls[hh][0] * corr[hh][0] + rs[hh][0];
+            ls[hh][1] = ls[hh][1] * corr[hh][1] + rs[hh][1];
+        }
+        if (k0 > kbeg) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    o[hh][nt][0] *= corr[hh][0]; o[hh][nt][1] *= corr[hh][0];
+                    o[hh][nt][2] *= corr[hh][1]; o[hh][nt][3] *= corr[hh][1];
+                }
+        }
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks) {
+            if (ks * 16 < kw) {
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    unsigned vb[2][4];
+                    ldsm_x4_trans(vb[0], vp + (k0 + ks * 16) * kPitch + np * 16);
+                    ldsm_x4_trans(vb[1], vp + (k0 + ks * 16) * kPitch + 32 + np * 16);
+                    hmma_16816_nv(o[0][np * 2 + 0], pa[0][ks], vb[0][0], vb[0][1]);
+                    hmma_16816_nv(o[1][np * 2 + 0], pa[1][ks], vb[1][0], vb[1][1]);
+                    hmma_16816_nv(o[0][np * 2 + 1], pa[0][ks], vb[0][2], vb[0][3]);
+                    hmma_16816_nv(o[1][np * 2 + 1], pa[1][ks], vb[1][2], vb[1][3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            ls[hh][i] += __shfl_xor_sync(0xffffffffu, ls[hh][i], 1);
+            ls[hh][i] += __shfl_xor_sync(0xffffffffu, ls[hh][i], 2);
+        }
+        const float i0 = rcp_fast(ls[hh][0]), i1 = rcp_fast(ls[hh][1]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { o[hh][nt][0] *= i0; o[hh][nt][1] *= i0; o[hh][nt][2] *= i1; o[hh][nt][3] *= i1; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // residual epilogue: h[m0 .. m0+127, 0..255] += acc (TMEM, 256 fp32 columns at tmem_acc) + bias.
 // The fp32 tile is staged through `stage` (64 KB, 1024-byte aligned) as [128 x 32] SWIZZLE_128B boxes and added to

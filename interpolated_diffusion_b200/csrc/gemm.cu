@@ -94,6 +94,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    __builtin_assume(__isShared(smem));             // keep LDS / STS (the integer round trip hides the address space)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     uint64_t* full_bar = bars;                              // [kStages]  TMA -> MMA
     uint64_t* empty_bar = bars + Cfg::kStages;              // [kStages]  MMA -> TMA

@@ -50,20 +50,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a
-// hung GPU.  ~4 s at 2 GHz.
+// hung GPU.  ~4 s at 2 GHz.  The clock is sampled every 1024 polls only (the poll loop of a waiting warp shares
+// issue slots and the shared-memory pipe with the warps doing the work); kBackoff adds a nanosleep between polls
+// for waiters that are far from the critical path (TMA producers).
 #ifndef IDB200_WAIT_LIMIT_CYCLES
 #define IDB200_WAIT_LIMIT_CYCLES (8000000000LL)
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, bool backoff) {
+    uint32_t polls = 0;
+    long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > IDB200_WAIT_LIMIT_CYCLES) {
-            printf("idb200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x,
-                   parity);
-            __trap();
+        if (backoff) __nanosleep(40);
+        if ((++polls & 1023u) == 0) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > IDB200_WAIT_LIMIT_CYCLES) {
+                printf("idb200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
+                __trap();
+            }
         }
     }
+}
+template <bool kBackoff = false>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, tag, kBackoff);             // out of line: keeps the instruction footprint of every wait small
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -78,6 +89,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+
+// 1-D bulk copy global -> shared (bytes % 16 == 0, 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // h[tile] += smem tile: TMA reduce-add (fp32) into global memory, bulk-group completion
@@ -143,6 +161,27 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// thread i of the warp writes TMEM lane (lane_base + i), columns c..c+31
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -61,6 +61,18 @@ def mlp_block(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], W1, b1, W
     return h
 
 
+def encoder_fused(h: torch.Tensor, pk: "PackedEncoder", film: Optional[torch.Tensor], Lseq: int, causal: bool):
+    """Every layer of the encoder in one persistent kernel (idb200_encoder_fused): h stays in tensor memory."""
+    M, d = h.shape
+    f = pk.fused
+    if film is not None and (film.stride(2) != 1 or film.stride(1) != 2 * d):
+        film = film.contiguous()
+    L.call("idb200_encoder_fused", h.data_ptr(), f["params"].data_ptr(), f["cb_total"].data_ptr(), L.ptr(film),
+           0 if film is None else film.stride(0), f["wqkv"].data_ptr(), f["wo"].data_ptr(), f["w1"].data_ptr(), f["w2"].data_ptr(),
+           M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(h.device))
+    return h
+
+
 def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((rows, dim), device=device, dtype=torch.float32)
     L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))
@@ -107,6 +119,7 @@ class PackedEncoder:
         self.ws = Workspace()
         self.fuse_mlp = True            # d_model == 256: FF1 + SiLU + FF2 + residual in one kernel
         self.fuse_blocks = True         # d_model == 256, 8 heads, L | 128: two kernels per layer (attn_block, mlp_block)
+        self.fuse_encoder = True        # ... and d_ff <= 1024: ONE kernel for all layers (encoder_fused)
 
     def _pack(self):
         layers = self.enc.layers
@@ -144,6 +157,22 @@ class PackedEncoder:
         self.d = layers[0].norm1.weight.shape[0]
         self.ff = layers[0].ff[0].weight.shape[0]
         self.n_heads = layers[0].attn.num_heads
+        self.fused = None
+        if self.d == 256 and self.n_heads == 8 and self.ff % 128 == 0 and self.ff <= 1024:
+            # stacked weights + per-layer parameter blobs of idb200_encoder_fused (layout: include/idb200.h)
+            cb = torch.zeros(self.d, device=self.layers[0]["bo"].device, dtype=torch.float32)
+            blobs = []
+            for e in self.layers:
+                cb2 = cb + e["bo"]
+                blobs += [e["n1w"], e["n1b"], cb, e["bqkv_g"], e["n2w"], e["n2b"], cb2, 0.5 * e["b1"]]
+                cb = cb2 + e["b2"]
+            self.fused = {
+                "params": torch.cat(blobs).contiguous(), "cb_total": cb.contiguous(),
+                "wqkv": torch.cat([e["wqkv_g"] for e in self.layers], dim=0).contiguous(),
+                "wo": torch.cat([e["wo"] for e in self.layers], dim=0).contiguous(),
+                "w1": torch.cat([e["w1"] for e in self.layers], dim=0).contiguous(),
+                "w2": torch.cat([e["w2"] for e in self.layers], dim=0).contiguous(),
+            }
         self._key = key
 
     def film_params(self, cond_vec: torch.Tensor) -> Optional[torch.Tensor]:
@@ -166,6 +195,8 @@ class PackedEncoder:
             fuse_attn = self.fuse_blocks and d == 256 and H == 8 and 128 % Lseq == 0 and M % Lseq == 0
             fuse_ln_mlp = self.fuse_blocks and fuse_mlp and (Lseq % 8 == 0 or 8 % Lseq == 0)
             fused = fuse_attn and fuse_ln_mlp
+            if fused and self.fuse_encoder and self.fused is not None:
+                return encoder_fused(h, self, film, Lseq, causal)
             if not fused:
                 a = self.ws.get("a", (M, d), torch.bfloat16, dev)
                 qkv = self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)

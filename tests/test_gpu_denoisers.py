@@ -202,17 +202,47 @@ def test_fused_transformer_blocks_vs_oracle(Lseq, B, causal):
     ref = odn.transformer_encoder(x, cv, sd, 8, causal)
     enc = enc.cuda()
     pk = enc.packed()
-    assert pk.fuse_blocks
-    got = enc(x.cuda(), cv.cuda())
+    assert pk.fuse_blocks and pk.fuse_encoder
+    whole = enc(x.cuda(), cv.cuda())                 # idb200_encoder_fused: one kernel for all layers
+    pk.fuse_encoder = False
+    got = enc(x.cuda(), cv.cuda())                   # attn_block + mlp_block per layer
     pk.fuse_blocks = False
     unfused = enc(x.cuda(), cv.cuda())
-    pk.fuse_blocks = True
+    pk.fuse_blocks = pk.fuse_encoder = True
     scale = ref.abs().max().item()
+    assert _maxabs(whole, ref) < 2e-2 * max(1.0, scale / 4), (_maxabs(whole, ref), scale)
     assert _maxabs(got, ref) < 2e-2 * max(1.0, scale / 4), (_maxabs(got, ref), scale)
     assert _maxabs(got, unfused) < 2e-2 * max(1.0, scale / 4), _maxabs(got, unfused)
+    assert _maxabs(whole, unfused) < 2e-2 * max(1.0, scale / 4), _maxabs(whole, unfused)
     # no FiLM
     enc2 = TransformerEncoder(d_model=256, n_layers=1, n_heads=8, d_ff=1024, cond_dim=None, causal=causal)
     sd2 = {"transformer.layers." + k[len("layers."):]: v.clone() for k, v in enc2.state_dict().items()}
     ref2 = odn.transformer_encoder(x, None, sd2, 8, causal)
     got2 = enc2.cuda()(x.cuda(), None)
     assert _maxabs(got2, ref2) < 2e-2 * max(1.0, ref2.abs().max().item() / 4), _maxabs(got2, ref2)
+
+
+@pytest.mark.parametrize("Lseq,B,n_layers,ff,causal", [(8, 16 * 148 * 2 + 37, 8, 1024, False), (64, 2 * 148 + 3, 3, 512, True)])
+def test_encoder_fused_many_tiles(Lseq, B, n_layers, ff, causal):
+    """idb200_encoder_fused with several tiles per CTA (persistent loop, parameter / weight rings wrapping across tiles and
+    layers, ragged last tile) against the unfused kernel sequence, and idempotent across repeated launches."""
+    from interpolated_diffusion_b200.models.transformer import TransformerEncoder
+    torch.manual_seed(3)
+    enc = TransformerEncoder(d_model=256, n_layers=n_layers, n_heads=8, d_ff=ff, cond_dim=128, causal=causal)
+    with torch.no_grad():
+        for l in enc.layers:
+            for p_ in (l.norm1.bias, l.norm2.bias, l.attn.in_proj_bias, l.attn.out_proj.bias, l.ff[2].bias):
+                p_.add_(0.1 * torch.randn_like(p_))
+    enc = enc.cuda()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((B, Lseq, 256), generator=gen, device="cuda")
+    cv = torch.randn((B, 128), generator=gen, device="cuda")
+    pk = enc.packed()
+    whole = enc(x, cv)
+    again = enc(x, cv)
+    pk.fuse_encoder = pk.fuse_blocks = False
+    unfused = enc(x, cv)
+    assert torch.isfinite(whole).all()
+    assert torch.equal(whole, again)
+    scale = unfused.abs().max().item()
+    assert _maxabs(whole, unfused) < 2e-2 * max(1.0, scale / 4), (_maxabs(whole, unfused), scale)
