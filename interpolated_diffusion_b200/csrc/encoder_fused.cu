@@ -184,9 +184,15 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
 }
 
 // kProf (dev, IDB200_PROF=1): compute warp 0 lane 0 accumulates clock64() spans per phase into p.prof[0..15]
-enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_N };
+enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
 
-template <bool kProf>
+// kPair: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  Each CTA still owns one 128-token tile (its
+// rows of h in its own TMEM, its own X / scratch / parameters), but the even CTA issues ONE M=256 MMA for both tiles
+// and each CTA stages only half of every weight tile (N/2 rows), so the L2 -> shared-memory weight stream per SM -- the
+// limiter of the single-CTA form at 128-token tiles -- is halved.  compute -> MMA barriers live in the even CTA (both
+// CTAs' compute warps arrive there), MMA -> compute / producer barriers are signalled in both CTAs by multicast commits.
+// tm_qk / tm_v / tm_w1: in pair mode tm_qk has a 96-row box (half of a head group's q|k|v rows), tm_w1 a 64-row box.
+template <bool kProf, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
                      const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_w1,
@@ -223,6 +229,12 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
     const long long tiles = (p.M + 127) / 128;
     const int pm_floats = 768 + p.ff;
     const int layer_floats = kPAFloats + pm_floats;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;          // 0 = the CTA that issues the pair's MMAs
+    constexpr int kArr = kPair ? 2 * kCW : kCW;                      // arrivals on the compute -> MMA barriers
+    // persistent loop: trip t handles tile t (single) or tiles 2t, 2t+1 (pair; a trailing odd tile leaves the peer a dead tile)
+    const long long trips = kPair ? (tiles + 1) / 2 : tiles;
+    const long long trip0 = kPair ? blockIdx.x / 2 : blockIdx.x;
+    const long long trip_stride = kPair ? gridDim.x / 2 : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_qk);
@@ -232,17 +244,17 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         tma_prefetch_desc(&tm_w2);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(x_full, kCW);
+        mbar_init(x_full, kArr);
         mbar_init(h_ready, 1);
         for (int i = 0; i < kSlots; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, kCW);
-        mbar_init(o_full, kCW);
+        mbar_init(acc_empty, kArr);
+        mbar_init(o_full, kArr);
         mbar_init(o_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc1_full[i], 1);
-            mbar_init(&acc1_empty[i], kCW);
-            mbar_init(&hb_full[i], kCW);
+            mbar_init(&acc1_empty[i], kArr);
+            mbar_init(&hb_full[i], kArr);
             mbar_init(&hb_empty[i], 1);
         }
         mbar_init(pa_full, 1);
@@ -253,11 +265,11 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if (kPair) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_h = tmem_base;
@@ -268,32 +280,56 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         if (lane == 0) {
             int slot = 0;
             uint32_t sphase = 0;
-            auto load = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
+            // one ring slot: `n` tile loads (each `bytes`, `step` apart in the slot); in pair mode this CTA loads its half of
+            // the rows and the bytes of both CTAs are credited to the even CTA's slot_full barrier
+            auto fill = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes, int n, int dc0, uint32_t step) {
                 mbar_wait(&slot_empty[slot], sphase ^ 1, 10);
-                mbar_arrive_expect_tx(&slot_full[slot], bytes);
-                tma_load_2d(smem + kOffRing + slot * kSlotBytes, m, &slot_full[slot], c0, c1);
+                uint8_t* dst = smem + kOffRing + slot * kSlotBytes;
+                if (kPair) {
+                    if (rank == 0) mbar_arrive_expect_tx(&slot_full[slot], 2 * n * bytes);
+                    for (int i = 0; i < n; ++i) tma_load_2d_2sm(dst + i * step, m, &slot_full[slot], c0 + i * dc0, c1);
+                } else {
+                    mbar_arrive_expect_tx(&slot_full[slot], n * bytes);
+                    for (int i = 0; i < n; ++i) tma_load_2d(dst + i * step, m, &slot_full[slot], c0 + i * dc0, c1);
+                }
                 if (++slot == kSlots) { slot = 0; sphase ^= 1; }
             };
-            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (long long trip = trip0; trip < trips; trip += trip_stride) {
                 for (int l = 0; l < NL; ++l) {
                     auto qkv = [&](int g) {
 #pragma unroll 1
                         for (int kb = 0; kb < 4; ++kb) {
-                            load(&tm_qk, kb * 64, l * 768 + g * 192, kTile);
-                            load(&tm_v, kb * 64, l * 768 + g * 192 + 128, kTile / 2);
+                            if (kPair) fill(&tm_qk, kb * 64, l * 768 + g * 192 + rank * 96, 96 * 128, 1, 0, 0);
+                            else {
+                                fill(&tm_qk, kb * 64, l * 768 + g * 192, kTile, 1, 0, 0);
+                                fill(&tm_v, kb * 64, l * 768 + g * 192 + 128, kTile / 2, 1, 0, 0);
+                            }
                         }
                     };
                     auto wo = [&](int g) {
-                        load(&tm_wo, g * 64, l * 256, kTile);
-                        load(&tm_wo, g * 64, l * 256 + 128, kTile);
+                        if (kPair) fill(&tm_wo, g * 64, l * 256 + rank * 128, kTile, 1, 0, 0);
+                        else {
+                            fill(&tm_wo, g * 64, l * 256, kTile, 1, 0, 0);
+                            fill(&tm_wo, g * 64, l * 256 + 128, kTile, 1, 0, 0);
+                        }
                     };
                     auto ff1 = [&](int c) {
+                        if (kPair) {                                         // 2 slots x (2 k-blocks of this CTA's 64 rows)
 #pragma unroll 1
-                        for (int kb = 0; kb < 4; ++kb) load(&tm_w1, kb * 64, l * p.ff + c * 128, kTile);
+                            for (int j = 0; j < 2; ++j) fill(&tm_w1, j * 128, l * p.ff + c * 128 + rank * 64, kTile / 2, 2, 64, kTile / 2);
+                        } else {
+#pragma unroll 1
+                            for (int kb = 0; kb < 4; ++kb) fill(&tm_w1, kb * 64, l * p.ff + c * 128, kTile, 1, 0, 0);
+                        }
                     };
                     auto ff2 = [&](int c) {
+                        if (kPair) {
 #pragma unroll 1
-                        for (int i = 0; i < 4; ++i) load(&tm_w2, c * 128 + (i & 1) * 64, l * 256 + (i >> 1) * 128, kTile);
+                            for (int kb = 0; kb < 2; ++kb) fill(&tm_w2, c * 128 + kb * 64, l * 256 + rank * 128, kTile, 1, 0, 0);
+                        } else {
+#pragma unroll 1
+                            for (int i = 0; i < 4; ++i) fill(&tm_w2, c * 128 + (i & 1) * 64, l * 256 + (i >> 1) * 128, kTile, 1, 0, 0);
+                        }
                     };
                     // attention half: G0 G1 O0 G2 O1 G3 O2 O3 (rolled: one copy of each body keeps the code small)
 #pragma unroll 1
@@ -310,77 +346,144 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
-            constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
+        // ===================== MMA issuer (pair mode: the even CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t kM = kPair ? 256 : 128;
+            constexpr uint32_t idesc64 = umma_idesc_bf16(kM, 64);
+            constexpr uint32_t idesc128 = umma_idesc_bf16(kM, 128);
+            constexpr uint32_t idesc192 = umma_idesc_bf16(kM, 192);
+            constexpr uint32_t idesc256 = umma_idesc_bf16(kM, 256);
             int slot = 0;
             uint32_t sphase = 0, n_x = 0, n_acc = 0, n_o = 0;
             uint32_t use1[2] = {0, 0}, useh[2] = {0, 0};
             const uint32_t sX = smem_u32(smem + kOffX), sO = smem_u32(smem + kOffO), sH = smem_u32(smem + kOffH), sR = smem_u32(smem + kOffRing);
-            // 4 x (K = 16) MMAs of one [.. x 64] k-block: A tile at a_addr, B = the current ring slot
-            auto mma_slot = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, bool first_zero, int tag) {
-                mbar_wait(&slot_full[slot], sphase, tag);
+            unsigned long long macc[3] = {0, 0, 0};
+            long long mprev = kProf ? clock64() : 0;
+            auto mstamp = [&](int what) {
+                if (kProf) {
+                    const long long t = clock64();
+                    macc[what] += static_cast<unsigned long long>(t - mprev);
+                    mprev = t;
+                }
+            };
+            auto wait = [&](uint64_t* bar, uint32_t parity, int tag) {   // barriers the peer CTA also arrives on / credits
+                mstamp(2);
+                mbar_wait(bar, parity, tag);
                 tc_fence_after();
+                mstamp(tag == 21 || tag == 22 || tag == 24 || tag == 25 || tag == 27 || tag == 29 ? 0 : 1);
+            };
+            auto commit = [&](uint64_t* bar) { if (kPair) umma_commit_2sm(bar); else umma_commit(bar); };
+            // 4 x (K = 16) MMAs of one 64-wide k-block: A tile at a_addr, B tile at b_addr
+            auto mma4 = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool first_zero) {
                 const uint64_t ad = umma_desc_sw128(a_addr);
-                const uint64_t bd = umma_desc_sw128(sR + slot * kSlotBytes);
+                const uint64_t bd = umma_desc_sw128(b_addr);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
-                umma_commit(&slot_empty[slot]);
+                for (int k = 0; k < 4; ++k) {
+                    if (kPair) umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
+                    else umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
+                }
+            };
+            auto slot_begin = [&](int tag) -> uint32_t {
+                wait(&slot_full[slot], sphase, tag);
+                return sR + slot * kSlotBytes;
+            };
+            auto slot_end = [&]() {
+                commit(&slot_empty[slot]);
                 if (++slot == kSlots) { slot = 0; sphase ^= 1; }
             };
             auto gemm = [&](int g) {
-                mbar_wait(acc_empty, (n_acc & 1) ^ 1, 20);              // EPI of the previous group drained the accumulator
-                tc_fence_after();
+                wait(acc_empty, (n_acc & 1) ^ 1, 20);                    // EPI of the previous group drained the accumulator
 #pragma unroll 1
                 for (int kb = 0; kb < 4; ++kb) {
-                    mma_slot(tmem_acc, sX + kb * kTile, idesc128, kb == 0, 21);          // q | k  (128 columns)
-                    mma_slot(tmem_acc + 128, sX + kb * kTile, idesc64, kb == 0, 22);     // v      (64 columns)
+                    if (kPair) {
+                        const uint32_t b = slot_begin(21);
+                        mma4(tmem_acc, sX + kb * kTile, b, idesc192, kb == 0);           // q | k | v (192 columns)
+                        slot_end();
+                    } else {
+                        uint32_t b = slot_begin(21);
+                        mma4(tmem_acc, sX + kb * kTile, b, idesc128, kb == 0);           // q | k  (128 columns)
+                        slot_end();
+                        b = slot_begin(22);
+                        mma4(tmem_acc + 128, sX + kb * kTile, b, idesc64, kb == 0);      // v      (64 columns)
+                        slot_end();
+                    }
                 }
-                umma_commit(acc_full);
+                commit(acc_full);
                 ++n_acc;
             };
             auto outp = [&](int g) {
-                mbar_wait(o_full, n_o & 1, 23);                          // ATT_g wrote O_g
-                tc_fence_after();
-                mma_slot(tmem_h, sO, idesc128, false, 24);               // h[:, 0:128]   += O_g . Wo[0:128, 64g..]^T
-                mma_slot(tmem_h + 128, sO, idesc128, false, 25);         // h[:, 128:256] += O_g . Wo[128:256, 64g..]^T
-                umma_commit(o_empty);
-                if (g == 3) umma_commit(h_ready);
+                wait(o_full, n_o & 1, 23);                               // ATT_g wrote O_g
+                if (kPair) {
+                    const uint32_t b = slot_begin(24);
+                    mma4(tmem_h, sO, b, idesc256, false);                // h += O_g . Wo[:, 64g..]^T
+                    slot_end();
+                } else {
+                    uint32_t b = slot_begin(24);
+                    mma4(tmem_h, sO, b, idesc128, false);                // h[:, 0:128]
+                    slot_end();
+                    b = slot_begin(25);
+                    mma4(tmem_h + 128, sO, b, idesc128, false);          // h[:, 128:256]
+                    slot_end();
+                }
+                commit(o_empty);
+                if (g == 3) commit(h_ready);
                 ++n_o;
             };
             auto ff1 = [&](int c) {
                 const int b = c & 1;
-                mbar_wait(&acc1_empty[b], (use1[b] & 1) ^ 1, 26);       // EPI1 drained acc1[b]
-                tc_fence_after();
+                wait(&acc1_empty[b], (use1[b] & 1) ^ 1, 26);            // EPI1 drained acc1[b]
+                if (kPair) {
 #pragma unroll 1
-                for (int kb = 0; kb < 4; ++kb) mma_slot(tmem_acc + b * 128, sX + kb * kTile, idesc128, kb == 0, 27);
-                umma_commit(&acc1_full[b]);
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t bs = slot_begin(27);
+                        mma4(tmem_acc + b * 128, sX + (2 * j) * kTile, bs, idesc128, j == 0);
+                        mma4(tmem_acc + b * 128, sX + (2 * j + 1) * kTile, bs + kTile / 2, idesc128, false);
+                        slot_end();
+                    }
+                } else {
+#pragma unroll 1
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t bs = slot_begin(27);
+                        mma4(tmem_acc + b * 128, sX + kb * kTile, bs, idesc128, kb == 0);
+                        slot_end();
+                    }
+                }
+                commit(&acc1_full[b]);
                 ++use1[b];
             };
             auto ff2 = [&](int c) {
                 const int b = c & 1;
-                mbar_wait(&hb_full[b], useh[b] & 1, 28);                 // EPI1 wrote H[b]
-                tc_fence_after();
+                wait(&hb_full[b], useh[b] & 1, 28);                      // EPI1 wrote H[b]
+                if (kPair) {
 #pragma unroll 1
-                for (int i = 0; i < 4; ++i) mma_slot(tmem_h + (i >> 1) * 128, sH + (b * 2 + (i & 1)) * kTile, idesc128, false, 29);
-                umma_commit(&hb_empty[b]);
-                if (c == nc - 1) umma_commit(h_ready);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint32_t bs = slot_begin(29);
+                        mma4(tmem_h, sH + (b * 2 + kb) * kTile, bs, idesc256, false);
+                        slot_end();
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t bs = slot_begin(29);
+                        mma4(tmem_h + (i >> 1) * 128, sH + (b * 2 + (i & 1)) * kTile, bs, idesc128, false);
+                        slot_end();
+                    }
+                }
+                commit(&hb_empty[b]);
+                if (c == nc - 1) commit(h_ready);
                 ++useh[b];
             };
-            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (long long trip = trip0; trip < trips; trip += trip_stride) {
                 for (int l = 0; l < NL; ++l) {
-                    mbar_wait(x_full, n_x & 1, 30);
+                    wait(x_full, n_x & 1, 30);
                     ++n_x;
-                    tc_fence_after();
 #pragma unroll 1
                     for (int i = 0; i < 8; ++i) {                        // G0 G1 O0 G2 O1 G3 O2 O3
                         if ((0x2Bu >> i) & 1u) gemm(i < 2 ? i : (i + 1) >> 1);
                         else outp(i < 7 ? (i >> 1) - 1 : 3);
                     }
-                    mbar_wait(x_full, n_x & 1, 31);
+                    wait(x_full, n_x & 1, 31);
                     ++n_x;
-                    tc_fence_after();
 #pragma unroll 1
                     for (int c = -2; c < nc; ++c) {
                         if (c >= 0) ff2(c);
@@ -388,12 +491,16 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     }
                 }
             }
+            if (kProf) {
+                mstamp(2);
+                for (int i = 0; i < 3; ++i) atomicAdd(p.prof + P_MSLOT + i, macc[i] * (kPair ? 2 : 1));   // per tile: the pair's issuer serves two
+            }
         }
     } else if (warp == 3) {
         // ===================== per-layer parameter loader =====================
         if (lane == 0) {
             uint32_t n = 0;
-            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (long long trip = trip0; trip < trips; trip += trip_stride) {
                 for (int l = 0; l < NL; ++l, ++n) {
                     const float* src = p.params + static_cast<long long>(l) * layer_floats;
                     mbar_wait<true>(pa_empty, (n & 1) ^ 1, 40);
@@ -435,17 +542,20 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
             if (film_smem && ew == 0 && lane == 0) {
                 const long long t0 = tile_ * 128 / L;
                 const long long left = p.M / L - t0;
-                const int nt = static_cast<int>(left < 128 / L ? left : 128 / L);
+                const int nt = left <= 0 ? 0 : static_cast<int>(left < 128 / L ? left : 128 / L);   // 0: the pair's dead tile
                 fence_proxy_async_smem();
                 mbar_arrive_expect_tx(film_full, static_cast<uint32_t>(nt) * 2048u);
                 for (int t = 0; t < nt; ++t)
                     bulk_load_1d(smem + kOffS + t * 2048, p.gb + (t0 + t) * p.gb_stride + (2 * l_ + which) * 512, 2048, film_full);
             }
         };
-        if (static_cast<long long>(blockIdx.x) < tiles) stage_film(blockIdx.x, 0, 0);
+        auto tile_of = [&](long long trip) { return kPair ? 2 * trip + rank : trip; };
+        auto arrive_mma = [&](uint64_t* bar) { if (kPair) mbar_arrive_leader(bar); else mbar_arrive(bar); };
+        if (trip0 < trips) stage_film(tile_of(trip0), 0, 0);
         // attention work unit of this warp: 16-row block rb, head hh of the group
         const int rb = ew & 7, hh = ew >> 3;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (long long trip = trip0; trip < trips; trip += trip_stride) {
+            const long long tile = tile_of(trip);
             const long long m0 = tile * 128;
             const long long m = m0 + row;
             const bool live = m < p.M;
@@ -481,7 +591,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(x_full);
+                if (lane == 0) arrive_mma(x_full);
                 if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; }
                 stamp(P_LN1);
                 const float* sbqkv = sPA + 768;
@@ -514,7 +624,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
+                    if (lane == 0) arrive_mma(acc_empty);
                     ++n_acc;
                     named_barrier_sync(2, kCT);                          // q|k|v of the whole tile are in shared memory
                     stamp(P_EPI);
@@ -550,7 +660,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(o_full);
+                    if (lane == 0) arrive_mma(o_full);
                     ++n_o;
                     stamp(P_OWR);
                 }
@@ -566,7 +676,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(x_full);
+                if (lane == 0) arrive_mma(x_full);
                 if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; }
                 stamp(P_LN2);
                 const float* sb1 = sPM + 768;
@@ -600,8 +710,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     fence_proxy_async_smem();                            // H writes -> visible to the tensor core
                     __syncwarp();
                     if (lane == 0) {
-                        mbar_arrive(&acc1_empty[b]);
-                        mbar_arrive(&hb_full[b]);
+                        arrive_mma(&acc1_empty[b]);
+                        arrive_mma(&hb_full[b]);
                     }
                     ++use1[b];
                     ++useh[b];
@@ -610,10 +720,10 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 if (lane == 0) mbar_arrive(pm_empty);
                 if (film_smem && ew == 0 && lane == 0) {
                     // H[0] is dead once FF2 of the last even chunk has completed: stage the next LayerNorm's FiLM rows there
-                    const long long nxt = (l + 1 < NL) ? tile : tile + gridDim.x;
-                    if (nxt < tiles) {
+                    const long long nxt = (l + 1 < NL) ? trip : trip + trip_stride;
+                    if (nxt < trips) {
                         mbar_wait(&hb_empty[0], (useh[0] & 1) ^ 1, 59);
-                        stage_film(nxt, (l + 1 < NL) ? l + 1 : 0, 0);
+                        stage_film(tile_of(nxt), (l + 1 < NL) ? l + 1 : 0, 0);
                     }
                 }
                 mbar_wait(h_ready, n_h & 1, 57);                         // the last FF2 has landed in h
@@ -647,10 +757,10 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();     // pair: the peer's shared memory / TMEM stay valid until both are done
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (kPair) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -668,47 +778,78 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     IDB_REQUIRE(h && params && cb_total && wqkv && wo && w1 && w2, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(aligned(h, 16) && aligned(params, 16) && aligned(cb_total, 16) && (!gb || (aligned(gb, 16) && gb_stride % 4 == 0)),
                 IDB200_EALIGN, "h / params / gamma_beta must be 16-byte aligned");
+    static const bool pair_env = !(getenv("IDB200_ENCODER_PAIR") && atoi(getenv("IDB200_ENCODER_PAIR")) == 0);
+    const long long tiles = (M + 127) / 128;
+    const bool pair = pair_env && tiles >= 2;
     CUtensorMap tqk, tv, two, t1, t2;
-    int rc = make_tmap_bf16_2d(&tqk, wqkv, static_cast<uint64_t>(n_layers) * 768, 256, 128, 64);
+    int rc = make_tmap_bf16_2d(&tqk, wqkv, static_cast<uint64_t>(n_layers) * 768, 256, pair ? 96 : 128, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tv, wqkv, static_cast<uint64_t>(n_layers) * 768, 256, 64, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&two, wo, static_cast<uint64_t>(n_layers) * 256, 256, 128, 64);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&t1, w1, static_cast<uint64_t>(n_layers) * ff, 256, 128, 64);
+    rc = make_tmap_bf16_2d(&t1, w1, static_cast<uint64_t>(n_layers) * ff, 256, pair ? 64 : 128, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&t2, w2, static_cast<uint64_t>(n_layers) * 256, ff, 128, 64);
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(ef::encoder_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ef::encoder_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(ef::encoder_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ef::encoder_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ef::encoder_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ef::encoder_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ef::kSmem);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", ef::kSmem, cudaGetErrorString(e));
         attr = true;
     }
-    const long long tiles = (M + 127) / 128;
-    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    int grid;
+    if (pair) {
+        const long long trips = (tiles + 1) / 2;
+        const long long pairs = trips < num_sms() / 2 ? trips : num_sms() / 2;
+        grid = static_cast<int>(2 * pairs);
+    } else {
+        grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+    }
     ef::Params p{h, params, cb_total, gb, gb_stride, M, L, causal, ff, n_layers, nullptr};
     static const bool prof = getenv("IDB200_PROF") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(ef::kThreads);
+    cfg.dynamicSmemBytes = ef::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pair ? 2 : 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    auto launch = [&](bool profiled) -> cudaError_t {
+        if (pair) return profiled ? cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<true, true>, tqk, tv, two, t1, t2, p)
+                                  : cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<false, true>, tqk, tv, two, t1, t2, p);
+        return profiled ? cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<true, false>, tqk, tv, two, t1, t2, p)
+                        : cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<false, false>, tqk, tv, two, t1, t2, p);
+    };
     if (prof) {                                                           // dev only: synchronous, prints the phase breakdown
         static unsigned long long* dprof = nullptr;
         if (!dprof) cudaMalloc(&dprof, ef::P_N * sizeof(unsigned long long));
         cudaMemsetAsync(dprof, 0, ef::P_N * sizeof(unsigned long long), st);
         p.prof = dprof;
-        ef::encoder_fused_kernel<true><<<grid, ef::kThreads, ef::kSmem, st>>>(tqk, tv, two, t1, t2, p);
+        cudaError_t e = launch(true);
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "encoder_fused_kernel<prof>: %s", cudaGetErrorString(e));
         unsigned long long hp[ef::P_N];
         cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         static const char* names[ef::P_N] = {"load", "ln1", "wait_acc", "epi", "att", "wait_o", "o_write", "wait_h1", "ln2", "wait_acc1", "epi1",
-                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film)"};
+                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film)", "[mma: wait_slot", "wait_compute", "issue]"};
         const double units = static_cast<double>(tiles) * n_layers;
-        fprintf(stderr, "encoder_fused prof (cycles per tile-layer, L=%d):", L);
+        fprintf(stderr, "encoder_fused prof (cycles per tile-layer, L=%d, pair=%d):", L, pair ? 1 : 0);
         double tot = 0;
         for (int i = 0; i < ef::P_N; ++i) { fprintf(stderr, " %s=%.0f", names[i], hp[i] / units); if (i < ef::P_LNP1) tot += hp[i] / units; }
         fprintf(stderr, " total=%.0f\n", tot);
         return check_launch("encoder_fused_kernel<prof>");
     }
-    ef::encoder_fused_kernel<false><<<grid, ef::kThreads, ef::kSmem, st>>>(tqk, tv, two, t1, t2, p);
+    cudaError_t e = launch(false);
+    if (e != cudaSuccess) return fail(IDB200_ECUDA, "encoder_fused_kernel: %s", cudaGetErrorString(e));
     return check_launch("encoder_fused_kernel");
 }
 
