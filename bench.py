@@ -49,7 +49,7 @@ DENSE_FLOPS = {
     "idb200_mlp_block": lambda a: 4.0 * a[9] * a[11] * a[12],
     "idb200_attn_block": _attn_block_flops,
     # every layer of the encoder in one launch: n_layers * M * (QKV + out-proj + attention + MLP)
-    "idb200_encoder_fused": lambda a: float(a[14]) * a[9] * (2.0 * a[11] * 3 * a[11] + 2.0 * a[11] * a[11] + 4.0 * a[10] * a[11] + 4.0 * a[11] * a[13]),
+    "idb200_encoder_fused": lambda a: float(a[15]) * a[10] * (2.0 * a[12] * 3 * a[12] + 2.0 * a[12] * a[12] + 4.0 * a[11] * a[12] + 4.0 * a[12] * a[14]),
 }
 
 

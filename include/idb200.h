@@ -247,17 +247,20 @@ int idb200_mlp_block(float* h, const float* ln_w, const float* ln_b, const float
                      idb200_stream_t stream);
 
 /* K3f  the whole TransformerEncoder (every layer of src/models/transformer.py:73-82) in ONE persistent tcgen05 kernel,
- * d_model = 256, 8 heads, d_ff % 128 == 0 (<= 1024), L | 128, M % L == 0.  A CTA carries a 128-token tile through all
- * layers with the fp32 residual stream resident in tensor memory; h is read and written once.
- *   layer_params fp32, per layer: [ln1_w 256 | ln1_b 256 | cb1 256 | bqkv_packed 768 | ln2_w 256 | ln2_b 256 | cb2 256 | 0.5 * b1 (ff)]
- *     cb1 / cb2 = sum of the out_proj / ff.2 biases of everything accumulated into h before that LayerNorm
- *     (the accumulating GEMMs never add their bias; LayerNorm reads h + cb), bias_total [256] = the final sum.
- *   gamma_beta: FiLM rows of trajectory m / L at stride gb_stride floats, [2 * n_layers][gamma 256 | beta 256]
- *     (row 2l = film1 of layer l, 2l+1 = film2), or NULL.
+ * d_model = 256, 8 heads, d_ff % 128 == 0 (<= 1024), L | 128, M % L == 0.  A CTA (pair) carries a 128-token tile through
+ * all layers with the fp32 residual stream resident in tensor memory; h is read and written once.
+ *   layer_params fp32, per layer: [ln1_w 256 | ln1_b 256 | pend1 256 | bqkv_packed 768 | ln2_w 256 | ln2_b 256 | pend2 256 |
+ *     0.5 * b1 (ff)].  pend1 / pend2 = the bias of the GEMM that accumulated into h just before that LayerNorm (ff.2 bias of
+ *     the previous layer, zero for layer 0 / out_proj bias of this layer): the accumulating GEMMs never add their own bias,
+ *     the LayerNorm that follows does.  bias_last [256] = ff.2 bias of the last layer (added when h is written back).
+ *   film: per-trajectory rows of trajectory m / L at stride film_stride floats, [2 * n_layers][512] (row 2l = film1 of layer
+ *     l, 2l+1 = film2), or NULL.  film_folded == 0: rows are [gamma | beta] (a = LN(h) * (1 + gamma) + beta); != 0: rows are
+ *     [scale | shift] with the LayerNorm affine folded in, scale = ln_w * (1 + gamma), shift = ln_b * (1 + gamma) + beta
+ *     (a = n * scale + shift, n = the normalised row) -- both are linear in cond_vec, so the host folds them into the FiLM GEMM.
  *   wqkv_packed bf16 [n_layers*768, 256] (per layer head-group-major, see idb200_attn_block), wo bf16 [n_layers*256, 256],
  *   w1 bf16 [n_layers*ff, 256], w2 bf16 [n_layers*256, ff]. */
-int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_total, const float* gamma_beta,
-                         int64_t gb_stride, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
+int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_last, const float* film, int64_t film_stride,
+                         int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
                          int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream);
 
 /* K4 (tensor-core path)  two-layer MazeEncoder conv stack of src/models/encoders.py:15-24 in one launch:

@@ -269,6 +269,68 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     }
 }
 
+// d % 4 == 0, 16-byte aligned rows: a warp handles the L tokens of one trajectory; a lane owns float4 column groups
+// {lane, lane + 32, ...} (kV of them), keeps the trajectory's row_a + row_b and its slice of Wf in registers (F <= kF)
+// and streams the tokens: per token one table-row read (L1/L2 resident) and one coalesced float4 store of h.
+// Same arithmetic order as embed_kernel: fma chain over the features, then + tab + row_a + row_b.
+template <int kF, int kV>
+__global__ void __launch_bounds__(256) embed_traj_kernel(const EmbedParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int F = p.n0 + p.n1 + p.n2;
+    const long long B = p.M / p.L;
+    const int d4 = p.d >> 2;
+    float4 w[kF][kV];
+#pragma unroll
+    for (int j = 0; j < kF; ++j)
+#pragma unroll
+        for (int v = 0; v < kV; ++v)
+            w[j][v] = (j < F && lane + 32 * v < d4) ? __ldg(reinterpret_cast<const float4*>(p.Wf + j * p.d) + lane + 32 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long b = warp; b < B; b += nwarps) {
+        float4 ra[kV], rb[kV];
+#pragma unroll
+        for (int v = 0; v < kV; ++v) {
+            if (lane + 32 * v < d4) {
+                ra[v] = __ldg(reinterpret_cast<const float4*>(p.row_a + b * p.row_a_stride) + lane + 32 * v);
+                rb[v] = __ldg(reinterpret_cast<const float4*>(p.row_b + b * p.d) + lane + 32 * v);
+            }
+        }
+#pragma unroll 2
+        for (int t = 0; t < p.L; ++t) {
+            const long long m = b * p.L + t;
+            float f[kF];
+#pragma unroll
+            for (int j = 0; j < kF; ++j) {
+                float v = 0.0f;
+                if (j < p.n0) v = p.src0[m * p.n0 + j];
+                else if (j < p.n0 + p.n1) v = p.src1[m * p.n1 + (j - p.n0)];
+                else if (j < F) v = p.src2[m * p.n2 + (j - p.n0 - p.n1)] ? 1.0f : 0.0f;
+                f[j] = v;
+            }
+            const long long trow = p.tab_idx ? p.tab_idx[m] : t;
+            const float4* tab = reinterpret_cast<const float4*>(p.tab + trow * p.d);
+            float4* out = reinterpret_cast<float4*>(p.h + m * p.d);
+#pragma unroll
+            for (int v = 0; v < kV; ++v) {
+                if (lane + 32 * v < d4) {
+                    const float4 tb = __ldg(tab + lane + 32 * v);
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < kF; ++j) {
+                        acc.x = fmaf(f[j], w[j][v].x, acc.x);
+                        acc.y = fmaf(f[j], w[j][v].y, acc.y);
+                        acc.z = fmaf(f[j], w[j][v].z, acc.z);
+                        acc.w = fmaf(f[j], w[j][v].w, acc.w);
+                    }
+                    out[lane + 32 * v] = make_float4(acc.x + tb.x + ra[v].x + rb[v].x, acc.y + tb.y + ra[v].y + rb[v].y,
+                                                     acc.z + tb.z + ra[v].z + rb[v].z, acc.w + tb.w + ra[v].w + rb[v].w);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (eps = 1e-5, affine) + FiLM: a = LN(h) * (1 + gamma[b]) + beta[b]   (transformer.py:28-41)
 //   one warp per token, row held in registers (d <= 512), two-pass variance like ATen.
@@ -458,6 +520,15 @@ extern "C" int idb200_embed_tokens(const float* src0, int n0, const float* src1,
     if (M == 0) return IDB200_OK;
     IDB_REQUIRE(src0 && Wf && tab && row_a && row_b && h, IDB200_EINVAL, "NULL pointer");
     EmbedParams p{src0, n0, src1, n1, src2, n2, Wf, tab, reinterpret_cast<const long long*>(tab_idx), row_a, row_a_stride, row_b, h, M, L, d};
+    const int F = n0 + n1 + n2;
+    const bool vec = d % 4 == 0 && d <= 256 && F <= 8 && M % L == 0 && aligned(Wf, 16) && aligned(tab, 16) && aligned(row_a, 16) &&
+                     aligned(row_b, 16) && aligned(h, 16) && row_a_stride % 4 == 0;
+    if (vec) {
+        const int grid = warp_grid(M / L);
+        if (d <= 128) embed_traj_kernel<8, 1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        else embed_traj_kernel<8, 2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        return check_launch("embed_traj_kernel");
+    }
     embed_kernel<<<warp_grid(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("embed_kernel");
 }

@@ -68,7 +68,7 @@ constexpr uint32_t kColAcc = 256;                   // TMEM scratch columns
 struct Params {
     float* h;                   // [M, 256] fp32 residual stream (in/out)
     const float* params;        // per layer: PA (1536 floats) | PM (768 + ff floats)
-    const float* cb_total;      // [256] sum of all accumulate-GEMM biases (added when h is written back)
+    const float* cb_total;      // [256] pending bias of the last layer's ff.2 (added when h is written back)
     const float* gb;            // FiLM [B, 2 * n_layers, 512] rows = [gamma | beta] per LayerNorm, or nullptr
     long long gb_stride;        // floats between trajectories
     long long M;
@@ -76,6 +76,7 @@ struct Params {
     int causal;
     int ff;
     int n_layers;
+    int film_mode;              // kFilmNone / kFilmRaw ([gamma | beta]) / kFilmFolded ([scale | shift], LayerNorm affine folded in)
     unsigned long long* prof;   // dev: [P_N] cycle sums (kProf kernels only)
 };
 
@@ -87,44 +88,62 @@ __device__ __forceinline__ float silu_half(float acc, float hb) {
     return fmaf(hx, t, hx);
 }
 
-// LayerNorm(eps 1e-5) * (1 + gamma) + beta of the tile's rows, read from the TMEM-resident residual stream.
-// Thread <-> (row, column quarter `part`): statistics are in-thread sums over 64 columns (shifted by the first element)
-// merged with the other three quarters' through shared memory (Chan's formula).  Output: the bf16 SWIZZLE_128B
-// k-block `part` of the A operand X.
-// film: this thread's trajectory FiLM row [gamma 256 | beta 256] -- in shared memory (kFilmSmem: staged by bulk copies,
-// wait on film_full before the first read) or in global memory -- or nullptr (no FiLM / dead row).
+// LayerNorm(eps 1e-5) + FiLM of the tile's rows, read from the TMEM-resident residual stream.
+// Thread <-> (row, column quarter `part`).  Pass 1 adds the pending bias of the last accumulating GEMM (which never adds
+// its own), writes the row back to TMEM, and sums statistics in-thread over its 64 columns (shifted by the first
+// element), merged with the other three quarters' through shared memory (Chan's formula).  Pass 2 normalises and
+// writes the bf16 SWIZZLE_128B k-block `part` of the A operand X.
+// film: this thread's trajectory row of 512 floats, or nullptr (dead row: plain LayerNorm affine).  mode:
+//   kFilmFolded  [scale | shift] with the LayerNorm affine already folded in: y = n * scale + shift
+//   kFilmRaw     [gamma | beta]: y = (n * w + b) * (1 + gamma) + beta        kFilmNone  y = n * w + b
+// kFilmSmem: the row is in shared memory (staged by bulk copies; wait on film_full first), else in global memory.
+enum { kFilmNone = 0, kFilmRaw = 1, kFilmFolded = 2 };
+// explicit shared-space 16-byte load (pointer selects hide the address space from the compiler: generic LD is ~3x slower here)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 template <bool kFilmSmem>
-__device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const float* sb, const float* scb, const float* film,
+__device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const float* sb, const float* spend, const float* film, int mode,
                                      uint64_t* film_full, uint32_t film_parity, float2* stat, uint8_t* X, int row, int part, long long* tt) {
     __builtin_assume(__isShared(sw));
     __builtin_assume(__isShared(sb));
-    __builtin_assume(__isShared(scb));
+    __builtin_assume(__isShared(spend));
     __builtin_assume(__isShared(stat));
     __builtin_assume(__isShared(X));
     if (kFilmSmem && film != nullptr) __builtin_assume(__isShared(film));
     const int c0 = part * 64;
     const uint32_t t0 = tmem_row + c0;
-    // ---- pass 1: statistics (both 32-column loads in flight) ----
+    // ---- pass 1: x = h + pending bias -> TMEM; statistics (both 32-column loads in flight) ----
     float xs, s1 = 0.0f, s2 = 0.0f;
     {
         uint32_t r[2][32];
         tmem_ld_32x32(t0, r[0]);
         tmem_ld_32x32(t0 + 32, r[1]);
         tmem_ld_wait();
-        const float4* cb4 = reinterpret_cast<const float4*>(scb + c0);
-        xs = __uint_as_float(r[0][0]) + cb4[0].x;
+        const uint32_t pb4 = smem_u32(spend + c0);
+        xs = __uint_as_float(r[0][0]) + lds128(pb4).x;
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 2; ++u) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 cb = cb4[u * 8 + j];
-                const float d0 = __uint_as_float(r[u][4 * j + 0]) + (cb.x - xs), d1 = __uint_as_float(r[u][4 * j + 1]) + (cb.y - xs);
-                const float d2 = __uint_as_float(r[u][4 * j + 2]) + (cb.z - xs), d3 = __uint_as_float(r[u][4 * j + 3]) + (cb.w - xs);
+                const float4 pb = lds128(pb4 + (u * 8 + j) * 16);
+                const float x0 = __uint_as_float(r[u][4 * j + 0]) + pb.x, x1 = __uint_as_float(r[u][4 * j + 1]) + pb.y;
+                const float x2 = __uint_as_float(r[u][4 * j + 2]) + pb.z, x3 = __uint_as_float(r[u][4 * j + 3]) + pb.w;
+                r[u][4 * j + 0] = __float_as_uint(x0);
+                r[u][4 * j + 1] = __float_as_uint(x1);
+                r[u][4 * j + 2] = __float_as_uint(x2);
+                r[u][4 * j + 3] = __float_as_uint(x3);
+                const float d0 = x0 - xs, d1 = x1 - xs, d2 = x2 - xs, d3 = x3 - xs;
                 s1 += (d0 + d1) + (d2 + d3);
                 s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
             }
+            tmem_st_32x32(t0 + u * 32, r[u]);
+        }
     }
     stat[part * 128 + row] = make_float2(xs + s1 * (1.0f / 64.0f), s2 - s1 * s1 * (1.0f / 64.0f));
+    tmem_st_wait();
     if (tt) tt[0] = clock64();
     named_barrier_sync(3, kCT);
     if (tt) tt[1] = clock64();
@@ -144,29 +163,39 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
     tmem_ld_32x32(t0, r[0]);
     tmem_ld_32x32(t0 + 32, r[1]);
     uint8_t* xt = X + part * kTile;
+    // scale / shift: the folded FiLM row (staged in shared memory, or in global memory when L < 8) or the LayerNorm affine
+    const bool folded = (mode == kFilmFolded) && film != nullptr;
+    const bool raw = (mode == kFilmRaw) && film != nullptr;
+    const bool gfold = !kFilmSmem && folded;
+    const uint32_t scs = smem_u32((kFilmSmem && folded) ? film : sw) + c0 * 4;
+    const uint32_t shs = smem_u32((kFilmSmem && folded) ? film + 256 : sb) + c0 * 4;
+    const uint32_t fls = (kFilmSmem && raw) ? smem_u32(film) + c0 * 4 : 0u;
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
         tmem_ld_wait();
         const int col = c0 + cc * 32;
-        const float4* cb4 = reinterpret_cast<const float4*>(scb + col);
-        const float4* w4 = reinterpret_cast<const float4*>(sw + col);
-        const float4* b4 = reinterpret_cast<const float4*>(sb + col);
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {                                 // 8 columns -> one 16-byte swizzle chunk
             float y[8];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int j = j2 * 2 + u;
-                const float4 cb = cb4[j], w = w4[j], b = b4[j];
-                // ((x + cb) - mean) * rstd = x * rstd + (cb * rstd + shift)
-                y[4 * u + 0] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 0]), rstd, fmaf(cb.x, rstd, shift)), w.x, b.x);
-                y[4 * u + 1] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 1]), rstd, fmaf(cb.y, rstd, shift)), w.y, b.y);
-                y[4 * u + 2] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 2]), rstd, fmaf(cb.z, rstd, shift)), w.z, b.z);
-                y[4 * u + 3] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 3]), rstd, fmaf(cb.w, rstd, shift)), w.w, b.w);
-                if (film != nullptr) {
+                float4 sc, sh;
+                if (!gfold) {
+                    sc = lds128(scs + (cc * 8 + j) * 16);
+                    sh = lds128(shs + (cc * 8 + j) * 16);
+                } else {
+                    sc = __ldg(reinterpret_cast<const float4*>(film + col) + j);
+                    sh = __ldg(reinterpret_cast<const float4*>(film + 256 + col) + j);
+                }
+                y[4 * u + 0] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 0]), rstd, shift), sc.x, sh.x);
+                y[4 * u + 1] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 1]), rstd, shift), sc.y, sh.y);
+                y[4 * u + 2] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 2]), rstd, shift), sc.z, sh.z);
+                y[4 * u + 3] = fmaf(fmaf(__uint_as_float(r[cc][4 * j + 3]), rstd, shift), sc.w, sh.w);
+                if (raw) {
                     const float4* f4 = reinterpret_cast<const float4*>(film + col) + j;
-                    const float4 g = kFilmSmem ? f4[0] : __ldg(f4);
-                    const float4 t = kFilmSmem ? f4[64] : __ldg(f4 + 64);
+                    const float4 g = kFilmSmem ? lds128(fls + (cc * 8 + j) * 16) : __ldg(f4);
+                    const float4 t = kFilmSmem ? lds128(fls + 1024 + (cc * 8 + j) * 16) : __ldg(f4 + 64);
                     y[4 * u + 0] = fmaf(y[4 * u + 0], 1.0f + g.x, t.x);
                     y[4 * u + 1] = fmaf(y[4 * u + 1], 1.0f + g.y, t.y);
                     y[4 * u + 2] = fmaf(y[4 * u + 2], 1.0f + g.z, t.z);
@@ -586,8 +615,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 mbar_wait(pa_full, n_p & 1, 50);
                 stamp(P_WPA);
                 long long tt[3] = {0, 0, 0};
-                if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
-                else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * 512 : nullptr, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * 512 : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -671,8 +700,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 ++n_h;
                 tc_fence_after();
                 stamp(P_WH1);
-                if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
-                else ln_tmem<false>(tmem_row, sPM, sPM + 256, sPM + 512, gbtraj ? gbtraj + (2 * l + 1) * 512 : nullptr, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                else ln_tmem<false>(tmem_row, sPM, sPM + 256, sPM + 512, gbtraj ? gbtraj + (2 * l + 1) * 512 : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -766,9 +795,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
 
 }  // namespace ef
 
-int encoder_fused(float* h, const float* params, const float* cb_total, const float* gb, long long gb_stride, const void* wqkv,
-                  const void* wo, const void* w1, const void* w2, long long M, int L, int d, int H, int ff, int n_layers, int causal,
-                  cudaStream_t st) {
+int encoder_fused(float* h, const float* params, const float* cb_total, const float* gb, long long gb_stride, int film_folded,
+                  const void* wqkv, const void* wo, const void* w1, const void* w2, long long M, int L, int d, int H, int ff, int n_layers,
+                  int causal, cudaStream_t st) {
     IDB_REQUIRE(d == kD && H == 8, IDB200_EUNSUPPORTED, "fused encoder is specialised for d_model = 256, 8 heads (got %d, %d)", d, H);
     IDB_REQUIRE(L >= 1 && L <= 128 && (128 % L) == 0, IDB200_EUNSUPPORTED, "fused encoder needs L | 128 (got %d)", L);
     IDB_REQUIRE(ff % 128 == 0 && ff >= 128 && ff <= ef::kMaxFF, IDB200_EUNSUPPORTED, "fused encoder needs d_ff a multiple of 128, <= 1024 (got %d)", ff);
@@ -809,7 +838,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     } else {
         grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     }
-    ef::Params p{h, params, cb_total, gb, gb_stride, M, L, causal, ff, n_layers, nullptr};
+    ef::Params p{h, params, cb_total, gb, gb_stride, M, L, causal, ff, n_layers, gb ? (film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone, nullptr};
     static const bool prof = getenv("IDB200_PROF") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -855,9 +884,9 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
 
 }  // namespace idb200
 
-extern "C" int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_total, const float* gamma_beta,
-                                    int64_t gb_stride, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
+extern "C" int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_last, const float* film, int64_t film_stride,
+                                    int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
                                     int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream) {
-    return idb200::encoder_fused(h, layer_params, bias_total, gamma_beta, gb_stride, wqkv_packed, wo, w1, w2, M, L, d, H, ff, n_layers,
-                                 causal, static_cast<cudaStream_t>(stream));
+    return idb200::encoder_fused(h, layer_params, bias_last, film, film_stride, film_folded, wqkv_packed, wo, w1, w2, M, L, d, H, ff,
+                                 n_layers, causal, static_cast<cudaStream_t>(stream));
 }

@@ -56,18 +56,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef IDB200_WAIT_LIMIT_CYCLES
 #define IDB200_WAIT_LIMIT_CYCLES (8000000000LL)
 #endif
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires), so a
+// waiting warp costs no issue slots and no shared-memory polls -- with 20 warps per CTA, spinning waiters were 40 % of all
+// executed instructions (ncu, round 1) and competed with the warps doing the work.
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, bool backoff) {
-    uint32_t polls = 0;
     long long t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (backoff) __nanosleep(40);
-        if ((++polls & 1023u) == 0) {
-            const long long t = clock64();
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > IDB200_WAIT_LIMIT_CYCLES) {
-                printf("idb200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
-                __trap();
-            }
+    while (!mbar_try_wait_suspend(bar, parity, 1000000u)) {
+        const long long t = clock64();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > IDB200_WAIT_LIMIT_CYCLES) {
+            printf("idb200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
+            __trap();
         }
     }
 }

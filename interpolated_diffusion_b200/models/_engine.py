@@ -61,15 +61,25 @@ def mlp_block(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], W1, b1, W
     return h
 
 
-def encoder_fused(h: torch.Tensor, pk: "PackedEncoder", film: Optional[torch.Tensor], Lseq: int, causal: bool):
+class Film:
+    """FiLM parameters of every LayerNorm of an encoder for a batch of trajectories: ``t`` [B, 2 * n_layers, 2d] fp32.
+    folded = False: rows are [gamma | beta] (transformer.py:37,43: a = LN(h) * (1 + gamma) + beta).
+    folded = True : rows are [scale | shift] with the LayerNorm affine folded in (the form idb200_encoder_fused reads)."""
+
+    def __init__(self, t: torch.Tensor, folded: bool):
+        self.t, self.folded = t, folded
+
+
+def encoder_fused(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causal: bool):
     """Every layer of the encoder in one persistent kernel (idb200_encoder_fused): h stays in tensor memory."""
     M, d = h.shape
     f = pk.fused
-    if film is not None and (film.stride(2) != 1 or film.stride(1) != 2 * d):
-        film = film.contiguous()
-    L.call("idb200_encoder_fused", h.data_ptr(), f["params"].data_ptr(), f["cb_total"].data_ptr(), L.ptr(film),
-           0 if film is None else film.stride(0), f["wqkv"].data_ptr(), f["wo"].data_ptr(), f["w1"].data_ptr(), f["w2"].data_ptr(),
-           M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(h.device))
+    ft = None if film is None else film.t
+    if ft is not None and (ft.stride(2) != 1 or ft.stride(1) != 2 * d):
+        ft = ft.contiguous()
+    L.call("idb200_encoder_fused", h.data_ptr(), f["params"].data_ptr(), f["bias_last"].data_ptr(), L.ptr(ft),
+           0 if ft is None else ft.stride(0), int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(h.device))
     return h
 
 
@@ -154,20 +164,34 @@ class PackedEncoder:
         if self.has_film:
             self.film_w = torch.cat(film_w, dim=0).contiguous()      # [n_layers * 2 * 2d, d_cond]
             self.film_b = torch.cat(film_b, dim=0).contiguous()
+            # LayerNorm affine folded into the FiLM linear (both are linear in cond_vec):
+            #   scale = ln_w * (1 + gamma) = (ln_w * W_g) c + ln_w * (1 + b_g)
+            #   shift = ln_b * (1 + gamma) + beta = (ln_b * W_g + W_b) c + ln_b * (1 + b_g) + b_b
+            d_ = layers[0].norm1.weight.shape[0]
+            fw, fb = [], []
+            for l, e in zip(layers, self.layers):
+                for film, nw, nb in ((l.film1, e["n1w"], e["n1b"]), (l.film2, e["n2w"], e["n2b"])):
+                    W, b = film.weight.detach().float(), film.bias.detach().float()
+                    Wg, Wb, bg, bb = W[:d_], W[d_:], b[:d_], b[d_:]
+                    fw += [nw[:, None] * Wg, nb[:, None] * Wg + Wb]
+                    fb += [nw * (1.0 + bg), nb * (1.0 + bg) + bb]
+            self.film_w_folded = torch.cat(fw, dim=0).contiguous()
+            self.film_b_folded = torch.cat(fb, dim=0).contiguous()
+            self.film_w16 = self.film_w.to(torch.bfloat16).contiguous()
+            self.film_w_folded16 = self.film_w_folded.to(torch.bfloat16).contiguous()
         self.d = layers[0].norm1.weight.shape[0]
         self.ff = layers[0].ff[0].weight.shape[0]
         self.n_heads = layers[0].attn.num_heads
         self.fused = None
         if self.d == 256 and self.n_heads == 8 and self.ff % 128 == 0 and self.ff <= 1024:
             # stacked weights + per-layer parameter blobs of idb200_encoder_fused (layout: include/idb200.h)
-            cb = torch.zeros(self.d, device=self.layers[0]["bo"].device, dtype=torch.float32)
+            pend = torch.zeros(self.d, device=self.layers[0]["bo"].device, dtype=torch.float32)
             blobs = []
             for e in self.layers:
-                cb2 = cb + e["bo"]
-                blobs += [e["n1w"], e["n1b"], cb, e["bqkv_g"], e["n2w"], e["n2b"], cb2, 0.5 * e["b1"]]
-                cb = cb2 + e["b2"]
+                blobs += [e["n1w"], e["n1b"], pend, e["bqkv_g"], e["n2w"], e["n2b"], e["bo"], 0.5 * e["b1"]]
+                pend = e["b2"]
             self.fused = {
-                "params": torch.cat(blobs).contiguous(), "cb_total": cb.contiguous(),
+                "params": torch.cat(blobs).contiguous(), "bias_last": pend.contiguous(),
                 "wqkv": torch.cat([e["wqkv_g"] for e in self.layers], dim=0).contiguous(),
                 "wo": torch.cat([e["wo"] for e in self.layers], dim=0).contiguous(),
                 "w1": torch.cat([e["w1"] for e in self.layers], dim=0).contiguous(),
@@ -175,17 +199,36 @@ class PackedEncoder:
             }
         self._key = key
 
-    def film_params(self, cond_vec: torch.Tensor) -> Optional[torch.Tensor]:
-        """All layers' FiLM [gamma|beta] in one fp32 GEMM: [B, n_layers*2, 2d] (loop-invariant across DDIM steps)."""
+    def fused_path(self, Lseq: int, precision: str = "bf16") -> bool:
+        """True when forward() will run the whole encoder as one kernel (idb200_encoder_fused)."""
+        self._pack()
+        return (precision == "bf16" and self.fuse_encoder and self.fuse_blocks and self.fuse_mlp and self.fused is not None
+                and 1 <= Lseq <= 128 and 128 % Lseq == 0)
+
+    def film_params(self, cond_vec: torch.Tensor, Lseq: Optional[int] = None, precision: str = "bf16") -> Optional[Film]:
+        """FiLM parameters of all layers in one GEMM: [B, n_layers*2, 2d] (loop-invariant across DDIM steps).  With Lseq
+        given and the fused-encoder path selected, the folded [scale | shift] form is produced (same GEMM, folded weights).
+        bf16 mode runs the GEMM on the tensor cores (bf16 operands, fp32 accumulate and output), fp32 mode on CUDA cores."""
         self._pack()
         if not self.has_film or cond_vec is None:
             return None
-        out = sgemm(cond_vec, self.film_w, self.film_b)
-        return out.view(cond_vec.shape[0], len(self.layers) * 2, 2 * self.d)
+        folded = Lseq is not None and self.fused_path(Lseq, precision)
+        B = cond_vec.shape[0]
+        if precision == "bf16" and cond_vec.shape[1] % 64 == 0:
+            out = torch.empty((B, self.film_w.shape[0]), device=cond_vec.device, dtype=torch.float32)
+            gemm_bf16(cond_vec.to(torch.bfloat16).contiguous(), self.film_w_folded16 if folded else self.film_w16,
+                      self.film_b_folded if folded else self.film_b, out, EPI_F32)
+        else:
+            out = sgemm(cond_vec, self.film_w_folded if folded else self.film_w, self.film_b_folded if folded else self.film_b)
+        return Film(out.view(B, len(self.layers) * 2, 2 * self.d), folded)
 
-    def forward(self, h: torch.Tensor, B: int, Lseq: int, film: Optional[torch.Tensor], precision: str = "bf16") -> torch.Tensor:
-        """In-place on the fp32 residual stream h [B*L, d]."""
+    def forward(self, h: torch.Tensor, B: int, Lseq: int, film, precision: str = "bf16") -> torch.Tensor:
+        """In-place on the fp32 residual stream h [B*L, d].  film: Film, a raw [gamma | beta] tensor, or None."""
         self._pack()
+        if isinstance(film, torch.Tensor):
+            film = Film(film, False)
+        if film is not None and film.folded and not self.fused_path(Lseq, precision):
+            raise ValueError("folded FiLM parameters can only be consumed by the fused-encoder path")
         M, d = h.shape
         dev = h.device
         H, ff = self.n_heads, self.ff
@@ -197,6 +240,7 @@ class PackedEncoder:
             fused = fuse_attn and fuse_ln_mlp
             if fused and self.fuse_encoder and self.fused is not None:
                 return encoder_fused(h, self, film, Lseq, causal)
+            film = None if film is None else film.t
             if not fused:
                 a = self.ws.get("a", (M, d), torch.bfloat16, dev)
                 qkv = self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
@@ -219,6 +263,7 @@ class PackedEncoder:
                     gemm_bf16(a, e["w1"], e["b1"], f, EPI_SILU_BF16)
                     gemm_bf16(f, e["w2"], e["b2"], h, EPI_RESID_F32)
         elif precision == "fp32":
+            film = None if film is None else film.t
             a = self.ws.get("a32", (M, d), torch.float32, dev)
             o = self.ws.get("o32", (M, d), torch.float32, dev)
             qkv = self.ws.get("qkv32", (M, 3 * d), torch.float32, dev)

@@ -106,7 +106,7 @@ class InterpLevelDenoiser(nn.Module):
             level_vec = self.level_vector(L.i64c(s))
         pk = self.transformer.packed()
         if film is None:
-            film = pk.film_params(cond_vec)
+            film = pk.film_params(cond_vec, T, self.precision)
         h = self._ws.get("h", (M, d), torch.float32, dev)
         E.embed_tokens(L.f32c(x_s).view(M, D), src1, src2, der["Wf"], der["tab"], None, level_vec, row_b, h, M, T, d)
         pk.forward(h, B, T, film, self.precision)

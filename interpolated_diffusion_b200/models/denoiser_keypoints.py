@@ -128,7 +128,7 @@ class KeypointDenoiser(nn.Module):
             t_vec = self.timestep_vector(L.i64c(t))
         pk = self.transformer.packed()
         if film is None:
-            film = pk.film_params(cond_vec)
+            film = pk.film_params(cond_vec, K, self.precision)
         M = B * K
         h = self._ws.get("h", (M, d), torch.float32, dev)
         E.embed_tokens(z.view(M, D), None if kp_feat is None else kp_feat.view(M, -1), km.view(M, D), der["Wf"], der["tab"],

@@ -51,6 +51,6 @@ class TransformerEncoder(nn.Module):
         h = x.detach().float().contiguous().clone().view(B * Lseq, d)
         pk = self.packed()
         if film is None and cond is not None:
-            film = pk.film_params(cond.detach().float().contiguous())
+            film = pk.film_params(cond.detach().float().contiguous(), Lseq, self.precision)
         pk.forward(h, B, Lseq, film, self.precision)
         return h.view(B, Lseq, d)

@@ -222,7 +222,7 @@ def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optiona
     ab = sched["alpha_bar_host"]
     cond_vec = kp_model.encode_cond(cond)
     pk = kp_model.transformer.packed()
-    film = pk.film_params(cond_vec)
+    film = pk.film_params(cond_vec, K, kp_model.precision)
     row_b = _cond_row(kp_model, cond_vec, T, dev)
     t_vecs = _cached(kp_model, ("t_vecs", tuple(times), str(dev)), [kp_model.t_embed[0].weight, kp_model.t_embed[0].bias, kp_model.t_embed[2].weight, kp_model.t_embed[2].bias],
                      lambda: kp_model.timestep_vector(torch.tensor(times[:-1], device=dev, dtype=torch.long)))
@@ -237,7 +237,7 @@ def generate(kp_model, interp_model, cond: Dict[str, torch.Tensor], cfg: Optiona
     # 7-10. Stage 2
     cond_vec2 = interp_model.encode_cond(cond)
     pk2 = interp_model.transformer.packed()
-    film2 = pk2.film_params(cond_vec2)
+    film2 = pk2.film_params(cond_vec2, T, interp_model.precision)
     row_b2 = _cond_row(interp_model, cond_vec2, T, dev)
     ac = dict(conf_teacher=cfg.anchor_conf_teacher, conf_student=cfg.anchor_conf_student,
               conf_endpoints=cfg.anchor_conf_endpoints, conf_missing=cfg.anchor_conf_missing,

@@ -154,7 +154,7 @@ def test_denoisers_full_size_vs_oracle(precision, tol):
     assert _maxabs(got, ref) < tol, _maxabs(got, ref)
     # hoisted loop-invariants give the same result as the plain call
     cv = il.encode_cond(_cuda(cond))
-    got2 = il(x.cuda(), s.cuda(), mask_in.cuda(), None, cond_vec=cv, film=il.transformer.packed().film_params(cv),
+    got2 = il(x.cuda(), s.cuda(), mask_in.cuda(), None, cond_vec=cv, film=il.transformer.packed().film_params(cv, T, il.precision),
               level_vec=il.level_vector(torch.tensor([3]).cuda()))
     assert _maxabs(got2, got) < 1e-6
 

@@ -12,9 +12,9 @@ pk = enc.packed()
 for L in Ls:
     h = torch.randn((B * L, 256), device="cuda")
     cv = torch.randn((B, 128), device="cuda")
-    film = pk.film_params(cv) if not os.environ.get("NOFILM") else None
     for mode in modes:
         pk.fuse_encoder = mode == "encoder"
+        film = pk.film_params(cv, L) if not os.environ.get("NOFILM") else None
         for _ in range(2): pk.forward(h.clone(), B, L, film)
         hh = h.clone()
         torch.cuda.synchronize()
