@@ -271,6 +271,15 @@ int idb200_conv_encoder_tc(const float* occ, const float* sdf, int64_t B, int H,
                            const float* w0, const float* b0, const void* w1_packed_bf16, const float* b1, float* pooled,
                            idb200_stream_t stream);
 
+/* Batched trajectory metrics, src/eval/metrics.py:68-128 (compute_metrics_batch; _pos_to_cell :13-24): the step right after
+ * the generation path (the reference loops over samples on the host, sample_generate.py:1323-1398).
+ *   occ fp32 [B,H,W] (occ_stride = H*W, or 0 to broadcast one map); traj fp32 [B,T,D], dims 0:2 = (x, y) in [0,1];
+ *   goal fp32 [B,D] (goal_stride = D or 0); gt fp32 [B,T,D] or NULL (gt_stride = T*D or 0); success_thr = 1 / W as fp32.
+ *   out fp32 [B, n_out]: collision_rate, goal_dist, success, path_length, smoothness (0 if T < 3) [, mse_to_gt if n_out == 6]. */
+int idb200_traj_metrics(const float* occ, int64_t occ_stride, const float* traj, const float* goal, int64_t goal_stride,
+                        const float* gt, int64_t gt_stride, int64_t B, int T, int D, int H, int W, float success_thr,
+                        float* out, int n_out, idb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

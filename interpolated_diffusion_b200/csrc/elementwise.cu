@@ -249,3 +249,89 @@ extern "C" int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student,
         conf_student, conf_endpoints, conf_missing, clamp_endpoints, B, T, C, conf, mask_in);
     return check_launch("anchor_conf_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Batched trajectory metrics (src/eval/metrics.py:13-24, 68-128): one warp per trajectory, lanes stride the timesteps.
+//   collision_rate = mean_t [occ[b, i(t), j(t)] > 0.5  or  position outside [0,1]^2],  (i, j) = round-half-even cell
+//   goal_dist = ||traj[T-1] - goal||, success = goal_dist < thr (thr = 1 / W as fp32, passed by the host),
+//   path_length = sum_t ||traj[t+1] - traj[t]||, smoothness = mean_t ||traj[t+2] - 2 traj[t+1] + traj[t]|| (0 if T < 3),
+//   mse_to_gt = mean over (t, d) of (traj - gt)^2.  occ_stride / goal_stride / gt_stride = 0 broadcast one row.
+// ------------------------------------------------------------------------------------------------
+namespace idb200 {
+__global__ void __launch_bounds__(256) traj_metrics_kernel(const float* __restrict__ occ, long long occ_stride, const float* __restrict__ traj,
+                                                           const float* __restrict__ goal, long long goal_stride,
+                                                           const float* __restrict__ gt, long long gt_stride, long long B, int T, int D,
+                                                           int H, int W, float thr, float* __restrict__ out, int n_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const float sw = static_cast<float>(W - 1 > 1 ? W - 1 : 1), sh = static_cast<float>(H - 1 > 1 ? H - 1 : 1);
+    for (long long b = warp; b < B; b += nwarps) {
+        const float* x = traj + b * T * D;
+        const float* oc = occ + b * occ_stride;
+        const float* g = gt ? gt + b * gt_stride : nullptr;
+        float coll = 0.0f, plen = 0.0f, smooth = 0.0f, mse = 0.0f;
+        for (int t = lane; t < T; t += 32) {
+            const float px = x[t * D], py = x[t * D + 1];
+            const bool oob = (px < 0.0f) | (px > 1.0f) | (py < 0.0f) | (py > 1.0f);
+            int j = static_cast<int>(rintf(px * sw)), i = static_cast<int>(rintf(py * sh));
+            i = min(max(i, 0), H - 1);
+            j = min(max(j, 0), W - 1);
+            coll += (oob || oc[i * W + j] > 0.5f) ? 1.0f : 0.0f;
+            float d1 = 0.0f, d2 = 0.0f;
+            for (int d = 0; d < D; ++d) {
+                const float v = x[t * D + d];
+                if (t + 1 < T) {
+                    const float e = x[(t + 1) * D + d] - v;
+                    d1 += e * e;
+                }
+                if (t + 2 < T) {
+                    const float a = x[(t + 2) * D + d] - 2.0f * x[(t + 1) * D + d] + v;
+                    d2 += a * a;
+                }
+                if (g) {
+                    const float e = v - g[t * D + d];
+                    mse += e * e;
+                }
+            }
+            if (t + 1 < T) plen += sqrtf(d1);
+            if (t + 2 < T) smooth += sqrtf(d2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            coll += __shfl_xor_sync(0xffffffffu, coll, o);
+            plen += __shfl_xor_sync(0xffffffffu, plen, o);
+            smooth += __shfl_xor_sync(0xffffffffu, smooth, o);
+            mse += __shfl_xor_sync(0xffffffffu, mse, o);
+        }
+        if (lane == 0) {
+            const float* gl = goal + b * goal_stride;
+            float gd = 0.0f;
+            for (int d = 0; d < D; ++d) {
+                const float e = x[(T - 1) * D + d] - gl[d];
+                gd += e * e;
+            }
+            gd = sqrtf(gd);
+            float* o = out + b * n_out;
+            o[0] = coll / static_cast<float>(T);
+            o[1] = gd;
+            o[2] = gd < thr ? 1.0f : 0.0f;
+            o[3] = plen;
+            o[4] = T < 3 ? 0.0f : smooth / static_cast<float>(T - 2);
+            if (n_out > 5) o[5] = mse / static_cast<float>(T * D);
+        }
+    }
+}
+}  // namespace idb200
+
+extern "C" int idb200_traj_metrics(const float* occ, int64_t occ_stride, const float* traj, const float* goal, int64_t goal_stride,
+                                   const float* gt, int64_t gt_stride, int64_t B, int T, int D, int H, int W, float success_thr,
+                                   float* out, int n_out, idb200_stream_t stream) {
+    IDB_REQUIRE(occ && traj && goal && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && T >= 1 && D >= 2 && H >= 1 && W >= 1, IDB200_EINVAL, "bad shape (traj needs at least the two position dims)");
+    IDB_REQUIRE(n_out == 5 || (n_out == 6 && gt), IDB200_EINVAL, "n_out must be 5, or 6 with gt");
+    if (B == 0) return IDB200_OK;
+    idb200::traj_metrics_kernel<<<idb200::grid_for(B, 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        occ, occ_stride, traj, goal, goal_stride, gt, gt_stride, B, T, D, H, W, success_thr, out, n_out);
+    return idb200::check_launch("traj_metrics_kernel");
+}
