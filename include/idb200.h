@@ -263,6 +263,32 @@ int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_
                          int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
                          int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream);
 
+/* The whole denoiser forward around the encoder in the same launch (denoiser_keypoints.py:102-113,
+ * denoiser_interp_levels.py:71-84): token assembly + in_proj as the tile prologue, the `out` Linear as the tile epilogue.
+ *   embed != NULL: h is not read; the tile's rows are built as in idb200_embed_tokens (same fp32 operation order).
+ *   head  != NULL: h is not written; y[M, D] = (h + bias_last) . W^T + bias, D <= 4.
+ *   h may be NULL when both are given.  Everything else as idb200_encoder_fused. */
+typedef struct {
+    const float* src0; int n0;                    /* [M, n0] fp32 token features */
+    const float* src1; int n1;                    /* [M, n1] fp32 or NULL */
+    const uint8_t* src2; int n2;                  /* [M, n2] uint8 (0/1) or NULL;  n0 + n1 + n2 <= 16 */
+    const float* Wf;                              /* [n0+n1+n2, 256] fp32 */
+    const float* tab;                             /* [rows, 256] fp32 */
+    const int64_t* tab_idx;                       /* [M] row of tab per token, or NULL: the token's position in its trajectory */
+    const float* row_a; int64_t row_a_stride;     /* [B or 1, 256] fp32 (stride 0 broadcasts one row) */
+    const float* row_b;                           /* [B, 256] fp32 */
+} idb200_embed_t;
+typedef struct {
+    const float* W;                               /* [D, 256] fp32 */
+    const float* bias;                            /* [D] */
+    float* y;                                     /* [M, D] */
+    int D;
+} idb200_head_t;
+int idb200_denoiser_fused(const idb200_embed_t* embed, const idb200_head_t* head, float* h, const float* layer_params,
+                          const float* bias_last, const float* film, int64_t film_stride, int film_folded,
+                          const void* wqkv_packed, const void* wo, const void* w1, const void* w2, int64_t M, int L, int d,
+                          int H, int ff, int n_layers, int causal, idb200_stream_t stream);
+
 /* K4 (tensor-core path)  two-layer MazeEncoder conv stack of src/models/encoders.py:15-24 in one launch:
  * conv3x3(cin->c1)+SiLU on CUDA cores into a shared-memory bf16 channels-last tile, conv3x3(c1->c2)+SiLU as an
  * implicit GEMM (mma.sync bf16, fp32 accumulate), spatial mean -> pooled [B, c2].

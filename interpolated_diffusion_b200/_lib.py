@@ -42,12 +42,24 @@ _SIGS = {
     "idb200_attn_block": [c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p],
     "idb200_mlp_block": [c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
     "idb200_encoder_fused": [c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "idb200_denoiser_fused": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "idb200_conv_encoder_tc": [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
     "idb200_traj_metrics": [c_p, c_l, c_p, c_p, c_l, c_p, c_l, c_l, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_p],
     "idb200_anchor_conf": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_l, c_i, c_i, c_p, c_p, c_p],
 }
 
 EINVAL, EALIGN, EUNSUPPORTED, ECUDA = -1, -2, -3, -4
+
+
+class EmbedDesc(ctypes.Structure):
+    """idb200_embed_t (include/idb200.h)."""
+    _fields_ = [("src0", c_p), ("n0", c_i), ("src1", c_p), ("n1", c_i), ("src2", c_p), ("n2", c_i), ("Wf", c_p), ("tab", c_p),
+                ("tab_idx", c_p), ("row_a", c_p), ("row_a_stride", c_l), ("row_b", c_p)]
+
+
+class HeadDesc(ctypes.Structure):
+    """idb200_head_t (include/idb200.h)."""
+    _fields_ = [("W", c_p), ("bias", c_p), ("y", c_p), ("D", c_i)]
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -76,6 +76,22 @@ struct Params {
     int causal;
     int ff;
     int n_layers;
+    // optional fused token assembly (replaces the read of h): idb200_embed_tokens semantics
+    const float* e_src0;        // [M, n0] fp32, or nullptr: read h
+    const float* e_src1;        // [M, n1] fp32 or nullptr
+    const unsigned char* e_src2;  // [M, n2] uint8 or nullptr
+    int e_n0, e_n1, e_n2;
+    const float* e_wf;          // [n0+n1+n2, 256]
+    const float* e_tab;         // [rows, 256]
+    const long long* e_tab_idx; // [M] or nullptr (row = position in the trajectory)
+    const float* e_row_a;       // [B or 1, 256]
+    long long e_row_a_stride;
+    const float* e_row_b;       // [B, 256]
+    // optional fused output head (replaces the write of h): y[M, D] = (h + bias_last) . W^T + b
+    const float* o_w;           // [D, 256] or nullptr: write h
+    const float* o_b;           // [D]
+    float* o_y;                 // [M, D]
+    int o_D;                    // <= 4
     int film_mode;              // kFilmNone / kFilmRaw ([gamma | beta]) / kFilmFolded ([scale | shift], LayerNorm affine folded in)
     unsigned long long* prof;   // dev: [P_N] cycle sums (kProf kernels only)
 };
@@ -589,7 +605,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
             const long long m = m0 + row;
             const bool live = m < p.M;
             // ---- residual stream tile -> TMEM (this thread: its row, columns part*64 .. +63) ----
-            {
+            if (p.e_src0 == nullptr) {
                 const float4* src = reinterpret_cast<const float4*>(p.h + m * kD + part * 64);
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -601,6 +617,56 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                         r[4 * j + 1] = __float_as_uint(v.y);
                         r[4 * j + 2] = __float_as_uint(v.z);
                         r[4 * j + 3] = __float_as_uint(v.w);
+                    }
+                    tmem_st_32x32(tmem_row + part * 64 + cc * 32, r);
+                }
+                tmem_st_wait();
+            } else {
+                // fused token assembly + in_proj (idb200_embed_tokens; same fp32 operation order):
+                //   h[m, :] = [src0 | src1 | src2][m, :] . Wf + tab[row] + row_a[b] + row_b[b]
+                const int F = p.e_n0 + p.e_n1 + p.e_n2;
+                float f[16];
+                long long trow = 0, bb = 0;
+                if (live) {
+                    bb = m / L;
+                    trow = p.e_tab_idx ? p.e_tab_idx[m] : (m - bb * L);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v = 0.0f;
+                        if (j < p.e_n0) v = p.e_src0[m * p.e_n0 + j];
+                        else if (j < p.e_n0 + p.e_n1) v = p.e_src1[m * p.e_n1 + (j - p.e_n0)];
+                        else if (j < F) v = p.e_src2[m * p.e_n2 + (j - p.e_n0 - p.e_n1)] ? 1.0f : 0.0f;
+                        f[j] = v;
+                    }
+                }
+                const float4* tab4 = reinterpret_cast<const float4*>(p.e_tab + trow * kD) + part * 16;
+                const float4* ra4 = reinterpret_cast<const float4*>(p.e_row_a + bb * p.e_row_a_stride) + part * 16;
+                const float4* rb4 = reinterpret_cast<const float4*>(p.e_row_b + bb * kD) + part * 16;
+                const float4* wf4 = reinterpret_cast<const float4*>(p.e_wf) + part * 16;
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (j < F) {
+                                    const float4 w = __ldg(wf4 + j * (kD / 4) + cc * 8 + j4);
+                                    acc.x = fmaf(f[j], w.x, acc.x);
+                                    acc.y = fmaf(f[j], w.y, acc.y);
+                                    acc.z = fmaf(f[j], w.z, acc.z);
+                                    acc.w = fmaf(f[j], w.w, acc.w);
+                                }
+                            }
+                            const float4 tb = __ldg(tab4 + cc * 8 + j4), a = __ldg(ra4 + cc * 8 + j4), b = __ldg(rb4 + cc * 8 + j4);
+                            acc = make_float4(acc.x + tb.x + a.x + b.x, acc.y + tb.y + a.y + b.y, acc.z + tb.z + a.z + b.z, acc.w + tb.w + a.w + b.w);
+                        }
+                        r[4 * j4 + 0] = __float_as_uint(acc.x);
+                        r[4 * j4 + 1] = __float_as_uint(acc.y);
+                        r[4 * j4 + 2] = __float_as_uint(acc.z);
+                        r[4 * j4 + 3] = __float_as_uint(acc.w);
                     }
                     tmem_st_32x32(tmem_row + part * 64 + cc * 32, r);
                 }
@@ -760,8 +826,42 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 tc_fence_after();
                 stamp(P_WH2);
             }
-            // ---- TMEM -> residual stream (+ the pending biases) ----
-            {
+            // ---- TMEM -> residual stream (+ the pending bias), or straight through the output head ----
+            if (p.o_w != nullptr) {
+                const float4* cbt = reinterpret_cast<const float4*>(p.cb_total + part * 64);
+                uint32_t r[2][32];
+                tmem_ld_32x32(tmem_row + part * 64, r[0]);
+                tmem_ld_32x32(tmem_row + part * 64 + 32, r[1]);
+                tmem_ld_wait();
+                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 cb = __ldg(cbt + cc * 8 + j);
+                        const float x0 = __uint_as_float(r[cc][4 * j + 0]) + cb.x, x1 = __uint_as_float(r[cc][4 * j + 1]) + cb.y;
+                        const float x2 = __uint_as_float(r[cc][4 * j + 2]) + cb.z, x3 = __uint_as_float(r[cc][4 * j + 3]) + cb.w;
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            if (o < p.o_D) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(p.o_w + o * kD + part * 64) + cc * 8 + j);
+                                acc[o] = fmaf(x0, w.x, fmaf(x1, w.y, fmaf(x2, w.z, fmaf(x3, w.w, acc[o]))));
+                            }
+                        }
+                    }
+                float4* hp = reinterpret_cast<float4*>(smem + kOffO + 8192);     // [4 parts][128 rows] partial dot products
+                hp[part * 128 + row] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                named_barrier_sync(3, kCT);
+                if (part == 0 && live) {
+                    const float4 a0 = hp[row], a1 = hp[128 + row], a2 = hp[256 + row], a3 = hp[384 + row];
+                    const float y[4] = {((a0.x + a1.x) + (a2.x + a3.x)), ((a0.y + a1.y) + (a2.y + a3.y)), ((a0.z + a1.z) + (a2.z + a3.z)),
+                                        ((a0.w + a1.w) + (a2.w + a3.w))};
+#pragma unroll
+                    for (int o = 0; o < 4; ++o)
+                        if (o < p.o_D) p.o_y[m * p.o_D + o] = y[o] + __ldg(p.o_b + o);
+                }
+                named_barrier_sync(3, kCT);                              // hp is reused as LayerNorm statistics / O tile by the next tile
+            } else {
                 float4* dst = reinterpret_cast<float4*>(p.h + m * kD + part * 64);
                 const float4* cbt = reinterpret_cast<const float4*>(p.cb_total + part * 64);
                 uint32_t r[2][32];
@@ -797,15 +897,27 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
 
 int encoder_fused(float* h, const float* params, const float* cb_total, const float* gb, long long gb_stride, int film_folded,
                   const void* wqkv, const void* wo, const void* w1, const void* w2, long long M, int L, int d, int H, int ff, int n_layers,
-                  int causal, cudaStream_t st) {
+                  int causal, const idb200_embed_t* emb, const idb200_head_t* head, cudaStream_t st) {
     IDB_REQUIRE(d == kD && H == 8, IDB200_EUNSUPPORTED, "fused encoder is specialised for d_model = 256, 8 heads (got %d, %d)", d, H);
     IDB_REQUIRE(L >= 1 && L <= 128 && (128 % L) == 0, IDB200_EUNSUPPORTED, "fused encoder needs L | 128 (got %d)", L);
     IDB_REQUIRE(ff % 128 == 0 && ff >= 128 && ff <= ef::kMaxFF, IDB200_EUNSUPPORTED, "fused encoder needs d_ff a multiple of 128, <= 1024 (got %d)", ff);
     IDB_REQUIRE(n_layers >= 1, IDB200_EINVAL, "n_layers must be >= 1");
     IDB_REQUIRE(M >= 0 && M % L == 0, IDB200_EINVAL, "M must be a multiple of L");
     if (M == 0) return IDB200_OK;
-    IDB_REQUIRE(h && params && cb_total && wqkv && wo && w1 && w2, IDB200_EINVAL, "NULL pointer");
-    IDB_REQUIRE(aligned(h, 16) && aligned(params, 16) && aligned(cb_total, 16) && (!gb || (aligned(gb, 16) && gb_stride % 4 == 0)),
+    IDB_REQUIRE(params && cb_total && wqkv && wo && w1 && w2, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE((h || (emb && head)), IDB200_EINVAL, "h may be NULL only when both the token assembly and the output head are fused");
+    if (emb) {
+        IDB_REQUIRE(emb->src0 && emb->Wf && emb->tab && emb->row_a && emb->row_b, IDB200_EINVAL, "NULL pointer in idb200_embed_t");
+        IDB_REQUIRE(emb->n0 >= 1 && emb->n1 >= 0 && emb->n2 >= 0 && emb->n0 + emb->n1 + emb->n2 <= 16, IDB200_EUNSUPPORTED, "at most 16 token features");
+        IDB_REQUIRE((emb->n1 == 0 || emb->src1) && (emb->n2 == 0 || emb->src2), IDB200_EINVAL, "NULL feature source");
+        IDB_REQUIRE(aligned(emb->Wf, 16) && aligned(emb->tab, 16) && aligned(emb->row_a, 16) && aligned(emb->row_b, 16) && emb->row_a_stride % 4 == 0,
+                    IDB200_EALIGN, "idb200_embed_t rows must be 16-byte aligned");
+    }
+    if (head) {
+        IDB_REQUIRE(head->W && head->bias && head->y && head->D >= 1 && head->D <= 4, IDB200_EUNSUPPORTED, "output head needs 1 <= D <= 4");
+        IDB_REQUIRE(aligned(head->W, 16), IDB200_EALIGN, "head weights must be 16-byte aligned");
+    }
+    IDB_REQUIRE((!h || aligned(h, 16)) && aligned(params, 16) && aligned(cb_total, 16) && (!gb || (aligned(gb, 16) && gb_stride % 4 == 0)),
                 IDB200_EALIGN, "h / params / gamma_beta must be 16-byte aligned");
     static const bool pair_env = !(getenv("IDB200_ENCODER_PAIR") && atoi(getenv("IDB200_ENCODER_PAIR")) == 0);
     const long long tiles = (M + 127) / 128;
@@ -838,7 +950,15 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     } else {
         grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     }
-    ef::Params p{h, params, cb_total, gb, gb_stride, M, L, causal, ff, n_layers, gb ? (film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone, nullptr};
+    ef::Params p{};
+    p.h = h; p.params = params; p.cb_total = cb_total; p.gb = gb; p.gb_stride = gb_stride; p.M = M; p.L = L; p.causal = causal;
+    p.ff = ff; p.n_layers = n_layers; p.film_mode = gb ? (film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone; p.prof = nullptr;
+    if (emb) {
+        p.e_src0 = emb->src0; p.e_src1 = emb->src1; p.e_src2 = emb->src2; p.e_n0 = emb->n0; p.e_n1 = emb->n1; p.e_n2 = emb->n2;
+        p.e_wf = emb->Wf; p.e_tab = emb->tab; p.e_tab_idx = reinterpret_cast<const long long*>(emb->tab_idx);
+        p.e_row_a = emb->row_a; p.e_row_a_stride = emb->row_a_stride; p.e_row_b = emb->row_b;
+    }
+    if (head) { p.o_w = head->W; p.o_b = head->bias; p.o_y = head->y; p.o_D = head->D; }
     static const bool prof = getenv("IDB200_PROF") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -888,5 +1008,13 @@ extern "C" int idb200_encoder_fused(float* h, const float* layer_params, const f
                                     int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
                                     int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream) {
     return idb200::encoder_fused(h, layer_params, bias_last, film, film_stride, film_folded, wqkv_packed, wo, w1, w2, M, L, d, H, ff,
-                                 n_layers, causal, static_cast<cudaStream_t>(stream));
+                                 n_layers, causal, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int idb200_denoiser_fused(const idb200_embed_t* embed, const idb200_head_t* head, float* h, const float* layer_params,
+                                     const float* bias_last, const float* film, int64_t film_stride, int film_folded,
+                                     const void* wqkv_packed, const void* wo, const void* w1, const void* w2, int64_t M, int L, int d,
+                                     int H, int ff, int n_layers, int causal, idb200_stream_t stream) {
+    return idb200::encoder_fused(h, layer_params, bias_last, film, film_stride, film_folded, wqkv_packed, wo, w1, w2, M, L, d, H, ff,
+                                 n_layers, causal, embed, head, static_cast<cudaStream_t>(stream));
 }

@@ -83,6 +83,25 @@ def encoder_fused(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Film"], 
     return h
 
 
+def denoiser_fused(pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causal: bool, M: int, src0, src1, src2, Wf, tab, tab_idx,
+                   row_a, row_b, W_out, b_out, y):
+    """embed_tokens + every encoder layer + out head in ONE launch (idb200_denoiser_fused): the residual stream exists
+    only in tensor memory.  Arguments as embed_tokens / out_head; y [M, D] is written."""
+    f = pk.fused
+    d = pk.d
+    ft = None if film is None else film.t
+    if ft is not None and (ft.stride(2) != 1 or ft.stride(1) != 2 * d):
+        ft = ft.contiguous()
+    emb = L.EmbedDesc(src0.data_ptr(), src0.shape[-1], L.ptr(src1), 0 if src1 is None else src1.shape[-1], L.ptr(src2),
+                      0 if src2 is None else src2.shape[-1], Wf.data_ptr(), tab.data_ptr(), L.ptr(tab_idx), row_a.data_ptr(),
+                      0 if row_a.shape[0] == 1 else row_a.stride(0), row_b.data_ptr())
+    head = L.HeadDesc(W_out.data_ptr(), b_out.data_ptr(), y.data_ptr(), W_out.shape[0])
+    L.call("idb200_denoiser_fused", ctypes.byref(emb), ctypes.byref(head), None, f["params"].data_ptr(), f["bias_last"].data_ptr(),
+           L.ptr(ft), 0 if ft is None else ft.stride(0), int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(y.device))
+    return y
+
+
 def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((rows, dim), device=device, dtype=torch.float32)
     L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))

@@ -34,6 +34,10 @@ class InterpLevelDenoiser(nn.Module):
                                               cond_dim=d_cond, causal=self._causal, use_checkpoint=use_checkpoint)
         self.out = nn.Linear(d_model, data_dim)
         self.precision = "bf16"
+        # token assembly + out head inside the fused-encoder launch (idb200_denoiser_fused): h never exists in HBM (saves the
+        # [M, 256] fp32 buffer, 4.3 GB at B = 65536, T = 64).  Off by default: the thread-per-row prologue is 2 % slower per
+        # generation than the dedicated embed / head kernels (measured, round 1).
+        self.fuse_io = False
         self._cache = {}
         self._ws = E.Workspace()
 
@@ -107,10 +111,16 @@ class InterpLevelDenoiser(nn.Module):
         pk = self.transformer.packed()
         if film is None:
             film = pk.film_params(cond_vec, T, self.precision)
+        if out is None:
+            out = torch.empty((B, T, D), device=dev, dtype=torch.float32)
+        W_out, b_out = self.out.weight.detach().float().contiguous(), self.out.bias.detach().float().contiguous()
+        if self.fuse_io and pk.fused_path(T, self.precision) and W_out.shape[0] <= 4 and (film is None or isinstance(film, E.Film)):
+            # token assembly, all encoder layers and the out head in one launch: h never exists in HBM
+            E.denoiser_fused(pk, film, T, bool(self.transformer.causal), M, L.f32c(x_s).view(M, D), src1, src2, der["Wf"], der["tab"], None,
+                             level_vec, row_b, W_out, b_out, out.view(M, D))
+            return out
         h = self._ws.get("h", (M, d), torch.float32, dev)
         E.embed_tokens(L.f32c(x_s).view(M, D), src1, src2, der["Wf"], der["tab"], None, level_vec, row_b, h, M, T, d)
         pk.forward(h, B, T, film, self.precision)
-        if out is None:
-            out = torch.empty((B, T, D), device=dev, dtype=torch.float32)
-        E.out_head(h, self.out.weight.detach().float().contiguous(), self.out.bias.detach().float().contiguous(), out.view(M, D))
+        E.out_head(h, W_out, b_out, out.view(M, D))
         return out

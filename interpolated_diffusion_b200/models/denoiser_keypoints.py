@@ -53,6 +53,10 @@ class KeypointDenoiser(nn.Module):
                                               cond_dim=d_cond, causal=False, use_checkpoint=use_checkpoint)
         self.out = nn.Linear(d_model, data_dim)
         self.precision = "bf16"          # "fp32" = check mode (SIMT fp32 GEMMs / attention)
+        # token assembly + out head inside the fused-encoder launch (idb200_denoiser_fused): h never exists in HBM (saves the
+        # [M, 256] fp32 buffer, 4.3 GB at B = 65536, T = 64).  Off by default: the thread-per-row prologue is 2 % slower per
+        # generation than the dedicated embed / head kernels (measured, round 1).
+        self.fuse_io = False
         self._cache = {}
         self._ws = E.Workspace()
 
@@ -130,11 +134,17 @@ class KeypointDenoiser(nn.Module):
         if film is None:
             film = pk.film_params(cond_vec, K, self.precision)
         M = B * K
-        h = self._ws.get("h", (M, d), torch.float32, dev)
-        E.embed_tokens(z.view(M, D), None if kp_feat is None else kp_feat.view(M, -1), km.view(M, D), der["Wf"], der["tab"],
-                       L.i64c(idx).view(M), t_vec, row_b, h, M, K, d)
-        pk.forward(h, B, K, film, self.precision)
         if out is None:
             out = torch.empty((B, K, D), device=dev, dtype=torch.float32)
-        E.out_head(h, self.out.weight.detach().float().contiguous(), self.out.bias.detach().float().contiguous(), out.view(M, D))
+        W_out, b_out = self.out.weight.detach().float().contiguous(), self.out.bias.detach().float().contiguous()
+        src1 = None if kp_feat is None else kp_feat.view(M, -1)
+        if self.fuse_io and pk.fused_path(K, self.precision) and W_out.shape[0] <= 4 and (film is None or isinstance(film, E.Film)):
+            # token assembly, all encoder layers and the out head in one launch: h never exists in HBM
+            E.denoiser_fused(pk, film, K, bool(self.transformer.causal), M, z.view(M, D), src1, km.view(M, D), der["Wf"], der["tab"],
+                             L.i64c(idx).view(M), t_vec, row_b, W_out, b_out, out.view(M, D))
+            return out
+        h = self._ws.get("h", (M, d), torch.float32, dev)
+        E.embed_tokens(z.view(M, D), src1, km.view(M, D), der["Wf"], der["tab"], L.i64c(idx).view(M), t_vec, row_b, h, M, K, d)
+        pk.forward(h, B, K, film, self.precision)
+        E.out_head(h, W_out, b_out, out.view(M, D))
         return out

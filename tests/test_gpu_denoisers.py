@@ -246,3 +246,30 @@ def test_encoder_fused_many_tiles(Lseq, B, n_layers, ff, causal):
     assert torch.equal(whole, again)
     scale = unfused.abs().max().item()
     assert _maxabs(whole, unfused) < 2e-2 * max(1.0, scale / 4), (_maxabs(whole, unfused), scale)
+
+
+@pytest.mark.parametrize("which", ["keypoints", "interp"])
+def test_denoiser_fused_io_matches_separate_kernels(which):
+    """idb200_denoiser_fused (token assembly + encoder + out head in one launch, h only in tensor memory) against the
+    three-launch sequence embed_tokens -> encoder_fused -> out_head on the same weights: the residual stream entering and
+    leaving the encoder is bit-identical (same fp32 operation order), only the 256-term head dot product is re-associated."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    torch.manual_seed(11)
+    gen = torch.Generator().manual_seed(12)
+    B, T, K, D = 37, 64, 8, 2
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float().cuda(), "start_goal": torch.rand((B, 4), generator=gen).cuda()}
+    if which == "keypoints":
+        m = KeypointDenoiser(data_dim=D).cuda()
+        idx = torch.sort(torch.stack([torch.randperm(T, generator=gen)[:K] for _ in range(B)]), dim=1).values.cuda()
+        args = (torch.randn((B, K, D), generator=gen).cuda(), torch.full((B,), 500, dtype=torch.long).cuda(), idx,
+                (torch.rand((B, K, D), generator=gen) < 0.3).cuda(), cond, T)
+    else:
+        m = InterpLevelDenoiser(data_dim=D, max_levels=3, mask_channels=2).cuda()
+        args = (torch.rand((B, T, D), generator=gen).cuda(), torch.full((B,), 2, dtype=torch.long).cuda(), torch.rand((B, T, 2), generator=gen).cuda(), cond)
+    m.fuse_io = True
+    fused = m(*args)
+    m.fuse_io = False
+    separate = m(*args)
+    assert torch.isfinite(fused).all()
+    assert _maxabs(fused, separate) < 1e-5 * max(1.0, separate.abs().max().item()), _maxabs(fused, separate)
