@@ -94,6 +94,7 @@ struct Params {
     int o_D;                    // <= 4
     int film_mode;              // kFilmNone / kFilmRaw ([gamma | beta]) / kFilmFolded ([scale | shift], LayerNorm affine folded in)
     unsigned long long* prof;   // dev: [P_N] cycle sums (kProf kernels only)
+    int dbg_skip;               // dev (kProf kernels only, IDB200_DBG_SKIP): compute warps only do the barrier handshakes (garbage results)
 };
 
 // SiLU(acc + b) = hx * tanh(hx) + hx with hx = 0.5 * (acc + b); hb = 0.5 * b
@@ -263,7 +264,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
     uint64_t* pm_full = pa_empty + 1;
     uint64_t* pm_empty = pm_full + 1;
     uint64_t* film_full = pm_empty + 1;             // FiLM rows of the next LayerNorm staged in the scratch region (tx bytes)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(film_full + 1);
+    uint64_t* stg_free = film_full + 1;             // every compute warp has read what it needs of the staged q|k|v (kCW arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 1);
     float2* stat = reinterpret_cast<float2*>(smem + kOffStat);
     float* sPA = reinterpret_cast<float*>(smem + kOffPA);
     float* sPM = reinterpret_cast<float*>(smem + kOffPM);
@@ -307,6 +309,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         mbar_init(pm_full, 1);
         mbar_init(pm_empty, kCW);
         mbar_init(film_full, 1);
+        mbar_init(stg_free, kCW);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -568,7 +571,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         uint8_t* sqb = smem + kOffQkv;
         uint8_t* so = smem + kOffO;
         const int L = p.L;
-        uint32_t n_acc = 0, n_o = 0, n_h = 0, n_p = 0, n_film = 0;
+        uint32_t n_acc = 0, n_o = 0, n_h = 0, n_p = 0, n_film = 0, n_sf = 0;
         uint32_t use1[2] = {0, 0}, useh[2] = {0, 0};
         unsigned long long pacc[P_N] = {};
         long long tprev = kProf ? clock64() : 0;
@@ -582,6 +585,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         // FiLM staging (L >= 8: at most 16 trajectories per tile): one thread copies the [gamma | beta] rows of the tile's
         // trajectories for LayerNorm `which` (0/1) of layer l into the first 32 KB of the scratch region, which is idle
         // between the last attention read and EPI1_0 / between FF2 of the last even chunk and EPI_0.
+        const bool skip = kProf && p.dbg_skip;
         const bool film_smem = (p.gb != nullptr) && L >= 8;
         auto stage_film = [&](long long tile_, int l_, int which) {
             if (film_smem && ew == 0 && lane == 0) {
@@ -599,6 +603,17 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         if (trip0 < trips) stage_film(tile_of(trip0), 0, 0);
         // attention work unit of this warp: 16-row block rb, head hh of the group
         const int rb = ew & 7, hh = ew >> 3;
+        uint32_t okbits = 0;                             // L < 16: block-diagonal mask of the 16 x 16 score block (per thread, fixed)
+        if (L < 16) {
+            const int lg = 31 - __clz(L);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int key = nt * 8 + (lane & 3) * 2 + (c & 1), qr = (lane >> 2) + (c < 2 ? 0 : 8);
+                    okbits |= ((((key ^ qr) >> lg) == 0) ? 1u : 0u) << (nt * 4 + c);
+                }
+        }
         for (long long trip = trip0; trip < trips; trip += trip_stride) {
             const long long tile = tile_of(trip);
             const long long m0 = tile * 128;
@@ -681,7 +696,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 mbar_wait(pa_full, n_p & 1, 50);
                 stamp(P_WPA);
                 long long tt[3] = {0, 0, 0};
-                if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                if (skip) { if (film_smem) { mbar_wait(film_full, n_film++ & 1, 58); } }
+                else if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * 512 : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -694,10 +710,10 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(acc_full, n_acc & 1, 51);
                     tc_fence_after();
-                    named_barrier_sync(1, kCT);                          // every warp is done reading the previous q|k|v
+                    if (g > 0) mbar_wait(stg_free, (n_sf - 1) & 1, 60);  // every warp is done reading the previous q|k|v
                     stamp(P_WACC);
                     // ---- EPI_g: acc + bias -> bf16 q|k|v rows (this thread: its row, 48 of the 192 columns) ----
-                    {
+                    if (!skip) {
                         uint32_t ra[32], rc[16];
                         tmem_ld_32x32(tmem_acc + lane_base + part * 48, ra);
                         tmem_ld_32x16(tmem_acc + lane_base + part * 48 + 32, rc);
@@ -724,25 +740,31 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     named_barrier_sync(2, kCT);                          // q|k|v of the whole tile are in shared memory
                     stamp(P_EPI);
                     // ---- ATT_g: this warp's (16-row block, head) ----
-                    float o[4][4];
-                    {
-                        int kbeg, kend, lgblk = -1;
-                        if (L < 16) { kbeg = rb * 16; kend = kbeg + 16; lgblk = 31 - __clz(L); }
-                        else {
-                            kbeg = (rb * 16 / L) * L;
-                            kend = p.causal ? rb * 16 + 16 : kbeg + L;
+                    float o[4][4] = {};
+                    if (!skip) {
+                        const __nv_bfloat16* qh = sq + hh * 32;
+                        if (L < 16) attn_unit_fast<2, 1>(qh, qh + 64, qh + 128, rb, rb * 16, rb * 16 + 16, okbits, lane, o);
+                        else if (p.causal) {
+                            const int kbeg = (rb * 16 / L) * L, kend = rb * 16 + 16;
+                            if (L == 16) attn_unit_fast<2, 2>(qh, qh + 64, qh + 128, rb, kbeg, kend, 0u, lane, o);
+                            else attn_unit_fast<4, 2>(qh, qh + 64, qh + 128, rb, kbeg, kend, 0u, lane, o);
+                        } else {
+                            const int kbeg = (rb * 16 / L) * L, kend = kbeg + L;
+                            if (L == 16) attn_unit_fast<2, 0>(qh, qh + 64, qh + 128, rb, kbeg, kend, 0u, lane, o);
+                            else attn_unit_fast<4, 0>(qh, qh + 64, qh + 128, rb, kbeg, kend, 0u, lane, o);
                         }
-                        if (L <= 16) attn_unit<2>(sq + hh * 32, sq + 64 + hh * 32, sq + 128 + hh * 32, rb, kbeg, kend, lgblk, p.causal, lane, o);
-                        else attn_unit<4>(sq + hh * 32, sq + 64 + hh * 32, sq + 128 + hh * 32, rb, kbeg, kend, lgblk, p.causal, lane, o);
                     }
-                    if (g == 3 && film_smem) {                           // the staging rows are dead: stage LN2's FiLM rows over them
-                        named_barrier_sync(1, kCT);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(stg_free);                // this warp is done reading the staged q|k|v
+                    ++n_sf;
+                    if (g == 3 && film_smem && ew == 0 && lane == 0) {   // once every warp is: stage LN2's FiLM rows over them
+                        mbar_wait(stg_free, (n_sf - 1) & 1, 61);
                         stage_film(tile, l, 1);
                     }
                     stamp(P_ATT);
                     mbar_wait(o_empty, (n_o & 1) ^ 1, 52);               // OUT_{g-1} finished reading O
                     stamp(P_WO);
-                    {
+                    if (!skip) {
                         const int gq = lane >> 2, tq = lane & 3;
                         const int r0 = rb * 16 + gq;
                         uint8_t* o0 = so + r0 * 128 + tq * 4;            // sw128_offset(r0, c): chunk (c >> 3) ^ (r0 & 7); r0 + 8: + 1024 bytes
@@ -766,7 +788,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 ++n_h;
                 tc_fence_after();
                 stamp(P_WH1);
-                if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                if (skip) { if (film_smem) { mbar_wait(film_full, n_film++ & 1, 58); } }
+                else if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 else ln_tmem<false>(tmem_row, sPM, sPM + 256, sPM + 512, gbtraj ? gbtraj + (2 * l + 1) * 512 : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -782,7 +805,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     mbar_wait(&hb_empty[b], (useh[b] & 1) ^ 1, 56);     // FF2 of the previous use finished reading H[b]
                     tc_fence_after();
                     stamp(P_WACC1);
-                    {
+                    if (!skip) {
                         // this thread: its row, columns part*32 .. +31 of the 128-column chunk (k-block part >> 1 of H[b])
                         uint8_t* hb = smem + kOffH + (b * 2 + (part >> 1)) * kTile;
                         uint32_t r[32];
@@ -953,6 +976,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     ef::Params p{};
     p.h = h; p.params = params; p.cb_total = cb_total; p.gb = gb; p.gb_stride = gb_stride; p.M = M; p.L = L; p.causal = causal;
     p.ff = ff; p.n_layers = n_layers; p.film_mode = gb ? (film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone; p.prof = nullptr;
+    p.dbg_skip = getenv("IDB200_DBG_SKIP") ? atoi(getenv("IDB200_DBG_SKIP")) : 0;
     if (emb) {
         p.e_src0 = emb->src0; p.e_src1 = emb->src1; p.e_src2 = emb->src2; p.e_n0 = emb->n0; p.e_n1 = emb->n1; p.e_n2 = emb->n2;
         p.e_wf = emb->Wf; p.e_tab = emb->tab; p.e_tab_idx = reinterpret_cast<const long long*>(emb->tab_idx);

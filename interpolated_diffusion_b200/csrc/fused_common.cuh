@@ -252,6 +252,105 @@ __device__ __forceinline__ float rcp_fast(float x) {
     return y;
 }
 
+// Leaner single-head unit used by the whole-encoder kernel (one unit per warp): softmax scale folded into the exponent
+// (p = 2^(s * c - m * c), one FFMA per score), ex2.approx / rcp.approx, non-volatile MMAs, and the mask specialised at
+// compile time: kMode 0 none (whole trajectories of >= 16 rows, bidirectional), 1 block-diagonal from 8 precomputed bits
+// (trajectories of < 16 rows share the 16-row block; bit nt*4+c of okbits), 2 causal (key <= query row).
+template <int NT, int kMode>
+__device__ __forceinline__ void attn_unit_fast(const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* V, int rb, int kbeg,
+                                               int kend, uint32_t okbits, int lane, float (&o)[4][4]) {
+    constexpr float kS = 0.17677669529663687f * 1.4426950408889634f;
+    unsigned qa[2][4];
+    {
+        const __nv_bfloat16* qp = Q + (rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 8;
+        ldsm_x4(qa[0], qp);
+        ldsm_x4(qa[1], qp + 16);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[nt][c] = 0.0f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    const int g = lane >> 2, tq = lane & 3;
+    const int qrow0 = rb * 16 + g, qrow1 = qrow0 + 8;
+    const __nv_bfloat16* kp = K + (lane & 7) * kPitch + (lane >> 3) * 8;
+    const __nv_bfloat16* vp = V + ((lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 8;
+    for (int k0 = kbeg; k0 < kend; k0 += 8 * NT) {
+        const int kw = min(8 * NT, kend - k0);                          // multiple of 16
+        float s[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[nt][c] = 0.0f;
+            if (nt * 8 < kw) {
+                unsigned kb[4];
+                ldsm_x4(kb, kp + (k0 + nt * 8) * kPitch);
+                hmma_16816_nv(s[nt], qa[0], kb[0], kb[1]);
+                hmma_16816_nv(s[nt], qa[1], kb[2], kb[3]);
+            }
+        }
+        float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bool ok = nt * 8 < kw;
+                if (kMode == 1) ok = ok && ((okbits >> (nt * 4 + c)) & 1u);
+                if (kMode == 2) ok = ok && (k0 + nt * 8 + tq * 2 + (c & 1) <= ((c < 2) ? qrow0 : qrow1));
+                if (kMode != 0 || NT * 8 > 16) s[nt][c] = ok ? s[nt][c] : -INFINITY;
+            }
+            bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+            bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);         // finite: a query always sees its own key
+        const float c0 = ex2_fast((m0 - mn0) * kS), c1 = ex2_fast((m1 - mn1) * kS);
+        m0 = mn0;
+        m1 = mn1;
+        const float n0 = -mn0 * kS, n1 = -mn1 * kS;
+        float rs0 = 0.0f, rs1 = 0.0f;
+        unsigned pa[NT / 2][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float p0 = ex2_fast(fmaf(s[nt][0], kS, n0)), p1 = ex2_fast(fmaf(s[nt][1], kS, n0));
+            const float p2 = ex2_fast(fmaf(s[nt][2], kS, n1)), p3 = ex2_fast(fmaf(s[nt][3], kS, n1));
+            rs0 += p0 + p1;
+            rs1 += p2 + p3;
+            pa[nt >> 1][(nt & 1) * 2 + 0] = pack2_bf16(p0, p1);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);
+        }
+        l0 = l0 * c0 + rs0;
+        l1 = l1 * c1 + rs1;
+        if (k0 > kbeg) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+        }
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks) {
+            if (ks * 16 < kw) {
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    unsigned vb[4];
+                    ldsm_x4_trans(vb, vp + (k0 + ks * 16) * kPitch + np * 16);
+                    hmma_16816_nv(o[np * 2 + 0], pa[ks], vb[0], vb[1]);
+                    hmma_16816_nv(o[np * 2 + 1], pa[ks], vb[2], vb[3]);
+                }
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = rcp_fast(l0), i1 = rcp_fast(l1);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= i0; o[nt][1] *= i0; o[nt][2] *= i1; o[nt][3] *= i1; }
+}
+
+
 // Both heads of a head group at once (two independent dependency chains interleaved instruction by instruction):
 // softmax(q k^T / sqrt(32)) v for the 16-row block rb, keys kbeg..kend-1 (tile rows), from the staged bf16 rows
 // sq[row][q 64 | k 64 | v 64] (pitch kPitch, head hh at column offset 32 hh of each part).  NT key tiles of 8 per step.
