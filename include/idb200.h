@@ -297,6 +297,13 @@ int idb200_conv_encoder_tc(const float* occ, const float* sdf, int64_t B, int H,
                            const float* w0, const float* b0, const void* w1_packed_bf16, const float* b1, float* pooled,
                            idb200_stream_t stream);
 
+/* K4' (tcgen05 path)  the same two-layer stack as idb200_conv_encoder_tc with the second conv on the 5th-generation
+ * tensor cores (TMEM accumulators, SWIZZLE_64B shifted activation copies instead of im2col; csrc/conv_tc5.cu).
+ * Specialised for maze_channels = (32, 64) and H * roundup8(W + 2) <= 512 (the 21 x 21 particle maze). */
+int idb200_conv_encoder_tc5(const float* occ, const float* sdf, int64_t B, int H, int W, int cin, int c1, int c2,
+                            const float* w0, const float* b0, const void* w1_packed_bf16, const float* b1,
+                            float* pooled, idb200_stream_t stream);
+
 /* Batched trajectory metrics, src/eval/metrics.py:68-128 (compute_metrics_batch; _pos_to_cell :13-24): the step right after
  * the generation path (the reference loops over samples on the host, sample_generate.py:1323-1398).
  *   occ fp32 [B,H,W] (occ_stride = H*W, or 0 to broadcast one map); traj fp32 [B,T,D], dims 0:2 = (x, y) in [0,1];

@@ -331,6 +331,24 @@ def conv_encoder_tc(occ: torch.Tensor, sdf: Optional[torch.Tensor], w0, b0, w1_p
     return pooled
 
 
+def conv_encoder_tc5(occ: torch.Tensor, sdf: Optional[torch.Tensor], w0, b0, w1_packed, b1) -> torch.Tensor:
+    """Two-layer conv stack with the second conv on tcgen05 (idb200_conv_encoder_tc5; maze_channels = (32, 64))."""
+    B, _, Hh, Ww = occ.shape
+    c1, cin = w0.shape[0], w0.shape[1]
+    c2 = w1_packed.shape[0]
+    pooled = torch.empty((B, c2), device=occ.device, dtype=torch.float32)
+    L.call("idb200_conv_encoder_tc5", occ.data_ptr(), L.ptr(sdf), B, Hh, Ww, cin, c1, c2, w0.data_ptr(), b0.data_ptr(),
+           w1_packed.data_ptr(), b1.data_ptr(), pooled.data_ptr(), L.stream(occ.device))
+    return pooled
+
+
+def conv_tc5_supported(convs, Hh: int, Ww: int) -> bool:
+    if len(convs) != 2 or convs[0].weight.shape[0] != 32 or convs[1].weight.shape[0] != 64:
+        return False
+    pw = (Ww + 2 + 7) & ~7
+    return Hh * pw <= 512 and convs[0].weight.shape[1] * (Hh + 2) * (Ww + 2) <= 2 * 26 * 26
+
+
 def conv_tc_supported(convs, Hh: int, Ww: int) -> bool:
     if len(convs) != 2:
         return False

@@ -39,9 +39,9 @@ class MazeEncoder(nn.Module):
                 w = convs[1].weight.detach().float()
                 self._w1_packed = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
                 self._w1_key = key
-            pooled = E.conv_encoder_tc(occ, sdf, convs[0].weight.detach().float().contiguous(),
-                                       convs[0].bias.detach().float().contiguous(), self._w1_packed,
-                                       convs[1].bias.detach().float().contiguous())
+            conv = E.conv_encoder_tc5 if (getattr(self, "use_tc5", True) and E.conv_tc5_supported(convs, x.shape[2], x.shape[3])) else E.conv_encoder_tc
+            pooled = conv(occ, sdf, convs[0].weight.detach().float().contiguous(), convs[0].bias.detach().float().contiguous(),
+                          self._w1_packed, convs[1].bias.detach().float().contiguous())
         else:
             pooled = E.conv_encoder(occ, sdf, [c.weight.detach().float().contiguous() for c in convs],
                                     [c.bias.detach().float().contiguous() for c in convs])

@@ -89,6 +89,22 @@ def test_small_kernels_vs_torch():
             w1p = ws[1].permute(0, 2, 3, 1).reshape(chans[2], -1).to(torch.bfloat16).contiguous()
             got_tc = E.conv_encoder_tc(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if chans[0] == 2 else None, ws[0], bs[0], w1p, bs[1])
             assert _maxabs(got_tc, ref) < 3e-3, (chans, _maxabs(got_tc, ref))
+    # tcgen05 conv encoder (maze_channels (32, 64)): several mazes per CTA (persistent loop, both accumulator buffers), sdf channel
+    for cin, B, H, W in [(1, 5, 21, 21), (1, 148 * 3 + 7, 21, 21), (2, 301, 21, 21), (1, 9, 12, 9)]:
+        x = torch.rand((B, cin, H, W), generator=g, device="cuda")
+        x[:, 0] = (x[:, 0] < 0.3).float()
+        ws = [torch.randn((32, cin, 3, 3), generator=g, device="cuda") * (cin * 9) ** -0.5, torch.randn((64, 32, 3, 3), generator=g, device="cuda") * (32 * 9) ** -0.5]
+        bs = [torch.randn((32,), generator=g, device="cuda") * 0.1, torch.randn((64,), generator=g, device="cuda") * 0.1]
+        ref = x.double()
+        for w_, b_ in zip(ws, bs):
+            ref = torch.nn.functional.silu(torch.nn.functional.conv2d(ref, w_.double(), b_.double(), padding=1))
+        ref = ref.mean(dim=[2, 3]).float()
+        w1p = ws[1].permute(0, 2, 3, 1).reshape(64, -1).to(torch.bfloat16).contiguous()
+        occ_, sdf_ = x[:, 0:1].contiguous(), (x[:, 1:2].contiguous() if cin == 2 else None)
+        got5 = E.conv_encoder_tc5(occ_, sdf_, ws[0], bs[0], w1p, bs[1])
+        assert torch.isfinite(got5).all()
+        assert _maxabs(got5, ref) < 3e-3, (cin, B, H, W, _maxabs(got5, ref))
+        assert torch.equal(got5, E.conv_encoder_tc5(occ_, sdf_, ws[0], bs[0], w1p, bs[1]))      # deterministic
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
