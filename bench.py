@@ -49,6 +49,8 @@ DENSE_FLOPS = {
     "idb200_mlp_block": lambda a: 4.0 * a[9] * a[11] * a[12],
     "idb200_attn_block": _attn_block_flops,
     # every layer of the encoder in one launch: n_layers * M * (QKV + out-proj + attention + MLP)
+    # the same kernel with the token assembly / out head fused in (the head adds 2 * M * 256 * D, negligible, not counted)
+    "idb200_denoiser_fused": lambda a: float(a[17]) * a[12] * (2.0 * a[14] * 3 * a[14] + 2.0 * a[14] * a[14] + 4.0 * a[13] * a[14] + 4.0 * a[14] * a[16]),
     "idb200_encoder_fused": lambda a: float(a[15]) * a[10] * (2.0 * a[12] * 3 * a[12] + 2.0 * a[12] * a[12] + 4.0 * a[11] * a[12] + 4.0 * a[12] * a[14]),
 }
 
@@ -271,7 +273,7 @@ def run_ours(args):
             all_fl = sum(t[2] for t in dense.values())
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "r01_encoder_fused_traffic.json")
-            if top == "idb200_encoder_fused" and os.path.exists(tpath) and B == 65536:
+            if top in ("idb200_encoder_fused", "idb200_denoiser_fused") and os.path.exists(tpath) and B == 65536:
                 # DRAM bytes (read + write) per launch from the committed ncu --set full captures of the same shapes:
                 # 19 Stage-1 launches (L = 8) + 1 Stage-2 launch (L = 64), averaged per launch
                 with open(tpath) as fh:

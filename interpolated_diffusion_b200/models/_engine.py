@@ -83,6 +83,21 @@ def encoder_fused(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Film"], 
     return h
 
 
+def encoder_fused_head(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causal: bool, W_out, b_out, y):
+    """Every encoder layer + the out head in one launch (idb200_denoiser_fused with embed = NULL): h is read once and never
+    written back; y [M, D] = out(h_final)."""
+    M, d = h.shape
+    f = pk.fused
+    ft = None if film is None else film.t
+    if ft is not None and (ft.stride(2) != 1 or ft.stride(1) != 2 * d):
+        ft = ft.contiguous()
+    head = L.HeadDesc(W_out.data_ptr(), b_out.data_ptr(), y.data_ptr(), W_out.shape[0])
+    L.call("idb200_denoiser_fused", None, ctypes.byref(head), h.data_ptr(), f["params"].data_ptr(), f["bias_last"].data_ptr(),
+           L.ptr(ft), 0 if ft is None else ft.stride(0), int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(y.device))
+    return y
+
+
 def denoiser_fused(pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causal: bool, M: int, src0, src1, src2, Wf, tab, tab_idx,
                    row_a, row_b, W_out, b_out, y):
     """embed_tokens + every encoder layer + out head in ONE launch (idb200_denoiser_fused): the residual stream exists

@@ -38,6 +38,7 @@ class InterpLevelDenoiser(nn.Module):
         # [M, 256] fp32 buffer, 4.3 GB at B = 65536, T = 64).  Off by default: the thread-per-row prologue is 2 % slower per
         # generation than the dedicated embed / head kernels (measured, round 1).
         self.fuse_io = False
+        self.fuse_head = True            # the out head as the tile epilogue of the fused-encoder launch (h is not written back)
         self._cache = {}
         self._ws = E.Workspace()
 
@@ -121,6 +122,10 @@ class InterpLevelDenoiser(nn.Module):
             return out
         h = self._ws.get("h", (M, d), torch.float32, dev)
         E.embed_tokens(L.f32c(x_s).view(M, D), src1, src2, der["Wf"], der["tab"], None, level_vec, row_b, h, M, T, d)
+        if self.fuse_head and pk.fused_path(T, self.precision) and W_out.shape[0] <= 4 and (film is None or isinstance(film, E.Film)):
+            # all encoder layers + the out head in one launch: the final residual stream is never written back
+            E.encoder_fused_head(h, pk, film, T, bool(self.transformer.causal), W_out, b_out, out.view(M, D))
+            return out
         pk.forward(h, B, T, film, self.precision)
         E.out_head(h, W_out, b_out, out.view(M, D))
         return out

@@ -286,6 +286,12 @@ def test_denoiser_fused_io_matches_separate_kernels(which):
     m.fuse_io = True
     fused = m(*args)
     m.fuse_io = False
-    separate = m(*args)
+    assert m.fuse_head
+    head_only = m(*args)                     # embed_tokens kernel -> encoder + head in one launch (the default)
+    m.fuse_head = False
+    separate = m(*args)                      # embed_tokens -> encoder_fused -> out_head
     assert torch.isfinite(fused).all()
-    assert _maxabs(fused, separate) < 1e-5 * max(1.0, separate.abs().max().item()), _maxabs(fused, separate)
+    tol = 1e-5 * max(1.0, separate.abs().max().item())
+    assert _maxabs(fused, separate) < tol, _maxabs(fused, separate)
+    assert _maxabs(head_only, separate) < tol, _maxabs(head_only, separate)
+    assert torch.equal(head_only, fused)     # same kernel, bit-identical residual stream
