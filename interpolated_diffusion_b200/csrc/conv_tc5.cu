@@ -128,10 +128,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
         if (static_cast<long long>(blockIdx.x) < p.B) load_plane(blockIdx.x, 0);
         for (long long b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
             const int buf = static_cast<int>(it & 1);
-            if (b + gridDim.x < p.B) load_plane(b + gridDim.x, buf ^ 1);
-            if (b + gridDim.x < p.B) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            named_barrier_sync(1, 256);                                 // the plane of this maze is complete for all 8 warps
+            asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's part of this maze's plane has landed
+            named_barrier_sync(1, 256);                                 // ... and everybody's; every warp is done reading the other buffer
+            if (b + gridDim.x < p.B) load_plane(b + gridDim.x, buf ^ 1);  // prefetch the next maze while this one is computed
             mbar_wait(act_empty, (it & 1) ^ 1, 70);                     // the MMAs of the previous maze have read the activations
             const float* pl = plane + buf * kMaxPlane;
             // item = (pixel, channel octet): 8 channels of one pixel -> one 16-byte chunk, written to the 3 shifted copies
