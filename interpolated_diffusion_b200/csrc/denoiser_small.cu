@@ -269,62 +269,60 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
     }
 }
 
-// d % 4 == 0, 16-byte aligned rows: a warp handles the L tokens of one trajectory; a lane owns float4 column groups
-// {lane, lane + 32, ...} (kV of them), keeps the trajectory's row_a + row_b and its slice of Wf in registers (F <= kF)
-// and streams the tokens: per token one table-row read (L1/L2 resident) and one coalesced float4 store of h.
-// Same arithmetic order as embed_kernel: fma chain over the features, then + tab + row_a + row_b.
-template <int kF, int kV>
-__global__ void __launch_bounds__(256) embed_traj_kernel(const EmbedParams p) {
+// d % 128 == 0, 16-byte aligned rows: a warp handles the L tokens of one trajectory for one 128-column slice (a lane owns
+// one float4 column group), keeps the trajectory's row_a + row_b and its slice of Wf in registers (F <= kF) and streams
+// the tokens four at a time (all loads of a group of tokens in flight): per token one table-row read (L1/L2 resident) and
+// one coalesced float4 store of h.  Same arithmetic order as embed_kernel: fma chain over the features, + tab + row_a + row_b.
+template <int kF>
+__global__ void __launch_bounds__(256, 2) embed_traj_kernel(const EmbedParams p) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const int F = p.n0 + p.n1 + p.n2;
     const long long B = p.M / p.L;
-    const int d4 = p.d >> 2;
-    float4 w[kF][kV];
+    const int d4 = p.d >> 2, ns = d4 >> 5;                              // column slices of 32 float4 per trajectory
+    for (long long u = warp; u < B * ns; u += nwarps) {
+        const long long b = u / ns;
+        const int c4 = static_cast<int>(u - b * ns) * 32 + lane;
+        float4 w[kF];
 #pragma unroll
-    for (int j = 0; j < kF; ++j)
+        for (int j = 0; j < kF; ++j) w[j] = (j < F) ? __ldg(reinterpret_cast<const float4*>(p.Wf + j * p.d) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 ra = __ldg(reinterpret_cast<const float4*>(p.row_a + b * p.row_a_stride) + c4);
+        const float4 rb = __ldg(reinterpret_cast<const float4*>(p.row_b + b * p.d) + c4);
+        for (int t0 = 0; t0 < p.L; t0 += 4) {
+            float f[4][kF];
+            float4 tb[4];
 #pragma unroll
-        for (int v = 0; v < kV; ++v)
-            w[j][v] = (j < F && lane + 32 * v < d4) ? __ldg(reinterpret_cast<const float4*>(p.Wf + j * p.d) + lane + 32 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long b = warp; b < B; b += nwarps) {
-        float4 ra[kV], rb[kV];
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + i;
+                if (t < p.L) {
+                    const long long m = b * p.L + t;
 #pragma unroll
-        for (int v = 0; v < kV; ++v) {
-            if (lane + 32 * v < d4) {
-                ra[v] = __ldg(reinterpret_cast<const float4*>(p.row_a + b * p.row_a_stride) + lane + 32 * v);
-                rb[v] = __ldg(reinterpret_cast<const float4*>(p.row_b + b * p.d) + lane + 32 * v);
+                    for (int j = 0; j < kF; ++j) {
+                        float v = 0.0f;
+                        if (j < p.n0) v = p.src0[m * p.n0 + j];
+                        else if (j < p.n0 + p.n1) v = p.src1[m * p.n1 + (j - p.n0)];
+                        else if (j < F) v = p.src2[m * p.n2 + (j - p.n0 - p.n1)] ? 1.0f : 0.0f;
+                        f[i][j] = v;
+                    }
+                    const long long trow = p.tab_idx ? p.tab_idx[m] : t;
+                    tb[i] = __ldg(reinterpret_cast<const float4*>(p.tab + trow * p.d) + c4);
+                }
             }
-        }
-#pragma unroll 2
-        for (int t = 0; t < p.L; ++t) {
-            const long long m = b * p.L + t;
-            float f[kF];
 #pragma unroll
-            for (int j = 0; j < kF; ++j) {
-                float v = 0.0f;
-                if (j < p.n0) v = p.src0[m * p.n0 + j];
-                else if (j < p.n0 + p.n1) v = p.src1[m * p.n1 + (j - p.n0)];
-                else if (j < F) v = p.src2[m * p.n2 + (j - p.n0 - p.n1)] ? 1.0f : 0.0f;
-                f[j] = v;
-            }
-            const long long trow = p.tab_idx ? p.tab_idx[m] : t;
-            const float4* tab = reinterpret_cast<const float4*>(p.tab + trow * p.d);
-            float4* out = reinterpret_cast<float4*>(p.h + m * p.d);
-#pragma unroll
-            for (int v = 0; v < kV; ++v) {
-                if (lane + 32 * v < d4) {
-                    const float4 tb = __ldg(tab + lane + 32 * v);
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + i;
+                if (t < p.L) {
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < kF; ++j) {
-                        acc.x = fmaf(f[j], w[j][v].x, acc.x);
-                        acc.y = fmaf(f[j], w[j][v].y, acc.y);
-                        acc.z = fmaf(f[j], w[j][v].z, acc.z);
-                        acc.w = fmaf(f[j], w[j][v].w, acc.w);
+                        acc.x = fmaf(f[i][j], w[j].x, acc.x);
+                        acc.y = fmaf(f[i][j], w[j].y, acc.y);
+                        acc.z = fmaf(f[i][j], w[j].z, acc.z);
+                        acc.w = fmaf(f[i][j], w[j].w, acc.w);
                     }
-                    out[lane + 32 * v] = make_float4(acc.x + tb.x + ra[v].x + rb[v].x, acc.y + tb.y + ra[v].y + rb[v].y,
-                                                     acc.z + tb.z + ra[v].z + rb[v].z, acc.w + tb.w + ra[v].w + rb[v].w);
+                    reinterpret_cast<float4*>(p.h + (b * p.L + t) * p.d)[c4] =
+                        make_float4(acc.x + tb[i].x + ra.x + rb.x, acc.y + tb[i].y + ra.y + rb.y, acc.z + tb[i].z + ra.z + rb.z, acc.w + tb[i].w + ra.w + rb.w);
                 }
             }
         }
@@ -521,12 +519,12 @@ extern "C" int idb200_embed_tokens(const float* src0, int n0, const float* src1,
     IDB_REQUIRE(src0 && Wf && tab && row_a && row_b && h, IDB200_EINVAL, "NULL pointer");
     EmbedParams p{src0, n0, src1, n1, src2, n2, Wf, tab, reinterpret_cast<const long long*>(tab_idx), row_a, row_a_stride, row_b, h, M, L, d};
     const int F = n0 + n1 + n2;
-    const bool vec = d % 4 == 0 && d <= 256 && F <= 8 && M % L == 0 && aligned(Wf, 16) && aligned(tab, 16) && aligned(row_a, 16) &&
+    const bool vec = d % 128 == 0 && F <= 8 && M % L == 0 && aligned(Wf, 16) && aligned(tab, 16) && aligned(row_a, 16) &&
                      aligned(row_b, 16) && aligned(h, 16) && row_a_stride % 4 == 0;
     if (vec) {
-        const int grid = warp_grid(M / L);
-        if (d <= 128) embed_traj_kernel<8, 1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-        else embed_traj_kernel<8, 2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        const int grid = grid_for((M / L) * (d / 128), 8, 2);
+        if (F <= 4) embed_traj_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        else embed_traj_kernel<8><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
         return check_launch("embed_traj_kernel");
     }
     embed_kernel<<<warp_grid(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
