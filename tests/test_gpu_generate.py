@@ -155,3 +155,35 @@ def test_sample_keypoints_ddim_mirror(golden):
     for i in (1, 5, 19):
         scale = max(1.0, float(np.abs(ref[i]).max()))
         assert np.abs(inter[i].cpu().numpy() - ref[i]).max() / scale < 5e-3, i
+
+
+def test_generation_graph_equals_eager_and_is_batch_invariant():
+    """Size-independent properties of the production path (BASELINE small models, bf16, whole-encoder kernel as CTA pairs,
+    tcgen05 conv encoder, CUDA graph): (1) the graph replay equals the eager call bit for bit, (2) a trajectory's sample does
+    not depend on what else is in the batch or where it sits in it (tile / CTA-pair position): generating two halves
+    separately gives the same bits as generating the whole batch -- every op on the path is row-independent in B
+    (SURVEY 8e), which is also what makes the multi-GPU sharding exact -- (3) the clamp policy holds on the result."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph, generate
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=2).cuda()
+    il = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=2).cuda()
+    cfg = GenerationConfig()
+    B = 2 * 148 * 16 + 37 * 16 + 5                       # several tiles per CTA pair in both stages, ragged last tile
+    gen = torch.Generator().manual_seed(9)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float().cuda(), "start_goal": torch.rand((B, 4), generator=gen).cuda()}
+    z_T = torch.randn((B, cfg.K_min, 2), generator=gen).cuda()
+    whole = generate(kp, il, cond, cfg, z_T=z_T).clone()
+    assert torch.isfinite(whole).all()
+    graph = GenerationGraph(kp, il, B, cfg)
+    replay = graph.run(cond, z_T).clone()
+    assert torch.equal(replay, whole)
+    assert torch.equal(graph.run(cond, z_T), whole)       # idempotent across replays
+    cut = 1000                                            # not a multiple of the 16 trajectories of a Stage-1 tile
+    parts = [generate(kp, il, {k: v[s] for k, v in cond.items()}, cfg, z_T=z_T[s]) for s in (slice(0, cut), slice(cut, B))]
+    assert torch.equal(torch.cat(parts, dim=0), whole)
+    # clamp_policy = endpoints, clamp_dims = pos: first / last positions are the start / goal of the conditioning
+    sg = cond["start_goal"]
+    # (through logit -> DDIM known-value clamp -> sigmoid: a few ulp of round trip)
+    assert (whole[:, 0, :2] - sg[:, :2]).abs().max().item() < 2e-5 and (whole[:, -1, :2] - sg[:, 2:]).abs().max().item() < 2e-5
