@@ -50,8 +50,8 @@ DENSE_FLOPS = {
     "idb200_attn_block": _attn_block_flops,
     # every layer of the encoder in one launch: n_layers * M * (QKV + out-proj + attention + MLP)
     # the same kernel with the token assembly / out head fused in (the head adds 2 * M * 256 * D, negligible, not counted)
-    "idb200_denoiser_fused": lambda a: float(a[17]) * a[12] * (2.0 * a[14] * 3 * a[14] + 2.0 * a[14] * a[14] + 4.0 * a[13] * a[14] + 4.0 * a[14] * a[16]),
-    "idb200_encoder_fused": lambda a: float(a[15]) * a[10] * (2.0 * a[12] * 3 * a[12] + 2.0 * a[12] * a[12] + 4.0 * a[11] * a[12] + 4.0 * a[12] * a[14]),
+    "idb200_denoiser_fused": lambda a: float(a[18]) * a[13] * (2.0 * a[15] * 3 * a[15] + 2.0 * a[15] * a[15] + 4.0 * a[14] * a[15] + 4.0 * a[15] * a[17]),
+    "idb200_encoder_fused": lambda a: float(a[16]) * a[11] * (2.0 * a[13] * 3 * a[13] + 2.0 * a[13] * a[13] + 4.0 * a[12] * a[13] + 4.0 * a[13] * a[15]),
 }
 
 

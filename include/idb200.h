@@ -253,14 +253,16 @@ int idb200_mlp_block(float* h, const float* ln_w, const float* ln_b, const float
  *     0.5 * b1 (ff)].  pend1 / pend2 = the bias of the GEMM that accumulated into h just before that LayerNorm (ff.2 bias of
  *     the previous layer, zero for layer 0 / out_proj bias of this layer): the accumulating GEMMs never add their own bias,
  *     the LayerNorm that follows does.  bias_last [256] = ff.2 bias of the last layer (added when h is written back).
- *   film: per-trajectory rows of trajectory m / L at stride film_stride floats, [2 * n_layers][512] (row 2l = film1 of layer
- *     l, 2l+1 = film2), or NULL.  film_folded == 0: rows are [gamma | beta] (a = LN(h) * (1 + gamma) + beta); != 0: rows are
+ *   film: FiLM table or NULL: the row (512 floats) of trajectory b = m / L for LayerNorm slot j (2l = film1 of layer l,
+ *     2l+1 = film2) is at film + b * film_stride + j * film_ln_stride.  [B][2 * n_layers][512] is (8192-ish, 512);
+ *     the LayerNorm-major form [2 * n_layers][B][512] (film_stride = 512, film_ln_stride = B * 512) makes the rows of a
+ *     tile contiguous, which the kernel stages with ONE bulk copy per LayerNorm (16 separate copies cost 3 k cycles).  film_folded == 0: rows are [gamma | beta] (a = LN(h) * (1 + gamma) + beta); != 0: rows are
  *     [scale | shift] with the LayerNorm affine folded in, scale = ln_w * (1 + gamma), shift = ln_b * (1 + gamma) + beta
  *     (a = n * scale + shift, n = the normalised row) -- both are linear in cond_vec, so the host folds them into the FiLM GEMM.
  *   wqkv_packed bf16 [n_layers*768, 256] (per layer head-group-major, see idb200_attn_block), wo bf16 [n_layers*256, 256],
  *   w1 bf16 [n_layers*ff, 256], w2 bf16 [n_layers*256, ff]. */
 int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_last, const float* film, int64_t film_stride,
-                         int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
+                         int64_t film_ln_stride, int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
                          int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream);
 
 /* The whole denoiser forward around the encoder in the same launch (denoiser_keypoints.py:102-113,
@@ -285,7 +287,7 @@ typedef struct {
     int D;
 } idb200_head_t;
 int idb200_denoiser_fused(const idb200_embed_t* embed, const idb200_head_t* head, float* h, const float* layer_params,
-                          const float* bias_last, const float* film, int64_t film_stride, int film_folded,
+                          const float* bias_last, const float* film, int64_t film_stride, int64_t film_ln_stride, int film_folded,
                           const void* wqkv_packed, const void* wo, const void* w1, const void* w2, int64_t M, int L, int d,
                           int H, int ff, int n_layers, int causal, idb200_stream_t stream);
 

@@ -70,7 +70,8 @@ struct Params {
     const float* params;        // per layer: PA (1536 floats) | PM (768 + ff floats)
     const float* cb_total;      // [256] pending bias of the last layer's ff.2 (added when h is written back)
     const float* gb;            // FiLM [B, 2 * n_layers, 512] rows = [gamma | beta] per LayerNorm, or nullptr
-    long long gb_stride;        // floats between trajectories
+    long long gb_stride;        // floats between trajectories (512: the rows of a tile are contiguous -> one bulk copy per LayerNorm)
+    long long gb_ln_stride;     // floats between the 2 * n_layers LayerNorm slots
     long long M;
     int L;
     int causal;
@@ -594,8 +595,12 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 const int nt = left <= 0 ? 0 : static_cast<int>(left < 128 / L ? left : 128 / L);   // 0: the pair's dead tile
                 fence_proxy_async_smem();
                 mbar_arrive_expect_tx(film_full, static_cast<uint32_t>(nt) * 2048u);
-                for (int t = 0; t < nt; ++t)
-                    bulk_load_1d(smem + kOffS + t * 2048, p.gb + (t0 + t) * p.gb_stride + (2 * l_ + which) * 512, 2048, film_full);
+                const float* src = p.gb + t0 * p.gb_stride + (2 * l_ + which) * p.gb_ln_stride;
+                if (p.gb_stride == 512) {                                // LayerNorm-major table: the tile's rows are contiguous
+                    if (nt > 0) bulk_load_1d(smem + kOffS, src, static_cast<uint32_t>(nt) * 2048u, film_full);
+                } else {
+                    for (int t = 0; t < nt; ++t) bulk_load_1d(smem + kOffS + t * 2048, src + t * p.gb_stride, 2048, film_full);
+                }
             }
         };
         auto tile_of = [&](long long trip) { return kPair ? 2 * trip + rank : trip; };
@@ -698,7 +703,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 long long tt[3] = {0, 0, 0};
                 if (skip) { if (film_smem) { mbar_wait(film_full, n_film++ & 1, 58); } }
                 else if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
-                else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * 512 : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * p.gb_ln_stride : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -757,10 +762,6 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(stg_free);                // this warp is done reading the staged q|k|v
                     ++n_sf;
-                    if (g == 3 && film_smem && ew == 0 && lane == 0) {   // once every warp is: stage LN2's FiLM rows over them
-                        mbar_wait(stg_free, (n_sf - 1) & 1, 61);
-                        stage_film(tile, l, 1);
-                    }
                     stamp(P_ATT);
                     mbar_wait(o_empty, (n_o & 1) ^ 1, 52);               // OUT_{g-1} finished reading O
                     stamp(P_WO);
@@ -781,6 +782,10 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     ++n_o;
                     stamp(P_OWR);
                 }
+                if (film_smem && ew == 0 && lane == 0) {                 // once every warp is done with the staged q|k|v: stage LN2's
+                    mbar_wait(stg_free, (n_sf - 1) & 1, 61);             // FiLM rows over them (after o_full: OUT_3 is not held up)
+                    stage_film(tile, l, 1);
+                }
                 if (lane == 0) mbar_arrive(pa_empty);                    // (after the __syncwarp above: the warp is done with PA)
                 // ================= MLP half =================
                 mbar_wait(pm_full, n_p & 1, 53);
@@ -790,7 +795,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 stamp(P_WH1);
                 if (skip) { if (film_smem) { mbar_wait(film_full, n_film++ & 1, 58); } }
                 else if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
-                else ln_tmem<false>(tmem_row, sPM, sPM + 256, sPM + 512, gbtraj ? gbtraj + (2 * l + 1) * 512 : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                else ln_tmem<false>(tmem_row, sPM, sPM + 256, sPM + 512, gbtraj ? gbtraj + (2 * l + 1) * p.gb_ln_stride : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -918,7 +923,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
 
 }  // namespace ef
 
-int encoder_fused(float* h, const float* params, const float* cb_total, const float* gb, long long gb_stride, int film_folded,
+int encoder_fused(float* h, const float* params, const float* cb_total, const float* gb, long long gb_stride, long long gb_ln_stride, int film_folded,
                   const void* wqkv, const void* wo, const void* w1, const void* w2, long long M, int L, int d, int H, int ff, int n_layers,
                   int causal, const idb200_embed_t* emb, const idb200_head_t* head, cudaStream_t st) {
     IDB_REQUIRE(d == kD && H == 8, IDB200_EUNSUPPORTED, "fused encoder is specialised for d_model = 256, 8 heads (got %d, %d)", d, H);
@@ -940,7 +945,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         IDB_REQUIRE(head->W && head->bias && head->y && head->D >= 1 && head->D <= 4, IDB200_EUNSUPPORTED, "output head needs 1 <= D <= 4");
         IDB_REQUIRE(aligned(head->W, 16), IDB200_EALIGN, "head weights must be 16-byte aligned");
     }
-    IDB_REQUIRE((!h || aligned(h, 16)) && aligned(params, 16) && aligned(cb_total, 16) && (!gb || (aligned(gb, 16) && gb_stride % 4 == 0)),
+    IDB_REQUIRE((!h || aligned(h, 16)) && aligned(params, 16) && aligned(cb_total, 16) && (!gb || (aligned(gb, 16) && gb_stride % 4 == 0 && gb_ln_stride % 4 == 0)),
                 IDB200_EALIGN, "h / params / gamma_beta must be 16-byte aligned");
     static const bool pair_env = !(getenv("IDB200_ENCODER_PAIR") && atoi(getenv("IDB200_ENCODER_PAIR")) == 0);
     const long long tiles = (M + 127) / 128;
@@ -974,7 +979,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     }
     ef::Params p{};
-    p.h = h; p.params = params; p.cb_total = cb_total; p.gb = gb; p.gb_stride = gb_stride; p.M = M; p.L = L; p.causal = causal;
+    p.h = h; p.params = params; p.cb_total = cb_total; p.gb = gb; p.gb_stride = gb_stride; p.gb_ln_stride = gb_ln_stride; p.M = M; p.L = L; p.causal = causal;
     p.ff = ff; p.n_layers = n_layers; p.film_mode = gb ? (film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone; p.prof = nullptr;
     p.dbg_skip = getenv("IDB200_DBG_SKIP") ? atoi(getenv("IDB200_DBG_SKIP")) : 0;
     if (emb) {
@@ -1029,16 +1034,16 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
 }  // namespace idb200
 
 extern "C" int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_last, const float* film, int64_t film_stride,
-                                    int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
+                                    int64_t film_ln_stride, int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2,
                                     int64_t M, int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream) {
-    return idb200::encoder_fused(h, layer_params, bias_last, film, film_stride, film_folded, wqkv_packed, wo, w1, w2, M, L, d, H, ff,
-                                 n_layers, causal, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+    return idb200::encoder_fused(h, layer_params, bias_last, film, film_stride, film_ln_stride, film_folded, wqkv_packed, wo, w1, w2, M, L, d, H,
+                                 ff, n_layers, causal, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int idb200_denoiser_fused(const idb200_embed_t* embed, const idb200_head_t* head, float* h, const float* layer_params,
-                                     const float* bias_last, const float* film, int64_t film_stride, int film_folded,
-                                     const void* wqkv_packed, const void* wo, const void* w1, const void* w2, int64_t M, int L, int d,
-                                     int H, int ff, int n_layers, int causal, idb200_stream_t stream) {
-    return idb200::encoder_fused(h, layer_params, bias_last, film, film_stride, film_folded, wqkv_packed, wo, w1, w2, M, L, d, H, ff,
-                                 n_layers, causal, embed, head, static_cast<cudaStream_t>(stream));
+                                     const float* bias_last, const float* film, int64_t film_stride, int64_t film_ln_stride,
+                                     int film_folded, const void* wqkv_packed, const void* wo, const void* w1, const void* w2, int64_t M,
+                                     int L, int d, int H, int ff, int n_layers, int causal, idb200_stream_t stream) {
+    return idb200::encoder_fused(h, layer_params, bias_last, film, film_stride, film_ln_stride, film_folded, wqkv_packed, wo, w1, w2, M, L, d, H,
+                                 ff, n_layers, causal, embed, head, static_cast<cudaStream_t>(stream));
 }

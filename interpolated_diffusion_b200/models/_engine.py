@@ -66,19 +66,24 @@ class Film:
     folded = False: rows are [gamma | beta] (transformer.py:37,43: a = LN(h) * (1 + gamma) + beta).
     folded = True : rows are [scale | shift] with the LayerNorm affine folded in (the form idb200_encoder_fused reads)."""
 
-    def __init__(self, t: torch.Tensor, folded: bool):
-        self.t, self.folded = t, folded
+    def __init__(self, t: torch.Tensor, folded: bool, ln_major: bool = False):
+        self.t, self.folded, self.ln_major = t, folded, ln_major        # ln_major: t is [2 * n_layers, B, 2d]
+
+    def strides(self):
+        """(table, floats between trajectories, floats between LayerNorm slots) as idb200_encoder_fused takes them."""
+        t = self.t
+        if t.stride(2) != 1:
+            t = self.t = t.contiguous()
+        return (t, t.stride(1), t.stride(0)) if self.ln_major else (t, t.stride(0), t.stride(1))
 
 
 def encoder_fused(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causal: bool):
     """Every layer of the encoder in one persistent kernel (idb200_encoder_fused): h stays in tensor memory."""
     M, d = h.shape
     f = pk.fused
-    ft = None if film is None else film.t
-    if ft is not None and (ft.stride(2) != 1 or ft.stride(1) != 2 * d):
-        ft = ft.contiguous()
+    ft, fts, ftl = (None, 0, 0) if film is None else film.strides()
     L.call("idb200_encoder_fused", h.data_ptr(), f["params"].data_ptr(), f["bias_last"].data_ptr(), L.ptr(ft),
-           0 if ft is None else ft.stride(0), int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           fts, ftl, int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
            f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(h.device))
     return h
 
@@ -88,12 +93,10 @@ def encoder_fused_head(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Fil
     written back; y [M, D] = out(h_final)."""
     M, d = h.shape
     f = pk.fused
-    ft = None if film is None else film.t
-    if ft is not None and (ft.stride(2) != 1 or ft.stride(1) != 2 * d):
-        ft = ft.contiguous()
+    ft, fts, ftl = (None, 0, 0) if film is None else film.strides()
     head = L.HeadDesc(W_out.data_ptr(), b_out.data_ptr(), y.data_ptr(), W_out.shape[0])
     L.call("idb200_denoiser_fused", None, ctypes.byref(head), h.data_ptr(), f["params"].data_ptr(), f["bias_last"].data_ptr(),
-           L.ptr(ft), 0 if ft is None else ft.stride(0), int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           L.ptr(ft), fts, ftl, int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
            f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(y.device))
     return y
 
@@ -104,15 +107,13 @@ def denoiser_fused(pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causa
     only in tensor memory.  Arguments as embed_tokens / out_head; y [M, D] is written."""
     f = pk.fused
     d = pk.d
-    ft = None if film is None else film.t
-    if ft is not None and (ft.stride(2) != 1 or ft.stride(1) != 2 * d):
-        ft = ft.contiguous()
+    ft, fts, ftl = (None, 0, 0) if film is None else film.strides()
     emb = L.EmbedDesc(src0.data_ptr(), src0.shape[-1], L.ptr(src1), 0 if src1 is None else src1.shape[-1], L.ptr(src2),
                       0 if src2 is None else src2.shape[-1], Wf.data_ptr(), tab.data_ptr(), L.ptr(tab_idx), row_a.data_ptr(),
                       0 if row_a.shape[0] == 1 else row_a.stride(0), row_b.data_ptr())
     head = L.HeadDesc(W_out.data_ptr(), b_out.data_ptr(), y.data_ptr(), W_out.shape[0])
     L.call("idb200_denoiser_fused", ctypes.byref(emb), ctypes.byref(head), None, f["params"].data_ptr(), f["bias_last"].data_ptr(),
-           L.ptr(ft), 0 if ft is None else ft.stride(0), int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           L.ptr(ft), fts, ftl, int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
            f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(y.device))
     return y
 
@@ -248,13 +249,24 @@ class PackedEncoder:
             return None
         folded = Lseq is not None and self.fused_path(Lseq, precision)
         B = cond_vec.shape[0]
-        if precision == "bf16" and cond_vec.shape[1] % 64 == 0:
+        nln, d2 = len(self.layers) * 2, 2 * self.d
+        tc = precision == "bf16" and cond_vec.shape[1] % 64 == 0
+        if folded:
+            # LayerNorm-major table [2 * n_layers, B, 2d]: the rows of a 128-token tile are contiguous for every LayerNorm
+            out = torch.empty((nln, B, d2), device=cond_vec.device, dtype=torch.float32)
+            a16 = cond_vec.to(torch.bfloat16).contiguous() if tc else None
+            for j in range(nln):
+                if tc:
+                    gemm_bf16(a16, self.film_w_folded16[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j], EPI_F32)
+                else:
+                    sgemm(cond_vec, self.film_w_folded[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j])
+            return Film(out, True, ln_major=True)
+        if tc:
             out = torch.empty((B, self.film_w.shape[0]), device=cond_vec.device, dtype=torch.float32)
-            gemm_bf16(cond_vec.to(torch.bfloat16).contiguous(), self.film_w_folded16 if folded else self.film_w16,
-                      self.film_b_folded if folded else self.film_b, out, EPI_F32)
+            gemm_bf16(cond_vec.to(torch.bfloat16).contiguous(), self.film_w16, self.film_b, out, EPI_F32)
         else:
-            out = sgemm(cond_vec, self.film_w_folded if folded else self.film_w, self.film_b_folded if folded else self.film_b)
-        return Film(out.view(B, len(self.layers) * 2, 2 * self.d), folded)
+            out = sgemm(cond_vec, self.film_w, self.film_b)
+        return Film(out.view(B, nln, d2), False)
 
     def forward(self, h: torch.Tensor, B: int, Lseq: int, film, precision: str = "bf16") -> torch.Tensor:
         """In-place on the fp32 residual stream h [B*L, d].  film: Film, a raw [gamma | beta] tensor, or None."""
