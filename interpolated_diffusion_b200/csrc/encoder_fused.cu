@@ -396,7 +396,12 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (pair mode: the even CTA only) =====================
-        if (lane == 0 && rank == 0) {
+        // The whole warp runs the schedule (warp-uniform control flow, uniform descriptors); only the tcgen05 instructions are
+        // predicated on one lane.  Issuing from inside an `if (lane == 0)` region made ptxas wrap every MMA in an
+        // ELECT / R2UR.BROADCAST waterfall loop (~18 instructions and ~100 cycles per MMA: the issue rate, not the tensor
+        // pipe, was the limit of the MLP half).
+        if (rank == 0) {
+            const bool issue = lane == 0;
             constexpr uint32_t kM = kPair ? 256 : 128;
             constexpr uint32_t idesc64 = umma_idesc_bf16(kM, 64);
             constexpr uint32_t idesc128 = umma_idesc_bf16(kM, 128);
@@ -421,16 +426,22 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 tc_fence_after();
                 mstamp(tag == 21 || tag == 22 || tag == 24 || tag == 25 || tag == 27 || tag == 29 ? 0 : 1);
             };
-            auto commit = [&](uint64_t* bar) { if (kPair) umma_commit_2sm(bar); else umma_commit(bar); };
+            auto commit = [&](uint64_t* bar) {
+                if (elect_one_sync()) { if (kPair) umma_commit_2sm(bar); else umma_commit(bar); }
+                __syncwarp();
+            };
             // 4 x (K = 16) MMAs of one 64-wide k-block: A tile at a_addr, B tile at b_addr
             auto mma4 = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool first_zero) {
                 const uint64_t ad = umma_desc_sw128(a_addr);
                 const uint64_t bd = umma_desc_sw128(b_addr);
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (kPair) umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
-                    else umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < 4; ++k) {
+                        if (kPair) umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
+                        else umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
+                    }
                 }
+                __syncwarp();
             };
             auto slot_begin = [&](int tag) -> uint32_t {
                 wait(&slot_full[slot], sphase, tag);
@@ -540,7 +551,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     }
                 }
             }
-            if (kProf) {
+            if (kProf && issue) {
                 mstamp(2);
                 for (int i = 0; i < 3; ++i) atomicAdd(p.prof + P_MSLOT + i, macc[i] * (kPair ? 2 : 1));   // per tile: the pair's issuer serves two
             }
