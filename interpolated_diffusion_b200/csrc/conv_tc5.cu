@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
             if (lane == 0) mbar_arrive(act_full);
         }
     } else if (warp == 4) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: warp-uniform schedule, one elected lane issues =====================
+        {
             constexpr uint32_t idesc = umma_idesc_bf16(128, kC2);
             const uint32_t sA = smem_u32(act), sW = smem_u32(wB);
             long long it = 0;
@@ -183,12 +183,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
                         const int ky = tap / 3, kx = tap - ky * 3;
                         const uint64_t ad = umma_desc_sw64(sA + kx * act_bytes + (t * 128 + ky * p.PW) * 64);
                         const uint64_t bd = umma_desc_sw64(sW + tap * 4096);
-                        umma_bf16(d, ad, bd, idesc, tap ? 1u : 0u);
-                        umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                        if (elect_one_sync()) {
+                            umma_bf16(d, ad, bd, idesc, tap ? 1u : 0u);
+                            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                        }
+                        __syncwarp();
                     }
                 }
-                umma_commit(act_empty);
-                umma_commit(&acc_full[buf]);
+                if (elect_one_sync()) {
+                    umma_commit(act_empty);
+                    umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
             }
         }
     } else {
