@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libidb200.so")
+LIB_PATH = os.environ.get("IDB200_LIB") or os.path.join(_HERE, "libidb200.so")      # IDB200_LIB: dev A/B of two builds in one run
 
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int
