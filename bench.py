@@ -167,6 +167,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the ONE JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     from interpolated_diffusion_b200 import _lib as L
     from interpolated_diffusion_b200.models import _engine as E
