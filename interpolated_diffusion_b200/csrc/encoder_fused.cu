@@ -133,10 +133,10 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
     if (kFilmSmem && film != nullptr) __builtin_assume(__isShared(film));
     const int c0 = part * 64;
     const uint32_t t0 = tmem_row + c0;
-    // ---- pass 1: x = h + pending bias -> TMEM; statistics (both 32-column loads in flight) ----
+    // ---- pass 1: x = h + pending bias (kept in registers for pass 2, written back to TMEM); statistics ----
     float xs, s1 = 0.0f, s2 = 0.0f;
+    uint32_t r[2][32];
     {
-        uint32_t r[2][32];
         tmem_ld_32x32(t0, r[0]);
         tmem_ld_32x32(t0 + 32, r[1]);
         tmem_ld_wait();
@@ -161,7 +161,6 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
         }
     }
     stat[part * 128 + row] = make_float2(xs + s1 * (1.0f / 64.0f), s2 - s1 * s1 * (1.0f / 64.0f));
-    tmem_st_wait();
     if (tt) tt[0] = clock64();
     named_barrier_sync(3, kCT);
     if (tt) tt[1] = clock64();
@@ -176,10 +175,7 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
     const float shift = -mean * rstd;
     if (kFilmSmem) mbar_wait(film_full, film_parity, 58);
     if (tt) tt[2] = clock64();
-    // ---- pass 2: normalise, FiLM, pack (the second 32-column load is in flight while the first is processed) ----
-    uint32_t r[2][32];
-    tmem_ld_32x32(t0, r[0]);
-    tmem_ld_32x32(t0 + 32, r[1]);
+    // ---- pass 2: normalise, FiLM, pack -- from the registers of pass 1 (no second TMEM read) ----
     uint8_t* xt = X + part * kTile;
     // scale / shift: the folded FiLM row (staged in shared memory, or in global memory when L < 8) or the LayerNorm affine
     const bool folded = (mode == kFilmFolded) && film != nullptr;
@@ -190,7 +186,6 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
     const uint32_t fls = (kFilmSmem && raw) ? smem_u32(film) + c0 * 4 : 0u;
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
-        tmem_ld_wait();
         const int col = c0 + cc * 32;
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {                                 // 8 columns -> one 16-byte swizzle chunk
@@ -228,6 +223,7 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
             *reinterpret_cast<uint4*>(xt + sw128_offset(row, cc * 32 + 8 * j2)) = pk;
         }
     }
+    tmem_st_wait();                                                      // the write-back of pass 1 has landed (before x_full is signalled)
 }
 
 // kProf (dev, IDB200_PROF=1): compute warp 0 lane 0 accumulates clock64() spans per phase into p.prof[0..15]
