@@ -383,9 +383,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                         else wo(i < 7 ? (i >> 1) - 1 : 3);
                     }
 #pragma unroll 1
-                    for (int c = -2; c < nc; ++c) {
-                        if (c >= 0) ff2(c);
+                    for (int c = -2; c < nc; ++c) {                    // FF1_{c+2} first: it only needs acc1 drained (signalled early)
                         if (c + 2 < nc) ff1(c + 2);
+                        if (c >= 0) ff2(c);
                     }
                 }
             }
@@ -541,9 +541,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     wait(x_full, n_x & 1, 31);
                     ++n_x;
 #pragma unroll 1
-                    for (int c = -2; c < nc; ++c) {
-                        if (c >= 0) ff2(c);
+                    for (int c = -2; c < nc; ++c) {                    // FF1_{c+2} first: it only needs acc1 drained (signalled early)
                         if (c + 2 < nc) ff1(c + 2);
+                        if (c >= 0) ff2(c);
                     }
                 }
             }
@@ -823,6 +823,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                         uint32_t r[32];
                         tmem_ld_32x32(tmem_acc + lane_base + b * 128 + part * 32, r);
                         tmem_ld_wait();
+                        tc_fence_before();                               // the accumulator is in registers: release it at once, so that
+                        __syncwarp();                                    // FF1_{c+2} runs under the SiLU / store work of this chunk
+                        if (lane == 0) arrive_mma(&acc1_empty[b]);
                         const float* bb = sb1 + c * 128 + part * 32;    // 0.5 * b1 (pre-halved on the host)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {                    // 8 columns -> one 16-byte swizzle chunk
@@ -839,10 +842,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     tc_fence_before();
                     fence_proxy_async_smem();                            // H writes -> visible to the tensor core
                     __syncwarp();
-                    if (lane == 0) {
-                        arrive_mma(&acc1_empty[b]);
-                        arrive_mma(&hb_full[b]);
-                    }
+                    if (skip && lane == 0) arrive_mma(&acc1_empty[b]);
+                    if (lane == 0) arrive_mma(&hb_full[b]);
                     ++use1[b];
                     ++useh[b];
                     stamp(P_EPI1);
