@@ -9,6 +9,8 @@
 // Every fp32 op is an explicitly rounded intrinsic in the reference's order (bit-identical to the
 // eager op-by-op evaluation; IEEE sqrt/div).  All kernels are grid-stride with grids sized in
 // multiples of the SM count; traffic is exactly one read of each input and one write of the output.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace idb200 {
@@ -36,6 +38,44 @@ __global__ void __launch_bounds__(kThreads) ddim_step_kernel(
         if (known_mask && known_mask[i]) r = known_values[i];                    // sample_generate.py:398
         if (pos_clip && (i % D) < 2) r = fminf(fmaxf(r, clip_min), clip_max);    // :382-386
         out[i] = r;
+    }
+}
+
+// Batch-constant timestep (the generation loop, sample_generate.py:394-395): the four square roots are per-launch scalars
+// and the row is streamed as float4 / uchar4 (n % 4 == 0, D | 4, 16-byte aligned).  Same operations in the same order as
+// ddim_step_kernel, so the result is bit-identical.
+__global__ void __launch_bounds__(kThreads) ddim_step_scalar4_kernel(
+    const float4* __restrict__ z, const float4* __restrict__ eps, float ab_t, float ab_p, long long n4, int D,
+    const uchar4* __restrict__ known_mask, const float4* __restrict__ known_values, int pos_clip, float clip_min, float clip_max,
+    float4* __restrict__ out) {
+    const float s_1mt = __fsqrt_rn(__fsub_rn(1.0f, ab_t)), s_t = __fsqrt_rn(ab_t);
+    const float s_p = __fsqrt_rn(ab_p), s_1mp = __fsqrt_rn(__fsub_rn(1.0f, ab_p));
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 zz = z[i], e = eps[i];
+        float r[4];
+        const float zv[4] = {zz.x, zz.y, zz.z, zz.w}, ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float x0 = __fdiv_rn(__fsub_rn(zv[j], __fmul_rn(s_1mt, ev[j])), s_t);            // ddpm.py:45
+            r[j] = __fadd_rn(__fmul_rn(s_p, x0), __fmul_rn(s_1mp, ev[j]));                       // ddpm.py:47
+        }
+        if (known_mask) {                                                                        // sample_generate.py:398
+            const uchar4 km = known_mask[i];
+            if (km.x | km.y | km.z | km.w) {
+                const float4 kv = known_values[i];
+                if (km.x) r[0] = kv.x;
+                if (km.y) r[1] = kv.y;
+                if (km.z) r[2] = kv.z;
+                if (km.w) r[3] = kv.w;
+            }
+        }
+        if (pos_clip) {                                                                          // :382-386 (dims 0, 1 of every D)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (((i * 4 + j) % D) < 2) r[j] = fminf(fmaxf(r[j], clip_min), clip_max);
+        }
+        out[i] = make_float4(r[0], r[1], r[2], r[3]);
     }
 }
 
@@ -122,6 +162,58 @@ __global__ void __launch_bounds__(kThreads) stage2_epilogue_kernel(
     }
 }
 
+// D = 2 or 4, aligned rows: one thread per token (b, t), the token's D values as one float2 / float4; no per-element integer
+// divisions.  Same operations in the same order as stage2_epilogue_kernel (bit-identical).
+template <int kD>
+__global__ void __launch_bounds__(kThreads) stage2_epilogue_vec_kernel(
+    const float* __restrict__ x_in, const float* __restrict__ delta, const float* __restrict__ x_ref,
+    const float* __restrict__ conf, float lam, int policy, const unsigned char* __restrict__ clamp_mask, int dims_all,
+    int pos_clip, float clip_min, float clip_max, long long BT, int T, float* __restrict__ out) {
+    using V = typename std::conditional<kD == 2, float2, float4>::type;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const bool soft = conf != nullptr && lam > 0.0f;
+    for (long long bt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; bt < BT; bt += stride) {
+        float x[kD], xr[kD];
+        {
+            const V v = reinterpret_cast<const V*>(x_in)[bt];
+            const float* vp = reinterpret_cast<const float*>(&v);
+#pragma unroll
+            for (int d = 0; d < kD; ++d) x[d] = vp[d];
+        }
+        if (delta) {
+            const V v = reinterpret_cast<const V*>(delta)[bt];
+            const float* vp = reinterpret_cast<const float*>(&v);
+#pragma unroll
+            for (int d = 0; d < kD; ++d) x[d] = __fadd_rn(x[d], vp[d]);
+        }
+        const int t = static_cast<int>(bt % T);
+        const bool hard = (policy == IDB200_CLAMP_ENDPOINTS) ? (t == 0 || t == T - 1) : (policy == IDB200_CLAMP_MASK) ? (clamp_mask[bt] != 0) : false;
+        if (soft || hard) {
+            const V v = reinterpret_cast<const V*>(x_ref)[bt];
+            const float* vp = reinterpret_cast<const float*>(&v);
+#pragma unroll
+            for (int d = 0; d < kD; ++d) xr[d] = vp[d];
+            const float w = soft ? __fmul_rn(conf[bt], lam) : 0.0f;
+#pragma unroll
+            for (int d = 0; d < kD; ++d) {
+                if (dims_all || d < 2) {
+                    if (soft) x[d] = __fadd_rn(x[d], __fmul_rn(w, __fsub_rn(xr[d], x[d])));
+                    if (hard) x[d] = xr[d];
+                }
+            }
+        }
+        if (pos_clip) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) x[d] = fminf(fmaxf(x[d], clip_min), clip_max);
+        }
+        V o;
+        float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int d = 0; d < kD; ++d) op[d] = x[d];
+        reinterpret_cast<V*>(out)[bt] = o;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) anchor_conf_kernel(
     const unsigned char* __restrict__ mask_s, const unsigned char* __restrict__ student,
     const unsigned char* __restrict__ mask_prev, const long long* __restrict__ s_row, int s_scalar, int levels, int anneal,
@@ -175,6 +267,14 @@ extern "C" int idb200_ddim_step(const float* z, const float* eps, const int64_t*
     IDB_REQUIRE((known_mask == nullptr) == (known_values == nullptr), IDB200_EINVAL, "known_mask/known_values mismatch");
     const long long n = n_rows * row_len;
     if (n == 0) return IDB200_OK;
+    if (t == nullptr && n % 4 == 0 && idb200::aligned(z, 16) && idb200::aligned(eps, 16) && idb200::aligned(z_out, 16) &&
+        (!known_mask || (idb200::aligned(known_mask, 4) && idb200::aligned(known_values, 16)))) {
+        ddim_step_scalar4_kernel<<<ew_grid(n / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(eps), ab_t, ab_prev, n / 4, D,
+            reinterpret_cast<const uchar4*>(known_mask), reinterpret_cast<const float4*>(known_values), pos_clip, clip_min, clip_max,
+            reinterpret_cast<float4*>(z_out));
+        return check_launch("ddim_step_scalar4_kernel");
+    }
     ddim_step_kernel<<<ew_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         z, eps, reinterpret_cast<const long long*>(t), reinterpret_cast<const long long*>(t_prev), alpha_bar, ab_t, ab_prev,
         n, row_len, D, known_mask, known_values, pos_clip, clip_min, clip_max, z_out);
@@ -230,6 +330,18 @@ extern "C" int idb200_stage2_epilogue(const float* x_in, const float* delta, con
     IDB_REQUIRE(policy != IDB200_CLAMP_MASK || clamp_mask, IDB200_EINVAL, "clamp_mask missing");
     IDB_REQUIRE((policy == IDB200_CLAMP_NONE && !(conf && lam > 0.0f)) || x_ref, IDB200_EINVAL, "x_ref missing");
     if (B == 0) return IDB200_OK;
+    const size_t al = D == 2 ? 8 : 16;
+    if ((D == 2 || D == 4) && idb200::aligned(x_in, al) && idb200::aligned(out, al) && (!delta || idb200::aligned(delta, al)) &&
+        (!x_ref || idb200::aligned(x_ref, al))) {
+        const int grid = ew_grid(B * T);
+        if (D == 2)
+            stage2_epilogue_vec_kernel<2><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                x_in, delta, x_ref, conf, lam, policy, clamp_mask, clamp_dims_all, pos_clip, clip_min, clip_max, B * T, T, out);
+        else
+            stage2_epilogue_vec_kernel<4><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                x_in, delta, x_ref, conf, lam, policy, clamp_mask, clamp_dims_all, pos_clip, clip_min, clip_max, B * T, T, out);
+        return check_launch("stage2_epilogue_vec_kernel");
+    }
     stage2_epilogue_kernel<<<ew_grid(B * T * D), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         x_in, delta, x_ref, conf, lam, policy, clamp_mask, clamp_dims_all, pos_clip, clip_min, clip_max, B, T, D, out);
     return check_launch("stage2_epilogue_kernel");
