@@ -174,6 +174,33 @@ def run_ours(args):
     from interpolated_diffusion_b200.models import _engine as E
     from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph
 
+    interp = None
+    if rank == 0 and not args.skip_interp:
+        # second half of BASELINE's metric ("interp GB/s", configs[1]): the Interp(x0|M_s) corruption kernel alone on 2^20 synthetic
+        # trajectories, T = 64, D = 4, 3 nested mask levels; algorithmic bytes = 4600 per trajectory; median of 20 launches
+        from interpolated_diffusion_b200.corruptions import keyframes as kf
+        Bi, Ti, Di, Si = 1 << 20, 64, 4, 3
+        gi = torch.Generator(device=dev).manual_seed(1234)
+        scores = torch.rand((Bi, Ti - 2), generator=gi, device=dev)
+        x0 = torch.rand((Bi, Ti, Di), generator=gi, device=dev)
+        K_list = kf._compute_k_schedule(Ti, K_MIN, Si)
+        for _ in range(3):
+            kf.nested_masks_interp(scores, Ti, K_list, x0=x0, levels_out=(1, Si), want_idx=False)
+        torch.cuda.synchronize(dev)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(21)]
+        evs[0].record()
+        for i in range(20):
+            kf.nested_masks_interp(scores, Ti, K_list, x0=x0, levels_out=(1, Si), want_idx=False)
+            evs[i + 1].record()
+        torch.cuda.synchronize(dev)
+        ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(20))[10]
+        nbytes = Bi * (Ti * Di * 4 * (1 + Si) + (Ti - 2) * 4 + (Si + 1) * Ti)
+        pk = peaks()
+        interp = {"workload": "Interp(x0|M_s): 2^20 trajectories, T=64, D=4, 3 nested levels (BASELINE.json configs[1])", "ms": ms,
+                  "GBps": nbytes / ms / 1e6, "peak_GBps": pk["hbm_gbs"], "frac": nbytes / ms / 1e6 / pk["hbm_gbs"],
+                  "trajectories_per_s": Bi / ms * 1e3, "bytes_per_trajectory": nbytes // Bi}
+        del scores, x0
+
     B = args.batch
     cfg = GenerationConfig(T=T, K_min=K_MIN, levels=LEVELS, data_dim=D)
     kp, il = build_models(dev)
@@ -304,7 +331,7 @@ def run_ours(args):
                        "cuda_graph": True, "l2": "per-step activation working set (~20 GB) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "roofline": roof, "kernels": breakdown,
+            "clocks": clocks, "roofline": roof, "kernels": breakdown, "interp": interp,
             "flops_per_traj_gemm": gemm_flops_per_traj(), "tflops_e2e": value * gemm_flops_per_traj() / 1e12,
         }
         if cpu_rate is not None:
@@ -325,6 +352,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024, help="trajectories of the CPU baseline sample")
     ap.add_argument("--ref-batch", type=int, default=512, help="trajectories per step of the reference arm")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-interp", action="store_true", help="skip the interp-kernel (configs[1]) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
