@@ -105,12 +105,17 @@ def synthetic_cond(B: int, seed: int, device="cpu", pin=False):
     return {"occ": occ.to(device), "start_goal": sg.to(device)}
 
 
-def build_models(device):
+# trainer defaults of the reference (train_interp_levels.py:57-62): the "large" models of SURVEY 8d (second line of cfg 3)
+LARGE = dict(d_model=384, n_layers=12, n_heads=12, d_ff=1536, maze_channels=(32, 64, 128, 128))
+
+
+def build_models(device, large: bool = False):
     from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
     from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
     torch.manual_seed(0)
-    kp = KeypointDenoiser(data_dim=D)
-    il = InterpLevelDenoiser(data_dim=D, max_levels=LEVELS, mask_channels=2)
+    kw = LARGE if large else {}
+    kp = KeypointDenoiser(data_dim=D, **kw)
+    il = InterpLevelDenoiser(data_dim=D, max_levels=LEVELS, mask_channels=2, **kw)
     return kp.to(device), il.to(device)
 
 
@@ -203,7 +208,7 @@ def run_ours(args):
 
     B = args.batch
     cfg = GenerationConfig(T=T, K_min=K_MIN, levels=LEVELS, data_dim=D)
-    kp, il = build_models(dev)
+    kp, il = build_models(dev, large=(args.model == "large"))
     graph = GenerationGraph(kp, il, B, cfg, device=dev)
     # count this library's kernel launches in one step (every L.call enqueues exactly one kernel here)
     calls = [0]
@@ -351,6 +356,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="trajectories per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="trajectories of the CPU baseline sample")
     ap.add_argument("--ref-batch", type=int, default=512, help="trajectories per step of the reference arm")
+    ap.add_argument("--model", default="small", choices=["small", "large"], help="small = BASELINE configs[2] (default); large = trainer-default models (dev)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-interp", action="store_true", help="skip the interp-kernel (configs[1]) measurement")
     args = ap.parse_args()
