@@ -306,6 +306,28 @@ int idb200_conv_encoder_tc5(const float* occ, const float* sdf, int64_t B, int H
                             const float* w0, const float* b0, const void* w1_packed_bf16, const float* b1,
                             float* pooled, idb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tail of the Stage-2 training step, src/train/train_interp_levels.py:1142-1173 (the network's backward pass between the
+ * loss gradient and the optimiser is NOT part of this library yet).
+ * ------------------------------------------------------------------------------------------------ */
+/* loss = sum_bt(w * ||delta_hat - target||^2) / (sum_bt(w) * D + 1e-8) / grad_accum, w = w_missing + (w_anchor - w_missing) *
+ * conf[b,t] (anchor_conf branch, conf fp32 [B,T]) or w_anchor / w_missing by mask[b,t] (uint8) -- exactly one of conf / mask.
+ * loss_scal[0] = loss, loss_scal[1] = the common factor of the gradient; grad_out (or NULL) = d loss / d delta_hat [B,T,D].
+ * scratch: 2 * 1184 doubles (per-block partial sums, reduced in a fixed order: deterministic). */
+int idb200_stage2_loss(const float* delta_hat, const float* target, const float* conf, const uint8_t* mask, float w_anchor,
+                       float w_missing, float grad_accum, int64_t B, int T, int D, double* scratch, float* loss_scal,
+                       float* grad_out, idb200_stream_t stream);
+
+/* torch.nn.utils.clip_grad_norm_ over ONE flat gradient buffer: norm_coef[0] = ||grad||_2, norm_coef[1] = min(1, max_norm /
+ * (norm + 1e-6)).  scratch: 1184 doubles.  The coefficient is consumed on the device by idb200_adamw_ema_step. */
+int idb200_grad_clip_coef(const float* grad, int64_t n, float max_norm, double* scratch, float* norm_coef, idb200_stream_t stream);
+
+/* torch.optim.AdamW step (decoupled weight decay, bias-corrected, torch's operation order) on grad * norm_coef[1] (norm_coef
+ * NULL: unclipped), followed by EMA.update (src/utils/ema.py:11-17; ema NULL: skipped).  step is 1-based.  36 B per parameter. */
+int idb200_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int64_t step, float ema_decay,
+                          const float* norm_coef, idb200_stream_t stream);
+
 /* Batched trajectory metrics, src/eval/metrics.py:68-128 (compute_metrics_batch; _pos_to_cell :13-24): the step right after
  * the generation path (the reference loops over samples on the host, sample_generate.py:1323-1398).
  *   occ fp32 [B,H,W] (occ_stride = H*W, or 0 to broadcast one map); traj fp32 [B,T,D], dims 0:2 = (x, y) in [0,1];

@@ -46,6 +46,9 @@ _SIGS = {
     "idb200_conv_encoder_tc": [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
     "idb200_traj_metrics": [c_p, c_l, c_p, c_p, c_l, c_p, c_l, c_l, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_p],
     "idb200_conv_encoder_tc5": [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
+    "idb200_stage2_loss": [c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_l, c_i, c_i, c_p, c_p, c_p, c_p],
+    "idb200_grad_clip_coef": [c_p, c_l, c_f, c_p, c_p, c_p],
+    "idb200_adamw_ema_step": [c_p, c_p, c_p, c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_f, c_l, c_f, c_p, c_p],
     "idb200_anchor_conf": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_l, c_i, c_i, c_p, c_p, c_p],
 }
 

@@ -1,0 +1,109 @@
+"""Tail of the reference's Stage-2 training step on libidb200 kernels (``src/train/train_interp_levels.py:1142-1173``):
+
+* ``stage2_loss``      -- the weighted MSE of :1144-1156 and its gradient with respect to the denoiser output (the seed of the
+                          backward pass; the network's backward itself is not part of this library yet);
+* ``FlatAdamW``        -- ``clip_grad_norm_`` + ``torch.optim.AdamW.step`` + ``EMA.update`` (:1162-1173, ``src/utils/ema.py``) as
+                          two launches over ONE flat fp32 arena holding every parameter (36 B of HBM traffic per parameter).
+
+CUDA only.  Same hyper-parameter names and defaults as the reference's call sites (lr 2e-4, weight_decay 1e-2, betas (0.9, 0.999),
+eps 1e-8, EMA decay 0.999, grad_clip 1.0)."""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+
+from .. import _lib as L
+
+_SCRATCH_DOUBLES = 2 * 1184
+
+
+def stage2_loss(delta_hat: torch.Tensor, target: torch.Tensor, weight_mask: torch.Tensor, *, anchor_conf: bool = True,
+                w_anchor: float = 0.1, w_missing: float = 1.0, grad_accum: int = 1, want_grad: bool = True
+                ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """loss (0-dim fp32 tensor, no host sync) and d loss / d delta_hat [B,T,D] (train_interp_levels.py:1144-1156).
+    ``weight_mask``: conf fp32 [B,T] when ``anchor_conf`` else the bool anchor mask [B,T]."""
+    dev = L.require_cuda(delta_hat, target, weight_mask)
+    dh, tg = L.f32c(delta_hat), L.f32c(target)
+    if dh.shape != tg.shape or dh.dim() != 3:
+        raise ValueError("delta_hat and target must both be [B,T,D]")
+    B, T, D = dh.shape
+    if tuple(weight_mask.shape) != (B, T):
+        raise ValueError("weight_mask must be [B,T]")
+    conf = L.f32c(weight_mask) if anchor_conf else None
+    mask = None if anchor_conf else L.u8c(weight_mask)
+    scratch = torch.empty((_SCRATCH_DOUBLES,), device=dev, dtype=torch.float64)
+    scal = torch.empty((2,), device=dev, dtype=torch.float32)
+    grad = torch.empty_like(dh) if want_grad else None
+    L.call("idb200_stage2_loss", dh.data_ptr(), tg.data_ptr(), L.ptr(conf), L.ptr(mask), float(w_anchor), float(w_missing),
+           float(grad_accum), B, T, D, scratch.data_ptr(), scal.data_ptr(), L.ptr(grad), L.stream(dev))
+    return scal[0], grad
+
+
+class FlatAdamW:
+    """``torch.optim.AdamW`` + ``clip_grad_norm_`` + ``EMA`` over one flat fp32 arena.  The parameters are re-pointed at views
+    of the arena (so the model keeps working on them); ``step()`` gathers ``p.grad`` (or takes a flat gradient, e.g. the output
+    of a reduce-scatter / all-reduce) and runs two launches: global-norm clip coefficient, fused AdamW + EMA."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, ema_decay: Optional[float] = 0.999, max_grad_norm: Optional[float] = 1.0):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("optimizer got an empty parameter list")
+        dev = L.require_cuda(*[p.data for p in self.params])
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.ema_decay, self.max_grad_norm = ema_decay, max_grad_norm
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4                   # 16-byte aligned slices
+        self.n = n
+        self.flat = torch.zeros((n,), device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
+            self.flat[o:o + p.numel()].copy_(p.data.detach().float().reshape(-1))
+            p.data = self.flat[o:o + p.numel()].view(p.shape)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.ema = self.flat.clone() if ema_decay is not None else None
+        self.grad = torch.zeros_like(self.flat)
+        self.scratch = torch.empty((_SCRATCH_DOUBLES,), device=dev, dtype=torch.float64)
+        self.norm_coef = torch.ones((2,), device=dev, dtype=torch.float32)
+        self.step_count = 0
+
+    def views(self, flat: torch.Tensor) -> List[torch.Tensor]:
+        return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]
+
+    @property
+    def ema_shadow(self) -> Optional[List[torch.Tensor]]:
+        """The EMA copies, one per parameter (``EMA.shadow`` of src/utils/ema.py)."""
+        return None if self.ema is None else self.views(self.ema)
+
+    def gather_grads(self) -> torch.Tensor:
+        for p, g in zip(self.params, self.views(self.grad)):
+            if p.grad is None:
+                g.zero_()
+            else:
+                g.copy_(p.grad)
+        return self.grad
+
+    @torch.no_grad()
+    def step(self, flat_grad: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """Returns the total gradient norm (device tensor) when clipping is on, like ``clip_grad_norm_``."""
+        g = self.gather_grads() if flat_grad is None else flat_grad
+        if g.numel() != self.n or g.dtype != torch.float32 or not g.is_contiguous():
+            raise ValueError("flat_grad must be a contiguous fp32 tensor with the arena's layout")
+        dev = self.flat.device
+        self.step_count += 1
+        coef = None
+        if self.max_grad_norm is not None:
+            L.call("idb200_grad_clip_coef", g.data_ptr(), self.n, float(self.max_grad_norm), self.scratch.data_ptr(),
+                   self.norm_coef.data_ptr(), L.stream(dev))
+            coef = self.norm_coef
+        L.call("idb200_adamw_ema_step", self.flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+               L.ptr(self.ema), self.n, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
+               float(self.ema_decay if self.ema_decay is not None else 0.0), L.ptr(coef), L.stream(dev))
+        return None if coef is None else self.norm_coef[0]
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            p.grad = None if set_to_none else (p.grad.zero_() if p.grad is not None else None)
