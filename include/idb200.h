@@ -308,7 +308,7 @@ int idb200_conv_encoder_tc5(const float* occ, const float* sdf, int64_t B, int H
 
 /* ------------------------------------------------------------------------------------------------
  * Tail of the Stage-2 training step, src/train/train_interp_levels.py:1142-1173 (the network's backward pass between the
- * loss gradient and the optimiser is NOT part of this library yet).
+ * loss gradient and the optimiser is built from the "Backward" entry points below).
  * ------------------------------------------------------------------------------------------------ */
 /* loss = sum_bt(w * ||delta_hat - target||^2) / (sum_bt(w) * D + 1e-8) / grad_accum, w = w_missing + (w_anchor - w_missing) *
  * conf[b,t] (anchor_conf branch, conf fp32 [B,T]) or w_anchor / w_missing by mask[b,t] (uint8) -- exactly one of conf / mask.
@@ -327,6 +327,51 @@ int idb200_grad_clip_coef(const float* grad, int64_t n, float max_norm, double* 
 int idb200_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n, float lr,
                           float beta1, float beta2, float eps, float weight_decay, int64_t step, float ema_decay,
                           const float* norm_coef, idb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of the denoisers (what loss.backward() does in src/train/train_interp_levels.py:1159 and
+ * src/train/train_keypoints.py:540 for the modules of src/models/{transformer,encoders,denoiser_*}.py).
+ * Dense contractions reuse idb200_gemm_bf16: dX = dY * W is the same GEMM with W^T as the weight operand; dW = dY^T * X is
+ * idb200_gemm_bf16_splitk on bf16 transposes (reduction over the tokens) followed by idb200_reduce_rows.
+ * ---------------------------------------------------------------------------------------------- */
+/* partial[s] [M,N] fp32 = A[:, K_s] * W[:, K_s]^T for the s-th of `splits` equal slices of K ((K / 64) % splits == 0). */
+int idb200_gemm_bf16_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int K, int splits,
+                            idb200_stream_t stream);
+/* dst bf16 [N,M] = src[M,N]^T (src fp32 or bf16). */
+int idb200_transpose_bf16(const void* src, int src_is_f32, int64_t M, int N, void* dst, idb200_stream_t stream);
+/* out[N] (+)= scale * column sums of src[M,N] (src_kind 0 fp32, 1 bf16); scratch: idb200_colsum_scratch_floats(M, N) floats. */
+int idb200_colsum_scratch_floats(int64_t M, int N);
+int idb200_colsum(const void* src, int src_kind, int64_t M, int N, float* scratch, float scale, int accumulate, float* out,
+                  idb200_stream_t stream);
+/* out[W] (+)= scale * sum_r partial[r, W] (fixed order). */
+int idb200_reduce_rows(const float* partial, int R, int64_t W, float scale, int accumulate, float* out, idb200_stream_t stream);
+/* bf16 elementwise, n even: mode 0 y = silu(u); mode 1 y = g * silu'(u). */
+int idb200_silu_bf16(const void* u, const void* g, int64_t n, int mode, void* y, idb200_stream_t stream);
+int idb200_silu_f32(const float* u, const float* g, int64_t n, int mode, float* y, idb200_stream_t stream);   /* fp32 variant */
+/* Backward of a = LayerNorm(h) * (1 + gamma) + beta (transformer.py:35-46): dh += ..., dh_bf16 (or NULL) = bf16 copy of the
+ * updated dh, dgb[b] = [dgamma | dbeta] (NULL iff gamma_beta is NULL), dwb_part [B, 2d] = per-trajectory [dw | db] partials. */
+int idb200_ln_film_bwd(const float* da, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
+                       int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb, int64_t dgb_stride,
+                       float* dwb_part, idb200_stream_t stream);
+/* Backward of the packed-QKV multi-head attention (head_dim 32, L <= 64): qkv, dqkv bf16 [B*L, 3d]; dO bf16 [B*L, d]. */
+int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, idb200_stream_t stream);
+/* dh[M,d] = dy[M,D] * W[D,d] (out head backward, D <= 8), plus an optional bf16 copy. */
+int idb200_head_bwd(const float* dy, const float* W, int64_t M, int d, int D, float* dh, void* dh_bf16, idb200_stream_t stream);
+/* out[n,K] (+)= A[M,n]^T * X[M,K], n <= 8 (out-head / in_proj weight gradients); scratch: ..._scratch_floats(M, n, K). */
+int idb200_narrow_outer_scratch_floats(int64_t M, int n, int K);
+int idb200_narrow_outer(const float* A, int n, const float* X, int64_t M, int K, float* scratch, int accumulate, float* out,
+                        idb200_stream_t stream);
+/* out[B,d] = sum over the L tokens of src[B,L,d]. */
+int idb200_token_sum(const float* src, int64_t B, int L, int d, float* out, idb200_stream_t stream);
+/* out[i,j] (+)= sum_k A[i*sa0 + k*sa1] * B[j*sb0 + k*sb1]: strided fp32 GEMM for the per-trajectory linears' backward. */
+int idb200_sgemm_strided(const float* A, int64_t sa0, int64_t sa1, const float* Bm, int64_t sb0, int64_t sb1, float* out,
+                         int64_t ldo, int M, int N, int K, int accumulate, idb200_stream_t stream);
+/* Conv encoder in training form (encoders.py:8-25), activations NHWC bf16 [B, H*W, C] holding pre-activations:
+ * col bf16 [B*H*W, Kpad], col[., (ky*3+kx)*C + c] = act(src[., y+ky-1, x+kx-1, c]) (act 1: SiLU), zero padding. */
+int idb200_im2col3x3(const void* src, int64_t B, int H, int W, int C, int Kpad, int act, void* col, idb200_stream_t stream);
+/* pooled[B,C] = mean_p silu(u[B,P,C]);  du = dpooled / P * silu'(u). */
+int idb200_pool_silu(const void* u, int64_t B, int P, int C, float* pooled, idb200_stream_t stream);
+int idb200_pool_silu_bwd(const void* u, const float* dpooled, int64_t B, int P, int C, void* du, idb200_stream_t stream);
 
 /* Batched trajectory metrics, src/eval/metrics.py:68-128 (compute_metrics_batch; _pos_to_cell :13-24): the step right after
  * the generation path (the reference loops over samples on the host, sample_generate.py:1323-1398).

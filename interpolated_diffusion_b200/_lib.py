@@ -49,6 +49,23 @@ _SIGS = {
     "idb200_stage2_loss": [c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_l, c_i, c_i, c_p, c_p, c_p, c_p],
     "idb200_grad_clip_coef": [c_p, c_l, c_f, c_p, c_p, c_p],
     "idb200_adamw_ema_step": [c_p, c_p, c_p, c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_f, c_l, c_f, c_p, c_p],
+    "idb200_gemm_bf16_splitk": [c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
+    "idb200_transpose_bf16": [c_p, c_i, c_l, c_i, c_p, c_p],
+    "idb200_colsum_scratch_floats": [c_l, c_i],
+    "idb200_colsum": [c_p, c_i, c_l, c_i, c_p, c_f, c_i, c_p, c_p],
+    "idb200_reduce_rows": [c_p, c_i, c_l, c_f, c_i, c_p, c_p],
+    "idb200_silu_bf16": [c_p, c_p, c_l, c_i, c_p, c_p],
+    "idb200_silu_f32": [c_p, c_p, c_l, c_i, c_p, c_p],
+    "idb200_ln_film_bwd": [c_p, c_p, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_p, c_p, c_p, c_l, c_p, c_p],
+    "idb200_attention_bwd": [c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
+    "idb200_head_bwd": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p],
+    "idb200_narrow_outer_scratch_floats": [c_l, c_i, c_i],
+    "idb200_narrow_outer": [c_p, c_i, c_p, c_l, c_i, c_p, c_i, c_p, c_p],
+    "idb200_token_sum": [c_p, c_l, c_i, c_i, c_p, c_p],
+    "idb200_sgemm_strided": [c_p, c_l, c_l, c_p, c_l, c_l, c_p, c_l, c_i, c_i, c_i, c_i, c_p],
+    "idb200_im2col3x3": [c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "idb200_pool_silu": [c_p, c_l, c_i, c_i, c_p, c_p],
+    "idb200_pool_silu_bwd": [c_p, c_p, c_l, c_i, c_i, c_p, c_p],
     "idb200_anchor_conf": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_l, c_i, c_i, c_p, c_p, c_p],
 }
 

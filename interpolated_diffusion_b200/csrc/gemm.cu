@@ -77,6 +77,7 @@ struct GemmParams {
     void* out;              // bf16 [M,N] (EPI_BF16 / EPI_SILU_BF16), fp32 [M,N] (EPI_F32), fp32 residual in/out (EPI_RESID_F32)
     long long M;
     int N, K, epilogue;
+    int splits;             // split-K: tile = (split, m, n); split s covers K/splits of the reduction, out += s * M * N (EPI_F32)
 };
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU (tanh.approx, rel. error ~2^-11, below the bf16
@@ -107,8 +108,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lane = threadIdx.x & 31;
     const int n_tiles = p.N / BN;
     const long long m_tiles = (p.M + kBM - 1) / kBM;
-    const long long tiles = m_tiles * n_tiles;
-    const int k_blocks = p.K / kBK;
+    const long long mn_tiles = m_tiles * n_tiles;
+    const long long tiles = mn_tiles * p.splits;
+    const int k_blocks = p.K / kBK / p.splits;             // per split
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -137,9 +139,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m0 = static_cast<int>(tile / n_tiles) * kBM;
-                const int n0 = static_cast<int>(tile % n_tiles) * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const long long mn = tile % mn_tiles;
+                const int kb0 = static_cast<int>(tile / mn_tiles) * k_blocks;
+                const int m0 = static_cast<int>(mn / n_tiles) * kBM;
+                const int n0 = static_cast<int>(mn % n_tiles) * BN;
+                for (int kb = kb0; kb < kb0 + k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + kBM * kBK * 2;
@@ -186,8 +190,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const long long m0 = (tile / n_tiles) * kBM;
-            const int n0 = static_cast<int>(tile % n_tiles) * BN;
+            const long long mn = tile % mn_tiles;
+            const long long m0 = (mn / n_tiles) * kBM;
+            const int n0 = static_cast<int>(mn % n_tiles) * BN;
             mbar_wait(&acc_full[acc], acc_phase, 4);
             tc_fence_after();
             const long long row = m0 + q * 32 + lane;
@@ -215,7 +220,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             if (p.bias) v[j] += __ldg(p.bias + n0 + c + j);
                         }
                     }
-                    const long long o = row * p.N + n0 + c;
+                    const long long o = (tile / mn_tiles) * p.M * p.N + row * p.N + n0 + c;
                     if (p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16) {
                         if (p.epilogue == EPI_SILU_BF16) {
 #pragma unroll
@@ -275,19 +280,21 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmP
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
-    const long long tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
+    const long long tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN) * p.splits;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, p);
     return check_launch("gemm_bf16_tn_kernel");
 }
 
 int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, long long M, int N, int K, int epilogue,
-                 cudaStream_t st) {
+                 cudaStream_t st, int splits) {
     IDB_REQUIRE(A && W && out, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(M >= 0 && N > 0 && K > 0, IDB200_EINVAL, "bad shape");
     IDB_REQUIRE(K % kBK == 0, IDB200_EUNSUPPORTED, "K must be a multiple of %d (got %d)", kBK, K);
     IDB_REQUIRE(N % 32 == 0, IDB200_EUNSUPPORTED, "N must be a multiple of 32 (got %d)", N);
     IDB_REQUIRE(epilogue >= 0 && epilogue <= 3, IDB200_EINVAL, "unknown epilogue %d", epilogue);
+    IDB_REQUIRE(splits >= 1 && (K / kBK) % splits == 0, IDB200_EINVAL, "splits (%d) must divide K / %d", splits, kBK);
+    IDB_REQUIRE(splits == 1 || (epilogue == EPI_F32 && bias == nullptr), IDB200_EINVAL, "split-K needs the fp32 epilogue without bias");
     IDB_REQUIRE(aligned(out, 16), IDB200_EALIGN, "out must be 16-byte aligned");
     if (M == 0) return IDB200_OK;
     int BN = 0;
@@ -298,7 +305,7 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint32_t>(BN), kBK);
     if (rc) return rc;
-    GemmParams p{bias, out, M, N, K, epilogue};
+    GemmParams p{bias, out, M, N, K, epilogue, splits};
     switch (BN) {
         case 256: return launch_gemm<256>(ta, tw, p, st);
         case 192: return launch_gemm<192>(ta, tw, p, st);
@@ -313,5 +320,10 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
 
 extern "C" int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K,
                                 int epilogue, idb200_stream_t stream) {
-    return idb200::gemm_bf16_tn(A, W, bias, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream));
+    return idb200::gemm_bf16_tn(A, W, bias, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream), 1);
+}
+
+extern "C" int idb200_gemm_bf16_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int K, int splits,
+                                       idb200_stream_t stream) {
+    return idb200::gemm_bf16_tn(A, W, nullptr, partial, M, N, K, IDB200_EPI_F32, static_cast<cudaStream_t>(stream), splits);
 }

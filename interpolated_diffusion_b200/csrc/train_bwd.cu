@@ -1,0 +1,722 @@
+// Backward kernels of the training steps (src/train/train_interp_levels.py:1142-1173, src/train/train_keypoints.py:505-556):
+// everything between the loss gradient (train_tail.cu) and the optimiser that is not a dense contraction.  The dense
+// contractions (dX = dY W, dW = dY^T X) run on the tcgen05 GEMM of gemm.cu: dX with the transposed weight as the
+// "W" operand, dW as a split-K GEMM over the token dimension on transposed bf16 copies made by transpose_to_bf16.
+// Reductions are two-level with a fixed order: results are deterministic run to run.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace idb200 {
+namespace tb {
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(unsigned char v) { return static_cast<float>(v); }
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fwd(float x) { return x * sigmoid_f(x); }
+__device__ __forceinline__ float silu_grad(float x) {
+    const float s = sigmoid_f(x);
+    return s * (1.0f + x * (1.0f - s));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dst[n, m] = bf16(src[m, n]): 64 x 64 tiles through shared memory, coalesced on both sides.
+template <typename TIn>
+__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const TIn* __restrict__ src, long long M, int N,
+                                                                __nv_bfloat16* __restrict__ dst) {
+    __shared__ float tile[64][65];
+    const long long m0 = static_cast<long long>(blockIdx.x) * 64;
+    const int n0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int r = ty; r < 64; r += 4) {
+        const long long m = m0 + r;
+        const int n = n0 + tx;
+        tile[r][tx] = (m < M && n < N) ? to_f(src[m * N + n]) : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 64; r += 4) {
+        const int n = n0 + r;
+        const long long m = m0 + tx;
+        if (n < N && m < M) dst[static_cast<long long>(n) * M + m] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Column sums of src[M, N] (bias gradients; LayerNorm affine gradients from per-trajectory partials).
+// Stage 1: block (32 columns, one row slice) -> partial[slice, N]; stage 2: reduce_rows.
+template <typename TIn>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const TIn* __restrict__ src, long long M, int N, long long rows_per_slice,
+                                                             float* __restrict__ partial) {
+    __shared__ float sh[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slice;
+    long long r1 = r0 + rows_per_slice;
+    if (r1 > M) r1 = M;
+    float acc = 0.0f;
+    if (c < N)
+        for (long long r = r0 + ty; r < r1; r += 8) acc += to_f(src[r * N + c]);
+    sh[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < N) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w][tx];
+        partial[static_cast<long long>(blockIdx.y) * N + c] = t;
+    }
+}
+
+// out[w] (+)= scale * sum_r partial[r, w]   (fixed order)
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partial, int R, long long W, float scale,
+                                                          int accumulate, float* __restrict__ out) {
+    const long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    float t = 0.0f;
+    for (int r = 0; r < R; ++r) t += partial[static_cast<long long>(r) * W + w];
+    t *= scale;
+    out[w] = accumulate ? out[w] + t : t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SiLU forward / backward on bf16 pairs.  mode 0: y = silu(u);  mode 1: y = g * silu'(u).
+__global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat162* __restrict__ u, const __nv_bfloat162* g, long long n2,
+                                                   int mode, __nv_bfloat162* y) {   // y may alias g
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const float2 uv = __bfloat1622float2(u[i]);
+        float2 o;
+        if (mode == 0) {
+            o = make_float2(silu_fwd(uv.x), silu_fwd(uv.y));
+        } else {
+            const float2 gv = __bfloat1622float2(g[i]);
+            o = make_float2(gv.x * silu_grad(uv.x), gv.y * silu_grad(uv.y));
+        }
+        y[i] = __floats2bfloat162_rn(o.x, o.y);
+    }
+}
+
+// fp32 variant for the per-trajectory MLPs (level_proj, sg.mlp, t_embed)
+__global__ void __launch_bounds__(256) silu_f32_kernel(const float* __restrict__ u, const float* g, long long n, int mode, float* y) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = mode == 0 ? silu_fwd(u[i]) : g[i] * silu_grad(u[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of a = LN(h) * (1 + gamma) + beta  (transformer.py:35-46: norm + FiLM), one block per trajectory.
+//   n = xhat * w + b;  dn = da * (1 + gamma);  dgamma = sum_t da * n;  dbeta = sum_t da;
+//   dw_part = sum_t dn * xhat;  db_part = sum_t dn;  dxhat = dn * w;
+//   dh += rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
+template <int kPerLane>
+__global__ void __launch_bounds__(256) ln_film_bwd_kernel(const float* __restrict__ da, const float* __restrict__ h,
+                                                          const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                          const float* __restrict__ gb, long long gb_stride, int L,
+                                                          float* __restrict__ dh, __nv_bfloat16* __restrict__ dh16,
+                                                          float* __restrict__ dgb, long long dgb_stride, float* __restrict__ dwb_part) {
+    constexpr int d = kPerLane * 32;
+    __shared__ float sh[8][d];
+    const long long b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float w[kPerLane], bb[kPerLane], g1[kPerLane];
+    float a_dg[kPerLane], a_db[kPerLane], a_dw[kPerLane], a_dbb[kPerLane];
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) {
+        const int c = lane + 32 * j;
+        w[j] = ln_w[c];
+        bb[j] = ln_b[c];
+        g1[j] = gb ? 1.0f + gb[b * gb_stride + c] : 1.0f;
+        a_dg[j] = a_db[j] = a_dw[j] = a_dbb[j] = 0.0f;
+    }
+    for (int t = warp; t < L; t += 8) {
+        const long long row = (b * L + t) * d;
+        float x[kPerLane], g[kPerLane];
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            x[j] = h[row + lane + 32 * j];
+            g[j] = da[row + lane + 32 * j];
+            s += x[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / d);
+        float v = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            x[j] -= mean;
+            v += x[j] * x[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float rstd = rsqrtf(v * (1.0f / d) + 1e-5f);
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            x[j] *= rstd;                                   // xhat
+            const float n = fmaf(x[j], w[j], bb[j]);
+            const float dn = g[j] * g1[j];
+            a_dg[j] = fmaf(g[j], n, a_dg[j]);
+            a_db[j] += g[j];
+            a_dw[j] = fmaf(dn, x[j], a_dw[j]);
+            a_dbb[j] += dn;
+            g[j] = dn * w[j];                               // dxhat
+            s1 += g[j];
+            s2 = fmaf(g[j], x[j], s2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        s1 *= (1.0f / d);
+        s2 *= (1.0f / d);
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            const long long o = row + lane + 32 * j;
+            const float v2 = dh[o] + rstd * (g[j] - s1 - x[j] * s2);
+            dh[o] = v2;
+            if (dh16) dh16[o] = __float2bfloat16_rn(v2);
+        }
+    }
+    // cross-warp sums, one quantity at a time, fixed order
+    float* outs[4] = {dgb ? dgb + b * dgb_stride : nullptr, dgb ? dgb + b * dgb_stride + d : nullptr, dwb_part + b * 2 * d,
+                      dwb_part + b * 2 * d + d};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float* acc = q == 0 ? a_dg : q == 1 ? a_db : q == 2 ? a_dw : a_dbb;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) sh[warp][lane + 32 * j] = acc[j];
+        __syncthreads();
+        if (outs[q])
+            for (int c = threadIdx.x; c < d; c += 256) {
+                float t = 0.0f;
+#pragma unroll
+                for (int wv = 0; wv < 8; ++wv) t += sh[wv][c];
+                outs[q][c] = t;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of softmax(q k^T / sqrt(32)) v for one (trajectory, head) per block (nn.MultiheadAttention inside
+// transformer.py:39, head_dim 32, L <= 64): recompute P, then dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(P o dP)),
+// dQ = dS K / sqrt(32), dK = dS^T Q / sqrt(32).  fp32 in shared memory; every product is an accumulation of outer
+// products over a reduction index r with both operands stored r-major.
+template <int kL, int kT>
+struct AttnBwdCfg {
+    static constexpr int kNb = kL / kT;                 // threads per tile edge
+    static constexpr int kThreads = kNb * kNb;
+    static constexpr int kC = 32 * kT / kL;             // columns per thread for the [kL, 32] outputs
+    // shared floats: Qt Kt Vt dOt [32][kL], Q K dO [kL][32], P [kL][kL], dSt [kL][kL]
+    static constexpr int kSmemFloats = 4 * 32 * kL + 3 * kL * 32 + 2 * kL * kL;
+};
+
+// C[a0 + i][b0 + j] += sum_r A[r][a0 + i] * B[r][b0 + j]
+template <int kI, int kJ>
+__device__ __forceinline__ void outer_acc(const float* __restrict__ A, int pa, const float* __restrict__ B, int pb, int R, int a0, int b0,
+                                          float (&acc)[kI][kJ]) {
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+        float av[kI], bv[kJ];
+        if constexpr (kI == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(A + r * pa + a0);
+            av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+        } else if constexpr (kI == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(A + r * pa + a0);
+            av[0] = t.x; av[1] = t.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kI; ++i) av[i] = A[r * pa + a0 + i];
+        }
+        if constexpr (kJ == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(B + r * pb + b0);
+            bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+        } else if constexpr (kJ == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(B + r * pb + b0);
+            bv[0] = t.x; bv[1] = t.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kJ; ++j) bv[j] = B[r * pb + b0 + j];
+        }
+#pragma unroll
+        for (int i = 0; i < kI; ++i)
+#pragma unroll
+            for (int j = 0; j < kJ; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+
+template <int kL, int kT>
+__global__ void __launch_bounds__(AttnBwdCfg<kL, kT>::kThreads) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                                     const __nv_bfloat16* __restrict__ dO,
+                                                                                     __nv_bfloat16* __restrict__ dqkv, int L, int H, int causal) {
+    using Cfg = AttnBwdCfg<kL, kT>;
+    constexpr int kNb = Cfg::kNb, kThreads = Cfg::kThreads, kC = Cfg::kC;
+    extern __shared__ __align__(16) float sm[];
+    float* Qt = sm;                      // [32][kL]
+    float* Kt = Qt + 32 * kL;
+    float* Vt = Kt + 32 * kL;
+    float* dOt = Vt + 32 * kL;
+    float* Q = dOt + 32 * kL;            // [kL][32]
+    float* K = Q + kL * 32;
+    float* dOr = K + kL * 32;
+    float* P = dOr + kL * 32;            // [kL][kL]  (P, then dS)
+    float* dSt = P + kL * kL;            // [kL][kL]  dS transposed
+    const int d = H * 32;
+    const long long b = blockIdx.x / H;
+    const int hh = blockIdx.x % H;
+    const int t = threadIdx.x;
+    const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
+
+    // load q, k, v, dO of this head: thread -> (row r fastest, bf16 pair kp)
+    for (int e = t; e < kL * 16; e += kThreads) {
+        const int r = e % kL, kp = e / kL;
+        float2 q = make_float2(0.f, 0.f), k = q, v = q, g = q;
+        if (r < L) {
+            const long long row = b * L + r;
+            const __nv_bfloat16* base = qkv + row * 3 * d + hh * 32 + 2 * kp;
+            q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base));
+            k = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + d));
+            v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + 2 * d));
+            g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + row * d + hh * 32 + 2 * kp));
+        }
+        Qt[(2 * kp) * kL + r] = q.x;  Qt[(2 * kp + 1) * kL + r] = q.y;
+        Kt[(2 * kp) * kL + r] = k.x;  Kt[(2 * kp + 1) * kL + r] = k.y;
+        Vt[(2 * kp) * kL + r] = v.x;  Vt[(2 * kp + 1) * kL + r] = v.y;
+        dOt[(2 * kp) * kL + r] = g.x; dOt[(2 * kp + 1) * kL + r] = g.y;
+        Q[r * 32 + 2 * kp] = q.x;     Q[r * 32 + 2 * kp + 1] = q.y;
+        K[r * 32 + 2 * kp] = k.x;     K[r * 32 + 2 * kp + 1] = k.y;
+        dOr[r * 32 + 2 * kp] = g.x;   dOr[r * 32 + 2 * kp + 1] = g.y;
+    }
+    __syncthreads();
+
+    const int ti = t / kNb, tj = t % kNb;
+    const int i0 = ti * kT, j0 = tj * kT;
+    // S = scale * Q K^T
+    {
+        float acc[kT][kT];
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+#pragma unroll
+            for (int j = 0; j < kT; ++j) acc[i][j] = 0.0f;
+        outer_acc<kT, kT>(Qt, kL, Kt, kL, 32, i0, j0, acc);
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+#pragma unroll
+            for (int j = 0; j < kT; ++j) P[(i0 + i) * kL + j0 + j] = acc[i][j] * scale;
+    }
+    __syncthreads();
+    // row softmax (one warp per row; kL <= 64: two entries per lane)
+    for (int i = t >> 5; i < kL; i += kThreads / 32) {
+        const int lane = t & 31;
+        float v0 = -INFINITY, v1 = -INFINITY;
+        const int jmax = causal ? (i + 1 < L ? i + 1 : L) : L;
+        if (lane < jmax) v0 = P[i * kL + lane];
+        if (kL > 32 && lane + 32 < jmax) v1 = P[i * kL + lane + 32];
+        float m = fmaxf(v0, v1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const bool live = i < L;
+        const float e0 = (live && lane < jmax) ? __expf(v0 - m) : 0.0f;
+        const float e1 = (live && kL > 32 && lane + 32 < jmax) ? __expf(v1 - m) : 0.0f;
+        float s = e0 + e1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float inv = live ? 1.0f / s : 0.0f;
+        if (lane < kL) P[i * kL + lane] = e0 * inv;
+        if (kL > 32) P[i * kL + lane + 32] = e1 * inv;
+    }
+    __syncthreads();
+
+    const int ra = (t / (32 / kC)) * kT;          // rows of the [kL, 32] outputs owned by this thread
+    const int cb = (t % (32 / kC)) * kC;          // columns
+    // dV[j][k] = sum_i P[i][j] dO[i][k]
+    {
+        float acc[kT][kC];
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+#pragma unroll
+            for (int j = 0; j < kC; ++j) acc[i][j] = 0.0f;
+        outer_acc<kT, kC>(P, kL, dOr, 32, kL, ra, cb, acc);
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+            if (ra + i < L)
+#pragma unroll
+                for (int j = 0; j < kC; ++j)
+                    dqkv[(b * L + ra + i) * 3 * d + 2 * d + hh * 32 + cb + j] = __float2bfloat16_rn(acc[i][j]);
+    }
+    // dP = dO V^T ; dS = P o (dP - delta)
+    {
+        float acc[kT][kT];
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+#pragma unroll
+            for (int j = 0; j < kT; ++j) acc[i][j] = 0.0f;
+        outer_acc<kT, kT>(dOt, kL, Vt, kL, 32, i0, j0, acc);
+        float pv[kT][kT];
+#pragma unroll
+        for (int i = 0; i < kT; ++i) {
+            float part = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kT; ++j) {
+                pv[i][j] = P[(i0 + i) * kL + j0 + j];
+                part = fmaf(pv[i][j], acc[i][j], part);
+            }
+            // the kNb threads of one row group are consecutive lanes
+#pragma unroll
+            for (int o = kNb / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+#pragma unroll
+            for (int j = 0; j < kT; ++j) acc[i][j] = pv[i][j] * (acc[i][j] - part) * scale;      // scale folded into dS
+        }
+        __syncthreads();                          // every thread has finished reading P (dV product above)
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+#pragma unroll
+            for (int j = 0; j < kT; ++j) {
+                P[(i0 + i) * kL + j0 + j] = acc[i][j];
+                dSt[(j0 + j) * kL + i0 + i] = acc[i][j];
+            }
+    }
+    __syncthreads();
+    // dQ[i][k] = sum_j dS[i][j] K[j][k]   (A = dSt: r = j, contiguous in i)
+    {
+        float acc[kT][kC];
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+#pragma unroll
+            for (int j = 0; j < kC; ++j) acc[i][j] = 0.0f;
+        outer_acc<kT, kC>(dSt, kL, K, 32, kL, ra, cb, acc);
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+            if (ra + i < L)
+#pragma unroll
+                for (int j = 0; j < kC; ++j) dqkv[(b * L + ra + i) * 3 * d + hh * 32 + cb + j] = __float2bfloat16_rn(acc[i][j]);
+    }
+    // dK[j][k] = sum_i dS[i][j] Q[i][k]   (A = dS: r = i, contiguous in j)
+    {
+        float acc[kT][kC];
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+#pragma unroll
+            for (int j = 0; j < kC; ++j) acc[i][j] = 0.0f;
+        outer_acc<kT, kC>(P, kL, Q, 32, kL, ra, cb, acc);
+#pragma unroll
+        for (int i = 0; i < kT; ++i)
+            if (ra + i < L)
+#pragma unroll
+                for (int j = 0; j < kC; ++j) dqkv[(b * L + ra + i) * 3 * d + d + hh * 32 + cb + j] = __float2bfloat16_rn(acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Out head backward (denoiser out = Linear(d, D), D <= 4): dh[m, :] = sum_j dy[m, j] W[j, :]  (fp32 + bf16 copies)
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ W, long long M, int d, int D,
+                                                       float* __restrict__ dh, __nv_bfloat16* __restrict__ dh16) {
+    const long long n = M * d;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long m = i / d;
+        const int c = static_cast<int>(i - m * d);
+        float v = 0.0f;
+        for (int j = 0; j < D; ++j) v = fmaf(dy[m * D + j], W[j * d + c], v);
+        dh[i] = v;
+        if (dh16) dh16[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// partial[slice][j][c] = sum over the slice's rows of A[m, j] * X[m, c]   (n <= 8 narrow columns of A)
+// out head:  A = dy [M, D], X = h_final  -> dW_out [D, d];  in_proj:  A = features [M, D + C], X = dh0 -> dWf [D + C, d]
+__global__ void __launch_bounds__(128) narrow_outer_partial_kernel(const float* __restrict__ A, int n, const float* __restrict__ X, long long M,
+                                                                   int K, long long rows_per_slice, float* __restrict__ partial) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slice;
+    long long r1 = r0 + rows_per_slice;
+    if (r1 > M) r1 = M;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    if (c < K) {
+        for (long long m = r0; m < r1; ++m) {
+            const float x = X[m * K + c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < n) acc[j] = fmaf(A[m * n + j], x, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < n) partial[(static_cast<long long>(blockIdx.y) * n + j) * K + c] = acc[j];
+    }
+}
+
+// out[b, c] = sum_t src[b, t, c]   (gradient of the per-trajectory rows added to every token: level vector, cond row)
+__global__ void __launch_bounds__(128) token_sum_kernel(const float* __restrict__ src, int L, int d, float* __restrict__ out) {
+    const long long b = blockIdx.x;
+    for (int c = threadIdx.x; c < d; c += 128) {
+        float t = 0.0f;
+        for (int l = 0; l < L; ++l) t += src[(b * L + l) * d + c];
+        out[b * d + c] = t;
+    }
+}
+
+// out[i, j] (+)= sum_k A[i * sa0 + k * sa1] * B[j * sb0 + k * sb1]: strided fp32 GEMM for the per-trajectory linears'
+// backward (level_proj, cond_proj, maze.fc, sg.mlp, t_embed: M = batch, all dims <= 512)
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, long long sa0, long long sa1, const float* __restrict__ B,
+                                                            long long sb0, long long sb1, float* __restrict__ out, long long ldo, int M, int N,
+                                                            int K, int accumulate) {
+    __shared__ float As[16][17], Bs[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+    float acc = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        const int ia = blockIdx.y * 16 + ty, ka = k0 + tx;
+        As[ty][tx] = (ia < M && ka < K) ? A[ia * sa0 + ka * sa1] : 0.0f;
+        const int jb = blockIdx.x * 16 + ty;
+        Bs[ty][tx] = (jb < N && ka < K) ? B[jb * sb0 + ka * sb1] : 0.0f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc = fmaf(As[ty][k], Bs[tx][k], acc);
+        __syncthreads();
+    }
+    if (i < M && j < N) out[i * ldo + j] = accumulate ? out[i * ldo + j] + acc : acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Conv encoder pieces (encoders.py:8-25): activations NHWC bf16 [B, H*W, C] holding the PRE-activation u of each layer.
+// col[b*P + p, (ky*3 + kx)*C + c] = act(src[b, (y+ky-1, x+kx-1), c]) (zero outside the plane, zero in the K padding)
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ src, long long B, int Hh, int Ww, int C, int Kpad,
+                                                        int act, __nv_bfloat16* __restrict__ col) {
+    const int P = Hh * Ww;
+    const long long total = B * P * static_cast<long long>(Kpad);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int kk = static_cast<int>(i % Kpad);
+        const long long bp = i / Kpad;
+        float v = 0.0f;
+        if (kk < 9 * C) {
+            const int tap = kk / C, c = kk - tap * C;
+            const int p = static_cast<int>(bp % P);
+            const long long b = bp / P;
+            const int y = p / Ww + tap / 3 - 1, x = p % Ww + tap % 3 - 1;
+            if (y >= 0 && y < Hh && x >= 0 && x < Ww) {
+                v = __bfloat162float(src[(b * P + y * Ww + x) * C + c]);
+                if (act) v = silu_fwd(v);
+            }
+        }
+        col[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// pooled[b, c] = mean_p silu(u[b, p, c])
+__global__ void __launch_bounds__(128) pool_silu_kernel(const __nv_bfloat16* __restrict__ u, int P, int C, float* __restrict__ pooled) {
+    const long long b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += 128) {
+        float t = 0.0f;
+        for (int p = 0; p < P; ++p) t += silu_fwd(__bfloat162float(u[(b * P + p) * C + c]));
+        pooled[b * C + c] = t / static_cast<float>(P);
+    }
+}
+
+// du[b, p, c] = dpooled[b, c] / P * silu'(u[b, p, c])
+__global__ void __launch_bounds__(256) pool_silu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const float* __restrict__ dpooled, long long B,
+                                                            int P, int C, __nv_bfloat16* __restrict__ du) {
+    const long long total = B * P * static_cast<long long>(C);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const float invP = 1.0f / static_cast<float>(P);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = static_cast<int>(i % C);
+        const long long b = i / (static_cast<long long>(P) * C);
+        du[i] = __float2bfloat16_rn(dpooled[b * C + c] * invP * silu_grad(__bfloat162float(u[i])));
+    }
+}
+
+template <int kL, int kT>
+int launch_attn_bwd(const void* qkv, const void* dO, void* dqkv, long long B, int L, int H, int causal, cudaStream_t st) {
+    using Cfg = AttnBwdCfg<kL, kT>;
+    constexpr int smem = Cfg::kSmemFloats * 4;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<kL, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    attention_bwd_kernel<kL, kT><<<static_cast<unsigned>(B * H), Cfg::kThreads, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dO), static_cast<__nv_bfloat16*>(dqkv), L, H, causal);
+    return check_launch("attention_bwd_kernel");
+}
+
+inline int slices_for(long long M, int col_blocks) {
+    long long s = (148 * 8 + col_blocks - 1) / col_blocks;
+    const long long max_s = (M + 63) / 64;
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    if (s > 1024) s = 1024;
+    return static_cast<int>(s);
+}
+
+}  // namespace tb
+}  // namespace idb200
+
+using namespace idb200;
+
+extern "C" int idb200_transpose_bf16(const void* src, int src_is_f32, int64_t M, int N, void* dst, idb200_stream_t stream) {
+    IDB_REQUIRE(src && dst, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(M >= 0 && N > 0, IDB200_EINVAL, "bad shape");
+    if (M == 0) return IDB200_OK;
+    const dim3 grid(static_cast<unsigned>((M + 63) / 64), static_cast<unsigned>((N + 63) / 64));
+    if (src_is_f32)
+        tb::transpose_to_bf16_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(src), M, N,
+                                                                                                   static_cast<__nv_bfloat16*>(dst));
+    else
+        tb::transpose_to_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(src), M, N, static_cast<__nv_bfloat16*>(dst));
+    return check_launch("transpose_to_bf16_kernel");
+}
+
+extern "C" int idb200_colsum_scratch_floats(int64_t M, int N) {
+    return tb::slices_for(M, (N + 31) / 32) * N;
+}
+
+extern "C" int idb200_colsum(const void* src, int src_kind, int64_t M, int N, float* scratch, float scale, int accumulate, float* out,
+                             idb200_stream_t stream) {
+    IDB_REQUIRE(src && out && scratch, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(M > 0 && N > 0, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(src_kind >= 0 && src_kind <= 1, IDB200_EINVAL, "src_kind: 0 fp32, 1 bf16");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cb = (N + 31) / 32;
+    const int S = tb::slices_for(M, cb);
+    const long long rps = (M + S - 1) / S;
+    const dim3 grid(cb, S);
+    if (src_kind == 0)
+        tb::colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), M, N, rps, scratch);
+    else
+        tb::colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), M, N, rps, scratch);
+    int rc = check_launch("colsum_partial_kernel");
+    if (rc) return rc;
+    tb::reduce_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, S, N, scale, accumulate, out);
+    return check_launch("reduce_rows_kernel");
+}
+
+extern "C" int idb200_reduce_rows(const float* partial, int R, int64_t W, float scale, int accumulate, float* out, idb200_stream_t stream) {
+    IDB_REQUIRE(partial && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(R > 0 && W > 0, IDB200_EINVAL, "bad shape");
+    tb::reduce_rows_kernel<<<static_cast<unsigned>((W + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, R, W, scale,
+                                                                                                                  accumulate, out);
+    return check_launch("reduce_rows_kernel");
+}
+
+extern "C" int idb200_silu_bf16(const void* u, const void* g, int64_t n, int mode, void* y, idb200_stream_t stream) {
+    IDB_REQUIRE(u && y && (mode == 0 || g), IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(n >= 0 && n % 2 == 0, IDB200_EINVAL, "element count must be even");
+    IDB_REQUIRE(mode == 0 || mode == 1, IDB200_EINVAL, "mode: 0 forward, 1 backward");
+    if (n == 0) return IDB200_OK;
+    tb::silu_kernel<<<grid_for(n / 2, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat162*>(u), static_cast<const __nv_bfloat162*>(g), n / 2, mode, static_cast<__nv_bfloat162*>(y));
+    return check_launch("silu_kernel");
+}
+
+extern "C" int idb200_silu_f32(const float* u, const float* g, int64_t n, int mode, float* y, idb200_stream_t stream) {
+    IDB_REQUIRE(u && y && (mode == 0 || g), IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(n >= 0 && (mode == 0 || mode == 1), IDB200_EINVAL, "bad arguments");
+    if (n == 0) return IDB200_OK;
+    tb::silu_f32_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(u, g, n, mode, y);
+    return check_launch("silu_f32_kernel");
+}
+
+extern "C" int idb200_ln_film_bwd(const float* da, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
+                                  int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb, int64_t dgb_stride,
+                                  float* dwb_part, idb200_stream_t stream) {
+    IDB_REQUIRE(da && h && ln_w && ln_b && dh && dwb_part, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE((gamma_beta == nullptr) == (dgb == nullptr), IDB200_EINVAL, "gamma_beta and dgb must be given together");
+    IDB_REQUIRE(B > 0 && L > 0, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(d == 256 || d == 384 || d == 128 || d == 512, IDB200_EUNSUPPORTED, "d_model must be 128, 256, 384 or 512 (got %d)", d);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* d16 = static_cast<__nv_bfloat16*>(dh_bf16);
+    const unsigned grid = static_cast<unsigned>(B);
+    switch (d / 32) {
+        case 4: tb::ln_film_bwd_kernel<4><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;
+        case 8: tb::ln_film_bwd_kernel<8><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;
+        case 12: tb::ln_film_bwd_kernel<12><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;
+        default: tb::ln_film_bwd_kernel<16><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;
+    }
+    return check_launch("ln_film_bwd_kernel");
+}
+
+extern "C" int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, idb200_stream_t stream) {
+    IDB_REQUIRE(qkv && dO && dqkv, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B > 0 && H > 0, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(L >= 1 && L <= 64, IDB200_EUNSUPPORTED, "attention backward supports L <= 64 (got %d)", L);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (L <= 8) return tb::launch_attn_bwd<8, 1>(qkv, dO, dqkv, B, L, H, causal, st);
+    if (L <= 16) return tb::launch_attn_bwd<16, 1>(qkv, dO, dqkv, B, L, H, causal, st);
+    if (L <= 32) return tb::launch_attn_bwd<32, 2>(qkv, dO, dqkv, B, L, H, causal, st);
+    return tb::launch_attn_bwd<64, 4>(qkv, dO, dqkv, B, L, H, causal, st);
+}
+
+extern "C" int idb200_head_bwd(const float* dy, const float* W, int64_t M, int d, int D, float* dh, void* dh_bf16, idb200_stream_t stream) {
+    IDB_REQUIRE(dy && W && dh, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(M > 0 && d > 0 && D > 0 && D <= 8, IDB200_EINVAL, "bad shape");
+    tb::head_bwd_kernel<<<grid_for(M * d, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, W, M, d, D, dh,
+                                                                                                    static_cast<__nv_bfloat16*>(dh_bf16));
+    return check_launch("head_bwd_kernel");
+}
+
+extern "C" int idb200_narrow_outer_scratch_floats(int64_t M, int n, int K) {
+    return tb::slices_for(M, (K + 127) / 128) * n * K;
+}
+
+extern "C" int idb200_narrow_outer(const float* A, int n, const float* X, int64_t M, int K, float* scratch, int accumulate, float* out,
+                                   idb200_stream_t stream) {
+    IDB_REQUIRE(A && X && scratch && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(M > 0 && K > 0 && n >= 1 && n <= 8, IDB200_EINVAL, "bad shape (n must be 1..8)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cb = (K + 127) / 128;
+    const int S = tb::slices_for(M, cb);
+    const long long rps = (M + S - 1) / S;
+    tb::narrow_outer_partial_kernel<<<dim3(cb, S), 128, 0, st>>>(A, n, X, M, K, rps, scratch);
+    int rc = check_launch("narrow_outer_partial_kernel");
+    if (rc) return rc;
+    const long long W = static_cast<long long>(n) * K;
+    tb::reduce_rows_kernel<<<static_cast<unsigned>((W + 255) / 256), 256, 0, st>>>(scratch, S, W, 1.0f, accumulate, out);
+    return check_launch("reduce_rows_kernel");
+}
+
+extern "C" int idb200_token_sum(const float* src, int64_t B, int L, int d, float* out, idb200_stream_t stream) {
+    IDB_REQUIRE(src && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B > 0 && L > 0 && d > 0, IDB200_EINVAL, "bad shape");
+    tb::token_sum_kernel<<<static_cast<unsigned>(B), 128, 0, static_cast<cudaStream_t>(stream)>>>(src, L, d, out);
+    return check_launch("token_sum_kernel");
+}
+
+extern "C" int idb200_sgemm_strided(const float* A, int64_t sa0, int64_t sa1, const float* Bm, int64_t sb0, int64_t sb1, float* out,
+                                    int64_t ldo, int M, int N, int K, int accumulate, idb200_stream_t stream) {
+    IDB_REQUIRE(A && Bm && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(M > 0 && N > 0 && K > 0, IDB200_EINVAL, "bad shape");
+    tb::sgemm_strided_kernel<<<dim3((N + 15) / 16, (M + 15) / 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sa0, sa1, Bm, sb0, sb1, out,
+                                                                                                               ldo, M, N, K, accumulate);
+    return check_launch("sgemm_strided_kernel");
+}
+
+extern "C" int idb200_im2col3x3(const void* src, int64_t B, int H, int W, int C, int Kpad, int act, void* col, idb200_stream_t stream) {
+    IDB_REQUIRE(src && col, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Kpad >= 9 * C, IDB200_EINVAL, "bad shape");
+    tb::im2col3x3_kernel<<<grid_for(B * H * W * Kpad, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src), B, H, W, C, Kpad, act, static_cast<__nv_bfloat16*>(col));
+    return check_launch("im2col3x3_kernel");
+}
+
+extern "C" int idb200_pool_silu(const void* u, int64_t B, int P, int C, float* pooled, idb200_stream_t stream) {
+    IDB_REQUIRE(u && pooled, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B > 0 && P > 0 && C > 0, IDB200_EINVAL, "bad shape");
+    tb::pool_silu_kernel<<<static_cast<unsigned>(B), 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(u), P, C, pooled);
+    return check_launch("pool_silu_kernel");
+}
+
+extern "C" int idb200_pool_silu_bwd(const void* u, const float* dpooled, int64_t B, int P, int C, void* du, idb200_stream_t stream) {
+    IDB_REQUIRE(u && dpooled && du, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B > 0 && P > 0 && C > 0, IDB200_EINVAL, "bad shape");
+    tb::pool_silu_bwd_kernel<<<grid_for(B * P * C, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(u), dpooled, B, P, C, static_cast<__nv_bfloat16*>(du));
+    return check_launch("pool_silu_bwd_kernel");
+}

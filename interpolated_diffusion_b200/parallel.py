@@ -1,7 +1,9 @@
 """Trajectory-batch sharding across the GPUs of one box (one process per GPU).
 
 The generation path is row-independent (no cross-sample statistic: LayerNorm is per token), so the batch is split into
-contiguous per-rank ranges with no data-path collective; the only exchange is the final all-gather of the samples."""
+contiguous per-rank ranges with no data-path collective; the only exchange is the final all-gather of the samples.
+The training step adds the one real exchange of that path: the data-parallel all-reduce of the flat fp32
+gradient arena."""
 from __future__ import annotations
 
 from typing import Tuple
@@ -43,3 +45,23 @@ def gather_samples(x_local: torch.Tensor, total: int | None = None) -> torch.Ten
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad)
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def all_reduce_sum_(flat: torch.Tensor, group=None, bucket_elems: int = 0) -> torch.Tensor:
+    """In-place sum over ranks of a flat gradient arena (no-op for one process).  Each rank's gradient already carries the
+    1 / world factor (it rides on the loss kernel), so the sum IS the data-parallel mean.  ``bucket_elems`` > 0 issues the
+    reduction as async buckets of that many elements (launch-latency sized, not link sized: NVSwitch reduces in the fabric)."""
+    if world_size(group) == 1:
+        return flat
+    if bucket_elems <= 0 or bucket_elems >= flat.numel():
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return flat
+    works = [dist.all_reduce(flat[o:o + bucket_elems], op=dist.ReduceOp.SUM, group=group, async_op=True)
+             for o in range(0, flat.numel(), bucket_elems)]
+    for w in works:
+        w.wait()
+    return flat

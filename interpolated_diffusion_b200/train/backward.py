@@ -1,0 +1,456 @@
+"""Training-form forward and hand-written backward of the Stage-2 denoiser on libidb200 kernels: what
+``loss.backward()`` computes in ``src/train/train_interp_levels.py:1142-1161`` for ``InterpLevelDenoiser``
+(``src/models/denoiser_interp_levels.py:64-84``, ``transformer.py:28-46``, ``encoders.py:8-71``) under bf16 autocast.
+
+Forward keeps what the backward needs (per layer: the residual stream before each LayerNorm in fp32; LN+FiLM outputs, packed
+qkv, attention output, MLP pre-activation and activation in bf16).  Backward walks the layers in reverse:
+
+* dense contractions on the tcgen05 GEMM: ``dX = dY W`` (transposed weight as the weight operand), ``dW = dY^T X`` (split-K over
+  the tokens on bf16 transposes, partials reduced in a fixed order);
+* everything else in ``csrc/train_bwd.cu``: LayerNorm+FiLM backward (one block per trajectory), attention backward (one block
+  per trajectory x head), SiLU', bias / LayerNorm-affine column sums, out-head and in_proj gradients, the conv stack as
+  im2col + GEMM (dgrad = the same conv with flipped weights).
+
+PyTorch owns memory and reshapes (weight transposes / packing, one-hot level rows); no arithmetic of the step runs in torch.
+Gradients are written into caller-provided fp32 tensors keyed by the reference's parameter names (``grads[name]``)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _lib as L
+from ..models import _engine as E
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# thin wrappers
+def transpose_bf16(src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    M, N = src.shape
+    L.call("idb200_transpose_bf16", src.data_ptr(), int(src.dtype == F32), M, N, out.data_ptr(), L.stream(src.device))
+    return out
+
+
+def silu_bf16(u: torch.Tensor, out: torch.Tensor, g: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L.call("idb200_silu_bf16", u.data_ptr(), L.ptr(g), u.numel(), 0 if g is None else 1, out.data_ptr(), L.stream(u.device))
+    return out
+
+
+def silu_f32(u: torch.Tensor, g: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out = torch.empty_like(u)
+    L.call("idb200_silu_f32", u.data_ptr(), L.ptr(g), u.numel(), 0 if g is None else 1, out.data_ptr(), L.stream(u.device))
+    return out
+
+
+def sgemm_strided(A: torch.Tensor, a_t: bool, Bm: torch.Tensor, b_t: bool, out: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    """out[i, j] (+)= sum_k A'[i, k] * B'[j, k] with A' = A^T if a_t, B' = B^T if b_t (A, B contiguous 2-D fp32)."""
+    sa = (1, A.shape[1]) if a_t else (A.shape[1], 1)
+    sb = (1, Bm.shape[1]) if b_t else (Bm.shape[1], 1)
+    M, K = (A.shape[1], A.shape[0]) if a_t else A.shape
+    N = Bm.shape[1] if b_t else Bm.shape[0]
+    assert (Bm.shape[0] if b_t else Bm.shape[1]) == K and out.shape == (M, N) and out.is_contiguous()
+    L.call("idb200_sgemm_strided", A.data_ptr(), sa[0], sa[1], Bm.data_ptr(), sb[0], sb[1], out.data_ptr(), N, M, N, K,
+           int(accumulate), L.stream(A.device))
+    return out
+
+
+class _Scratch:
+    """Workspaces shared by the backward helpers."""
+
+    def __init__(self):
+        self.ws = E.Workspace()
+
+    def colsum(self, src: torch.Tensor, out: torch.Tensor, scale: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+        M, N = src.shape
+        n = L.lib().idb200_colsum_scratch_floats(M, N)
+        sc = self.ws.get("colsum", (n,), F32, src.device)
+        L.call("idb200_colsum", src.data_ptr(), int(src.dtype == BF16), M, N, sc.data_ptr(), float(scale), int(accumulate),
+               out.data_ptr(), L.stream(src.device))
+        return out
+
+    def narrow_outer(self, A: torch.Tensor, X: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """out[n, K] = A[M, n]^T X[M, K] (n <= 8)."""
+        M, n = A.shape
+        K = X.shape[1]
+        cnt = L.lib().idb200_narrow_outer_scratch_floats(M, n, K)
+        sc = self.ws.get("narrow", (cnt,), F32, A.device)
+        L.call("idb200_narrow_outer", A.data_ptr(), n, X.data_ptr(), M, K, sc.data_ptr(), 0, out.data_ptr(), L.stream(A.device))
+        return out
+
+    def dweight(self, dy_t: torch.Tensor, x_t: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """out[N_out, K_in] = dY^T X from the bf16 transposes dy_t [N_out, M], x_t [K_in, M]: split-K tcgen05 GEMM over the M
+        tokens, partial products reduced in a fixed order."""
+        n_out, m_tok = dy_t.shape
+        k_in = x_t.shape[0]
+        if m_tok % 64 != 0:
+            raise ValueError(f"the weight-gradient GEMM reduces over the tokens in blocks of 64 (got {m_tok} rows)")
+        kb = m_tok // 64
+        bn = next(c for c in (256, 192, 128, 96, 64, 32) if k_in % c == 0)
+        tiles = ((n_out + 127) // 128) * (k_in // bn)
+        want = max(1, min(32, 296 // tiles))
+        splits = max(s for s in range(1, want + 1) if kb % s == 0)
+        part = self.ws.get("splitk", (splits, n_out, k_in), F32, dy_t.device)
+        L.call("idb200_gemm_bf16_splitk", dy_t.data_ptr(), x_t.data_ptr(), part.data_ptr(), n_out, k_in, m_tok, splits,
+               L.stream(dy_t.device))
+        L.call("idb200_reduce_rows", part.data_ptr(), splits, n_out * k_in, 1.0, 0, out.data_ptr(), L.stream(dy_t.device))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class EncoderBackprop:
+    """``TransformerEncoder`` (transformer.py:49-82) in training form."""
+
+    def __init__(self, encoder, scratch: Optional[_Scratch] = None):
+        self.enc = encoder
+        self.sc = scratch or _Scratch()
+        self.saved = None
+
+    def _weights(self):
+        out = []
+        for l in self.enc.layers:
+            f = lambda t: t.detach().float().contiguous()
+            w = {"wqkv": f(l.attn.in_proj_weight), "bqkv": f(l.attn.in_proj_bias), "wo": f(l.attn.out_proj.weight), "bo": f(l.attn.out_proj.bias),
+                 "w1": f(l.ff[0].weight), "b1": f(l.ff[0].bias), "w2": f(l.ff[2].weight), "b2": f(l.ff[2].bias),
+                 "n1w": f(l.norm1.weight), "n1b": f(l.norm1.bias), "n2w": f(l.norm2.weight), "n2b": f(l.norm2.bias)}
+            for k in ("wqkv", "wo", "w1", "w2"):
+                w[k + "16"] = w[k].to(BF16)
+                w[k + "t16"] = w[k].t().contiguous().to(BF16)
+            out.append(w)
+        return out
+
+    def forward(self, h: torch.Tensor, B: int, Lseq: int, cond_vec: Optional[torch.Tensor]) -> torch.Tensor:
+        """In place on the fp32 residual stream h [B*L, d]; keeps the activations the backward needs."""
+        M, d = h.shape
+        dev = h.device
+        layers = self.enc.layers
+        nl, H, ff = len(layers), layers[0].attn.num_heads, layers[0].ff[0].weight.shape[0]
+        W = self._weights()
+        film = film_w = None
+        if layers[0].film1 is not None and cond_vec is not None:
+            film_w = torch.cat([m.weight.detach().float() for l in layers for m in (l.film1, l.film2)], dim=0).contiguous()
+            film_b = torch.cat([m.bias.detach().float() for l in layers for m in (l.film1, l.film2)], dim=0).contiguous()
+            film = torch.empty((B, 2 * nl, 2 * d), device=dev, dtype=F32)
+            if cond_vec.shape[1] % 64 == 0:
+                E.gemm_bf16(cond_vec.to(BF16).contiguous(), film_w.to(BF16), film_b, film.view(B, -1), E.EPI_F32)
+            else:
+                E.sgemm(cond_vec, film_w, film_b, film.view(B, -1))
+        sv = {"h_in": torch.empty((nl, M, d), device=dev, dtype=F32), "h_mid": torch.empty((nl, M, d), device=dev, dtype=F32),
+              "a1": torch.empty((nl, M, d), device=dev, dtype=BF16), "qkv": torch.empty((nl, M, 3 * d), device=dev, dtype=BF16),
+              "o": torch.empty((nl, M, d), device=dev, dtype=BF16), "a2": torch.empty((nl, M, d), device=dev, dtype=BF16),
+              "u": torch.empty((nl, M, ff), device=dev, dtype=BF16), "f": torch.empty((nl, M, ff), device=dev, dtype=BF16)}
+        causal = bool(self.enc.causal)
+        for i, w in enumerate(W):
+            g1 = film[:, 2 * i] if film is not None else None
+            g2 = film[:, 2 * i + 1] if film is not None else None
+            sv["h_in"][i].copy_(h)
+            E.ln_film(h, w["n1w"], w["n1b"], g1, sv["a1"][i], Lseq)
+            E.gemm_bf16(sv["a1"][i], w["wqkv16"], w["bqkv"], sv["qkv"][i], E.EPI_BF16)
+            E.attention(sv["qkv"][i], sv["o"][i], B, Lseq, H, causal)
+            E.gemm_bf16(sv["o"][i], w["wo16"], w["bo"], h, E.EPI_RESID_F32)
+            sv["h_mid"][i].copy_(h)
+            E.ln_film(h, w["n2w"], w["n2b"], g2, sv["a2"][i], Lseq)
+            E.gemm_bf16(sv["a2"][i], w["w116"], w["b1"], sv["u"][i], E.EPI_BF16)
+            silu_bf16(sv["u"][i], sv["f"][i])
+            E.gemm_bf16(sv["f"][i], w["w216"], w["b2"], h, E.EPI_RESID_F32)
+        self.saved = {"sv": sv, "W": W, "film": film, "film_w": film_w, "cond_vec": cond_vec, "B": B, "L": Lseq, "H": H, "ff": ff,
+                      "causal": causal}
+        return h
+
+    def backward(self, dh: torch.Tensor, dh16: torch.Tensor, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> Optional[torch.Tensor]:
+        """dh [M, d] fp32 (in/out: gradient w.r.t. the encoder output -> w.r.t. its input), dh16 its bf16 copy (kept in sync).
+        Writes the parameter gradients into ``grads`` and returns d loss / d cond_vec [B, d_cond] (None without FiLM)."""
+        S = self.saved
+        sv, W, film = S["sv"], S["W"], S["film"]
+        B, Lseq, H, ff, causal = S["B"], S["L"], S["H"], S["ff"], S["causal"]
+        M, d = dh.shape
+        dev = dh.device
+        nl = len(W)
+        sc, ws = self.sc, self.sc.ws
+        t_a = ws.get("t_a", (max(3 * d, ff), M), BF16, dev)
+        t_b = ws.get("t_b", (max(3 * d, ff), M), BF16, dev)
+        da = ws.get("da", (M, d), F32, dev)
+        do16 = ws.get("do16", (M, d), BF16, dev)
+        dwb = ws.get("dwb", (B, 2 * d), F32, dev)
+        dwb_sum = ws.get("dwb_sum", (2 * d,), F32, dev)
+        dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
+        st = L.stream(dev)
+
+        def ln_bwd(h_saved, nw, nb, j, name):
+            gb = film[:, j] if film is not None else None
+            dg = dgb[:, j] if film is not None else None
+            L.call("idb200_ln_film_bwd", da.data_ptr(), h_saved.data_ptr(), nw.data_ptr(), nb.data_ptr(), L.ptr(gb),
+                   0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), dh16.data_ptr(), L.ptr(dg),
+                   0 if dg is None else dg.stride(0), dwb.data_ptr(), st)
+            sc.colsum(dwb, dwb_sum)
+            grads[name + ".weight"].copy_(dwb_sum[:d])
+            grads[name + ".bias"].copy_(dwb_sum[d:])
+
+        for i in range(nl - 1, -1, -1):
+            w = W[i]
+            p = f"{prefix}layers.{i}."
+            # ---- MLP: h_out = h_mid + ff.2(silu(ff.0(a2)))
+            tdh = transpose_bf16(dh, t_a[:d])
+            tf = transpose_bf16(sv["f"][i], t_b[:ff])
+            sc.dweight(tdh, tf, grads[p + "ff.2.weight"])
+            sc.colsum(dh, grads[p + "ff.2.bias"])
+            du = ws.get("du16", (M, ff), BF16, dev)
+            E.gemm_bf16(dh16, w["w2t16"], None, du, E.EPI_BF16)                         # dF = dh W2
+            silu_bf16(sv["u"][i], du, g=du)                                            # du = dF * silu'(u)
+            tdu = transpose_bf16(du, t_a[:ff])
+            ta2 = transpose_bf16(sv["a2"][i], t_b[:d])
+            sc.dweight(tdu, ta2, grads[p + "ff.0.weight"])
+            sc.colsum(du, grads[p + "ff.0.bias"])
+            E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_F32)                            # da2 = du W1
+            ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1, p + "norm2")
+            # ---- attention: h_mid = h_in + out_proj(MHA(a1))
+            tdh = transpose_bf16(dh, t_a[:d])
+            to = transpose_bf16(sv["o"][i], t_b[:d])
+            sc.dweight(tdh, to, grads[p + "attn.out_proj.weight"])
+            sc.colsum(dh, grads[p + "attn.out_proj.bias"])
+            E.gemm_bf16(dh16, w["wot16"], None, do16, E.EPI_BF16)                       # dO = dh Wo
+            dqkv = ws.get("dqkv16", (M, 3 * d), BF16, dev)
+            L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), st)
+            tdq = transpose_bf16(dqkv, t_a[:3 * d])
+            ta1 = transpose_bf16(sv["a1"][i], t_b[:d])
+            sc.dweight(tdq, ta1, grads[p + "attn.in_proj_weight"])
+            sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
+            E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_F32)                        # da1 = dqkv Wqkv
+            ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, p + "norm1")
+
+        if film is None:
+            return None
+        # FiLM linears of all LayerNorms at once: gb = cond_vec W_all^T + b_all  (W_all [2 nl * 2d, d_cond])
+        cond_vec, film_w = S["cond_vec"], S["film_w"]
+        dc = cond_vec.shape[1]
+        dgb2 = dgb.view(B, -1)
+        n_all = dgb2.shape[1]
+        db_all = ws.get("film_db", (n_all,), F32, dev)
+        sc.colsum(dgb2, db_all)
+        dW_all = ws.get("film_dw", (n_all, dc), F32, dev)
+        dcond = torch.empty((B, dc), device=dev, dtype=F32)
+        if B % 64 == 0 and dc % 32 == 0:
+            tdg = transpose_bf16(dgb2, ws.get("t_dgb", (n_all, B), BF16, dev))
+            tcv = transpose_bf16(cond_vec, ws.get("t_cv", (dc, B), BF16, dev))
+            sc.dweight(tdg, tcv, dW_all)
+            E.gemm_bf16(dgb2.to(BF16), film_w.t().contiguous().to(BF16), None, dcond, E.EPI_F32)
+        else:
+            sgemm_strided(dgb2, True, cond_vec, True, dW_all)
+            sgemm_strided(dgb2, False, film_w, True, dcond)
+        two_d = 2 * d
+        for i in range(nl):
+            for k, nm in enumerate(("film1", "film2")):
+                r0 = (2 * i + k) * two_d
+                grads[f"{prefix}layers.{i}.{nm}.weight"].copy_(dW_all[r0:r0 + two_d])
+                grads[f"{prefix}layers.{i}.{nm}.bias"].copy_(db_all[r0:r0 + two_d])
+        return dcond
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class _MLP2:
+    """Linear -> SiLU -> Linear on per-trajectory rows [B, *] in fp32 (level_proj, sg.mlp, t_embed)."""
+
+    def __init__(self, seq, scratch: _Scratch):
+        self.l0, self.l2, self.sc = seq[0], seq[2], scratch
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        f = lambda t: t.detach().float().contiguous()
+        self.x = x
+        self.pre = E.sgemm(x, f(self.l0.weight), f(self.l0.bias))
+        self.hid = silu_f32(self.pre)
+        return E.sgemm(self.hid, f(self.l2.weight), f(self.l2.bias), out, accumulate=out is not None)
+
+    def backward(self, dy: torch.Tensor, grads: Dict[str, torch.Tensor], prefix: str, want_dx: bool = True) -> Optional[torch.Tensor]:
+        f = lambda t: t.detach().float().contiguous()
+        sgemm_strided(dy, True, self.hid, True, grads[prefix + "2.weight"])
+        self.sc.colsum(dy, grads[prefix + "2.bias"])
+        dhid = torch.empty_like(self.hid)
+        sgemm_strided(dy, False, f(self.l2.weight), True, dhid)
+        dpre = silu_f32(self.pre, g=dhid)
+        sgemm_strided(dpre, True, self.x, True, grads[prefix + "0.weight"])
+        self.sc.colsum(dpre, grads[prefix + "0.bias"])
+        if not want_dx:
+            return None
+        dx = torch.empty_like(self.x)
+        sgemm_strided(dpre, False, f(self.l0.weight), True, dx)
+        return dx
+
+
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+class CondEncoderBackprop:
+    """``MazeConditionEncoder`` (encoders.py:41-71) in training form: the conv stack as im2col + tcgen05 GEMM on NHWC bf16
+    pre-activations, mean pool, fc, start/goal MLP."""
+
+    def __init__(self, cond_enc, scratch: _Scratch):
+        self.m, self.sc = cond_enc, scratch
+        self.sg = _MLP2(cond_enc.sg.mlp, scratch) if cond_enc.sg is not None else None
+
+    def _col(self, src: torch.Tensor, B: int, Hh: int, Ww: int, C: int, act: bool, name: str) -> torch.Tensor:
+        kpad = _pad64(9 * C)
+        col = self.sc.ws.get(name, (B * Hh * Ww, kpad), BF16, src.device)
+        L.call("idb200_im2col3x3", src.data_ptr(), B, Hh, Ww, C, kpad, int(act), col.data_ptr(), L.stream(src.device))
+        return col
+
+    def forward(self, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
+        m = self.m
+        occ = L.f32c(cond["occ"])
+        if m.use_sdf:
+            if cond.get("sdf") is None:
+                raise ValueError("use_sdf is True but sdf missing from cond")
+            x = torch.cat([occ, L.f32c(cond["sdf"])], dim=1)
+        else:
+            x = occ
+        B, C0, Hh, Ww = x.shape
+        dev = x.device
+        convs = [c for c in m.maze.convs if isinstance(c, torch.nn.Conv2d)]
+        self.x0 = x.permute(0, 2, 3, 1).reshape(B, Hh * Ww, C0).to(BF16).contiguous()
+        self.dims = (B, Hh, Ww)
+        self.us: List[torch.Tensor] = []
+        self.wmats = []
+        src, C = self.x0, C0
+        for li, c in enumerate(convs):
+            w = c.weight.detach().float()
+            co = w.shape[0]
+            kpad = _pad64(9 * C)
+            wm = torch.zeros((co, kpad), device=dev, dtype=BF16)
+            wm[:, :9 * C] = w.permute(0, 2, 3, 1).reshape(co, 9 * C).to(BF16)
+            col = self._col(src, B, Hh, Ww, C, li > 0, "col")
+            u = torch.empty((B * Hh * Ww, co), device=dev, dtype=BF16)
+            E.gemm_bf16(col, wm, c.bias.detach().float().contiguous(), u, E.EPI_BF16)
+            self.us.append(u)
+            self.wmats.append(wm)
+            src, C = u, co
+        self.pooled = torch.empty((B, C), device=dev, dtype=F32)
+        L.call("idb200_pool_silu", src.data_ptr(), B, Hh * Ww, C, self.pooled.data_ptr(), L.stream(dev))
+        emb = E.sgemm(self.pooled, m.maze.fc.weight.detach().float().contiguous(), m.maze.fc.bias.detach().float().contiguous())
+        if m.use_start_goal:
+            if "start_goal" not in cond:
+                raise ValueError("use_start_goal is True but start_goal missing from cond")
+            self.sg.forward(L.f32c(cond["start_goal"]), out=emb)
+        return emb
+
+    def backward(self, dcv: torch.Tensor, grads: Dict[str, torch.Tensor], prefix: str = "cond_enc.") -> None:
+        m, sc, ws = self.m, self.sc, self.sc.ws
+        B, Hh, Ww = self.dims
+        P = Hh * Ww
+        dev = dcv.device
+        st = L.stream(dev)
+        if self.sg is not None:
+            self.sg.backward(dcv, grads, prefix + "sg.mlp.", want_dx=False)
+        fcw = m.maze.fc.weight.detach().float().contiguous()
+        sgemm_strided(dcv, True, self.pooled, True, grads[prefix + "maze.fc.weight"])
+        sc.colsum(dcv, grads[prefix + "maze.fc.bias"])
+        dpooled = torch.empty_like(self.pooled)
+        sgemm_strided(dcv, False, fcw, True, dpooled)
+        convs = [(k, c) for k, c in enumerate(m.maze.convs) if isinstance(c, torch.nn.Conv2d)]
+        n = len(convs)
+        C_last = self.us[-1].shape[1]
+        du = torch.empty_like(self.us[-1])
+        L.call("idb200_pool_silu_bwd", self.us[-1].data_ptr(), dpooled.data_ptr(), B, P, C_last, du.data_ptr(), st)
+        for li in range(n - 1, -1, -1):
+            seq_idx, c = convs[li]
+            co, ci = c.weight.shape[0], c.weight.shape[1]
+            src = self.x0 if li == 0 else self.us[li - 1]
+            col = self._col(src, B, Hh, Ww, ci, li > 0, "col")
+            kpad = col.shape[1]
+            tdu = transpose_bf16(du, ws.get("t_du", (co, B * P), BF16, dev))
+            tcol = transpose_bf16(col, ws.get("t_col", (kpad, B * P), BF16, dev))
+            dwm = ws.get("dwm", (co, kpad), F32, dev)
+            sc.dweight(tdu, tcol, dwm)
+            grads[f"{prefix}maze.convs.{seq_idx}.weight"].copy_(dwm[:, :9 * ci].reshape(co, 3, 3, ci).permute(0, 3, 1, 2))
+            sc.colsum(du, grads[f"{prefix}maze.convs.{seq_idx}.bias"])
+            if li == 0:
+                break
+            # dgrad = conv3x3(du, W flipped and transposed):  Wflip[ci, (ky, kx, co)] = W[co, ci, 2 - ky, 2 - kx]
+            w = c.weight.detach().float()
+            kp2 = _pad64(9 * co)
+            wf = torch.zeros((ci, kp2), device=dev, dtype=BF16)
+            wf[:, :9 * co] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).to(BF16)
+            colg = self._col(du, B, Hh, Ww, co, False, "colg")
+            dact = torch.empty((B * P, ci), device=dev, dtype=BF16)
+            E.gemm_bf16(colg, wf, None, dact, E.EPI_BF16)
+            du = silu_bf16(self.us[li - 1], dact, g=dact)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class InterpLevelBackprop:
+    """``InterpLevelDenoiser.forward`` (denoiser_interp_levels.py:64-84) + its backward."""
+
+    def __init__(self, model):
+        self.model = model
+        self.sc = _Scratch()
+        self.enc = EncoderBackprop(model.transformer, self.sc)
+        self.cond = CondEncoderBackprop(model.cond_enc, self.sc) if hasattr(model.cond_enc, "maze") else None
+        self.level = _MLP2(model.level_proj, self.sc)
+
+    def param_names(self) -> List[str]:
+        return [n for n, _ in self.model.named_parameters()]
+
+    def new_grads(self) -> Dict[str, torch.Tensor]:
+        return {n: torch.zeros_like(p, dtype=F32) for n, p in self.model.named_parameters()}
+
+    def forward(self, x_s: torch.Tensor, s: torch.Tensor, mask: torch.Tensor, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
+        m = self.model
+        dev = L.require_cuda(x_s, s, mask)
+        B, T, D = x_s.shape
+        d = m.in_proj.weight.shape[0]
+        C = 1 if mask.dim() == 2 else mask.shape[-1]
+        if C != m.mask_channels:
+            raise ValueError(f"mask has {C} channels, expected {m.mask_channels}")
+        M = B * T
+        f = lambda t: t.detach().float().contiguous()
+        # token features [x_s | mask] as fp32 (the in_proj weight gradient reads them back)
+        self.feat = torch.cat([L.f32c(x_s).view(M, D), mask.reshape(M, C).to(F32)], dim=1).contiguous()
+        if self.cond is None:
+            raise ValueError("training needs the built-in MazeConditionEncoder")
+        self.cond_vec = self.cond.forward(cond)
+        Wf = f(m.in_proj.weight).t().contiguous()
+        tab = m._positional_embedding(T, dev, d)
+        row_b = E.sgemm(self.cond_vec, f(m.cond_proj.weight), (f(m.cond_proj.bias) + f(m.in_proj.bias)).contiguous())
+        s64 = L.i64c(s)
+        self.onehot = torch.zeros((B, m.level_emb.weight.shape[0]), device=dev, dtype=F32)
+        self.onehot.scatter_(1, s64.view(B, 1), 1.0)
+        emb = f(m.level_emb.weight)[s64].contiguous()
+        level_vec = self.level.forward(emb)
+        h = torch.empty((M, d), device=dev, dtype=F32)
+        E.embed_tokens(self.feat, None, None, Wf, tab, None, level_vec, row_b, h, M, T, d)
+        self.enc.forward(h, B, T, self.cond_vec)
+        self.h_final = h
+        self.shape = (B, T, D, d, M)
+        out = torch.empty((B, T, D), device=dev, dtype=F32)
+        E.out_head(h, f(m.out.weight), f(m.out.bias), out.view(M, D))
+        return out
+
+    def backward(self, d_out: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+        """d_out = d loss / d delta_hat [B, T, D]; fills ``grads`` (every parameter of the model)."""
+        m, sc = self.model, self.sc
+        B, T, D, d, M = self.shape
+        dev = d_out.device
+        st = L.stream(dev)
+        f = lambda t: t.detach().float().contiguous()
+        dy = L.f32c(d_out).view(M, D)
+        sc.narrow_outer(dy, self.h_final, grads["out.weight"])
+        sc.colsum(dy, grads["out.bias"])
+        dh = torch.empty((M, d), device=dev, dtype=F32)
+        dh16 = torch.empty((M, d), device=dev, dtype=BF16)
+        L.call("idb200_head_bwd", dy.data_ptr(), f(m.out.weight).data_ptr(), M, d, D, dh.data_ptr(), dh16.data_ptr(), st)
+        dcond = self.enc.backward(dh, dh16, grads, "transformer.")
+        # token assembly: h0 = feat Wf + pos[t] + level_vec[b] + (cond_proj(cond_vec) + biases)[b]
+        dWf = torch.empty((self.feat.shape[1], d), device=dev, dtype=F32)
+        sc.narrow_outer(self.feat, dh, dWf)
+        grads["in_proj.weight"].copy_(dWf.t())
+        tok = torch.empty((B, d), device=dev, dtype=F32)
+        L.call("idb200_token_sum", dh.data_ptr(), B, T, d, tok.data_ptr(), st)
+        sc.colsum(tok, grads["in_proj.bias"])
+        grads["cond_proj.bias"].copy_(grads["in_proj.bias"])
+        sgemm_strided(tok, True, self.cond_vec, True, grads["cond_proj.weight"])
+        if dcond is None:
+            dcond = torch.zeros_like(self.cond_vec)
+        sgemm_strided(tok, False, f(m.cond_proj.weight), True, dcond, accumulate=True)
+        demb = self.level.backward(tok, grads, "level_proj.")
+        sgemm_strided(self.onehot, True, demb, True, grads["level_emb.weight"])
+        self.cond.backward(dcond, grads, "cond_enc.")

@@ -1,0 +1,107 @@
+"""One optimisation step of the reference's Stage-2 trainer (``src/train/train_interp_levels.py:1034-1173``) on libidb200:
+on-device corruption (``build_interp_adjacent_batch`` / ``build_interp_level_batch``), confidence channels, denoiser forward,
+weighted-MSE loss, hand-written backward (``train/backward.py``), data-parallel gradient all-reduce, global-norm clip,
+fused AdamW + EMA (``train/optim.py``).  Argument names and defaults are the reference's CLI defaults (:40-140).
+
+Data parallel: one process per GPU, every rank holds the full model and a B/N slice of the batch; the flat fp32
+gradient arena is all-reduced once per step (``torch.distributed`` over NCCL/NVLink) and divided by the world size, i.e. the
+mean of the per-rank losses' gradients -- DDP semantics.  (The reference normalises each rank's loss by its own sum of
+weights, :1154; the mean over ranks of those ratios is what DDP would produce for it too.)"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .. import _lib as L
+from .. import parallel as P
+from . import train_interp_levels as TI
+from .backward import InterpLevelBackprop
+from .optim import FlatAdamW, stage2_loss
+
+
+class Stage2Trainer:
+    def __init__(self, model, *, K_min: int = 8, levels: int = 3, stage2_mode: str = "adj", anchor_conf: bool = True,
+                 anchor_conf_teacher: float = 0.95, anchor_conf_student: float = 0.5, anchor_conf_endpoints: float = 1.0,
+                 anchor_conf_missing: float = 0.0, anchor_conf_anneal: bool = True, anchor_conf_anneal_mode: str = "linear",
+                 corrupt_mode: str = "dist", corrupt_sigma_max: float = 0.08, corrupt_sigma_min: float = 0.012,
+                 corrupt_sigma_pow: float = 0.75, corrupt_anchor_frac: float = 0.25, corrupt_index_jitter_max: int = 0,
+                 corrupt_index_jitter_prob: float = 0.0, corrupt_index_jitter_pow: float = 1.0, clamp_endpoints: bool = True,
+                 recompute_vel: bool = True, pos_clip: bool = False, pos_clip_min: float = 0.0, pos_clip_max: float = 1.0,
+                 level_sampling: str = "high", level_high_prob: float = 0.5, w_anchor: float = 0.1, w_missing: float = 1.0,
+                 lr: float = 2e-4, weight_decay: float = 1e-2, grad_clip: Optional[float] = 1.0, ema: bool = True,
+                 ema_decay: float = 0.999, process_group=None):
+        if stage2_mode not in ("adj", "x0"):
+            raise ValueError("stage2_mode must be 'adj' or 'x0'")
+        self.model = model
+        self.cfg = dict(K_min=K_min, levels=levels, stage2_mode=stage2_mode, anchor_conf=bool(anchor_conf),
+                        conf=(anchor_conf_teacher, anchor_conf_student, anchor_conf_endpoints, anchor_conf_missing),
+                        anneal=bool(anchor_conf_anneal), anneal_mode=anchor_conf_anneal_mode, clamp_endpoints=bool(clamp_endpoints),
+                        recompute_vel=bool(recompute_vel), level_sampling=level_sampling, level_high_prob=level_high_prob,
+                        w_anchor=w_anchor, w_missing=w_missing)
+        self.corrupt = dict(corrupt_mode=corrupt_mode, corrupt_sigma_max=corrupt_sigma_max, corrupt_sigma_min=corrupt_sigma_min,
+                            corrupt_sigma_pow=corrupt_sigma_pow, corrupt_anchor_frac=corrupt_anchor_frac,
+                            corrupt_index_jitter_max=corrupt_index_jitter_max, corrupt_index_jitter_prob=corrupt_index_jitter_prob,
+                            corrupt_index_jitter_pow=corrupt_index_jitter_pow, clamp_endpoints=bool(clamp_endpoints),
+                            pos_clip=bool(pos_clip), pos_clip_min=pos_clip_min, pos_clip_max=pos_clip_max)
+        self.opt = FlatAdamW(model.parameters(), lr=lr, weight_decay=weight_decay, ema_decay=ema_decay if ema else None,
+                             max_grad_norm=grad_clip)
+        self.bp = InterpLevelBackprop(model)
+        self.flat_grad = torch.zeros_like(self.opt.flat)
+        by_id = {id(p): g for p, g in zip(self.opt.params, self.opt.views(self.flat_grad))}
+        self.grads: Dict[str, torch.Tensor] = {n: by_id[id(p)] for n, p in model.named_parameters() if id(p) in by_id}
+        self.pg = process_group
+        self.last_grad_norm: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def build_batch(self, x0: torch.Tensor, gen: torch.Generator) -> Tuple[torch.Tensor, ...]:
+        """train_interp_levels.py:1034-1135 without the bootstrap branch: (x_s, s_idx, mask_in, target, weight_mask)."""
+        c = self.cfg
+        dev = L.require_cuda(x0)
+        B = x0.shape[0]
+        s_idx = TI._sample_level_indices(B, c["levels"], gen, dev, c["level_sampling"], c["level_high_prob"])
+        conf_t, conf_st, conf_e, conf_m = c["conf"]
+        if c["stage2_mode"] == "adj":
+            x_s, x_prev, mask_s, mask_prev, s_idx, _, _ = TI.build_interp_adjacent_batch(
+                x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], s_idx=s_idx, **self.corrupt)
+            conf_s = TI._build_anchor_conf(mask_s, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
+            conf_prev = TI._build_anchor_conf(mask_prev, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
+            if c["anneal"]:
+                conf_s = TI._anneal_conf(conf_s, s_idx, c["levels"], c["anneal_mode"])
+                conf_prev = TI._anneal_conf(conf_prev, torch.clamp(s_idx - 1, min=0), c["levels"], c["anneal_mode"])
+            if c["anchor_conf"]:
+                mask_in = torch.stack([mask_s.float(), mask_prev.float(), conf_s], dim=-1)
+            else:
+                mask_in = torch.stack([mask_s, mask_prev], dim=-1)
+            return x_s, s_idx, mask_in, x_prev - x_s, (conf_prev if c["anchor_conf"] else mask_prev)
+        x_s, mask_s, s_idx, _, _ = TI.build_interp_level_batch(
+            x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], s_idx=s_idx, **self.corrupt)
+        conf_s = TI._build_anchor_conf(mask_s, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
+        if c["anneal"]:
+            conf_s = TI._anneal_conf(conf_s, s_idx, c["levels"], c["anneal_mode"])
+        mask_in = torch.stack([mask_s.float(), conf_s], dim=-1) if c["anchor_conf"] else mask_s
+        return x_s, s_idx, mask_in, x0 - x_s, (conf_s if c["anchor_conf"] else mask_s)
+
+    def loss_and_grads(self, x_s, s_idx, mask_in, cond, target, weight_mask) -> torch.Tensor:
+        """Forward + loss + backward; the parameter gradients land in ``self.flat_grad`` (views: ``self.grads``)."""
+        c = self.cfg
+        delta_hat = self.bp.forward(x_s, s_idx, mask_in, cond)
+        # the 1 / world factor of the data-parallel mean rides on the loss kernel's grad_accum divisor
+        world = P.world_size(self.pg)
+        loss, dgrad = stage2_loss(delta_hat, target, weight_mask, anchor_conf=c["anchor_conf"], w_anchor=c["w_anchor"],
+                                  w_missing=c["w_missing"], grad_accum=world)
+        self.bp.backward(dgrad, self.grads)
+        return loss * world if world > 1 else loss
+
+    def reduce_gradients(self) -> None:
+        """Data-parallel all-reduce of the flat gradient arena (each rank's gradient already carries 1 / world)."""
+        P.all_reduce_sum_(self.flat_grad, self.pg)
+
+    def step(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> torch.Tensor:
+        """One full training step; returns the (local) loss as a 0-dim device tensor (no host sync)."""
+        batch = self.build_batch(x0, gen)
+        x_s, s_idx, mask_in, target, weight_mask = batch
+        loss = self.loss_and_grads(x_s, s_idx, mask_in, cond, target, weight_mask)
+        self.reduce_gradients()
+        self.last_grad_norm = self.opt.step(self.flat_grad)
+        return loss

@@ -69,3 +69,60 @@ def test_sharded_generation_equals_single_process(B):
     assert got.shape == ref.shape
     # identical rows, identical math: only BLAS blocking may differ with the batch size
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-4)
+
+
+# ---- data-parallel gradient all-reduce of the training step: flat arena, 1 / world on the loss --------------------
+def _tiny_grads(rows, world):
+    """Flat gradient of (1 / world) * local Stage-2 loss for the rows [lo, hi), computed by autograd on the oracle."""
+    sys.path.insert(0, ROOT)
+    from oracle import denoiser_torch as O
+    g = dict(np.load(GOLD))
+    sd = {k[len("il/"):]: torch.from_numpy(v).clone().requires_grad_() for k, v in g.items() if k.startswith("il/")}
+    B, T = 6, 64
+    gen = torch.Generator().manual_seed(5)
+    x_s = torch.rand((B, T, 2), generator=gen)
+    C = sd["in_proj.weight"].shape[1] - 2
+    mask = (torch.rand((B, T, C), generator=gen) < 0.3).float()
+    s = torch.randint(1, 4, (B,), generator=gen)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    target = 0.1 * torch.randn((B, T, 2), generator=gen)
+    conf = torch.rand((B, T), generator=gen)
+    lo, hi = rows
+    out = O.interp_level_denoiser(sd, 2, x_s[lo:hi], s[lo:hi], mask[lo:hi], {k: v[lo:hi] for k, v in cond.items()})
+    w = 1.0 + (0.1 - 1.0) * conf[lo:hi]
+    loss = (w[..., None] * (out - target[lo:hi]) ** 2).sum() / (w.sum() * 2 + 1e-8) / world
+    loss.backward()
+    return torch.cat([v.grad.reshape(-1) for _, v in sorted(sd.items())])
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        from interpolated_diffusion_b200.parallel import all_reduce_sum_, shard_range, world_size
+        assert world_size() == world
+        flat = _tiny_grads(shard_range(6, rank, world), world)
+        all_reduce_sum_(flat, bucket_elems=100_000)               # bucketed async path
+        if rank == 0:
+            q.put(flat.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_is_the_mean_of_rank_gradients():
+    sys.path.insert(0, ROOT)
+    from interpolated_diffusion_b200.parallel import shard_range
+    ref = sum(_tiny_grads(shard_range(6, r, 2), 2) for r in range(2)).numpy()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-7)
