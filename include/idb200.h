@@ -332,11 +332,16 @@ int idb200_adamw_ema_step(float* param, const float* grad, float* exp_avg, float
  * Backward of the denoisers (what loss.backward() does in src/train/train_interp_levels.py:1159 and
  * src/train/train_keypoints.py:540 for the modules of src/models/{transformer,encoders,denoiser_*}.py).
  * Dense contractions reuse idb200_gemm_bf16: dX = dY * W is the same GEMM with W^T as the weight operand; dW = dY^T * X is
- * idb200_gemm_bf16_splitk on bf16 transposes (reduction over the tokens) followed by idb200_reduce_rows.
+ * idb200_gemm_bf16_nn_splitk (reduction over the tokens, operands read in place) followed by idb200_reduce_rows.
  * ---------------------------------------------------------------------------------------------- */
 /* partial[s] [M,N] fp32 = A[:, K_s] * W[:, K_s]^T for the s-th of `splits` equal slices of K ((K / 64) % splits == 0). */
 int idb200_gemm_bf16_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int K, int splits,
                             idb200_stream_t stream);
+/* partial[s] [M,N] fp32 = A[K_s, M]^T * W[K_s, N]: both operands row-major with the REDUCTION index as rows (the weight
+ * gradient dW = dY^T X straight from the token-major activations, no transposes: MN-major UMMA operands).  M % 8 == 0,
+ * N % 64 == 0, K % 64 == 0, (K / 64) % splits == 0. */
+int idb200_gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int64_t K, int splits,
+                               idb200_stream_t stream);
 /* dst bf16 [N,M] = src[M,N]^T (src fp32 or bf16). */
 int idb200_transpose_bf16(const void* src, int src_is_f32, int64_t M, int N, void* dst, idb200_stream_t stream);
 /* out[N] (+)= scale * column sums of src[M,N] (src_kind 0 fp32, 1 bf16); scratch: idb200_colsum_scratch_floats(M, N) floats. */

@@ -50,6 +50,7 @@ _SIGS = {
     "idb200_grad_clip_coef": [c_p, c_l, c_f, c_p, c_p, c_p],
     "idb200_adamw_ema_step": [c_p, c_p, c_p, c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_f, c_l, c_f, c_p, c_p],
     "idb200_gemm_bf16_splitk": [c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
+    "idb200_gemm_bf16_nn_splitk": [c_p, c_p, c_p, c_l, c_i, c_l, c_i, c_p],
     "idb200_transpose_bf16": [c_p, c_i, c_l, c_i, c_p, c_p],
     "idb200_colsum_scratch_floats": [c_l, c_i],
     "idb200_colsum": [c_p, c_i, c_l, c_i, c_p, c_f, c_i, c_p, c_p],

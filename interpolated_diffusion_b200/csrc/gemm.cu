@@ -89,7 +89,12 @@ __device__ __forceinline__ float silu_f(float x) {
     return fmaf(h, t, h);
 }
 
-template <int BN>
+// kMN = false: A [M,K], W [N,K] row-major (K-major operands): out = A W^T.
+// kMN = true : both operands stored reduction-major, A [K,M], W [K,N] row-major (MN-major UMMA operands): out = A^T W.  This is
+// the weight-gradient form dW = dY^T X with the tokens as K: TMA boxes are [64 tokens x 64 features] (one SW128 atom column),
+// an operand tile is a row of such boxes 8 KB apart (descriptor LBO), 8-token groups 1 KB apart (SBO), and one UMMA_K = 16
+// tokens advances the start address by 2 KB.
+template <int BN, bool kMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -148,8 +153,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + kBM * kBK * 2;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
-                    tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBK, n0);
+                    if constexpr (kMN) {
+#pragma unroll
+                        for (int hb = 0; hb < kBM / 64; ++hb) tma_load_2d(sa + hb * 8192, &tmap_a, &full_bar[stage], m0 + hb * 64, kb * kBK);
+#pragma unroll
+                        for (int hb = 0; hb < BN / 64; ++hb) tma_load_2d(sb + hb * 8192, &tmap_w, &full_bar[stage], n0 + hb * 64, kb * kBK);
+                    } else {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+                        tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBK, n0);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -157,7 +169,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN) | (kMN ? ((1u << 15) | (1u << 16)) : 0u);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -170,11 +182,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(&full_bar[stage], phase, 3);         // TMA bytes landed
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(sa + kBM * kBK * 2);
+                    const uint64_t adesc = kMN ? umma_desc_sw128_mn(sa) : umma_desc_sw128(sa);
+                    const uint64_t bdesc = kMN ? umma_desc_sw128_mn(sa + kBM * kBK * 2) : umma_desc_sw128(sa + kBM * kBK * 2);
+                    constexpr int kStep = kMN ? 128 : 2;            // 16-byte units per UMMA_K
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb | k) ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);                // smem slot free once these MMAs retire
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -271,19 +284,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
-template <int BN>
+template <int BN, bool kMN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
     const long long tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN) * p.splits;
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, p);
+    gemm_bf16_tn_kernel<BN, kMN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, p);
     return check_launch("gemm_bf16_tn_kernel");
+}
+
+// out[s] [M,N] fp32 = A[K_s, M]^T W[K_s, N] for the s-th slice of the K rows (MN-major operands, see the kernel comment)
+int gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, long long M, int N, long long K, int splits, cudaStream_t st) {
+    IDB_REQUIRE(A && W && partial, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(M > 0 && N > 0 && K > 0 && M % 8 == 0 && K < (1ll << 31), IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(K % kBK == 0, IDB200_EUNSUPPORTED, "K (rows of both operands) must be a multiple of %d (got %lld)", kBK, K);
+    IDB_REQUIRE(N % 64 == 0, IDB200_EUNSUPPORTED, "N must be a multiple of 64 (got %d)", N);
+    IDB_REQUIRE(splits >= 1 && (K / kBK) % splits == 0, IDB200_EINVAL, "splits (%d) must divide K / %d", splits, kBK);
+    IDB_REQUIRE(aligned(partial, 16), IDB200_EALIGN, "out must be 16-byte aligned");
+    int BN = 0;
+    for (int cand : {256, 192, 128, 64})
+        if (N % cand == 0) { BN = cand; break; }
+    CUtensorMap ta, tw;
+    int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tw, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), 64, 64);
+    if (rc) return rc;
+    GemmParams p{nullptr, partial, M, N, static_cast<int>(K), EPI_F32, splits};
+    switch (BN) {
+        case 256: return launch_gemm<256, true>(ta, tw, p, st);
+        case 192: return launch_gemm<192, true>(ta, tw, p, st);
+        case 128: return launch_gemm<128, true>(ta, tw, p, st);
+        default: return launch_gemm<64, true>(ta, tw, p, st);
+    }
 }
 
 int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, long long M, int N, int K, int epilogue,
@@ -321,6 +359,11 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
 extern "C" int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K,
                                 int epilogue, idb200_stream_t stream) {
     return idb200::gemm_bf16_tn(A, W, bias, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream), 1);
+}
+
+extern "C" int idb200_gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int64_t K, int splits,
+                                          idb200_stream_t stream) {
+    return idb200::gemm_bf16_nn_splitk(A, W, partial, M, N, K, splits, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int idb200_gemm_bf16_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int K, int splits,

@@ -305,6 +305,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 // advancing by one UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the address field
 
+// MN-major operand, SWIZZLE_128B: the tile is a row of [64 k-rows x 64 MN elements] TMA boxes (each k-row one 128-byte line);
+// LBO = distance between 64-element MN chunks (8 KB boxes), SBO = distance between 8-row k groups (1 KB).  One UMMA_K = 16
+// k-rows = 2 KB: +128 in the address field.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(8192 >> 4) << 16) |
+           (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 // Instruction descriptor, kind::f16: [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3   [24,29) M >> 4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {

@@ -43,6 +43,40 @@ __global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const TIn* __res
     }
 }
 
+// bf16 -> bf16 with 16-byte accesses on both sides (M % 8 == 0, N % 8 == 0): 64 x 64 tile, each thread moves two 8-element
+// vectors in and two out.
+__global__ void __launch_bounds__(256) transpose_bf16_vec_kernel(const __nv_bfloat16* __restrict__ src, long long M, int N,
+                                                                 __nv_bfloat16* __restrict__ dst) {
+    __shared__ __nv_bfloat16 tile[64][66];                 // pitch 33 words
+    const long long m0 = static_cast<long long>(blockIdx.x) * 64;
+    const int n0 = blockIdx.y * 64;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int v = threadIdx.x + it * 256;              // 512 vectors: row r = v / 8, 8-column group cg = v % 8
+        const int r = v >> 3, cg = v & 7;
+        const long long m = m0 + r;
+        const int n = n0 + cg * 8;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (m < M && n < N) val = *reinterpret_cast<const uint4*>(src + m * N + n);
+        uint32_t* t32 = reinterpret_cast<uint32_t*>(&tile[r][cg * 8]);
+        t32[0] = val.x; t32[1] = val.y; t32[2] = val.z; t32[3] = val.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int v = threadIdx.x + it * 256;              // output row n = v / 8 (source column), m group mg = v % 8
+        const int c = v >> 3, mg = v & 7;
+        const int n = n0 + c;
+        const long long m = m0 + mg * 8;
+        if (n < N && m < M) {
+            __align__(16) __nv_bfloat16 e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = tile[mg * 8 + j][c];
+            *reinterpret_cast<uint4*>(dst + static_cast<long long>(n) * M + m) = *reinterpret_cast<const uint4*>(e);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Column sums of src[M, N] (bias gradients; LayerNorm affine gradients from per-trajectory partials).
 // Stage 1: block (32 columns, one row slice) -> partial[slice, N]; stage 2: reduce_rows.
@@ -508,6 +542,38 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __r
     }
 }
 
+// C % 8 == 0: one thread moves 8 channels (16 bytes) of one tap
+__global__ void __launch_bounds__(256) im2col3x3_vec_kernel(const __nv_bfloat16* __restrict__ src, long long B, int Hh, int Ww, int C, int Kpad,
+                                                            int act, __nv_bfloat16* __restrict__ col) {
+    const int P = Hh * Ww;
+    const int kv = Kpad / 8;
+    const long long total = B * P * static_cast<long long>(kv);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int kk = static_cast<int>(i % kv) * 8;
+        const long long bp = i / kv;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (kk < 9 * C) {
+            const int tap = kk / C, c = kk - tap * C;
+            const int p = static_cast<int>(bp % P);
+            const long long b = bp / P;
+            const int y = p / Ww + tap / 3 - 1, x = p % Ww + tap % 3 - 1;
+            if (y >= 0 && y < Hh && x >= 0 && x < Ww) {
+                val = *reinterpret_cast<const uint4*>(src + (b * P + y * Ww + x) * C + c);
+                if (act) {
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(h2[j]);
+                        h2[j] = __floats2bfloat162_rn(silu_fwd(f.x), silu_fwd(f.y));
+                    }
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(col + i * 8) = val;
+    }
+}
+
 // pooled[b, c] = mean_p silu(u[b, p, c])
 __global__ void __launch_bounds__(128) pool_silu_kernel(const __nv_bfloat16* __restrict__ u, int P, int C, float* __restrict__ pooled) {
     const long long b = blockIdx.x;
@@ -568,6 +634,9 @@ extern "C" int idb200_transpose_bf16(const void* src, int src_is_f32, int64_t M,
     if (src_is_f32)
         tb::transpose_to_bf16_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(src), M, N,
                                                                                                    static_cast<__nv_bfloat16*>(dst));
+    else if (M % 8 == 0 && N % 8 == 0 && aligned(src, 16) && aligned(dst, 16))
+        tb::transpose_bf16_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(src), M, N,
+                                                                                            static_cast<__nv_bfloat16*>(dst));
     else
         tb::transpose_to_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(src), M, N, static_cast<__nv_bfloat16*>(dst));
@@ -701,6 +770,11 @@ extern "C" int idb200_sgemm_strided(const float* A, int64_t sa0, int64_t sa1, co
 extern "C" int idb200_im2col3x3(const void* src, int64_t B, int H, int W, int C, int Kpad, int act, void* col, idb200_stream_t stream) {
     IDB_REQUIRE(src && col, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Kpad >= 9 * C, IDB200_EINVAL, "bad shape");
+    if (C % 8 == 0 && Kpad % 8 == 0 && aligned(src, 16) && aligned(col, 16)) {
+        tb::im2col3x3_vec_kernel<<<grid_for(B * H * W * (Kpad / 8), 256 * 2, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(src), B, H, W, C, Kpad, act, static_cast<__nv_bfloat16*>(col));
+        return check_launch("im2col3x3_vec_kernel");
+    }
     tb::im2col3x3_kernel<<<grid_for(B * H * W * Kpad, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(src), B, H, W, C, Kpad, act, static_cast<__nv_bfloat16*>(col));
     return check_launch("im2col3x3_kernel");

@@ -79,18 +79,34 @@ class _Scratch:
         L.call("idb200_narrow_outer", A.data_ptr(), n, X.data_ptr(), M, K, sc.data_ptr(), 0, out.data_ptr(), L.stream(A.device))
         return out
 
-    def dweight(self, dy_t: torch.Tensor, x_t: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        """out[N_out, K_in] = dY^T X from the bf16 transposes dy_t [N_out, M], x_t [K_in, M]: split-K tcgen05 GEMM over the M
-        tokens, partial products reduced in a fixed order."""
-        n_out, m_tok = dy_t.shape
-        k_in = x_t.shape[0]
+    def _splits(self, n_out: int, k_in: int, m_tok: int, bns) -> int:
         if m_tok % 64 != 0:
             raise ValueError(f"the weight-gradient GEMM reduces over the tokens in blocks of 64 (got {m_tok} rows)")
         kb = m_tok // 64
-        bn = next(c for c in (256, 192, 128, 96, 64, 32) if k_in % c == 0)
+        bn = next(c for c in bns if k_in % c == 0)
         tiles = ((n_out + 127) // 128) * (k_in // bn)
         want = max(1, min(32, 296 // tiles))
-        splits = max(s for s in range(1, want + 1) if kb % s == 0)
+        return max(s for s in range(1, want + 1) if kb % s == 0)
+
+    def dweight(self, dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """out[N_out, K_in] = dY^T X from dy [M, N_out], x [M, K_in] (bf16, row-major): split-K tcgen05 GEMM over the M tokens
+        with both operands read as MN-major UMMA tiles straight from their row-major storage (no transposes); partial
+        products reduced in a fixed order."""
+        m_tok, n_out = dy.shape
+        k_in = x.shape[1]
+        assert dy.dtype == BF16 and x.dtype == BF16 and dy.is_contiguous() and x.is_contiguous() and x.shape[0] == m_tok
+        splits = self._splits(n_out, k_in, m_tok, (256, 192, 128, 64))
+        part = self.ws.get("splitk", (splits, n_out, k_in), F32, dy.device)
+        L.call("idb200_gemm_bf16_nn_splitk", dy.data_ptr(), x.data_ptr(), part.data_ptr(), n_out, k_in, m_tok, splits,
+               L.stream(dy.device))
+        L.call("idb200_reduce_rows", part.data_ptr(), splits, n_out * k_in, 1.0, 0, out.data_ptr(), L.stream(dy.device))
+        return out
+
+    def dweight_t(self, dy_t: torch.Tensor, x_t: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Same product from bf16 transposes dy_t [N_out, M], x_t [K_in, M] (K-major operands; kept as a cross-check)."""
+        n_out, m_tok = dy_t.shape
+        k_in = x_t.shape[0]
+        splits = self._splits(n_out, k_in, m_tok, (256, 192, 128, 96, 64, 32))
         part = self.ws.get("splitk", (splits, n_out, k_in), F32, dy_t.device)
         L.call("idb200_gemm_bf16_splitk", dy_t.data_ptr(), x_t.data_ptr(), part.data_ptr(), n_out, k_in, m_tok, splits,
                L.stream(dy_t.device))
@@ -168,8 +184,6 @@ class EncoderBackprop:
         dev = dh.device
         nl = len(W)
         sc, ws = self.sc, self.sc.ws
-        t_a = ws.get("t_a", (max(3 * d, ff), M), BF16, dev)
-        t_b = ws.get("t_b", (max(3 * d, ff), M), BF16, dev)
         da = ws.get("da", (M, d), F32, dev)
         do16 = ws.get("do16", (M, d), BF16, dev)
         dwb = ws.get("dwb", (B, 2 * d), F32, dev)
@@ -191,30 +205,22 @@ class EncoderBackprop:
             w = W[i]
             p = f"{prefix}layers.{i}."
             # ---- MLP: h_out = h_mid + ff.2(silu(ff.0(a2)))
-            tdh = transpose_bf16(dh, t_a[:d])
-            tf = transpose_bf16(sv["f"][i], t_b[:ff])
-            sc.dweight(tdh, tf, grads[p + "ff.2.weight"])
+            sc.dweight(dh16, sv["f"][i], grads[p + "ff.2.weight"])
             sc.colsum(dh, grads[p + "ff.2.bias"])
             du = ws.get("du16", (M, ff), BF16, dev)
             E.gemm_bf16(dh16, w["w2t16"], None, du, E.EPI_BF16)                         # dF = dh W2
             silu_bf16(sv["u"][i], du, g=du)                                            # du = dF * silu'(u)
-            tdu = transpose_bf16(du, t_a[:ff])
-            ta2 = transpose_bf16(sv["a2"][i], t_b[:d])
-            sc.dweight(tdu, ta2, grads[p + "ff.0.weight"])
+            sc.dweight(du, sv["a2"][i], grads[p + "ff.0.weight"])
             sc.colsum(du, grads[p + "ff.0.bias"])
             E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_F32)                            # da2 = du W1
             ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1, p + "norm2")
             # ---- attention: h_mid = h_in + out_proj(MHA(a1))
-            tdh = transpose_bf16(dh, t_a[:d])
-            to = transpose_bf16(sv["o"][i], t_b[:d])
-            sc.dweight(tdh, to, grads[p + "attn.out_proj.weight"])
+            sc.dweight(dh16, sv["o"][i], grads[p + "attn.out_proj.weight"])
             sc.colsum(dh, grads[p + "attn.out_proj.bias"])
             E.gemm_bf16(dh16, w["wot16"], None, do16, E.EPI_BF16)                       # dO = dh Wo
             dqkv = ws.get("dqkv16", (M, 3 * d), BF16, dev)
             L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), st)
-            tdq = transpose_bf16(dqkv, t_a[:3 * d])
-            ta1 = transpose_bf16(sv["a1"][i], t_b[:d])
-            sc.dweight(tdq, ta1, grads[p + "attn.in_proj_weight"])
+            sc.dweight(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
             sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
             E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_F32)                        # da1 = dqkv Wqkv
             ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, p + "norm1")
@@ -230,11 +236,10 @@ class EncoderBackprop:
         sc.colsum(dgb2, db_all)
         dW_all = ws.get("film_dw", (n_all, dc), F32, dev)
         dcond = torch.empty((B, dc), device=dev, dtype=F32)
-        if B % 64 == 0 and dc % 32 == 0:
-            tdg = transpose_bf16(dgb2, ws.get("t_dgb", (n_all, B), BF16, dev))
-            tcv = transpose_bf16(cond_vec, ws.get("t_cv", (dc, B), BF16, dev))
-            sc.dweight(tdg, tcv, dW_all)
-            E.gemm_bf16(dgb2.to(BF16), film_w.t().contiguous().to(BF16), None, dcond, E.EPI_F32)
+        if B % 64 == 0 and dc % 64 == 0:
+            dgb16 = dgb2.to(BF16)
+            sc.dweight(dgb16, cond_vec.to(BF16).contiguous(), dW_all)
+            E.gemm_bf16(dgb16, film_w.t().contiguous().to(BF16), None, dcond, E.EPI_F32)
         else:
             sgemm_strided(dgb2, True, cond_vec, True, dW_all)
             sgemm_strided(dgb2, False, film_w, True, dcond)
@@ -357,10 +362,8 @@ class CondEncoderBackprop:
             src = self.x0 if li == 0 else self.us[li - 1]
             col = self._col(src, B, Hh, Ww, ci, li > 0, "col")
             kpad = col.shape[1]
-            tdu = transpose_bf16(du, ws.get("t_du", (co, B * P), BF16, dev))
-            tcol = transpose_bf16(col, ws.get("t_col", (kpad, B * P), BF16, dev))
             dwm = ws.get("dwm", (co, kpad), F32, dev)
-            sc.dweight(tdu, tcol, dwm)
+            sc.dweight(du, col, dwm)
             grads[f"{prefix}maze.convs.{seq_idx}.weight"].copy_(dwm[:, :9 * ci].reshape(co, 3, 3, ci).permute(0, 3, 1, 2))
             sc.colsum(du, grads[f"{prefix}maze.convs.{seq_idx}.bias"])
             if li == 0:

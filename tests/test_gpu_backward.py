@@ -28,7 +28,8 @@ def dev():
 def test_transpose_colsum_reduce(dev):
     from interpolated_diffusion_b200.train import backward as BW
     g = torch.Generator(device="cpu").manual_seed(0)
-    for M, N, dt in ((192, 96, torch.float32), (130, 40, torch.bfloat16), (4096, 384, torch.float32)):
+    for M, N, dt in ((192, 96, torch.float32), (130, 40, torch.bfloat16), (4096, 384, torch.float32), (4096, 1536, torch.bfloat16),
+                     (512, 96, torch.bfloat16)):
         x = torch.randn((M, N), generator=g).to(dt).to(dev)
         out = torch.empty((N, M), device=dev, dtype=torch.bfloat16)
         BW.transpose_bf16(x, out)
@@ -45,19 +46,23 @@ def test_transpose_colsum_reduce(dev):
 def test_splitk_weight_gradient_gemm(dev):
     from interpolated_diffusion_b200.train import backward as BW
     g = torch.Generator(device="cpu").manual_seed(1)
-    for M, n_out, k_in in ((4096, 384, 128), (8192, 96, 64), (1024, 1152, 384)):
+    for M, n_out, k_in in ((4096, 384, 128), (8192, 96, 64), (1024, 1152, 384), (2048, 32, 320), (4096, 1536, 384), (640, 200, 192)):
         dy = torch.randn((M, n_out), generator=g).to(torch.bfloat16)
         x = torch.randn((M, k_in), generator=g).to(torch.bfloat16)
         sc = BW._Scratch()
         tdy = BW.transpose_bf16(dy.to(dev), torch.empty((n_out, M), device=dev, dtype=torch.bfloat16))
         tx = BW.transpose_bf16(x.to(dev), torch.empty((k_in, M), device=dev, dtype=torch.bfloat16))
         out = torch.empty((n_out, k_in), device=dev, dtype=torch.float32)
-        sc.dweight(tdy, tx, out)
+        sc.dweight_t(tdy, tx, out)                           # K-major operands (transposed copies)
         ref = dy.double().t() @ x.double()
         assert _rel(out, ref) < 1e-5, (M, n_out, k_in)
         out2 = torch.empty_like(out)
-        sc.dweight(tdy, tx, out2)
+        sc.dweight_t(tdy, tx, out2)
         assert torch.equal(out, out2)                       # fixed reduction order
+        if k_in % 64 == 0:
+            out3 = torch.empty_like(out)
+            sc.dweight(dy.to(dev), x.to(dev), out3)         # MN-major operands, no transposes
+            assert _rel(out3, ref) < 1e-5, ("mn", M, n_out, k_in)
 
 
 def test_small_fp32_backward_kernels(dev):
