@@ -358,8 +358,11 @@ int idb200_silu_f32(const float* u, const float* g, int64_t n, int mode, float* 
 int idb200_ln_film_bwd(const float* da, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
                        int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb, int64_t dgb_stride,
                        float* dwb_part, idb200_stream_t stream);
-/* Backward of the packed-QKV multi-head attention (head_dim 32, L <= 64): qkv, dqkv bf16 [B*L, 3d]; dO bf16 [B*L, d]. */
-int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, idb200_stream_t stream);
+/* Backward of the packed-QKV multi-head attention (head_dim 32, L <= 64): qkv, dqkv bf16 [B*L, 3d]; dO bf16 [B*L, d].
+ * 32 < L <= 64 runs on mma.sync tensor cores (P and dS rounded to bf16 for the second products, as the forward rounds P);
+ * force_simt != 0 selects the fp32 shared-memory kernel that serves L <= 32. */
+int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, int force_simt,
+                         idb200_stream_t stream);
 /* dh[M,d] = dy[M,D] * W[D,d] (out head backward, D <= 8), plus an optional bf16 copy. */
 int idb200_head_bwd(const float* dy, const float* W, int64_t M, int d, int D, float* dh, void* dh_bf16, idb200_stream_t stream);
 /* out[n,K] (+)= A[M,n]^T * X[M,K], n <= 8 (out-head / in_proj weight gradients); scratch: ..._scratch_floats(M, n, K). */

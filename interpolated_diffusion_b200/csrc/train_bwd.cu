@@ -445,6 +445,199 @@ __global__ void __launch_bounds__(AttnBwdCfg<kL, kT>::kThreads) attention_bwd_ke
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core attention backward for 32 < L <= 64 (mma.sync m16n8k16 bf16 + ldmatrix; the products are 64 x 64 x 32 per head,
+// far below a tcgen05 tile).  One block of 4 warps per (trajectory, head).
+//   phase 1, warp w owns query rows 16w..16w+15: S = Q K^T, row softmax in registers, dP = dO V^T, delta = rowsum(P o dP),
+//            dS = P o (dP - delta) / sqrt(32), dQ = dS K (register A fragments) -> global; P and dS (bf16) -> shared memory;
+//   phase 2, warp w owns key rows 16w..16w+15: dV = P^T dO, dK = dS^T Q with the transposed A fragments read by
+//            ldmatrix.trans.  No cross-warp reduction: deterministic.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ldsm4(unsigned (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr_u32(p)));
+}
+__device__ __forceinline__ void ldsm4t(unsigned (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned*>(&v);
+}
+
+__global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dO,
+                                                                __nv_bfloat16* __restrict__ dqkv, int L, int H, int causal) {
+    constexpr int PQ = 40;                  // bf16 pitch of the [64][32] operand tiles (80 B rows: conflict-free ldmatrix)
+    constexpr int PP = 72;                  // bf16 pitch of the [64][64] P / dS tiles (144 B rows)
+    __shared__ __align__(16) __nv_bfloat16 sQ[64 * PQ], sK[64 * PQ], sV[64 * PQ], sG[64 * PQ], sP[64 * PP], sS[64 * PP];
+    const int d = H * 32;
+    const long long b = blockIdx.x / H;
+    const int hh = blockIdx.x % H;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    // load: 64 rows x 4 chunks of 8 bf16 per operand
+    for (int e = t; e < 64 * 4; e += 128) {
+        const int r = e >> 2, ch = e & 3;
+        uint4 q = make_uint4(0u, 0u, 0u, 0u), k = q, v = q, g = q;
+        if (r < L) {
+            const long long row = b * L + r;
+            const __nv_bfloat16* base = qkv + row * 3 * d + hh * 32 + ch * 8;
+            q = *reinterpret_cast<const uint4*>(base);
+            k = *reinterpret_cast<const uint4*>(base + d);
+            v = *reinterpret_cast<const uint4*>(base + 2 * d);
+            g = *reinterpret_cast<const uint4*>(dO + row * d + hh * 32 + ch * 8);
+        }
+        *reinterpret_cast<uint4*>(&sQ[r * PQ + ch * 8]) = q;
+        *reinterpret_cast<uint4*>(&sK[r * PQ + ch * 8]) = k;
+        *reinterpret_cast<uint4*>(&sV[r * PQ + ch * 8]) = v;
+        *reinterpret_cast<uint4*>(&sG[r * PQ + ch * 8]) = g;
+    }
+    __syncthreads();
+    const int g8 = lane >> 2, tq = lane & 3;
+    constexpr float kScale = 0.17677669529663687f;
+    constexpr float kScaleLog2 = kScale * 1.4426950408889634f;
+    {   // ---- phase 1: query block w
+        unsigned qa[2][4], ga[2][4];
+        const int arow = w * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            ldsm4(qa[ks], &sQ[arow * PQ + ks * 16 + (lane >> 4) * 8]);
+            ldsm4(ga[ks], &sG[arow * PQ + ks * 16 + (lane >> 4) * 8]);
+        }
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[nt][c] = dp[nt][c] = 0.0f;
+            unsigned kb[4], vb[4];
+            ldsm4(kb, &sK[(nt * 8 + (lane & 7)) * PQ + (lane >> 3) * 8]);
+            mma16816(s[nt], qa[0], kb[0], kb[1]);
+            mma16816(s[nt], qa[1], kb[2], kb[3]);
+            ldsm4(vb, &sV[(nt * 8 + (lane & 7)) * PQ + (lane >> 3) * 8]);
+            mma16816(dp[nt], ga[0], vb[0], vb[1]);
+            mma16816(dp[nt], ga[1], vb[2], vb[3]);
+        }
+        const int i0 = w * 16 + g8, i1 = i0 + 8;
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = nt * 8 + tq * 2 + (c & 1);
+                const int i = (c < 2) ? i0 : i1;
+                const bool ok = j < L && (!causal || j <= i);
+                s[nt][c] = ok ? s[nt][c] * kScaleLog2 : -INFINITY;
+                if (c < 2) m0 = fmaxf(m0, s[nt][c]); else m1 = fmaxf(m1, s[nt][c]);
+            }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s[nt][c] = exp2f(s[nt][c] - ((c < 2) ? m0 : m1));          // key 0 is always visible: the max is finite
+                if (c < 2) l0 += s[nt][c]; else l1 += s[nt][c];
+            }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+        float dl0 = 0.0f, dl1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] *= inv0; s[nt][1] *= inv0; s[nt][2] *= inv1; s[nt][3] *= inv1;
+            dl0 = fmaf(s[nt][0], dp[nt][0], fmaf(s[nt][1], dp[nt][1], dl0));
+            dl1 = fmaf(s[nt][2], dp[nt][2], fmaf(s[nt][3], dp[nt][3], dl1));
+        }
+        dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
+        dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+        dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
+        dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+        unsigned dsa[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const unsigned p01 = pack_bf16x2(s[nt][0], s[nt][1]), p23 = pack_bf16x2(s[nt][2], s[nt][3]);
+            const float e0 = s[nt][0] * (dp[nt][0] - dl0) * kScale, e1 = s[nt][1] * (dp[nt][1] - dl0) * kScale;
+            const float e2 = s[nt][2] * (dp[nt][2] - dl1) * kScale, e3 = s[nt][3] * (dp[nt][3] - dl1) * kScale;
+            const unsigned d01 = pack_bf16x2(e0, e1), d23 = pack_bf16x2(e2, e3);
+            const int col = nt * 8 + tq * 2;
+            *reinterpret_cast<unsigned*>(&sP[i0 * PP + col]) = p01;
+            *reinterpret_cast<unsigned*>(&sP[i1 * PP + col]) = p23;
+            *reinterpret_cast<unsigned*>(&sS[i0 * PP + col]) = d01;
+            *reinterpret_cast<unsigned*>(&sS[i1 * PP + col]) = d23;
+            dsa[nt >> 1][(nt & 1) * 2 + 0] = d01;
+            dsa[nt >> 1][(nt & 1) * 2 + 1] = d23;
+        }
+        float o[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[nt][c] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                unsigned kb[4];
+                ldsm4t(kb, &sK[(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PQ + np * 16 + (lane >> 4) * 8]);
+                mma16816(o[np * 2 + 0], dsa[ks], kb[0], kb[1]);
+                mma16816(o[np * 2 + 1], dsa[ks], kb[2], kb[3]);
+            }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int col = hh * 32 + nt * 8 + tq * 2;
+            if (i0 < L) *reinterpret_cast<unsigned*>(&dqkv[(b * L + i0) * 3 * d + col]) = pack_bf16x2(o[nt][0], o[nt][1]);
+            if (i1 < L) *reinterpret_cast<unsigned*>(&dqkv[(b * L + i1) * 3 * d + col]) = pack_bf16x2(o[nt][2], o[nt][3]);
+        }
+    }
+    __syncthreads();
+    {   // ---- phase 2: key block w
+        float dv[4][4], dk[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dv[nt][c] = dk[nt][c] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            unsigned pa[4], sa[4];
+            const int off = (ks * 16 + ((lane >> 4) & 1) * 8 + (lane & 7)) * PP + w * 16 + ((lane >> 3) & 1) * 8;
+            ldsm4t(pa, &sP[off]);
+            ldsm4t(sa, &sS[off]);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                unsigned gb[4], qb[4];
+                const int boff = (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PQ + np * 16 + (lane >> 4) * 8;
+                ldsm4t(gb, &sG[boff]);
+                mma16816(dv[np * 2 + 0], pa, gb[0], gb[1]);
+                mma16816(dv[np * 2 + 1], pa, gb[2], gb[3]);
+                ldsm4t(qb, &sQ[boff]);
+                mma16816(dk[np * 2 + 0], sa, qb[0], qb[1]);
+                mma16816(dk[np * 2 + 1], sa, qb[2], qb[3]);
+            }
+        }
+        const int j0 = w * 16 + g8, j1 = j0 + 8;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int col = hh * 32 + nt * 8 + tq * 2;
+            if (j0 < L) {
+                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j0) * 3 * d + d + col]) = pack_bf16x2(dk[nt][0], dk[nt][1]);
+                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j0) * 3 * d + 2 * d + col]) = pack_bf16x2(dv[nt][0], dv[nt][1]);
+            }
+            if (j1 < L) {
+                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j1) * 3 * d + d + col]) = pack_bf16x2(dk[nt][2], dk[nt][3]);
+                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j1) * 3 * d + 2 * d + col]) = pack_bf16x2(dv[nt][2], dv[nt][3]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Out head backward (denoiser out = Linear(d, D), D <= 4): dh[m, :] = sum_j dy[m, j] W[j, :]  (fp32 + bf16 copies)
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ W, long long M, int d, int D,
                                                        float* __restrict__ dh, __nv_bfloat16* __restrict__ dh16) {
@@ -712,15 +905,21 @@ extern "C" int idb200_ln_film_bwd(const float* da, const float* h, const float* 
     return check_launch("ln_film_bwd_kernel");
 }
 
-extern "C" int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, idb200_stream_t stream) {
+extern "C" int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, int force_simt,
+                                    idb200_stream_t stream) {
     IDB_REQUIRE(qkv && dO && dqkv, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(B > 0 && H > 0, IDB200_EINVAL, "bad shape");
     IDB_REQUIRE(L >= 1 && L <= 64, IDB200_EUNSUPPORTED, "attention backward supports L <= 64 (got %d)", L);
+    IDB_REQUIRE(aligned(qkv, 16) && aligned(dO, 16) && aligned(dqkv, 4), IDB200_EALIGN, "qkv / dO must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (L <= 8) return tb::launch_attn_bwd<8, 1>(qkv, dO, dqkv, B, L, H, causal, st);
     if (L <= 16) return tb::launch_attn_bwd<16, 1>(qkv, dO, dqkv, B, L, H, causal, st);
     if (L <= 32) return tb::launch_attn_bwd<32, 2>(qkv, dO, dqkv, B, L, H, causal, st);
-    return tb::launch_attn_bwd<64, 4>(qkv, dO, dqkv, B, L, H, causal, st);
+    if (force_simt) return tb::launch_attn_bwd<64, 4>(qkv, dO, dqkv, B, L, H, causal, st);
+    tb::attention_bwd_mma_kernel<<<static_cast<unsigned>(B * H), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                                               static_cast<const __nv_bfloat16*>(dO),
+                                                                               static_cast<__nv_bfloat16*>(dqkv), L, H, causal);
+    return check_launch("attention_bwd_mma_kernel");
 }
 
 extern "C" int idb200_head_bwd(const float* dy, const float* W, int64_t M, int d, int D, float* dh, void* dh_bf16, idb200_stream_t stream) {

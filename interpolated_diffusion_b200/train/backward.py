@@ -219,7 +219,7 @@ class EncoderBackprop:
             sc.colsum(dh, grads[p + "attn.out_proj.bias"])
             E.gemm_bf16(dh16, w["wot16"], None, do16, E.EPI_BF16)                       # dO = dh Wo
             dqkv = ws.get("dqkv16", (M, 3 * d), BF16, dev)
-            L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), st)
+            L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), 0, st)
             sc.dweight(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
             sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
             E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_F32)                        # da1 = dqkv Wqkv
