@@ -72,6 +72,10 @@ _SIGS = {
 
 EINVAL, EALIGN, EUNSUPPORTED, ECUDA = -1, -2, -3, -4
 
+# bumped by every in-place parameter update made outside torch's version counters (train/optim.py: the fused AdamW kernel);
+# part of the key of every packed-weight cache (models/_engine.py::_sig)
+PARAM_EPOCH = 0
+
 
 class EmbedDesc(ctypes.Structure):
     """idb200_embed_t (include/idb200.h)."""

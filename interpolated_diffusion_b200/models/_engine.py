@@ -14,7 +14,7 @@ EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2, 3
 
 
 def _sig(params) -> Tuple:
-    return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
+    return (L.PARAM_EPOCH,) + tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
 
 
 def sgemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None, *, act: int = 0,

@@ -380,21 +380,72 @@ class CondEncoderBackprop:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-class InterpLevelBackprop:
-    """``InterpLevelDenoiser.forward`` (denoiser_interp_levels.py:64-84) + its backward."""
+class _DenoiserBackprop:
+    """Shared by both denoisers: cond encoder -> token assembly -> encoder -> out head, and the way back."""
 
     def __init__(self, model):
         self.model = model
         self.sc = _Scratch()
         self.enc = EncoderBackprop(model.transformer, self.sc)
         self.cond = CondEncoderBackprop(model.cond_enc, self.sc) if hasattr(model.cond_enc, "maze") else None
-        self.level = _MLP2(model.level_proj, self.sc)
 
     def param_names(self) -> List[str]:
         return [n for n, _ in self.model.named_parameters()]
 
     def new_grads(self) -> Dict[str, torch.Tensor]:
         return {n: torch.zeros_like(p, dtype=F32) for n, p in self.model.named_parameters()}
+
+    def _cond_rows(self, cond: Dict[str, torch.Tensor]):
+        m = self.model
+        if self.cond is None:
+            raise ValueError("training needs the built-in MazeConditionEncoder")
+        f = lambda t: t.detach().float().contiguous()
+        self.cond_vec = self.cond.forward(cond)
+        return E.sgemm(self.cond_vec, f(m.cond_proj.weight), (f(m.cond_proj.bias) + f(m.in_proj.bias)).contiguous())
+
+    def _encode_and_head(self, h: torch.Tensor, B: int, Lseq: int, D: int) -> torch.Tensor:
+        m = self.model
+        f = lambda t: t.detach().float().contiguous()
+        M, d = h.shape
+        self.enc.forward(h, B, Lseq, self.cond_vec)
+        self.h_final = h
+        self.shape = (B, Lseq, D, d, M)
+        out = torch.empty((B, Lseq, D), device=h.device, dtype=F32)
+        E.out_head(h, f(m.out.weight), f(m.out.bias), out.view(M, D))
+        return out
+
+    def _backward_to_tokens(self, d_out: torch.Tensor, grads: Dict[str, torch.Tensor]):
+        """out head + encoder backward; returns (dh0 fp32 [M,d], its bf16 copy, per-trajectory token sums [B,d], d cond_vec)."""
+        m, sc = self.model, self.sc
+        B, Lseq, D, d, M = self.shape
+        dev = d_out.device
+        st = L.stream(dev)
+        f = lambda t: t.detach().float().contiguous()
+        dy = L.f32c(d_out).view(M, D)
+        sc.narrow_outer(dy, self.h_final, grads["out.weight"])
+        sc.colsum(dy, grads["out.bias"])
+        dh = torch.empty((M, d), device=dev, dtype=F32)
+        dh16 = torch.empty((M, d), device=dev, dtype=BF16)
+        L.call("idb200_head_bwd", dy.data_ptr(), f(m.out.weight).data_ptr(), M, d, D, dh.data_ptr(), dh16.data_ptr(), st)
+        dcond = self.enc.backward(dh, dh16, grads, "transformer.")
+        tok = torch.empty((B, d), device=dev, dtype=F32)
+        L.call("idb200_token_sum", dh.data_ptr(), B, Lseq, d, tok.data_ptr(), st)
+        # every token carries in_proj.bias and cond_proj(cond_vec): their gradients are the per-trajectory token sums
+        sc.colsum(tok, grads["in_proj.bias"])
+        grads["cond_proj.bias"].copy_(grads["in_proj.bias"])
+        sgemm_strided(tok, True, self.cond_vec, True, grads["cond_proj.weight"])
+        if dcond is None:
+            dcond = torch.zeros_like(self.cond_vec)
+        sgemm_strided(tok, False, f(m.cond_proj.weight), True, dcond, accumulate=True)
+        return dh, dh16, tok, dcond
+
+
+class InterpLevelBackprop(_DenoiserBackprop):
+    """``InterpLevelDenoiser.forward`` (denoiser_interp_levels.py:64-84) + its backward."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.level = _MLP2(model.level_proj, self.sc)
 
     def forward(self, x_s: torch.Tensor, s: torch.Tensor, mask: torch.Tensor, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
         m = self.model
@@ -408,12 +459,9 @@ class InterpLevelBackprop:
         f = lambda t: t.detach().float().contiguous()
         # token features [x_s | mask] as fp32 (the in_proj weight gradient reads them back)
         self.feat = torch.cat([L.f32c(x_s).view(M, D), mask.reshape(M, C).to(F32)], dim=1).contiguous()
-        if self.cond is None:
-            raise ValueError("training needs the built-in MazeConditionEncoder")
-        self.cond_vec = self.cond.forward(cond)
+        row_b = self._cond_rows(cond)
         Wf = f(m.in_proj.weight).t().contiguous()
         tab = m._positional_embedding(T, dev, d)
-        row_b = E.sgemm(self.cond_vec, f(m.cond_proj.weight), (f(m.cond_proj.bias) + f(m.in_proj.bias)).contiguous())
         s64 = L.i64c(s)
         self.onehot = torch.zeros((B, m.level_emb.weight.shape[0]), device=dev, dtype=F32)
         self.onehot.scatter_(1, s64.view(B, 1), 1.0)
@@ -421,39 +469,71 @@ class InterpLevelBackprop:
         level_vec = self.level.forward(emb)
         h = torch.empty((M, d), device=dev, dtype=F32)
         E.embed_tokens(self.feat, None, None, Wf, tab, None, level_vec, row_b, h, M, T, d)
-        self.enc.forward(h, B, T, self.cond_vec)
-        self.h_final = h
-        self.shape = (B, T, D, d, M)
-        out = torch.empty((B, T, D), device=dev, dtype=F32)
-        E.out_head(h, f(m.out.weight), f(m.out.bias), out.view(M, D))
-        return out
+        return self._encode_and_head(h, B, T, D)
 
     def backward(self, d_out: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
         """d_out = d loss / d delta_hat [B, T, D]; fills ``grads`` (every parameter of the model)."""
-        m, sc = self.model, self.sc
-        B, T, D, d, M = self.shape
-        dev = d_out.device
-        st = L.stream(dev)
-        f = lambda t: t.detach().float().contiguous()
-        dy = L.f32c(d_out).view(M, D)
-        sc.narrow_outer(dy, self.h_final, grads["out.weight"])
-        sc.colsum(dy, grads["out.bias"])
-        dh = torch.empty((M, d), device=dev, dtype=F32)
-        dh16 = torch.empty((M, d), device=dev, dtype=BF16)
-        L.call("idb200_head_bwd", dy.data_ptr(), f(m.out.weight).data_ptr(), M, d, D, dh.data_ptr(), dh16.data_ptr(), st)
-        dcond = self.enc.backward(dh, dh16, grads, "transformer.")
+        dh, _, tok, dcond = self._backward_to_tokens(d_out, grads)
+        d = dh.shape[1]
         # token assembly: h0 = feat Wf + pos[t] + level_vec[b] + (cond_proj(cond_vec) + biases)[b]
-        dWf = torch.empty((self.feat.shape[1], d), device=dev, dtype=F32)
-        sc.narrow_outer(self.feat, dh, dWf)
+        dWf = torch.empty((self.feat.shape[1], d), device=dh.device, dtype=F32)
+        self.sc.narrow_outer(self.feat, dh, dWf)
         grads["in_proj.weight"].copy_(dWf.t())
-        tok = torch.empty((B, d), device=dev, dtype=F32)
-        L.call("idb200_token_sum", dh.data_ptr(), B, T, d, tok.data_ptr(), st)
-        sc.colsum(tok, grads["in_proj.bias"])
-        grads["cond_proj.bias"].copy_(grads["in_proj.bias"])
-        sgemm_strided(tok, True, self.cond_vec, True, grads["cond_proj.weight"])
-        if dcond is None:
-            dcond = torch.zeros_like(self.cond_vec)
-        sgemm_strided(tok, False, f(m.cond_proj.weight), True, dcond, accumulate=True)
         demb = self.level.backward(tok, grads, "level_proj.")
         sgemm_strided(self.onehot, True, demb, True, grads["level_emb.weight"])
+        self.cond.backward(dcond, grads, "cond_enc.")
+
+
+class KeypointBackprop(_DenoiserBackprop):
+    """``KeypointDenoiser.forward`` (denoiser_keypoints.py:82-113) + its backward (Stage-1 training, train_keypoints.py:505-556)."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.t_embed = _MLP2(model.t_embed, self.sc)
+
+    def forward(self, z_t: torch.Tensor, t: torch.Tensor, idx: torch.Tensor, known_mask: torch.Tensor, cond: Dict[str, torch.Tensor],
+                T: int) -> torch.Tensor:
+        from ..models.denoiser_keypoints import timestep_embedding
+        m = self.model
+        dev = L.require_cuda(z_t, t, idx, known_mask)
+        B, K, D = z_t.shape
+        d = m.in_proj.weight.shape[0]
+        P, Fk = m.pos_dim, m.kp_feat_dim
+        M = B * K
+        f = lambda x: x.detach().float().contiguous()
+        z = L.f32c(z_t).view(M, D)
+        km = known_mask.reshape(M, D).to(F32)
+        if Fk > 0:
+            kp = L.f32c(cond["kp_feat"]).view(M, Fk) if (cond is not None and "kp_feat" in cond) else torch.zeros((M, Fk), device=dev)
+        else:
+            kp = None
+        pos_tab = E.sinusoid(T, P - (P % 2), device=dev)                      # sinusoid(r / max(1, T - 1)), r = 0..T-1
+        if P % 2 == 1:
+            pos_tab = torch.nn.functional.pad(pos_tab, (0, 1))
+        idx64 = L.i64c(idx).view(M)
+        # reference feature order (denoiser_keypoints.py:99-102): [z_t | pos_emb | known_mask | kp_feat]
+        parts = [z, pos_tab[idx64], km] + ([kp] if kp is not None else [])
+        x_full = torch.cat(parts, dim=1)
+        fan_in = x_full.shape[1]
+        self.x16 = torch.zeros((M, _pad64(fan_in)), device=dev, dtype=BF16)
+        self.x16[:, :fan_in] = x_full
+        self.fan_in = fan_in
+        row_b = self._cond_rows(cond)
+        t_vec = self.t_embed.forward(timestep_embedding(L.i64c(t), d))
+        # token assembly by the inference kernel: h0 = [z | kp | km] Wf + (pos_tab W_pos^T)[idx] + t_vec[b] + row_b[b]
+        W = f(m.in_proj.weight)
+        Wf = torch.cat([W[:, :D], W[:, 2 * D + P:], W[:, D + P: 2 * D + P]], dim=1).t().contiguous()
+        tab = E.sgemm(pos_tab[:, :P - (P % 2)].contiguous(), W[:, D: D + P - (P % 2)].contiguous(), None)
+        h = torch.empty((M, d), device=dev, dtype=F32)
+        E.embed_tokens(z, kp, L.u8c(known_mask).view(M, D), Wf, tab, idx64, t_vec, row_b, h, M, K, d)
+        return self._encode_and_head(h, B, K, D)
+
+    def backward(self, d_out: torch.Tensor, grads: Dict[str, torch.Tensor]) -> None:
+        """d_out = d loss / d eps_hat [B, K, D]; fills ``grads``."""
+        dh, dh16, tok, dcond = self._backward_to_tokens(d_out, grads)
+        d = dh.shape[1]
+        dW = self.sc.ws.get("dw_in", (d, self.x16.shape[1]), F32, dh.device)
+        self.sc.dweight(dh16, self.x16, dW)                                   # in_proj.weight: dh0^T [z | pos | km | kp]
+        grads["in_proj.weight"].copy_(dW[:, :self.fan_in])
+        self.t_embed.backward(tok, grads, "t_embed.", want_dx=False)
         self.cond.backward(dcond, grads, "cond_enc.")

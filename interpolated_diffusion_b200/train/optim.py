@@ -102,6 +102,7 @@ class FlatAdamW:
         L.call("idb200_adamw_ema_step", self.flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                L.ptr(self.ema), self.n, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
                float(self.ema_decay if self.ema_decay is not None else 0.0), L.ptr(coef), L.stream(dev))
+        L.PARAM_EPOCH += 1                                  # the kernel wrote the parameters behind torch's version counters
         return None if coef is None else self.norm_coef[0]
 
     def zero_grad(self, set_to_none: bool = True):

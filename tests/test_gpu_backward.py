@@ -268,3 +268,62 @@ def test_stage2_trainer_step(dev):
     # and a full step() with fresh corruption runs end to end
     l2 = tr.step(x0.to(dev), cond, gen)
     assert math.isfinite(float(l2))
+
+
+def test_stage1_backward_and_trainer(dev):
+    """KeypointDenoiser gradients for the Stage-1 loss (train_keypoints.py:526-540) against autograd on the oracle, then a few
+    optimisation steps on a fixed batch."""
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.train.train_keypoints import Stage1Trainer
+    B, T, K = 64, 64, 8
+    torch.manual_seed(0)
+    model = KeypointDenoiser(d_model=128, n_layers=2, n_heads=4, d_ff=256, data_dim=2, kp_feat_dim=3)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    model = model.to(dev)
+    sd = {k: v.detach().cpu().float().clone().requires_grad_() for k, v in model.state_dict().items()}
+    tr = Stage1Trainer(model, T=T, K=K)
+    g = torch.Generator(device="cpu").manual_seed(31)
+    x0 = (0.1 + 0.8 * torch.rand((B, T, 2), generator=g)).to(dev)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=g) < 0.2).float().to(dev), "start_goal": torch.rand((B, 4), generator=g).to(dev),
+            "kp_feat": torch.rand((B, K, 3), generator=g).to(dev)}
+    gen = torch.Generator(device=dev).manual_seed(33)
+    z_t, t, idx, km, eps = tr.build_batch(x0, cond, gen)
+    assert z_t.shape == (B, K, 2) and bool((eps[km] == 0).all())
+    loss = tr.loss_and_grads(z_t, t, idx, km, cond, eps)
+    cpu = lambda v: v.detach().cpu()
+    ref = O.keypoint_denoiser(sd, 4, cpu(z_t), cpu(t), cpu(idx), cpu(km), {k: cpu(v) for k, v in cond.items()}, T)
+    valid = (~cpu(km)).float()
+    ref_loss = (((ref - cpu(eps)) ** 2) * valid).sum() / (valid.sum() + 1e-8)
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss.detach())) < 2e-2 * float(ref_loss.detach())
+    bad = [(k, _rel(tr.grads[k], v.grad)) for k, v in sd.items() if not (_rel(tr.grads[k], v.grad) < 3e-2)]
+    assert not bad, bad
+    losses = [float(loss)]
+    for _ in range(6):
+        tr.opt.step(tr.flat_grad)
+        losses.append(float(tr.loss_and_grads(z_t, t, idx, km, cond, eps)))
+    assert losses[-1] < 0.95 * losses[0], losses
+    assert math.isfinite(float(tr.step(x0, cond, gen)))
+
+
+def test_inference_caches_follow_the_optimizer(dev):
+    """The fused AdamW kernel updates parameters in place behind torch's version counters; the packed-weight caches of the
+    inference modules must still notice (PARAM_EPOCH in their key)."""
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    model = _make_model(dev, 256, 2, 8, 512, (32, 64), 3)
+    x_s, mask, s, cond, target, conf = _batch(64, 64, 3, 5)
+    to = lambda t: t.to(dev)
+    args = (to(x_s), to(s), to(mask), {k: to(v) for k, v in cond.items()})
+    before = model(*args).clone()
+    tr = Stage2Trainer(model, lr=2e-3)
+    for _ in range(3):
+        tr.loss_and_grads(args[0], args[1], args[2], args[3], to(target), to(conf))
+        tr.opt.step(tr.flat_grad)
+    after = model(*args)
+    sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
+    ref = O.interp_level_denoiser(sd, 8, x_s, s, mask, cond)
+    assert float((after.cpu() - ref).abs().max()) < 2e-2 * max(1.0, float(ref.abs().max()))
+    assert float((after - before).abs().max()) > 1e-3
