@@ -347,6 +347,62 @@ def conv_encoder(occ: torch.Tensor, sdf: Optional[torch.Tensor], weights: List[t
     return pooled
 
 
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def conv_weight_matrix(w: torch.Tensor) -> torch.Tensor:
+    """[C_out, C_in, 3, 3] -> bf16 [C_out, pad64(9 C_in)], k = (ky * 3 + kx) * C_in + c (zero K padding)."""
+    co, ci = w.shape[0], w.shape[1]
+    wm = torch.zeros((co, _pad64(9 * ci)), device=w.device, dtype=torch.bfloat16)
+    wm[:, :9 * ci] = w.detach().float().permute(0, 2, 3, 1).reshape(co, 9 * ci).to(torch.bfloat16)
+    return wm
+
+
+def im2col3x3(src: torch.Tensor, B: int, Hh: int, Ww: int, C: int, act: bool, out: torch.Tensor) -> torch.Tensor:
+    L.call("idb200_im2col3x3", src.data_ptr(), B, Hh, Ww, C, out.shape[1], int(act), out.data_ptr(), L.stream(src.device))
+    return out
+
+
+def conv_stack_gemm(x: torch.Tensor, weights: List[torch.Tensor], biases: List[torch.Tensor], ws: "Workspace", keep: bool = False,
+                    chunk: int = 4096):
+    """MazeEncoder conv stack (encoders.py:15-24) of any depth as im2col + tcgen05 GEMM on NHWC bf16 PRE-activations (SiLU is
+    applied when the next layer gathers its patches / by the pooling kernel).  x fp32 [B, C0, H, W] -> pooled fp32 [B, C_last].
+    keep=True also returns (x0 NHWC bf16, [u_l]) for the backward (training batches fit one chunk); otherwise the batch is
+    processed in chunks so the patch matrix stays bounded (4096 trajectories x 441 x 9 C x 2 B)."""
+    B, C0, Hh, Ww = x.shape
+    dev = x.device
+    P = Hh * Ww
+    wms = [conv_weight_matrix(w) for w in weights]
+    x0 = x.permute(0, 2, 3, 1).reshape(B, P, C0).to(torch.bfloat16).contiguous()
+    C_last = weights[-1].shape[0]
+    pooled = torch.empty((B, C_last), device=dev, dtype=torch.float32)
+    if keep:
+        chunk = B
+    us_all = []
+    for lo in range(0, B, chunk):
+        n = min(chunk, B - lo)
+        src, C = x0[lo:lo + n], C0
+        us = []
+        for li, (wm, b) in enumerate(zip(wms, biases)):
+            col = ws.get("col", (n * P, wm.shape[1]), torch.bfloat16, dev)
+            im2col3x3(src, n, Hh, Ww, C, li > 0, col)
+            co = wm.shape[0]
+            u = torch.empty((n * P, co), device=dev, dtype=torch.bfloat16) if keep else ws.get(f"u{li % 2}", (n * P, co), torch.bfloat16, dev)
+            gemm_bf16(col, wm, b, u, EPI_BF16)
+            us.append(u)
+            src, C = u, co
+        L.call("idb200_pool_silu", src.data_ptr(), n, P, C, pooled[lo:lo + n].data_ptr(), L.stream(dev))
+        us_all = us
+    if keep:
+        return pooled, x0, us_all, wms
+    return pooled
+
+
+def conv_gemm_supported(convs) -> bool:
+    return all(c.weight.shape[0] % 32 == 0 and tuple(c.weight.shape[2:]) == (3, 3) for c in convs)
+
+
 def conv_encoder_tc(occ: torch.Tensor, sdf: Optional[torch.Tensor], w0, b0, w1_packed, b1) -> torch.Tensor:
     """Two-layer conv stack on tensor cores (idb200_conv_encoder_tc); w1_packed = bf16 [c2, 9*c1], k = tap*c1 + c."""
     B, _, Hh, Ww = occ.shape

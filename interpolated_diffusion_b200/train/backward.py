@@ -295,10 +295,8 @@ class CondEncoderBackprop:
         self.sg = _MLP2(cond_enc.sg.mlp, scratch) if cond_enc.sg is not None else None
 
     def _col(self, src: torch.Tensor, B: int, Hh: int, Ww: int, C: int, act: bool, name: str) -> torch.Tensor:
-        kpad = _pad64(9 * C)
-        col = self.sc.ws.get(name, (B * Hh * Ww, kpad), BF16, src.device)
-        L.call("idb200_im2col3x3", src.data_ptr(), B, Hh, Ww, C, kpad, int(act), col.data_ptr(), L.stream(src.device))
-        return col
+        col = self.sc.ws.get(name, (B * Hh * Ww, _pad64(9 * C)), BF16, src.device)
+        return E.im2col3x3(src, B, Hh, Ww, C, act, col)
 
     def forward(self, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
         m = self.m
@@ -309,28 +307,11 @@ class CondEncoderBackprop:
             x = torch.cat([occ, L.f32c(cond["sdf"])], dim=1)
         else:
             x = occ
-        B, C0, Hh, Ww = x.shape
-        dev = x.device
+        B, _, Hh, Ww = x.shape
         convs = [c for c in m.maze.convs if isinstance(c, torch.nn.Conv2d)]
-        self.x0 = x.permute(0, 2, 3, 1).reshape(B, Hh * Ww, C0).to(BF16).contiguous()
         self.dims = (B, Hh, Ww)
-        self.us: List[torch.Tensor] = []
-        self.wmats = []
-        src, C = self.x0, C0
-        for li, c in enumerate(convs):
-            w = c.weight.detach().float()
-            co = w.shape[0]
-            kpad = _pad64(9 * C)
-            wm = torch.zeros((co, kpad), device=dev, dtype=BF16)
-            wm[:, :9 * C] = w.permute(0, 2, 3, 1).reshape(co, 9 * C).to(BF16)
-            col = self._col(src, B, Hh, Ww, C, li > 0, "col")
-            u = torch.empty((B * Hh * Ww, co), device=dev, dtype=BF16)
-            E.gemm_bf16(col, wm, c.bias.detach().float().contiguous(), u, E.EPI_BF16)
-            self.us.append(u)
-            self.wmats.append(wm)
-            src, C = u, co
-        self.pooled = torch.empty((B, C), device=dev, dtype=F32)
-        L.call("idb200_pool_silu", src.data_ptr(), B, Hh * Ww, C, self.pooled.data_ptr(), L.stream(dev))
+        self.pooled, self.x0, self.us, self.wmats = E.conv_stack_gemm(
+            x, [c.weight for c in convs], [c.bias.detach().float().contiguous() for c in convs], self.sc.ws, keep=True)
         emb = E.sgemm(self.pooled, m.maze.fc.weight.detach().float().contiguous(), m.maze.fc.bias.detach().float().contiguous())
         if m.use_start_goal:
             if "start_goal" not in cond:

@@ -295,3 +295,25 @@ def test_denoiser_fused_io_matches_separate_kernels(which):
     assert _maxabs(fused, separate) < tol, _maxabs(fused, separate)
     assert _maxabs(head_only, separate) < tol, _maxabs(head_only, separate)
     assert torch.equal(head_only, fused)     # same kernel, bit-identical residual stream
+
+
+@pytest.mark.parametrize("chan,use_sdf,B", [((32, 64, 128, 128), False, 37), ((32, 64, 64), True, 5), ((64,), False, 4100)])
+def test_deep_conv_stack_gemm_vs_oracle(chan, use_sdf, B):
+    """The trainer-default conditioning encoder (maze_channels 32,64,128,128) and other depths: im2col + tcgen05 GEMM per layer
+    (encoders.py:8-25), including a batch larger than one chunk of the patch matrix."""
+    from interpolated_diffusion_b200.models.encoders import MazeConditionEncoder
+    gen = torch.Generator().manual_seed(9)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    if use_sdf:
+        cond["sdf"] = torch.rand((B, 1, 21, 21), generator=gen)
+    torch.manual_seed(2)
+    m = MazeConditionEncoder(use_sdf=use_sdf, d_cond=128, maze_channels=chan)
+    sd = {"cond_enc." + k: v.clone() for k, v in m.state_dict().items()}
+    ref = odn.cond_encoder(sd, cond)
+    m = m.cuda()
+    got = m(_cuda(cond))
+    assert _maxabs(got, ref) < 2e-2 * max(1.0, ref.abs().max().item()), _maxabs(got, ref)
+    m.precision = "fp32"
+    if B <= 64:
+        got = m(_cuda(cond))
+        assert _maxabs(got, ref) < 1e-4, _maxabs(got, ref)
