@@ -151,3 +151,96 @@ def generate(sd_kp, sd_interp, n_heads: int, cond: Dict[str, torch.Tensor], z_T:
         x_hat = sp.apply_clamp(x_hat, x_pred, cm, clamp_dims)
     out["x_hat"] = x_hat
     return out
+
+
+def generate_causal_chunked(sd_kp, sd_interp, n_heads: int, cond: Dict[str, torch.Tensor], *, T: int, chunk: int, K_min: int,
+                            levels: int, idx_chunks: List[np.ndarray], z_T_chunks: List[np.ndarray], D: int = 2,
+                            ddim_steps: int = 20, n_train: int = 1000, beta_schedule: str = "cosine", logit_space: bool = False,
+                            logit_eps: float = 1e-5, recompute_vel: bool = True, clamp_endpoints: bool = True,
+                            clamp_policy: str = "endpoints", clamp_dims: str = "pos") -> np.ndarray:
+    """The chunk loop of ``src/sample/sample_generate_causal.py:485-583`` (long-horizon causal generation), restated for a
+    batch: the reference runs it sample by sample (B = 1) but every quantity that shapes the loop (cur, end, local_T, full_len)
+    depends only on T and chunk, so the samples advance in lockstep with identical per-sample arithmetic.  The random anchors
+    of each chunk (``sample_fixed_k_indices_batch``, :511) and the DDIM noise (:194) are inputs.  PARITY NOTE: this chunk loop
+    is restated from the source, not pinned against a run of the live script (its ``main`` needs the D4RL datasets); every
+    function it composes (DDIM sampler, interpolation, denoisers, clamps) is pinned by the golden vectors."""
+    B = cond["start_goal"].shape[0]
+    schedule = df.make_alpha_bars(df.make_beta_schedule(beta_schedule, n_train))
+    sg = cond["start_goal"].numpy().astype(F32)
+    start, goal = sg[:, :2], sg[:, 2:]
+    x_gen = np.zeros((B, T, D), F32)
+    x_gen[:, 0, :2] = start                                                    # :493-496
+    cur, c = 1, 0
+    while cur < T:                                                             # :504
+        end = min(T - 1, cur + chunk - 1)
+        L = end - cur + 1
+        remaining = T - cur
+        left = x_gen[:, cur - 1, :2].copy()
+        if end == T - 1:
+            right = goal.copy()
+        else:                                                                  # _heuristic_right, :86-88
+            frac = F32(min(1.0, float(L) / max(1, remaining)))
+            right = (left + frac * (goal - left)).astype(F32)
+        local_T = L + 1
+        idx = idx_chunks[c].astype(np.int64)
+        mask_local = kf._mask_from_idx(idx, local_T)
+        K = idx.shape[1]
+        known_mask = np.zeros((B, K, D), bool)
+        known_values = np.zeros((B, K, D), F32)
+        if clamp_endpoints:                                                    # :516-524
+            first, last = (idx == 0)[..., None], (idx == local_T - 1)[..., None]
+            known_mask[:, :, :2] = first | last
+            known_values[:, :, :2] = np.where(first, left[:, None, :], known_values[:, :, :2])
+            known_values[:, :, :2] = np.where(last, right[:, None, :], known_values[:, :, :2])
+        if logit_space:
+            known_values = sp.logit_pos(known_values, eps=logit_eps)
+        cond_chunk = dict(cond)
+        cond_chunk["start_goal"] = _t(np.concatenate([left, right], axis=1).astype(F32))          # :528-529
+        z_hat = sample_keypoints_ddim(sd_kp, n_heads, schedule, idx, known_mask, known_values, cond_chunk, ddim_steps, local_T,
+                                      z_T_chunks[c], schedule_name="linear")
+        if logit_space:
+            z_hat = sp.sigmoid_pos(z_hat)
+        x_s = kf.interpolate_from_indices(idx, z_hat, local_T, recompute_velocity=recompute_vel)   # :555
+        full_len = end + 1                                                      # :558-566
+        x_full = np.zeros((B, full_len, D), F32)
+        mask_full = np.zeros((B, full_len), bool)
+        if cur > 1:
+            x_full[:, :cur - 1] = x_gen[:, :cur - 1]
+            mask_full[:, :cur - 1] = True
+        x_full[:, cur - 1:full_len] = x_s
+        mask_full[:, cur - 1:full_len] = mask_local
+        delta = dn.interp_level_denoiser(sd_interp, n_heads, _t(x_full), torch.full((B,), levels), _t(mask_full), cond_chunk,
+                                         causal=True).numpy()
+        x_hat = (x_full + delta).astype(F32)
+        if clamp_policy == "all_anchors":
+            clamp_mask = mask_full
+        elif clamp_policy == "endpoints":
+            clamp_mask = np.zeros_like(mask_full)
+            clamp_mask[:, cur - 1] = True
+            clamp_mask[:, full_len - 1] = True
+        else:
+            clamp_mask = None
+        if clamp_mask is not None:
+            x_hat = sp.apply_clamp(x_hat, x_full, clamp_mask, clamp_dims)
+        x_gen[:, cur:end + 1, :2] = x_hat[:, cur:end + 1, :2]                   # :583-585
+        if D > 2 and recompute_vel:
+            x_gen[:, cur:end + 1, 2:] = x_hat[:, cur:end + 1, 2:]
+        cur = end + 1
+        c += 1
+    if D > 2 and recompute_vel:                                                 # :632-638
+        pos = x_gen[:, :, :2]
+        v = np.zeros_like(pos)
+        v[:, :-1] = (pos[:, 1:] - pos[:, :-1]) / F32(1.0 / float(T))
+        x_gen = np.concatenate([pos, v], axis=-1).astype(F32)
+    return x_gen
+
+
+def causal_chunk_plan(T: int, chunk: int, K_min: int):
+    """(cur, end, local_T, K) of every chunk of the loop above."""
+    plan, cur = [], 1
+    while cur < T:
+        end = min(T - 1, cur + chunk - 1)
+        local_T = end - cur + 2
+        plan.append((cur, end, local_T, min(K_min, local_T)))
+        cur = end + 1
+    return plan

@@ -187,3 +187,82 @@ def test_generation_graph_equals_eager_and_is_batch_invariant():
     sg = cond["start_goal"]
     # (through logit -> DDIM known-value clamp -> sigmoid: a few ulp of round trip)
     assert (whole[:, 0, :2] - sg[:, :2]).abs().max().item() < 2e-5 and (whole[:, -1, :2] - sg[:, 2:]).abs().max().item() < 2e-5
+
+
+def test_generate_long_horizon_causal_cfg5():
+    """BASELINE configs[4] shape: T = 256, K = 32, levels = 4 (K schedule [256,256,128,64,32]), causal Stage-2 denoiser, tiny
+    random-init models.  fp32 check mode free-running against the CPU oracle's whole pipeline; bf16 mode teacher-forced from
+    the same keypoints (Stage-2 jump + clamps within 2e-2)."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels_causal import InterpLevelCausalDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, generate
+    from oracle import denoiser_torch as odn
+    B, T, K, S, D = 3, 256, 32, 4, 2
+    gen = torch.Generator().manual_seed(13)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    torch.manual_seed(3)
+    kp = KeypointDenoiser(data_dim=D, **TINY)
+    il = InterpLevelCausalDenoiser(data_dim=D, max_levels=S, mask_channels=2, **TINY)
+    sd_kp = {k: v.clone() for k, v in kp.state_dict().items()}
+    sd_il = {k: v.clone() for k, v in il.state_dict().items()}
+    kp, il = kp.cuda(), il.cuda()
+    ccond = {k: v.cuda() for k, v in cond.items()}
+    z_T = torch.randn((B, K, D), generator=gen)
+    cfg = GenerationConfig(T=T, K_min=K, levels=S, ddim_steps=6)
+    ref = og.generate(sd_kp, sd_il, 2, cond, z_T.numpy(), T=T, K_min=K, levels=S, D=D, ddim_steps=6, causal=True)
+    kp.precision = il.precision = "fp32"
+    out = generate(kp, il, ccond, cfg, z_T=z_T.cuda(), return_all=True)
+    assert np.array_equal(out["idx"].cpu().numpy(), ref["idx"])
+    np.testing.assert_allclose(out["x_pred"].cpu().numpy(), ref["x_pred"], atol=3e-3, rtol=0)
+    np.testing.assert_allclose(out["x_hat"].cpu().numpy(), ref["x_hat"], atol=3e-3, rtol=0)
+    # bf16: Stage-2 continuation from the CUDA path's own x_pred
+    kp.precision = il.precision = "bf16"
+    out = generate(kp, il, ccond, cfg, z_T=z_T.cuda(), return_all=True)
+    x_pred = out["x_pred"].cpu().numpy()
+    idx, masks = okf.sample_fixed_k_indices_uniform_batch(B, T, K)
+    conf = osp.build_anchor_conf(masks, masks, True, 0.95, 0.5, 1.0, 0.0, True)
+    mask_in = np.stack([masks.astype(np.float32), osp.anneal_conf(conf, S, S, "linear")], axis=-1)
+    delta = odn.interp_level_denoiser(sd_il, 2, torch.from_numpy(x_pred), torch.full((B,), S), torch.from_numpy(mask_in), cond, causal=True).numpy()
+    x_hat = (x_pred + delta).astype(np.float32)
+    x_hat = osp.apply_soft_clamp(x_hat, x_pred, conf, 1.0, "pos")
+    cm = np.zeros_like(masks); cm[:, 0] = cm[:, -1] = True
+    x_hat = osp.apply_clamp(x_hat, x_pred, cm, "pos")
+    assert np.abs(out["x_hat"].cpu().numpy() - x_hat).max() < 2e-2
+
+
+@pytest.mark.parametrize("T,chunk,K,policy", [(64, 16, 8, "endpoints"), (50, 16, 8, "all_anchors"), (40, 12, 6, "none")])
+def test_causal_chunked_generation_vs_oracle(T, chunk, K, policy):
+    """Batched chunk loop of sample_generate_causal.py:485-583 (Stage-1 on each chunk, causal Stage-2 over prefix + chunk):
+    fp32 check mode against the CPU restatement with the same anchors and DDIM noise per chunk (tiny models)."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels_causal import InterpLevelCausalDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.sample.sample_generate_causal import chunk_plan, generate_causal_chunked
+    B, D, S = 3, 2, 3
+    gen = torch.Generator().manual_seed(19)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": 0.1 + 0.8 * torch.rand((B, 4), generator=gen)}
+    torch.manual_seed(4)
+    kp = KeypointDenoiser(data_dim=D, **TINY)
+    il = InterpLevelCausalDenoiser(data_dim=D, max_levels=S, mask_channels=1, **TINY)
+    sd_kp = {k: v.clone() for k, v in kp.state_dict().items()}
+    sd_il = {k: v.clone() for k, v in il.state_dict().items()}
+    kp, il = kp.cuda(), il.cuda()
+    kp.precision = il.precision = "fp32"
+    plan = chunk_plan(T, chunk, K)
+    assert plan == og.causal_chunk_plan(T, chunk, K)
+    idx_chunks, z_chunks = [], []
+    for (_, _, local_T, k) in plan:
+        # random strictly-increasing anchors with both endpoints
+        rows = [np.sort(np.concatenate([[0, local_T - 1], 1 + torch.randperm(local_T - 2, generator=gen)[:k - 2].numpy()])) for _ in range(B)]
+        idx_chunks.append(np.stack(rows).astype(np.int64))
+        z_chunks.append(torch.randn((B, k, D), generator=gen))
+    ref = og.generate_causal_chunked(sd_kp, sd_il, 2, cond, T=T, chunk=chunk, K_min=K, levels=S, idx_chunks=idx_chunks,
+                                     z_T_chunks=[z.numpy() for z in z_chunks], D=D, ddim_steps=5, clamp_policy=policy, logit_space=True)
+    got = generate_causal_chunked(kp, il, {k: v.cuda() for k, v in cond.items()}, T=T, chunk=chunk, K_min=K, levels=S, data_dim=D,
+                                  ddim_steps=5, clamp_policy=policy, logit_space=True, idx_chunks=[torch.from_numpy(i).cuda() for i in idx_chunks],
+                                  z_T_chunks=[z.cuda() for z in z_chunks])
+    assert got.shape == (B, T, D)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, atol=3e-3, rtol=0)
+    # the free-running batched call (own anchors / noise) runs and respects the endpoint clamp of the first chunk
+    out = generate_causal_chunked(kp, il, {k: v.cuda() for k, v in cond.items()}, T=T, chunk=chunk, K_min=K, levels=S, ddim_steps=3,
+                                  logit_space=True, generator=torch.Generator(device="cuda").manual_seed(1))
+    assert torch.isfinite(out).all() and torch.equal(out[:, 0, :2].cpu(), cond["start_goal"][:, :2])
