@@ -381,6 +381,12 @@ int idb200_im2col3x3(const void* src, int64_t B, int H, int W, int C, int Kpad, 
 int idb200_pool_silu(const void* u, int64_t B, int P, int C, float* pooled, idb200_stream_t stream);
 int idb200_pool_silu_bwd(const void* u, const float* dpooled, int64_t B, int P, int C, void* du, idb200_stream_t stream);
 
+/* DP anchor placement, src/selection/epiplexity_dp.py:171-228 (dp_select_indices_batch): the producer of idx for
+ * kp_index_mode = dp.  C fp32 [B,T,T] segment costs (inf = no segment); idx int64 [B,K], 2 <= K <= T, idx[:,0] = 0,
+ * idx[:,K-1] = T-1, minimising sum C[idx[k-1], idx[k]] with torch.argmin's first-minimum tie rule (bit-identical indices).
+ * status int32 [B]: 0 ok, 1 no finite path to T-1, 2 backtrack failed (the reference raises RuntimeError for both). */
+int idb200_dp_select(const float* C, int64_t B, int T, int K, int64_t* idx, int* status, idb200_stream_t stream);
+
 /* Batched trajectory metrics, src/eval/metrics.py:68-128 (compute_metrics_batch; _pos_to_cell :13-24): the step right after
  * the generation path (the reference loops over samples on the host, sample_generate.py:1323-1398).
  *   occ fp32 [B,H,W] (occ_stride = H*W, or 0 to broadcast one map); traj fp32 [B,T,D], dims 0:2 = (x, y) in [0,1];

@@ -295,3 +295,17 @@ def test_generate_tiny(golden):
     out = og.generate(sd_kp, sd_il3, 2, cond, g["z_T"], T=T, K_min=K, levels=S, D=D, stage2_mode="adj",
                       masks_levels=g["adj_masks_levels"])
     np.testing.assert_allclose(out["x_hat"], g["x_hat_adj"], atol=2e-3, rtol=0)
+
+
+def test_dp_select_oracle_matches_live_reference_golden():
+    """oracle/selection_np.py against indices produced by the live reference (tests/golden/make_golden_dp.py)."""
+    import os
+    import numpy as np
+    from oracle import selection_np as osel
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dp_select.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) == 5
+    for n in names:
+        idx = osel.dp_select_indices_batch(g[n + "/C"], int(g[n + "/K"]))
+        assert np.array_equal(idx, g[n + "/idx"]), n
+        assert (idx[:, 0] == 0).all() and (idx[:, -1] == g[n + "/C"].shape[1] - 1).all() and (np.diff(idx, axis=1) > 0).all()
