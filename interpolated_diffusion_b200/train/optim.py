@@ -105,6 +105,74 @@ class FlatAdamW:
         L.PARAM_EPOCH += 1                                  # the kernel wrote the parameters behind torch's version counters
         return None if coef is None else self.norm_coef[0]
 
+    # ---- torch.optim.AdamW-compatible state (src/utils/checkpoint.py:21-22, 41-42 save / restore ``optimizer.state_dict()``) -------
+    def state_dict(self) -> dict:
+        """Same structure as ``torch.optim.AdamW(params).state_dict()``: per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``
+        (copies) and one param group, so a checkpoint written here resumes under the reference's optimizer and vice versa."""
+        group = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=self.lr, betas=self.betas, eps=self.eps,
+                                  weight_decay=self.weight_decay).state_dict()["param_groups"][0]
+        group["params"] = list(range(len(self.params)))
+        state = {}
+        if self.step_count > 0:
+            for i, (m, v) in enumerate(zip(self.views(self.exp_avg), self.views(self.exp_avg_sq))):
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        g = groups[0]
+        self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"]), float(g["weight_decay"])
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, (m, v) in enumerate(zip(self.views(self.exp_avg), self.views(self.exp_avg_sq))):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            m.copy_(st["exp_avg"])
+            v.copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ; the fused step keeps one count for the whole arena")
+        self.step_count = steps.pop() if steps else 0
+
+    @property
+    def ema_state(self) -> "EMAState":
+        """An object with the reference EMA's ``state_dict`` / ``load_state_dict`` / ``copy_to`` (src/utils/ema.py:19-35)."""
+        if self.ema is None:
+            raise ValueError("this optimizer was built without an EMA")
+        return EMAState(self)
+
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
             p.grad = None if set_to_none else (p.grad.zero_() if p.grad is not None else None)
+
+
+class EMAState:
+    """View of the EMA arena with the interface of ``src/utils/ema.py``'s ``EMA`` (what save_checkpoint / load_checkpoint use)."""
+
+    def __init__(self, opt: FlatAdamW):
+        self.opt = opt
+
+    @property
+    def decay(self) -> float:
+        return float(self.opt.ema_decay)
+
+    @property
+    def shadow(self) -> List[torch.Tensor]:
+        return self.opt.ema_shadow
+
+    def copy_to(self, parameters: Iterable[torch.nn.Parameter]) -> None:
+        for p, s in zip([p for p in parameters if p.requires_grad], self.shadow):
+            p.data.copy_(s)
+        L.PARAM_EPOCH += 1
+
+    def state_dict(self) -> dict:
+        return {"decay": self.decay, "shadow": [t.clone() for t in self.shadow]}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.opt.ema_decay = state["decay"]
+        for dst, src in zip(self.shadow, state["shadow"]):
+            dst.copy_(src)

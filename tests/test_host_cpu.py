@@ -88,3 +88,33 @@ def test_schedule_tables_and_timesteps_host(golden):
             assert np.array_equal(got, g[key]), key
     assert ddpm._timesteps(1000, 20, "quadratic").tolist() == \
         [999, 896, 799, 708, 622, 542, 467, 398, 334, 276, 224, 177, 135, 99, 69, 44, 24, 11, 2, 0]
+
+
+def test_checkpoint_and_samples_formats(tmp_path):
+    """On-disk formats of the reference (checkpoint.py:6-49 payload keys; samples.npz keys of sample_generate.py:1665-1689):
+    pure host logic, exercised with a plain torch module / optimizer."""
+    import numpy as np
+    import torch
+    from interpolated_diffusion_b200.sample.io import save_samples_npz
+    from interpolated_diffusion_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+    m = torch.nn.Linear(4, 3)
+    opt = torch.optim.AdamW(m.parameters(), lr=2e-4)
+    m(torch.ones(2, 4)).sum().backward()
+    opt.step()
+    p = str(tmp_path / "ckpt.pt")
+    save_checkpoint(p, m, opt, 7, meta={"stage": "interp_levels", "T": 64})
+    payload = torch.load(p)
+    assert set(payload) == {"model", "step", "optimizer", "meta"} and payload["step"] == 7
+    m2 = torch.nn.Linear(4, 3)
+    opt2 = torch.optim.AdamW(m2.parameters(), lr=1.0)
+    step, pl = load_checkpoint(p, m2, opt2, return_payload=True)
+    assert step == 7 and torch.equal(m2.weight, m.weight) and opt2.param_groups[0]["lr"] == 2e-4 and pl["meta"]["T"] == 64
+    save_checkpoint(p, m, opt, 8, save_optimizer=False)
+    assert set(torch.load(p)) == {"model", "step"}
+    n, T, K, D = 5, 64, 8, 2
+    path = save_samples_npz(str(tmp_path), interp=torch.zeros(n, T, D), refined=torch.ones(n, T, D), keypoints=torch.zeros(n, K, D),
+                            idx=torch.zeros(n, K, dtype=torch.long), mask=torch.zeros(n, T, dtype=torch.bool), start_goal=torch.zeros(n, 4),
+                            occ=torch.zeros(n, 21, 21))
+    z = np.load(path)
+    assert set(z.files) == {"interp", "refined", "keypoints", "idx", "mask", "start_goal", "occ"}
+    assert z["idx"].dtype == np.int64 and z["mask"].dtype == np.bool_ and z["refined"].shape == (n, T, D)

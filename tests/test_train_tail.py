@@ -65,3 +65,45 @@ def test_cuda_loss_clip_adamw_ema_vs_golden(golden):
     assert (np.abs(opt2.ema_shadow[0].cpu().numpy() - er) <= 2.4e-7 * np.maximum(1.0, np.abs(er))).all()
     with pytest.raises(ValueError):
         stage2_loss(torch.zeros((2, 3, 2)).cuda(), torch.zeros((2, 3, 2)).cuda(), torch.zeros((2, 4)).cuda())
+
+
+@pytest.mark.gpu
+def test_flat_adamw_state_dict_interchanges_with_torch_adamw(tmp_path):
+    """FlatAdamW.state_dict() has torch.optim.AdamW's structure: resume a torch AdamW from it (and back) and take one more step
+    on both sides with the same gradients -> same parameters; EMA state round-trips through save/load_checkpoint."""
+    import torch
+    from interpolated_diffusion_b200.train.optim import FlatAdamW
+    from interpolated_diffusion_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.SiLU(), torch.nn.Linear(32, 5)).to(dev)
+    ref = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.SiLU(), torch.nn.Linear(32, 5)).to(dev)
+    ref.load_state_dict(net.state_dict())
+    opt = FlatAdamW(net.parameters(), lr=1e-3, max_grad_norm=None)
+    g = torch.Generator(device=dev).manual_seed(1)
+    for _ in range(3):
+        for p in net.parameters():
+            p.grad = torch.randn(p.shape, device=dev, generator=g)
+        opt.step()
+    p = str(tmp_path / "c.pt")
+    save_checkpoint(p, net, opt, 3, ema=opt.ema_state)
+    topt = torch.optim.AdamW(ref.parameters(), lr=5.0)
+    assert load_checkpoint(p, ref, topt) == 3                       # torch's AdamW accepts the state
+    assert topt.param_groups[0]["lr"] == 1e-3 and float(topt.state[next(iter(ref.parameters()))]["step"]) == 3.0
+    grads = [torch.randn(q.shape, device=dev, generator=g) for q in net.parameters()]
+    for q, gr in zip(net.parameters(), grads):
+        q.grad = gr.clone()
+    for q, gr in zip(ref.parameters(), grads):
+        q.grad = gr.clone()
+    opt.step()
+    topt.step()
+    for a, b in zip(net.parameters(), ref.parameters()):
+        assert float((a - b).abs().max()) <= 2.4e-7 * max(1.0, float(b.abs().max()))
+    # and back: a FlatAdamW resumes from torch's state dict; EMA shadow restored
+    net2 = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.SiLU(), torch.nn.Linear(32, 5)).to(dev)
+    opt2 = FlatAdamW(net2.parameters(), lr=9.0, max_grad_norm=None)
+    save_checkpoint(p, ref, topt, 4, ema=opt.ema_state)
+    assert load_checkpoint(p, net2, opt2, ema=opt2.ema_state) == 4
+    assert opt2.step_count == 4 and opt2.lr == 1e-3
+    assert all(torch.equal(a, b) for a, b in zip(opt2.ema_shadow, opt.ema_shadow))
+    assert all(float((a - b).abs().max()) <= 2.4e-7 * max(1.0, float(b.abs().max())) for a, b in zip(opt2.views(opt2.exp_avg), opt.views(opt.exp_avg)))
