@@ -64,12 +64,20 @@ constexpr int kBiasFloats = 2048;       // bias vector staged in shared memory (
 
 enum { EPI_BF16 = 0, EPI_SILU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3 };
 
-template <int BN>
+// kPair: two CTAs of a cluster work on one [256 x BN] tile with tcgen05 cta_group::2: each CTA stages its own 128 rows of A but
+// only BN/2 rows of W, so the L2 -> shared-memory fill per flop drops by (128 + BN) / (128 + BN/2) (the unpaired kernel is bound
+// by that fill: 40 KB per k-block at BN = 192 against 72 B/ns per SM measured -> at most ~49 % of the tensor peak).
+template <int BN, bool kPair = false>
 struct GemmCfg {
-    static constexpr int kStageBytes = kBM * kBK * 2 + BN * kBK * 2;
-    static constexpr int kStages = (BN <= 128) ? 6 : 4;
+    static constexpr int kBRows = kPair ? BN / 2 : BN;                       // rows of W staged by one CTA
+    static constexpr int kStageBytes = kBM * kBK * 2 + kBRows * kBK * 2;
+    // shared memory: [ring | barriers 256 | bias 8 KB | pad | 4 x 16 KB output staging slabs (TMA-store epilogue)]
+    static constexpr int kStagingBytes = 4 * 16384;
+    static constexpr int kFixedBytes = 1024 /*align*/ + 256 /*barriers*/ + kBiasFloats * 4 + 1024 /*align*/ + kStagingBytes;
+    static constexpr int kFit = (227 * 1024 - kFixedBytes) / kStageBytes;
+    static constexpr int kStages = kFit < 8 ? kFit : 8;
     static constexpr int kAccStages = (2 * BN <= 512) ? 2 : 1;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kBiasFloats * 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
 };
 
 struct GemmParams {
@@ -78,6 +86,7 @@ struct GemmParams {
     long long M;
     int N, K, epilogue;
     int splits;             // split-K: tile = (split, m, n); split s covers K/splits of the reduction, out += s * M * N (EPI_F32)
+    int tma_out;            // 1: the epilogue stages 16 KB slabs in shared memory and writes them with TMA (tmap_out)
 };
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU (tanh.approx, rel. error ~2^-11, below the bf16
@@ -94,10 +103,11 @@ __device__ __forceinline__ float silu_f(float x) {
 // the weight-gradient form dW = dY^T X with the tokens as K: TMA boxes are [64 tokens x 64 features] (one SW128 atom column),
 // an operand tile is a row of such boxes 8 KB apart (descriptor LBO), 8-token groups 1 KB apart (SBO), and one UMMA_K = 16
 // tokens advances the start address by 2 KB.
-template <int BN, bool kMN>
+template <int BN, bool kMN, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+    using Cfg = GemmCfg<BN, kPair>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     __builtin_assume(__isShared(smem));             // keep LDS / STS (the integer round trip hides the address space)
@@ -108,14 +118,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* acc_empty = acc_full + Cfg::kAccStages;       // [kAccStages] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::kAccStages);
     float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+    uint8_t* staging = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem + Cfg::kStages * Cfg::kStageBytes + 256 + kBiasFloats * 4) + 1023) & ~static_cast<uintptr_t>(1023));
+    __builtin_assume(__isShared(staging));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tiles = p.N / BN;
-    const long long m_tiles = (p.M + kBM - 1) / kBM;
+    // pair mode: a "tile" is a pair of 128-row M tiles; CTA `rank` of the cluster owns rows (2 * pm + rank) * 128
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const long long m_tiles = kPair ? (p.M + 2 * kBM - 1) / (2 * kBM) : (p.M + kBM - 1) / kBM;
     const long long mn_tiles = m_tiles * n_tiles;
     const long long tiles = mn_tiles * p.splits;
     const int k_blocks = p.K / kBK / p.splits;             // per split
+    const long long tile0 = kPair ? blockIdx.x / 2 : blockIdx.x;
+    const long long tile_stride = kPair ? gridDim.x / 2 : gridDim.x;
+    constexpr int kMRows = kPair ? 2 * kBM : kBM;          // rows of one scheduling tile
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -123,18 +141,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPair ? 16 : 8); }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if constexpr (kPair) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     const bool bias_smem = p.bias != nullptr && p.N <= kBiasFloats;
     if (bias_smem)
         for (int i = threadIdx.x; i < p.N; i += kGemmThreads) sbias[i] = p.bias[i];
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();               // the peer's barriers must exist before remote arrives / TMA credits
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -143,15 +162,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (long long tile = tile0; tile < tiles; tile += tile_stride) {
                 const long long mn = tile % mn_tiles;
                 const int kb0 = static_cast<int>(tile / mn_tiles) * k_blocks;
-                const int m0 = static_cast<int>(mn / n_tiles) * kBM;
-                const int n0 = static_cast<int>(mn % n_tiles) * BN;
+                const int m0 = static_cast<int>(mn / n_tiles) * kMRows + static_cast<int>(rank) * kBM;
+                const int n0 = static_cast<int>(mn % n_tiles) * BN + static_cast<int>(rank) * Cfg::kBRows * (kPair ? 1 : 0);
                 for (int kb = kb0; kb < kb0 + k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + kBM * kBK * 2;
+                    if constexpr (kPair) {
+                        // both CTAs' bytes are credited to the even CTA's barrier (it issues the pair MMA)
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        if constexpr (kMN) {
+#pragma unroll
+                            for (int hb = 0; hb < kBM / 64; ++hb) tma_load_2d_2sm(sa + hb * 8192, &tmap_a, &full_bar[stage], m0 + hb * 64, kb * kBK);
+#pragma unroll
+                            for (int hb = 0; hb < Cfg::kBRows / 64; ++hb) tma_load_2d_2sm(sb + hb * 8192, &tmap_w, &full_bar[stage], n0 + hb * 64, kb * kBK);
+                        } else {
+                            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+                            tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], kb * kBK, n0);
+                        }
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     if constexpr (kMN) {
 #pragma unroll
@@ -167,14 +201,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN) | (kMN ? ((1u << 15) | (1u << 16)) : 0u);
+        // ===== MMA issuer =====  (the whole warp walks the schedule; one elected lane issues: tcgen05 instructions inside a
+        // divergent `if (lane == 0)` compile to ELECT / BRA.U.ANY waterfall loops of ~100 cycles each, which made the issue of a
+        // k-block (4 MMAs + commit) as long as its execution)
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kMRows, BN) | (kMN ? ((1u << 15) | (1u << 16)) : 0u);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            for (long long tile = tile0; tile < tiles; tile += tile_stride) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1, 2);      // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -185,13 +221,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint64_t adesc = kMN ? umma_desc_sw128_mn(sa) : umma_desc_sw128(sa);
                     const uint64_t bdesc = kMN ? umma_desc_sw128_mn(sa + kBM * kBK * 2) : umma_desc_sw128(sa + kBM * kBK * 2);
                     constexpr int kStep = kMN ? 128 : 2;            // 16-byte units per UMMA_K
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)
-                        umma_bf16(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);                // smem slot free once these MMAs retire
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            if constexpr (kPair) umma_bf16_2sm(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb | k) ? 1u : 0u);
+                            else umma_bf16(d_tmem, adesc + kStep * k, bdesc + kStep * k, idesc, (kb | k) ? 1u : 0u);
+                        }
+                        if constexpr (kPair) umma_commit_2sm(&empty_bar[stage]);   // both CTAs' slots free once these MMAs retire
+                        else umma_commit(&empty_bar[stage]);       // smem slot free once these MMAs retire
+                    }
+                    __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&acc_full[acc]);                       // accumulator complete
+                if (elect_one_sync()) {
+                    if constexpr (kPair) umma_commit_2sm(&acc_full[acc]);
+                    else umma_commit(&acc_full[acc]);              // accumulator complete
+                }
+                __syncwarp();
                 if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -202,14 +248,85 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int q = ew & 3, half = ew >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        uint32_t slab_it = 0;
+        for (long long tile = tile0; tile < tiles; tile += tile_stride) {
             const long long mn = tile % mn_tiles;
-            const long long m0 = (mn / n_tiles) * kBM;
+            const long long m0 = (mn / n_tiles) * kMRows + static_cast<long long>(rank) * kBM;
             const int n0 = static_cast<int>(mn % n_tiles) * BN;
             mbar_wait(&acc_full[acc], acc_phase, 4);
             tc_fence_after();
             const long long row = m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            if (p.tma_out) {
+                // Coalesced epilogue.  A thread owns one ROW of the accumulator (tcgen05.ld 32x32b), so direct stores touch 32
+                // different lines per instruction: measured, they (not the MMAs) bounded the kernel at ~45 % of its store-less
+                // speed.  Instead each half (4 warps = 128 rows) fills a 16 KB slab (64 bf16 / 32 fp32 columns, SWIZZLE_128B
+                // rows) in shared memory and one thread hands it to TMA (store, or reduce-add for the residual epilogue); two
+                // slabs per half ping-pong so the conversion of slab i+1 overlaps the store of slab i.
+                const bool out16 = p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16;
+                const int slab_cols = out16 ? 64 : 32;
+                const int n_slabs = BN / slab_cols;
+                const int r_in = q * 32 + lane;
+                uint8_t* stage_h = staging + half * 2 * 16384;
+                for (int sl = half; sl < n_slabs; sl += 2) {
+                    uint8_t* buf = stage_h + (slab_it & 1) * 16384;
+                    if (q == 0 && lane == 0) tma_store_wait_read<1>();          // the store that last read `buf` is done with it
+                    named_barrier_sync(1 + half, 128);
+                    const int nch = out16 ? 2 : 1;
+                    for (int cc = 0; cc < nch; ++cc) {
+                        const int c = sl * slab_cols + cc * 32;
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + c, r);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        if (bias_smem) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 bv = *reinterpret_cast<const float4*>(&sbias[n0 + c + 4 * j]);
+                                v[4 * j + 0] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+                            }
+                        } else if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c + j);
+                        }
+                        if (out16) {
+                            if (p.epilogue == EPI_SILU_BF16) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 pk;
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                const int piece = cc * 4 + j;
+                                *reinterpret_cast<uint4*>(buf + r_in * 128 + ((piece ^ (r_in & 7)) << 4)) = pk;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(buf + r_in * 128 + ((j ^ (r_in & 7)) << 4)) =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_barrier_sync(3 + half, 128);
+                    if (q == 0 && lane == 0) {
+                        if (p.epilogue == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, buf, n0 + sl * slab_cols, static_cast<int>(m0));
+                        else tma_store_2d(&tmap_out, buf, n0 + sl * slab_cols, static_cast<int>(m0));
+                        tma_store_commit();
+                    }
+                    ++slab_it;
+                }
+            } else {
 #pragma unroll 1
             for (int c = half * 32; c < BN; c += 64) {
                 uint32_t r[32];
@@ -269,34 +386,82 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
             }
+            }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (lane == 0) {
+                if constexpr (kPair) mbar_arrive_leader(&acc_empty[acc]);      // the even CTA's issuer waits for both epilogues
+                else mbar_arrive(&acc_empty[acc]);
+            }
             if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_out && q == 0 && lane == 0) tma_store_wait_all();           // stores complete before the CTA exits
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (kPair) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
-template <int BN, bool kMN = false>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
+static bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IDB200_GEMM_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <int BN, bool kMN, bool kPair>
+static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kMN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
-    const long long tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN) * p.splits;
-    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    gemm_bf16_tn_kernel<BN, kMN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, p);
-    return check_launch("gemm_bf16_tn_kernel");
+    const long long rows = kPair ? 2 * kBM : kBM;
+    const long long tiles = ((p.M + rows - 1) / rows) * (p.N / BN) * p.splits;
+    if constexpr (kPair) {
+        const int clusters = static_cast<int>(tiles < num_sms() / 2 ? tiles : num_sms() / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, kMN, true>, ta, tw, to, p);
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaLaunchKernelEx(gemm pair): %s", cudaGetErrorString(e));
+        return check_launch("gemm_bf16_tn_kernel<pair>");
+    } else {
+        const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+        gemm_bf16_tn_kernel<BN, kMN, false><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, to, p);
+        return check_launch("gemm_bf16_tn_kernel");
+    }
+}
+
+// pair mode needs BN / 2 rows of W per CTA to be whole swizzle atoms (K-major: 8 rows; MN-major: 64-feature boxes) and at least
+// two M tiles of work
+template <int BN, bool kMN = false>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tw_half, const CUtensorMap& to, const GemmParams& p,
+                       cudaStream_t st) {
+    constexpr bool can_pair = kMN ? (BN % 128 == 0) : (BN % 64 == 0);
+    if constexpr (can_pair) {
+        if (pair_enabled() && p.M > kBM) return launch_gemm_impl<BN, kMN, true>(ta, tw_half, to, p, st);
+    }
+    return launch_gemm_impl<BN, kMN, false>(ta, tw, to, p, st);
 }
 
 // out[s] [M,N] fp32 = A[K_s, M]^T W[K_s, N] for the s-th slice of the K rows (MN-major operands, see the kernel comment)
@@ -315,12 +480,12 @@ int gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, long long 
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tw, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), 64, 64);
     if (rc) return rc;
-    GemmParams p{nullptr, partial, M, N, static_cast<int>(K), EPI_F32, splits};
-    switch (BN) {
-        case 256: return launch_gemm<256, true>(ta, tw, p, st);
-        case 192: return launch_gemm<192, true>(ta, tw, p, st);
-        case 128: return launch_gemm<128, true>(ta, tw, p, st);
-        default: return launch_gemm<64, true>(ta, tw, p, st);
+    GemmParams p{nullptr, partial, M, N, static_cast<int>(K), EPI_F32, splits, 0};
+    switch (BN) {                                           // MN-major boxes are [64 x 64] in both modes: same tensor map
+        case 256: return launch_gemm<256, true>(ta, tw, tw, ta, p, st);
+        case 192: return launch_gemm<192, true>(ta, tw, tw, ta, p, st);
+        case 128: return launch_gemm<128, true>(ta, tw, tw, ta, p, st);
+        default: return launch_gemm<64, true>(ta, tw, tw, ta, p, st);
     }
 }
 
@@ -343,14 +508,28 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint32_t>(BN), kBK);
     if (rc) return rc;
-    GemmParams p{bias, out, M, N, K, epilogue, splits};
+    CUtensorMap tw_half = tw;                               // pair mode: each CTA stages BN / 2 rows of W
+    if (BN % 64 == 0) {
+        rc = make_tmap_bf16_2d(&tw_half, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint32_t>(BN / 2), kBK);
+        if (rc) return rc;
+    }
+    // TMA-store epilogue: 16 KB slabs of 64 bf16 / 32 fp32 columns (N % 64 == 0 covers both); split-K partials keep the direct stores
+    static const bool tma_epi = !(getenv("IDB200_GEMM_TMA_EPI") && getenv("IDB200_GEMM_TMA_EPI")[0] == '0');
+    const bool out16 = epilogue == EPI_BF16 || epilogue == EPI_SILU_BF16;
+    const int use_tma = (tma_epi && splits == 1 && BN % 64 == 0 && M < (1ll << 31)) ? 1 : 0;
+    CUtensorMap to = ta;
+    if (use_tma) {
+        rc = make_tmap_2d(&to, out, out16 ? 2 : 4, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kBM, out16 ? 64 : 32);
+        if (rc) return rc;
+    }
+    GemmParams p{bias, out, M, N, K, epilogue, splits, use_tma};
     switch (BN) {
-        case 256: return launch_gemm<256>(ta, tw, p, st);
-        case 192: return launch_gemm<192>(ta, tw, p, st);
-        case 128: return launch_gemm<128>(ta, tw, p, st);
-        case 96: return launch_gemm<96>(ta, tw, p, st);
-        case 64: return launch_gemm<64>(ta, tw, p, st);
-        default: return launch_gemm<32>(ta, tw, p, st);
+        case 256: return launch_gemm<256>(ta, tw, tw_half, to, p, st);
+        case 192: return launch_gemm<192>(ta, tw, tw_half, to, p, st);
+        case 128: return launch_gemm<128>(ta, tw, tw_half, to, p, st);
+        case 96: return launch_gemm<96>(ta, tw, tw_half, to, p, st);
+        case 64: return launch_gemm<64>(ta, tw, tw_half, to, p, st);
+        default: return launch_gemm<32>(ta, tw, tw_half, to, p, st);
     }
 }
 

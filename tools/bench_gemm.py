@@ -5,8 +5,11 @@ import torch
 from interpolated_diffusion_b200 import _lib as L
 
 res = {}
-for (M, N, K, epi) in [(524288, 768, 256, 0), (524288, 256, 256, 2), (524288, 1024, 256, 1), (524288, 256, 1024, 2),
-                       (4194304, 768, 256, 0), (4194304, 1024, 256, 1), (4194304, 256, 1024, 2)]:
+SHAPES = [(524288, 768, 256, 0), (524288, 256, 256, 2), (524288, 1024, 256, 1), (524288, 256, 1024, 2),
+          (4194304, 768, 256, 0), (4194304, 1024, 256, 1), (4194304, 256, 1024, 2)]
+if len(sys.argv) > 1:                                   # "M,N,K,epi;M,N,K,epi;..."
+    SHAPES = [tuple(int(v) for v in t.split(",")) for t in sys.argv[1].split(";")]
+for (M, N, K, epi) in SHAPES:
     A = torch.randn((M, K), device="cuda").bfloat16()
     W = torch.randn((N, K), device="cuda").bfloat16()
     bias = torch.randn((N,), device="cuda")
