@@ -442,7 +442,9 @@ class InterpLevelBackprop(_DenoiserBackprop):
         self.feat = torch.cat([L.f32c(x_s).view(M, D), mask.reshape(M, C).to(F32)], dim=1).contiguous()
         row_b = self._cond_rows(cond)
         Wf = f(m.in_proj.weight).t().contiguous()
-        tab = m._positional_embedding(T, dev, d)
+        if getattr(self, "_tab_key", None) != (T, d, dev):              # input-independent table: built once (host linspace)
+            self._tab, self._tab_key = m._positional_embedding(T, dev, d), (T, d, dev)
+        tab = self._tab
         s64 = L.i64c(s)
         self.onehot = torch.zeros((B, m.level_emb.weight.shape[0]), device=dev, dtype=F32)
         self.onehot.scatter_(1, s64.view(B, 1), 1.0)

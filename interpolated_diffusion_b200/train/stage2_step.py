@@ -30,7 +30,7 @@ class Stage2Trainer:
                  recompute_vel: bool = True, pos_clip: bool = False, pos_clip_min: float = 0.0, pos_clip_max: float = 1.0,
                  level_sampling: str = "high", level_high_prob: float = 0.5, w_anchor: float = 0.1, w_missing: float = 1.0,
                  lr: float = 2e-4, weight_decay: float = 1e-2, grad_clip: Optional[float] = 1.0, ema: bool = True,
-                 ema_decay: float = 0.999, process_group=None):
+                 ema_decay: float = 0.999, process_group=None, cuda_graph: bool = False):
         if stage2_mode not in ("adj", "x0"):
             raise ValueError("stage2_mode must be 'adj' or 'x0'")
         self.model = model
@@ -52,6 +52,10 @@ class Stage2Trainer:
         self.grads: Dict[str, torch.Tensor] = {n: by_id[id(p)] for n, p in model.named_parameters() if id(p) in by_id}
         self.pg = process_group
         self.last_grad_norm: Optional[torch.Tensor] = None
+        # cuda_graph: forward + loss + backward (~700 launches for the 12-layer model) are captured once per batch shape and
+        # replayed; batch building (host-side level counts), the all-reduce and the optimiser (host-side step count) stay eager
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
 
     # ------------------------------------------------------------------------------------------------------------------
     def build_batch(self, x0: torch.Tensor, gen: torch.Generator) -> Tuple[torch.Tensor, ...]:
@@ -93,6 +97,27 @@ class Stage2Trainer:
         self.bp.backward(dgrad, self.grads)
         return loss * world if world > 1 else loss
 
+    def _graphed_loss_and_grads(self, x_s, s_idx, mask_in, cond, target, weight_mask) -> torch.Tensor:
+        args = [x_s, s_idx, mask_in, target, weight_mask] + [cond[k] for k in sorted(cond)]
+        sig = tuple((tuple(a.shape), a.dtype) for a in args)
+        if self._graph is None or self._graph["sig"] != sig:
+            static = [a.clone() for a in args]
+            scond = {k: static[5 + i] for i, k in enumerate(sorted(cond))}
+            stream = torch.cuda.Stream()
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):                         # warm-up on the side stream (kernel attributes, workspaces)
+                for _ in range(2):
+                    self.loss_and_grads(static[0], static[1], static[2], scond, static[3], static[4])
+            torch.cuda.current_stream().wait_stream(stream)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self.loss_and_grads(static[0], static[1], static[2], scond, static[3], static[4])
+            self._graph = {"sig": sig, "g": g, "static": static, "loss": loss}
+        for dst, src in zip(self._graph["static"], args):
+            dst.copy_(src)
+        self._graph["g"].replay()
+        return self._graph["loss"]
+
     def reduce_gradients(self) -> None:
         """Data-parallel all-reduce of the flat gradient arena (each rank's gradient already carries 1 / world)."""
         P.all_reduce_sum_(self.flat_grad, self.pg)
@@ -101,7 +126,8 @@ class Stage2Trainer:
         """One full training step; returns the (local) loss as a 0-dim device tensor (no host sync)."""
         batch = self.build_batch(x0, gen)
         x_s, s_idx, mask_in, target, weight_mask = batch
-        loss = self.loss_and_grads(x_s, s_idx, mask_in, cond, target, weight_mask)
+        fn = self._graphed_loss_and_grads if self.cuda_graph else self.loss_and_grads
+        loss = fn(x_s, s_idx, mask_in, cond, target, weight_mask)
         self.reduce_gradients()
         self.last_grad_norm = self.opt.step(self.flat_grad)
         return loss

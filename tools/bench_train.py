@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--graph", type=int, default=0, help="1: forward + loss + backward replayed as one CUDA graph")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -57,12 +58,17 @@ def main():
         ev[0].record()
         x_s, s_idx, mask_in, target, wm = tr.build_batch(x0, gen)
         ev[1].record()
-        delta = tr.bp.forward(x_s, s_idx, mask_in, cond)
-        ev[2].record()
-        from interpolated_diffusion_b200.train.optim import stage2_loss
-        loss, dgrad = stage2_loss(delta, target, wm, anchor_conf=True, w_anchor=0.1, w_missing=1.0, grad_accum=world)
-        ev[3].record()
-        tr.bp.backward(dgrad, tr.grads)
+        if a.graph:
+            ev[2].record()
+            ev[3].record()
+            loss = tr._graphed_loss_and_grads(x_s, s_idx, mask_in, cond, target, wm)      # phases: all under "backward"
+        else:
+            delta = tr.bp.forward(x_s, s_idx, mask_in, cond)
+            ev[2].record()
+            from interpolated_diffusion_b200.train.optim import stage2_loss
+            loss, dgrad = stage2_loss(delta, target, wm, anchor_conf=True, w_anchor=0.1, w_missing=1.0, grad_accum=world)
+            ev[3].record()
+            tr.bp.backward(dgrad, tr.grads)
         ev[4].record()
         tr.reduce_gradients()
         ev[5].record()
@@ -79,7 +85,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
     res = {"config": f"stage2 train step, {a.model} model, B={B}/GPU x {world} GPU, T=64, adj, anchor_conf", "ms_per_step": ms,
-           "traj_per_s": B * world / ms * 1e3, "tflops_per_gpu": B * gf_per_traj / ms, "loss": float(loss) * world,
+           "traj_per_s": B * world / ms * 1e3, "tflops_per_gpu": B * gf_per_traj / ms, "loss": float(loss) * (1 if a.graph else world), "cuda_graph": bool(a.graph),
            "phases_ms": {n: acc[n] / a.steps for n in names}, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
     if rank == 0:
         print(json.dumps(res))
