@@ -118,3 +118,18 @@ def test_checkpoint_and_samples_formats(tmp_path):
     z = np.load(path)
     assert set(z.files) == {"interp", "refined", "keypoints", "idx", "mask", "start_goal", "occ"}
     assert z["idx"].dtype == np.int64 and z["mask"].dtype == np.bool_ and z["refined"].shape == (n, T, D)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the shipped package may import it (tests/, __graft_entry__.smoke() and
+    bench.py's CPU-baseline arm are the only users)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "interpolated_diffusion_b200")
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    bad = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py") and pat.search(open(os.path.join(d, f), encoding="utf-8").read()):
+                bad.append(os.path.join(d, f))
+    assert not bad, bad
