@@ -357,7 +357,9 @@ int idb200_silu_f32(const float* u, const float* g, int64_t n, int mode, float* 
  * updated dh, dgb[b] = [dgamma | dbeta] (NULL iff gamma_beta is NULL), dwb_part [B, 2d] = per-trajectory [dw | db] partials. */
 int idb200_ln_film_bwd(const float* da, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
                        int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb, int64_t dgb_stride,
-                       float* dwb_part, idb200_stream_t stream);
+                       float* dwb_part, float* stats_scratch, idb200_stream_t stream);
+/* stats_scratch: fp32 [B*L, 4] (16-byte aligned) selects the two-pass form (row scalars by a warp per token, then a thread per
+ * column over the trajectory's tokens: coalesced, low register count); NULL runs the one-block-per-trajectory kernel. */
 /* Backward of the packed-QKV multi-head attention (head_dim 32, L <= 64): qkv, dqkv bf16 [B*L, 3d]; dO bf16 [B*L, d].
  * 32 < L <= 64 runs on mma.sync tensor cores (P and dS rounded to bf16 for the second products, as the forward rounds P);
  * force_simt != 0 selects the fp32 shared-memory kernel that serves L <= 32. */

@@ -234,6 +234,97 @@ __global__ void __launch_bounds__(256) ln_film_bwd_kernel(const float* __restric
     }
 }
 
+// Two-pass form of the same backward (the default): the one-block-per-trajectory kernel above keeps 4 x d/32 accumulators per
+// lane (128 registers, 25 % occupancy) and ran at 1.7 TB/s.  Pass A: a warp per token reduces the four row scalars
+// (mean, rstd, mean(dxhat), mean(dxhat * xhat)) -> stats[M, 4].  Pass B: a thread per COLUMN walks the L tokens of its
+// trajectory: fully coalesced, no shuffles, ~32 registers; accumulates the column's dgamma / dbeta / dw / db and updates dh.
+template <int kPerLane>
+__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(const float* __restrict__ da, const float* __restrict__ h,
+                                                           const float* __restrict__ ln_w, const float* __restrict__ gb, long long gb_stride,
+                                                           int L, long long M, float4* __restrict__ stats) {
+    constexpr int d = kPerLane * 32;
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    float w[kPerLane];
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) w[j] = ln_w[lane + 32 * j];
+    for (long long m = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+        const long long b = m / L;
+        const long long row = m * d;
+        float x[kPerLane], g[kPerLane];
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            x[j] = h[row + lane + 32 * j];
+            g[j] = da[row + lane + 32 * j];
+            if (gb) g[j] *= 1.0f + gb[b * gb_stride + lane + 32 * j];
+            g[j] *= w[j];                                   // dxhat
+            s += x[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / d);
+        float v = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            x[j] -= mean;
+            v += x[j] * x[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float rstd = rsqrtf(v * (1.0f / d) + 1e-5f);
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            s1 += g[j];
+            s2 = fmaf(g[j], x[j] * rstd, s2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) stats[m] = make_float4(mean, rstd, s1 * (1.0f / d), s2 * (1.0f / d));
+    }
+}
+
+__global__ void __launch_bounds__(128) ln_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ h,
+                                                           const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                           const float* __restrict__ gb, long long gb_stride, int L, int d,
+                                                           const float4* __restrict__ stats, float* __restrict__ dh,
+                                                           __nv_bfloat16* __restrict__ dh16, float* __restrict__ dgb, long long dgb_stride,
+                                                           float* __restrict__ dwb_part) {
+    const long long b = blockIdx.y;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= d) return;
+    const float w = ln_w[c], bb = ln_b[c];
+    const float g1 = gb ? 1.0f + gb[b * gb_stride + c] : 1.0f;
+    float a_dg = 0.0f, a_db = 0.0f, a_dw = 0.0f, a_dbb = 0.0f;
+#pragma unroll 4
+    for (int t = 0; t < L; ++t) {
+        const long long m = b * L + t;
+        const float4 st = stats[m];                         // broadcast load
+        const long long o = m * d + c;
+        const float xh = (h[o] - st.x) * st.y;
+        const float g = da[o];
+        const float n = fmaf(xh, w, bb);
+        const float dn = g * g1;
+        a_dg = fmaf(g, n, a_dg);
+        a_db += g;
+        a_dw = fmaf(dn, xh, a_dw);
+        a_dbb += dn;
+        const float v2 = dh[o] + st.y * (dn * w - st.z - xh * st.w);
+        dh[o] = v2;
+        if (dh16) dh16[o] = __float2bfloat16_rn(v2);
+    }
+    if (dgb) {
+        dgb[b * dgb_stride + c] = a_dg;
+        dgb[b * dgb_stride + d + c] = a_db;
+    }
+    dwb_part[b * 2 * d + c] = a_dw;
+    dwb_part[b * 2 * d + d + c] = a_dbb;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Backward of softmax(q k^T / sqrt(32)) v for one (trajectory, head) per block (nn.MultiheadAttention inside
 // transformer.py:39, head_dim 32, L <= 64): recompute P, then dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(P o dP)),
@@ -888,7 +979,7 @@ extern "C" int idb200_silu_f32(const float* u, const float* g, int64_t n, int mo
 
 extern "C" int idb200_ln_film_bwd(const float* da, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
                                   int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb, int64_t dgb_stride,
-                                  float* dwb_part, idb200_stream_t stream) {
+                                  float* dwb_part, float* stats_scratch, idb200_stream_t stream) {
     IDB_REQUIRE(da && h && ln_w && ln_b && dh && dwb_part, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE((gamma_beta == nullptr) == (dgb == nullptr), IDB200_EINVAL, "gamma_beta and dgb must be given together");
     IDB_REQUIRE(B > 0 && L > 0, IDB200_EINVAL, "bad shape");
@@ -896,6 +987,24 @@ extern "C" int idb200_ln_film_bwd(const float* da, const float* h, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     __nv_bfloat16* d16 = static_cast<__nv_bfloat16*>(dh_bf16);
     const unsigned grid = static_cast<unsigned>(B);
+    if (stats_scratch) {                                    // two-pass form: stats_scratch fp32 [B*L, 4], 16-byte aligned
+        IDB_REQUIRE(aligned(stats_scratch, 16), IDB200_EALIGN, "stats_scratch must be 16-byte aligned");
+        const long long M = B * L;
+        float4* stats = reinterpret_cast<float4*>(stats_scratch);
+        const int g1 = grid_for(M * 32, 256, 8);
+        switch (d / 32) {
+            case 4: tb::ln_bwd_stats_kernel<4><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+            case 8: tb::ln_bwd_stats_kernel<8><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+            case 12: tb::ln_bwd_stats_kernel<12><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+            default: tb::ln_bwd_stats_kernel<16><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+        }
+        int rc = check_launch("ln_bwd_stats_kernel");
+        if (rc) return rc;
+        IDB_REQUIRE(B <= 65535, IDB200_EUNSUPPORTED, "two-pass LayerNorm backward takes at most 65535 trajectories per call");
+        tb::ln_bwd_apply_kernel<<<dim3((d + 127) / 128, grid), 128, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, d, stats, dh, d16, dgb,
+                                                                            dgb_stride, dwb_part);
+        return check_launch("ln_bwd_apply_kernel");
+    }
     switch (d / 32) {
         case 4: tb::ln_film_bwd_kernel<4><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;
         case 8: tb::ln_film_bwd_kernel<8><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;

@@ -188,6 +188,7 @@ class EncoderBackprop:
         do16 = ws.get("do16", (M, d), BF16, dev)
         dwb = ws.get("dwb", (B, 2 * d), F32, dev)
         dwb_sum = ws.get("dwb_sum", (2 * d,), F32, dev)
+        stats = ws.get("ln_stats", (M, 4), F32, dev)
         dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
         st = L.stream(dev)
 
@@ -196,7 +197,7 @@ class EncoderBackprop:
             dg = dgb[:, j] if film is not None else None
             L.call("idb200_ln_film_bwd", da.data_ptr(), h_saved.data_ptr(), nw.data_ptr(), nb.data_ptr(), L.ptr(gb),
                    0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), dh16.data_ptr(), L.ptr(dg),
-                   0 if dg is None else dg.stride(0), dwb.data_ptr(), st)
+                   0 if dg is None else dg.stride(0), dwb.data_ptr(), stats.data_ptr(), st)
             sc.colsum(dwb, dwb_sum)
             grads[name + ".weight"].copy_(dwb_sum[:d])
             grads[name + ".bias"].copy_(dwb_sum[d:])

@@ -106,8 +106,9 @@ def test_small_fp32_backward_kernels(dev):
     assert _rel(BW.silu_f32(u.to(dev), g=gg.to(dev)), ur.grad) < 2e-6
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("d,Lseq,with_film", [(128, 8, True), (256, 64, True), (384, 64, True), (256, 16, False)])
-def test_ln_film_backward_matches_autograd(dev, d, Lseq, with_film):
+def test_ln_film_backward_matches_autograd(dev, d, Lseq, with_film, two_pass):
     from interpolated_diffusion_b200 import _lib as L
     g = torch.Generator(device="cpu").manual_seed(3)
     B = 6
@@ -127,8 +128,9 @@ def test_ln_film_backward_matches_autograd(dev, d, Lseq, with_film):
     dwb = torch.empty((B, 2 * d), device=dev)
     gbd = gb.detach().to(dev) if with_film else None
     da_d, h_d, w_d, b_d = da.to(dev), h.detach().to(dev), w.detach().to(dev), b.detach().to(dev)
+    stats = torch.empty((B * Lseq, 4), device=dev) if two_pass else None
     L.call("idb200_ln_film_bwd", da_d.data_ptr(), h_d.data_ptr(), w_d.data_ptr(), b_d.data_ptr(), L.ptr(gbd), 2 * d if with_film else 0, B, Lseq, d, dh.data_ptr(), dh16.data_ptr(), L.ptr(dgb),
-           2 * d if with_film else 0, dwb.data_ptr(), L.stream(dev))
+           2 * d if with_film else 0, dwb.data_ptr(), L.ptr(stats), L.stream(dev))
     assert _rel(dh.view(B, Lseq, d), dh0 + h.grad) < 2e-5
     assert _rel(dh16.view(B, Lseq, d), dh0 + h.grad) < 4e-3
     assert _rel(dwb.sum(0)[:d], w.grad) < 2e-5 and _rel(dwb.sum(0)[d:], b.grad) < 2e-5
