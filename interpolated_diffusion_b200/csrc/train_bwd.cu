@@ -102,6 +102,49 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const TIn* __restri
     }
 }
 
+// vector form: a thread owns kV consecutive columns (one 16-byte load per row); block = 32 column groups x 8 row lanes
+template <typename TIn, int kV>
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const TIn* __restrict__ src, long long M, int N, long long rows_per_slice,
+                                                                 float* __restrict__ partial) {
+    __shared__ float sh[8][32 * kV + 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * 32 + tx) * kV;
+    const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slice;
+    long long r1 = r0 + rows_per_slice;
+    if (r1 > M) r1 = M;
+    float acc[kV];
+#pragma unroll
+    for (int j = 0; j < kV; ++j) acc[j] = 0.0f;
+    if (c0 < N) {
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + r * N + c0);
+            if constexpr (kV == 8) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
+            } else {
+                acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kV; ++j) sh[ty][tx * kV + j] = acc[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * kV; c += 256) {
+        const int col = blockIdx.x * 32 * kV + c;
+        if (col < N) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += sh[w][c];
+            partial[static_cast<long long>(blockIdx.y) * N + col] = t;
+        }
+    }
+}
+
 // out[w] (+)= scale * sum_r partial[r, w]   (fixed order)
 __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partial, int R, long long W, float scale,
                                                           int accumulate, float* __restrict__ out) {
@@ -128,6 +171,30 @@ __global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat162* __restr
             o = make_float2(gv.x * silu_grad(uv.x), gv.y * silu_grad(uv.y));
         }
         y[i] = __floats2bfloat162_rn(o.x, o.y);
+    }
+}
+
+// 16-byte (8 x bf16) form of the same kernel for n % 8 == 0 and 16-byte aligned pointers
+__global__ void __launch_bounds__(256) silu_vec_kernel(const uint4* __restrict__ u, const uint4* g, long long n8, int mode, uint4* y) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        uint4 uv = u[i];
+        uint4 gv = mode ? g[i] : make_uint4(0u, 0u, 0u, 0u);
+        __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&uv);
+        __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&gv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = __bfloat1622float2(u2[j]);
+            float2 o;
+            if (mode == 0) {
+                o = make_float2(silu_fwd(a.x), silu_fwd(a.y));
+            } else {
+                const float2 b = __bfloat1622float2(g2[j]);
+                o = make_float2(b.x * silu_grad(a.x), b.y * silu_grad(a.y));
+            }
+            u2[j] = __floats2bfloat162_rn(o.x, o.y);
+        }
+        y[i] = uv;
     }
 }
 
@@ -858,6 +925,60 @@ __global__ void __launch_bounds__(256) im2col3x3_vec_kernel(const __nv_bfloat16*
     }
 }
 
+// row-blocked form: a block takes kRows consecutive patch rows; a thread keeps its (tap, channel-group) fixed across them, so the
+// integer divisions happen once per thread and once per row instead of once per 16-byte element
+constexpr int kIm2colRows = 16;
+__global__ void __launch_bounds__(256) im2col3x3_rows_kernel(const __nv_bfloat16* __restrict__ src, long long rows_total, int Hh, int Ww, int C,
+                                                             int Kpad, int act, __nv_bfloat16* __restrict__ col) {
+    __shared__ long long s_base[kIm2colRows];              // element offset of (b, y, x, 0) in src
+    __shared__ int s_y[kIm2colRows], s_x[kIm2colRows];
+    const int P = Hh * Ww;
+    const int kv = Kpad / 8;
+    const long long row0 = static_cast<long long>(blockIdx.x) * kIm2colRows;
+    if (threadIdx.x < kIm2colRows) {
+        const long long row = row0 + threadIdx.x;
+        if (row < rows_total) {
+            const long long b = row / P;
+            const int p = static_cast<int>(row - b * P);
+            s_y[threadIdx.x] = p / Ww;
+            s_x[threadIdx.x] = p % Ww;
+            s_base[threadIdx.x] = (b * P + p) * C;
+        }
+    }
+    __syncthreads();
+    const int kvs = kv < 256 ? kv : 256;                   // threads along the patch row; the rest of the block strides over rows
+    const int lanes_r = 256 / kvs;
+    const int rl = threadIdx.x / kvs;
+    if (rl >= lanes_r) return;
+    for (int k8 = threadIdx.x % kvs; k8 < kv; k8 += kvs) {
+        const int kk = k8 * 8;
+        const bool live = kk < 9 * C;
+        const int tap = live ? kk / C : 0;
+        const int c = kk - tap * C;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const long long doff = static_cast<long long>(dy * Ww + dx) * C + c;
+#pragma unroll 4
+        for (int r = rl; r < kIm2colRows; r += lanes_r) {
+            const long long row = row0 + r;
+            if (row >= rows_total) break;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            const int y = s_y[r] + dy, x = s_x[r] + dx;
+            if (live && y >= 0 && y < Hh && x >= 0 && x < Ww) {
+                val = *reinterpret_cast<const uint4*>(src + s_base[r] + doff);
+                if (act) {
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(h2[j]);
+                        h2[j] = __floats2bfloat162_rn(silu_fwd(f.x), silu_fwd(f.y));
+                    }
+                }
+            }
+            *reinterpret_cast<uint4*>(col + row * Kpad + kk) = val;
+        }
+    }
+}
+
 // pooled[b, c] = mean_p silu(u[b, p, c])
 __global__ void __launch_bounds__(128) pool_silu_kernel(const __nv_bfloat16* __restrict__ u, int P, int C, float* __restrict__ pooled) {
     const long long b = blockIdx.x;
@@ -938,16 +1059,30 @@ extern "C" int idb200_colsum(const void* src, int src_kind, int64_t M, int N, fl
     IDB_REQUIRE(src_kind >= 0 && src_kind <= 1, IDB200_EINVAL, "src_kind: 0 fp32, 1 bf16");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cb = (N + 31) / 32;
-    const int S = tb::slices_for(M, cb);
-    const long long rps = (M + S - 1) / S;
-    const dim3 grid(cb, S);
-    if (src_kind == 0)
-        tb::colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), M, N, rps, scratch);
-    else
-        tb::colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), M, N, rps, scratch);
+    const int S = tb::slices_for(M, cb);                   // (the scratch is sized for this, the larger, slice count)
+    const int kV = src_kind == 0 ? 4 : 8;
+    int S_used = S;
+    if (N % kV == 0 && aligned(src, 16)) {
+        const int cbv = (N + 32 * kV - 1) / (32 * kV);
+        S_used = tb::slices_for(M, cbv);
+        if (S_used > S) S_used = S;
+        const long long rps = (M + S_used - 1) / S_used;
+        const dim3 grid(cbv, S_used);
+        if (src_kind == 0)
+            tb::colsum_partial_vec_kernel<float, 4><<<grid, 256, 0, st>>>(static_cast<const float*>(src), M, N, rps, scratch);
+        else
+            tb::colsum_partial_vec_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), M, N, rps, scratch);
+    } else {
+        const long long rps = (M + S - 1) / S;
+        const dim3 grid(cb, S);
+        if (src_kind == 0)
+            tb::colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), M, N, rps, scratch);
+        else
+            tb::colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), M, N, rps, scratch);
+    }
     int rc = check_launch("colsum_partial_kernel");
     if (rc) return rc;
-    tb::reduce_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, S, N, scale, accumulate, out);
+    tb::reduce_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, S_used, N, scale, accumulate, out);
     return check_launch("reduce_rows_kernel");
 }
 
@@ -964,6 +1099,11 @@ extern "C" int idb200_silu_bf16(const void* u, const void* g, int64_t n, int mod
     IDB_REQUIRE(n >= 0 && n % 2 == 0, IDB200_EINVAL, "element count must be even");
     IDB_REQUIRE(mode == 0 || mode == 1, IDB200_EINVAL, "mode: 0 forward, 1 backward");
     if (n == 0) return IDB200_OK;
+    if (n % 8 == 0 && aligned(u, 16) && aligned(y, 16) && (mode == 0 || aligned(g, 16))) {
+        tb::silu_vec_kernel<<<grid_for(n / 8, 256 * 2, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const uint4*>(u), static_cast<const uint4*>(g), n / 8, mode, static_cast<uint4*>(y));
+        return check_launch("silu_vec_kernel");
+    }
     tb::silu_kernel<<<grid_for(n / 2, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat162*>(u), static_cast<const __nv_bfloat162*>(g), n / 2, mode, static_cast<__nv_bfloat162*>(y));
     return check_launch("silu_kernel");
@@ -1079,6 +1219,13 @@ extern "C" int idb200_im2col3x3(const void* src, int64_t B, int H, int W, int C,
     IDB_REQUIRE(src && col, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Kpad >= 9 * C, IDB200_EINVAL, "bad shape");
     if (C % 8 == 0 && Kpad % 8 == 0 && aligned(src, 16) && aligned(col, 16)) {
+        const long long rows = B * H * W;
+        const long long blocks = (rows + tb::kIm2colRows - 1) / tb::kIm2colRows;
+        if (Kpad / 8 >= 64 && blocks < (1ll << 31)) {
+            tb::im2col3x3_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                static_cast<const __nv_bfloat16*>(src), rows, H, W, C, Kpad, act, static_cast<__nv_bfloat16*>(col));
+            return check_launch("im2col3x3_rows_kernel");
+        }
         tb::im2col3x3_vec_kernel<<<grid_for(B * H * W * (Kpad / 8), 256 * 2, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(src), B, H, W, C, Kpad, act, static_cast<__nv_bfloat16*>(col));
         return check_launch("im2col3x3_vec_kernel");
