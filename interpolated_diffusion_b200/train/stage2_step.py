@@ -20,6 +20,38 @@ from .backward import InterpLevelBackprop
 from .optim import FlatAdamW, stage2_loss
 
 
+class GraphedStep:
+    """Replays ``fn(*tensors)`` (a forward + loss + backward that writes into fixed gradient buffers and returns the loss) as one
+    CUDA graph per input signature: inputs are copied into static buffers, ~700 launches become one replay."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.state = None
+
+    def __call__(self, tensors, cond):
+        keys = sorted(cond)
+        args = list(tensors) + [cond[k] for k in keys]
+        sig = tuple((tuple(a.shape), a.dtype) for a in args)
+        if self.state is None or self.state["sig"] != sig:
+            static = [a.clone() for a in args]
+            n = len(tensors)
+            scond = {k: static[n + i] for i, k in enumerate(keys)}
+            stream = torch.cuda.Stream()
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):                         # warm-up on a side stream (kernel attributes, workspaces)
+                for _ in range(2):
+                    self.fn(*static[:n], scond)
+            torch.cuda.current_stream().wait_stream(stream)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self.fn(*static[:n], scond)
+            self.state = {"sig": sig, "g": g, "static": static, "loss": loss}
+        for dst, src in zip(self.state["static"], args):
+            dst.copy_(src)
+        self.state["g"].replay()
+        return self.state["loss"]
+
+
 class Stage2Trainer:
     def __init__(self, model, *, K_min: int = 8, levels: int = 3, stage2_mode: str = "adj", anchor_conf: bool = True,
                  anchor_conf_teacher: float = 0.95, anchor_conf_student: float = 0.5, anchor_conf_endpoints: float = 1.0,
@@ -98,25 +130,9 @@ class Stage2Trainer:
         return loss * world if world > 1 else loss
 
     def _graphed_loss_and_grads(self, x_s, s_idx, mask_in, cond, target, weight_mask) -> torch.Tensor:
-        args = [x_s, s_idx, mask_in, target, weight_mask] + [cond[k] for k in sorted(cond)]
-        sig = tuple((tuple(a.shape), a.dtype) for a in args)
-        if self._graph is None or self._graph["sig"] != sig:
-            static = [a.clone() for a in args]
-            scond = {k: static[5 + i] for i, k in enumerate(sorted(cond))}
-            stream = torch.cuda.Stream()
-            stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(stream):                         # warm-up on the side stream (kernel attributes, workspaces)
-                for _ in range(2):
-                    self.loss_and_grads(static[0], static[1], static[2], scond, static[3], static[4])
-            torch.cuda.current_stream().wait_stream(stream)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                loss = self.loss_and_grads(static[0], static[1], static[2], scond, static[3], static[4])
-            self._graph = {"sig": sig, "g": g, "static": static, "loss": loss}
-        for dst, src in zip(self._graph["static"], args):
-            dst.copy_(src)
-        self._graph["g"].replay()
-        return self._graph["loss"]
+        if self._graph is None:
+            self._graph = GraphedStep(lambda xs, si, mi, tg, wm, c: self.loss_and_grads(xs, si, mi, c, tg, wm))
+        return self._graph((x_s, s_idx, mask_in, target, weight_mask), cond)
 
     def reduce_gradients(self) -> None:
         """Data-parallel all-reduce of the flat gradient arena (each rank's gradient already carries 1 / world)."""

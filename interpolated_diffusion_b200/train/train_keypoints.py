@@ -45,7 +45,8 @@ def _build_keypoint_batch(x0: torch.Tensor, K: int, cond: dict, generator: torch
 class Stage1Trainer:
     def __init__(self, model, *, T: int = 64, K: int = 8, N_train: int = 1000, schedule: str = "cosine", logit_space: bool = True,
                  logit_eps: float = 1e-5, clamp_endpoints: bool = True, lr: float = 2e-4, weight_decay: float = 1e-2,
-                 grad_clip: Optional[float] = 1.0, ema: bool = True, ema_decay: float = 0.999, process_group=None):
+                 grad_clip: Optional[float] = 1.0, ema: bool = True, ema_decay: float = 0.999, process_group=None,
+                 cuda_graph: bool = False):
         self.model = model
         self.T, self.K, self.N_train = T, K, N_train
         self.logit_space, self.logit_eps, self.clamp_endpoints = bool(logit_space), logit_eps, bool(clamp_endpoints)
@@ -59,6 +60,8 @@ class Stage1Trainer:
         self.grads: Dict[str, torch.Tensor] = {n: by_id[id(p)] for n, p in model.named_parameters() if id(p) in by_id}
         self.pg = process_group
         self.last_grad_norm: Optional[torch.Tensor] = None
+        self.cuda_graph = bool(cuda_graph)                     # forward + loss + backward replayed as one CUDA graph
+        self._graph = None
 
     def build_batch(self, x0: torch.Tensor, cond: dict, gen: torch.Generator, idx_override: Optional[torch.Tensor] = None,
                     noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, ...]:
@@ -84,7 +87,13 @@ class Stage1Trainer:
 
     def step(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> torch.Tensor:
         z_t, t, idx, known_mask, eps = self.build_batch(x0, cond, gen)
-        loss = self.loss_and_grads(z_t, t, idx, known_mask, cond, eps)
+        if self.cuda_graph:
+            if self._graph is None:
+                from .stage2_step import GraphedStep
+                self._graph = GraphedStep(lambda z, tt, ii, km, ee, c: self.loss_and_grads(z, tt, ii, km, c, ee))
+            loss = self._graph((z_t, t, idx, known_mask, eps), cond)
+        else:
+            loss = self.loss_and_grads(z_t, t, idx, known_mask, cond, eps)
         P.all_reduce_sum_(self.flat_grad, self.pg)
         self.last_grad_norm = self.opt.step(self.flat_grad)
         return loss

@@ -346,3 +346,22 @@ def test_stage2_trainer_cuda_graph_equals_eager(dev):
         l_g = float(tr._graphed_loss_and_grads(*args))
         assert l_e == l_g and torch.equal(g_e, tr.flat_grad)
         tr.opt.step(tr.flat_grad)
+
+
+def test_stage1_trainer_cuda_graph_steps(dev):
+    """Stage-1 trainer with the graphed forward + backward: identical losses to the eager trainer over a few steps (same seeds)."""
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.train.train_keypoints import Stage1Trainer
+    losses = {}
+    for graph in (False, True):
+        torch.manual_seed(0)
+        model = KeypointDenoiser(d_model=128, n_layers=2, n_heads=4, d_ff=256, data_dim=2, kp_feat_dim=3).to(dev)
+        tr = Stage1Trainer(model, T=64, K=8, cuda_graph=graph)
+        g = torch.Generator(device="cpu").manual_seed(41)
+        x0 = (0.1 + 0.8 * torch.rand((64, 64, 2), generator=g)).to(dev)
+        cond = {"occ": (torch.rand((64, 1, 21, 21), generator=g) < 0.2).float().to(dev), "start_goal": torch.rand((64, 4), generator=g).to(dev),
+                "kp_feat": torch.rand((64, 8, 3), generator=g).to(dev)}
+        gen = torch.Generator(device=dev).manual_seed(43)
+        torch.manual_seed(7)                                         # t / noise come from the global RNG like the reference
+        losses[graph] = [float(tr.step(x0, cond, gen)) for _ in range(4)]
+    assert losses[False] == losses[True], losses
