@@ -53,7 +53,8 @@ class GraphedStep:
 
 
 class Stage2Trainer:
-    def __init__(self, model, *, K_min: int = 8, levels: int = 3, stage2_mode: str = "adj", anchor_conf: bool = True,
+    def __init__(self, model, *, K_min: int = 8, levels: int = 3, stage2_mode: str = "adj", kp_index_mode: str = "random_nested",
+                 k_schedule: str = "doubling", k_geom_gamma: Optional[float] = None, anchor_conf: bool = True,
                  anchor_conf_teacher: float = 0.95, anchor_conf_student: float = 0.5, anchor_conf_endpoints: float = 1.0,
                  anchor_conf_missing: float = 0.0, anchor_conf_anneal: bool = True, anchor_conf_anneal_mode: str = "linear",
                  corrupt_mode: str = "dist", corrupt_sigma_max: float = 0.08, corrupt_sigma_min: float = 0.012,
@@ -65,6 +66,14 @@ class Stage2Trainer:
                  ema_decay: float = 0.999, process_group=None, cuda_graph: bool = False):
         if stage2_mode not in ("adj", "x0"):
             raise ValueError("stage2_mode must be 'adj' or 'x0'")
+        # mask policies of train_interp_levels.py:890-967.  The CLI default "random" is only reachable through --mask_policy_mix,
+        # where it means "random_nested" (:893-894; on its own it falls through to "Unknown kp_index_mode", :958); "selector"
+        # needs the selector model and is fed through build_batch(masks_levels=, idx_levels=).
+        if kp_index_mode == "random":
+            kp_index_mode = "random_nested"
+        if kp_index_mode not in ("random_nested", "uniform", "dp_precomputed"):
+            raise ValueError(f"Unknown kp_index_mode: {kp_index_mode}")
+        self.kp_index_mode, self.k_schedule, self.k_geom_gamma = kp_index_mode, k_schedule, k_geom_gamma
         self.model = model
         self.cfg = dict(K_min=K_min, levels=levels, stage2_mode=stage2_mode, anchor_conf=bool(anchor_conf),
                         conf=(anchor_conf_teacher, anchor_conf_student, anchor_conf_endpoints, anchor_conf_missing),
@@ -90,16 +99,39 @@ class Stage2Trainer:
         self._graph = None
 
     # ------------------------------------------------------------------------------------------------------------------
-    def build_batch(self, x0: torch.Tensor, gen: torch.Generator) -> Tuple[torch.Tensor, ...]:
-        """train_interp_levels.py:1034-1135 without the bootstrap branch: (x_s, s_idx, mask_in, target, weight_mask)."""
+    def build_masks(self, x0: torch.Tensor, gen: torch.Generator, cond: Optional[dict] = None):
+        """Nested anchor masks of the batch by ``kp_index_mode`` (train_interp_levels.py:890-967)."""
+        from ..corruptions import keyframes as kf
+        B, T, _ = x0.shape
+        dev = x0.device
+        c = self.cfg
+        if self.kp_index_mode == "random_nested":
+            return kf.build_nested_masks_batch(B, T, c["K_min"], c["levels"], generator=gen, device=dev, k_schedule=self.k_schedule,
+                                               k_geom_gamma=self.k_geom_gamma)
+        if self.kp_index_mode == "dp_precomputed":
+            if cond is None or "kp_idx" not in cond:
+                raise ValueError("kp_index_mode=dp_precomputed requires kp_idx in dataset")
+            idx_base = cond["kp_idx"].to(dev)
+        else:
+            idx_base, _ = kf.sample_fixed_k_indices_uniform_batch(B, T, c["K_min"], generator=gen, device=dev, ensure_endpoints=True)
+        return kf.build_nested_masks_from_base(idx_base, T, c["levels"], generator=gen, device=dev, k_schedule=self.k_schedule,
+                                               k_geom_gamma=self.k_geom_gamma)
+
+    def build_batch(self, x0: torch.Tensor, gen: torch.Generator, cond: Optional[dict] = None, masks_levels=None, idx_levels=None
+                    ) -> Tuple[torch.Tensor, ...]:
+        """train_interp_levels.py:890-1135 without the bootstrap branch: (x_s, s_idx, mask_in, target, weight_mask).  Draw order
+        on ``gen`` as in the reference: masks, then the level indices, then the corruption noise."""
         c = self.cfg
         dev = L.require_cuda(x0)
         B = x0.shape[0]
+        if masks_levels is None or idx_levels is None:
+            masks_levels, idx_levels = self.build_masks(x0, gen, cond)
         s_idx = TI._sample_level_indices(B, c["levels"], gen, dev, c["level_sampling"], c["level_high_prob"])
         conf_t, conf_st, conf_e, conf_m = c["conf"]
         if c["stage2_mode"] == "adj":
             x_s, x_prev, mask_s, mask_prev, s_idx, _, _ = TI.build_interp_adjacent_batch(
-                x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], s_idx=s_idx, **self.corrupt)
+                x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], masks_levels=masks_levels,
+                idx_levels=idx_levels, s_idx=s_idx, **self.corrupt)
             conf_s = TI._build_anchor_conf(mask_s, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
             conf_prev = TI._build_anchor_conf(mask_prev, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
             if c["anneal"]:
@@ -111,7 +143,8 @@ class Stage2Trainer:
                 mask_in = torch.stack([mask_s, mask_prev], dim=-1)
             return x_s, s_idx, mask_in, x_prev - x_s, (conf_prev if c["anchor_conf"] else mask_prev)
         x_s, mask_s, s_idx, _, _ = TI.build_interp_level_batch(
-            x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], s_idx=s_idx, **self.corrupt)
+            x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], masks_levels=masks_levels, idx_levels=idx_levels,
+            s_idx=s_idx, **self.corrupt)
         conf_s = TI._build_anchor_conf(mask_s, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
         if c["anneal"]:
             conf_s = TI._anneal_conf(conf_s, s_idx, c["levels"], c["anneal_mode"])
@@ -140,8 +173,7 @@ class Stage2Trainer:
 
     def step(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> torch.Tensor:
         """One full training step; returns the (local) loss as a 0-dim device tensor (no host sync)."""
-        batch = self.build_batch(x0, gen)
-        x_s, s_idx, mask_in, target, weight_mask = batch
+        x_s, s_idx, mask_in, target, weight_mask = self.build_batch(x0, gen, cond)
         fn = self._graphed_loss_and_grads if self.cuda_graph else self.loss_and_grads
         loss = fn(x_s, s_idx, mask_in, cond, target, weight_mask)
         self.reduce_gradients()

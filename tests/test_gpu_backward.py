@@ -365,3 +365,27 @@ def test_stage1_trainer_cuda_graph_steps(dev):
         torch.manual_seed(7)                                         # t / noise come from the global RNG like the reference
         losses[graph] = [float(tr.step(x0, cond, gen)) for _ in range(4)]
     assert losses[False] == losses[True], losses
+
+
+def test_stage2_trainer_mask_policies(dev):
+    """kp_index_mode of train_interp_levels.py:890-967: 'uniform' nests every level around the uniform K_min anchors; 'random'
+    is the mix-only alias of 'random_nested'; unknown modes raise like the reference."""
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    model = _make_model(dev, 128, 2, 4, 256, (32, 64), 3)
+    with pytest.raises(ValueError, match="Unknown kp_index_mode"):
+        Stage2Trainer(model, kp_index_mode="selector_only")
+    tr = Stage2Trainer(model, kp_index_mode="uniform")
+    assert Stage2Trainer.__init__.__kwdefaults__["kp_index_mode"] == "random_nested"
+    B, T = 64, 64
+    x0 = torch.rand((B, T, 2), device=dev)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    masks, idxs = tr.build_masks(x0, gen)
+    uni, umask = kf.sample_fixed_k_indices_uniform_batch(B, T, 8, device=dev)
+    assert torch.equal(idxs[3], uni) and torch.equal(masks[:, 3], umask)
+    for s in range(3):
+        assert bool((masks[:, s] | ~masks[:, s + 1]).all())          # M_{s+1} subset of M_s
+        assert int(masks[:, s].sum(1).min()) == int(masks[:, s].sum(1).max()) == idxs[s].shape[1]
+    x_s, s_idx, mask_in, target, wm = tr.build_batch(x0, gen)
+    top = s_idx == 3
+    assert torch.equal(mask_in[top][..., 0].bool(), umask[top])
