@@ -63,7 +63,12 @@ class Stage2Trainer:
                  recompute_vel: bool = True, pos_clip: bool = False, pos_clip_min: float = 0.0, pos_clip_max: float = 1.0,
                  level_sampling: str = "high", level_high_prob: float = 0.5, w_anchor: float = 0.1, w_missing: float = 1.0,
                  lr: float = 2e-4, weight_decay: float = 1e-2, grad_clip: Optional[float] = 1.0, ema: bool = True,
-                 ema_decay: float = 0.999, process_group=None, cuda_graph: bool = False):
+                 ema_decay: float = 0.999, process_group=None, cuda_graph: bool = False, bootstrap_model=None,
+                 bootstrap_schedule: Optional[Dict[str, torch.Tensor]] = None, bootstrap_logit: bool = False,
+                 bootstrap_logit_eps: float = 1e-5, bootstrap_ddim_steps: int = 5, bootstrap_ddim_schedule: str = "quadratic",
+                 bootstrap_prob_start: float = 0.0, bootstrap_prob_end: float = 0.3, bootstrap_warmup_steps: int = 5000,
+                 bootstrap_prob_cap: float = 0.5, bootstrap_mode: str = "batch", bootstrap_replace_prob: float = 0.5,
+                 clamp_endpoints_kp: Optional[bool] = None):
         if stage2_mode not in ("adj", "x0"):
             raise ValueError("stage2_mode must be 'adj' or 'x0'")
         # mask policies of train_interp_levels.py:890-967.  The CLI default "random" is only reachable through --mask_policy_mix,
@@ -91,6 +96,21 @@ class Stage2Trainer:
         self.flat_grad = torch.zeros_like(self.opt.flat)
         by_id = {id(p): g for p, g in zip(self.opt.params, self.opt.views(self.flat_grad))}
         self.grads: Dict[str, torch.Tensor] = {n: by_id[id(p)] for n, p in model.named_parameters() if id(p) in by_id}
+        # bootstrap (train_interp_levels.py:970-1032): a frozen Stage-1 model samples the level-S anchors; with probability
+        # bootstrap_replace_prob an interior anchor's position is replaced by the student's prediction (marked in student_mask, which
+        # lowers its confidence channel)
+        self.boot = None
+        if bootstrap_model is not None:
+            if bootstrap_schedule is None:
+                raise ValueError("bootstrap_model needs bootstrap_schedule (make_alpha_bars of the Stage-1 checkpoint's schedule)")
+            if bootstrap_mode not in ("batch", "per_example"):
+                raise ValueError("bootstrap_mode must be 'batch' or 'per_example'")
+            self.boot = dict(model=bootstrap_model, schedule=bootstrap_schedule, logit=bool(bootstrap_logit), eps=bootstrap_logit_eps,
+                             steps=bootstrap_ddim_steps, sched_name=bootstrap_ddim_schedule, p0=bootstrap_prob_start,
+                             p1=bootstrap_prob_end, warm=bootstrap_warmup_steps, cap=bootstrap_prob_cap, mode=bootstrap_mode,
+                             replace=bootstrap_replace_prob,
+                             clamp_kp=bool(clamp_endpoints if clamp_endpoints_kp is None else clamp_endpoints_kp))
+        self.step_index = 0
         self.pg = process_group
         self.last_grad_norm: Optional[torch.Tensor] = None
         # cuda_graph: forward + loss + backward (~700 launches for the 12-layer model) are captured once per batch shape and
@@ -117,23 +137,76 @@ class Stage2Trainer:
         return kf.build_nested_masks_from_base(idx_base, T, c["levels"], generator=gen, device=dev, k_schedule=self.k_schedule,
                                                k_geom_gamma=self.k_geom_gamma)
 
+    def _bootstrap(self, x0: torch.Tensor, cond: dict, idx_levels, gen: torch.Generator, z_T: Optional[torch.Tensor] = None):
+        """train_interp_levels.py:970-1032 -> (x0_used, student_mask [B,T] bool)."""
+        from ..sample.sample_generate import _build_known_mask_values, _kp_feat_from_idx, _sample_keypoints_ddim
+        from ..utils.normalize import logit_pos, sigmoid_pos
+        b = self.boot
+        B, T, D = x0.shape
+        dev = x0.device
+        if b["warm"] <= 0:
+            p_boot = b["p1"]
+        else:
+            frac = min(1.0, float(self.step_index) / float(b["warm"]))
+            p_boot = b["p0"] + frac * (b["p1"] - b["p0"])
+        p_boot = min(p_boot, b["cap"])
+        if b["mode"] == "batch":
+            use_boot = torch.rand((), generator=gen, device=dev) < p_boot
+            use_mask = torch.full((B,), bool(use_boot), device=dev, dtype=torch.bool)
+        else:
+            use_mask = torch.rand((B,), generator=gen, device=dev) < p_boot
+        student_mask = torch.zeros((B, T), device=dev, dtype=torch.bool)
+        if not bool(torch.any(use_mask)):
+            return x0, student_mask
+        idx_s = idx_levels[self.cfg["levels"]]
+        known_mask, known_values = _build_known_mask_values(idx_s, cond, D, T, b["clamp_kp"])
+        if b["logit"]:
+            known_values = logit_pos(known_values, eps=b["eps"])
+        cond_boot = cond
+        kp_feat_dim = int(getattr(b["model"], "kp_feat_dim", 0))
+        if kp_feat_dim > 0:
+            cond_boot = dict(cond)
+            cond_boot["kp_feat"] = _kp_feat_from_idx(idx_s, T, kp_feat_dim, None, None)
+        z_hat = _sample_keypoints_ddim(b["model"], b["schedule"], idx_s, known_mask, known_values, cond_boot, b["steps"], T,
+                                       schedule_name=b["sched_name"], z_T=z_T)
+        if b["logit"]:
+            z_hat = sigmoid_pos(z_hat)
+        K = idx_s.shape[1]
+        x0_aug = x0.clone()
+        replace_mask = torch.rand((B, K), generator=gen, device=dev) < float(b["replace"])
+        replace_mask = replace_mask & use_mask.view(-1, 1)
+        replace_mask = replace_mask & ~(idx_s == 0) & ~(idx_s == (T - 1))
+        student_mask.scatter_(1, idx_s, replace_mask)
+        gidx = idx_s.unsqueeze(-1).expand(-1, K, 2)
+        vals = x0_aug[:, :, :2].gather(1, gidx)
+        vals = torch.where(replace_mask.unsqueeze(-1), z_hat[:, :, :2], vals)
+        pos = x0_aug[:, :, :2].scatter(1, gidx, vals)
+        x0_aug[:, :, :2] = pos
+        x0_used = torch.where(use_mask.view(-1, 1, 1), x0_aug, x0) if bool(torch.any(replace_mask)) else x0
+        return x0_used, student_mask
+
     def build_batch(self, x0: torch.Tensor, gen: torch.Generator, cond: Optional[dict] = None, masks_levels=None, idx_levels=None
                     ) -> Tuple[torch.Tensor, ...]:
-        """train_interp_levels.py:890-1135 without the bootstrap branch: (x_s, s_idx, mask_in, target, weight_mask).  Draw order
+        """train_interp_levels.py:890-1135: (x_s, s_idx, mask_in, target, weight_mask).  Draw order
         on ``gen`` as in the reference: masks, then the level indices, then the corruption noise."""
         c = self.cfg
         dev = L.require_cuda(x0)
         B = x0.shape[0]
         if masks_levels is None or idx_levels is None:
             masks_levels, idx_levels = self.build_masks(x0, gen, cond)
+        x0_used, student = None, None
+        if self.boot is not None:
+            if cond is None:
+                raise ValueError("the bootstrap branch needs the conditioning (Stage-1 sampling)")
+            x0_used, student = self._bootstrap(x0, cond, idx_levels, gen)
         s_idx = TI._sample_level_indices(B, c["levels"], gen, dev, c["level_sampling"], c["level_high_prob"])
         conf_t, conf_st, conf_e, conf_m = c["conf"]
         if c["stage2_mode"] == "adj":
             x_s, x_prev, mask_s, mask_prev, s_idx, _, _ = TI.build_interp_adjacent_batch(
-                x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], masks_levels=masks_levels,
+                x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], x0_override=x0_used, masks_levels=masks_levels,
                 idx_levels=idx_levels, s_idx=s_idx, **self.corrupt)
-            conf_s = TI._build_anchor_conf(mask_s, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
-            conf_prev = TI._build_anchor_conf(mask_prev, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
+            conf_s = TI._build_anchor_conf(mask_s, student, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
+            conf_prev = TI._build_anchor_conf(mask_prev, student, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
             if c["anneal"]:
                 conf_s = TI._anneal_conf(conf_s, s_idx, c["levels"], c["anneal_mode"])
                 conf_prev = TI._anneal_conf(conf_prev, torch.clamp(s_idx - 1, min=0), c["levels"], c["anneal_mode"])
@@ -143,9 +216,9 @@ class Stage2Trainer:
                 mask_in = torch.stack([mask_s, mask_prev], dim=-1)
             return x_s, s_idx, mask_in, x_prev - x_s, (conf_prev if c["anchor_conf"] else mask_prev)
         x_s, mask_s, s_idx, _, _ = TI.build_interp_level_batch(
-            x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], masks_levels=masks_levels, idx_levels=idx_levels,
-            s_idx=s_idx, **self.corrupt)
-        conf_s = TI._build_anchor_conf(mask_s, None, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
+            x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], x0_override=x0_used, masks_levels=masks_levels,
+            idx_levels=idx_levels, s_idx=s_idx, **self.corrupt)
+        conf_s = TI._build_anchor_conf(mask_s, student, conf_t, conf_st, conf_e, conf_m, c["clamp_endpoints"])
         if c["anneal"]:
             conf_s = TI._anneal_conf(conf_s, s_idx, c["levels"], c["anneal_mode"])
         mask_in = torch.stack([mask_s.float(), conf_s], dim=-1) if c["anchor_conf"] else mask_s
@@ -178,4 +251,5 @@ class Stage2Trainer:
         loss = fn(x_s, s_idx, mask_in, cond, target, weight_mask)
         self.reduce_gradients()
         self.last_grad_norm = self.opt.step(self.flat_grad)
+        self.step_index += 1
         return loss

@@ -389,3 +389,40 @@ def test_stage2_trainer_mask_policies(dev):
     x_s, s_idx, mask_in, target, wm = tr.build_batch(x0, gen)
     top = s_idx == 3
     assert torch.equal(mask_in[top][..., 0].bool(), umask[top])
+
+
+def test_stage2_trainer_bootstrap_branch(dev):
+    """train_interp_levels.py:970-1032: a frozen Stage-1 model replaces interior level-S anchors by its own samples; those
+    positions are flagged in student_mask (lower confidence), everything else of x0 is untouched."""
+    from interpolated_diffusion_b200.diffusion.schedules import make_alpha_bars, make_beta_schedule
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.sample.sample_generate import _build_known_mask_values, _sample_keypoints_ddim
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    from interpolated_diffusion_b200.utils.normalize import logit_pos, sigmoid_pos
+    model = _make_model(dev, 128, 2, 4, 256, (32, 64), 3)
+    torch.manual_seed(1)
+    kp = KeypointDenoiser(d_model=128, n_layers=2, n_heads=4, d_ff=256, data_dim=2).to(dev)
+    sched = {k: v.to(dev) for k, v in make_alpha_bars(make_beta_schedule("cosine", 1000)).items()}
+    tr = Stage2Trainer(model, corrupt_mode="none", bootstrap_model=kp, bootstrap_schedule=sched, bootstrap_logit=True,
+                       bootstrap_prob_end=1.0, bootstrap_warmup_steps=0, bootstrap_prob_cap=1.0, bootstrap_mode="per_example",
+                       bootstrap_replace_prob=1.0, bootstrap_ddim_steps=3)
+    B, T = 64, 64
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x0 = (0.1 + 0.8 * torch.rand((B, T, 2), generator=g)).to(dev)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=g) < 0.2).float().to(dev), "start_goal": torch.rand((B, 4), generator=g).to(dev)}
+    gen = torch.Generator(device=dev).manual_seed(5)
+    masks, idxs = tr.build_masks(x0, gen)
+    z_T = torch.randn((B, 8, 2), generator=g).to(dev)
+    x0_used, student = tr._bootstrap(x0, cond, idxs, gen, z_T=z_T)
+    idx_s = idxs[3]
+    interior = torch.zeros((B, T), device=dev, dtype=torch.bool).scatter_(1, idx_s, (idx_s != 0) & (idx_s != T - 1))
+    assert torch.equal(student, interior)                                   # replace_prob = 1, every sample bootstrapped
+    km, kv = _build_known_mask_values(idx_s, cond, 2, T, True)
+    z = sigmoid_pos(_sample_keypoints_ddim(kp, sched, idx_s, km, logit_pos(kv), cond, 3, T, schedule_name="quadratic", z_T=z_T))
+    got = x0_used.gather(1, idx_s.unsqueeze(-1).expand(-1, -1, 2))
+    inner = ((idx_s != 0) & (idx_s != T - 1)).unsqueeze(-1)
+    assert torch.equal(torch.where(inner, got, z), z)                        # student predictions at the interior anchors
+    assert torch.equal(x0_used[~student], x0[~student])                      # nothing else moved
+    # the confidence channel sees the student anchors (0.5 instead of 0.95 before annealing) and a full step runs
+    x_s, s_idx, mask_in, target, wm = tr.build_batch(x0, gen, cond)
+    assert mask_in.shape == (B, T, 3) and math.isfinite(float(tr.step(x0, cond, gen)))
