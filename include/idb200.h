@@ -383,6 +383,15 @@ int idb200_im2col3x3(const void* src, int64_t B, int H, int W, int C, int Kpad, 
 int idb200_pool_silu(const void* u, int64_t B, int P, int C, float* pooled, idb200_stream_t stream);
 int idb200_pool_silu_bwd(const void* u, const float* dpooled, int64_t B, int P, int C, void* du, idb200_stream_t stream);
 
+/* KeypointSelector pieces (src/models/keypoint_selector.py:22-188; the producer of anchor logits for kp_index_mode = selector).
+ * Cross attention of nn.MultiheadAttention(q, memory, memory), head_dim 32: q bf16 [B,Lq,d] (projected queries, Lq % 16 == 0),
+ * kv_a bf16 [B,La,2d] and kv_b bf16 [B,Lb,2d] (or NULL, Lb = 0): [K | V] projections of the memory tokens in two buffers
+ * (spatial tokens, extra tokens; key order does not matter), out bf16 [B,Lq,d]. */
+int idb200_cross_attention(const void* q, const void* kv_a, const void* kv_b, void* out, int64_t B, int Lq, int La, int Lb, int H,
+                           idb200_stream_t stream);
+/* Gaussian start / goal maps (:113-146, sigma > 0): out fp32 [B,2,H,W] = exp(-((x - cx)^2 + (y - cy)^2) / (2 sigma^2)). */
+int idb200_sg_map(const float* start_goal, int64_t B, int H, int W, float sigma, float* out, idb200_stream_t stream);
+
 /* DP anchor placement, src/selection/epiplexity_dp.py:171-228 (dp_select_indices_batch): the producer of idx for
  * kp_index_mode = dp.  C fp32 [B,T,T] segment costs (inf = no segment); idx int64 [B,K], 2 <= K <= T, idx[:,0] = 0,
  * idx[:,K-1] = T-1, minimising sum C[idx[k-1], idx[k]] with torch.argmin's first-minimum tie rule (bit-identical indices).

@@ -269,6 +269,142 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cross attention (KeypointSelector, src/models/keypoint_selector.py:22-38): Lq query tokens attend La + Lb memory tokens
+// (La spatial tokens + Lb extra tokens kept in a second buffer; key order is irrelevant to softmax(QK^T)V).
+//   q [B, Lq, d] bf16 (projected queries), kv_a [B, La, 2d], kv_b [B, Lb, 2d] bf16 ([K | V] projections), out [B, Lq, d].
+// One CTA per (sample, head): Q, K, V of the head staged in shared memory (keys padded to a multiple of 16 with zeros and
+// masked), 16-query blocks per warp, online softmax over 64-key steps, same mma.sync / ldmatrix fragments as attn_mma_kernel.
+__global__ void __launch_bounds__(128) cross_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv_a,
+                                                             const __nv_bfloat16* __restrict__ kv_b, __nv_bfloat16* __restrict__ out,
+                                                             int Lq, int La, int Lb, int H) {
+    extern __shared__ __align__(16) unsigned char smem_attn[];
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+    const int d = H * kHD;
+    const int Lk = La + Lb, Lkp = (Lk + 15) & ~15;
+    __nv_bfloat16* Ks = Qs + static_cast<size_t>(Lq) * kPitch;
+    __nv_bfloat16* Vs = Ks + static_cast<size_t>(Lkp) * kPitch;
+    const long long b = blockIdx.x / H;
+    const int hh = blockIdx.x % H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float scale_log2 = rsqrtf(static_cast<float>(kHD)) * 1.4426950408889634f;
+    for (int e = threadIdx.x; e < Lq * 4; e += blockDim.x) {
+        const int tok = e >> 2, ck = e & 3;
+        *reinterpret_cast<uint4*>(Qs + tok * kPitch + ck * 8) = *reinterpret_cast<const uint4*>(q + (b * Lq + tok) * d + hh * kHD + ck * 8);
+    }
+    for (int e = threadIdx.x; e < Lkp * 8; e += blockDim.x) {
+        const int tok = e >> 3, r = e & 7, third = r >> 2, ck = r & 3;              // third: 0 = K, 1 = V
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (tok < La) v = *reinterpret_cast<const uint4*>(kv_a + (b * La + tok) * 2 * d + third * d + hh * kHD + ck * 8);
+        else if (tok < Lk) v = *reinterpret_cast<const uint4*>(kv_b + (b * Lb + (tok - La)) * 2 * d + third * d + hh * kHD + ck * 8);
+        *reinterpret_cast<uint4*>((third ? Vs : Ks) + tok * kPitch + ck * 8) = v;
+    }
+    __syncthreads();
+    const int g = lane >> 2, tq = lane & 3;
+    for (int qb = warp; qb < Lq / 16; qb += blockDim.x >> 5) {
+        unsigned qa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            ldmatrix_x4(qa[ks], Qs + (qb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + ks * 16 + (lane >> 4) * 8);
+        float o[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[nt][c] = 0.0f;
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+        for (int k0 = 0; k0 < Lkp; k0 += 64) {
+            const int kw = min(64, Lkp - k0);
+            float sc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sc[nt][c] = 0.0f;
+                if (nt * 8 < kw) {
+                    unsigned kb[4];
+                    ldmatrix_x4(kb, Ks + (k0 + nt * 8 + (lane & 7)) * kPitch + (lane >> 3) * 8);
+                    mma_bf16_16816(sc[nt], qa[0], kb[0], kb[1]);
+                    mma_bf16_16816(sc[nt], qa[1], kb[2], kb[3]);
+                }
+            }
+            float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int key = k0 + nt * 8 + tq * 2 + (c & 1);
+                    sc[nt][c] = (nt * 8 < kw && key < Lk) ? sc[nt][c] * scale_log2 : -INFINITY;
+                }
+                bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+                bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+            }
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+            const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);          // finite: key 0 exists (Lk >= 1)
+            const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+            m0 = mn0; m1 = mn1;
+            float rs0 = 0.0f, rs1 = 0.0f;
+            unsigned pa[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p0 = exp2f(sc[nt][0] - mn0), p1 = exp2f(sc[nt][1] - mn0);
+                const float p2 = exp2f(sc[nt][2] - mn1), p3 = exp2f(sc[nt][3] - mn1);
+                rs0 += p0 + p1;
+                rs1 += p2 + p3;
+                pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+                pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+            }
+            l0 = l0 * c0 + rs0;
+            l1 = l1 * c1 + rs1;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                if (ks * 16 < kw) {
+#pragma unroll
+                    for (int np = 0; np < 2; ++np) {
+                        unsigned vb[4];
+                        ldmatrix_x4_trans(vb, Vs + (k0 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + np * 16 + (lane >> 4) * 8);
+                        mma_bf16_16816(o[np * 2 + 0], pa[ks], vb[0], vb[1]);
+                        mma_bf16_16816(o[np * 2 + 1], pa[ks], vb[2], vb[3]);
+                    }
+                }
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        __nv_bfloat16* o0 = out + (b * Lq + qb * 16 + g) * d + hh * kHD;
+        __nv_bfloat16* o1 = o0 + 8 * d;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<unsigned*>(o0 + nt * 8 + tq * 2) = pack_bf16(o[nt][0] * i0, o[nt][1] * i0);
+            *reinterpret_cast<unsigned*>(o1 + nt * 8 + tq * 2) = pack_bf16(o[nt][2] * i1, o[nt][3] * i1);
+        }
+    }
+}
+
+// Gaussian start / goal maps of the selector (keypoint_selector.py:113-146), sigma > 0: out [B, 2, H, W]
+__global__ void __launch_bounds__(256) sg_map_kernel(const float* __restrict__ sg, long long B, int Hh, int Ww, float inv_2sigma2,
+                                                     float* __restrict__ out) {
+    const long long total = B * 2 * Hh * Ww;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int x = static_cast<int>(i % Ww);
+        const int y = static_cast<int>((i / Ww) % Hh);
+        const int which = static_cast<int>((i / (static_cast<long long>(Ww) * Hh)) % 2);
+        const long long b = i / (2ll * Hh * Ww);
+        const float cx = fminf(fmaxf(sg[b * 4 + which * 2 + 0], 0.0f), 1.0f) * static_cast<float>(Ww - 1);
+        const float cy = fminf(fmaxf(sg[b * 4 + which * 2 + 1], 0.0f), 1.0f) * static_cast<float>(Hh - 1);
+        const float dx = static_cast<float>(x) - cx, dy = static_cast<float>(y) - cy;
+        out[i] = expf(-(dx * dx + dy * dy) * inv_2sigma2);
+    }
+}
+
 }  // namespace idb200
 
 using namespace idb200;
@@ -319,4 +455,37 @@ extern "C" int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t
         attn_simt_kernel<float><<<grid, warps * 32, smem, st>>>(static_cast<const float*>(qkv), static_cast<float*>(out), B, L, H, causal);
     }
     return check_launch("attn_simt_kernel");
+}
+
+extern "C" int idb200_cross_attention(const void* q, const void* kv_a, const void* kv_b, void* out, int64_t B, int Lq, int La, int Lb,
+                                      int H, idb200_stream_t stream) {
+    IDB_REQUIRE(q && kv_a && out && (Lb == 0 || kv_b), IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && H >= 1 && La >= 1 && Lb >= 0, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(Lq >= 16 && Lq % 16 == 0, IDB200_EUNSUPPORTED, "the number of queries must be a multiple of 16 (got %d)", Lq);
+    IDB_REQUIRE(aligned(q, 16) && aligned(kv_a, 16) && (Lb == 0 || aligned(kv_b, 16)) && aligned(out, 4), IDB200_EALIGN,
+                "q / kv must be 16-byte aligned");
+    if (B == 0) return IDB200_OK;
+    const int Lkp = (La + Lb + 15) & ~15;
+    const size_t smem = (static_cast<size_t>(Lq) + 2 * static_cast<size_t>(Lkp)) * kPitch * 2;
+    IDB_REQUIRE(smem <= 200 * 1024, IDB200_EUNSUPPORTED, "too many memory tokens for one CTA (%d)", La + Lb);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(cross_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        smem_set = smem;
+    }
+    IDB_REQUIRE(B * H < (1ll << 31), IDB200_EUNSUPPORTED, "batch too large");
+    cross_attn_mma_kernel<<<static_cast<unsigned>(B * H), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kv_a), static_cast<const __nv_bfloat16*>(kv_b),
+        static_cast<__nv_bfloat16*>(out), Lq, La, Lb, H);
+    return check_launch("cross_attn_mma_kernel");
+}
+
+extern "C" int idb200_sg_map(const float* start_goal, int64_t B, int H, int W, float sigma, float* out, idb200_stream_t stream) {
+    IDB_REQUIRE(start_goal && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && H >= 1 && W >= 1 && sigma > 0.0f, IDB200_EINVAL, "bad arguments (sigma must be > 0)");
+    if (B == 0) return IDB200_OK;
+    sg_map_kernel<<<grid_for(B * 2 * H * W, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(start_goal, B, H, W,
+                                                                                                      1.0f / (2.0f * sigma * sigma), out);
+    return check_launch("sg_map_kernel");
 }

@@ -68,16 +68,19 @@ class Stage2Trainer:
                  bootstrap_logit_eps: float = 1e-5, bootstrap_ddim_steps: int = 5, bootstrap_ddim_schedule: str = "quadratic",
                  bootstrap_prob_start: float = 0.0, bootstrap_prob_end: float = 0.3, bootstrap_warmup_steps: int = 5000,
                  bootstrap_prob_cap: float = 0.5, bootstrap_mode: str = "batch", bootstrap_replace_prob: float = 0.5,
-                 clamp_endpoints_kp: Optional[bool] = None):
+                 clamp_endpoints_kp: Optional[bool] = None, selector_model=None):
         if stage2_mode not in ("adj", "x0"):
             raise ValueError("stage2_mode must be 'adj' or 'x0'")
         # mask policies of train_interp_levels.py:890-967.  The CLI default "random" is only reachable through --mask_policy_mix,
         # where it means "random_nested" (:893-894; on its own it falls through to "Unknown kp_index_mode", :958); "selector"
-        # needs the selector model and is fed through build_batch(masks_levels=, idx_levels=).
+        # ranks the interior positions by the logits of a frozen KeypointSelector (:911-947, the plain non-level variant).
         if kp_index_mode == "random":
             kp_index_mode = "random_nested"
-        if kp_index_mode not in ("random_nested", "uniform", "dp_precomputed"):
+        if kp_index_mode not in ("random_nested", "uniform", "dp_precomputed", "selector"):
             raise ValueError(f"Unknown kp_index_mode: {kp_index_mode}")
+        if kp_index_mode == "selector" and selector_model is None:
+            raise ValueError("kp_index_mode=selector but selector model not loaded")
+        self.selector_model = selector_model
         self.kp_index_mode, self.k_schedule, self.k_geom_gamma = kp_index_mode, k_schedule, k_geom_gamma
         self.model = model
         self.cfg = dict(K_min=K_min, levels=levels, stage2_mode=stage2_mode, anchor_conf=bool(anchor_conf),
@@ -128,6 +131,12 @@ class Stage2Trainer:
         if self.kp_index_mode == "random_nested":
             return kf.build_nested_masks_batch(B, T, c["K_min"], c["levels"], generator=gen, device=dev, k_schedule=self.k_schedule,
                                                k_geom_gamma=self.k_geom_gamma)
+        if self.kp_index_mode == "selector":
+            if cond is None:
+                raise ValueError("kp_index_mode=selector needs the conditioning")
+            logits = self.selector_model(cond)
+            return kf.build_nested_masks_from_logits(logits, c["K_min"], c["levels"], k_schedule=self.k_schedule,
+                                                     k_geom_gamma=self.k_geom_gamma)
         if self.kp_index_mode == "dp_precomputed":
             if cond is None or "kp_idx" not in cond:
                 raise ValueError("kp_index_mode=dp_precomputed requires kp_idx in dataset")

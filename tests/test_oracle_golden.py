@@ -309,3 +309,26 @@ def test_dp_select_oracle_matches_live_reference_golden():
         idx = osel.dp_select_indices_batch(g[n + "/C"], int(g[n + "/K"]))
         assert np.array_equal(idx, g[n + "/idx"]), n
         assert (idx[:, 0] == 0).all() and (idx[:, -1] == g[n + "/C"].shape[1] - 1).all() and (np.diff(idx, axis=1) > 0).all()
+
+
+SELECTOR_CFG = {
+    "default": dict(T=64, n_heads=2, pos_dim=64),
+    "full": dict(T=48, n_heads=2, pos_dim=32, use_sdf=True, sg_map_sigma=2.0),
+}
+
+
+def test_selector_oracle_matches_live_reference_golden():
+    """oracle/selector_torch.py (functional restatement of KeypointSelector) against logits of the live reference, and the
+    top-k index selection of the package (pure index logic, runs anywhere) against the reference's."""
+    import os
+    import numpy as np
+    import torch
+    from interpolated_diffusion_b200.models.keypoint_selector import select_topk_indices
+    from oracle import selector_torch as osel
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "selector.npz"))
+    for name, kw in SELECTOR_CFG.items():
+        sd = {k[len(name) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + "/sd/")}
+        cond = {k[len(name) + 6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + "/cond/")}
+        logits = osel.keypoint_selector(sd, cond, **kw)
+        np.testing.assert_allclose(logits.numpy(), g[name + "/logits"], atol=2e-5, rtol=0)
+        assert np.array_equal(select_topk_indices(torch.from_numpy(g[name + "/logits"]), 8).numpy(), g[name + "/idx_k8"])
