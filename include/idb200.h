@@ -398,6 +398,12 @@ int idb200_sg_map(const float* start_goal, int64_t B, int H, int W, float sigma,
  * status int32 [B]: 0 ok, 1 no finite path to T-1, 2 backtrack failed (the reference raises RuntimeError for both). */
 int idb200_dp_select(const float* C, int64_t B, int T, int K, int64_t* idx, int* status, idb200_stream_t stream);
 
+/* Segment costs for the DP placement, src/selection/epiplexity_dp.py:120-147 (compute_segment_costs_batch): x_pos fp32 [B,T,D]
+ * (D >= 2), segments s = (seg_i[s], seg_j[s]) with n sample points t_idx [S,n] (int64) at chord fractions alpha [S,n] and
+ * weight [S]; out fp32 [B,S] = weight * weight_scale * sum_n ||x[t] - (x_i + alpha (x_j - x_i))||^2 over the 2 position dims. */
+int idb200_segment_costs(const float* x_pos, int64_t B, int T, int D, const int64_t* seg_i, const int64_t* seg_j, const int64_t* t_idx,
+                         const float* alpha, const float* weight, int S, int n, float weight_scale, float* out, idb200_stream_t stream);
+
 /* Batched trajectory metrics, src/eval/metrics.py:68-128 (compute_metrics_batch; _pos_to_cell :13-24): the step right after
  * the generation path (the reference loops over samples on the host, sample_generate.py:1323-1398).
  *   occ fp32 [B,H,W] (occ_stride = H*W, or 0 to broadcast one map); traj fp32 [B,T,D], dims 0:2 = (x, y) in [0,1];

@@ -69,6 +69,7 @@ _SIGS = {
     "idb200_pool_silu_bwd": [c_p, c_p, c_l, c_i, c_i, c_p, c_p],
     "idb200_cross_attention": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p],
     "idb200_sg_map": [c_p, c_l, c_i, c_i, c_f, c_p, c_p],
+    "idb200_segment_costs": [c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p],
     "idb200_dp_select": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "idb200_anchor_conf": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_l, c_i, c_i, c_p, c_p, c_p],
 }

@@ -78,3 +78,50 @@ extern "C" int idb200_dp_select(const float* C, int64_t B, int T, int K, int64_t
     sel::dp_select_kernel<<<static_cast<unsigned>(B), threads, smem, static_cast<cudaStream_t>(stream)>>>(C, T, K, reinterpret_cast<long long*>(idx), status);
     return check_launch("dp_select_kernel");
 }
+
+// Segment costs, src/selection/epiplexity_dp.py:120-147 (compute_segment_costs_batch): for every sample b and segment s = (i, j),
+//   cost = weight[s] * weight_scale * sum_n || x[t_idx[s,n]] - (x_i + alpha[s,n] (x_j - x_i)) ||^2   over the 2 position dims,
+// the squared deviation of the trajectory from the chord at the segment's sample points.  One thread per (b, s); the reference
+// materialises [B, S, n, 2] gathers.  fp32 in the reference's operation order.
+namespace idb200 {
+namespace sel {
+__global__ void __launch_bounds__(256) segment_costs_kernel(const float* __restrict__ x, long long B, int T, int D, const long long* __restrict__ seg_i,
+                                                            const long long* __restrict__ seg_j, const long long* __restrict__ t_idx,
+                                                            const float* __restrict__ alpha, const float* __restrict__ weight, int S, int n,
+                                                            float weight_scale, int apply_scale, float* __restrict__ out) {
+    const long long total = B * S;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int s = static_cast<int>(e % S);
+        const long long b = e / S;
+        const float* xb = x + b * T * D;
+        const float xi0 = xb[seg_i[s] * D], xi1 = xb[seg_i[s] * D + 1];
+        const float d0 = __fsub_rn(xb[seg_j[s] * D], xi0), d1 = __fsub_rn(xb[seg_j[s] * D + 1], xi1);
+        float acc = 0.0f;
+        for (int k = 0; k < n; ++k) {
+            const float a = alpha[s * n + k];
+            const long long t = t_idx[s * n + k];
+            const float e0 = __fsub_rn(xb[t * D], __fadd_rn(xi0, __fmul_rn(a, d0)));
+            const float e1 = __fsub_rn(xb[t * D + 1], __fadd_rn(xi1, __fmul_rn(a, d1)));
+            acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1)));
+        }
+        float c = __fmul_rn(acc, weight[s]);
+        if (apply_scale) c = __fmul_rn(c, weight_scale);
+        out[e] = c;
+    }
+}
+}  // namespace sel
+}  // namespace idb200
+
+extern "C" int idb200_segment_costs(const float* x_pos, int64_t B, int T, int D, const int64_t* seg_i, const int64_t* seg_j, const int64_t* t_idx,
+                                    const float* alpha, const float* weight, int S, int n, float weight_scale, float* out,
+                                    idb200_stream_t stream) {
+    IDB_REQUIRE(x_pos && seg_i && seg_j && t_idx && alpha && weight && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && T >= 2 && S >= 1 && n >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(D >= 2, IDB200_EINVAL, "x_pos must have at least 2 dims");
+    if (B == 0) return IDB200_OK;
+    sel::segment_costs_kernel<<<grid_for(B * S, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_pos, B, T, D, reinterpret_cast<const long long*>(seg_i), reinterpret_cast<const long long*>(seg_j),
+        reinterpret_cast<const long long*>(t_idx), alpha, weight, S, n, weight_scale, weight_scale != 1.0f ? 1 : 0, out);
+    return check_launch("segment_costs_kernel");
+}

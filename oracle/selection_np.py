@@ -32,3 +32,16 @@ def dp_select_indices_batch(C: np.ndarray, K: int) -> np.ndarray:
             raise RuntimeError("DP backtrack failed.")
         idx[:, k - 1] = cur
     return idx
+
+
+def compute_segment_costs_batch(x_pos: np.ndarray, seg_i, seg_j, t_idx, alpha, weight, weight_scale: float = 1.0) -> np.ndarray:
+    """``epiplexity_dp.py:120-147``: squared deviation of the trajectory from the chord (i, j) at the sample points."""
+    x = x_pos[..., :2].astype(np.float32)
+    x_i, x_j = x[:, seg_i], x[:, seg_j]                                     # [B, S, 2]
+    mu = x_i[:, :, None, :] + alpha[None, :, :, None].astype(np.float32) * (x_j - x_i)[:, :, None, :]
+    x_t = x[:, t_idx.reshape(-1)].reshape(x.shape[0], t_idx.shape[0], t_idx.shape[1], 2)
+    diff = x_t - mu
+    cost = (diff * diff).sum(-1).sum(-1) * weight[None, :].astype(np.float32)
+    if weight_scale != 1.0:
+        cost = cost * np.float32(weight_scale)
+    return cost.astype(np.float32)

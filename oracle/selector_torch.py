@@ -84,3 +84,18 @@ def keypoint_selector(sd: SD, cond: Dict[str, torch.Tensor], *, T: int, n_heads:
     for i in range(n_blocks):
         q = cross_attn_block(q, memory, sd, f"blocks.{i}.", n_heads)
     return _lin(q, sd, "out").squeeze(-1)
+
+
+def segment_cost_predictor(sd: SD, cond: Dict[str, torch.Tensor], seg_feat: torch.Tensor) -> torch.Tensor:
+    """``src/models/segment_cost.py:43-57``: MLP over [cond_vec | seg_feat] for every segment -> [B, S]."""
+    from .denoiser_torch import cond_encoder
+    cond_vec = cond_encoder(sd, cond)
+    if seg_feat.dim() == 2:
+        seg_feat = seg_feat.unsqueeze(0).expand(cond_vec.shape[0], -1, -1)
+    x = torch.cat([cond_vec.unsqueeze(1).expand(-1, seg_feat.shape[1], -1), seg_feat.float()], dim=-1)
+    ids = sorted({int(k.split(".")[1]) for k in sd if k.startswith("mlp.") and k.endswith(".weight")})
+    for n, i in enumerate(ids):
+        x = _lin(x, sd, f"mlp.{i}")
+        if n < len(ids) - 1:
+            x = F.silu(x)
+    return x.squeeze(-1)

@@ -41,3 +41,35 @@ def test_dp_select_large_batch_vs_oracle_and_errors():
     bad[1, :, T - 1] = float("inf")                               # sample 1 cannot reach T-1
     with pytest.raises(RuntimeError, match="valid path"):
         dp_select_indices_batch(bad.cuda(), K)
+
+
+def test_segment_costs_and_dphi_match_reference_golden():
+    """compute_segment_costs_batch (kernel) and SegmentCostPredictor (d_phi) against the live reference's outputs; then the whole
+    DP placement pipeline (costs -> matrix -> dp_select) against the oracle."""
+    from interpolated_diffusion_b200.models.segment_cost import SegmentCostPredictor
+    from interpolated_diffusion_b200.selection import epiplexity_dp as S
+    g = np.load(os.path.join(os.path.dirname(GOLD), "segments.npz"))
+    dev = torch.device("cuda", 0)
+    for T, n in ((16, 1), (16, 4), (33, 3)):
+        tag = f"pc_T{T}_n{n}"
+        pc = S.build_segment_precompute(T, n, dev)
+        x = torch.from_numpy(g[f"{tag}/x"]).to(dev)
+        np.testing.assert_allclose(S.compute_segment_costs_batch(x, pc, 1.0).cpu().numpy(), g[f"{tag}/cost"], rtol=2e-6, atol=1e-10)
+        np.testing.assert_allclose(S.compute_segment_costs_batch(x, pc, 2.5).cpu().numpy(), g[f"{tag}/cost_scaled"], rtol=2e-6, atol=1e-10)
+    m = SegmentCostPredictor(hidden_dim=128, n_layers=3)
+    m.load_state_dict({k[len("dphi/sd/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("dphi/sd/")})
+    m = m.to(dev)
+    cond = {k[len("dphi/cond/"):]: torch.from_numpy(g[k]).to(dev) for k in g.files if k.startswith("dphi/cond/")}
+    for feat, key in (("dphi/seg_feat", "dphi/pred_shared"), ("dphi/seg_feat_b", "dphi/pred_batched")):
+        pred = m(cond, torch.from_numpy(g[feat]).to(dev)).cpu().numpy()
+        assert np.abs(pred - g[key]).max() < 2e-2 * max(1.0, np.abs(g[key]).max()), key
+    # pipeline: true segment costs of random walks -> DP anchors, bit-exact against the numpy oracle
+    T, K, B = 64, 8, 256
+    pc = S.build_segment_precompute(T, 2, dev)
+    gen = torch.Generator().manual_seed(12)
+    x = (torch.randn((B, T, 2), generator=gen) * 0.05).cumsum(1).to(dev)
+    cost = S.compute_segment_costs_batch(x, pc, 1.0)
+    C = S.build_cost_matrix_from_segments_batch(cost, pc, T)
+    idx = S.dp_select_indices_batch(C, K).cpu().numpy()
+    assert np.array_equal(idx, osel.dp_select_indices_batch(C.cpu().numpy(), K))
+    assert (idx[:, 0] == 0).all() and (idx[:, -1] == T - 1).all()

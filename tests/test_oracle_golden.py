@@ -332,3 +332,41 @@ def test_selector_oracle_matches_live_reference_golden():
         logits = osel.keypoint_selector(sd, cond, **kw)
         np.testing.assert_allclose(logits.numpy(), g[name + "/logits"], atol=2e-5, rtol=0)
         assert np.array_equal(select_topk_indices(torch.from_numpy(g[name + "/logits"]), 8).numpy(), g[name + "/idx_k8"])
+
+
+def test_segment_bookkeeping_and_oracles_match_live_reference_golden():
+    """Host-side segment tables of the DP placement (package code: pure tensor logic, runs on CPU) and the oracles of the
+    segment costs / d_phi predictor against tests/golden/segments.npz (made by the live reference)."""
+    import os
+    import numpy as np
+    import torch
+    from interpolated_diffusion_b200.selection import epiplexity_dp as S
+    from oracle import selection_np as osel
+    from oracle import selector_torch as ost
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "segments.npz"))
+    for T, n in ((16, 1), (16, 4), (33, 3)):
+        tag = f"pc_T{T}_n{n}"
+        pc = S.build_segment_precompute(T, n, torch.device("cpu"))
+        for k in ("seg_i", "seg_j", "seg_len", "t_idx", "seg_id"):
+            assert np.array_equal(getattr(pc, k).numpy(), g[f"{tag}/{k}"]), (tag, k)
+        for k in ("alpha", "weight"):
+            assert np.array_equal(getattr(pc, k).numpy(), g[f"{tag}/{k}"]), (tag, k)
+        assert np.array_equal(S.build_segment_features(T, pc.seg_i, pc.seg_j).numpy(), g[f"{tag}/feat"])
+        for scale, key in ((1.0, "cost"), (2.5, "cost_scaled")):
+            c = osel.compute_segment_costs_batch(g[f"{tag}/x"], g[f"{tag}/seg_i"], g[f"{tag}/seg_j"], g[f"{tag}/t_idx"], g[f"{tag}/alpha"],
+                                                 g[f"{tag}/weight"], scale)
+            np.testing.assert_allclose(c, g[f"{tag}/{key}"], rtol=1e-5, atol=1e-9)
+        C = S.build_cost_matrix_from_segments_batch(torch.from_numpy(g[f"{tag}/cost"]), pc, T).numpy()
+        assert np.array_equal(C, g[f"{tag}/C"])
+    idx = torch.tensor([[0, 3, 7, 12, 15], [0, 1, 2, 9, 15]])
+    assert np.array_equal(S.build_kp_feat_batch(idx, 16).numpy(), g["kp_feat"])
+    assert np.array_equal(S.build_kp_feat(idx[0], 16).numpy(), g["kp_feat"][0])
+    assert np.array_equal(S.build_segment_features_from_idx(idx, 16, 3).numpy(), g["seg_feat_idx3"])
+    assert np.array_equal(S.build_segment_features_from_idx(idx, 16, 5).numpy(), g["seg_feat_idx5"])
+    snr, w = S.build_snr_weights("cosine", 1000, 0.01, 100.0, 0.5)
+    np.testing.assert_allclose(w.numpy(), g["snr_w"], rtol=1e-6)
+    assert np.array_equal(S.sample_timesteps_log_snr(snr, 12).numpy(), g["ts_log_snr"])
+    sd = {k[len("dphi/sd/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("dphi/sd/")}
+    cond = {k[len("dphi/cond/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("dphi/cond/")}
+    np.testing.assert_allclose(ost.segment_cost_predictor(sd, cond, torch.from_numpy(g["dphi/seg_feat"])).numpy(), g["dphi/pred_shared"], atol=2e-5)
+    np.testing.assert_allclose(ost.segment_cost_predictor(sd, cond, torch.from_numpy(g["dphi/seg_feat_b"])).numpy(), g["dphi/pred_batched"], atol=2e-5)
