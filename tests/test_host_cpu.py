@@ -133,3 +133,33 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(".py") and pat.search(open(os.path.join(d, f), encoding="utf-8").read()):
                 bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_prepared_dataset_reader(tmp_path):
+    """dataset.npz of src/data/dataset.py:682-747: per-sample dicts as the reference returns them, and batch() == default collate."""
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader
+    from interpolated_diffusion_b200.data.dataset import PreparedTrajectoryDataset
+    rng = np.random.default_rng(0)
+    N, T, K = 7, 16, 4
+    full = dict(x=rng.random((N, T, 2)), start_goal=rng.random((N, 4)), occ=(rng.random((N, 9, 9)) < 0.2), sdf=rng.random((9, 9)),
+                kp_idx=np.sort(rng.integers(0, T, (N, K)), axis=1), kp_feat=rng.random((N, K, 3)), kp_mask_levels=rng.random((3, T)) < 0.5,
+                difficulty=rng.integers(0, 3, N))
+    p = str(tmp_path / "dataset.npz")
+    np.savez(p, **full)
+    ds = PreparedTrajectoryDataset(p, use_sdf=True)
+    assert len(ds) == N
+    s = ds[3]
+    assert set(s) == {"x", "cond", "difficulty"} and set(s["cond"]) == {"occ", "start_goal", "kp_idx", "kp_feat", "kp_mask_levels", "sdf"}
+    assert s["x"].dtype == torch.float32 and s["cond"]["occ"].shape == (1, 9, 9) and s["cond"]["sdf"].shape == (1, 9, 9)
+    assert s["cond"]["kp_idx"].dtype == torch.int64 and s["cond"]["kp_mask_levels"].dtype == torch.bool
+    assert np.array_equal(s["cond"]["occ"][0].numpy(), full["occ"][3].astype(np.float32)) and int(s["difficulty"]) == int(full["difficulty"][3])
+    col = next(iter(DataLoader(ds, batch_size=4, shuffle=False)))
+    b = ds.batch([0, 1, 2, 3])
+    assert torch.equal(b["x"], col["x"]) and torch.equal(b["difficulty"], col["difficulty"])
+    for k in col["cond"]:
+        assert torch.equal(b["cond"][k], col["cond"][k]), k
+    np.savez(p, x=full["x"], start_goal=full["start_goal"], occ=full["occ"][0])          # minimal file, one shared map
+    ds2 = PreparedTrajectoryDataset(p, use_sdf=True)
+    assert set(ds2[0]["cond"]) == {"occ", "start_goal"} and ds2.batch([1, 5])["cond"]["occ"].shape == (2, 1, 9, 9)
