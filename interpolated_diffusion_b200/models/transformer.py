@@ -39,6 +39,16 @@ class TransformerEncoder(nn.Module):
         self.precision = "bf16"
         self._packed = None
 
+    def flops_per_token(self, Lseq: int) -> float:
+        """Dense FLOPs (2 per multiply-add) one token costs in this encoder at sequence length ``Lseq``: per layer the packed QKV
+        projection, the attention products, the out projection and the two MLP GEMMs (SURVEY 8d's per-layer formula, without
+        the per-trajectory FiLM linears).  Used by the benches to turn a measured time into tensor-pipe utilisation."""
+        blk = self.layers[0]
+        d = blk.norm1.weight.shape[0]
+        ff = blk.ff[0].weight.shape[0]
+        per_layer = 2.0 * d * 3 * d + 2.0 * d * d + 4.0 * Lseq * d + 4.0 * d * ff
+        return per_layer * len(self.layers)
+
     def packed(self) -> E.PackedEncoder:
         if self._packed is None:
             self._packed = E.PackedEncoder(self)
