@@ -126,10 +126,13 @@ def _compute_sigma_for_level(K_s: int, K_min: int, sigma_max: float, sigma_min: 
 def _sample_keypoints_ddim(model, schedule, idx: torch.Tensor, known_mask: torch.Tensor, known_values: torch.Tensor,
                            cond: dict, steps: int, T: int, schedule_name: str = "linear",
                            return_intermediates: bool = False, pos_clip: bool = False, pos_clip_min: float = 0.0,
-                           pos_clip_max: float = 1.0, *, z_T: Optional[torch.Tensor] = None):
+                           pos_clip_max: float = 1.0, *, z_T: Optional[torch.Tensor] = None, cond_vec: Optional[torch.Tensor] = None):
     """sample_generate.py:363-404.  The DDIM update and the known-value ``torch.where`` (:397-399) are one
     launch per step with the step's two alpha-bar entries as kernel arguments (no per-row table gather,
-    no host sync).  ``z_T=`` injects the initial noise (the reference draws it from the global RNG, :389)."""
+    no host sync).  ``z_T=`` injects the initial noise (the reference draws it from the global RNG, :389).
+    Everything the reference recomputes inside every denoiser call although it does not change across steps -- the
+    conditioning encoder, the FiLM tables, the cond_proj row, the timestep MLP -- is computed once before the loop
+    (``cond_vec=`` lets a caller hoist the encoder further, e.g. across the chunks of the causal sampler)."""
     dev = L.require_cuda(idx, known_mask, known_values)
     B, K = idx.shape
     D = known_values.shape[-1]
@@ -141,9 +144,20 @@ def _sample_keypoints_ddim(model, schedule, idx: torch.Tensor, known_mask: torch
     if pos_clip:
         z[..., :2] = z[..., :2].clamp(min=pos_clip_min, max=pos_clip_max)
     intermediates = [z.detach().clone()] if return_intermediates else None
+    hoist = {}
+    if hasattr(model, "encode_cond") and hasattr(model, "timestep_vector") and len(times) > 1:
+        if cond_vec is None and cond and model.cond_enc is not None:
+            cond_vec = model.encode_cond(cond)
+        if cond_vec is not None:
+            hoist = {"cond_vec": cond_vec, "film": model.transformer.packed().film_params(cond_vec, K, model.precision),
+                     "row_b": _cond_row(model, cond_vec, T, dev)}
+        t_vecs = model.timestep_vector(torch.tensor(times[:-1], device=dev, dtype=torch.long))
     for i in range(len(times) - 1):
         t = torch.full((B,), int(times[i]), device=dev, dtype=torch.long)
-        eps = model(z, t, idx, known_mask, cond, T)
+        if hoist:
+            eps = model(z, t, idx, known_mask, cond, T, t_vec=t_vecs[i:i + 1], **hoist)
+        else:
+            eps = model(z, t, idx, known_mask, cond, T)
         z = ddim_step_scalar(z, eps, float(alpha_bar[times[i]]), float(alpha_bar[times[i + 1]]), known_mask=known_mask,
                              known_values=known_values, pos_clip=pos_clip, pos_clip_min=pos_clip_min,
                              pos_clip_max=pos_clip_max)

@@ -29,6 +29,32 @@ def _heuristic_right(left: torch.Tensor, goal: torch.Tensor, L_: int, remaining:
     return left + frac * (goal - left)
 
 
+def _maze_embedding(model, cond: Dict[str, torch.Tensor]) -> Optional[torch.Tensor]:
+    """maze.fc(mean-pooled conv stack(occ[, sdf])) of the model's conditioning encoder (encoders.py:56-65), or None when the
+    encoder is not the built-in MazeConditionEncoder."""
+    enc = getattr(model, "cond_enc", None)
+    if enc is None or not hasattr(enc, "maze"):
+        return None
+    x = cond["occ"]
+    if enc.use_sdf:
+        if cond.get("sdf") is None:
+            raise ValueError("use_sdf is True but sdf missing from cond")
+        x = torch.cat([x, cond["sdf"]], dim=1)
+    enc.maze.precision = getattr(model, "precision", "bf16")
+    return enc.maze(x)
+
+
+def _chunk_cond_vec(model, maze_emb: Optional[torch.Tensor], cond_chunk: Dict[str, torch.Tensor]) -> Optional[torch.Tensor]:
+    """cond_vec of a chunk = hoisted maze embedding + start/goal MLP of the chunk's [left, right] (encoders.py:66-70)."""
+    if maze_emb is None:
+        return None
+    enc = model.cond_enc
+    emb = maze_emb.clone()
+    if enc.use_start_goal:
+        enc.sg(cond_chunk["start_goal"], out=emb)
+    return emb
+
+
 def chunk_plan(T: int, chunk: int, K_min: int):
     """(cur, end, local_T, K) per chunk (:504-513)."""
     plan, cur = [], 1
@@ -60,6 +86,8 @@ def generate_causal_chunked(kp_model, interp_model, cond: Dict[str, torch.Tensor
     x_gen = torch.zeros((B, T, D), device=dev, dtype=torch.float32)
     x_gen[:, 0, :2] = start
     s_level = torch.full((B,), levels, device=dev, dtype=torch.long)
+    # the maze part of the conditioning does not change from chunk to chunk (only start_goal does): encode it once per model
+    maze_emb = [_maze_embedding(m, cond) for m in (kp_model, interp_model)]
     for c, (cur, end, local_T, K) in enumerate(chunk_plan(T, chunk, K_min)):
         L_ = end - cur + 1
         left = x_gen[:, cur - 1, :2].contiguous()
@@ -75,8 +103,9 @@ def generate_causal_chunked(kp_model, interp_model, cond: Dict[str, torch.Tensor
         known_mask, known_values = _build_known_mask_values(idx_local, cond_chunk, D, local_T, clamp_endpoints)
         if logit_space:
             known_values = logit_pos(known_values, eps=logit_eps)
+        cv_kp, cv_il = (_chunk_cond_vec(m, e, cond_chunk) for m, e in zip((kp_model, interp_model), maze_emb))
         z_hat = _sample_keypoints_ddim(kp_model, schedule, idx_local, known_mask, known_values, cond_chunk, ddim_steps, local_T,
-                                       z_T=None if z_T_chunks is None else z_T_chunks[c])
+                                       z_T=None if z_T_chunks is None else z_T_chunks[c], cond_vec=cv_kp)
         if logit_space:
             z_hat = sigmoid_pos(z_hat)
         x_s = kf.interpolate_from_indices(idx_local, z_hat, local_T, recompute_velocity=recompute_vel)
@@ -88,7 +117,7 @@ def generate_causal_chunked(kp_model, interp_model, cond: Dict[str, torch.Tensor
             mask_full[:, :cur - 1] = True
         x_full[:, cur - 1:full_len] = x_s
         mask_full[:, cur - 1:full_len] = mask_local
-        delta_hat = interp_model(x_full, s_level, mask_full, cond_chunk)
+        delta_hat = interp_model(x_full, s_level, mask_full, cond_chunk, cond_vec=cv_il)
         x_hat = x_full + delta_hat
         if clamp_policy == "all_anchors":
             clamp_mask = mask_full
