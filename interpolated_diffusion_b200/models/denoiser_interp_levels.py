@@ -39,6 +39,7 @@ class InterpLevelDenoiser(nn.Module):
         # generation than the dedicated embed / head kernels (measured, round 1).
         self.fuse_io = False
         self.fuse_head = True            # the out head as the tile epilogue of the fused-encoder launch (h is not written back)
+        self.pad_causal = True           # causal models: right-pad T < 128 to a divisor of 128 so the whole-encoder kernel applies
         self._cache = {}
         self._ws = E.Workspace()
 
@@ -63,6 +64,23 @@ class InterpLevelDenoiser(nn.Module):
         }
         self._cache["derived"] = (key, val)
         return val
+
+    @torch.no_grad()
+    def _forward_padded(self, xs_p, s, mk_p, cond, cond_vec, T_real: int) -> torch.Tensor:
+        """forward() on a right-padded causal sequence with the positional table of the real length."""
+        Tp = xs_p.shape[1]
+        dev = xs_p.device
+        d = self.in_proj.weight.shape[0]
+        der = dict(self._derived(T_real, dev))
+        der["tab"] = torch.nn.functional.pad(der["tab"], (0, 0, 0, Tp - T_real)).contiguous()
+        key = self._cache.get("derived")
+        self._cache["derived"] = ((Tp, E._sig([self.in_proj.weight, self.in_proj.bias, self.cond_proj.bias])), der)
+        try:
+            self.pad_causal = False
+            return self.forward(xs_p, s, mk_p, cond, cond_vec=cond_vec)
+        finally:
+            self.pad_causal = True
+            self._cache["derived"] = key
 
     @torch.no_grad()
     def _sync_precision(self):
@@ -93,6 +111,15 @@ class InterpLevelDenoiser(nn.Module):
         C = 1 if mask.dim() == 2 else mask.shape[-1]
         if C != self.mask_channels:
             raise ValueError(f"mask has {C} channels, expected {self.mask_channels}")
+        if self._causal and self.pad_causal and T < 128 and 128 % T != 0 and out is None and level_vec is None and row_b is None \
+                and (film is None) and self.transformer.packed().fused_path(128, self.precision):
+            # Causal attention never looks to the right, so right-padding the sequence to a length the whole-encoder kernel takes
+            # (a divisor of 128) leaves every real token's result unchanged; the positional table is built for the real length.
+            Tp = 1 << (T - 1).bit_length()
+            pad = Tp - T
+            xs_p = torch.nn.functional.pad(L.f32c(x_s), (0, 0, 0, pad))
+            mk_p = torch.nn.functional.pad(mask, (0, pad) if mask.dim() == 2 else (0, 0, 0, pad))
+            return self._forward_padded(xs_p, s, mk_p, cond, cond_vec, T)[:, :T].contiguous()
         der = self._derived(T, dev)
         M = B * T
         src1 = src2 = None

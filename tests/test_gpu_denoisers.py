@@ -317,3 +317,26 @@ def test_deep_conv_stack_gemm_vs_oracle(chan, use_sdf, B):
     if B <= 64:
         got = m(_cuda(cond))
         assert _maxabs(got, ref) < 1e-4, _maxabs(got, ref)
+
+
+@pytest.mark.parametrize("T", [17, 49, 100])
+def test_causal_denoiser_padded_to_fused_path(T):
+    """A causal Stage-2 model at a length that does not divide 128 is right-padded to one that does and runs through the
+    whole-encoder kernel: every real token equals the unpadded generic path (causal attention never looks right) and the oracle."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels_causal import InterpLevelCausalDenoiser
+    B, D = 5, 2
+    gen = torch.Generator().manual_seed(T)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    torch.manual_seed(2)
+    m = InterpLevelCausalDenoiser(data_dim=D, max_levels=3, mask_channels=1)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    x = torch.rand((B, T, D), generator=gen)
+    mask = torch.rand((B, T), generator=gen) < 0.3
+    s = torch.full((B,), 3)
+    ref = odn.interp_level_denoiser(sd, 8, x, s, mask, cond, causal=True)
+    got = m(x.cuda(), s.cuda(), mask.cuda(), _cuda(cond))
+    assert got.shape == (B, T, D) and _maxabs(got, ref) < 2e-2, _maxabs(got, ref)
+    m.pad_causal = False
+    plain = m(x.cuda(), s.cuda(), mask.cuda(), _cuda(cond))
+    assert _maxabs(got, plain) < 2e-2
