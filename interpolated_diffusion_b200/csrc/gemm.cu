@@ -473,8 +473,14 @@ int gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, long long 
     IDB_REQUIRE(splits >= 1 && (K / kBK) % splits == 0, IDB200_EINVAL, "splits (%d) must divide K / %d", splits, kBK);
     IDB_REQUIRE(aligned(partial, 16), IDB200_EALIGN, "out must be 16-byte aligned");
     int BN = 0;
-    for (int cand : {256, 192, 128, 64})
-        if (N % cand == 0) { BN = cand; break; }
+    static const bool prefer_pair = !(getenv("IDB200_GEMM_NN_PREFER_PAIR") && getenv("IDB200_GEMM_NN_PREFER_PAIR")[0] == '0');
+    if (prefer_pair) {                                    // pair mode needs BN % 128 == 0 here: 128 before 192
+        for (int cand : {256, 128, 192, 64})
+            if (N % cand == 0) { BN = cand; break; }
+    } else {
+        for (int cand : {256, 192, 128, 64})
+            if (N % cand == 0) { BN = cand; break; }
+    }
     CUtensorMap ta, tw;
     int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), 64, 64);
     if (rc) return rc;
