@@ -68,12 +68,12 @@ class Stage2Trainer:
                  bootstrap_logit_eps: float = 1e-5, bootstrap_ddim_steps: int = 5, bootstrap_ddim_schedule: str = "quadratic",
                  bootstrap_prob_start: float = 0.0, bootstrap_prob_end: float = 0.3, bootstrap_warmup_steps: int = 5000,
                  bootstrap_prob_cap: float = 0.5, bootstrap_mode: str = "batch", bootstrap_replace_prob: float = 0.5,
-                 clamp_endpoints_kp: Optional[bool] = None, selector_model=None):
+                 clamp_endpoints_kp: Optional[bool] = None, selector_model=None, selector_level_mode: str = "k_norm"):
         if stage2_mode not in ("adj", "x0"):
             raise ValueError("stage2_mode must be 'adj' or 'x0'")
         # mask policies of train_interp_levels.py:890-967.  The CLI default "random" is only reachable through --mask_policy_mix,
         # where it means "random_nested" (:893-894; on its own it falls through to "Unknown kp_index_mode", :958); "selector"
-        # ranks the interior positions by the logits of a frozen KeypointSelector (:911-947, the plain non-level variant).
+        # ranks the interior positions by the logits of a frozen KeypointSelector (:911-947; per level when it is level-conditioned).
         if kp_index_mode == "random":
             kp_index_mode = "random_nested"
         if kp_index_mode not in ("random_nested", "uniform", "dp_precomputed", "selector"):
@@ -81,6 +81,7 @@ class Stage2Trainer:
         if kp_index_mode == "selector" and selector_model is None:
             raise ValueError("kp_index_mode=selector but selector model not loaded")
         self.selector_model = selector_model
+        self.selector_level_mode = selector_level_mode
         self.kp_index_mode, self.k_schedule, self.k_geom_gamma = kp_index_mode, k_schedule, k_geom_gamma
         self.model = model
         self.cfg = dict(K_min=K_min, levels=levels, stage2_mode=stage2_mode, anchor_conf=bool(anchor_conf),
@@ -134,6 +135,20 @@ class Stage2Trainer:
         if self.kp_index_mode == "selector":
             if cond is None:
                 raise ValueError("kp_index_mode=selector needs the conditioning")
+            if getattr(self.selector_model, "use_level", False):
+                # level-conditioned selector (:916-937): one ranking per level, conditioned on s / S or K_s / (T - 1)
+                k_list = kf._compute_k_schedule(T, c["K_min"], c["levels"], schedule=self.k_schedule, geom_gamma=self.k_geom_gamma)
+                per_level = []
+                for s_lvl in range(c["levels"] + 1):
+                    if self.selector_level_mode == "s_norm":
+                        level_val = float(s_lvl) / float(max(1, c["levels"]))
+                    else:
+                        level_val = float(k_list[s_lvl]) / float(max(1, T - 1))
+                    cond_sel = dict(cond)
+                    cond_sel["level"] = torch.full((B, 1), level_val, device=dev)
+                    per_level.append(self.selector_model(cond_sel))
+                return kf.build_nested_masks_from_level_logits(torch.stack(per_level, dim=1), c["K_min"], c["levels"],
+                                                               k_schedule=self.k_schedule, k_geom_gamma=self.k_geom_gamma)
             logits = self.selector_model(cond)
             return kf.build_nested_masks_from_logits(logits, c["K_min"], c["levels"], k_schedule=self.k_schedule,
                                                      k_geom_gamma=self.k_geom_gamma)

@@ -426,3 +426,29 @@ def test_stage2_trainer_bootstrap_branch(dev):
     # the confidence channel sees the student anchors (0.5 instead of 0.95 before annealing) and a full step runs
     x_s, s_idx, mask_in, target, wm = tr.build_batch(x0, gen, cond)
     assert mask_in.shape == (B, T, 3) and math.isfinite(float(tr.step(x0, cond, gen)))
+
+
+def test_stage2_trainer_selector_policies(dev):
+    """kp_index_mode = selector (train_interp_levels.py:911-947): masks ranked by a frozen KeypointSelector, plain and
+    level-conditioned; nested, right sizes, endpoints kept."""
+    from interpolated_diffusion_b200.models.keypoint_selector import KeypointSelector
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    model = _make_model(dev, 128, 2, 4, 256, (32, 64), 3)
+    B, T = 64, 64
+    g = torch.Generator(device="cpu").manual_seed(2)
+    x0 = torch.rand((B, T, 2), generator=g).to(dev)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=g) < 0.2).float().to(dev), "start_goal": torch.rand((B, 4), generator=g).to(dev)}
+    gen = torch.Generator(device=dev).manual_seed(1)
+    for use_level in (False, True):
+        torch.manual_seed(5)
+        sel = KeypointSelector(T=T, d_model=64, n_heads=2, d_ff=128, use_level=use_level).to(dev)
+        tr = Stage2Trainer(model, kp_index_mode="selector", selector_model=sel)
+        masks, idxs = tr.build_masks(x0, gen, cond)
+        assert masks.shape == (B, 4, T) and [i.shape[1] for i in idxs] == [64, 32, 16, 8]
+        assert bool(masks[:, :, 0].all()) and bool(masks[:, :, -1].all())
+        if not use_level:                                            # one ranking: levels are nested by construction
+            for s in range(3):
+                assert bool((masks[:, s] | ~masks[:, s + 1]).all())
+        assert math.isfinite(float(tr.step(x0, cond, gen)))
+    with pytest.raises(ValueError, match="selector model not loaded"):
+        Stage2Trainer(model, kp_index_mode="selector")
