@@ -361,8 +361,8 @@ __global__ void __launch_bounds__(128) ln_bwd_apply_kernel(const float* __restri
                                                            const float4* __restrict__ stats, float* __restrict__ dh,
                                                            __nv_bfloat16* __restrict__ dh16, float* __restrict__ dgb, long long dgb_stride,
                                                            float* __restrict__ dwb_part) {
-    const long long b = blockIdx.y;
-    const int c = blockIdx.x * 128 + threadIdx.x;
+    const long long b = blockIdx.x;                        // trajectories on the wide grid dimension
+    const int c = blockIdx.y * 128 + threadIdx.x;
     if (c >= d) return;
     const float w = ln_w[c], bb = ln_b[c];
     const float g1 = gb ? 1.0f + gb[b * gb_stride + c] : 1.0f;
@@ -1140,8 +1140,7 @@ extern "C" int idb200_ln_film_bwd(const float* da, const float* h, const float* 
         }
         int rc = check_launch("ln_bwd_stats_kernel");
         if (rc) return rc;
-        IDB_REQUIRE(B <= 65535, IDB200_EUNSUPPORTED, "two-pass LayerNorm backward takes at most 65535 trajectories per call");
-        tb::ln_bwd_apply_kernel<<<dim3((d + 127) / 128, grid), 128, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, d, stats, dh, d16, dgb,
+        tb::ln_bwd_apply_kernel<<<dim3(grid, (d + 127) / 128), 128, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, d, stats, dh, d16, dgb,
                                                                             dgb_stride, dwb_part);
         return check_launch("ln_bwd_apply_kernel");
     }
