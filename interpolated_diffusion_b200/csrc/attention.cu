@@ -140,15 +140,32 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
         const long long b = cta / groups_per_b;
         const int h0 = static_cast<int>(cta - b * groups_per_b) * HG;
         __syncthreads();
-        // stage: 16-byte chunks; per token row, per third (q/k/v), HG*32 contiguous bf16 = HG*4 chunks
+        // stage: 16-byte chunks; per token row, per third (q/k/v), HG*32 contiguous bf16 = HG*4 chunks.  A warp takes whole
+        // token rows and a lane keeps its chunk slots (third, head, 16-byte piece) fixed across them: the index divisions run
+        // once per lane and unit instead of once per chunk (they were a quarter of this kernel's instructions)
         const int chunks_per_tok = 3 * HG * 4;
-        for (int e = threadIdx.x; e < L * chunks_per_tok; e += blockDim.x) {
-            const int tok = e / chunks_per_tok, r = e - tok * chunks_per_tok;
-            const int third = r / (HG * 4), rr = r - third * (HG * 4);
-            const int hh = rr >> 2, ck = rr & 3;
-            const __nv_bfloat16* src = qkv + (b * L + tok) * 3 * d + third * d + (h0 + hh) * kHD + ck * 8;
-            __nv_bfloat16* dst = sm + third * part + (static_cast<size_t>(hh) * L + tok) * kPitch + ck * 8;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+        if (chunks_per_tok >= 32) {
+            const __nv_bfloat16* gbase = qkv + b * L * 3 * d + h0 * kHD;
+            for (int r = lane; r < chunks_per_tok; r += 32) {
+                const int third = r / (HG * 4), rr = r - third * (HG * 4);
+                const int hh = rr >> 2, ck = rr & 3;
+                const __nv_bfloat16* src0 = gbase + third * d + hh * kHD + ck * 8;
+                __nv_bfloat16* dst0 = sm + third * part + static_cast<size_t>(hh) * L * kPitch + ck * 8;
+                for (int tok = warp; tok < L; tok += nwarps) {
+                    const __nv_bfloat16* src = src0 + static_cast<size_t>(tok) * 3 * d;
+                    __nv_bfloat16* dst = dst0 + tok * kPitch;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+                }
+            }
+        } else {                                                     // few heads per unit (long sequences): flat chunk loop
+            for (int e = threadIdx.x; e < L * chunks_per_tok; e += blockDim.x) {
+                const int tok = e / chunks_per_tok, r = e - tok * chunks_per_tok;
+                const int third = r / (HG * 4), rr = r - third * (HG * 4);
+                const int hh = rr >> 2, ck = rr & 3;
+                const __nv_bfloat16* src = qkv + (b * L + tok) * 3 * d + third * d + (h0 + hh) * kHD + ck * 8;
+                __nv_bfloat16* dst = sm + third * part + (static_cast<size_t>(hh) * L + tok) * kPitch + ck * 8;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncthreads();
@@ -176,6 +193,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
             float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;   // rows g and g+8 of the 16-row block
             const int g = lane >> 2, tq = lane & 3;
             const int qrow0 = qb * 16 + g, qrow1 = qrow0 + 8;
+            const int lgblk = blk > 0 ? 31 - __clz(blk) : 0;
             int kbeg = 0, kend = causal ? (qb + 1) * 16 : L;               // keys needed by this query block
             if (blk > 0) {                                                 // only the blocks the 16 query rows belong to
                 kbeg = (((qb * 16) / blk) * blk) & ~15;
@@ -201,11 +219,17 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
                 float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
+                    if (nt * 8 >= kw) {                                     // dead key tile of a short step: no mask / max work
+                        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
+                        continue;
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int key = k0 + nt * 8 + tq * 2 + (c & 1);
                         const int qr = (c < 2) ? qrow0 : qrow1;
-                        const bool ok = (nt * 8 < kw) && (!causal || key <= qr) && (blk <= 0 || key / blk == qr / blk);
+                        // blk is a power of two (2, 4, 8): same-trajectory test by shift, not by two integer divisions per element
+                        // (measured: the divisions made this kernel ALU-issue bound, 1700 instructions per 16-row task)
+                        const bool ok = (nt * 8 < kw) && (!causal || key <= qr) && (blk <= 0 || ((key ^ qr) >> lgblk) == 0);
                         s[nt][c] = ok ? s[nt][c] * scale_log2 : -INFINITY;
                     }
                     bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
@@ -222,6 +246,11 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
                 unsigned pa[4][4];                                          // P as A fragments, one per 16-key step
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
+                    if (nt * 8 >= kw) {
+                        pa[nt >> 1][(nt & 1) * 2 + 0] = 0u;
+                        pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;
+                        continue;
+                    }
                     const float p0 = exp2f(s[nt][0] - mn0), p1 = exp2f(s[nt][1] - mn0);
                     const float p2 = exp2f(s[nt][2] - mn1), p3 = exp2f(s[nt][3] - mn1);
                     rs0 += p0 + p1;
