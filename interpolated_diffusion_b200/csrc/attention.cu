@@ -126,6 +126,9 @@ constexpr int kPitch = 40;      // bf16 elements per staged row (80 bytes): conf
 // grid.x = B * (H / HG); CTA stages Q, K, V of HG heads of one trajectory: [3][HG][L][kPitch] bf16
 // blk > 0: block-diagonal attention -- the L rows of a "sequence" are L / blk independent trajectories of blk tokens
 // (Stage 1: blk = 8 tokens per trajectory, 8 trajectories per 64-row sequence), a query only sees keys of its own block.
+// kBlk: block-diagonal (short-trajectory) instantiation; it alone skips the dead key tiles of its 16-key steps (in the long-sequence
+// instantiation the extra branches cost 8 % at L = 256, measured)
+template <bool kBlk>
 __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                        long long B, int L, int H, int HG, int causal, int blk) {
     extern __shared__ __align__(16) unsigned char smem_attn[];
@@ -193,9 +196,9 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
             float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;   // rows g and g+8 of the 16-row block
             const int g = lane >> 2, tq = lane & 3;
             const int qrow0 = qb * 16 + g, qrow1 = qrow0 + 8;
-            const int lgblk = blk > 0 ? 31 - __clz(blk) : 0;
+            const int lgblk = kBlk ? 31 - __clz(blk) : 0;
             int kbeg = 0, kend = causal ? (qb + 1) * 16 : L;               // keys needed by this query block
-            if (blk > 0) {                                                 // only the blocks the 16 query rows belong to
+            if (kBlk) {                                                    // only the blocks the 16 query rows belong to
                 kbeg = (((qb * 16) / blk) * blk) & ~15;
                 const int ke = ((qb * 16 + 15) / blk + 1) * blk;
                 kend = min(kend, min(L, (ke + 15) & ~15));
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
                 float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    if (nt * 8 >= kw) {                                     // dead key tile of a short step: no mask / max work
+                    if (kBlk && nt * 8 >= kw) {                             // dead key tile of a short step: no mask / max work
                         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
                         continue;
                     }
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
                         const int qr = (c < 2) ? qrow0 : qrow1;
                         // blk is a power of two (2, 4, 8): same-trajectory test by shift, not by two integer divisions per element
                         // (measured: the divisions made this kernel ALU-issue bound, 1700 instructions per 16-row task)
-                        const bool ok = (nt * 8 < kw) && (!causal || key <= qr) && (blk <= 0 || ((key ^ qr) >> lgblk) == 0);
+                        const bool ok = (nt * 8 < kw) && (!causal || key <= qr) && (!kBlk || ((key ^ qr) >> lgblk) == 0);
                         s[nt][c] = ok ? s[nt][c] * scale_log2 : -INFINITY;
                     }
                     bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const __nv_bfloat16* __re
                 unsigned pa[4][4];                                          // P as A fragments, one per 16-key step
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    if (nt * 8 >= kw) {
+                    if (kBlk && nt * 8 >= kw) {
                         pa[nt >> 1][(nt & 1) * 2 + 0] = 0u;
                         pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;
                         continue;
@@ -458,15 +461,20 @@ extern "C" int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t
         int HG = H;
         while (HG > 1 && (3 * static_cast<size_t>(HG) * Lp * kPitch * 2 > 100 * 1024 || H % HG != 0)) --HG;
         const size_t smem = 3 * static_cast<size_t>(HG) * Lp * kPitch * 2;
-        static size_t smem_set = 0;
-        if (smem > smem_set) {
-            cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        static size_t smem_set[2] = {0, 0};
+        const int variant = blk > 0 ? 1 : 0;
+        if (smem > smem_set[variant]) {
+            cudaError_t e = variant ? cudaFuncSetAttribute(attn_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                                    : cudaFuncSetAttribute(attn_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            smem_set = smem;
+            smem_set[variant] = smem;
         }
         const int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
         const int grid = grid_for(Bp * (H / HG), 1, per_sm > 0 ? per_sm : 1);
-        attn_mma_kernel<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), Bp, Lp, H, HG, causal, blk);
+        if (variant)
+            attn_mma_kernel<true><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), Bp, Lp, H, HG, causal, blk);
+        else
+            attn_mma_kernel<false><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), Bp, Lp, H, HG, causal, blk);
         return check_launch("attn_mma_kernel");
     }
     const int G = (L < 32) ? 32 / L : 1;
