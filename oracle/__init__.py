@@ -14,5 +14,8 @@ Parity status: PINNED.  ``tests/golden/*.npz`` were produced by importing the
 live Python reference in the build container (``tests/golden/make_golden.py``
 is the committed generator); ``tests/test_oracle_golden.py`` checks every
 oracle function against them (bit-exact for masks / indices / interpolation /
-DDIM arithmetic, 1e-5 for the dense model forwards).
+DDIM arithmetic, 1e-5 for the dense model forwards).  One exception, stated in
+its docstring: the batched chunk loop ``generate.generate_causal_chunked`` is
+restated from the source (the live script needs the D4RL datasets); every
+function it composes is pinned.
 """
