@@ -186,7 +186,8 @@ def _batch(B, T, C, seed):
     return x_s, mask, s, cond, target, conf
 
 
-@pytest.mark.parametrize("d,nl,H,ff,chan,C,causal", [(128, 2, 4, 256, (32, 64), 3, False), (256, 2, 8, 512, (32, 64, 64), 2, True)])
+@pytest.mark.parametrize("d,nl,H,ff,chan,C,causal", [(128, 2, 4, 256, (32, 64), 3, False), (256, 2, 8, 512, (32, 64, 64), 2, True),
+                                                     (384, 2, 12, 1536, (32, 64, 128, 128), 3, False)])   # cfg-4 widths, 2 of 12 layers
 def test_stage2_backward_matches_autograd(dev, d, nl, H, ff, chan, C, causal):
     """Every parameter gradient of InterpLevelDenoiser for the Stage-2 loss (train_interp_levels.py:1142-1159)."""
     from interpolated_diffusion_b200.train.backward import InterpLevelBackprop
