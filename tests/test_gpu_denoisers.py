@@ -340,3 +340,35 @@ def test_causal_denoiser_padded_to_fused_path(T):
     m.pad_causal = False
     plain = m(x.cuda(), s.cuda(), mask.cuda(), _cuda(cond))
     assert _maxabs(got, plain) < 2e-2
+
+
+def test_denoisers_large_model_vs_oracle():
+    """The trainer-default ("large") widths -- d_model 384, 12 heads, ff 1536, maze 32-64-128-128 -- with 3 of the 12 layers:
+    Stage-1 (K = 8) and Stage-2 (T = 64) single evaluations through the generic tcgen05 GEMM (pair mode, TMA-store epilogue),
+    the packed block-diagonal attention kernel and the im2col + GEMM conv stack, bf16, against the CPU oracle."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    kw = dict(d_model=384, n_layers=3, n_heads=12, d_ff=1536, maze_channels=(32, 64, 128, 128))
+    B, T, K, D = 40, 64, 8, 2
+    gen = torch.Generator().manual_seed(15)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=D, **kw)
+    il = InterpLevelDenoiser(data_dim=D, max_levels=3, mask_channels=3, **kw)
+    sd_kp = {k: v.clone() for k, v in kp.state_dict().items()}
+    sd_il = {k: v.clone() for k, v in il.state_dict().items()}
+    kp, il = kp.cuda(), il.cuda()
+    idx = torch.tensor([0, 9, 18, 27, 36, 45, 54, 63]).repeat(B, 1)
+    z = torch.randn((B, K, D), generator=gen)
+    km = torch.zeros((B, K, D), dtype=torch.bool)
+    km[:, 0] = km[:, -1] = True
+    t = torch.full((B,), 500, dtype=torch.long)
+    ref = odn.keypoint_denoiser(sd_kp, 12, z, t, idx, km, cond, T)
+    got = kp(z.cuda(), t.cuda(), idx.cuda(), km.cuda(), _cuda(cond), T)
+    assert _maxabs(got, ref) < 2e-2, _maxabs(got, ref)
+    x = torch.rand((B, T, D), generator=gen)
+    mask_in = torch.rand((B, T, 3), generator=gen)
+    s = torch.randint(1, 4, (B,), generator=gen)
+    ref = odn.interp_level_denoiser(sd_il, 12, x, s, mask_in, cond)
+    got = il(x.cuda(), s.cuda(), mask_in.cuda(), _cuda(cond))
+    assert _maxabs(got, ref) < 2e-2, _maxabs(got, ref)
