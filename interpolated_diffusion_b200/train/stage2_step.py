@@ -121,6 +121,10 @@ class Stage2Trainer:
         # replayed; batch building (host-side level counts), the all-reduce and the optimiser (host-side step count) stay eager
         self.cuda_graph = bool(cuda_graph)
         self._graph = None
+        # prefetch(): the next batch (corruption, masks, confidence channels: launch- and host-sync-bound, ~1.3 ms) is built on a
+        # side stream while the current step's graph runs on the main stream
+        self._side = None
+        self._next = None
 
     # ------------------------------------------------------------------------------------------------------------------
     def build_masks(self, x0: torch.Tensor, gen: torch.Generator, cond: Optional[dict] = None):
@@ -268,9 +272,31 @@ class Stage2Trainer:
         """Data-parallel all-reduce of the flat gradient arena (each rank's gradient already carries 1 / world)."""
         P.all_reduce_sum_(self.flat_grad, self.pg)
 
+    def prefetch(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> None:
+        """Build the batch of the NEXT step now, on a side stream (call right after ``step()``: the step's kernels are still
+        running).  The following ``step()`` consumes it instead of building its own; its x0 / cond arguments must be the ones
+        given here.  x0 / cond must already be complete on the device (e.g. loaded before the previous step was enqueued): the
+        side stream does NOT wait for the main stream -- that wait would put the build behind the running step again."""
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        with torch.cuda.stream(self._side):
+            batch = self.build_batch(x0, gen, cond)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._next = (batch, ev)
+
     def step(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> torch.Tensor:
         """One full training step; returns the (local) loss as a 0-dim device tensor (no host sync)."""
-        x_s, s_idx, mask_in, target, weight_mask = self.build_batch(x0, gen, cond)
+        if self._next is not None:
+            batch, ev = self._next
+            self._next = None
+            main = torch.cuda.current_stream()
+            main.wait_event(ev)
+            for t in batch:
+                t.record_stream(main)                        # allocated on the side stream, consumed here
+            x_s, s_idx, mask_in, target, weight_mask = batch
+        else:
+            x_s, s_idx, mask_in, target, weight_mask = self.build_batch(x0, gen, cond)
         fn = self._graphed_loss_and_grads if self.cuda_graph else self.loss_and_grads
         loss = fn(x_s, s_idx, mask_in, cond, target, weight_mask)
         self.reduce_gradients()

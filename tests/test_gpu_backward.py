@@ -453,3 +453,24 @@ def test_stage2_trainer_selector_policies(dev):
         assert math.isfinite(float(tr.step(x0, cond, gen)))
     with pytest.raises(ValueError, match="selector model not loaded"):
         Stage2Trainer(model, kp_index_mode="selector")
+
+
+def test_stage2_trainer_prefetch_equals_plain_steps(dev):
+    """step() + prefetch() (next batch built on a side stream) walks exactly the same losses as plain step() calls: same
+    generator draws in the same order, same data."""
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    losses = {}
+    for mode in ("plain", "prefetch"):
+        model = _make_model(dev, 128, 2, 4, 256, (32, 64), 3)
+        tr = Stage2Trainer(model, cuda_graph=True)
+        g = torch.Generator(device="cpu").manual_seed(77)
+        x0 = torch.rand((64, 64, 2), generator=g).to(dev)
+        cond = {"occ": (torch.rand((64, 1, 21, 21), generator=g) < 0.2).float().to(dev), "start_goal": torch.rand((64, 4), generator=g).to(dev)}
+        gen = torch.Generator(device=dev).manual_seed(9)
+        out = []
+        for _ in range(5):
+            out.append(tr.step(x0, cond, gen))
+            if mode == "prefetch":
+                tr.prefetch(x0, cond, gen)
+        losses[mode] = [float(v) for v in out]
+    assert losses["plain"] == losses["prefetch"], losses

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--out", default=None)
     ap.add_argument("--graph", type=int, default=0, help="1: forward + loss + backward replayed as one CUDA graph")
+    ap.add_argument("--overlap", type=int, default=0, help="1: whole steps through trainer.step() with the next batch prefetched on a side stream")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -47,6 +48,35 @@ def main():
     x0 = torch.rand((B, T, 2), device=dev, generator=g)
     cond = {"occ": (torch.rand((B, 1, 21, 21), device=dev, generator=g) < 0.2).float(), "start_goal": torch.rand((B, 4), device=dev, generator=g)}
     gen = torch.Generator(device=dev).manual_seed(23 + rank)
+    if a.overlap:
+        tr.cuda_graph = bool(a.graph)
+        for _ in range(a.warmup):
+            loss = tr.step(x0, cond, gen)
+            tr.prefetch(x0, cond, gen)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            loss = tr.step(x0, cond, gen)
+            tr.prefetch(x0, cond, gen)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        res = {"config": f"stage2 train step, {a.model} model, B={B}/GPU x {world} GPU, T=64, adj, anchor_conf, next batch prefetched", "ms_per_step": ms,
+               "traj_per_s": B * world / ms * 1e3, "tflops_per_gpu": B * gf_per_traj / ms, "loss": float(loss), "cuda_graph": bool(a.graph)}
+        if rank == 0:
+            print(json.dumps(res))
+            if a.out:
+                with open(a.out, "w") as f:
+                    json.dump(res, f, indent=1)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     names = ["batch", "forward", "loss", "backward", "allreduce", "optimizer"]
     acc = {n: 0.0 for n in names}
     total = 0.0
