@@ -12,6 +12,38 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def bench_stage1(a, dev, rank, world):
+    """Stage-1 step (train_keypoints.py:505-556): keypoint gather + q_sample + KeypointDenoiser forward / backward + AdamW + EMA."""
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.train.train_keypoints import Stage1Trainer
+    kw = dict(d_model=384, n_layers=12, n_heads=12, d_ff=1536, maze_channels=(32, 64, 128, 128)) if a.model == "large" else {}
+    model = KeypointDenoiser(data_dim=2, kp_feat_dim=0, **kw).to(dev)
+    gf = 3 * ((345.6 + 211.6) if a.model == "large" else (103.3 + 16.5)) / 1000.0
+    tr = Stage1Trainer(model, T=64, K=8, cuda_graph=bool(a.graph))
+    B = a.batch
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x0 = 0.1 + 0.8 * torch.rand((B, 64, 2), device=dev, generator=g)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), device=dev, generator=g) < 0.2).float(), "start_goal": torch.rand((B, 4), device=dev, generator=g)}
+    gen = torch.Generator(device=dev).manual_seed(23 + rank)
+    for _ in range(a.warmup):
+        loss = tr.step(x0, cond, gen)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = tr.step(x0, cond, gen)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    res = {"config": f"stage1 train step, {a.model} model, B={B}/GPU x {world} GPU, K=8 of T=64", "ms_per_step": ms,
+           "traj_per_s": B * world / ms * 1e3, "tflops_per_gpu": B * gf / ms, "loss": float(loss), "cuda_graph": bool(a.graph)}
+    if rank == 0:
+        print(json.dumps(res))
+        if a.out:
+            with open(a.out, "w") as f:
+                json.dump(res, f, indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=512, help="trajectories per GPU")
@@ -19,6 +51,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--stage", type=int, default=2, help="2: Stage-2 interp-levels step (cfg 4); 1: Stage-1 keypoint step (K = 8 tokens)")
     ap.add_argument("--graph", type=int, default=0, help="1: forward + loss + backward replayed as one CUDA graph")
     ap.add_argument("--overlap", type=int, default=0, help="1: whole steps through trainer.step() with the next batch prefetched on a side stream")
     a = ap.parse_args()
@@ -34,6 +67,8 @@ def main():
     from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
     from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
     torch.manual_seed(0)
+    if a.stage == 1:
+        return bench_stage1(a, dev, rank, world)
     if a.model == "large":
         model = InterpLevelDenoiser(d_model=384, n_layers=12, n_heads=12, d_ff=1536, data_dim=2, max_levels=3, mask_channels=3,
                                     maze_channels=(32, 64, 128, 128))
