@@ -286,7 +286,8 @@ class Stage2Trainer:
         self._next = (batch, ev)
 
     def step(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> torch.Tensor:
-        """One full training step; returns the (local) loss as a 0-dim device tensor (no host sync)."""
+        """One full training step; returns the (local) loss as a 0-dim device tensor (no host sync).  With ``cuda_graph`` the
+        returned tensor is the graph's static output: read it (``float(loss)``) or clone it before the next ``step()``."""
         if self._next is not None:
             batch, ev = self._next
             self._next = None
