@@ -163,3 +163,18 @@ def test_prepared_dataset_reader(tmp_path):
     np.savez(p, x=full["x"], start_goal=full["start_goal"], occ=full["occ"][0])          # minimal file, one shared map
     ds2 = PreparedTrajectoryDataset(p, use_sdf=True)
     assert set(ds2[0]["cond"]) == {"occ", "start_goal"} and ds2.batch([1, 5])["cond"]["occ"].shape == (2, 1, 9, 9)
+
+
+def test_causal_chunk_plan_host_logic():
+    """(cur, end, local_T, K) of the chunk loop (sample_generate_causal.py:504-513): package and oracle agree, chunks tile 1..T-1."""
+    from interpolated_diffusion_b200.sample.sample_generate_causal import _heuristic_right, chunk_plan
+    from oracle import generate as og
+    import torch
+    for T, chunk, K in ((64, 16, 8), (256, 16, 8), (50, 16, 8), (40, 12, 6), (17, 16, 32), (2, 16, 8)):
+        plan = chunk_plan(T, chunk, K)
+        assert plan == og.causal_chunk_plan(T, chunk, K)
+        assert [c for c, _, _, _ in plan] == [1] + [e + 1 for _, e, _, _ in plan[:-1]] and plan[-1][1] == T - 1
+        assert all(lt == e - c + 2 and k == min(K, lt) for c, e, lt, k in plan)
+    left, goal = torch.tensor([[0.0, 0.0]]), torch.tensor([[1.0, 2.0]])
+    assert torch.allclose(_heuristic_right(left, goal, 16, 64), torch.tensor([[0.25, 0.5]]))
+    assert torch.allclose(_heuristic_right(left, goal, 16, 8), goal)
