@@ -62,6 +62,8 @@ class Stage1Trainer:
         self.last_grad_norm: Optional[torch.Tensor] = None
         self.cuda_graph = bool(cuda_graph)                     # forward + loss + backward replayed as one CUDA graph
         self._graph = None
+        self._side = None                                      # prefetch(): next batch built on a side stream
+        self._next = None
 
     def build_batch(self, x0: torch.Tensor, cond: dict, gen: torch.Generator, idx_override: Optional[torch.Tensor] = None,
                     noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, ...]:
@@ -85,8 +87,28 @@ class Stage1Trainer:
         self.bp.backward(dgrad.view(B, K, D), self.grads)
         return loss * world if world > 1 else loss
 
+    def prefetch(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> None:
+        """Build the NEXT step's batch on a side stream while the current step runs (see ``Stage2Trainer.prefetch``: x0 / cond
+        must already be complete on the device; the following ``step()`` must get the same x0 / cond)."""
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        with torch.cuda.stream(self._side):
+            batch = self.build_batch(x0, cond, gen)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._next = (batch, ev)
+
     def step(self, x0: torch.Tensor, cond: Dict[str, torch.Tensor], gen: torch.Generator) -> torch.Tensor:
-        z_t, t, idx, known_mask, eps = self.build_batch(x0, cond, gen)
+        if self._next is not None:
+            batch, ev = self._next
+            self._next = None
+            main = torch.cuda.current_stream()
+            main.wait_event(ev)
+            for tns in batch:
+                tns.record_stream(main)
+            z_t, t, idx, known_mask, eps = batch
+        else:
+            z_t, t, idx, known_mask, eps = self.build_batch(x0, cond, gen)
         if self.cuda_graph:
             if self._graph is None:
                 from .stage2_step import GraphedStep

@@ -364,7 +364,11 @@ def test_stage1_trainer_cuda_graph_steps(dev):
                 "kp_feat": torch.rand((64, 8, 3), generator=g).to(dev)}
         gen = torch.Generator(device=dev).manual_seed(43)
         torch.manual_seed(7)                                         # t / noise come from the global RNG like the reference
-        losses[graph] = [float(tr.step(x0, cond, gen)) for _ in range(4)]
+        losses[graph] = []
+        for _ in range(4):
+            losses[graph].append(float(tr.step(x0, cond, gen)))
+            if graph:
+                tr.prefetch(x0, cond, gen)                           # graphed trainer also prefetches the next batch
     assert losses[False] == losses[True], losses
 
 

@@ -319,7 +319,7 @@ def test_deep_conv_stack_gemm_vs_oracle(chan, use_sdf, B):
         assert _maxabs(got, ref) < 1e-4, _maxabs(got, ref)
 
 
-@pytest.mark.parametrize("T", [17, 49, 100])
+@pytest.mark.parametrize("T", [17, 49, 100, 145])
 def test_causal_denoiser_padded_to_fused_path(T):
     """A causal Stage-2 model at a length that does not divide 128 is right-padded to one that does and runs through the
     whole-encoder kernel: every real token equals the unpadded generic path (causal attention never looks right) and the oracle."""
