@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
 // one float4 column group), keeps the trajectory's row_a + row_b and its slice of Wf in registers (F <= kF) and streams
 // the tokens four at a time (all loads of a group of tokens in flight): per token one table-row read (L1/L2 resident) and
 // one coalesced float4 store of h.  Same arithmetic order as embed_kernel: fma chain over the features, + tab + row_a + row_b.
-template <int kF>
+template <int kF, int kTok>
 __global__ void __launch_bounds__(256, 2) embed_traj_kernel(const EmbedParams p) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -289,11 +289,11 @@ __global__ void __launch_bounds__(256, 2) embed_traj_kernel(const EmbedParams p)
         for (int j = 0; j < kF; ++j) w[j] = (j < F) ? __ldg(reinterpret_cast<const float4*>(p.Wf + j * p.d) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 ra = __ldg(reinterpret_cast<const float4*>(p.row_a + b * p.row_a_stride) + c4);
         const float4 rb = __ldg(reinterpret_cast<const float4*>(p.row_b + b * p.d) + c4);
-        for (int t0 = 0; t0 < p.L; t0 += 4) {
-            float f[4][kF];
-            float4 tb[4];
+        for (int t0 = 0; t0 < p.L; t0 += kTok) {
+            float f[kTok][kF];
+            float4 tb[kTok];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kTok; ++i) {
                 const int t = t0 + i;
                 if (t < p.L) {
                     const long long m = b * p.L + t;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256, 2) embed_traj_kernel(const EmbedParams p)
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kTok; ++i) {
                 const int t = t0 + i;
                 if (t < p.L) {
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -523,8 +523,8 @@ extern "C" int idb200_embed_tokens(const float* src0, int n0, const float* src1,
                      aligned(row_b, 16) && aligned(h, 16) && row_a_stride % 4 == 0;
     if (vec) {
         const int grid = grid_for((M / L) * (d / 128), 8, 2);
-        if (F <= 4) embed_traj_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-        else embed_traj_kernel<8><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        if (F <= 4) embed_traj_kernel<4, 2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        else embed_traj_kernel<8, 2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
         return check_launch("embed_traj_kernel");
     }
     embed_kernel<<<warp_grid(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
