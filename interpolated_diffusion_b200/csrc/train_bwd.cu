@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(128) ln_bwd_apply_kernel(const float* __restri
     const float w = ln_w[c], bb = ln_b[c];
     const float g1 = gb ? 1.0f + gb[b * gb_stride + c] : 1.0f;
     float a_dg = 0.0f, a_db = 0.0f, a_dw = 0.0f, a_dbb = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
     for (int t = 0; t < L; ++t) {
         const long long m = b * L + t;
         const float4 st = stats[m];                         // broadcast load
