@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
 // the tokens four at a time (all loads of a group of tokens in flight): per token one table-row read (L1/L2 resident) and
 // one coalesced float4 store of h.  Same arithmetic order as embed_kernel: fma chain over the features, + tab + row_a + row_b.
 template <int kF, int kTok>
-__global__ void __launch_bounds__(256, 2) embed_traj_kernel(const EmbedParams p) {
+__global__ void __launch_bounds__(256, 3) embed_traj_kernel(const EmbedParams p) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -522,7 +522,7 @@ extern "C" int idb200_embed_tokens(const float* src0, int n0, const float* src1,
     const bool vec = d % 128 == 0 && F <= 8 && M % L == 0 && aligned(Wf, 16) && aligned(tab, 16) && aligned(row_a, 16) &&
                      aligned(row_b, 16) && aligned(h, 16) && row_a_stride % 4 == 0;
     if (vec) {
-        const int grid = grid_for((M / L) * (d / 128), 8, 2);
+        const int grid = grid_for((M / L) * (d / 128), 8, 3);
         if (F <= 4) embed_traj_kernel<4, 2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
         else embed_traj_kernel<8, 2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
         return check_launch("embed_traj_kernel");
