@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the generation hot path (BASELINE.json: end-to-end trajectories/sec, DDIM-20 + interp + Stage-2).
+"""Benchmark of the generation hot path (BASELINE.json: end-to-end trajectories/sec, DDIM-20 + interp + Stage-2; interp GB/s).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference itself on the host cores (baseline/_ref; oracle port if absent)
 
 One "step" = one batch of synthetic particle-maze conditioning through the whole path: Stage-1 K=8 keypoint DDIM
 (20 timesteps = 19 denoiser evaluations), sigmoid, piecewise-linear interpolation to T=64, Stage-2 one-step jump,
-soft + hard clamp (clamp_policy=endpoints) -- BASELINE.json configs[2], B = 65536 trajectories per GPU, small
-random-init models (d=256, 8 layers, 8 heads, ff 1024, maze 32-64).  Prints ONE JSON line on rank 0.
+soft + hard clamp (clamp_policy=endpoints) -- BASELINE.json configs[2], B = 65536 trajectories per GPU (weak scaling), small
+random-init models (d=256, 8 layers, 8 heads, ff 1024, maze 32-64).  Prints ONE JSON line on rank 0.  The same line carries
+the other BASELINE configurations as extra keys, each measured in this run at this N:
+    interp        configs[1]: the Interp(x0|M_s) kernel alone, 2^20 trajectories (rank 0)
+    strong        configs[2] with the GLOBAL batch fixed at 65536 (B/N per GPU)
+    train         configs[3]: Stage-2 training step, large model, global batch 4096 over N ranks (DP all-reduce)
+    long_horizon  configs[4]: T=256 K=32 levels=4 causal, global batch 8192 (+ interp GB/s at T=256)
 """
 from __future__ import annotations
 
@@ -120,7 +125,14 @@ def build_models(device, large: bool = False):
 
 
 def cpu_reference_rate(sample_B: int, steps: int = 1, warmup: int = 0):
-    """The reference algorithm (oracle port of sample_generate.py:974-1285) on the host cores."""
+    """The reference's generation path on the host cores -> (trajectories/s, s/step, threads, kind).  kind = "reference": the
+    UNMODIFIED reference modules vendored under baseline/_ref (oracle/vendor_reference.py; git-ignored, travels with the gpurun
+    snapshot) driven through their own component functions (oracle/ref_driver.py); kind = "port": the oracle restatement
+    (oracle/generate.py of sample_generate.py:974-1285) when the vendored copy is absent."""
+    from oracle import ref_driver
+    if ref_driver.reference_root() is not None and not os.environ.get("IDB200_BENCH_PORT"):
+        rate, dt, cores = ref_driver.timed_rate(lambda B: synthetic_cond(B, 0), sample_B, steps=steps, warmup=warmup)
+        return rate, dt, cores, "reference"
     import numpy as np
     from oracle import generate as og
     torch.manual_seed(0)
@@ -142,7 +154,7 @@ def cpu_reference_rate(sample_B: int, steps: int = 1, warmup: int = 0):
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return sample_B / dt, dt, torch.get_num_threads()
+    return sample_B / dt, dt, torch.get_num_threads(), "port"
 
 
 def run_reference(args):
@@ -150,61 +162,229 @@ def run_reference(args):
     if rank != 0:
         return
     sample_B = args.ref_batch
-    rate, dt, cores = cpu_reference_rate(sample_B, steps=args.steps, warmup=min(args.warmup, 1))
+    rate, dt, cores, kind = cpu_reference_rate(sample_B, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "generation: Stage-1 DDIM-20 K=8 + interp T=64 + Stage-2 one-step, small model, clamp_policy=endpoints",
+        "config": {"workload": "generation: Stage-1 DDIM-20 K=8 + interp T=64 + Stage-2 one-step (x0), small model 256x8 ff1024, "
+                               "clamp_policy=endpoints, D=2 (BASELINE.json configs[2])",
                    "sample": f"{sample_B} trajectories per step (bounded CPU sample of the same workload)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{sample_B} trajectories/step x {args.steps} steps"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{sample_B} trajectories/step x {args.steps} steps"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
+class _Ctx:
+    """Per-process state shared by the bench sections."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the ONE JSON line (NCCL prints its version banner there)
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v: float) -> float:
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup, sample_clocks=False, finish=None):
+        """W warm-ups, then K steps bracketed by barrier + synchronize, CUDA events on the launching stream, MAX over ranks.
+        ``finish`` (optional) is enqueued after the last step inside the timed region (joins side streams)."""
+        for _ in range(warmup):
+            fn()
+        if finish:
+            finish()
+        torch.cuda.synchronize(self.dev)
+        self.barrier()
+        sampler = ClockSampler(self.local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(self.dev)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if finish:
+            finish()
+        e1.record()
+        torch.cuda.synchronize(self.dev)
+        self.barrier()
+        clocks = sampler.stop() if sampler else None
+        return self.max_over_ranks(e0.elapsed_time(e1)), clocks
+
+
+class GatherOverlap:
+    """The final all-gather of the samples taken off the compute stream: the step's samples are copied into one of
+    two staging buffers (33 MB device copy) and all-gathered by NCCL on a side stream while the next step's graph runs."""
+
+    def __init__(self, ctx: _Ctx, B: int, Tn: int, Dn: int):
+        self.ctx = ctx
+        self.side = torch.cuda.Stream(device=ctx.dev)
+        self.stage = [torch.empty((B, Tn, Dn), device=ctx.dev) for _ in range(2)]
+        self.out = [torch.empty((ctx.world * B, Tn, Dn), device=ctx.dev) for _ in range(2)]
+        self.done = [None, None]
+        self.i = 0
+
+    def submit(self, x: torch.Tensor) -> torch.Tensor:
+        k = self.i & 1
+        self.i += 1
+        main = torch.cuda.current_stream(self.ctx.dev)
+        if self.done[k] is not None:
+            main.wait_event(self.done[k])               # the all-gather that last read this staging buffer has finished
+        self.stage[k].copy_(x, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            self.ctx.dist.all_gather_into_tensor(self.out[k], self.stage[k])
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[k] = ev
+        return self.out[k]
+
+    def join(self):
+        torch.cuda.current_stream(self.ctx.dev).wait_stream(self.side)
+
+
+def section_interp(ctx, Ti: int, Kmin: int, Si: int, Bi: int, label: str):
+    """"interp GB/s": the Interp(x0|M_s) corruption kernel alone, D = 4; algorithmic bytes per trajectory = x0 read + S level writes
+    + scores + (S+1) byte masks (4600 B at T=64/S=3, 22 776 B at T=256/S=4); median of 20 launches."""
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    dev = ctx.dev
+    Di = 4
+    gi = torch.Generator(device=dev).manual_seed(1234)
+    scores = torch.rand((Bi, Ti - 2), generator=gi, device=dev)
+    x0 = torch.rand((Bi, Ti, Di), generator=gi, device=dev)
+    K_list = kf._compute_k_schedule(Ti, Kmin, Si)
+    for _ in range(3):
+        kf.nested_masks_interp(scores, Ti, K_list, x0=x0, levels_out=(1, Si), want_idx=False)
+    torch.cuda.synchronize(dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(21)]
+    evs[0].record()
+    for i in range(20):
+        kf.nested_masks_interp(scores, Ti, K_list, x0=x0, levels_out=(1, Si), want_idx=False)
+        evs[i + 1].record()
+    torch.cuda.synchronize(dev)
+    ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(20))[10]
+    nbytes = Bi * (Ti * Di * 4 * (1 + Si) + (Ti - 2) * 4 + (Si + 1) * Ti)
+    pk = peaks()
+    return {"workload": label, "ms": ms, "GBps": nbytes / ms / 1e6, "peak_GBps": pk["hbm_gbs"], "frac": nbytes / ms / 1e6 / pk["hbm_gbs"],
+            "trajectories_per_s": Bi / ms * 1e3, "bytes_per_trajectory": nbytes // Bi, "K_list": list(K_list)}
+
+
+def section_train(ctx, args):
+    """BASELINE.json configs[3]: Stage-2 interp-levels training step, T=64, K_min=8, levels=3, adj mode, anchor_conf (C=3), dist
+    corruption on the device, large model (trainer defaults, train_interp_levels.py:57-62), bf16 GEMMs, AdamW + EMA, GLOBAL batch
+    4096 sharded over the ranks (data parallel, gradient all-reduce over NCCL).  Forward + loss + backward replay as one CUDA graph;
+    the next batch's corruption is built on a side stream."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    GB = args.train_batch
+    B = GB // world
+    torch.manual_seed(0)
+    model = InterpLevelDenoiser(data_dim=D, max_levels=LEVELS, mask_channels=3, **LARGE).to(dev)
+    tr = Stage2Trainer(model, cuda_graph=True)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x0 = torch.rand((B, T, D), device=dev, generator=g)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), device=dev, generator=g) < 0.2).float(), "start_goal": torch.rand((B, 4), device=dev, generator=g)}
+    gen = torch.Generator(device=dev).manual_seed(23 + rank)
+    loss = [None]
+
+    def step():
+        loss[0] = tr.step(x0, cond, gen)
+        tr.prefetch(x0, cond, gen)
+
+    ms, _ = ctx.timed(step, args.train_steps, 3)
+    ms /= args.train_steps
+    # exposed all-reduce: time of step() with and without the reduction is not separable inside a graph; measure the collective
+    # itself on the (idle) compute stream, after the timed region
+    ar_ms = 0.0
+    if world > 1:
+        torch.cuda.synchronize(dev)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            tr.reduce_gradients()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ar_ms = ctx.max_over_ranks(e0.elapsed_time(e1) / 5)
+    gf = 3 * (2798.1 + 211.6) / 1000.0            # SURVEY 8d: 3 x (Stage-2 forward + conv encoder) GFLOP per trajectory
+    pk = peaks()
+    res = {"workload": "Stage-2 interp-levels training step, large model 384x12 ff1536 maze 32-64-128-128, T=64 K_min=8 levels=3, adj, "
+                       "anchor_conf, dist corruption on device, bf16 GEMMs, AdamW+EMA (BASELINE.json configs[3])",
+           "global_batch": B * world, "batch_per_gpu": B, "n_gpus": world, "ms_per_step": ms, "trajectories_per_s": B * world / ms * 1e3,
+           "tflops_per_gpu": B * gf / ms, "frac_of_sustained_bf16": B * gf / ms / pk["bf16"], "allreduce_ms_standalone": ar_ms,
+           "allreduce_overlapped": bool(getattr(tr, "overlap_allreduce", False)), "grad_bytes": int(tr.flat_grad.numel()) * 4,
+           "steps": args.train_steps, "loss": float(loss[0]), "cuda_graph": True, "prefetch": True}
+    del tr, model
+    return res
+
+
+def section_long_horizon(ctx, args):
+    """BASELINE.json configs[4]: T=256, K=32, levels=4, causal Stage-2 denoiser (small models), B = 8192 sharded over the ranks."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels_causal import InterpLevelCausalDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    B = args.lh_batch // world
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=D).to(dev)
+    il = InterpLevelCausalDenoiser(data_dim=D, max_levels=4, mask_channels=2).to(dev)
+    cfg = GenerationConfig(T=256, K_min=32, levels=4, data_dim=D)
+    graph = GenerationGraph(kp, il, B, cfg, device=dev)
+    graph.capture()
+    cond = synthetic_cond(B, 2000 + rank, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+
+    def step():
+        z_T = torch.randn((B, 32, D), generator=gen, device=dev)
+        graph.run(cond, z_T)
+
+    ms, _ = ctx.timed(step, 3, 1)
+    ms /= 3
+    gf = (19 * 413.1 + 3760.0 / 2 + 16.5) / 1000.0    # SURVEY 8d: Stage-1 L=32 evals + causal Stage-2 (half of dense) + conv
+    pk = peaks()
+    res = {"workload": "long horizon: T=256 K=32 levels=4, Stage-1 DDIM-20 + interp + causal Stage-2 one-step, small models (BASELINE.json configs[4])",
+           "global_batch": B * world, "batch_per_gpu": B, "n_gpus": world, "ms_per_step": ms, "trajectories_per_s": B * world / ms * 1e3,
+           "tflops_per_gpu": B * gf / ms, "frac_of_sustained_bf16": B * gf / ms / pk["bf16"]}
+    del graph, kp, il
+    torch.cuda.empty_cache()
+    if rank == 0:
+        res["interp"] = section_interp(ctx, 256, 32, 4, 1 << 18, "Interp(x0|M_s): 2^18 trajectories, T=256, D=4, 4 nested levels")
+    return res
+
+
 def run_ours(args):
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the ONE JSON line (NCCL prints its version banner there)
-        dist.init_process_group("nccl", device_id=dev)
+    ctx = _Ctx()
+    dist, world, rank, dev = ctx.dist, ctx.world, ctx.rank, ctx.dev
     from interpolated_diffusion_b200 import _lib as L
-    from interpolated_diffusion_b200.models import _engine as E
     from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph
+    sections = set(args.sections.split(",")) if args.sections != "all" else {"interp", "strong", "train", "long_horizon"}
+    extras = {}
 
     interp = None
-    if rank == 0 and not args.skip_interp:
-        # second half of BASELINE's metric ("interp GB/s", configs[1]): the Interp(x0|M_s) corruption kernel alone on 2^20 synthetic
-        # trajectories, T = 64, D = 4, 3 nested mask levels; algorithmic bytes = 4600 per trajectory; median of 20 launches
-        from interpolated_diffusion_b200.corruptions import keyframes as kf
-        Bi, Ti, Di, Si = 1 << 20, 64, 4, 3
-        gi = torch.Generator(device=dev).manual_seed(1234)
-        scores = torch.rand((Bi, Ti - 2), generator=gi, device=dev)
-        x0 = torch.rand((Bi, Ti, Di), generator=gi, device=dev)
-        K_list = kf._compute_k_schedule(Ti, K_MIN, Si)
-        for _ in range(3):
-            kf.nested_masks_interp(scores, Ti, K_list, x0=x0, levels_out=(1, Si), want_idx=False)
-        torch.cuda.synchronize(dev)
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(21)]
-        evs[0].record()
-        for i in range(20):
-            kf.nested_masks_interp(scores, Ti, K_list, x0=x0, levels_out=(1, Si), want_idx=False)
-            evs[i + 1].record()
-        torch.cuda.synchronize(dev)
-        ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(20))[10]
-        nbytes = Bi * (Ti * Di * 4 * (1 + Si) + (Ti - 2) * 4 + (Si + 1) * Ti)
-        pk = peaks()
-        interp = {"workload": "Interp(x0|M_s): 2^20 trajectories, T=64, D=4, 3 nested levels (BASELINE.json configs[1])", "ms": ms,
-                  "GBps": nbytes / ms / 1e6, "peak_GBps": pk["hbm_gbs"], "frac": nbytes / ms / 1e6 / pk["hbm_gbs"],
-                  "trajectories_per_s": Bi / ms * 1e3, "bytes_per_trajectory": nbytes // Bi}
-        del scores, x0
+    if rank == 0 and "interp" in sections:
+        # second half of BASELINE's metric ("interp GB/s", configs[1])
+        interp = section_interp(ctx, 64, K_MIN, 3, 1 << 20, "Interp(x0|M_s): 2^20 trajectories, T=64, D=4, 3 nested levels (BASELINE.json configs[1])")
+        torch.cuda.empty_cache()
 
     B = args.batch
     cfg = GenerationConfig(T=T, K_min=K_MIN, levels=LEVELS, data_dim=D)
@@ -228,47 +408,33 @@ def run_ours(args):
     host_out = torch.empty((B, T, D), dtype=torch.float32).pin_memory()
     dcond = {k: v.to(dev) for k, v in host.items()}
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    gathered = torch.empty((world * B, T, D), device=dev) if world > 1 else None
 
-    def step_device():
-        z_T = torch.randn((B, K_MIN, D), generator=gen, device=dev)
-        x = graph.run(dcond, z_T)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, x)
-        return x
+    def make_steps(graph, B, dcond, host, host_out):
+        """(device-resident step, end-to-end step, finish).  At N > 1 both include the all-gather of the samples (every rank ends
+        up with all N*B trajectories); it runs on a side stream against the next step's replay and is joined inside the timed
+        region.  The end-to-end step copies the conditioning H2D from pinned memory and this rank's samples D2H."""
+        go = GatherOverlap(ctx, B, T, D) if world > 1 else None
 
-    def step_e2e():
-        z_T = torch.randn((B, K_MIN, D), generator=gen, device=dev)
-        x = graph.run(host, z_T)                      # H2D of occ + start_goal from pinned memory inside the step
-        host_out.copy_(x, non_blocking=True)          # D2H of the samples
-        return x
+        def step_device():
+            z_T = torch.randn((B, K_MIN, D), generator=gen, device=dev)
+            x = graph.run(dcond, z_T)
+            if go:
+                go.submit(x)
+            return x
 
-    def timed(fn, steps, warmup, sample_clocks=False):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop() if sampler else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), clocks
+        def step_e2e():
+            z_T = torch.randn((B, K_MIN, D), generator=gen, device=dev)
+            x = graph.run(host, z_T)                      # H2D of occ + start_goal from pinned memory inside the step
+            if go:
+                go.submit(x)
+            host_out.copy_(x, non_blocking=True)          # D2H of the samples
+            return x
 
-    ms_dev, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=(rank == 0))
-    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup // 2, 1))
+        return step_device, step_e2e, (go.join if go else None)
+
+    step_device, step_e2e, finish = make_steps(graph, B, dcond, host, host_out)
+    ms_dev, clocks = ctx.timed(step_device, args.steps, args.warmup, sample_clocks=(rank == 0), finish=finish)
+    ms_e2e, _ = ctx.timed(step_e2e, args.steps, max(args.warmup // 2, 1), finish=finish)
 
     # roofline of the dominant kernel: one instrumented eager step, every library call bracketed by CUDA events on the
     # launching stream (each L.call enqueues exactly one kernel), grouped by entry point
@@ -306,8 +472,9 @@ def run_ours(args):
             all_ms = sum(t[1] for t in dense.values())
             all_fl = sum(t[2] for t in dense.values())
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_encoder_fused_traffic.json")
-            if top in ("idb200_encoder_fused", "idb200_denoiser_fused") and os.path.exists(tpath) and B == 65536:
+            tpath = next((p for p in (os.path.join(ROOT, "profiles", f) for f in ("r02_encoder_fused_traffic.json", "r01_encoder_fused_traffic.json"))
+                          if os.path.exists(p)), None)
+            if top in ("idb200_encoder_fused", "idb200_denoiser_fused") and tpath and B == 65536 and args.model == "small":
                 # DRAM bytes (read + write) per launch from the committed ncu --set full captures of the same shapes:
                 # 19 Stage-1 launches (L = 8) + 1 Stage-2 launch (L = 64), averaged per launch
                 with open(tpath) as fh:
@@ -321,27 +488,68 @@ def run_ours(args):
                     "all_dense_kernels": {"achieved": all_fl / (all_ms * 1e-3) / 1e12, "frac": all_fl / (all_ms * 1e-3) / 1e12 / pk["bf16"],
                                           "share_of_step": all_ms / total_ms}}
 
+    per_step = ms_dev / args.steps
+    value = world * B / (per_step * 1e-3)
+    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+
+    def guarded(name, fn):
+        """A secondary section must never take the headline line down with it."""
+        try:
+            extras[name] = fn()
+        except Exception as exc:                           # noqa: BLE001 -- reported in the line
+            extras[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        torch.cuda.empty_cache()
+
+    # strong scaling of the same workload (SURVEY 8d cfg 3: "B = 65 536 per run, sharded B/N per GPU")
+    if "strong" in sections:
+        def strong():
+            GB = args.strong_batch
+            if world == 1 and GB == B:
+                return {"global_batch": GB, "batch_per_gpu": GB, "ms_per_step": per_step, "trajectories_per_s": value,
+                        "e2e_trajectories_per_s": e2e_value, "note": "N = 1: the weak and strong workloads coincide"}
+            Bs = GB // world
+            g2 = GenerationGraph(kp, il, Bs, cfg, device=dev).capture()
+            h2 = synthetic_cond(Bs, 3000 + rank, pin=True)
+            ho2 = torch.empty((Bs, T, D), dtype=torch.float32).pin_memory()
+            d2 = {k: v.to(dev) for k, v in h2.items()}
+            sd, se, fin = make_steps(g2, Bs, d2, h2, ho2)
+            m1, _ = ctx.timed(sd, args.steps, args.warmup, finish=fin)
+            m2, _ = ctx.timed(se, args.steps, max(args.warmup // 2, 1), finish=fin)
+            return {"global_batch": Bs * world, "batch_per_gpu": Bs, "ms_per_step": m1 / args.steps,
+                    "trajectories_per_s": Bs * world / (m1 / args.steps * 1e-3), "e2e_trajectories_per_s": Bs * world / (m2 / args.steps * 1e-3),
+                    "tiles_per_gpu_stage1": Bs * K_MIN // 128, "tiles_per_gpu_stage2": Bs * T // 128}
+        guarded("strong", strong)
+    del graph
+    torch.cuda.empty_cache()
+    if "long_horizon" in sections:
+        guarded("long_horizon", lambda: section_long_horizon(ctx, args))
+    if "train" in sections:
+        guarded("train", lambda: section_train(ctx, args))
+
     if rank == 0:
-        cpu_rate, cpu_dt, cores = cpu_reference_rate(args.cpu_sample, steps=1, warmup=0) if world == 1 and not args.skip_cpu else (None, None, None)
-        per_step = ms_dev / args.steps
-        value = world * B / (per_step * 1e-3)
-        e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+        cpu = cpu_reference_rate(args.cpu_sample, steps=1, warmup=0) if world == 1 and not args.skip_cpu else None
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "generation: Stage-1 DDIM-20 K=8 + interp T=64 + Stage-2 one-step (x0), small model 256x8 ff1024, "
-                                   "clamp_policy=endpoints, D=2 (BASELINE.json configs[2])",
-                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"trajectory-sharded x{world}" + (" + NCCL all-gather of samples" if world > 1 else ""),
+            "config": {"workload": "generation: Stage-1 DDIM-20 K=8 + interp T=64 + Stage-2 one-step (x0), "
+                                   + ("small model 256x8 ff1024" if args.model == "small" else "large model 384x12 ff1536") +
+                                   ", clamp_policy=endpoints, D=2 (BASELINE.json configs[2])",
+                       "batch_per_gpu": B, "global_batch": world * B,
+                       "parallelism": f"trajectory-sharded x{world}" + (" + NCCL all-gather of samples on a side stream (joined inside the timed region)" if world > 1 else ""),
                        "cuda_graph": True, "l2": "per-step activation working set (~20 GB) >> 126 MB L2"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
+                    "includes_all_gather": world > 1},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roof, "kernels": breakdown, "interp": interp,
             "flops_per_traj_gemm": gemm_flops_per_traj(), "tflops_e2e": value * gemm_flops_per_traj() / 1e12,
         }
-        if cpu_rate is not None:
-            line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample} trajectories, one pass of the oracle port ({cpu_dt:.1f} s)"}
+        line.update(extras)
+        if cpu is not None:
+            cpu_rate, cpu_dt, cores, kind = cpu
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{args.cpu_sample} trajectories, one pass of the " +
+                                              ("unmodified reference (baseline/_ref)" if kind == "reference" else "oracle port") + f" ({cpu_dt:.1f} s)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -358,7 +566,12 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=512, help="trajectories per step of the reference arm")
     ap.add_argument("--model", default="small", choices=["small", "large"], help="small = BASELINE configs[2] (default); large = trainer-default models (dev)")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--skip-interp", action="store_true", help="skip the interp-kernel (configs[1]) measurement")
+    ap.add_argument("--sections", default="all", help="comma list of the secondary measurements carried in the line: interp (configs[1]), "
+                    "strong (configs[2], global batch sharded), long_horizon (configs[4]), train (configs[3]); 'none' = headline only")
+    ap.add_argument("--strong-batch", type=int, default=65536, help="global batch of the strong-scaling run")
+    ap.add_argument("--train-batch", type=int, default=4096, help="global batch of the training step (configs[3])")
+    ap.add_argument("--train-steps", type=int, default=8)
+    ap.add_argument("--lh-batch", type=int, default=8192, help="global batch of the long-horizon run (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

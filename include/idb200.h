@@ -95,6 +95,23 @@ int idb200_corrupt_from_anchors(const float* source, const int64_t* idx, const i
                                 int clamp_endpoints, int recompute_velocity, float* out,
                                 idb200_stream_t stream);
 
+/* K1c, single launch for the whole batch: build_interp_adjacent_batch / build_interp_level_batch,
+ * src/train/train_interp_levels.py:227-383.  Row b uses level s = s_idx[b]: x_s = corrupt(Interp(source | M_s)), and when
+ * x_prev != NULL x_prev = corrupt(Interp(source | M_{s-1})); mask_s / mask_prev (uint8 [B,T], may be NULL) are the rows
+ * M_s / M_{s-1}.  Rows with s outside [1, n_levels) are zero-filled (the reference's loop skips them).  The anchor lists
+ * are read off masks_levels [B, n_levels, T] (ascending set bits == idx_levels[s]).  sigma_levels / anchor_sigma_levels:
+ * HOST arrays [n_levels] (per-level sigma of :386-401 and sigma * corrupt_anchor_frac).  Noise:
+ *   parity mode  anchor_noise [B,2,Kmax,2] and path_noise [B,2,T,2] fp32 (slot 0 = x_s, slot 1 = x_prev), drawn by the caller;
+ *   Philox mode  both NULL: N(0,1) from Philox4x32-10 + Box-Muller keyed by (seed, offset, row, slot, kind, position);
+ *                anchor_noise_out / path_noise_out (same layouts, may be NULL) export what was drawn.
+ * Index jitter (:471-483) is not handled here (callers with corrupt_index_jitter_max > 0 use idb200_corrupt_from_anchors). */
+int idb200_corrupt_adjacent(const float* source, const uint8_t* masks_levels, const int64_t* s_idx, int64_t B, int T, int D,
+                            int n_levels, const float* sigma_levels, const float* anchor_sigma_levels,
+                            const float* anchor_noise, const float* path_noise, int Kmax, uint64_t seed, uint64_t offset,
+                            float* anchor_noise_out, float* path_noise_out, int mode_dist, int clamp_endpoints,
+                            int recompute_velocity, float* x_s, float* x_prev, uint8_t* mask_s, uint8_t* mask_prev,
+                            idb200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2  DDIM update (+ known-value clamp), src/diffusion/ddpm.py:37-48 (eta = 0) fused with the
  *     torch.where at src/sample/sample_generate.py:397-399:
@@ -313,13 +330,14 @@ int idb200_conv_encoder_tc5(const float* occ, const float* sdf, int64_t B, int H
 /* loss = sum_bt(w * ||delta_hat - target||^2) / (sum_bt(w) * D + 1e-8) / grad_accum, w = w_missing + (w_anchor - w_missing) *
  * conf[b,t] (anchor_conf branch, conf fp32 [B,T]) or w_anchor / w_missing by mask[b,t] (uint8) -- exactly one of conf / mask.
  * loss_scal[0] = loss, loss_scal[1] = the common factor of the gradient; grad_out (or NULL) = d loss / d delta_hat [B,T,D].
- * scratch: 2 * 1184 doubles (per-block partial sums, reduced in a fixed order: deterministic). */
+ * scratch: idb200_tail_scratch_doubles() doubles (per-block partial sums, reduced in a fixed order: deterministic). */
+int64_t idb200_tail_scratch_doubles(void);   /* capacity both reduction entry points below need (their grids are clamped to it) */
 int idb200_stage2_loss(const float* delta_hat, const float* target, const float* conf, const uint8_t* mask, float w_anchor,
                        float w_missing, float grad_accum, int64_t B, int T, int D, double* scratch, float* loss_scal,
                        float* grad_out, idb200_stream_t stream);
 
 /* torch.nn.utils.clip_grad_norm_ over ONE flat gradient buffer: norm_coef[0] = ||grad||_2, norm_coef[1] = min(1, max_norm /
- * (norm + 1e-6)).  scratch: 1184 doubles.  The coefficient is consumed on the device by idb200_adamw_ema_step. */
+ * (norm + 1e-6)).  scratch: idb200_tail_scratch_doubles() doubles.  The coefficient is consumed on the device by idb200_adamw_ema_step. */
 int idb200_grad_clip_coef(const float* grad, int64_t n, float max_norm, double* scratch, float* norm_coef, idb200_stream_t stream);
 
 /* torch.optim.AdamW step (decoupled weight decay, bias-corrected, torch's operation order) on grad * norm_coef[1] (norm_coef
@@ -389,7 +407,8 @@ int idb200_pool_silu_bwd(const void* u, const float* dpooled, int64_t B, int P, 
  * (spatial tokens, extra tokens; key order does not matter), out bf16 [B,Lq,d]. */
 int idb200_cross_attention(const void* q, const void* kv_a, const void* kv_b, void* out, int64_t B, int Lq, int La, int Lb, int H,
                            idb200_stream_t stream);
-/* Gaussian start / goal maps (:113-146, sigma > 0): out fp32 [B,2,H,W] = exp(-((x - cx)^2 + (y - cy)^2) / (2 sigma^2)). */
+/* Start / goal maps (:113-146): out fp32 [B,2,H,W] = exp(-((x - cx)^2 + (y - cy)^2) / (2 sigma^2)) for sigma > 0, one-hot at the
+ * rounded (half-to-even) cell for sigma <= 0 (:129-139). */
 int idb200_sg_map(const float* start_goal, int64_t B, int H, int W, float sigma, float* out, idb200_stream_t stream);
 
 /* DP anchor placement, src/selection/epiplexity_dp.py:171-228 (dp_select_indices_batch): the producer of idx for

@@ -24,6 +24,8 @@ _SIGS = {
     "idb200_nested_masks_interp": [c_p, c_p, c_l, c_l, c_i, c_i, c_i, ctypes.POINTER(c_i), c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
     "idb200_interpolate_from_indices": [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p],
     "idb200_corrupt_from_anchors": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_f, c_f, c_i, c_i, c_i, c_p, c_p],
+    "idb200_corrupt_adjacent": [c_p, c_p, c_p, c_l, c_i, c_i, c_i, ctypes.POINTER(c_f), ctypes.POINTER(c_f), c_p, c_p, c_i, ctypes.c_uint64,
+                                ctypes.c_uint64, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "idb200_ddim_step": [c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_l, c_l, c_i, c_p, c_p, c_i, c_f, c_f, c_p, c_p],
     "idb200_q_sample": [c_p, c_p, c_p, c_p, c_p, c_i, c_l, c_l, c_p, c_p],
     "idb200_known_mask_values": [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p],
@@ -53,6 +55,7 @@ _SIGS = {
     "idb200_gemm_bf16_nn_splitk": [c_p, c_p, c_p, c_l, c_i, c_l, c_i, c_p],
     "idb200_transpose_bf16": [c_p, c_i, c_l, c_i, c_p, c_p],
     "idb200_colsum_scratch_floats": [c_l, c_i],
+    "idb200_tail_scratch_doubles": [],
     "idb200_colsum": [c_p, c_i, c_l, c_i, c_p, c_f, c_i, c_p, c_p],
     "idb200_reduce_rows": [c_p, c_i, c_l, c_f, c_i, c_p, c_p],
     "idb200_silu_bf16": [c_p, c_p, c_l, c_i, c_p, c_p],

@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(128) cross_attn_mma_kernel(const __nv_bfloat16
     }
 }
 
-// Gaussian start / goal maps of the selector (keypoint_selector.py:113-146), sigma > 0: out [B, 2, H, W]
+// Start / goal maps of the selector (keypoint_selector.py:113-146): out [B, 2, H, W].  inv_2sigma2 > 0: Gaussian bumps;
+// inv_2sigma2 <= 0 (the reference's sg_map_sigma <= 0 branch, :129-139): one-hot at the rounded cell (torch.round = half to even).
 __global__ void __launch_bounds__(256) sg_map_kernel(const float* __restrict__ sg, long long B, int Hh, int Ww, float inv_2sigma2,
                                                      float* __restrict__ out) {
     const long long total = B * 2 * Hh * Ww;
@@ -432,6 +433,11 @@ __global__ void __launch_bounds__(256) sg_map_kernel(const float* __restrict__ s
         const long long b = i / (2ll * Hh * Ww);
         const float cx = fminf(fmaxf(sg[b * 4 + which * 2 + 0], 0.0f), 1.0f) * static_cast<float>(Ww - 1);
         const float cy = fminf(fmaxf(sg[b * 4 + which * 2 + 1], 0.0f), 1.0f) * static_cast<float>(Hh - 1);
+        if (inv_2sigma2 <= 0.0f) {
+            const int xi = min(max(static_cast<int>(rintf(cx)), 0), Ww - 1), yi = min(max(static_cast<int>(rintf(cy)), 0), Hh - 1);
+            out[i] = (x == xi && y == yi) ? 1.0f : 0.0f;
+            continue;
+        }
         const float dx = static_cast<float>(x) - cx, dy = static_cast<float>(y) - cy;
         out[i] = expf(-(dx * dx + dy * dy) * inv_2sigma2);
     }
@@ -520,9 +526,9 @@ extern "C" int idb200_cross_attention(const void* q, const void* kv_a, const voi
 
 extern "C" int idb200_sg_map(const float* start_goal, int64_t B, int H, int W, float sigma, float* out, idb200_stream_t stream) {
     IDB_REQUIRE(start_goal && out, IDB200_EINVAL, "NULL pointer");
-    IDB_REQUIRE(B >= 0 && H >= 1 && W >= 1 && sigma > 0.0f, IDB200_EINVAL, "bad arguments (sigma must be > 0)");
+    IDB_REQUIRE(B >= 0 && H >= 1 && W >= 1, IDB200_EINVAL, "bad arguments");
     if (B == 0) return IDB200_OK;
-    sg_map_kernel<<<grid_for(B * 2 * H * W, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(start_goal, B, H, W,
-                                                                                                      1.0f / (2.0f * sigma * sigma), out);
+    sg_map_kernel<<<grid_for(B * 2 * H * W, 256 * 4, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        start_goal, B, H, W, sigma > 0.0f ? 1.0f / (2.0f * sigma * sigma) : 0.0f, out);
     return check_launch("sg_map_kernel");
 }

@@ -17,9 +17,16 @@ namespace idb200 {
 
 constexpr int kThreads = 256;
 
+// schedule-table index of a timestep: torch's indexing wraps negatives once; anything still outside [0, n) is clamped so a
+// bad timestep can never read outside the table (the reference raises IndexError: the Python mirror's check_t does too)
+__device__ __forceinline__ long long table_index(long long t, int n) {
+    if (t < 0) t += n;
+    return t < 0 ? 0 : (t >= n ? n - 1 : t);
+}
+
 __global__ void __launch_bounds__(kThreads) ddim_step_kernel(
     const float* __restrict__ z, const float* __restrict__ eps, const long long* __restrict__ t,
-    const long long* __restrict__ t_prev, const float* __restrict__ alpha_bar, float ab_t_s, float ab_p_s, long long n,
+    const long long* __restrict__ t_prev, const float* __restrict__ alpha_bar, int n_train, float ab_t_s, float ab_p_s, long long n,
     long long row_len, int D, const unsigned char* __restrict__ known_mask, const float* __restrict__ known_values,
     int pos_clip, float clip_min, float clip_max, float* __restrict__ out) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -27,8 +34,8 @@ __global__ void __launch_bounds__(kThreads) ddim_step_kernel(
         float ab_t = ab_t_s, ab_p = ab_p_s;
         if (t) {
             const long long row = i / row_len;
-            ab_t = __ldg(alpha_bar + t[row]);
-            ab_p = __ldg(alpha_bar + t_prev[row]);
+            ab_t = __ldg(alpha_bar + table_index(t[row], n_train));
+            ab_p = __ldg(alpha_bar + table_index(t_prev[row], n_train));
         }
         const float e = eps[i];
         // x0 = (rt - sqrt(1 - ab_t) * eps) / sqrt(ab_t)                       ddpm.py:45
@@ -81,11 +88,11 @@ __global__ void __launch_bounds__(kThreads) ddim_step_scalar4_kernel(
 
 __global__ void __launch_bounds__(kThreads) q_sample_kernel(const float* __restrict__ r0, const float* __restrict__ noise,
                                                             const long long* __restrict__ t, const float* __restrict__ sab,
-                                                            const float* __restrict__ s1m, long long n, long long row_len,
+                                                            const float* __restrict__ s1m, int n_train, long long n, long long row_len,
                                                             float* __restrict__ out) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const long long tt = t[i / row_len];
+        const long long tt = table_index(t[i / row_len], n_train);
         out[i] = __fadd_rn(__fmul_rn(__ldg(sab + tt), r0[i]), __fmul_rn(__ldg(s1m + tt), noise[i]));  // ddpm.py:24
     }
 }
@@ -276,7 +283,7 @@ extern "C" int idb200_ddim_step(const float* z, const float* eps, const int64_t*
         return check_launch("ddim_step_scalar4_kernel");
     }
     ddim_step_kernel<<<ew_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        z, eps, reinterpret_cast<const long long*>(t), reinterpret_cast<const long long*>(t_prev), alpha_bar, ab_t, ab_prev,
+        z, eps, reinterpret_cast<const long long*>(t), reinterpret_cast<const long long*>(t_prev), alpha_bar, n_train, ab_t, ab_prev,
         n, row_len, D, known_mask, known_values, pos_clip, clip_min, clip_max, z_out);
     return check_launch("ddim_step_kernel");
 }
@@ -289,7 +296,7 @@ extern "C" int idb200_q_sample(const float* r0, const float* noise, const int64_
     const long long n = n_rows * row_len;
     if (n == 0) return IDB200_OK;
     q_sample_kernel<<<ew_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        r0, noise, reinterpret_cast<const long long*>(t), sqrt_ab, sqrt_1m_ab, n, row_len, out);
+        r0, noise, reinterpret_cast<const long long*>(t), sqrt_ab, sqrt_1m_ab, n_train, n, row_len, out);
     return check_launch("q_sample_kernel");
 }
 

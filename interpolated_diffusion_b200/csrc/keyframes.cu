@@ -688,6 +688,168 @@ __global__ void __launch_bounds__(128) corrupt_from_anchors_kernel(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K1c, single launch: build_interp_adjacent_batch / build_interp_level_batch (train_interp_levels.py:227-383) for the
+// WHOLE batch -- each row picks its own level s = s_idx[row], so K_s, sigma_s and the anchor set are per-row quantities and
+// there is no per-level python loop, boolean-mask gather or host sync.  One CTA per row; the anchor list of level s (and
+// s - 1 for x_prev) is compacted from the row's nested mask by a ballot scan (the masks ARE the index lists: idx_levels[s]
+// is the ascending set of M_s), then the body is corrupt_from_anchors_kernel's: noisy anchors, interpolation, tent-weighted
+// path noise, velocity.  Noise: either PROVIDED (parity mode: the caller drew it with the reference's generator calls;
+// per-row layout anchor_noise [B, 2, Kmax, 2], path_noise [B, 2, T, 2], slot 0 = x_s, slot 1 = x_prev) or drawn in the
+// kernel from Philox4x32-10 + Box-Muller keyed by (seed, offset | row, slot, kind, position) (speed mode: same
+// distribution, not the reference's stream); the drawn noise can be exported in the provided-noise layout, which makes the
+// two modes checkable against each other bit for bit.
+// ------------------------------------------------------------------------------------------------
+struct AdjParams {
+    const float* source;
+    const unsigned char* masks;       // [B, n_levels, T]
+    const long long* s_idx;           // [B]
+    const float* anchor_noise;        // [B, 2, Kmax, 2] or nullptr
+    const float* path_noise;          // [B, 2, T, 2] or nullptr
+    float* anchor_noise_out;          // export (Philox mode) or nullptr
+    float* path_noise_out;
+    unsigned long long seed, offset;
+    float sigma[kMaxLevels + 1];
+    float anchor_sigma[kMaxLevels + 1];
+    long long B;
+    int T, D, n_levels, Kmax, mode_dist, clamp_endpoints, vel, philox, adjacent;
+    float dt;
+    float* x_s;
+    float* x_prev;
+    unsigned char* mask_s;
+    unsigned char* mask_prev;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// two independent N(0,1) draws for (row, slot, kind, pos): counter = (pos, kind | slot << 1 | offset_lo << 2, row_lo, row_hi ^ offset_hi)
+__device__ __forceinline__ float2 philox_normal2(const AdjParams& p, long long row, int slot, int kind, int pos) {
+    const uint4 ctr = make_uint4(static_cast<unsigned>(pos), static_cast<unsigned>(kind | (slot << 1)) | (static_cast<unsigned>(p.offset) << 2),
+                                 static_cast<unsigned>(row), static_cast<unsigned>(static_cast<unsigned long long>(row) >> 32) ^ static_cast<unsigned>(p.offset >> 30));
+    const uint4 r = philox4x32_10(ctr, make_uint2(static_cast<unsigned>(p.seed), static_cast<unsigned>(p.seed >> 32)));
+    const float u1 = __fmul_rn(__fadd_rn(static_cast<float>(r.x >> 8), 0.5f), 5.9604644775390625e-8f);     // (0, 1): 24 bits + 1/2 ulp
+    const float u2 = __fmul_rn(__fadd_rn(static_cast<float>(r.y >> 8), 0.5f), 5.9604644775390625e-8f);
+    const float rad = sqrtf(__fmul_rn(-2.0f, logf(u1)));
+    float sn, cs;
+    sincospif(__fmul_rn(2.0f, u2), &sn, &cs);
+    return make_float2(__fmul_rn(rad, cs), __fmul_rn(rad, sn));
+}
+
+__global__ void __launch_bounds__(128) corrupt_adjacent_kernel(const AdjParams p) {
+    extern __shared__ int smem_i[];
+    int* sidx = smem_i;                                          // [T]
+    float* svals = reinterpret_cast<float*>(smem_i + p.T);       // [T * D]
+    float* spos = svals + p.T * p.D;                             // [T * 2]
+    __shared__ int sK;
+    const int T = p.T, D = p.D;
+    for (long long row = blockIdx.x; row < p.B; row += gridDim.x) {
+        const long long s = p.s_idx[row];
+        const float* src = p.source + row * T * D;
+        for (int slot = 0; slot < (p.adjacent ? 2 : 1); ++slot) {
+            float* orow = (slot ? p.x_prev : p.x_s) + row * T * D;
+            unsigned char* mrow_out = slot ? p.mask_prev : p.mask_s;
+            const long long lvl = s - slot;
+            if (s < 1 || s >= p.n_levels) {                      // rows outside 1..levels stay zero (:328 loops s = 1..levels)
+                for (int i = threadIdx.x; i < T * D; i += blockDim.x) orow[i] = 0.0f;
+                if (mrow_out) for (int t = threadIdx.x; t < T; t += blockDim.x) mrow_out[row * T + t] = 0;
+                continue;
+            }
+            const unsigned char* mrow = p.masks + (row * p.n_levels + lvl) * T;
+            __syncthreads();                                     // previous slot / row is done with the shared lists
+            if (threadIdx.x < 32) {                              // ordered compaction of the set bits (ascending t)
+                int base = 0;
+                for (int c = 0; c < T; c += 32) {
+                    const int t = c + threadIdx.x;
+                    const bool bit = t < T && mrow[t] != 0;
+                    const unsigned b = __ballot_sync(0xffffffffu, bit);
+                    if (bit) sidx[base + __popc(b & ((1u << threadIdx.x) - 1u))] = t;
+                    base += __popc(b);
+                }
+                if (threadIdx.x == 0) sK = base;
+            }
+            __syncthreads();
+            const int K = sK;
+            if (mrow_out) for (int t = threadIdx.x; t < T; t += blockDim.x) mrow_out[row * T + t] = mrow[t];
+            if (K < 2) {                                         // cannot happen for masks with endpoints; keep the row defined
+                for (int i = threadIdx.x; i < T * D; i += blockDim.x) orow[i] = 0.0f;
+                continue;
+            }
+            const float sigma = p.sigma[lvl], asig = p.anchor_sigma[lvl];
+            const long long nslot = row * 2 + slot;
+            for (int k = threadIdx.x; k < K; k += blockDim.x) {  // :484-494 (index jitter is not supported here: host falls back)
+                const int g = sidx[k];
+                float nz[2] = {0.0f, 0.0f};
+                if (asig > 0.0f) {
+                    if (p.philox) {
+                        const float2 n2 = philox_normal2(p, row, slot, 0, k);
+                        nz[0] = n2.x; nz[1] = n2.y;
+                        if (p.anchor_noise_out) { p.anchor_noise_out[(nslot * p.Kmax + k) * 2] = n2.x; p.anchor_noise_out[(nslot * p.Kmax + k) * 2 + 1] = n2.y; }
+                    } else {
+                        nz[0] = p.anchor_noise[(nslot * p.Kmax + k) * 2];
+                        nz[1] = p.anchor_noise[(nslot * p.Kmax + k) * 2 + 1];
+                    }
+                }
+                const bool endp = p.clamp_endpoints && (g == 0 || g == T - 1);
+                for (int d = 0; d < D; ++d) {
+                    float v = src[static_cast<long long>(g) * D + d];
+                    if (asig > 0.0f && d < 2) v = __fadd_rn(v, endp ? 0.0f : __fmul_rn(nz[d], asig));
+                    svals[k * D + d] = v;
+                }
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < T; t += blockDim.x) {
+                float nz[2] = {0.0f, 0.0f};
+                float alpha = 1.0f;
+                if (sigma > 0.0f) {                              // :496-504
+                    if (p.philox) {
+                        const float2 n2 = philox_normal2(p, row, slot, 1, t);
+                        nz[0] = n2.x; nz[1] = n2.y;
+                        if (p.path_noise_out) { p.path_noise_out[(nslot * T + t) * 2] = n2.x; p.path_noise_out[(nslot * T + t) * 2 + 1] = n2.y; }
+                    } else {
+                        nz[0] = p.path_noise[(nslot * T + t) * 2];
+                        nz[1] = p.path_noise[(nslot * T + t) * 2 + 1];
+                    }
+                    if (p.mode_dist) {                           // _distance_alpha :444-455
+                        const int cnt = upper_bound_smem(sidx, K, t);
+                        const int seg = min(max(cnt - 1, 0), K - 2);
+                        const int l = sidx[seg], rr = sidx[seg + 1];
+                        const int gap = max(rr - l, 1);
+                        const int dist = min(t - l, rr - t);
+                        alpha = __fdiv_rn(__fmul_rn(2.0f, static_cast<float>(dist)), static_cast<float>(gap));
+                        alpha = fminf(fmaxf(alpha, 0.0f), 1.0f);
+                    }
+                }
+                for (int d = 0; d < D; ++d) {
+                    if (p.vel && d >= 2) continue;
+                    float x = interp_eval(sidx, svals, K, D, t, d);
+                    if (sigma > 0.0f && d < 2) x = __fadd_rn(x, __fmul_rn(__fmul_rn(nz[d], sigma), alpha));
+                    if (p.vel && d < 2) spos[t * 2 + d] = x;
+                    orow[t * D + d] = x;
+                }
+            }
+            if (p.vel) {                                         // :505-509
+                __syncthreads();
+                for (int i = threadIdx.x; i < T * 2; i += blockDim.x) {
+                    const int t = i >> 1, d = i & 1;
+                    const float v = (t == T - 1) ? 0.0f : __fdiv_rn(__fsub_rn(spos[(t + 1) * 2 + d], spos[t * 2 + d]), p.dt);
+                    orow[t * D + 2 + d] = v;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace idb200
 
 using namespace idb200;
@@ -785,4 +947,36 @@ extern "C" int idb200_corrupt_from_anchors(const float* source, const int64_t* i
         reinterpret_cast<const long long*>(row_index), B, K, T, D, sigma, anchor_sigma, mode_dist, clamp_endpoints, vel,
         static_cast<float>(1.0 / static_cast<double>(T)), out);
     return check_launch("corrupt_from_anchors_kernel");
+}
+
+extern "C" int idb200_corrupt_adjacent(const float* source, const uint8_t* masks_levels, const int64_t* s_idx, int64_t B, int T, int D,
+                                       int n_levels, const float* sigma_levels, const float* anchor_sigma_levels,
+                                       const float* anchor_noise, const float* path_noise, int Kmax, uint64_t seed, uint64_t offset,
+                                       float* anchor_noise_out, float* path_noise_out, int mode_dist, int clamp_endpoints,
+                                       int recompute_velocity, float* x_s, float* x_prev, uint8_t* mask_s, uint8_t* mask_prev,
+                                       idb200_stream_t stream) {
+    IDB_REQUIRE(B >= 0 && D >= 1 && T >= 2, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(n_levels >= 2 && n_levels <= kMaxLevels + 1, IDB200_EUNSUPPORTED, "n_levels must be in [2,%d]", kMaxLevels + 1);
+    IDB_REQUIRE(B == 0 || (source && masks_levels && s_idx && x_s && sigma_levels && anchor_sigma_levels), IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE((anchor_noise == nullptr) == (path_noise == nullptr), IDB200_EINVAL, "anchor_noise and path_noise must both be given (parity mode) or both NULL (Philox mode)");
+    IDB_REQUIRE(Kmax >= 2 && Kmax <= T, IDB200_EINVAL, "Kmax must be in [2, T]");
+    bool any_noise = false;
+    for (int l = 0; l < n_levels; ++l) any_noise = any_noise || sigma_levels[l] > 0.0f || anchor_sigma_levels[l] > 0.0f;
+    IDB_REQUIRE(!any_noise || D >= 2, IDB200_EINVAL, "noise needs D >= 2");
+    const size_t smem = sizeof(int) * T + sizeof(float) * (static_cast<size_t>(T) * D + 2 * static_cast<size_t>(T));
+    IDB_REQUIRE(smem <= 48 * 1024, IDB200_EUNSUPPORTED, "T*D too large for one CTA (%zu bytes)", smem);
+    if (B == 0) return IDB200_OK;
+    AdjParams p{};
+    p.source = source; p.masks = masks_levels; p.s_idx = reinterpret_cast<const long long*>(s_idx);
+    p.anchor_noise = anchor_noise; p.path_noise = path_noise; p.anchor_noise_out = anchor_noise_out; p.path_noise_out = path_noise_out;
+    p.seed = seed; p.offset = offset;
+    for (int l = 0; l < n_levels; ++l) { p.sigma[l] = sigma_levels[l]; p.anchor_sigma[l] = anchor_sigma_levels[l]; }
+    p.B = B; p.T = T; p.D = D; p.n_levels = n_levels; p.Kmax = Kmax; p.mode_dist = mode_dist; p.clamp_endpoints = clamp_endpoints;
+    p.vel = (recompute_velocity && D == 4) ? 1 : 0;
+    p.philox = anchor_noise == nullptr ? 1 : 0;
+    p.adjacent = x_prev != nullptr ? 1 : 0;
+    p.dt = static_cast<float>(1.0 / static_cast<double>(T));
+    p.x_s = x_s; p.x_prev = x_prev; p.mask_s = mask_s; p.mask_prev = mask_prev;
+    corrupt_adjacent_kernel<<<grid_for(B, 1, 16), 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("corrupt_adjacent_kernel");
 }

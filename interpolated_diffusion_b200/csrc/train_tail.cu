@@ -138,6 +138,14 @@ __global__ void __launch_bounds__(kThreads) adamw_ema_kernel(float* __restrict__
 
 using namespace idb200;
 
+// The reduction kernels write one (loss: two) fp64 partial per block into a caller-provided scratch buffer whose size is a
+// CONTRACT of the C ABI (idb200_tail_scratch_doubles): the grid is clamped to that capacity, so a device with more SMs than
+// the B200's 148 can never overrun a buffer sized by the exported count.
+static constexpr int kTailMaxBlocks = 2048;
+static inline int tail_grid(int grid) { return grid < kTailMaxBlocks ? grid : kTailMaxBlocks; }
+
+extern "C" int64_t idb200_tail_scratch_doubles() { return 2 * static_cast<int64_t>(kTailMaxBlocks); }
+
 extern "C" int idb200_stage2_loss(const float* delta_hat, const float* target, const float* conf, const uint8_t* mask, float w_anchor,
                                   float w_missing, float grad_accum, int64_t B, int T, int D, double* scratch, float* loss_scal,
                                   float* grad_out, idb200_stream_t stream) {
@@ -146,7 +154,7 @@ extern "C" int idb200_stage2_loss(const float* delta_hat, const float* target, c
     IDB_REQUIRE(B >= 1 && T >= 1 && D >= 1 && grad_accum > 0.0f, IDB200_EINVAL, "bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long BT = static_cast<long long>(B) * T;
-    const int grid = grid_for(BT, tt::kThreads, 8);
+    const int grid = tail_grid(grid_for(BT, tt::kThreads, 8));
     tt::loss_partial_kernel<<<grid, tt::kThreads, 0, st>>>(delta_hat, target, conf, mask, w_anchor, w_missing, BT, D, scratch);
     tt::loss_final_kernel<<<1, 32, 0, st>>>(scratch, grid, D, grad_accum, loss_scal);
     if (grad_out) tt::loss_grad_kernel<<<grid, tt::kThreads, 0, st>>>(delta_hat, target, conf, mask, w_anchor, w_missing, BT, D, loss_scal, grad_out);
@@ -159,7 +167,7 @@ extern "C" int idb200_grad_clip_coef(const float* grad, int64_t n, float max_nor
     IDB_REQUIRE(aligned(grad, 16), IDB200_EALIGN, "grad must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long n4 = n / 4;
-    const int grid = grid_for(n4 > 0 ? n4 : 1, tt::kThreads * 4, 8);
+    const int grid = tail_grid(grid_for(n4 > 0 ? n4 : 1, tt::kThreads * 4, 8));
     tt::sq_norm_partial_kernel<<<grid, tt::kThreads, 0, st>>>(reinterpret_cast<const float4*>(grad), n4, grad + n4 * 4, static_cast<int>(n - n4 * 4), scratch);
     tt::clip_final_kernel<<<1, 32, 0, st>>>(scratch, grid, max_norm, norm_coef);
     return check_launch("grad_clip kernels");

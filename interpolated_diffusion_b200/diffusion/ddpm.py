@@ -27,7 +27,20 @@ def _table(schedule: Dict[str, torch.Tensor], key: str, dev: torch.device) -> to
     return tab
 
 
-def q_sample(r0: torch.Tensor, t: torch.Tensor, schedule: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None):
+def _check_timesteps(t: torch.Tensor, t_prev: Optional[torch.Tensor], n_train: int) -> None:
+    """The reference's table gather raises IndexError for a timestep outside [0, n_train) (ddpm.py:6-12); the kernels clamp
+    the table index instead of reading out of bounds.  ``check_t=True`` restores the reference's error at the cost of one
+    host sync (off on the hot path, where the timesteps come from ``_timesteps``)."""
+    lo = int(t.min().item()) if t.numel() else 0
+    hi = int(t.max().item()) if t.numel() else 0
+    if t_prev is not None and t_prev.numel():
+        lo, hi = min(lo, int(t_prev.min().item())), max(hi, int(t_prev.max().item()))
+    if lo < -n_train or hi >= n_train:
+        raise IndexError(f"timestep out of range for a schedule of {n_train} steps (got [{lo}, {hi}])")
+
+
+def q_sample(r0: torch.Tensor, t: torch.Tensor, schedule: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None, *,
+             check_t: bool = False):
     """ddpm.py:15-24"""
     dev = L.require_cuda(r0, t)
     if noise is None:
@@ -36,6 +49,8 @@ def q_sample(r0: torch.Tensor, t: torch.Tensor, schedule: Dict[str, torch.Tensor
     n_rows, row_len = _row_shape(r0c, tc)
     sab = _table(schedule, "sqrt_alpha_bar", dev)
     s1m = _table(schedule, "sqrt_one_minus_alpha_bar", dev)
+    if check_t:
+        _check_timesteps(tc, None, sab.numel())
     out = torch.empty_like(r0c)
     L.call("idb200_q_sample", L.ptr(r0c), L.ptr(nc), L.ptr(tc), L.ptr(sab), L.ptr(s1m), sab.numel(), n_rows, row_len,
            L.ptr(out), L.stream(dev))
@@ -45,7 +60,7 @@ def q_sample(r0: torch.Tensor, t: torch.Tensor, schedule: Dict[str, torch.Tensor
 def ddim_step(rt: torch.Tensor, eps: torch.Tensor, t: torch.Tensor, t_prev: torch.Tensor,
               schedule: Dict[str, torch.Tensor], eta: float = 0.0, *, known_mask: Optional[torch.Tensor] = None,
               known_values: Optional[torch.Tensor] = None, pos_clip: bool = False, pos_clip_min: float = 0.0,
-              pos_clip_max: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              pos_clip_max: float = 1.0, out: Optional[torch.Tensor] = None, check_t: bool = False) -> torch.Tensor:
     """ddpm.py:37-57.  eta == 0 (the hot path) is one launch, optionally fused with the known-value clamp of
     sample_generate.py:397-399 (keyword-only extras).  The stochastic branch (eta != 0, unused on the hot
     path) composes the same kernel with the reference's sigma formula."""
@@ -53,13 +68,27 @@ def ddim_step(rt: torch.Tensor, eps: torch.Tensor, t: torch.Tensor, t_prev: torc
     rtc, ec, tc, tpc = L.f32c(rt), L.f32c(eps), L.i64c(t), L.i64c(t_prev)
     n_rows, row_len = _row_shape(rtc, tc)
     ab = _table(schedule, "alpha_bar", dev)
+    if check_t:
+        _check_timesteps(tc, tpc, ab.numel())
     if eta != 0.0:
+        # stochastic branch (ddpm.py:50-57; not on the hot path): torch composition with the reference's sigma formula,
+        # followed by the same keyword extras the fused kernel applies (known-value clamp, position clip, out=)
         shape = list(tc.shape) + [1] * (rtc.dim() - tc.dim())
         ab_t, ab_p = ab[tc].view(shape), ab[tpc].view(shape)
         x0 = (rtc - torch.sqrt(1.0 - ab_t) * ec) / torch.sqrt(ab_t)
         sigma = eta * torch.sqrt((1.0 - ab_p) / (1.0 - ab_t)) * torch.sqrt(1.0 - ab_t / ab_p)
         noise = torch.randn_like(rtc)
-        return torch.sqrt(ab_p) * x0 + torch.sqrt(1.0 - ab_p - sigma ** 2) * ec + sigma * noise
+        res = torch.sqrt(ab_p) * x0 + torch.sqrt(1.0 - ab_p - sigma ** 2) * ec + sigma * noise
+        if known_mask is not None:
+            if known_values is None:
+                raise ValueError("known_mask needs known_values")
+            res = torch.where(known_mask, L.f32c(known_values), res)
+        if pos_clip:
+            res[..., :2] = res[..., :2].clamp(min=pos_clip_min, max=pos_clip_max)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
     if out is None:
         out = torch.empty_like(rtc)
     km = L.u8c(known_mask) if known_mask is not None else None

@@ -137,11 +137,24 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, Lseq: int, H: int, c
     return out
 
 
+# number of CUDA graphs captured so far in this process (sample.GenerationGraph / train.GraphedStep bump it).  A captured
+# graph bakes device addresses in: once one exists, a Workspace never frees a buffer it outgrows (see Workspace.get).
+GRAPHS_CAPTURED = 0
+
+
+def note_graph_captured() -> None:
+    global GRAPHS_CAPTURED
+    GRAPHS_CAPTURED += 1
+
+
 class Workspace:
-    """Grow-only device buffers keyed by name (stable addresses once sized: CUDA-graph friendly)."""
+    """Grow-only device buffers keyed by name (stable addresses once sized: CUDA-graph friendly).  When a larger request
+    replaces a buffer after a CUDA graph has been captured, the old buffer is retired, not freed: a graph captured at the
+    smaller shape keeps replaying into memory that still belongs to this workspace (never into re-allocated memory)."""
 
     def __init__(self):
         self.bufs: Dict[str, torch.Tensor] = {}
+        self.retired: List[torch.Tensor] = []
 
     def get(self, name: str, shape, dtype, device) -> torch.Tensor:
         n = 1
@@ -149,6 +162,8 @@ class Workspace:
             n *= int(s)
         buf = self.bufs.get(name)
         if buf is None or buf.numel() < n or buf.dtype != dtype or buf.device != device:
+            if buf is not None and GRAPHS_CAPTURED > 0:
+                self.retired.append(buf)
             buf = torch.empty((max(n, 1),), dtype=dtype, device=device)
             self.bufs[name] = buf
         return buf[:n].view(*shape)

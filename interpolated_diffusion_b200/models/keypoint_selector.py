@@ -2,7 +2,8 @@
 same constructor, parameter tree (``state_dict`` keys / shapes) and ``forward(cond) -> logits [B, T]``; the forward runs on
 libidb200: Gaussian start/goal maps, the spatial conv stack as im2col + tcgen05 GEMM, the 1x1 projection / K|V / Q / out / MLP
 token GEMMs on tcgen05, LayerNorm, and cross attention over the H*W (+ extra) memory tokens by ``idb200_cross_attention``.
-bf16 tensor-core path only (fp32 accumulate).  ``use_cond_bias`` is not implemented (raises)."""
+bf16 tensor-core path only (fp32 accumulate).  ``use_cond_bias`` (both ``cond_bias_mode``s, :101-111, :170-175) and one-hot
+start / goal maps (``sg_map_sigma <= 0``, :129-139) are covered."""
 from typing import Dict
 
 import torch
@@ -32,17 +33,13 @@ class KeypointSelector(nn.Module):
                  cond_bias_mode: str = "memory", use_level: bool = False, level_mode: str = "k_norm", sg_map_sigma: float = 1.5,
                  maze_channels: tuple = (32, 64)) -> None:
         super().__init__()
-        if use_cond_bias:
-            raise NotImplementedError("KeypointSelector(use_cond_bias=True) is not implemented on the B200 path")
         if d_model // n_heads != 32 or d_model % n_heads != 0:
             raise ValueError("the B200 attention kernels are specialised for head_dim == 32")
         if d_model % 64 != 0 or d_ff % 64 != 0 or any(c % 32 != 0 for c in maze_channels) or maze_channels[-1] % 64 != 0:
             raise ValueError("d_model, d_ff and the last conv width must be multiples of 64, conv widths multiples of 32")
-        if float(sg_map_sigma) <= 0 and use_start_goal and use_sg_map:
-            raise NotImplementedError("sg_map_sigma <= 0 (one-hot maps) is not implemented on the B200 path")
         self.T, self.d_model, self.n_heads, self.pos_dim = int(T), int(d_model), int(n_heads), int(pos_dim)
         self.use_sdf, self.use_start_goal, self.use_sg_map = bool(use_sdf), bool(use_start_goal), bool(use_sg_map)
-        self.use_sg_token, self.use_goal_dist_token, self.use_cond_bias = bool(use_sg_token), bool(use_goal_dist_token), False
+        self.use_sg_token, self.use_goal_dist_token, self.use_cond_bias = bool(use_sg_token), bool(use_goal_dist_token), bool(use_cond_bias)
         self.cond_bias_mode, self.use_level, self.level_mode = str(cond_bias_mode), bool(use_level), str(level_mode)
         self.sg_map_sigma = float(sg_map_sigma)
         in_channels = 1 + (1 if self.use_sdf else 0) + (2 if self.use_sg_map else 0)
@@ -64,6 +61,13 @@ class KeypointSelector(nn.Module):
             self.level_mlp = nn.Sequential(nn.Linear(1, d_model), nn.SiLU(), nn.Linear(d_model, d_model))
         self.cond_bias = None
         self.cond_enc = None
+        if self.use_cond_bias:                                        # keypoint_selector.py:101-111
+            self.cond_bias = nn.Sequential(nn.Linear(d_model, d_model), nn.SiLU(), nn.Linear(d_model, d_model))
+            if self.cond_bias_mode not in {"memory", "encoder"}:
+                raise ValueError(f"cond_bias_mode must be 'memory' or 'encoder', got {self.cond_bias_mode}")
+            if self.cond_bias_mode == "encoder":
+                self.cond_enc = MazeConditionEncoder(use_sdf=self.use_sdf, d_cond=d_model, use_start_goal=self.use_start_goal,
+                                                     maze_channels=maze_channels)
         self.blocks = nn.ModuleList([CrossAttnBlock(d_model, n_heads, d_ff, dropout=dropout) for _ in range(max(1, n_layers))])
         self.out = nn.Linear(d_model, 1)
         self._ws = E.Workspace()
@@ -122,6 +126,18 @@ class KeypointSelector(nn.Module):
             emb = torch.nn.functional.pad(emb, (0, 1))
         q0 = E.sgemm(emb, f(self.time_proj.weight), f(self.time_proj.bias))                      # [T, d]
         q = q0.unsqueeze(0).expand(B, T, d).contiguous()
+        if self.use_cond_bias:                                            # :170-175
+            if self.cond_bias_mode == "encoder":
+                cond_vec = self.cond_enc(cond)
+            else:
+                # mean over ALL memory tokens (extras + the H*W spatial tokens): fp32 token sums of the bf16 spatial memory
+                tot = torch.empty((B, d), device=dev, dtype=F32)
+                mem32 = mem.float()
+                L.call("idb200_token_sum", mem32.data_ptr(), B, P, d, tot.data_ptr(), L.stream(dev))
+                for e in extras:
+                    tot = tot + e
+                cond_vec = (tot / float(P + n_ex)).contiguous()
+            q = q + self._mlp2(self.cond_bias, cond_vec).unsqueeze(1)
         if self.use_level:
             if "level" not in cond:
                 raise ValueError("use_level is True but level missing from cond")

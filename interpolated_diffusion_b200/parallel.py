@@ -65,3 +65,31 @@ def all_reduce_sum_(flat: torch.Tensor, group=None, bucket_elems: int = 0) -> to
     for w in works:
         w.wait()
     return flat
+
+
+def broadcast_replica_state(tensors, step_count: int = 0, group=None, src: int = 0) -> int:
+    """Make every rank's replica state equal rank ``src``'s: the tensors (parameter arena, EMA, Adam moments) are broadcast in
+    place and the broadcast step count is returned.  DDP does this at construction; without it, ranks that built the model
+    with different seeds -- or of which only some loaded a checkpoint -- would silently all-reduce gradients taken at different
+    weights.  No-op for one process."""
+    if world_size(group) == 1:
+        return int(step_count)
+    for t in tensors:
+        if t is not None:
+            dist.broadcast(t, src=src, group=group)
+    dev = next((t.device for t in tensors if t is not None), torch.device("cpu"))
+    sc = torch.tensor([int(step_count)], dtype=torch.int64, device=dev)
+    dist.broadcast(sc, src=src, group=group)
+    return int(sc.item())
+
+
+def replicas_in_sync(flat: torch.Tensor, group=None) -> bool:
+    """True when every rank holds the same arena (compares an order-independent checksum pair: sum and sum of squares in fp64)."""
+    if world_size(group) == 1:
+        return True
+    f = flat.detach().double()
+    mine = torch.stack([f.sum(), (f * f).sum()])
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool(torch.equal(lo, hi))

@@ -298,7 +298,8 @@ def _uniform_idx_cache(B: int, T: int, K: int, dev):
     from ..corruptions import keyframes as kf
     key = (B, T, K, str(dev))
     if key not in _UNIFORM_IDX:
-        _UNIFORM_IDX.clear()                      # keep one shape (static addresses for graph replay)
+        # one entry per shape, never evicted: a captured GenerationGraph reads these tensors on every replay (8 B x K per
+        # trajectory; evicting on a new shape would free memory an older graph still points at)
         _UNIFORM_IDX[key] = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device=dev)
     return _UNIFORM_IDX[key]
 
@@ -338,6 +339,29 @@ def _cond_row(model, cond_vec: torch.Tensor, T: int, dev) -> torch.Tensor:
     return E.sgemm(cond_vec, model.cond_proj.weight.detach().float().contiguous(), der["bias_b"])
 
 
+def _captured_tensors(*roots):
+    """Every tensor reachable from the models' derived-tensor caches / packed encoders / workspaces (references, not copies)."""
+    seen, out, stack = set(), [], list(roots)
+    while stack:
+        o = stack.pop()
+        if o is None or id(o) in seen:
+            continue
+        seen.add(id(o))
+        if isinstance(o, torch.Tensor):
+            out.append(o)
+        elif isinstance(o, dict):
+            stack.extend(o.values())
+        elif isinstance(o, (list, tuple)):
+            stack.extend(o)
+        elif isinstance(o, torch.nn.Module):
+            for name in ("_cache", "_ws", "_packed", "_gemm_ws", "_w1_packed"):
+                stack.append(getattr(o, name, None))
+            stack.extend(o.children())
+        elif hasattr(o, "__dict__") and type(o).__module__.startswith("interpolated_diffusion_b200"):
+            stack.extend(v for k, v in vars(o).items() if k != "enc")
+    return out
+
+
 class GenerationGraph:
     """The whole generation call captured once as a single CUDA graph for a fixed batch shape (19 Stage-1
     evaluations + DDIM updates, sigmoid, interpolation, Stage-2, clamp: ~600 kernel launches replayed with one
@@ -362,6 +386,13 @@ class GenerationGraph:
             self.masks_levels, _ = kf.build_nested_masks_from_base(idx, T, self.cfg.levels)
         self.graph = None
         self.launches = 0
+        self._plist = [p for m in (kp_model, interp_model) for p in m.parameters()]
+        self._sig = None
+        self._owned = None
+
+    def _weights_sig(self):
+        from ..models import _engine as E
+        return E._sig(self._plist)
 
     def _body(self):
         generate(self.kp, self.il, self.cond, self.cfg, z_T=self.z_T, masks_levels=self.masks_levels, out=self.x_hat)
@@ -374,13 +405,23 @@ class GenerationGraph:
                 self._body()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        from ..models import _engine as E
+        E.note_graph_captured()                    # from here on workspaces retire (never free) buffers they outgrow
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._body()
+        # The graph reads tensors it does not allocate: packed bf16 weights, folded FiLM weights, timestep / level vectors,
+        # position tables, the uniform anchor rows.  They were produced by the warm-up (cache hits during capture), so the
+        # graph is only valid for the parameter version it was captured at: remember it (run() re-captures on a mismatch) and
+        # keep the captured tensors alive for as long as this graph exists.
+        self._sig = self._weights_sig()
+        self._owned = _captured_tensors(self.kp, self.il, E._CONV_WS, _UNIFORM_IDX.get((self.z_T.shape[0], self.cfg.T, self.cfg.K_min, str(self.dev))))
         return self
 
     def run(self, cond: Optional[Dict[str, torch.Tensor]] = None, z_T: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if self.graph is None:
+        if self.graph is None or self._sig != self._weights_sig():
+            # first use, or the weights changed since capture (optimizer step, EMA copy_to, load_state_dict): the captured
+            # launches point at packed copies of the OLD weights -- capture again instead of silently sampling stale weights
             self.capture()
         if cond is not None:
             for k, buf in self.cond.items():

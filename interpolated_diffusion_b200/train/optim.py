@@ -15,7 +15,12 @@ import torch
 
 from .. import _lib as L
 
-_SCRATCH_DOUBLES = 2 * 1184
+
+
+def _scratch_doubles() -> int:
+    """fp64 partial-sum slots the loss / grad-norm reductions need: asked of the library (their grids are clamped to it), not
+    derived from an assumed SM count."""
+    return int(L.lib().idb200_tail_scratch_doubles())
 
 
 def stage2_loss(delta_hat: torch.Tensor, target: torch.Tensor, weight_mask: torch.Tensor, *, anchor_conf: bool = True,
@@ -32,7 +37,7 @@ def stage2_loss(delta_hat: torch.Tensor, target: torch.Tensor, weight_mask: torc
         raise ValueError("weight_mask must be [B,T]")
     conf = L.f32c(weight_mask) if anchor_conf else None
     mask = None if anchor_conf else L.u8c(weight_mask)
-    scratch = torch.empty((_SCRATCH_DOUBLES,), device=dev, dtype=torch.float64)
+    scratch = torch.empty((_scratch_doubles(),), device=dev, dtype=torch.float64)
     scal = torch.empty((2,), device=dev, dtype=torch.float32)
     grad = torch.empty_like(dh) if want_grad else None
     L.call("idb200_stage2_loss", dh.data_ptr(), tg.data_ptr(), L.ptr(conf), L.ptr(mask), float(w_anchor), float(w_missing),
@@ -66,9 +71,18 @@ class FlatAdamW:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.ema = self.flat.clone() if ema_decay is not None else None
         self.grad = torch.zeros_like(self.flat)
-        self.scratch = torch.empty((_SCRATCH_DOUBLES,), device=dev, dtype=torch.float64)
+        self.scratch = torch.empty((_scratch_doubles(),), device=dev, dtype=torch.float64)
         self.norm_coef = torch.ones((2,), device=dev, dtype=torch.float32)
         self.step_count = 0
+
+    def sync_replicas(self, group=None, src: int = 0) -> None:
+        """Data parallel: broadcast rank ``src``'s parameters, EMA, Adam moments and step count to every rank (call after
+        construction -- the trainers do -- and after ``load_state_dict`` / a checkpoint load on any subset of ranks)."""
+        from .. import parallel as P
+        if P.world_size(group) == 1:
+            return
+        self.step_count = P.broadcast_replica_state([self.flat, self.ema, self.exp_avg, self.exp_avg_sq], self.step_count, group, src)
+        L.PARAM_EPOCH += 1                                  # the parameters may have changed behind torch's version counters
 
     def views(self, flat: torch.Tensor) -> List[torch.Tensor]:
         return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]
@@ -79,6 +93,10 @@ class FlatAdamW:
         return None if self.ema is None else self.views(self.ema)
 
     def gather_grads(self) -> torch.Tensor:
+        """Copies ``p.grad`` into the flat arena.  A parameter whose grad is None contributes ZEROS, so the fused step still
+        applies weight decay / moment decay to it and its step count advances with the arena's -- ``torch.optim.AdamW`` would
+        skip it.  On this path every parameter of both denoisers receives a gradient each step (tested:
+        test_gpu_backward), so the two agree; a model with unused parameters should exclude them from ``params``."""
         for p, g in zip(self.params, self.views(self.grad)):
             if p.grad is None:
                 g.zero_()

@@ -42,6 +42,8 @@ class GraphedStep:
                 for _ in range(2):
                     self.fn(*static[:n], scond)
             torch.cuda.current_stream().wait_stream(stream)
+            from ..models import _engine as E
+            E.note_graph_captured()                                 # workspaces retire (never free) buffers from here on
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 loss = self.fn(*static[:n], scond)
@@ -68,7 +70,8 @@ class Stage2Trainer:
                  bootstrap_logit_eps: float = 1e-5, bootstrap_ddim_steps: int = 5, bootstrap_ddim_schedule: str = "quadratic",
                  bootstrap_prob_start: float = 0.0, bootstrap_prob_end: float = 0.3, bootstrap_warmup_steps: int = 5000,
                  bootstrap_prob_cap: float = 0.5, bootstrap_mode: str = "batch", bootstrap_replace_prob: float = 0.5,
-                 clamp_endpoints_kp: Optional[bool] = None, selector_model=None, selector_level_mode: str = "k_norm"):
+                 clamp_endpoints_kp: Optional[bool] = None, selector_model=None, selector_level_mode: str = "k_norm",
+                 batch_mode: str = "reference_draws"):
         if stage2_mode not in ("adj", "x0"):
             raise ValueError("stage2_mode must be 'adj' or 'x0'")
         # mask policies of train_interp_levels.py:890-967.  The CLI default "random" is only reachable through --mask_policy_mix,
@@ -114,8 +117,17 @@ class Stage2Trainer:
                              p1=bootstrap_prob_end, warm=bootstrap_warmup_steps, cap=bootstrap_prob_cap, mode=bootstrap_mode,
                              replace=bootstrap_replace_prob,
                              clamp_kp=bool(clamp_endpoints if clamp_endpoints_kp is None else clamp_endpoints_kp))
+        # batch_mode: "reference_draws" (default) builds the batch with the reference's generator calls in the reference's order
+        # (per-level noise shapes -> one host sync per batch, 2 launches per level): bit-identical corruption under a shared
+        # generator state.  "fused" is the speed mode: level indices without the data-dependent draw count, ONE corruption launch
+        # for the whole batch with Philox noise drawn in the kernel (same distributions, a different random stream), no host sync.
+        if batch_mode not in ("reference_draws", "fused"):
+            raise ValueError("batch_mode must be 'reference_draws' or 'fused'")
+        self.batch_mode = batch_mode
+        self._noise_calls = 0
         self.step_index = 0
         self.pg = process_group
+        self.sync_replicas()                                   # DDP semantics: every replica starts from rank 0's state
         self.last_grad_norm: Optional[torch.Tensor] = None
         # cuda_graph: forward + loss + backward (~700 launches for the 12-layer model) are captured once per batch shape and
         # replayed; batch building (host-side level counts), the all-reduce and the optimiser (host-side step count) stay eager
@@ -127,6 +139,11 @@ class Stage2Trainer:
         self._next = None
 
     # ------------------------------------------------------------------------------------------------------------------
+    def sync_replicas(self, src: int = 0) -> None:
+        """Broadcast rank ``src``'s parameters / EMA / Adam moments / step count to all ranks of the process group (no-op for
+        one process).  Called at construction; call it again after loading a checkpoint."""
+        self.opt.sync_replicas(self.pg, src)
+
     def build_masks(self, x0: torch.Tensor, gen: torch.Generator, cond: Optional[dict] = None):
         """Nested anchor masks of the batch by ``kp_index_mode`` (train_interp_levels.py:890-967)."""
         from ..corruptions import keyframes as kf
@@ -227,8 +244,10 @@ class Stage2Trainer:
             if cond is None:
                 raise ValueError("the bootstrap branch needs the conditioning (Stage-1 sampling)")
             x0_used, student = self._bootstrap(x0, cond, idx_levels, gen)
-        s_idx = TI._sample_level_indices(B, c["levels"], gen, dev, c["level_sampling"], c["level_high_prob"])
         conf_t, conf_st, conf_e, conf_m = c["conf"]
+        if self.batch_mode == "fused" and not (self.corrupt["corrupt_index_jitter_max"] > 0 and self.corrupt["corrupt_index_jitter_prob"] > 0.0):
+            return self._build_batch_fused(x0, x0_used, student, masks_levels, gen)
+        s_idx = TI._sample_level_indices(B, c["levels"], gen, dev, c["level_sampling"], c["level_high_prob"])
         if c["stage2_mode"] == "adj":
             x_s, x_prev, mask_s, mask_prev, s_idx, _, _ = TI.build_interp_adjacent_batch(
                 x0, c["K_min"], c["levels"], gen, recompute_velocity=c["recompute_vel"], x0_override=x0_used, masks_levels=masks_levels,
@@ -251,6 +270,40 @@ class Stage2Trainer:
             conf_s = TI._anneal_conf(conf_s, s_idx, c["levels"], c["anneal_mode"])
         mask_in = torch.stack([mask_s.float(), conf_s], dim=-1) if c["anchor_conf"] else mask_s
         return x_s, s_idx, mask_in, x0 - x_s, (conf_s if c["anchor_conf"] else mask_s)
+
+    def _build_batch_fused(self, x0, x0_used, student, masks_levels, gen):
+        """Speed-mode batch (see ``batch_mode``): sync-free level draw, one ``idb200_corrupt_adjacent`` launch, two
+        ``idb200_anchor_conf`` launches (confidence + anneal + stacked mask_in), one subtraction."""
+        from ..corruptions import keyframes as kf
+        from ..sample.sample_generate import anchor_conf_mask_in
+        c = self.cfg
+        B, T, _ = x0.shape
+        dev = x0.device
+        S = c["levels"]
+        s_idx = TI._sample_level_indices(B, S, gen, dev, c["level_sampling"], c["level_high_prob"], sync_free=True)
+        K_list = kf._compute_k_schedule(T, c["K_min"], S, schedule=self.k_schedule, geom_gamma=self.k_geom_gamma)
+        cr = self.corrupt
+        adj = c["stage2_mode"] == "adj"
+        self._noise_calls += 1
+        x_s, x_prev, mask_s, mask_prev = TI.corrupt_adjacent_fused(
+            x0 if x0_used is None else x0_used, masks_levels, s_idx, K_list, c["K_min"], adjacent=adj, recompute_velocity=c["recompute_vel"],
+            corrupt_mode=cr["corrupt_mode"], corrupt_sigma_max=cr["corrupt_sigma_max"], corrupt_sigma_min=cr["corrupt_sigma_min"],
+            corrupt_sigma_pow=cr["corrupt_sigma_pow"], corrupt_anchor_frac=cr["corrupt_anchor_frac"], clamp_endpoints=cr["clamp_endpoints"],
+            pos_clip=cr["pos_clip"], pos_clip_min=cr["pos_clip_min"], pos_clip_max=cr["pos_clip_max"], seed=gen.initial_seed(),
+            offset=self._noise_calls)
+        conf_t, conf_st, conf_e, conf_m = c["conf"]
+        mode = c["anneal_mode"] if c["anneal"] else "none"
+        ac = dict(conf_teacher=conf_t, conf_student=conf_st, conf_endpoints=conf_e, conf_missing=conf_m, clamp_endpoints=c["clamp_endpoints"])
+        if adj:
+            if c["anchor_conf"]:
+                _, mask_in = anchor_conf_mask_in(mask_s, student, mask_prev, s_idx, S, mode, want_conf=False, channels=3, **ac)
+                conf_prev, _ = anchor_conf_mask_in(mask_prev, student, None, torch.clamp(s_idx - 1, min=0), S, mode, **ac)
+                return x_s, s_idx, mask_in, x_prev - x_s, conf_prev
+            return x_s, s_idx, torch.stack([mask_s, mask_prev], dim=-1), x_prev - x_s, mask_prev
+        if c["anchor_conf"]:
+            conf_s, mask_in = anchor_conf_mask_in(mask_s, student, None, s_idx, S, mode, channels=2, **ac)
+            return x_s, s_idx, mask_in, x0 - x_s, conf_s
+        return x_s, s_idx, mask_s, x0 - x_s, mask_s
 
     def loss_and_grads(self, x_s, s_idx, mask_in, cond, target, weight_mask) -> torch.Tensor:
         """Forward + loss + backward; the parameter gradients land in ``self.flat_grad`` (views: ``self.grads``)."""

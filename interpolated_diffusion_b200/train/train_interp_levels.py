@@ -177,16 +177,82 @@ def _anneal_conf(conf: torch.Tensor, s_idx: torch.Tensor, levels: int, mode: str
 
 
 def _sample_level_indices(B: int, levels: int, generator: torch.Generator, device: torch.device, mode: str,
-                          high_prob: float) -> torch.Tensor:
-    """train_interp_levels.py:578-596.  Same draws in the same order (``rand(B)`` then ``randint`` with the
-    data-dependent count of non-high rows), so the generator stream stays aligned with the reference."""
+                          high_prob: float, *, sync_free: bool = False) -> torch.Tensor:
+    """train_interp_levels.py:578-596.  Default (parity mode): same draws in the same order (``rand(B)`` then ``randint``
+    with the data-dependent count of non-high rows), so the generator stream stays aligned with the reference -- at the price
+    of one host sync (the count).  ``sync_free=True`` (speed mode): the low-level candidate is drawn for ALL B rows and
+    selected with ``where`` -- the same distribution (s = S w.p. high_prob, else U{1..S}), no ``.item()``, but a different
+    number of generator draws, so the stream after this call differs from the reference's."""
     if mode == "uniform" or levels <= 1:
         return torch.randint(1, levels + 1, (B,), generator=generator, device=device, dtype=torch.long)
     high_prob = float(max(0.0, min(1.0, high_prob)))
     draw = torch.rand((B,), generator=generator, device=device)
     high = draw < high_prob
+    if sync_free:
+        low = torch.randint(1, levels + 1, (B,), generator=generator, device=device, dtype=torch.long)
+        return torch.where(high, torch.full_like(low, levels), low)
     s_idx = torch.full((B,), levels, device=device, dtype=torch.long)
     n_low = int((~high).sum().item())
     if n_low > 0:
         s_idx[~high] = torch.randint(1, levels + 1, (n_low,), generator=generator, device=device, dtype=torch.long)
     return s_idx
+
+
+def level_sigmas(K_list, K_min: int, corrupt_mode: str, corrupt_sigma_max: float, corrupt_sigma_min: float, corrupt_sigma_pow: float,
+                 corrupt_anchor_frac: float):
+    """Per-level (sigma, anchor_sigma) as :335-341 computes them from K_s (zeros when corrupt_mode == "none")."""
+    sig = [0.0 if corrupt_mode == "none" else _compute_sigma_for_level(int(k), K_min, corrupt_sigma_max, corrupt_sigma_min, corrupt_sigma_pow)
+           for k in K_list]
+    return sig, [x * float(corrupt_anchor_frac) for x in sig]
+
+
+def corrupt_adjacent_fused(x0: torch.Tensor, masks_levels: torch.Tensor, s_idx: torch.Tensor, K_list, K_min: int, *,
+                           adjacent: bool = True, recompute_velocity: bool = False, corrupt_mode: str = "none",
+                           corrupt_sigma_max: float = 0.0, corrupt_sigma_min: float = 0.0, corrupt_sigma_pow: float = 1.0,
+                           corrupt_anchor_frac: float = 0.0, clamp_endpoints: bool = True, pos_clip: bool = False,
+                           pos_clip_min: float = 0.0, pos_clip_max: float = 1.0, anchor_noise: Optional[torch.Tensor] = None,
+                           path_noise: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0, export_noise: bool = False):
+    """``build_interp_adjacent_batch`` (:294-383; ``adjacent=False``: ``build_interp_level_batch`` :227-291) for the whole batch
+    in ONE launch (``idb200_corrupt_adjacent``): per-row level, no per-level loop, no host sync.
+
+    Noise: ``anchor_noise`` [B,2,Kmax,2] / ``path_noise`` [B,2,T,2] given -> parity mode (bit-identical to the per-level path
+    when they hold the reference's draws); both None -> Philox in the kernel keyed by (seed, offset).
+    Returns (x_s, x_prev | None, mask_s, mask_prev | None[, anchor_noise_drawn, path_noise_drawn])."""
+    dev = L.require_cuda(x0, masks_levels, s_idx)
+    B, T, D = x0.shape
+    n_levels = masks_levels.shape[1]
+    if len(K_list) != n_levels:
+        raise ValueError("K_list must have one entry per mask level")
+    sig, asig = level_sigmas(K_list, K_min, corrupt_mode, corrupt_sigma_max, corrupt_sigma_min, corrupt_sigma_pow, corrupt_anchor_frac)
+    Kmax = int(min(T, max(int(k) for k in K_list)))
+    import ctypes
+    fa = (ctypes.c_float * n_levels)(*sig)
+    fb = (ctypes.c_float * n_levels)(*asig)
+    src = L.f32c(x0)
+    x_s = torch.empty((B, T, D), device=dev, dtype=torch.float32)
+    x_prev = torch.empty((B, T, D), device=dev, dtype=torch.float32) if adjacent else None
+    mask_s = torch.empty((B, T), device=dev, dtype=torch.bool)
+    mask_prev = torch.empty((B, T), device=dev, dtype=torch.bool) if adjacent else None
+    an_out = pn_out = None
+    if export_noise:
+        if anchor_noise is not None:
+            raise ValueError("export_noise is for the Philox mode")
+        an_out = torch.zeros((B, 2, Kmax, 2), device=dev, dtype=torch.float32)
+        pn_out = torch.zeros((B, 2, T, 2), device=dev, dtype=torch.float32)
+    if (anchor_noise is None) != (path_noise is None):
+        raise ValueError("anchor_noise and path_noise must be given together")
+    if anchor_noise is not None:
+        if tuple(anchor_noise.shape) != (B, 2, Kmax, 2) or tuple(path_noise.shape) != (B, 2, T, 2):
+            raise ValueError(f"noise shapes must be [B,2,{Kmax},2] and [B,2,{T},2]")
+        anchor_noise, path_noise = L.f32c(anchor_noise), L.f32c(path_noise)
+    L.call("idb200_corrupt_adjacent", L.ptr(src), L.ptr(L.u8c(masks_levels)), L.ptr(L.i64c(s_idx)), B, T, D, n_levels, fa, fb,
+           L.ptr(anchor_noise), L.ptr(path_noise), Kmax, int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), L.ptr(an_out), L.ptr(pn_out),
+           int(corrupt_mode == "dist"), int(bool(clamp_endpoints)), int(bool(recompute_velocity)), L.ptr(x_s), L.ptr(x_prev),
+           L.ptr(mask_s), L.ptr(mask_prev), L.stream(dev))
+    if pos_clip:
+        x_s[..., :2] = x_s[..., :2].clamp(min=pos_clip_min, max=pos_clip_max)
+        if x_prev is not None:
+            x_prev[..., :2] = x_prev[..., :2].clamp(min=pos_clip_min, max=pos_clip_max)
+    if export_noise:
+        return x_s, x_prev, mask_s, mask_prev, an_out, pn_out
+    return x_s, x_prev, mask_s, mask_prev

@@ -59,11 +59,17 @@ class Stage1Trainer:
         by_id = {id(p): g for p, g in zip(self.opt.params, self.opt.views(self.flat_grad))}
         self.grads: Dict[str, torch.Tensor] = {n: by_id[id(p)] for n, p in model.named_parameters() if id(p) in by_id}
         self.pg = process_group
+        self.sync_replicas()                                   # DDP semantics: every replica starts from rank 0's state
         self.last_grad_norm: Optional[torch.Tensor] = None
         self.cuda_graph = bool(cuda_graph)                     # forward + loss + backward replayed as one CUDA graph
         self._graph = None
         self._side = None                                      # prefetch(): next batch built on a side stream
         self._next = None
+
+    def sync_replicas(self, src: int = 0) -> None:
+        """Broadcast rank ``src``'s parameters / EMA / Adam moments / step count to all ranks of the process group (no-op for
+        one process).  Called at construction; call it again after loading a checkpoint."""
+        self.opt.sync_replicas(self.pg, src)
 
     def build_batch(self, x0: torch.Tensor, cond: dict, gen: torch.Generator, idx_override: Optional[torch.Tensor] = None,
                     noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, ...]:

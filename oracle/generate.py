@@ -161,9 +161,10 @@ def generate_causal_chunked(sd_kp, sd_interp, n_heads: int, cond: Dict[str, torc
     """The chunk loop of ``src/sample/sample_generate_causal.py:485-583`` (long-horizon causal generation), restated for a
     batch: the reference runs it sample by sample (B = 1) but every quantity that shapes the loop (cur, end, local_T, full_len)
     depends only on T and chunk, so the samples advance in lockstep with identical per-sample arithmetic.  The random anchors
-    of each chunk (``sample_fixed_k_indices_batch``, :511) and the DDIM noise (:194) are inputs.  PARITY NOTE: this chunk loop
-    is restated from the source, not pinned against a run of the live script (its ``main`` needs the D4RL datasets); every
-    function it composes (DDIM sampler, interpolation, denoisers, clamps) is pinned by the golden vectors."""
+    of each chunk (``sample_fixed_k_indices_batch``, :511) and the DDIM noise (:194) are inputs.  PARITY: pinned against a run of the
+    live script's own ``main()`` (``tests/golden/make_golden_r2.py::gold_causal_chunks``: tiny checkpoints, the particle-maze
+    samples handed over as a prepared dataset.npz, plotting stubbed, every draw recorded) by
+    ``tests/test_oracle_golden_r2.py::test_causal_chunk_loop_against_live_main``."""
     B = cond["start_goal"].shape[0]
     schedule = df.make_alpha_bars(df.make_beta_schedule(beta_schedule, n_train))
     sg = cond["start_goal"].numpy().astype(F32)

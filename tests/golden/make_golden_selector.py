@@ -16,6 +16,12 @@ CFG = {
     "default": dict(T=64, d_model=64, n_heads=2, d_ff=128, n_layers=2, pos_dim=64, maze_channels=(32, 64)),
     "full": dict(T=48, d_model=64, n_heads=2, d_ff=128, n_layers=2, pos_dim=32, use_sdf=True, use_goal_dist_token=True, use_level=True,
                  sg_map_sigma=2.0, maze_channels=(32, 32, 64)),
+    # round 2: query bias from the mean memory token + one-hot start / goal maps (:101-111, :129-139, :170-175)
+    "cbmem": dict(T=32, d_model=64, n_heads=2, d_ff=128, n_layers=1, pos_dim=32, use_cond_bias=True, cond_bias_mode="memory",
+                  sg_map_sigma=0.0, use_goal_dist_token=True, maze_channels=(32, 64)),
+    # query bias from a MazeConditionEncoder of its own
+    "cbenc": dict(T=32, d_model=64, n_heads=2, d_ff=128, n_layers=1, pos_dim=32, use_cond_bias=True, cond_bias_mode="encoder",
+                  maze_channels=(32, 64)),
 }
 for name, kw in CFG.items():
     torch.manual_seed(11)

@@ -126,3 +126,37 @@ def test_data_parallel_gradient_allreduce_is_the_mean_of_rank_gradients():
         p.join(timeout=60)
         assert p.exitcode == 0
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-7)
+
+
+# ---- replica state broadcast (DDP semantics at trainer construction / after a checkpoint load on some ranks) ------------------
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        from interpolated_diffusion_b200.parallel import broadcast_replica_state, replicas_in_sync
+        torch.manual_seed(100 + rank)                              # every rank builds "its model" with a different seed
+        flat, ema, m, v = (torch.randn(1000) for _ in range(4))
+        before = replicas_in_sync(flat)
+        step = broadcast_replica_state([flat, ema, None, m, v], step_count=7 * (rank + 1))
+        after = replicas_in_sync(flat) and replicas_in_sync(ema) and replicas_in_sync(m) and replicas_in_sync(v)
+        q.put((rank, before, after, step, float(flat.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replica_state_broadcast_makes_ranks_identical():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [g[1] for g in got] == [False, False]                   # different seeds: the replicas started out different
+    assert [g[2] for g in got] == [True, True]
+    assert [g[3] for g in got] == [7, 7]                           # rank 0's step count everywhere
+    assert got[0][4] == got[1][4]

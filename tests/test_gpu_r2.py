@@ -1,0 +1,229 @@
+"""Round-2 GPU parity tests.
+
+* cfg 1 literally (BASELINE.json configs[0]): ``ParticleMazeDataset(16, T=64, seed=123)`` conditioning, DEFAULT-size random-init
+  models (seeded init == the reference's weights, checksummed), every DDIM step teacher-forced on the reference's own z_t
+  (``tests/golden/cfg1.npz`` from the live reference): bf16 2e-2, fp32 check mode 1e-4 -- both relative to the step's
+  magnitude, because a random-init rollout blows |z_t| up to ~8e4 (first DDIM step multiplies by ~3243).
+* K1c single-launch corruption (``idb200_corrupt_adjacent``): bit-exact against the live-reference golden of
+  ``build_interp_adjacent_batch`` with its recorded draws scattered into the per-row layout; Philox mode == parity mode on
+  the exported noise, moments of the in-kernel normals; the fused trainer batch.
+* a GenerationGraph re-captures when the weights change and survives a larger eager call on the same models.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.asarray(a)).cuda()
+
+
+def _checksum(sd):
+    rows = []
+    for v in sd.values():
+        a = v.detach().cpu().numpy().astype(np.float64).reshape(-1)
+        rows.append([a.sum(), (a * a).sum(), a[0], a[-1]])
+    return np.array(rows, dtype=np.float64)
+
+
+def _cfg1_models(g):
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=2)
+    il = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=2)
+    assert np.array_equal(_checksum(kp.state_dict()), g["kp_checksum"]) and np.array_equal(_checksum(il.state_dict()), g["il_checksum"])
+    return kp.cuda(), il.cuda()
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("fp32", 1e-4)])
+def test_cfg1_default_models_teacher_forced(golden, precision, tol):
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    from interpolated_diffusion_b200.diffusion.ddpm import _timesteps
+    from interpolated_diffusion_b200.sample import sample_generate as sg
+    g = golden("cfg1")
+    kp, il = _cfg1_models(g)
+    kp.precision = il.precision = precision
+    B, T, K, D, S = 16, 64, 8, 2, 3
+    cond = {"occ": dev(g["occ"]), "start_goal": dev(g["start_goal"])}
+    idx, masks = kf.sample_fixed_k_indices_uniform_batch(B, T, K, device="cuda")
+    assert torch.equal(idx.cpu(), torch.from_numpy(g["idx"])) and torch.equal(masks.cpu(), torch.from_numpy(g["masks"]))
+    km, kv = sg._build_known_mask_values(idx, cond, D, T, True, logit_space=True)
+    assert torch.equal(km.cpu(), torch.from_numpy(g["known_mask"]))
+    assert np.abs(kv.cpu().numpy() - g["known_values"]).max() <= 2e-6
+    times = _timesteps(1000, 20, "quadratic").tolist()
+    assert times == g["times"].tolist()
+    worst = 0.0
+    for i in range(19):
+        t = torch.full((B,), times[i], device="cuda", dtype=torch.long)
+        eps = kp(dev(g["z_inter"][i]), t, idx, km, cond, T)
+        scale = max(1.0, float(np.abs(g["eps"][i]).max()))
+        err = float(np.abs(eps.cpu().numpy() - g["eps"][i]).max()) / scale
+        worst = max(worst, err)
+        assert err < tol, (i, err, scale)
+    # interpolation of the reference's keypoints, Stage-2 one-step on the reference's x_pred, clamp
+    from interpolated_diffusion_b200.utils.normalize import sigmoid_pos
+    x_pred = kf.interpolate_from_indices(idx, sigmoid_pos(dev(g["z"])), T, recompute_velocity=True)
+    assert np.abs(x_pred.cpu().numpy() - g["x_pred"]).max() <= 1.2e-7
+    conf, mask_in = sg.anchor_conf_mask_in(masks, masks, None, S, S, "linear", 0.95, 0.5, 1.0, 0.0, True, channels=2)
+    assert np.array_equal(mask_in.cpu().numpy(), g["mask_in"])
+    delta = il(dev(g["x_pred"]), torch.full((B,), S, device="cuda", dtype=torch.long), mask_in, cond)
+    assert np.abs(delta.cpu().numpy() - g["delta"]).max() < tol * max(1.0, float(np.abs(g["delta"]).max()))
+    from interpolated_diffusion_b200.utils.clamp import stage2_epilogue
+    x_hat = stage2_epilogue(dev(g["x_pred"]), dev(g["delta"]), dev(g["x_pred"]), dev(g["conf_pred"]), 1.0, "endpoints", masks, "pos")
+    assert np.abs(x_hat.cpu().numpy() - g["x_hat"]).max() <= 1.2e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def _scatter_reference_draws(g, s_idx, K_list, T, sig_on=True):
+    """The live reference's per-level draws (order: for s = 1..S over rows s_idx == s: x_s anchor, x_s path, x_prev anchor,
+    x_prev path; train_interp_levels.py:328-372) scattered into the per-row layout of idb200_corrupt_adjacent."""
+    B = s_idx.shape[0]
+    Kmax = max(K_list)
+    an = np.zeros((B, 2, Kmax, 2), np.float32)
+    pn = np.zeros((B, 2, T, 2), np.float32)
+    n = int(g["ad_dist_n"][0])
+    draws = [g[f"ad_dist_draw{i}"] for i in range(n)]
+    pos = 0
+    for s in range(1, len(K_list)):
+        rows = np.nonzero(s_idx == s)[0]
+        if rows.size == 0:
+            continue
+        for slot, lvl in ((0, s), (1, s - 1)):
+            a = draws[pos]; pos += 1
+            assert a.shape == (rows.size, K_list[lvl], 2), (a.shape, rows.size, K_list[lvl])
+            an[rows, slot, :K_list[lvl]] = a
+            p = draws[pos]; pos += 1
+            assert p.shape == (rows.size, T, 2)
+            pn[rows, slot] = p
+    assert pos == n
+    return an, pn
+
+
+def test_corrupt_adjacent_single_launch_equals_live_reference(golden):
+    from interpolated_diffusion_b200.train import train_interp_levels as tr
+    g = golden("sampling")
+    x0, masks, s_idx = dev(g["ad_x0"]), dev(g["ad_masks"]), dev(g["ad_s_idx"])
+    B, T, D = x0.shape
+    K_list = [int(g[f"ad_idx{s}"].shape[1]) for s in range(4)]
+    # no corruption: pure Interp(x0 | M_s), Interp(x0 | M_{s-1})
+    xs, xp, ms, mp = tr.corrupt_adjacent_fused(x0, masks, s_idx, K_list, 8)
+    assert np.array_equal(xs.cpu().numpy(), g["ad_none_xs"]) and np.array_equal(xp.cpu().numpy(), g["ad_none_xp"])
+    assert np.array_equal(ms.cpu().numpy(), g["ad_none_ms"]) and np.array_equal(mp.cpu().numpy(), g["ad_none_mp"])
+    xs1, none, ms1, _ = tr.corrupt_adjacent_fused(x0, masks, s_idx, K_list, 8, adjacent=False)
+    assert none is None and np.array_equal(xs1.cpu().numpy(), g["lv_none_xs"]) and np.array_equal(ms1.cpu().numpy(), g["lv_none_ms"])
+    # dist corruption with the reference's recorded draws
+    an, pn = _scatter_reference_draws(g, g["ad_s_idx"], K_list, T)
+    kw = dict(corrupt_mode="dist", corrupt_sigma_max=0.08, corrupt_sigma_min=0.012, corrupt_sigma_pow=0.75, corrupt_anchor_frac=0.25)
+    xs, xp, ms, mp = tr.corrupt_adjacent_fused(x0, masks, s_idx, K_list, 8, anchor_noise=dev(an), path_noise=dev(pn), **kw)
+    assert np.array_equal(xs.cpu().numpy(), g["ad_dist_xs"]), np.abs(xs.cpu().numpy() - g["ad_dist_xs"]).max()
+    assert np.array_equal(xp.cpu().numpy(), g["ad_dist_xp"])
+
+
+@pytest.mark.parametrize("T,K_min,S,D", [(64, 8, 3, 2), (64, 8, 3, 4), (256, 32, 4, 2), (33, 5, 2, 2)])
+def test_corrupt_adjacent_philox_mode(T, K_min, S, D):
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    from interpolated_diffusion_b200.train import train_interp_levels as tr
+    B = 4096 if T <= 64 else 512
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x0 = torch.rand((B, T, D), device="cuda", generator=gen)
+    masks, idx_levels = kf.build_nested_masks_batch(B, T, K_min, S, generator=gen, device="cuda")
+    K_list = kf._compute_k_schedule(T, K_min, S)
+    s_idx = tr._sample_level_indices(B, S, gen, torch.device("cuda"), "high", 0.5, sync_free=True)
+    kw = dict(corrupt_mode="dist", corrupt_sigma_max=0.08, corrupt_sigma_min=0.012, corrupt_sigma_pow=0.75, corrupt_anchor_frac=0.25,
+              recompute_velocity=True)
+    xs, xp, ms, mp, an, pn = tr.corrupt_adjacent_fused(x0, masks, s_idx, K_list, K_min, seed=1234, offset=7, export_noise=True, **kw)
+    # (1) parity mode on the exported noise reproduces the Philox run bit for bit
+    xs2, xp2, ms2, mp2 = tr.corrupt_adjacent_fused(x0, masks, s_idx, K_list, K_min, anchor_noise=an, path_noise=pn, **kw)
+    assert torch.equal(xs, xs2) and torch.equal(xp, xp2) and torch.equal(ms, ms2) and torch.equal(mp, mp2)
+    # (2) ... and parity mode is the per-level reference-order path given the same noise (generator replay)
+    rows = torch.arange(B, device="cuda")
+    assert torch.equal(ms, masks[rows, s_idx]) and torch.equal(mp, masks[rows, s_idx - 1])
+    from oracle import sampling_np as osp
+    x0n, idxn = x0.cpu().numpy(), [i.cpu().numpy() for i in idx_levels]
+    sn = s_idx.cpu().numpy()
+    ann, pnn = an.cpu().numpy(), pn.cpu().numpy()
+    for b in range(0, B, max(1, B // 64)):
+        for slot, out in ((0, xs), (1, xp)):
+            lvl = int(sn[b]) - slot
+            K = K_list[lvl]
+            sigma = osp.compute_sigma_for_level(K, K_min, 0.08, 0.012, 0.75)
+            tape = osp.NoiseTape([ann[b:b + 1, slot, :K], pnn[b:b + 1, slot]])
+            ref = osp.corrupt_from_anchors(x0n[b:b + 1], idxn[lvl][b:b + 1], T, tape, sigma, sigma * 0.25, 0, 0.0, "dist", True, True)
+            assert np.array_equal(out[b:b + 1].cpu().numpy(), ref), (b, slot)
+    # (3) the in-kernel normals: N(0,1) moments, independent across slots / seeds, deterministic
+    used = pn[:, :, :, :].reshape(-1).double()
+    assert abs(float(used.mean())) < 5e-3 and abs(float(used.var()) - 1.0) < 1e-2
+    assert abs(float((used ** 3).mean())) < 3e-2 and abs(float((used ** 4).mean()) - 3.0) < 1e-1
+    c = float((pn[:, 0].reshape(-1) * pn[:, 1].reshape(-1)).mean())
+    assert abs(c) < 1e-2
+    again = tr.corrupt_adjacent_fused(x0, masks, s_idx, K_list, K_min, seed=1234, offset=7, **kw)
+    other = tr.corrupt_adjacent_fused(x0, masks, s_idx, K_list, K_min, seed=1234, offset=8, **kw)
+    assert torch.equal(again[0], xs) and not torch.equal(other[0], xs)
+
+
+def test_stage2_trainer_fused_batch_mode():
+    """batch_mode='fused': same batch structure as the reference-draw mode (masks, level marginals, targets consistent with the
+    masks), no host sync inside build_batch, and a training step runs on it."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    TINY = dict(d_model=64, n_layers=2, n_heads=2, d_ff=128, d_cond=32, maze_channels=(8, 16))
+    torch.manual_seed(0)
+    model = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=3, **TINY).cuda()
+    tr = Stage2Trainer(model, batch_mode="fused")
+    B, T = 2048, 64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x0 = torch.rand((B, T, 2), device="cuda", generator=g)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), device="cuda", generator=g) < 0.2).float(), "start_goal": torch.rand((B, 4), device="cuda", generator=g)}
+    x_s, s_idx, mask_in, target, wm = tr.build_batch(x0, g, cond)
+    assert x_s.shape == (B, T, 2) and mask_in.shape == (B, T, 3) and target.shape == (B, T, 2) and wm.shape == (B, T)
+    p = torch.bincount(s_idx, minlength=4).float() / B
+    assert abs(float(p[3]) - (0.5 + 0.5 / 3)) < 0.05 and float(p[0]) == 0.0
+    m_s, m_prev = mask_in[..., 0] > 0.5, mask_in[..., 1] > 0.5
+    K_list = [64, 32, 16, 8]
+    assert torch.equal(m_s.sum(1), torch.tensor(K_list, device="cuda")[s_idx]) and torch.equal(m_prev.sum(1), torch.tensor(K_list, device="cuda")[s_idx - 1])
+    assert bool((m_prev | ~m_s).all())                                 # nested: M_s subset of M_{s-1}
+    # corruption noise is bounded by a few sigma: x_s stays close to the clean interpolation at the anchors of M_s
+    assert float((x_s - x0)[m_s].abs().max()) < 0.5
+    # endpoints carry conf_endpoints = 1 -> weight w = 1 + (0.1 - 1) * conf uses wm = conf_prev: endpoints 1.0
+    assert torch.all(wm[:, 0] == 1.0) and torch.all(wm[:, -1] == 1.0)
+    l0 = float(tr.step(x0, cond, g))
+    l1 = float(tr.step(x0, cond, g))
+    assert np.isfinite(l0) and np.isfinite(l1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_generation_graph_recaptures_on_weight_change_and_survives_growth():
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph, generate
+    torch.manual_seed(0)
+    kp = KeypointDenoiser(data_dim=2).cuda()
+    il = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=2).cuda()
+    cfg = GenerationConfig()
+    B = 64
+    g = torch.Generator().manual_seed(2)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=g) < 0.2).float().cuda(), "start_goal": torch.rand((B, 4), generator=g).cuda()}
+    z_T = torch.randn((B, 8, 2), generator=g).cuda()
+    graph = GenerationGraph(kp, il, B, cfg)
+    a = graph.run(cond, z_T).clone()
+    assert torch.equal(a, generate(kp, il, cond, cfg, z_T=z_T))
+    # a larger eager call on the same models grows every workspace: the captured graph must keep replaying correctly
+    B2 = 4 * B
+    cond2 = {"occ": (torch.rand((B2, 1, 21, 21), generator=g) < 0.2).float().cuda(), "start_goal": torch.rand((B2, 4), generator=g).cuda()}
+    big = generate(kp, il, cond2, cfg, z_T=torch.randn((B2, 8, 2), generator=g).cuda())
+    junk = [torch.randn((1 << 20,), device="cuda") for _ in range(8)]      # re-use whatever memory a wrongly freed buffer left
+    assert torch.isfinite(big).all()
+    assert torch.equal(graph.run(cond, z_T), a)
+    del junk
+    # weights change in place (what an optimizer step / EMA copy_to / load_state_dict does): run() must not replay the stale capture
+    with torch.no_grad():
+        for p in il.parameters():
+            p.mul_(1.01)
+        for p in kp.parameters():
+            p.add_(1e-3)
+    b = graph.run(cond, z_T).clone()
+    assert not torch.equal(a, b)
+    assert torch.equal(b, generate(kp, il, cond, cfg, z_T=z_T))

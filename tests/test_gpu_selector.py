@@ -14,10 +14,16 @@ CFG = {
     "default": dict(T=64, d_model=64, n_heads=2, d_ff=128, n_layers=2, pos_dim=64, maze_channels=(32, 64)),
     "full": dict(T=48, d_model=64, n_heads=2, d_ff=128, n_layers=2, pos_dim=32, use_sdf=True, use_goal_dist_token=True, use_level=True,
                  sg_map_sigma=2.0, maze_channels=(32, 32, 64)),
+    # round 2: query bias from the mean memory token + one-hot start / goal maps (:101-111, :129-139, :170-175)
+    "cbmem": dict(T=32, d_model=64, n_heads=2, d_ff=128, n_layers=1, pos_dim=32, use_cond_bias=True, cond_bias_mode="memory",
+                  sg_map_sigma=0.0, use_goal_dist_token=True, maze_channels=(32, 64)),
+    # query bias from a MazeConditionEncoder of its own
+    "cbenc": dict(T=32, d_model=64, n_heads=2, d_ff=128, n_layers=1, pos_dim=32, use_cond_bias=True, cond_bias_mode="encoder",
+                  maze_channels=(32, 64)),
 }
 
 
-@pytest.mark.parametrize("name", ["default", "full"])
+@pytest.mark.parametrize("name", ["default", "full", "cbmem", "cbenc"])
 def test_selector_matches_reference_golden(name):
     from interpolated_diffusion_b200.models.keypoint_selector import KeypointSelector, select_topk_indices
     g = np.load(GOLD)
