@@ -298,7 +298,7 @@ def section_train(ctx, args):
     B = GB // world
     torch.manual_seed(0)
     model = InterpLevelDenoiser(data_dim=D, max_levels=LEVELS, mask_channels=3, **LARGE).to(dev)
-    tr = Stage2Trainer(model, cuda_graph=True)
+    tr = Stage2Trainer(model, cuda_graph=True, batch_mode="fused")
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x0 = torch.rand((B, T, D), device=dev, generator=g)
     cond = {"occ": (torch.rand((B, 1, 21, 21), device=dev, generator=g) < 0.2).float(), "start_goal": torch.rand((B, 4), device=dev, generator=g)}

@@ -233,8 +233,11 @@ int idb200_out_head(const float* h, const float* W, const float* bias, float* y,
                     idb200_stream_t stream);
 
 /* multi-head self-attention of nn.MultiheadAttention (transformer.py:11,39) on a packed qkv [B*L, 3*H*32]:
- * out[B*L, H*32] = softmax(q k^T / sqrt(32) [+ causal mask]) v per trajectory and head.  bf16 (mma.sync
- * path when L % 16 == 0, else / force_simt: fp32 CUDA-core math) or fp32 in/out.  L <= 256. */
+ * out[B*L, H*32] = softmax(q k^T / sqrt(32) [+ causal mask]) v per trajectory and head, L <= 256, bf16 or fp32 in/out.
+ * force_simt = 0: bf16 runs on tcgen05 (csrc/attention_tc5.cu: S = Q K^T and O = P V as tcgen05.mma with the score tile and
+ *                the output accumulator in tensor memory, any L, H even; H odd falls to the legacy path); fp32 on CUDA cores.
+ * force_simt = 1: fp32-arithmetic CUDA-core kernel (check mode).   force_simt = 2: legacy mma.sync kernel (L % 16 == 0 or
+ *                L in {2,4,8}; otherwise the CUDA-core kernel) -- kept as a cross-check. */
 int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t B, int L, int H, int causal, int force_simt,
                      idb200_stream_t stream);
 

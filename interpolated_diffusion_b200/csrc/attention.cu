@@ -14,9 +14,15 @@
 // qkv: [M, 3d] rows = tokens, columns [q | k | v], head h at columns h*32 inside each third.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace idb200 {
+
+// attention_tc5.cu: the tcgen05 / TMEM path (default for bf16)
+bool attention_tc5_supported(const void* qkv, const void* out, long long B, int L, int H);
+int attention_tc5(const void* qkv, void* out, long long B, int L, int H, int causal, cudaStream_t st);
 
 constexpr int kHD = 32;
 
@@ -454,6 +460,11 @@ extern "C" int idb200_attention(const void* qkv, void* out, int is_bf16, int64_t
     if (B == 0) return IDB200_OK;
     IDB_REQUIRE(qkv && out, IDB200_EINVAL, "NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // force_simt: 0 = auto (bf16: tcgen05 path, any L), 1 = fp32-arithmetic SIMT kernel, 2 = legacy mma.sync path (A/B + cross-check)
+    static const bool tc5_env = !(getenv("IDB200_ATTN_TC5") && atoi(getenv("IDB200_ATTN_TC5")) == 0);
+    if (is_bf16 && force_simt == 0 && tc5_env && attention_tc5_supported(qkv, out, B, L, H))
+        return attention_tc5(qkv, out, B, L, H, causal, st);
+    if (force_simt == 2) force_simt = 0;
     // short sequences (Stage 1, L = 8): pack Lp / L trajectories into one block-diagonal "sequence" for the mma path
     int Lp = L, blk = 0;
     long long Bp = B;

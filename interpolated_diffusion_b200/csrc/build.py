@@ -48,8 +48,9 @@ def build(verbose: bool = False, force: bool = False) -> str:
     nvcc = _nvcc()
     sources = sorted(f for f in os.listdir(HERE) if f.endswith(".cu"))
     objs, jobs = [], []
+    extra = os.environ.get("IDB200_NVCC_EXTRA", "").split()      # dev: e.g. -DIDB200_WAIT_LIMIT_CYCLES=400000000LL
     for src in sources:
-        flags = list(NVCC_FLAGS) + (["-fmad=false"] if src in NO_FMAD else [])
+        flags = list(NVCC_FLAGS) + extra + (["-fmad=false"] if src in NO_FMAD else [])
         path = os.path.join(HERE, src)
         obj = os.path.join(OBJ, src[:-3] + ".o")
         stamp = obj + ".sha"

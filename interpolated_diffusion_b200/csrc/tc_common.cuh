@@ -74,12 +74,17 @@ __device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t pa
 }
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, bool backoff) {
     long long t0 = 0;
+    bool reported = false;
     while (!mbar_try_wait_suspend(bar, parity, 1000000u)) {
         const long long t = clock64();
         if (t0 == 0) t0 = t;
         else if (t - t0 > IDB200_WAIT_LIMIT_CYCLES) {
-            printf("idb200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
-            __trap();
+            // report once, keep waiting for a grace period (so that EVERY stuck waiter of the pipeline gets to report: the
+            // first trap kills the kernel), then trap
+            if (!reported && (threadIdx.x & 31) == 0)
+                printf("idb200: mbarrier wait timed out (tag %d, block %d, warp %d, parity %u)\n", tag, blockIdx.x, threadIdx.x >> 5, parity);
+            reported = true;
+            if (t - t0 > IDB200_WAIT_LIMIT_CYCLES + IDB200_WAIT_LIMIT_CYCLES / 4) __trap();
         }
     }
 }

@@ -131,7 +131,10 @@ def ln_film(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], out: torch.
     return out
 
 
-def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, Lseq: int, H: int, causal: bool, force_simt: bool = False):
+def attention(qkv: torch.Tensor, out: torch.Tensor, B: int, Lseq: int, H: int, causal: bool, force_simt=False):
+    """softmax(Q K^T / sqrt(32) [+ causal mask]) V per (trajectory, head) on packed qkv [B*L, 3d].  bf16 inputs run on the
+    tcgen05 path (any L <= 256); fp32 inputs / ``force_simt=True`` on the fp32-arithmetic SIMT kernel (check mode);
+    ``force_simt=2`` selects the legacy mma.sync kernel (cross-check)."""
     L.call("idb200_attention", qkv.data_ptr(), out.data_ptr(), int(qkv.dtype == torch.bfloat16), B, Lseq, H, int(causal),
            int(force_simt), L.stream(qkv.device))
     return out

@@ -31,7 +31,10 @@ def test_attention_kernels_vs_torch():
     g = torch.Generator(device="cuda").manual_seed(0)
     for (B, L, H, causal) in [(5, 8, 8, False), (3, 64, 8, False), (2, 64, 8, True), (2, 256, 4, True), (3, 16, 2, False),
                               (2, 32, 4, True), (7, 8, 2, True), (1, 256, 8, False), (2, 128, 2, False), (3, 5, 2, False),
-                              (16, 8, 8, False), (24, 8, 8, True), (6, 8, 8, True), (12, 8, 2, False), (64, 8, 4, False)]:
+                              (16, 8, 8, False), (24, 8, 8, True), (6, 8, 8, True), (12, 8, 2, False), (64, 8, 4, False),
+                              # round 2: lengths that are not a multiple of 16 run on the tcgen05 path too (key masking, no SIMT fallback)
+                              (7, 33, 2, False), (7, 33, 2, True), (5, 100, 2, False), (3, 129, 2, True), (3, 200, 8, False), (37, 8, 12, False),
+                              (9, 48, 12, True), (1, 1, 2, False), (130, 2, 2, True)]:
         d = H * 32
         qkv = torch.randn((B * L, 3 * d), generator=g, device="cuda")
         q, k, v = [t.view(B, L, H, 32).transpose(1, 2) for t in qkv.split(d, dim=-1)]
@@ -41,8 +44,12 @@ def test_attention_kernels_vs_torch():
         qb = qkv.bfloat16()
         qf, kf, vf = [t.float().view(B, L, H, 32).transpose(1, 2) for t in qb.split(d, dim=-1)]
         refb = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, is_causal=causal).transpose(1, 2).reshape(B * L, d)
-        outb = E.attention(qb, torch.empty((B * L, d), device="cuda", dtype=torch.bfloat16), B, L, H, causal)
-        assert _maxabs(outb, refb) < 2.5e-2, (B, L, H, causal, "mma" if (L % 16 == 0 or L == 8) else "simt")
+        # default bf16 path: tcgen05 (S = Q K^T and O = P V as tcgen05.mma, scores / output accumulators in tensor memory)
+        outb = E.attention(qb, torch.full((B * L, d), float("nan"), device="cuda", dtype=torch.bfloat16), B, L, H, causal)
+        assert _maxabs(outb, refb) < 2.5e-2, (B, L, H, causal, "tcgen05")
+        # legacy mma.sync path (force_simt = 2), kept as a cross-check
+        outl = E.attention(qb, torch.empty((B * L, d), device="cuda", dtype=torch.bfloat16), B, L, H, causal, force_simt=2)
+        assert _maxabs(outl, refb) < 2.5e-2, (B, L, H, causal, "mma" if (L % 16 == 0 or L == 8) else "simt")
         outs = E.attention(qb, torch.empty((B * L, d), device="cuda", dtype=torch.bfloat16), B, L, H, causal, force_simt=True)
         assert _maxabs(outs, refb) < 1e-2, (B, L, H, causal, "simt-bf16")
 

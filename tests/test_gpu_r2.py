@@ -169,9 +169,9 @@ def test_stage2_trainer_fused_batch_mode():
     masks), no host sync inside build_batch, and a training step runs on it."""
     from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
     from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
-    TINY = dict(d_model=64, n_layers=2, n_heads=2, d_ff=128, d_cond=32, maze_channels=(8, 16))
+    SMALL = dict(d_model=128, n_layers=2, n_heads=4, d_ff=256, maze_channels=(32, 64))   # conv widths the training GEMMs take
     torch.manual_seed(0)
-    model = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=3, **TINY).cuda()
+    model = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=3, **SMALL).cuda()
     tr = Stage2Trainer(model, batch_mode="fused")
     B, T = 2048, 64
     g = torch.Generator(device="cuda").manual_seed(1)
