@@ -189,6 +189,19 @@ int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student, const uint
 int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K, int epilogue,
                      idb200_stream_t stream);
 
+/* Implicit-GEMM 3x3 convolution stack (MazeEncoder, src/models/encoders.py:15-25) on zero-bordered NHWC activations
+ * act [B, (H+2)*(W+2), C] bf16 (border positions are zeros = the conv's zero padding): the input pixel of tap (ky, kx) for the
+ * output position m is the ROW m + (ky-1)*(W+2) + (kx-1), so each k-block of the tcgen05 GEMM is a TMA box at a shifted row --
+ * no im2col matrix.  idb200_conv_first_nhwc: first layer (C_in <= 2) + SiLU on CUDA cores from NCHW fp32 input;
+ * idb200_conv3x3_gemm: one further layer, out = epi(conv(act) + bias) (epilogue 0: bf16, 1: SiLU + bf16), C_in == 32 or a
+ * multiple of 64 (<= 256), C_out % 64 == 0, Wm bf16 [C_out, nkb*64] in the k-block order documented in csrc/gemm.cu;
+ * idb200_pool_bordered: pooled[B, C] = mean over the H*W interior positions. */
+int idb200_conv_first_nhwc(const float* x, int64_t B, int Cin, int H, int W, const float* w, const float* bias, int C1, void* out,
+                           idb200_stream_t stream);
+int idb200_conv3x3_gemm(const void* act, int C, const void* Wm, const float* bias, void* out, int N, int64_t B, int H, int W,
+                        int epilogue, idb200_stream_t stream);
+int idb200_pool_bordered(const void* act, int64_t B, int H, int W, int C, float* pooled, idb200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Denoiser building blocks (KeypointDenoiser / InterpLevelDenoiser forwards,
  * src/models/denoiser_keypoints.py:82-113, src/models/denoiser_interp_levels.py:64-84,

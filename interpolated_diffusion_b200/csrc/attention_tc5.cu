@@ -37,9 +37,20 @@ constexpr int kThreads = 384;
 constexpr int kTile = 128 * 64 * 2;                 // [128 x 64] bf16 SWIZZLE_128B block
 constexpr float kScaleLog2 = 0.17677669529663687f * 1.4426950408889634f;     // log2(e) / sqrt(32)
 
-template <int kNK>
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// kCtas = CTAs per SM.  kNK = 128: two co-resident CTAs (one load stage each, 256 TMEM columns each) overlap each other's
+// MMA <-> softmax hand-offs -- best when the softmax dominates (L >= 32: 0.61 -> 0.57 ms at L = 64, H = 12, B = 8192); one CTA
+// with two load stages is better when the unit is load-bound (L = 8: 48 KB per unit for 8 keys per row; 0.43 vs 0.55 ms).
+template <int kNK, int kCtas>
 struct Cfg {
-    static constexpr int kStages = kNK == 128 ? 2 : 1;
+    static constexpr int kStages = (kNK == 128 && kCtas == 1) ? 2 : 1;
+    static constexpr int kCtasPerSm = kCtas;
+    static constexpr int kTmemCols = 2 * kNK;                                 // S_g at column g * kNK (O_g aliased onto its first columns)
     static constexpr int kQTiles = kNK == 128 ? 1 : 2;
     static constexpr int kQBytes = kQTiles * kTile;
     static constexpr int kKBytes = kNK * 128;
@@ -60,9 +71,9 @@ struct Params {
     int pv_wide;                // 1: P V with N = 64 (both heads' V columns; each group keeps its 32): fallback form
 };
 
-template <int kNK>
-__global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Params p) {
-    using C = Cfg<kNK>;
+template <int kNK, int kCtas>
+__global__ void __launch_bounds__(kThreads, kCtas) attn_tc5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Params p) {
+    using C = Cfg<kNK, kCtas>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     __builtin_assume(__isShared(smem));
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_cons
         }
         fence_mbar_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == 2) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -151,8 +162,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_cons
                     const uint64_t ad = umma_desc_sw128(sQ + qt * kTile) + 4 * g;
                     const uint64_t bd = umma_desc_sw128(sK) + 4 * g;
                     if (elect_one_sync()) {
-                        umma_bf16(tmem_base + g * 256, ad, bd, idesc_s, 0u);
-                        umma_bf16(tmem_base + g * 256, ad + 2, bd + 2, idesc_s, 1u);
+                        umma_bf16(tmem_base + g * kNK, ad, bd, idesc_s, 0u);
+                        umma_bf16(tmem_base + g * kNK, ad + 2, bd + 2, idesc_s, 1u);
                         umma_commit(&s_full[g]);
                     }
                     __syncwarp();
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_cons
                     if (elect_one_sync()) {
                         for (int ks = 0; ks < keff / 16; ++ks) {
                             const uint64_t pd = umma_desc_sw128(sP + (ks >> 2) * kTile) + 2 * (ks & 3);
-                            umma_bf16(tmem_base + g * 256, pd, vd + 128 * ks, idesc_o, ks > 0 ? 1u : 0u);
+                            umma_bf16(tmem_base + g * kNK, pd, vd + 128 * ks, idesc_o, ks > 0 ? 1u : 0u);
                         }
                         umma_commit(&o_full[g]);
                     }
@@ -191,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_cons
         const int g = (warp - 4) >> 2;                                   // group <-> head of the pair
         const int q = warp & 3;                                          // TMEM lane quadrant
         const int row = q * 32 + lane;
-        const uint32_t tS = tmem_base + g * 256 + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t tS = tmem_base + g * kNK + (static_cast<uint32_t>(q * 32) << 16);
         // (explicit st.shared below: a __builtin_assume(__isShared()) on this derived pointer made the compiler treat the whole
         // branch as unreachable and delete it)
         const uint32_t sPw = smem_u32(smem + C::kOffP + g * C::kPBytes);
@@ -233,10 +244,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_cons
                     uint32_t r[32];
                     tmem_ld_32x32(tS + c0, r);
                     tmem_ld_wait();
+                    if (__all_sync(0xffffffffu, c0 >= lo && c0 + 32 <= hi)) {      // every row of the warp attends to the whole chunk
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = c0 + j;
-                        if (c >= lo && c < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int c = c0 + j;
+                            if (c >= lo && c < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        }
                     }
                 }
                 const float mneg = (mx == -INFINITY) ? 0.0f : mx * kScaleLog2;
@@ -249,11 +265,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_cons
                         uint32_t r[32];
                         tmem_ld_32x32(tS + c0, r);
                         tmem_ld_wait();
+                        const bool full = __all_sync(0xffffffffu, c0 >= lo && c0 + 32 <= hi);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int c = c0 + 2 * j;
-                            const float e0 = (c >= lo && c < hi) ? exp2f(fmaf(__uint_as_float(r[2 * j]), kScaleLog2, -mneg)) : 0.0f;
-                            const float e1 = (c + 1 >= lo && c + 1 < hi) ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), kScaleLog2, -mneg)) : 0.0f;
+                            float e0 = ex2(fmaf(__uint_as_float(r[2 * j]), kScaleLog2, -mneg));
+                            float e1 = ex2(fmaf(__uint_as_float(r[2 * j + 1]), kScaleLog2, -mneg));
+                            if (!full) {
+                                e0 = (c >= lo && c < hi) ? e0 : 0.0f;
+                                e1 = (c + 1 >= lo && c + 1 < hi) ? e1 : 0.0f;
+                            }
                             sum += e0 + e1;
                             __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
                             pk[j] = *reinterpret_cast<uint32_t*>(&b2);
@@ -306,21 +327,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn_tc5_kernel(const __grid_cons
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, C::kTmemCols);
     }
 }
 
-template <int kNK>
+template <int kNK, int kCtas>
 static int launch(const CUtensorMap& tm, const Params& p, long long units, cudaStream_t st) {
-    using C = Cfg<kNK>;
+    using C = Cfg<kNK, kCtas>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc5_kernel<kNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc5_kernel<kNK, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(attn_tc5, smem=%d): %s", C::kSmem, cudaGetErrorString(e));
         attr = true;
     }
-    const int grid = static_cast<int>(units < num_sms() ? units : num_sms());
-    attn_tc5_kernel<kNK><<<grid, kThreads, C::kSmem, st>>>(tm, p);
+    const long long cap = static_cast<long long>(num_sms()) * C::kCtasPerSm;
+    const int grid = static_cast<int>(units < cap ? units : cap);
+    attn_tc5_kernel<kNK, kCtas><<<grid, kThreads, C::kSmem, st>>>(tm, p);
     return check_launch("attn_tc5_kernel");
 }
 
@@ -345,11 +367,12 @@ int attention_tc5(const void* qkv, void* out, long long B, int L, int H, int cau
     if (L <= 128) {
         p.G = 128 / L;
         p.tiles = (B + p.G - 1) / p.G;
-        return at5::launch<128>(tm, p, p.tiles * (H / 2), st);
+        if (L < 32) return at5::launch<128, 1>(tm, p, p.tiles * (H / 2), st);
+        return at5::launch<128, 2>(tm, p, p.tiles * (H / 2), st);
     }
     p.G = 1;
     p.tiles = B;
-    return at5::launch<256>(tm, p, p.tiles * (H / 2), st);
+    return at5::launch<256, 1>(tm, p, p.tiles * (H / 2), st);
 }
 
 }  // namespace idb200

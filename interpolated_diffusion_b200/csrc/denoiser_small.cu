@@ -15,6 +15,8 @@
 //   out_head      h[M,d] . W_out[D,d]^T + b  (D = 2 or 4: memory-bound dot products)
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace idb200 {
@@ -401,6 +403,149 @@ __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ 
     }
 }
 
+
+
+// TMA-staged form (the default): the residual rows stream through a 3-stage shared-memory ring of 16-row chunks filled by
+// cp.async.bulk (one elected thread issues, mbarrier completion), so ~70 KB per CTA are in flight regardless of what the warps
+// are doing; the register-resident kernel above keeps one 1.5 KB row per warp in flight only while that warp is in its load
+// phase and measured 3.3-3.5 TB/s (two rows per warp: 3.1 TB/s, more registers, fewer warps -- rejected).  Same per-lane
+// element assignment and reduction order as ln_film_kernel: bit-identical results.
+constexpr int kLnRows = 16;          // rows per chunk: one per warp
+constexpr int kLnStages = 3;
+constexpr int kLnFilmRows = 3;       // FiLM rows staged per chunk (L >= 8: a 16-row chunk touches at most 3 trajectories)
+constexpr int kLnThreads = 512;
+
+__device__ __forceinline__ void ln_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))), "r"(parity)
+            : "memory");
+    }
+}
+
+// stage layout: [kLnRows x d] residual rows | [kLnFilmRows x 2d] FiLM rows of the chunk's trajectories
+template <typename TO, int VPL>
+__global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float* __restrict__ h, const float* __restrict__ lnw,
+                                                                  const float* __restrict__ lnb, const float* __restrict__ gb,
+                                                                  long long gb_stride, TO* __restrict__ out, long long M, int L, int d) {
+    extern __shared__ __align__(128) unsigned char ln_smem[];
+    const size_t stage_floats = static_cast<size_t>(kLnRows) * d + static_cast<size_t>(kLnFilmRows) * 2 * d;
+    float* ring = reinterpret_cast<float*>(ln_smem);
+    float* saff = ring + kLnStages * stage_floats;                // LayerNorm affine [w | b] (2d floats)
+    uint64_t* full = reinterpret_cast<uint64_t*>(saff + 2 * d);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long chunks = (M + kLnRows - 1) / kLnRows;
+    for (int i = threadIdx.x; i < d; i += kLnThreads) { saff[i] = lnw[i]; saff[d + i] = lnb[i]; }
+    const bool film_smem = gb != nullptr && L >= 8 && (gb_stride % 4 == 0);
+    auto issue = [&](long long chunk, int stage) {
+        const long long r0 = chunk * kLnRows;
+        const long long rows = (M - r0 < kLnRows) ? (M - r0) : kLnRows;
+        const uint32_t bytes = static_cast<uint32_t>(rows * d * 4);
+        const long long t0 = r0 / L, t1 = (r0 + rows - 1) / L;
+        const int nt = film_smem ? static_cast<int>(t1 - t0 + 1) : 0;
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[stage]));
+        float* dst = ring + stage * stage_floats;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes + static_cast<uint32_t>(nt) * d * 8u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                     "l"(reinterpret_cast<uint64_t>(h + r0 * d)), "r"(bytes), "r"(bar)
+                     : "memory");
+        for (int t = 0; t < nt; ++t)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             static_cast<uint32_t>(__cvta_generic_to_shared(dst + static_cast<size_t>(kLnRows) * d + static_cast<size_t>(t) * 2 * d))),
+                         "l"(reinterpret_cast<uint64_t>(gb + (t0 + t) * gb_stride)), "r"(static_cast<uint32_t>(d) * 8u), "r"(bar)
+                         : "memory");
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kLnStages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&full[s]))) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int s = 0; s < kLnStages; ++s) {
+            const long long c = blockIdx.x + static_cast<long long>(s) * gridDim.x;
+            if (c < chunks) issue(c, s);
+        }
+    long long it = 0;
+    for (long long chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x, ++it) {
+        const int stage = static_cast<int>(it % kLnStages);
+        ln_mbar_wait(&full[stage], static_cast<uint32_t>((it / kLnStages) & 1));
+        const float* tile = ring + stage * stage_floats;
+        const float* film = tile + static_cast<size_t>(kLnRows) * d;
+        const long long t0 = (chunk * kLnRows) / L;
+#pragma unroll 1
+        for (int rr = 0; rr < kLnRows / 16; ++rr) {
+            const int r = warp + 16 * rr;
+            const long long m = chunk * kLnRows + r;
+            if (m >= M) break;
+            const float4* row = reinterpret_cast<const float4*>(tile + static_cast<size_t>(r) * d);
+            float4 v[VPL];
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int c4 = lane + 32 * i;
+                if (c4 * 4 < d) {
+                    v[i] = row[c4];
+                    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / static_cast<float>(d);
+            float sq = 0.0f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int c4 = lane + 32 * i;
+                if (c4 * 4 < d) {
+                    const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                    sq += a * a + b2 * b2 + c * c + e * e;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = rsqrtf(sq / static_cast<float>(d) + 1e-5f);
+            const float* g = nullptr;
+            if (gb) g = film_smem ? film + static_cast<size_t>(m / L - t0) * 2 * d : gb + (m / L) * gb_stride;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int c4 = lane + 32 * i;
+                if (c4 * 4 < d) {
+                    const float4 w4 = reinterpret_cast<const float4*>(saff)[c4];
+                    const float4 b4 = reinterpret_cast<const float4*>(saff + d)[c4];
+                    float o0 = (v[i].x - mean) * rstd * w4.x + b4.x;
+                    float o1 = (v[i].y - mean) * rstd * w4.y + b4.y;
+                    float o2 = (v[i].z - mean) * rstd * w4.z + b4.z;
+                    float o3 = (v[i].w - mean) * rstd * w4.w + b4.w;
+                    if (g) {
+                        const float4 ga = reinterpret_cast<const float4*>(g)[c4];
+                        const float4 be = reinterpret_cast<const float4*>(g + d)[c4];
+                        o0 = o0 * (1.0f + ga.x) + be.x;
+                        o1 = o1 * (1.0f + ga.y) + be.y;
+                        o2 = o2 * (1.0f + ga.z) + be.z;
+                        o3 = o3 * (1.0f + ga.w) + be.w;
+                    }
+                    if constexpr (sizeof(TO) == 2) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<unsigned*>(&p0);
+                        pk.y = *reinterpret_cast<unsigned*>(&p1);
+                        reinterpret_cast<uint2*>(out + m * d)[c4] = pk;
+                    } else {
+                        reinterpret_cast<float4*>(out + m * d)[c4] = make_float4(o0, o1, o2, o3);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                         // every warp is done reading this stage
+        const long long nxt = chunk + static_cast<long long>(kLnStages) * gridDim.x;
+        if (threadIdx.x == 0 && nxt < chunks) issue(nxt, stage);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // output head: y[m, j] = h[m, :] . W[j, :] + b[j], j < D (D <= 4): one warp per token
 // ------------------------------------------------------------------------------------------------
@@ -537,6 +682,32 @@ extern "C" int idb200_ln_film(const float* h, const float* ln_w, const float* ln
     if (M == 0) return IDB200_OK;
     IDB_REQUIRE(h && ln_w && ln_b && out, IDB200_EINVAL, "NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool bulk_env = !(getenv("IDB200_LN_BULK") && atoi(getenv("IDB200_LN_BULK")) == 0);
+    if (bulk_env && d % 4 == 0 && aligned(h, 16) && (!gamma_beta || aligned(gamma_beta, 16)) && M >= 4096) {
+        const size_t smem = (static_cast<size_t>(kLnStages) * (static_cast<size_t>(kLnRows) * d + static_cast<size_t>(kLnFilmRows) * 2 * d) + 2 * static_cast<size_t>(d)) * 4 + 64;
+        const long long chunks = (M + kLnRows - 1) / kLnRows;
+        int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+        if (per_sm > 2) per_sm = 2;
+        const int grid_b = grid_for(chunks, 1, per_sm > 0 ? per_sm : 1);
+        auto run = [&](auto kern) -> int {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(ln_film_bulk, smem=%zu): %s", smem, cudaGetErrorString(e));
+            return IDB200_OK;
+        };
+#define IDB_LN_LAUNCH(TO, VPL)                                                                                                     \
+    do {                                                                                                                           \
+        int rc_ = run(ln_film_bulk_kernel<TO, VPL>);                                                                               \
+        if (rc_) return rc_;                                                                                                       \
+        ln_film_bulk_kernel<TO, VPL><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d); \
+    } while (0)
+        if (out_is_bf16) {
+            if (d <= 256) IDB_LN_LAUNCH(__nv_bfloat16, 2); else if (d <= 384) IDB_LN_LAUNCH(__nv_bfloat16, 3); else IDB_LN_LAUNCH(__nv_bfloat16, 4);
+        } else {
+            if (d <= 256) IDB_LN_LAUNCH(float, 2); else if (d <= 384) IDB_LN_LAUNCH(float, 3); else IDB_LN_LAUNCH(float, 4);
+        }
+#undef IDB_LN_LAUNCH
+        return check_launch("ln_film_bulk_kernel");
+    }
     const int grid = warp_grid(M);
     if (out_is_bf16) ln_film_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<__nv_bfloat16*>(out), M, L, d);
     else ln_film_kernel<float, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<float*>(out), M, L, d);

@@ -51,6 +51,25 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
     return IDB200_OK;
 }
 
+// bf16 [rows, cols] view with an explicit row pitch (bytes, multiple of 16); pitch < cols * 2 gives OVERLAPPING rows (row r =
+// elements [r * pitch / 2, r * pitch / 2 + cols)): legal for TMA loads, used by the implicit conv to read two adjacent
+// 32-channel pixels as one 64-wide k-block
+int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
+                            uint32_t box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(IDB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if (!aligned(base, 16) || pitch_bytes % 16 != 0) return fail(IDB200_EALIGN, "TMA needs 16-byte aligned base and row pitch");
+    if (box_cols * 2 != 128) return fail(IDB200_EINVAL, "SWIZZLE_128B boxes are 128 bytes wide");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IDB200_ECUDA, "cuTensorMapEncodeTiled (pitched) failed (%d)", static_cast<int>(r));
+    return IDB200_OK;
+}
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
     return make_tmap_2d(out, base, 2, rows, cols, box_rows, box_cols);
 }
@@ -63,6 +82,7 @@ constexpr int kGemmThreads = 384;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 i
 constexpr int kBiasFloats = 2048;       // bias vector staged in shared memory (N <= 2048)
 
 enum { EPI_BF16 = 0, EPI_SILU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3 };
+constexpr int kConvMaxKB = 36;         // k-blocks of the implicit conv: 9 taps x C / 64 (C <= 256)
 
 // kPair: two CTAs of a cluster work on one [256 x BN] tile with tcgen05 cta_group::2: each CTA stages its own 128 rows of A but
 // only BN/2 rows of W, so the L2 -> shared-memory fill per flop drops by (128 + BN) / (128 + BN/2) (the unpaired kernel is bound
@@ -87,6 +107,13 @@ struct GemmParams {
     int N, K, epilogue;
     int splits;             // split-K: tile = (split, m, n); split s covers K/splits of the reduction, out += s * M * N (EPI_F32)
     int tma_out;            // 1: the epilogue stages 16 KB slabs in shared memory and writes them with TMA (tmap_out)
+    // implicit 3x3 convolution ("tap-shifted" GEMM, conv_P2 > 0): A is a zero-bordered NHWC activation [B * P2, C] (P2 = (H+2) *
+    // (W+2) padded positions per image); k-block kb reads the A box at row m0 + conv_shift[kb], column conv_col[kb] -- the input
+    // pixel of tap (ky, kx) for output position m is row m + (ky-1) * PW + (kx-1) -- so no im2col matrix exists.  The epilogue
+    // writes zeros to border positions (the next layer's zero padding).
+    int conv_P2, conv_PW, conv_PH;
+    int conv_shift[kConvMaxKB];
+    int conv_col[kConvMaxKB];
 };
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU (tanh.approx, rel. error ~2^-11, below the bf16
@@ -180,7 +207,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                             for (int hb = 0; hb < Cfg::kBRows / 64; ++hb) tma_load_2d_2sm(sb + hb * 8192, &tmap_w, &full_bar[stage], n0 + hb * 64, kb * kBK);
                         } else {
-                            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+                            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], p.conv_P2 ? p.conv_col[kb] : kb * kBK, p.conv_P2 ? m0 + p.conv_shift[kb] : m0);
                             tma_load_2d_2sm(sb, &tmap_w, &full_bar[stage], kb * kBK, n0);
                         }
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -193,7 +220,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int hb = 0; hb < BN / 64; ++hb) tma_load_2d(sb + hb * 8192, &tmap_w, &full_bar[stage], n0 + hb * 64, kb * kBK);
                     } else {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m0);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], p.conv_P2 ? p.conv_col[kb] : kb * kBK, p.conv_P2 ? m0 + p.conv_shift[kb] : m0);
                         tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBK, n0);
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -257,6 +284,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc_fence_after();
             const long long row = m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            bool border = false;                                    // implicit conv: this row is a zero-padding position
+            if (p.conv_P2) {
+                const int pos = static_cast<int>(row % p.conv_P2);
+                const int y = pos / p.conv_PW, x = pos - y * p.conv_PW;
+                border = y == 0 || y == p.conv_PH - 1 || x == 0 || x == p.conv_PW - 1;
+            }
             if (p.tma_out) {
                 // Coalesced epilogue.  A thread owns one ROW of the accumulator (tcgen05.ld 32x32b), so direct stores touch 32
                 // different lines per instruction: measured, they (not the MMAs) bounded the kernel at ~45 % of its store-less
@@ -295,6 +328,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             if (p.epilogue == EPI_SILU_BF16) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                            }
+                            if (border) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = 0.0f;
                             }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -539,7 +576,64 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
     }
 }
 
+
+// 3x3 convolution (padding 1) as a tap-shifted GEMM on zero-bordered NHWC activations (encoders.py:15-24, one conv layer):
+//   act [B * P2, C] bf16, P2 = (H + 2) * (W + 2); out [B * P2, N] bf16 = epi(conv(act) + bias), border positions written as zeros.
+//   Wm: bf16 [N, nkb * 64], k-block layout (host: models/_engine.py::conv_tap_weight):
+//     C % 64 == 0: k = tap * C + c (tap = ky * 3 + kx), nkb = 9 C / 64;
+//     C == 32:     k-block (ky, j) = [tap (ky, 2j) channels | tap (ky, 2j + 1) channels (zeros for the missing 4th tap)], nkb = 6 -- the A box
+//                  is two ADJACENT pixels read through an overlapping-row view of the activation tensor.
+int conv3x3_gemm(const void* act, int C, const void* Wm, const float* bias, void* out, int N, long long B, int H, int Wd, int epilogue,
+                 cudaStream_t st) {
+    IDB_REQUIRE(act && Wm && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(B >= 0 && H >= 1 && Wd >= 1, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(C == 32 || (C % 64 == 0 && 9 * C / 64 <= kConvMaxKB), IDB200_EUNSUPPORTED, "implicit conv needs C_in == 32 or a multiple of 64 up to 256 (got %d)", C);
+    IDB_REQUIRE(N % 64 == 0, IDB200_EUNSUPPORTED, "implicit conv needs C_out %% 64 == 0 (got %d)", N);
+    IDB_REQUIRE(epilogue == EPI_BF16 || epilogue == EPI_SILU_BF16, IDB200_EINVAL, "implicit conv writes bf16 (epilogue 0 or 1)");
+    if (B == 0) return IDB200_OK;
+    const int PW = Wd + 2, PH = H + 2, P2 = PW * PH;
+    const long long M = B * P2;
+    IDB_REQUIRE(M < (1ll << 31), IDB200_EUNSUPPORTED, "batch too large for one call");
+    GemmParams p{bias, out, M, N, 0, epilogue, 1, 1};
+    p.conv_P2 = P2; p.conv_PW = PW; p.conv_PH = PH;
+    int nkb = 0;
+    CUtensorMap ta;
+    int rc;
+    if (C == 32) {
+        for (int ky = 0; ky < 3; ++ky)
+            for (int j = 0; j < 2; ++j) { p.conv_shift[nkb] = (ky - 1) * PW + (j == 0 ? -1 : 1); p.conv_col[nkb] = 0; ++nkb; }
+        rc = make_tmap_bf16_2d_pitch(&ta, act, static_cast<uint64_t>(M - 1), 64, 64, kBM, kBK);    // row r = pixels r, r + 1
+    } else {
+        for (int tap = 0; tap < 9; ++tap)
+            for (int cb = 0; cb < C / 64; ++cb) { p.conv_shift[nkb] = (tap / 3 - 1) * PW + (tap % 3 - 1); p.conv_col[nkb] = cb * 64; ++nkb; }
+        rc = make_tmap_bf16_2d(&ta, act, static_cast<uint64_t>(M), static_cast<uint64_t>(C), kBM, kBK);
+    }
+    if (rc) return rc;
+    p.K = nkb * kBK;
+    int BN = 0;
+    for (int cand : {256, 192, 128, 64})
+        if (N % cand == 0) { BN = cand; break; }
+    CUtensorMap tw, tw_half, to;
+    rc = make_tmap_bf16_2d(&tw, Wm, static_cast<uint64_t>(N), static_cast<uint64_t>(p.K), static_cast<uint32_t>(BN), kBK);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tw_half, Wm, static_cast<uint64_t>(N), static_cast<uint64_t>(p.K), static_cast<uint32_t>(BN / 2), kBK);
+    if (rc) return rc;
+    rc = make_tmap_2d(&to, out, 2, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kBM, 64);
+    if (rc) return rc;
+    switch (BN) {
+        case 256: return launch_gemm<256>(ta, tw, tw_half, to, p, st);
+        case 192: return launch_gemm<192>(ta, tw, tw_half, to, p, st);
+        case 128: return launch_gemm<128>(ta, tw, tw_half, to, p, st);
+        default: return launch_gemm<64>(ta, tw, tw_half, to, p, st);
+    }
+}
+
 }  // namespace idb200
+
+extern "C" int idb200_conv3x3_gemm(const void* act, int C, const void* Wm, const float* bias, void* out, int N, int64_t B, int H, int W,
+                                   int epilogue, idb200_stream_t stream) {
+    return idb200::conv3x3_gemm(act, C, Wm, bias, out, N, B, H, W, epilogue, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K,
                                 int epilogue, idb200_stream_t stream) {

@@ -422,6 +422,70 @@ def conv_stack_gemm(x: torch.Tensor, weights: List[torch.Tensor], biases: List[t
     return pooled
 
 
+def conv_tap_weight(w: torch.Tensor) -> torch.Tensor:
+    """[C_out, C_in, 3, 3] -> bf16 [C_out, nkb * 64] in the k-block order of idb200_conv3x3_gemm (csrc/gemm.cu): C_in % 64 == 0:
+    k = (ky * 3 + kx) * C_in + c; C_in == 32: k-block (ky, j) = [tap (ky, 2j) | tap (ky, 2j + 1)] with zeros for the missing tap."""
+    co, ci = w.shape[0], w.shape[1]
+    wt = w.detach().float().permute(0, 2, 3, 1)                          # [co, ky, kx, ci]
+    if ci == 32:
+        wm = torch.zeros((co, 3, 4, 32), device=w.device, dtype=torch.float32)
+        wm[:, :, :3] = wt
+        return wm.reshape(co, 384).to(torch.bfloat16).contiguous()
+    return wt.reshape(co, 9 * ci).to(torch.bfloat16).contiguous()
+
+
+def conv_implicit_supported(convs) -> bool:
+    """Stacks the tap-shifted implicit GEMM takes: first layer C_in <= 2 -> 32 or 64 channels (CUDA cores), every further layer
+    C_in in {32} or a multiple of 64 (<= 256) and C_out a multiple of 64."""
+    if len(convs) < 2 or any(tuple(c.weight.shape[2:]) != (3, 3) for c in convs):
+        return False
+    if convs[0].weight.shape[1] > 2 or convs[0].weight.shape[0] not in (32, 64):
+        return False
+    for c in convs[1:]:
+        ci, co = c.weight.shape[1], c.weight.shape[0]
+        if not (ci == 32 or (ci % 64 == 0 and ci <= 256)) or co % 64 != 0:
+            return False
+    return True
+
+
+def conv_stack_implicit(x: torch.Tensor, convs, ws: "Workspace", chunk: int = 8192) -> torch.Tensor:
+    """MazeEncoder conv stack (encoders.py:15-24) + mean pool without an im2col matrix: zero-bordered NHWC bf16 activations
+    [B, (H+2)(W+2), C], first layer on CUDA cores, every further layer as ONE tap-shifted tcgen05 GEMM (SiLU in the epilogue,
+    border positions re-zeroed), pooling over the bordered layout.  x fp32 [B, C0, H, W] -> pooled fp32 [B, C_last]."""
+    B, C0, Hh, Ww = x.shape
+    dev = x.device
+    P2 = (Hh + 2) * (Ww + 2)
+    key = _sig([c.weight for c in convs[1:]])
+    if ws.bufs.get("_tapw_key") != key:
+        ws.bufs["_tapw"] = [conv_tap_weight(c.weight) for c in convs[1:]]
+        ws.bufs["_tapw_key"] = key
+    tapw = ws.bufs["_tapw"]
+    f = lambda t: t.detach().float().contiguous()
+    C_last = convs[-1].weight.shape[0]
+    pooled = torch.empty((B, C_last), device=dev, dtype=torch.float32)
+    st = L.stream(dev)
+    x = x.contiguous()
+    for lo in range(0, B, chunk):
+        n = min(chunk, B - lo)
+        c1 = convs[0].weight.shape[0]
+        # one extra (zero) row: the overlapping-row view of a 32-channel activation reads pixel r + 1 with pixel r
+        a = ws.get("act0", (n * P2 + 1, c1), torch.bfloat16, dev)
+        a[n * P2:].zero_()
+        L.call("idb200_conv_first_nhwc", x[lo:lo + n].data_ptr(), n, C0, Hh, Ww, f(convs[0].weight).data_ptr(), f(convs[0].bias).data_ptr(),
+               c1, a.data_ptr(), st)
+        C = c1
+        for li, c in enumerate(convs[1:]):
+            co = c.weight.shape[0]
+            o = ws.get(f"act{1 + li % 2}", (n * P2 + 1, co), torch.bfloat16, dev)
+            if co == 32:
+                o[n * P2:].zero_()
+            L.call("idb200_conv3x3_gemm", a.data_ptr(), C, tapw[li].data_ptr(), f(c.bias).data_ptr(), o.data_ptr(), co, n, Hh, Ww,
+                   EPI_SILU_BF16, st)
+            a, C = o, co
+        L.call("idb200_pool_bordered", a.data_ptr(), n, Hh, Ww, C, pooled[lo:lo + n].data_ptr(), st)
+    return pooled
+
+
 def conv_gemm_supported(convs) -> bool:
     return all(c.weight.shape[0] % 32 == 0 and tuple(c.weight.shape[2:]) == (3, 3) for c in convs)
 

@@ -42,6 +42,11 @@ class MazeEncoder(nn.Module):
             conv = E.conv_encoder_tc5 if (getattr(self, "use_tc5", True) and E.conv_tc5_supported(convs, x.shape[2], x.shape[3])) else E.conv_encoder_tc
             pooled = conv(occ, sdf, convs[0].weight.detach().float().contiguous(), convs[0].bias.detach().float().contiguous(),
                           self._w1_packed, convs[1].bias.detach().float().contiguous())
+        elif getattr(self, "precision", "bf16") == "bf16" and getattr(self, "use_implicit", True) and E.conv_implicit_supported(convs):
+            # deeper / wider stacks (the trainer default 32,64,128,128): tap-shifted implicit GEMM per layer, no im2col matrix
+            if not hasattr(self, "_gemm_ws"):
+                self._gemm_ws = E.Workspace()
+            pooled = E.conv_stack_implicit(x, convs, self._gemm_ws)
         elif getattr(self, "precision", "bf16") == "bf16" and E.conv_gemm_supported(convs):
             # deeper / wider stacks (the trainer default 32,64,128,128): im2col + tcgen05 GEMM per layer
             if not hasattr(self, "_gemm_ws"):

@@ -304,10 +304,11 @@ def test_denoiser_fused_io_matches_separate_kernels(which):
     assert torch.equal(head_only, fused)     # same kernel, bit-identical residual stream
 
 
-@pytest.mark.parametrize("chan,use_sdf,B", [((32, 64, 128, 128), False, 37), ((32, 64, 64), True, 5), ((64,), False, 4100)])
+@pytest.mark.parametrize("chan,use_sdf,B", [((32, 64, 128, 128), False, 37), ((32, 64, 64), True, 5), ((64,), False, 4100),
+                                            ((64, 128), False, 9), ((32, 64, 128, 128), False, 8300)])
 def test_deep_conv_stack_gemm_vs_oracle(chan, use_sdf, B):
-    """The trainer-default conditioning encoder (maze_channels 32,64,128,128) and other depths: im2col + tcgen05 GEMM per layer
-    (encoders.py:8-25), including a batch larger than one chunk of the patch matrix."""
+    """The trainer-default conditioning encoder (maze_channels 32,64,128,128) and other depths (encoders.py:8-25): the tap-shifted
+    implicit GEMM (default for stacks it takes; a batch larger than one chunk included) and the im2col + tcgen05 GEMM path."""
     from interpolated_diffusion_b200.models.encoders import MazeConditionEncoder
     gen = torch.Generator().manual_seed(9)
     cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float(), "start_goal": torch.rand((B, 4), generator=gen)}
@@ -320,6 +321,9 @@ def test_deep_conv_stack_gemm_vs_oracle(chan, use_sdf, B):
     m = m.cuda()
     got = m(_cuda(cond))
     assert _maxabs(got, ref) < 2e-2 * max(1.0, ref.abs().max().item()), _maxabs(got, ref)
+    m.maze.use_implicit = False                  # im2col + GEMM form of the same stack
+    got2 = m(_cuda(cond))
+    assert _maxabs(got2, ref) < 2e-2 * max(1.0, ref.abs().max().item()), _maxabs(got2, ref)
     m.precision = "fp32"
     if B <= 64:
         got = m(_cuda(cond))
