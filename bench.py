@@ -13,6 +13,7 @@ the other BASELINE configurations as extra keys, each measured in this run at th
     strong        configs[2] with the GLOBAL batch fixed at 65536 (B/N per GPU)
     train         configs[3]: Stage-2 training step, large model, global batch 4096 over N ranks (DP all-reduce)
     long_horizon  configs[4]: T=256 K=32 levels=4 causal, global batch 8192 (+ interp GB/s at T=256)
+    large_model   configs[2] with the trainer-default 384x12 models (9.58 GFLOP per trajectory), 16384 trajectories per GPU
 """
 from __future__ import annotations
 
@@ -336,6 +337,34 @@ def section_train(ctx, args):
     return res
 
 
+def section_large(ctx, args):
+    """SURVEY 8d, second line of cfg 3: the same generation workload with the trainer-default ("large") models -- d_model 384, 12
+    layers, 12 heads, ff 1536, maze 32-64-128-128 -- 9.58 GFLOP per trajectory; batch per GPU fixed (weak)."""
+    from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    B = args.large_batch
+    kp, il = build_models(dev, large=True)
+    cfg = GenerationConfig(T=T, K_min=K_MIN, levels=LEVELS, data_dim=D)
+    graph = GenerationGraph(kp, il, B, cfg, device=dev).capture()
+    cond = synthetic_cond(B, 4000 + rank, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+
+    def step():
+        graph.run(cond, torch.randn((B, K_MIN, D), generator=gen, device=dev))
+
+    ms, _ = ctx.timed(step, 3, 2)
+    ms /= 3
+    gf = (19 * 345.6 + 2798.1 + 211.6) / 1000.0
+    pk = peaks()
+    res = {"workload": "generation with the trainer-default models (384x12 ff1536, maze 32-64-128-128): Stage-1 DDIM-20 K=8 + interp T=64 + "
+                       "Stage-2 one-step, 9.58 GFLOP per trajectory (SURVEY 8d, second line of cfg 3)",
+           "batch_per_gpu": B, "global_batch": B * world, "n_gpus": world, "ms_per_step": ms, "trajectories_per_s": B * world / ms * 1e3,
+           "tflops_per_gpu": B * gf / ms, "frac_of_sustained_bf16": B * gf / ms / pk["bf16"]}
+    del graph, kp, il
+    torch.cuda.empty_cache()
+    return res
+
+
 def section_long_horizon(ctx, args):
     """BASELINE.json configs[4]: T=256, K=32, levels=4, causal Stage-2 denoiser (small models), B = 8192 sharded over the ranks."""
     from interpolated_diffusion_b200.models.denoiser_interp_levels_causal import InterpLevelCausalDenoiser
@@ -377,7 +406,7 @@ def run_ours(args):
     dist, world, rank, dev = ctx.dist, ctx.world, ctx.rank, ctx.dev
     from interpolated_diffusion_b200 import _lib as L
     from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig, GenerationGraph
-    sections = set(args.sections.split(",")) if args.sections != "all" else {"interp", "strong", "train", "long_horizon"}
+    sections = set(args.sections.split(",")) if args.sections != "all" else {"interp", "strong", "train", "long_horizon", "large"}
     extras = {}
 
     interp = None
@@ -523,6 +552,8 @@ def run_ours(args):
     torch.cuda.empty_cache()
     if "long_horizon" in sections:
         guarded("long_horizon", lambda: section_long_horizon(ctx, args))
+    if "large" in sections:
+        guarded("large_model", lambda: section_large(ctx, args))
     if "train" in sections:
         guarded("train", lambda: section_train(ctx, args))
 
@@ -567,11 +598,13 @@ def main():
     ap.add_argument("--model", default="small", choices=["small", "large"], help="small = BASELINE configs[2] (default); large = trainer-default models (dev)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--sections", default="all", help="comma list of the secondary measurements carried in the line: interp (configs[1]), "
-                    "strong (configs[2], global batch sharded), long_horizon (configs[4]), train (configs[3]); 'none' = headline only")
+                    "strong (configs[2], global batch sharded), long_horizon (configs[4]), train (configs[3]), large (configs[2] with the "
+                    "trainer-default models); 'none' = headline only")
     ap.add_argument("--strong-batch", type=int, default=65536, help="global batch of the strong-scaling run")
     ap.add_argument("--train-batch", type=int, default=4096, help="global batch of the training step (configs[3])")
     ap.add_argument("--train-steps", type=int, default=8)
     ap.add_argument("--lh-batch", type=int, default=8192, help="global batch of the long-horizon run (configs[4])")
+    ap.add_argument("--large-batch", type=int, default=16384, help="trajectories per GPU of the large-model generation run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -346,6 +346,297 @@ static int launch(const CUtensorMap& tm, const Params& p, long long units, cudaS
     return check_launch("attn_tc5_kernel");
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Double-buffered form for L <= 128 (one CTA per SM, 640 threads).  In the kernel above a group's chain
+//   S MMA -> softmax -> P V MMA -> O read-out -> (next) S MMA
+// is serial: four MMA <-> CUDA-core hand-offs per problem, and at L = 8 (8 keys per row) the hand-offs ARE the time
+// (3.4 us per unit measured against 1.2 us of HBM time).  Here every group has TWO score / output buffers in tensor memory
+// (4 x 128 columns = all 512) and two P tiles, the O read-out belongs to separate epilogue warps, and the MMA warp issues
+// S(u+1) before P V(u): the softmax warps of a group run back to back, the read-out of O(u-1) and the MMAs of u+1 hide under
+// softmax(u).  The row sums travel from the softmax to the epilogue warps through a dead score column of the same buffer.
+// Warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4..11 softmax (group = (w-4)/4), 12..19 epilogue (group = (w-12)/4).
+// ------------------------------------------------------------------------------------------------
+constexpr int kDbThreads = 640;
+struct DbCfg {
+    static constexpr int kStageBytes = 3 * kTile;                            // Q | K | V tiles [128 x 64]
+    static constexpr int kPBytes = 2 * kTile;                                // [128 x 128] bf16
+    static constexpr int kOffP = 2 * kStageBytes;
+    static constexpr int kOffBar = kOffP + 4 * kPBytes;
+    static constexpr int kSmem = kOffBar + 256 + 1024;
+    static_assert(kSmem <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kDbThreads, 1) attn_tc5_db_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Params p) {
+    using C = DbCfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    __builtin_assume(__isShared(smem));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+    uint64_t* qk_full = bars;                       // [2 stages]
+    uint64_t* v_full = bars + 2;
+    uint64_t* qk_empty = bars + 4;
+    uint64_t* v_empty = bars + 6;
+    uint64_t* s_full = bars + 8;                    // [group * 2 + buffer]
+    uint64_t* p_full = bars + 12;
+    uint64_t* o_full = bars + 16;
+    uint64_t* s_free = bars + 20;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = p.H * 32;
+    const int HP = p.H / 2;
+    const long long units = p.tiles * HP;
+    const int L = p.L;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qk_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&qk_empty[i], 1);
+            mbar_init(&v_empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&s_free[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto unit_rows = [&](long long u, long long& row0, int& hp) {
+        const long long t = u / HP;
+        hp = static_cast<int>(u - t * HP);
+        row0 = t * p.G * L;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long long it = 0;
+            for (long long u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+                const int st = static_cast<int>(it & 1);
+                const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+                long long row0;
+                int hp;
+                unit_rows(u, row0, hp);
+                uint8_t* base = smem + st * C::kStageBytes;
+                mbar_wait(&qk_empty[st], ph ^ 1, 10);
+                mbar_arrive_expect_tx(&qk_full[st], 2 * kTile);
+                tma_load_2d(base, &tm_qkv, &qk_full[st], hp * 64, static_cast<int>(row0));
+                tma_load_2d(base + kTile, &tm_qkv, &qk_full[st], d + hp * 64, static_cast<int>(row0));
+                mbar_wait(&v_empty[st], ph ^ 1, 11);
+                mbar_arrive_expect_tx(&v_full[st], kTile);
+                tma_load_2d(base + 2 * kTile, &tm_qkv, &v_full[st], 2 * d + hp * 64, static_cast<int>(row0));
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);          // B (V) MN-major
+        long long n_units = 0;
+        for (long long u = blockIdx.x; u < units; u += gridDim.x) ++n_units;
+        auto pv_phase = [&](long long it) {                                       // P V of the unit with local index `it`
+            const int st = static_cast<int>(it & 1);
+            const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+            const int b = static_cast<int>(it & 1);
+            const uint32_t sV = smem_u32(smem + st * C::kStageBytes + 2 * kTile);
+            mbar_wait(&v_full[st], ph, 22);
+            tc_fence_after();
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(&p_full[g * 2 + b], ph, 23);
+                tc_fence_after();
+                const uint32_t sP = smem_u32(smem + C::kOffP + (g * 2 + b) * C::kPBytes);
+                const uint64_t vd = umma_desc_sw128_mn(sV) + 4 * g;
+                const uint32_t dcol = tmem_base + (g * 2 + b) * 128;
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_bf16(dcol, umma_desc_sw128(sP + (ks >> 2) * kTile) + 2 * (ks & 3), vd + 128 * ks, idesc_o, ks > 0 ? 1u : 0u);
+                    umma_commit(&o_full[g * 2 + b]);
+                }
+                __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit(&v_empty[st]);
+            __syncwarp();
+        };
+        for (long long it = 0; it < n_units; ++it) {
+            const int st = static_cast<int>(it & 1);
+            const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+            const int b = static_cast<int>(it & 1);
+            const uint32_t sQ = smem_u32(smem + st * C::kStageBytes), sK = sQ + kTile;
+            mbar_wait(&qk_full[st], ph, 20);
+            tc_fence_after();
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(&s_free[g * 2 + b], ph ^ 1, 21);                        // O of problem it - 2 has been read out of this buffer
+                tc_fence_after();
+                const uint64_t ad = umma_desc_sw128(sQ) + 4 * g, bd = umma_desc_sw128(sK) + 4 * g;
+                const uint32_t dcol = tmem_base + (g * 2 + b) * 128;
+                if (elect_one_sync()) {
+                    umma_bf16(dcol, ad, bd, idesc_s, 0u);
+                    umma_bf16(dcol, ad + 2, bd + 2, idesc_s, 1u);
+                    umma_commit(&s_full[g * 2 + b]);
+                }
+                __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit(&qk_empty[st]);
+            __syncwarp();
+            if (it > 0) pv_phase(it - 1);
+        }
+        if (n_units > 0) pv_phase(n_units - 1);
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== softmax warps =====================
+        const int g = (warp - 4) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        long long it = 0;
+        for (long long u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+            const int b = static_cast<int>(it & 1);
+            const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+            const uint32_t tS = tmem_base + (g * 2 + b) * 128 + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t sPw = smem_u32(smem + C::kOffP + (g * 2 + b) * C::kPBytes);
+            const long long tile = u / HP;
+            int lo = 0, hi = 0;
+            {
+                const int j = row / L;
+                if (j < p.G && tile * p.G + j < p.B) {
+                    lo = j * L;
+                    hi = p.causal ? row + 1 : lo + L;
+                }
+            }
+            const int wlo = __reduce_min_sync(0xffffffffu, hi > lo ? (lo & ~31) : 0x7fffffff);
+            const int whi = __reduce_max_sync(0xffffffffu, hi > lo ? hi : 0);
+            mbar_wait(&s_full[g * 2 + b], ph, 30);
+            tc_fence_after();
+            float mx = -INFINITY;
+            for (int c0 = wlo; c0 < whi; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tS + c0, r);
+                tmem_ld_wait();
+                if (__all_sync(0xffffffffu, c0 >= lo && c0 + 32 <= hi)) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int c = c0 + j;
+                        if (c >= lo && c < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    }
+                }
+            }
+            const float mneg = (mx == -INFINITY) ? 0.0f : mx * kScaleLog2;
+            float sum = 0.0f;
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t pk[16];
+                if (c0 >= wlo && c0 < whi) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tS + c0, r);
+                    tmem_ld_wait();
+                    const bool full = __all_sync(0xffffffffu, c0 >= lo && c0 + 32 <= hi);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + 2 * j;
+                        float e0 = ex2(fmaf(__uint_as_float(r[2 * j]), kScaleLog2, -mneg));
+                        float e1 = ex2(fmaf(__uint_as_float(r[2 * j + 1]), kScaleLog2, -mneg));
+                        if (!full) {
+                            e0 = (c >= lo && c < hi) ? e0 : 0.0f;
+                            e1 = (c + 1 >= lo && c + 1 < hi) ? e1 : 0.0f;
+                        }
+                        sum += e0 + e1;
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                }
+                const uint32_t blk = sPw + (c0 >> 6) * kTile;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + sw128_offset(row, (c0 & 63) + 8 * i)), "r"(pk[4 * i]),
+                                 "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                                 : "memory");
+            }
+            tmem_st_32x1(tS + 32, __float_as_uint(sum));                   // row sum -> a dead score column (O only takes columns 0..31)
+            tmem_st_wait();
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g * 2 + b]);
+        }
+    } else if (warp >= 12) {
+        // ===================== epilogue warps: O / rowsum -> bf16 -> global =====================
+        const int g = (warp - 12) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        long long it = 0;
+        for (long long u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+            const int b = static_cast<int>(it & 1);
+            const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+            const uint32_t tS = tmem_base + (g * 2 + b) * 128 + (static_cast<uint32_t>(q * 32) << 16);
+            long long row0;
+            int hp;
+            unit_rows(u, row0, hp);
+            const long long tile = u / HP;
+            const int j = row / L;
+            const bool live = j < p.G && tile * p.G + j < p.B;
+            mbar_wait(&o_full[g * 2 + b], ph, 31);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32(tS, r);
+            const float sum = __uint_as_float(tmem_ld_32x1(tS + 32));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g * 2 + b]);
+            if (live) {
+                const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (row0 + row) * d + hp * 64 + g * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 2 * k]) * inv, __uint_as_float(r[8 * i + 2 * k + 1]) * inv);
+                        w[k] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int launch_db(const CUtensorMap& tm, const Params& p, long long units, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc5_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DbCfg::kSmem);
+        if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(attn_tc5_db, smem=%d): %s", DbCfg::kSmem, cudaGetErrorString(e));
+        attr = true;
+    }
+    const int grid = static_cast<int>(units < num_sms() ? units : num_sms());
+    attn_tc5_db_kernel<<<grid, kDbThreads, DbCfg::kSmem, st>>>(tm, p);
+    return check_launch("attn_tc5_db_kernel");
+}
+
 }  // namespace at5
 
 // bf16 qkv [B*L, 3d] -> out bf16 [B*L, d]; H even, L <= 256.  Returns IDB200_EUNSUPPORTED (without setting an error the
@@ -367,6 +658,8 @@ int attention_tc5(const void* qkv, void* out, long long B, int L, int H, int cau
     if (L <= 128) {
         p.G = 128 / L;
         p.tiles = (B + p.G - 1) / p.G;
+        static const int db = getenv("IDB200_ATT5_DB") ? atoi(getenv("IDB200_ATT5_DB")) : 1;
+        if (db) return at5::launch_db(tm, p, p.tiles * (H / 2), st);
         if (L < 32) return at5::launch<128, 1>(tm, p, p.tiles * (H / 2), st);
         return at5::launch<128, 2>(tm, p, p.tiles * (H / 2), st);
     }

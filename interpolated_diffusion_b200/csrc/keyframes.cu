@@ -154,13 +154,72 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
         if (lane < n4 - n) ws.sc[n + lane] = kInf;
         __syncwarp();
 
-        // ---- stable rank by all-pairs count -----------------------------------------------------
-        // rank(j) = #{u : s_u < s_j}: every lane streams the staged scores with broadcast 16-byte
-        // loads and counts sign bits of the packed differences (one FADD2 + two shift-adds per pair
-        // of candidates).  A tie makes both partners miss a count, so sum(rank) < n(n-1)/2 detects
-        // ties exactly; those rows (~1e-4 of torch.rand rows) take the index-tie-break path.
+        // ---- which interior positions does each level take? -------------------------------------
+        // Level s takes the thr_s lowest-ranked scores.  E <= 2 (T <= 64): stable rank by an all-pairs count -- every lane streams
+        // the staged scores with broadcast 16-byte loads and counts sign bits of packed differences; a tie makes both partners
+        // miss a count, so sum(rank) < n(n-1)/2 detects ties exactly and those rows take the index-tie-break loop.
+        // E >= 4 (T = 128 / 256): the all-pairs count is O(n^2) = 3.1 k instructions per lane at n = 254 and bounded the kernel
+        // (0.34 of the HBM roofline).  Only the level CUTS matter, so the warp sorts the scores instead -- a bitonic network over
+        // the 32 E register-resident values, ~0.8 k instructions -- and a position is in level s iff its score is below the
+        // thr_s-th sorted value.  A tie straddling a cut (sorted[thr-1] == sorted[thr]) routes the row to the exact loop.
         int cnt[E];
-        {
+        float cut[kMaxLevels];
+        bool by_cut = false;
+        if constexpr (E >= 4) {
+            float v[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = me[e];                 // any initial arrangement; virtual index i = lane * E + e
+#pragma unroll
+            for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (j < E) {                                       // partner in the same lane
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            if ((e & j) == 0) {
+                                const bool up = (((lane * E + e) & k) == 0);
+                                const float lo = fminf(v[e], v[e | j]), hi = fmaxf(v[e], v[e | j]);
+                                v[e] = up ? lo : hi;
+                                v[e | j] = up ? hi : lo;
+                            }
+                        }
+                    } else {                                           // partner in lane ^ (j / E)
+                        const int lj = j / E;
+                        const bool upper = (lane & lj) != 0;
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            const float o = __shfl_xor_sync(kFull, v[e], lj);
+                            const bool up = (((lane * E + e) & k) == 0);
+                            v[e] = (up != upper) ? fminf(v[e], o) : fmaxf(v[e], o);
+                        }
+                    }
+                }
+            }
+            float* sorted = reinterpret_cast<float*>(ws.cv);           // idle until the interpolation stage
+#pragma unroll
+            for (int e = 0; e < E; ++e) sorted[lane * E + e] = v[e];
+            __syncwarp();
+            by_cut = true;
+            for (int s = 0; s < p.n_levels; ++s) {
+                const int thr = p.thr[s];
+                if (thr <= 0) cut[s] = -kInf;
+                else if (thr >= n) cut[s] = kInf;
+                else {
+                    cut[s] = sorted[thr];
+                    if (sorted[thr - 1] == sorted[thr]) by_cut = false;   // tie across the cut: exact path (warp-uniform)
+                }
+            }
+            __syncwarp();
+            if (!by_cut) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) cnt[e] = 0;
+                for (int u = 0; u < n; ++u) {
+                    const float su = ws.sc[u];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) cnt[e] += ((su < me[e]) || (su == me[e] && u < jj[e])) ? 1 : 0;
+                }
+            }
+        } else {
             unsigned long long m2[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) { cnt[e] = 0; m2[e] = pack2(me[e], me[e]); }
@@ -172,18 +231,18 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
                     count_lt2(cnt[e], v.z, v.w, m2[e]);
                 }
             }
-        }
-        int rsum = 0;
+            int rsum = 0;
 #pragma unroll
-        for (int e = 0; e < E; ++e) rsum += (jj[e] >= 0) ? cnt[e] : 0;
-        rsum = __reduce_add_sync(kFull, rsum);
-        if (rsum != (n * (n - 1)) / 2) {   // warp-uniform: exact stable order (lower index first)
+            for (int e = 0; e < E; ++e) rsum += (jj[e] >= 0) ? cnt[e] : 0;
+            rsum = __reduce_add_sync(kFull, rsum);
+            if (rsum != (n * (n - 1)) / 2) {   // warp-uniform: exact stable order (lower index first)
 #pragma unroll
-            for (int e = 0; e < E; ++e) cnt[e] = 0;
-            for (int u = 0; u < n; ++u) {
-                const float su = ws.sc[u];
+                for (int e = 0; e < E; ++e) cnt[e] = 0;
+                for (int u = 0; u < n; ++u) {
+                    const float su = ws.sc[u];
 #pragma unroll
-                for (int e = 0; e < E; ++e) cnt[e] += ((su < me[e]) || (su == me[e] && u < jj[e])) ? 1 : 0;
+                    for (int e = 0; e < E; ++e) cnt[e] += ((su < me[e]) || (su == me[e] && u < jj[e])) ? 1 : 0;
+                }
             }
         }
 
@@ -193,7 +252,8 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int t = lane + 32 * e;
-                const bool a = (t < T) && ((!noend && (t == 0 || t == T - 1)) || (jj[e] >= 0 && cnt[e] < thr));
+                const bool in = by_cut ? (me[e] < cut[s]) : (cnt[e] < thr);
+                const bool a = (t < T) && ((!noend && (t == 0 || t == T - 1)) || (jj[e] >= 0 && in));
                 const unsigned w = __ballot_sync(kFull, a);
                 if (lane == 0) ws.mw[s * E + e] = w;
             }
