@@ -188,6 +188,14 @@ int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student, const uint
 
 int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K, int epilogue,
                      idb200_stream_t stream);
+/* Training forms of the same GEMM with a second bf16 [M,N] tensor (N % 64 == 0), replacing the separate SiLU passes of the MLP
+ * (transformer.py:43-45) in the forward / backward of the training step, bit-identical to them:
+ *   epilogue 4: out = bf16(acc + bias) (pre-activation u), aux = bf16(SiLU(out))            -- ff.0 forward, both kept
+ *   epilogue 5: out = bf16(bf16(acc) * SiLU'(aux)), aux = u (read through TMA)               -- dU = (dY W2) . SiLU'(u) */
+#define IDB200_EPI_BF16_SILU_DUAL 4
+#define IDB200_EPI_BF16_DSILU 5
+int idb200_gemm_bf16_aux(const void* A, const void* W, const float* bias, void* out, void* aux, int64_t M, int N, int K, int epilogue,
+                         idb200_stream_t stream);
 
 /* Implicit-GEMM 3x3 convolution stack (MazeEncoder, src/models/encoders.py:15-25) on zero-bordered NHWC activations
  * act [B, (H+2)*(W+2), C] bf16 (border positions are zeros = the conv's zero padding): the input pixel of tap (ky, kx) for the

@@ -81,7 +81,11 @@ constexpr int kBK = 64;
 constexpr int kGemmThreads = 384;      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr int kBiasFloats = 2048;       // bias vector staged in shared memory (N <= 2048)
 
-enum { EPI_BF16 = 0, EPI_SILU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3 };
+// 4 / 5: training forms with a second bf16 [M,N] tensor `aux` (idb200_gemm_bf16_aux):
+//   EPI_BF16_SILU_DUAL  out = bf16(acc + bias) (the pre-activation u, kept for the backward), aux = bf16(SiLU(out)) -- ff.0 forward
+//   EPI_BF16_DSILU      out = bf16(bf16(acc) * SiLU'(aux)), aux = u read through TMA -- dU = (dY W2) . SiLU'(u) of the backward
+// Both reproduce the separate SiLU kernels of csrc/train_bwd.cu bit for bit (same roundings, x * sigmoid(x) with __expf).
+enum { EPI_BF16 = 0, EPI_SILU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3, EPI_BF16_SILU_DUAL = 4, EPI_BF16_DSILU = 5 };
 constexpr int kConvMaxKB = 36;         // k-blocks of the implicit conv: 9 taps x C / 64 (C <= 256)
 
 // kPair: two CTAs of a cluster work on one [256 x BN] tile with tcgen05 cta_group::2: each CTA stages its own 128 rows of A but
@@ -125,6 +129,9 @@ __device__ __forceinline__ float silu_f(float x) {
     return fmaf(h, t, h);
 }
 
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
 // kMN = false: A [M,K], W [N,K] row-major (K-major operands): out = A W^T.
 // kMN = true : both operands stored reduction-major, A [K,M], W [K,N] row-major (MN-major UMMA operands): out = A^T W.  This is
 // the weight-gradient form dW = dY^T X with the tokens as K: TMA boxes are [64 tokens x 64 features] (one SW128 atom column),
@@ -133,7 +140,7 @@ __device__ __forceinline__ float silu_f(float x) {
 template <int BN, bool kMN, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p) {
     using Cfg = GemmCfg<BN, kPair>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -144,6 +151,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* acc_full = bars + 2 * Cfg::kStages;           // [kAccStages] MMA -> epilogue
     uint64_t* acc_empty = acc_full + Cfg::kAccStages;       // [kAccStages] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::kAccStages);
+    uint64_t* aux_bar = acc_empty + Cfg::kAccStages + 1;   // [2] EPI_BF16_DSILU: the u slab of an epilogue half has landed
     float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
     uint8_t* staging = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem + Cfg::kStages * Cfg::kStageBytes + 256 + kBiasFloats * 4) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -169,6 +177,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPair ? 16 : 8); }
+        mbar_init(&aux_bar[0], 1);
+        mbar_init(&aux_bar[1], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -276,6 +286,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t slab_it = 0;
+        uint32_t aux_phase = 0;
         for (long long tile = tile0; tile < tiles; tile += tile_stride) {
             const long long mn = tile % mn_tiles;
             const long long m0 = (mn / n_tiles) * kMRows + static_cast<long long>(rank) * kBM;
@@ -296,15 +307,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // speed.  Instead each half (4 warps = 128 rows) fills a 16 KB slab (64 bf16 / 32 fp32 columns, SWIZZLE_128B
                 // rows) in shared memory and one thread hands it to TMA (store, or reduce-add for the residual epilogue); two
                 // slabs per half ping-pong so the conversion of slab i+1 overlaps the store of slab i.
-                const bool out16 = p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16;
+                const bool out16 = p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16 || p.epilogue >= EPI_BF16_SILU_DUAL;
                 const int slab_cols = out16 ? 64 : 32;
                 const int n_slabs = BN / slab_cols;
                 const int r_in = q * 32 + lane;
                 uint8_t* stage_h = staging + half * 2 * 16384;
-                for (int sl = half; sl < n_slabs; sl += 2) {
+                const int passes = p.epilogue == EPI_BF16_SILU_DUAL ? 2 : 1;
+                // dual-output form: each slab is staged twice (pass 0: pre-activation -> out, pass 1: SiLU -> aux)
+                for (int sl = half; sl < n_slabs; sl += 2)
+                for (int pass = 0; pass < passes; ++pass) {
                     uint8_t* buf = stage_h + (slab_it & 1) * 16384;
                     if (q == 0 && lane == 0) tma_store_wait_read<1>();          // the store that last read `buf` is done with it
                     named_barrier_sync(1 + half, 128);
+                    if (p.epilogue == EPI_BF16_DSILU) {                        // bring the u slab in (same box as the output slab)
+                        if (q == 0 && lane == 0) {
+                            mbar_arrive_expect_tx(&aux_bar[half], 16384);
+                            tma_load_2d(buf, &tmap_aux, &aux_bar[half], n0 + sl * slab_cols, static_cast<int>(m0));
+                        }
+                        mbar_wait(&aux_bar[half], aux_phase, 6);
+                        aux_phase ^= 1;
+                    }
                     const int nch = out16 ? 2 : 1;
                     for (int cc = 0; cc < nch; ++cc) {
                         const int c = sl * slab_cols + cc * 32;
@@ -328,6 +350,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             if (p.epilogue == EPI_SILU_BF16) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                            } else if (p.epilogue == EPI_BF16_SILU_DUAL && pass == 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { const float u = bf16_round(v[j]); v[j] = u * sigmoid_exact(u); }
+                            } else if (p.epilogue == EPI_BF16_DSILU) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int piece = cc * 4 + j;
+                                    const uint4 uu = *reinterpret_cast<const uint4*>(buf + r_in * 128 + ((piece ^ (r_in & 7)) << 4));
+                                    const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&uu);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 uf = __bfloat1622float2(u2[k]);
+                                        const float s0 = sigmoid_exact(uf.x), s1 = sigmoid_exact(uf.y);
+                                        v[8 * j + 2 * k] = bf16_round(v[8 * j + 2 * k]) * (s0 * (1.0f + uf.x * (1.0f - s0)));
+                                        v[8 * j + 2 * k + 1] = bf16_round(v[8 * j + 2 * k + 1]) * (s1 * (1.0f + uf.y * (1.0f - s1)));
+                                    }
+                                }
                             }
                             if (border) {
 #pragma unroll
@@ -358,6 +397,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     named_barrier_sync(3 + half, 128);
                     if (q == 0 && lane == 0) {
                         if (p.epilogue == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, buf, n0 + sl * slab_cols, static_cast<int>(m0));
+                        else if (pass == 1) tma_store_2d(&tmap_aux, buf, n0 + sl * slab_cols, static_cast<int>(m0));
                         else tma_store_2d(&tmap_out, buf, n0 + sl * slab_cols, static_cast<int>(m0));
                         tma_store_commit();
                     }
@@ -455,7 +495,9 @@ static bool pair_enabled() {
 }
 
 template <int BN, bool kMN, bool kPair>
-static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmParams& p, cudaStream_t st,
+                            const CUtensorMap* taux = nullptr) {
+    const CUtensorMap& tx = taux ? *taux : to;
     using Cfg = GemmCfg<BN, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -479,12 +521,12 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
         attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, kMN, true>, ta, tw, to, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, kMN, true>, ta, tw, to, tx, p);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaLaunchKernelEx(gemm pair): %s", cudaGetErrorString(e));
         return check_launch("gemm_bf16_tn_kernel<pair>");
     } else {
         const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-        gemm_bf16_tn_kernel<BN, kMN, false><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, to, p);
+        gemm_bf16_tn_kernel<BN, kMN, false><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, to, tx, p);
         return check_launch("gemm_bf16_tn_kernel");
     }
 }
@@ -493,12 +535,12 @@ static int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tw, const 
 // two M tiles of work
 template <int BN, bool kMN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tw_half, const CUtensorMap& to, const GemmParams& p,
-                       cudaStream_t st) {
+                       cudaStream_t st, const CUtensorMap* taux = nullptr) {
     constexpr bool can_pair = kMN ? (BN % 128 == 0) : (BN % 64 == 0);
     if constexpr (can_pair) {
-        if (pair_enabled() && p.M > kBM) return launch_gemm_impl<BN, kMN, true>(ta, tw_half, to, p, st);
+        if (pair_enabled() && p.M > kBM) return launch_gemm_impl<BN, kMN, true>(ta, tw_half, to, p, st, taux);
     }
-    return launch_gemm_impl<BN, kMN, false>(ta, tw, to, p, st);
+    return launch_gemm_impl<BN, kMN, false>(ta, tw, to, p, st, taux);
 }
 
 // out[s] [M,N] fp32 = A[K_s, M]^T W[K_s, N] for the s-th slice of the K rows (MN-major operands, see the kernel comment)
@@ -533,15 +575,17 @@ int gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, long long 
 }
 
 int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, long long M, int N, int K, int epilogue,
-                 cudaStream_t st, int splits) {
+                 cudaStream_t st, int splits, void* aux = nullptr) {
     IDB_REQUIRE(A && W && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE((epilogue >= EPI_BF16_SILU_DUAL) == (aux != nullptr), IDB200_EINVAL, "epilogues 4 / 5 need the aux tensor (and only they take one)");
     IDB_REQUIRE(M >= 0 && N > 0 && K > 0, IDB200_EINVAL, "bad shape");
     IDB_REQUIRE(K % kBK == 0, IDB200_EUNSUPPORTED, "K must be a multiple of %d (got %d)", kBK, K);
     IDB_REQUIRE(N % 32 == 0, IDB200_EUNSUPPORTED, "N must be a multiple of 32 (got %d)", N);
-    IDB_REQUIRE(epilogue >= 0 && epilogue <= 3, IDB200_EINVAL, "unknown epilogue %d", epilogue);
+    IDB_REQUIRE(epilogue >= 0 && epilogue <= 5, IDB200_EINVAL, "unknown epilogue %d", epilogue);
     IDB_REQUIRE(splits >= 1 && (K / kBK) % splits == 0, IDB200_EINVAL, "splits (%d) must divide K / %d", splits, kBK);
     IDB_REQUIRE(splits == 1 || (epilogue == EPI_F32 && bias == nullptr), IDB200_EINVAL, "split-K needs the fp32 epilogue without bias");
-    IDB_REQUIRE(aligned(out, 16), IDB200_EALIGN, "out must be 16-byte aligned");
+    IDB_REQUIRE(aligned(out, 16) && (!aux || aligned(aux, 16)), IDB200_EALIGN, "out / aux must be 16-byte aligned");
+    IDB_REQUIRE(!aux || (N % 64 == 0 && M < (1ll << 31)), IDB200_EUNSUPPORTED, "the aux epilogues need N %% 64 == 0");
     if (M == 0) return IDB200_OK;
     int BN = 0;
     for (int cand : {256, 192, 128, 96, 64, 32})
@@ -558,21 +602,26 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
     }
     // TMA-store epilogue: 16 KB slabs of 64 bf16 / 32 fp32 columns (N % 64 == 0 covers both); split-K partials keep the direct stores
     static const bool tma_epi = !(getenv("IDB200_GEMM_TMA_EPI") && getenv("IDB200_GEMM_TMA_EPI")[0] == '0');
-    const bool out16 = epilogue == EPI_BF16 || epilogue == EPI_SILU_BF16;
-    const int use_tma = (tma_epi && splits == 1 && BN % 64 == 0 && M < (1ll << 31)) ? 1 : 0;
-    CUtensorMap to = ta;
+    const bool out16 = epilogue == EPI_BF16 || epilogue == EPI_SILU_BF16 || aux != nullptr;
+    const int use_tma = ((tma_epi || aux) && splits == 1 && BN % 64 == 0 && M < (1ll << 31)) ? 1 : 0;
+    CUtensorMap to = ta, tx = ta;
     if (use_tma) {
         rc = make_tmap_2d(&to, out, out16 ? 2 : 4, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kBM, out16 ? 64 : 32);
         if (rc) return rc;
+        if (aux) {
+            rc = make_tmap_2d(&tx, aux, 2, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kBM, 64);
+            if (rc) return rc;
+        }
     }
     GemmParams p{bias, out, M, N, K, epilogue, splits, use_tma};
+    const CUtensorMap* px = aux ? &tx : nullptr;
     switch (BN) {
-        case 256: return launch_gemm<256>(ta, tw, tw_half, to, p, st);
-        case 192: return launch_gemm<192>(ta, tw, tw_half, to, p, st);
-        case 128: return launch_gemm<128>(ta, tw, tw_half, to, p, st);
-        case 96: return launch_gemm<96>(ta, tw, tw_half, to, p, st);
-        case 64: return launch_gemm<64>(ta, tw, tw_half, to, p, st);
-        default: return launch_gemm<32>(ta, tw, tw_half, to, p, st);
+        case 256: return launch_gemm<256>(ta, tw, tw_half, to, p, st, px);
+        case 192: return launch_gemm<192>(ta, tw, tw_half, to, p, st, px);
+        case 128: return launch_gemm<128>(ta, tw, tw_half, to, p, st, px);
+        case 96: return launch_gemm<96>(ta, tw, tw_half, to, p, st, px);
+        case 64: return launch_gemm<64>(ta, tw, tw_half, to, p, st, px);
+        default: return launch_gemm<32>(ta, tw, tw_half, to, p, st, px);
     }
 }
 
@@ -638,6 +687,11 @@ extern "C" int idb200_conv3x3_gemm(const void* act, int C, const void* Wm, const
 extern "C" int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K,
                                 int epilogue, idb200_stream_t stream) {
     return idb200::gemm_bf16_tn(A, W, bias, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream), 1);
+}
+
+extern "C" int idb200_gemm_bf16_aux(const void* A, const void* W, const float* bias, void* out, void* aux, int64_t M, int N, int K,
+                                    int epilogue, idb200_stream_t stream) {
+    return idb200::gemm_bf16_tn(A, W, bias, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream), 1, aux);
 }
 
 extern "C" int idb200_gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int64_t K, int splits,

@@ -15,6 +15,7 @@ PyTorch owns memory and reshapes (weight transposes / packing, one-hot level row
 Gradients are written into caller-provided fp32 tensors keyed by the reference's parameter names (``grads[name]``)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -30,6 +31,25 @@ BF16, F32 = torch.bfloat16, torch.float32
 def transpose_bf16(src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     M, N = src.shape
     L.call("idb200_transpose_bf16", src.data_ptr(), int(src.dtype == F32), M, N, out.data_ptr(), L.stream(src.device))
+    return out
+
+
+EPI_BF16_SILU_DUAL, EPI_BF16_DSILU = 4, 5
+
+
+def gemm_bf16_aux(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, aux: torch.Tensor, epilogue: int,
+                  fused: bool = False) -> torch.Tensor:
+    """The token GEMM + the MLP's SiLU pass (4: out = u, aux = SiLU(u); 5: out = (A W^T) * SiLU'(aux)).
+    ``fused=True`` (or IDB200_TRAIN_FUSED_SILU=1) folds the SiLU pass into the GEMM epilogue (idb200_gemm_bf16_aux), bit-identical
+    to the two-launch form.  MEASURED AND REJECTED as the default: the tcgen05 GEMM is bound by its epilogue, and the
+    extra MUFU work / second staging pass there costs more than the separate HBM-bound pass saves -- cfg-4 step 17.1 ms with the
+    two launches, 19.2 ms fused (B = 512 per GPU)."""
+    M, K = A.shape
+    if not (fused or os.environ.get("IDB200_TRAIN_FUSED_SILU")):
+        E.gemm_bf16(A, W, bias, out, E.EPI_BF16)
+        return silu_bf16(out, aux) if epilogue == EPI_BF16_SILU_DUAL else silu_bf16(aux, out, g=out)
+    L.call("idb200_gemm_bf16_aux", A.data_ptr(), W.data_ptr(), L.ptr(bias), out.data_ptr(), aux.data_ptr(), M, W.shape[0], K, epilogue,
+           L.stream(A.device))
     return out
 
 
@@ -167,8 +187,8 @@ class EncoderBackprop:
             E.gemm_bf16(sv["o"][i], w["wo16"], w["bo"], h, E.EPI_RESID_F32)
             sv["h_mid"][i].copy_(h)
             E.ln_film(h, w["n2w"], w["n2b"], g2, sv["a2"][i], Lseq)
-            E.gemm_bf16(sv["a2"][i], w["w116"], w["b1"], sv["u"][i], E.EPI_BF16)
-            silu_bf16(sv["u"][i], sv["f"][i])
+            # ff.0 with both outputs from one epilogue: u (pre-activation, for the backward) and f = SiLU(u)
+            gemm_bf16_aux(sv["a2"][i], w["w116"], w["b1"], sv["u"][i], sv["f"][i], EPI_BF16_SILU_DUAL)
             E.gemm_bf16(sv["f"][i], w["w216"], w["b2"], h, E.EPI_RESID_F32)
         self.saved = {"sv": sv, "W": W, "film": film, "film_w": film_w, "cond_vec": cond_vec, "B": B, "L": Lseq, "H": H, "ff": ff,
                       "causal": causal}
@@ -209,8 +229,7 @@ class EncoderBackprop:
             sc.dweight(dh16, sv["f"][i], grads[p + "ff.2.weight"])
             sc.colsum(dh, grads[p + "ff.2.bias"])
             du = ws.get("du16", (M, ff), BF16, dev)
-            E.gemm_bf16(dh16, w["w2t16"], None, du, E.EPI_BF16)                         # dF = dh W2
-            silu_bf16(sv["u"][i], du, g=du)                                            # du = dF * silu'(u)
+            gemm_bf16_aux(dh16, w["w2t16"], None, du, sv["u"][i], EPI_BF16_DSILU)      # du = (dh W2) * silu'(u), one launch
             sc.dweight(du, sv["a2"][i], grads[p + "ff.0.weight"])
             sc.colsum(du, grads[p + "ff.0.bias"])
             E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_F32)                            # da2 = du W1

@@ -227,3 +227,37 @@ def test_generation_graph_recaptures_on_weight_change_and_survives_growth():
     b = graph.run(cond, z_T).clone()
     assert not torch.equal(a, b)
     assert torch.equal(b, generate(kp, il, cond, cfg, z_T=z_T))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(32768, 1536, 384), (1000, 1024, 256), (257, 64, 64), (4096, 192, 128)])
+def test_gemm_silu_epilogues_equal_the_separate_passes(M, N, K):
+    """idb200_gemm_bf16_aux (epilogue 4: u and SiLU(u) from one launch; 5: (A W^T) * SiLU'(u)) == token GEMM + silu_bf16 kernels,
+    bit for bit, and against torch on the bf16-rounded operands."""
+    from interpolated_diffusion_b200.models import _engine as E
+    from interpolated_diffusion_b200.train import backward as bw
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = (torch.randn((M, K), device="cuda", generator=g)).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g)
+    u = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    f = torch.empty_like(u)
+    bw.gemm_bf16_aux(A, W, bias, u, f, bw.EPI_BF16_SILU_DUAL, fused=True)
+    u_ref = torch.empty_like(u)
+    E.gemm_bf16(A, W, bias, u_ref, E.EPI_BF16)
+    f_ref = bw.silu_bf16(u_ref, torch.empty_like(u))
+    assert torch.equal(u, u_ref) and torch.equal(f, f_ref)
+    t = A.float() @ W.float().t() + bias
+    assert (u.float() - t).abs().max().item() < 2e-2 * max(1.0, t.abs().max().item())
+    assert (f.float() - torch.nn.functional.silu(u.float())).abs().max().item() < 2e-2
+    # backward form: dU = (dY W2) * SiLU'(u)
+    du = torch.empty_like(u)
+    bw.gemm_bf16_aux(A, W, None, du, u, bw.EPI_BF16_DSILU, fused=True)
+    dF = torch.empty_like(u)
+    E.gemm_bf16(A, W, None, dF, E.EPI_BF16)
+    du_ref = bw.silu_bf16(u, dF, g=dF)
+    assert torch.equal(du, du_ref)
+    x = u.float()
+    s = torch.sigmoid(x)
+    want = (A.float() @ W.float().t()).bfloat16().float() * (s * (1 + x * (1 - s)))
+    assert (du.float() - want).abs().max().item() < 2e-2 * max(1.0, want.abs().max().item())
