@@ -196,7 +196,12 @@ class EncoderBackprop:
 
     def backward(self, dh: torch.Tensor, dh16: torch.Tensor, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> Optional[torch.Tensor]:
         """dh [M, d] fp32 (in/out: gradient w.r.t. the encoder output -> w.r.t. its input), dh16 its bf16 copy (kept in sync).
-        Writes the parameter gradients into ``grads`` and returns d loss / d cond_vec [B, d_cond] (None without FiLM)."""
+        Writes the parameter gradients into ``grads`` and returns d loss / d cond_vec [B, d_cond] (None without FiLM).
+        = ``backward_layers`` (every per-layer gradient except the FiLM linears: final when it returns) + ``backward_film``."""
+        self.backward_layers(dh, dh16, grads, prefix)
+        return self.backward_film(grads, prefix)
+
+    def backward_layers(self, dh: torch.Tensor, dh16: torch.Tensor, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> None:
         S = self.saved
         sv, W, film = S["sv"], S["W"], S["film"]
         B, Lseq, H, ff, causal = S["B"], S["L"], S["H"], S["ff"], S["causal"]
@@ -244,9 +249,19 @@ class EncoderBackprop:
             sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
             E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_F32)                        # da1 = dqkv Wqkv
             ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, p + "norm1")
+        self._dgb = dgb
 
+    def backward_film(self, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> Optional[torch.Tensor]:
+        """FiLM linears of all LayerNorms (gradients w.r.t. film1 / film2 of every layer, and d cond_vec)."""
+        S = self.saved
+        film, dgb, W = S["film"], self._dgb, S["W"]
+        B = S["B"]
+        nl = len(W)
+        ws, sc = self.sc.ws, self.sc
         if film is None:
             return None
+        d = dgb.shape[2] // 2
+        dev = dgb.device
         # FiLM linears of all LayerNorms at once: gb = cond_vec W_all^T + b_all  (W_all [2 nl * 2d, d_cond])
         cond_vec, film_w = S["cond_vec"], S["film_w"]
         dc = cond_vec.shape[1]
@@ -389,6 +404,12 @@ class _DenoiserBackprop:
         self.sc = _Scratch()
         self.enc = EncoderBackprop(model.transformer, self.sc)
         self.cond = CondEncoderBackprop(model.cond_enc, self.sc) if hasattr(model.cond_enc, "maze") else None
+        self.split_hook = None                  # called once per backward at the split point (see _backward_to_tokens)
+
+    def early_param_names(self) -> List[str]:
+        """Parameters whose gradients are final at the split point of the backward."""
+        return [n for n, _ in self.model.named_parameters()
+                if n.startswith("out.") or (n.startswith("transformer.") and ".film" not in n)]
 
     def param_names(self) -> List[str]:
         return [n for n, _ in self.model.named_parameters()]
@@ -428,7 +449,13 @@ class _DenoiserBackprop:
         dh = torch.empty((M, d), device=dev, dtype=F32)
         dh16 = torch.empty((M, d), device=dev, dtype=BF16)
         L.call("idb200_head_bwd", dy.data_ptr(), f(m.out.weight).data_ptr(), M, d, D, dh.data_ptr(), dh16.data_ptr(), st)
-        dcond = self.enc.backward(dh, dh16, grads, "transformer.")
+        self.enc.backward_layers(dh, dh16, grads, "transformer.")
+        # ---- split point of the data-parallel step: out.* and every transformer gradient except the FiLM linears are final here
+        # (``early_param_names``); what follows (FiLM, token assembly, level / timestep MLP, conditioning encoder) takes ~2.5 ms
+        # at the cfg-4 shapes, enough to hide the all-reduce of the first group (Stage2Trainer.overlap_allreduce)
+        if self.split_hook is not None:
+            self.split_hook()
+        dcond = self.enc.backward_film(grads, "transformer.")
         tok = torch.empty((B, d), device=dev, dtype=F32)
         L.call("idb200_token_sum", dh.data_ptr(), B, Lseq, d, tok.data_ptr(), st)
         # every token carries in_proj.bias and cond_proj(cond_vec): their gradients are the per-trajectory token sums

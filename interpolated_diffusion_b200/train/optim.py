@@ -51,17 +51,26 @@ class FlatAdamW:
     of a reduce-scatter / all-reduce) and runs two launches: global-norm clip coefficient, fused AdamW + EMA."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, ema_decay: Optional[float] = 0.999, max_grad_norm: Optional[float] = 1.0):
+                 weight_decay: float = 1e-2, ema_decay: Optional[float] = 0.999, max_grad_norm: Optional[float] = 1.0,
+                 early: Optional[Iterable[torch.nn.Parameter]] = None):
+        """``early``: parameters to place FIRST in the arena (``[0, n_early)``), e.g. those whose gradients are final before the
+        rest of the backward -- a data-parallel step can all-reduce that slice while the backward's tail still runs.  Only the
+        arena layout changes: ``params`` (and with it ``state_dict()``) keeps the order given."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("optimizer got an empty parameter list")
         dev = L.require_cuda(*[p.data for p in self.params])
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.ema_decay, self.max_grad_norm = ema_decay, max_grad_norm
-        self.offsets, n = [], 0
-        for p in self.params:
-            self.offsets.append(n)
-            n += (p.numel() + 3) // 4 * 4                   # 16-byte aligned slices
+        early_ids = {id(p) for p in early} if early is not None else set()
+        self.offsets, n = [0] * len(self.params), 0
+        for want_early in (True, False):
+            for i, p in enumerate(self.params):
+                if (id(p) in early_ids) == want_early:
+                    self.offsets[i] = n
+                    n += (p.numel() + 3) // 4 * 4           # 16-byte aligned slices
+            if want_early:
+                self.n_early = n
         self.n = n
         self.flat = torch.zeros((n,), device=dev, dtype=torch.float32)
         for p, o in zip(self.params, self.offsets):

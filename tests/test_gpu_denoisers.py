@@ -271,6 +271,32 @@ def test_encoder_fused_many_tiles(Lseq, B, n_layers, ff, causal):
     assert _maxabs(whole, unfused) < 2e-2 * max(1.0, scale / 4), (_maxabs(whole, unfused), scale)
 
 
+def test_encoder_fused_many_tiles_vs_oracle():
+    """Round 2: the many-tile regime of the whole-encoder kernel held to the ORACLE (CPU fp32), not to another CUDA path: rows are
+    sampled from every region of a launch that gives each CTA pair several tiles (first / middle / ragged last tiles), so ring
+    wrap-around, the pair's dead tile and the parameter reloads are all covered by an independent reference."""
+    from interpolated_diffusion_b200.models.transformer import TransformerEncoder
+    for (Lseq, B, causal) in [(8, 16 * 148 * 2 + 37, False), (64, 2 * 148 * 2 + 3, True)]:
+        torch.manual_seed(11)
+        enc = TransformerEncoder(d_model=256, n_layers=4, n_heads=8, d_ff=1024, cond_dim=128, causal=causal)
+        sd = {"transformer.layers." + k[len("layers."):]: v.clone() for k, v in enc.state_dict().items()}
+        gen = torch.Generator().manual_seed(6)
+        x = torch.randn((B, Lseq, 256), generator=gen)
+        cv = torch.randn((B, 128), generator=gen)
+        enc = enc.cuda()
+        assert enc.packed().fused_path(Lseq)
+        got = enc(x.cuda(), cv.cuda()).cpu()
+        per_tile = 128 // Lseq
+        n_tiles = (B + per_tile - 1) // per_tile
+        # trajectories from the first tiles, a wrap-around region in the middle, and the ragged tail
+        pick = sorted(set(list(range(0, 3 * per_tile)) + list(range((n_tiles // 2) * per_tile, (n_tiles // 2 + 2) * per_tile))
+                          + list(range(B - per_tile - 5, B))))
+        pick = [b for b in pick if 0 <= b < B]
+        ref = odn.transformer_encoder(x[pick], cv[pick], sd, 8, causal)
+        scale = ref.abs().max().item()
+        assert _maxabs(got[pick], ref) < 2e-2 * max(1.0, scale / 4), (Lseq, _maxabs(got[pick], ref), scale)
+
+
 @pytest.mark.parametrize("which", ["keypoints", "interp"])
 def test_denoiser_fused_io_matches_separate_kernels(which):
     """idb200_denoiser_fused (token assembly + encoder + out head in one launch, h only in tensor memory) against the

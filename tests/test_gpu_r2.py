@@ -261,3 +261,33 @@ def test_gemm_silu_epilogues_equal_the_separate_passes(M, N, K):
     s = torch.sigmoid(x)
     want = (A.float() @ W.float().t()).bfloat16().float() * (s * (1 + x * (1 - s)))
     assert (du.float() - want).abs().max().item() < 2e-2 * max(1.0, want.abs().max().item())
+
+
+def test_split_graph_step_equals_single_graph_step():
+    """The data-parallel overlap machinery on one GPU: the backward captured as TWO graphs cut where the transformer gradients
+    are final (and the arena laid out so that those gradients are one leading slice) gives the same losses and parameters as the
+    single-graph step, bit for bit."""
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    from interpolated_diffusion_b200.train.stage2_step import Stage2Trainer
+    SMALL = dict(d_model=128, n_layers=2, n_heads=4, d_ff=256, maze_channels=(32, 64))
+    B, T = 256, 64
+    g0 = torch.Generator(device="cuda").manual_seed(1)
+    x0 = torch.rand((B, T, 2), device="cuda", generator=g0)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), device="cuda", generator=g0) < 0.2).float(), "start_goal": torch.rand((B, 4), device="cuda", generator=g0)}
+    out = []
+    for overlap in (True, False):
+        torch.manual_seed(0)
+        model = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=3, **SMALL).cuda()
+        tr = Stage2Trainer(model, cuda_graph=True, overlap_allreduce=overlap)
+        names = [n for n, _ in model.named_parameters()]
+        early = set(tr.bp.early_param_names())
+        assert all(n.startswith("out.") or n.startswith("transformer.") for n in early) and not any(".film" in n for n in early)
+        # arena: early parameters occupy [0, n_early), the others [n_early, n)
+        for n_, off, p in zip(names, tr.opt.offsets, tr.opt.params):
+            assert (off < tr.opt.n_early) == (n_ in early), n_
+        assert 0 < tr.opt.n_early < tr.opt.n
+        gen = torch.Generator(device="cuda").manual_seed(23)
+        losses = [float(tr.step(x0, cond, gen)) for _ in range(3)]
+        out.append((losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()))
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1])
