@@ -102,7 +102,7 @@ struct WarpScratch {
 
 // E = ceil(T / 32) mask words per level; D in {0 (masks only), 2, 4}.
 template <int E, int D>
-__global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_kernel(const NestedParams p) {
+__global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32, (E >= 8 ? 4 : 1)) nested_masks_interp_kernel(const NestedParams p) {
     constexpr int kWarps = K1Cfg<E>::kWarps;
     __shared__ WarpScratch<E, D> scratch[kWarps];
     __shared__ float rtab[256];            // rtab[g] = RN(1 / max(g, 1))
@@ -329,10 +329,12 @@ __global__ void __launch_bounds__(K1Cfg<E>::kWarps * 32) nested_masks_interp_ker
                 __syncwarp();
                 const int klast = base - 1;
                 V yv[E];
+                const bool all_anchors = (base == T);               // K_s = T (e.g. levels 0 / 1 of T = 256, K = 32, S = 4): Interp is the identity
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int t = lane + 32 * e;
                     if (t >= T) continue;
+                    if (all_anchors) { yv[e] = xv[e]; continue; }
                     const int k1 = min(seg[e] + 1, klast);
                     const int2 lr = ws.seg_lr[seg[e]];
                     const V vl = reinterpret_cast<const V*>(ws.cv)[seg[e]];

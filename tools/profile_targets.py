@@ -1,0 +1,85 @@
+"""One warm-up + two launches of ONE hot kernel at its bench shape, for `ncu --set full -k regex:<kernel>`:
+    python tools/profile_targets.py <target>
+targets: encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from interpolated_diffusion_b200 import _lib as L  # noqa: E402
+from interpolated_diffusion_b200.models import _engine as E  # noqa: E402
+
+t = sys.argv[1]
+torch.manual_seed(0)
+dev = "cuda"
+
+
+def run(fn, n=3):
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+
+
+if t in ("encoder_L8", "encoder_L64"):
+    from interpolated_diffusion_b200.models.transformer import TransformerEncoder
+    Lq = 8 if t == "encoder_L8" else 64
+    B = 65536
+    enc = TransformerEncoder(d_model=256, n_layers=8, n_heads=8, d_ff=1024, cond_dim=128).cuda()
+    pk = enc.packed()
+    h = torch.randn((B * Lq, 256), device=dev)
+    film = pk.film_params(torch.randn((B, 128), device=dev), Lq)
+    run(lambda: pk.forward(h, B, Lq, film))
+elif t in ("attn_L8", "attn_L64", "attn_L256"):
+    B, Lq, H, causal = {"attn_L8": (65536, 8, 12, 0), "attn_L64": (16384, 64, 12, 0), "attn_L256": (8192, 256, 8, 1)}[t]
+    d = H * 32
+    qkv = torch.randn((B * Lq, 3 * d), device=dev).bfloat16()
+    out = torch.empty((B * Lq, d), device=dev, dtype=torch.bfloat16)
+    run(lambda: E.attention(qkv, out, B, Lq, H, bool(causal)))
+elif t == "conv_tap":
+    from interpolated_diffusion_b200.models.encoders import MazeEncoder
+    m = MazeEncoder(1, 128, channels=(32, 64, 128, 128)).cuda()
+    x = (torch.rand((8192, 1, 21, 21), device=dev) < 0.2).float()
+    run(lambda: m(x))
+elif t == "ln_film":
+    M, d, Lq = 16384 * 64, 384, 64
+    h = torch.randn((M, d), device=dev)
+    w, b = torch.randn(d, device=dev), torch.randn(d, device=dev)
+    gb = torch.randn((M // Lq, 2 * d), device=dev)
+    out = torch.empty((M, d), device=dev, dtype=torch.bfloat16)
+    run(lambda: E.ln_film(h, w, b, gb, out, Lq))
+elif t in ("embed", "sgemm"):
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    il = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=2).cuda()
+    B = 65536
+    x = torch.rand((B, 64, 2), device=dev)
+    mask = torch.rand((B, 64, 2), device=dev)
+    cond = {"occ": (torch.rand((B, 1, 21, 21), device=dev) < 0.2).float(), "start_goal": torch.rand((B, 4), device=dev)}
+    s = torch.full((B,), 3, device=dev, dtype=torch.long)
+    run(lambda: il(x, s, mask, cond), n=2)
+elif t in ("interp_T256", "interp_T64"):
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    T, K, S, B = (256, 32, 4, 1 << 18) if t == "interp_T256" else (64, 8, 3, 1 << 20)
+    sc = torch.rand((B, T - 2), device=dev)
+    x0 = torch.rand((B, T, 4), device=dev)
+    KL = kf._compute_k_schedule(T, K, S)
+    run(lambda: kf.nested_masks_interp(sc, T, KL, x0=x0, levels_out=(1, S), want_idx=False))
+elif t == "gemm_qkv384":
+    M = 16384 * 64
+    A = torch.randn((M, 384), device=dev).bfloat16()
+    W = torch.randn((1152, 384), device=dev).bfloat16()
+    bias = torch.randn((1152,), device=dev)
+    out = torch.empty((M, 1152), device=dev, dtype=torch.bfloat16)
+    run(lambda: E.gemm_bf16(A, W, bias, out, E.EPI_BF16))
+elif t == "corrupt_adj":
+    from interpolated_diffusion_b200.corruptions import keyframes as kf
+    from interpolated_diffusion_b200.train import train_interp_levels as tr
+    B, T = 1 << 18, 64
+    x0 = torch.rand((B, T, 2), device=dev)
+    masks, _ = kf.build_nested_masks_batch(B, T, 8, 3, device=dev)
+    s_idx = torch.randint(1, 4, (B,), device=dev)
+    kw = dict(corrupt_mode="dist", corrupt_sigma_max=0.08, corrupt_sigma_min=0.012, corrupt_sigma_pow=0.75, corrupt_anchor_frac=0.25)
+    run(lambda: tr.corrupt_adjacent_fused(x0, masks, s_idx, [64, 32, 16, 8], 8, seed=1, offset=1, **kw))
+else:
+    raise SystemExit(f"unknown target {t}")
+print("ok", t)
