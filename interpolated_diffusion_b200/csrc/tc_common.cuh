@@ -49,16 +49,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-// Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a
-// hung GPU.  ~4 s at 2 GHz.  The clock is sampled every 1024 polls only (the poll loop of a waiting warp shares
-// issue slots and the shared-memory pipe with the warps doing the work); kBackoff adds a nanosleep between polls
-// for waiters that are far from the critical path (TMA producers).
-#ifndef IDB200_WAIT_LIMIT_CYCLES
-#define IDB200_WAIT_LIMIT_CYCLES (8000000000LL)
+// Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU.
+//
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or its own time limit expires: a
+// FAILED poll takes ~7900 cycles on B200 whatever the hint says, tools/poll_time.cu), so a waiting warp costs no issue slots and no
+// shared-memory polls -- with 20 warps per CTA, spinning waiters were 40 % of all executed instructions (ncu, round 1).
+//
+// The wait is fully INLINE and bounded by a poll budget (one register, two instructions per failed poll; 2^20 polls ~ 4 s).  An
+// out-of-line slow path (call + clock64 + printf) looks harmless but is not: every wait site then keeps the caller's live state in
+// callee-saved registers or spills it, and the wake-up latency of a parked waiter is on the critical path of each pipeline
+// hand-off -- the whole-encoder kernel (~26 dependent MMA <-> compute hand-offs per tile-layer) measured 796 TF/s with a
+// reporting slow path, 919 TF/s with a leaner one, 947 TF/s inline (same source otherwise).  -DIDB200_WAIT_DIAG=1 builds the
+// reporting variant (prints tag / block / warp of every stuck waiter before trapping) for debugging a deadlock.
+#ifndef IDB200_WAIT_POLL_BUDGET
+#define IDB200_WAIT_POLL_BUDGET (1u << 20)
 #endif
-// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires), so a
-// waiting warp costs no issue slots and no shared-memory polls -- with 20 warps per CTA, spinning waiters were 40 % of all
-// executed instructions (ncu, round 1) and competed with the warps doing the work.
+#ifndef IDB200_WAIT_DIAG
+#define IDB200_WAIT_DIAG 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns) {
     uint32_t ok;
     asm volatile(
@@ -72,26 +80,28 @@ __device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
-static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag, bool backoff) {
-    long long t0 = 0;
-    bool reported = false;
+#if IDB200_WAIT_DIAG
+static __device__ __noinline__ void mbar_wait_diag(uint64_t* bar, uint32_t parity, int tag) {
+    uint32_t polls = 0;
     while (!mbar_try_wait_suspend(bar, parity, 1000000u)) {
-        const long long t = clock64();
-        if (t0 == 0) t0 = t;
-        else if (t - t0 > IDB200_WAIT_LIMIT_CYCLES) {
-            // report once, keep waiting for a grace period (so that EVERY stuck waiter of the pipeline gets to report: the
-            // first trap kills the kernel), then trap
-            if (!reported && (threadIdx.x & 31) == 0)
-                printf("idb200: mbarrier wait timed out (tag %d, block %d, warp %d, parity %u)\n", tag, blockIdx.x, threadIdx.x >> 5, parity);
-            reported = true;
-            if (t - t0 > IDB200_WAIT_LIMIT_CYCLES + IDB200_WAIT_LIMIT_CYCLES / 4) __trap();
-        }
+        if (++polls == IDB200_WAIT_POLL_BUDGET / 8 && (threadIdx.x & 31) == 0)   // report, then keep waiting so that EVERY stuck
+            printf("idb200: mbarrier wait timed out (tag %d, block %d, warp %d, parity %u)\n", tag, blockIdx.x, threadIdx.x >> 5, parity);
+        if (polls == IDB200_WAIT_POLL_BUDGET / 4) __trap();                       // waiter reports before the first trap
     }
 }
+#endif
 template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
     if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(bar, parity, tag, kBackoff);             // out of line: keeps the instruction footprint of every wait small
+#if IDB200_WAIT_DIAG
+    mbar_wait_diag(bar, parity, tag);
+#else
+    uint32_t budget = IDB200_WAIT_POLL_BUDGET;
+#pragma unroll 1
+    while (!mbar_try_wait_suspend(bar, parity, 1000000u)) {
+        if (--budget == 0) __trap();
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -253,21 +263,6 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag = 0) {
-    if (mbar_try_wait_cluster(bar, parity)) return;
-    uint32_t polls = 0;
-    long long t0 = 0;
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if ((++polls & 1023u) == 0) {
-            const long long t = clock64();
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > IDB200_WAIT_LIMIT_CYCLES) {
-                printf("idb200: cluster mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
-                __trap();
-            }
-        }
-    }
 }
 // TMA tile load whose completion bytes are credited to the barrier at this offset in the even CTA of the pair
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
