@@ -43,6 +43,11 @@ constexpr int kThreads = 640;
 constexpr int kCW = 16;                             // compute warps
 constexpr int kCT = kCW * 32;                       // compute threads (named-barrier width)
 constexpr int kSlots = 5;
+#ifndef IDB200_EF_REGS_AUX
+#define IDB200_EF_REGS_AUX 32
+#define IDB200_EF_REGS_COMPUTE 112
+#endif
+constexpr int kRegsAux = IDB200_EF_REGS_AUX, kRegsCompute = IDB200_EF_REGS_COMPUTE;   // 128 * aux + 512 * compute <= 640 * 96
 constexpr int kSlotBytes = kTile;                   // [128 x 64] bf16 (the V tile [64 x 64] uses half a slot)
 constexpr int kMaxFF = 1024;
 constexpr int kOffX = 0;                            // 4 x [128 x 64] bf16
@@ -320,6 +325,11 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
     const uint32_t tmem_h = tmem_base;
     const uint32_t tmem_acc = tmem_base + kColAcc;
 
+    // Register re-balancing (setmaxnreg, per warpgroup of 4 warps): the kernel is compiled for 96 registers per thread (640 threads);
+    // warps 0..3 (producer / MMA issuer / allocator / parameter loader) give theirs back, the 16 compute warps -- whose LayerNorm
+    // holds 64 row values per thread across a barrier and spilled at 96 -- take them.
+    if (warp < 4) {
+    setmaxnreg_dec<kRegsAux>();
     if (warp == 0) {
         // ===================== TMA producer (weights) =====================
         if (lane == 0) {
@@ -416,10 +426,13 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     mprev = t;
                 }
             };
+            unsigned long long mtag[12] = {};                            // kProf: wait cycles per barrier tag (20..31)
             auto wait = [&](uint64_t* bar, uint32_t parity, int tag) {   // barriers the peer CTA also arrives on / credits
                 mstamp(2);
+                const long long tw = kProf ? clock64() : 0;
                 mbar_wait(bar, parity, tag);
                 tc_fence_after();
+                if (kProf) mtag[tag - 20] += static_cast<unsigned long long>(clock64() - tw);
                 mstamp(tag == 21 || tag == 22 || tag == 24 || tag == 25 || tag == 27 || tag == 29 ? 0 : 1);
             };
             auto commit = [&](uint64_t* bar) {
@@ -550,6 +563,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
             if (kProf && issue) {
                 mstamp(2);
                 for (int i = 0; i < 3; ++i) atomicAdd(p.prof + P_MSLOT + i, macc[i] * (kPair ? 2 : 1));   // per tile: the pair's issuer serves two
+                for (int i = 0; i < 12; ++i) atomicAdd(p.prof + P_N + i, mtag[i] * (kPair ? 2 : 1));
             }
         }
     } else if (warp == 3) {
@@ -568,7 +582,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 }
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        setmaxnreg_inc<kRegsCompute>();
         // ===================== compute warps =====================
         const int ew = warp - 4;
         const int q = ew & 3, part = ew >> 2;            // TMEM lane quadrant (warp % 4), column quarter
@@ -1017,12 +1033,12 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     };
     if (prof) {                                                           // dev only: synchronous, prints the phase breakdown
         static unsigned long long* dprof = nullptr;
-        if (!dprof) cudaMalloc(&dprof, ef::P_N * sizeof(unsigned long long));
-        cudaMemsetAsync(dprof, 0, ef::P_N * sizeof(unsigned long long), st);
+        if (!dprof) cudaMalloc(&dprof, (ef::P_N + 12) * sizeof(unsigned long long));
+        cudaMemsetAsync(dprof, 0, (ef::P_N + 12) * sizeof(unsigned long long), st);
         p.prof = dprof;
         cudaError_t e = launch(true);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "encoder_fused_kernel<prof>: %s", cudaGetErrorString(e));
-        unsigned long long hp[ef::P_N];
+        unsigned long long hp[ef::P_N + 12];
         cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         static const char* names[ef::P_N] = {"load", "ln1", "wait_acc", "epi", "att", "wait_o", "o_write", "wait_h1", "ln2", "wait_acc1", "epi1",
@@ -1032,6 +1048,10 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         double tot = 0;
         for (int i = 0; i < ef::P_N; ++i) { fprintf(stderr, " %s=%.0f", names[i], hp[i] / units); if (i < ef::P_LNP1) tot += hp[i] / units; }
         fprintf(stderr, " total=%.0f\n", tot);
+        static const char* tags[12] = {"acc_empty", "slot_qkv", "slot_v", "o_full", "slot_wo", "slot_wo2", "acc1_empty", "slot_ff1", "hb_full", "slot_ff2", "x_full_ln1", "x_full_ln2"};
+        fprintf(stderr, "  mma issuer waits by barrier:");
+        for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%.0f", tags[i], hp[ef::P_N + i] / units);
+        fprintf(stderr, "\n");
         return check_launch("encoder_fused_kernel<prof>");
     }
     cudaError_t e = launch(false);
