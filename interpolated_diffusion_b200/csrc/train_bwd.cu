@@ -5,6 +5,8 @@
 // Reductions are two-level with a fixed order: results are deterministic run to run.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace idb200 {
@@ -116,8 +118,7 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const TIn* __re
 #pragma unroll
     for (int j = 0; j < kV; ++j) acc[j] = 0.0f;
     if (c0 < N) {
-        for (long long r = r0 + ty; r < r1; r += 8) {
-            const uint4 v = *reinterpret_cast<const uint4*>(src + r * N + c0);
+        auto add = [&](const uint4& v) {
             if constexpr (kV == 8) {
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -129,7 +130,18 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const TIn* __re
             } else {
                 acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
             }
+        };
+        // four independent 16-byte loads in flight per thread (the one-load-per-iteration form was latency bound: 2.1 TB/s);
+        // the summation order per thread is unchanged (rows r, r + 8, r + 16, ...), so the result is bit-identical
+        long long r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src + r * N + c0));
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src + (r + 8) * N + c0));
+            const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(src + (r + 16) * N + c0));
+            const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(src + (r + 24) * N + c0));
+            add(v0); add(v1); add(v2); add(v3);
         }
+        for (; r < r1; r += 8) add(__ldg(reinterpret_cast<const uint4*>(src + r * N + c0)));
     }
 #pragma unroll
     for (int j = 0; j < kV; ++j) sh[ty][tx * kV + j] = acc[j];
@@ -151,7 +163,13 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
     const long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (w >= W) return;
     float t = 0.0f;
-    for (int r = 0; r < R; ++r) t += partial[static_cast<long long>(r) * W + w];
+    int r = 0;
+    for (; r + 4 <= R; r += 4) {                           // four loads in flight; same (sequential) summation order
+        const float p0 = partial[static_cast<long long>(r) * W + w], p1 = partial[static_cast<long long>(r + 1) * W + w];
+        const float p2 = partial[static_cast<long long>(r + 2) * W + w], p3 = partial[static_cast<long long>(r + 3) * W + w];
+        t += p0; t += p1; t += p2; t += p3;
+    }
+    for (; r < R; ++r) t += partial[static_cast<long long>(r) * W + w];
     t *= scale;
     out[w] = accumulate ? out[w] + t : t;
 }
@@ -979,6 +997,47 @@ __global__ void __launch_bounds__(256) im2col3x3_rows_kernel(const __nv_bfloat16
     }
 }
 
+// scatter form (the default for C % 8 == 0): a thread owns ONE 16-byte channel group of ONE input pixel: one load, the activation
+// applied once (the gather forms above apply it once per tap: 9x the MUFU work -- the 128-channel layer was MUFU-bound at 2.1 TB/s),
+// then up to nine 16-byte stores: col[(y - dy, x - dx), tap(dy, dx)] = a[(y, x)].  The zero entries of the patch matrix (taps of a
+// border pixel that fall outside the plane) are written by the thread of that pixel; the K padding by the pixel's first thread.
+// Consecutive threads hold consecutive channel groups of a pixel, so every store instruction covers C * 2 contiguous bytes per pixel.
+__global__ void __launch_bounds__(256) im2col3x3_scatter_kernel(const __nv_bfloat16* __restrict__ src, long long B, int Hh, int Ww, int C,
+                                                                int Kpad, int act, __nv_bfloat16* __restrict__ col) {
+    const int P = Hh * Ww;
+    const int cg = C / 8;
+    const long long total = B * P * static_cast<long long>(cg);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long pix = i / cg;                       // b * P + p
+        const int c = static_cast<int>(i - pix * cg) * 8;
+        const int p = static_cast<int>(pix % P);
+        const int y = p / Ww, x = p - y * Ww;
+        uint4 val = __ldg(reinterpret_cast<const uint4*>(src + pix * C + c));
+        if (act) {
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                h2[j] = __floats2bfloat162_rn(silu_fwd(f.x), silu_fwd(f.y));
+            }
+        }
+        __nv_bfloat16* self = col + pix * Kpad + c;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            // this pixel as the (dy, dx) neighbour of output pixel (y - dy, x - dx)
+            if (y - dy >= 0 && y - dy < Hh && x - dx >= 0 && x - dx < Ww)
+                *reinterpret_cast<uint4*>(self - static_cast<long long>(dy * Ww + dx) * Kpad + tap * C) = val;
+            // this pixel's own tap (dy, dx) falls outside the plane: zero
+            if (y + dy < 0 || y + dy >= Hh || x + dx < 0 || x + dx >= Ww) *reinterpret_cast<uint4*>(self + tap * C) = zero;
+        }
+        if (c == 0)
+            for (int k = 9 * C; k < Kpad; k += 8) *reinterpret_cast<uint4*>(col + pix * Kpad + k) = zero;
+    }
+}
+
 // pooled[b, c] = mean_p silu(u[b, p, c])
 __global__ void __launch_bounds__(128) pool_silu_kernel(const __nv_bfloat16* __restrict__ u, int P, int C, float* __restrict__ pooled) {
     const long long b = blockIdx.x;
@@ -1049,7 +1108,9 @@ extern "C" int idb200_transpose_bf16(const void* src, int src_is_f32, int64_t M,
 }
 
 extern "C" int idb200_colsum_scratch_floats(int64_t M, int N) {
-    return tb::slices_for(M, (N + 31) / 32) * N;
+    // the scalar path (32 columns per block) or the vector path (32 x 4 fp32 / 32 x 8 bf16 columns per block), whichever slices more
+    const int a = tb::slices_for(M, (N + 31) / 32), b = tb::slices_for(M, (N + 127) / 128), c = tb::slices_for(M, (N + 255) / 256);
+    return (a > b ? (a > c ? a : c) : (b > c ? b : c)) * N;
 }
 
 extern "C" int idb200_colsum(const void* src, int src_kind, int64_t M, int N, float* scratch, float scale, int accumulate, float* out,
@@ -1064,8 +1125,7 @@ extern "C" int idb200_colsum(const void* src, int src_kind, int64_t M, int N, fl
     int S_used = S;
     if (N % kV == 0 && aligned(src, 16)) {
         const int cbv = (N + 32 * kV - 1) / (32 * kV);
-        S_used = tb::slices_for(M, cbv);
-        if (S_used > S) S_used = S;
+        S_used = tb::slices_for(M, cbv);                    // (idb200_colsum_scratch_floats covers the larger of the two)
         const long long rps = (M + S_used - 1) / S_used;
         const dim3 grid(cbv, S_used);
         if (src_kind == 0)
@@ -1220,6 +1280,12 @@ extern "C" int idb200_im2col3x3(const void* src, int64_t B, int H, int W, int C,
     if (C % 8 == 0 && Kpad % 8 == 0 && aligned(src, 16) && aligned(col, 16)) {
         const long long rows = B * H * W;
         const long long blocks = (rows + tb::kIm2colRows - 1) / tb::kIm2colRows;
+        static const bool gather = getenv("IDB200_IM2COL_GATHER") != nullptr;        // dev A/B
+        if (!gather) {
+            tb::im2col3x3_scatter_kernel<<<grid_for(rows * (C / 8), 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                static_cast<const __nv_bfloat16*>(src), B, H, W, C, Kpad, act, static_cast<__nv_bfloat16*>(col));
+            return check_launch("im2col3x3_scatter_kernel");
+        }
         if (Kpad / 8 >= 64 && blocks < (1ll << 31)) {
             tb::im2col3x3_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                 static_cast<const __nv_bfloat16*>(src), rows, H, W, C, Kpad, act, static_cast<__nv_bfloat16*>(col));
