@@ -145,6 +145,7 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
         tmem_ld_32x32(t0, r[0]);
         tmem_ld_32x32(t0 + 32, r[1]);
         tmem_ld_wait();
+        if (tt) tt[3] = clock64();
         const uint32_t pb4 = smem_u32(spend + c0);
         xs = __uint_as_float(r[0][0]) + lds128(pb4).x;
 #pragma unroll
@@ -232,7 +233,7 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
 }
 
 // kProf (dev, IDB200_PROF=1): compute warp 0 lane 0 accumulates clock64() spans per phase into p.prof[0..15]
-enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
+enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_LNLD, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
 
 // kPair: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  Each CTA still owns one 128-token tile (its
 // rows of h in its own TMEM, its own X / scratch / parameters), but the even CTA issues ONE M=256 MMA for both tiles
@@ -723,7 +724,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 // ================= attention half =================
                 mbar_wait(pa_full, n_p & 1, 50);
                 stamp(P_WPA);
-                long long tt[3] = {0, 0, 0};
+                long long tt[4] = {0, 0, 0, 0};
                 if (skip) { if (film_smem) { mbar_wait(film_full, n_film++ & 1, 58); } }
                 else if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * p.gb_ln_stride : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
@@ -731,7 +732,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) arrive_mma(x_full);
-                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; }
+                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; pacc[P_LNLD] += tt[3] - tprev; }
                 stamp(P_LN1);
                 const float* sbqkv = sPA + 768;
 #pragma unroll 1
@@ -823,7 +824,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) arrive_mma(x_full);
-                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; }
+                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; pacc[P_LNLD] += tt[3] - tprev; }
                 stamp(P_LN2);
                 const float* sb1 = sPM + 768;
 #pragma unroll 1
@@ -1042,7 +1043,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         static const char* names[ef::P_N] = {"load", "ln1", "wait_acc", "epi", "att", "wait_o", "o_write", "wait_h1", "ln2", "wait_acc1", "epi1",
-                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film)", "[mma: wait_slot", "wait_compute", "issue]"};
+                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film", "ln_tmem_ld)", "[mma: wait_slot", "wait_compute", "issue]"};
         const double units = static_cast<double>(tiles) * n_layers;
         fprintf(stderr, "encoder_fused prof (cycles per tile-layer, L=%d, pair=%d):", L, pair ? 1 : 0);
         double tot = 0;
