@@ -427,7 +427,12 @@ __device__ __forceinline__ void ln_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // stage layout: [kLnRows x d] residual rows | [kLnFilmRows x 2d] FiLM rows of the chunk's trajectories
-template <typename TO, int VPL>
+// kExact: d == VPL * 128 (256 / 384 / 512): no per-access column predicates.  The first revision executed 389 warp-instructions
+// per row at d = 384 and was ISSUE bound (68 % issue-active, 3.3 TB/s): a 64-bit m / L per row, a predicate per access, separate
+// subtract / scale / affine / FiLM steps.  Now the chunk's first trajectory and row phase advance incrementally (warp-uniform
+// integers, one division per CTA), the row's trajectory slot is two compares (L >= 8: a 16-row chunk spans at most 3), and the
+// per-element arithmetic is three FFMAs (normalise; affine; FiLM).
+template <typename TO, int VPL, bool kExact>
 __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float* __restrict__ h, const float* __restrict__ lnw,
                                                                   const float* __restrict__ lnb, const float* __restrict__ gb,
                                                                   long long gb_stride, TO* __restrict__ out, long long M, int L, int d) {
@@ -470,25 +475,26 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float
             const long long c = blockIdx.x + static_cast<long long>(s) * gridDim.x;
             if (c < chunks) issue(c, s);
         }
+    // phase of the chunk's first row inside its trajectory, advanced incrementally (rows per step = kLnRows * gridDim.x)
+    const long long step_rows = static_cast<long long>(kLnRows) * gridDim.x;
+    const int step_rem = static_cast<int>(step_rows % L);
+    int rem = static_cast<int>((static_cast<long long>(blockIdx.x) * kLnRows) % L);
     long long it = 0;
     for (long long chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x, ++it) {
         const int stage = static_cast<int>(it % kLnStages);
         ln_mbar_wait(&full[stage], static_cast<uint32_t>((it / kLnStages) & 1));
         const float* tile = ring + stage * stage_floats;
         const float* film = tile + static_cast<size_t>(kLnRows) * d;
-        const long long t0 = (chunk * kLnRows) / L;
-#pragma unroll 1
-        for (int rr = 0; rr < kLnRows / 16; ++rr) {
-            const int r = warp + 16 * rr;
-            const long long m = chunk * kLnRows + r;
-            if (m >= M) break;
+        const int r = warp;
+        const long long m = chunk * kLnRows + r;
+        if (m < M) {
             const float4* row = reinterpret_cast<const float4*>(tile + static_cast<size_t>(r) * d);
             float4 v[VPL];
             float sum = 0.0f;
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
                 const int c4 = lane + 32 * i;
-                if (c4 * 4 < d) {
+                if (kExact || c4 * 4 < d) {
                     v[i] = row[c4];
                     sum += v[i].x + v[i].y + v[i].z + v[i].w;
                 }
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
                 const int c4 = lane + 32 * i;
-                if (c4 * 4 < d) {
+                if (kExact || c4 * 4 < d) {
                     const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
                     sq += a * a + b2 * b2 + c * c + e * e;
                 }
@@ -509,11 +515,18 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float
             for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
             const float rstd = rsqrtf(sq / static_cast<float>(d) + 1e-5f);
             const float* g = nullptr;
-            if (gb) g = film_smem ? film + static_cast<size_t>(m / L - t0) * 2 * d : gb + (m / L) * gb_stride;
+            if (gb) {
+                if (film_smem) {
+                    const int x = rem + r;                       // < L + 16 <= 3 L
+                    g = film + static_cast<size_t>((x >= L) + (x >= 2 * L)) * 2 * d;
+                } else {
+                    g = gb + (m / L) * gb_stride;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
                 const int c4 = lane + 32 * i;
-                if (c4 * 4 < d) {
+                if (kExact || c4 * 4 < d) {
                     const float4 w4 = reinterpret_cast<const float4*>(saff)[c4];
                     const float4 b4 = reinterpret_cast<const float4*>(saff + d)[c4];
                     float o0 = (v[i].x - mean) * rstd * w4.x + b4.x;
@@ -543,6 +556,8 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float
         __syncthreads();                                         // every warp is done reading this stage
         const long long nxt = chunk + static_cast<long long>(kLnStages) * gridDim.x;
         if (threadIdx.x == 0 && nxt < chunks) issue(nxt, stage);
+        rem += step_rem;
+        if (rem >= L) rem -= L;
     }
 }
 
@@ -696,9 +711,15 @@ extern "C" int idb200_ln_film(const float* h, const float* ln_w, const float* ln
         };
 #define IDB_LN_LAUNCH(TO, VPL)                                                                                                     \
     do {                                                                                                                           \
-        int rc_ = run(ln_film_bulk_kernel<TO, VPL>);                                                                               \
-        if (rc_) return rc_;                                                                                                       \
-        ln_film_bulk_kernel<TO, VPL><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d); \
+        if (d == VPL * 128) {                                                                                                      \
+            int rc_ = run(ln_film_bulk_kernel<TO, VPL, true>);                                                                     \
+            if (rc_) return rc_;                                                                                                   \
+            ln_film_bulk_kernel<TO, VPL, true><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d); \
+        } else {                                                                                                                   \
+            int rc_ = run(ln_film_bulk_kernel<TO, VPL, false>);                                                                    \
+            if (rc_) return rc_;                                                                                                   \
+            ln_film_bulk_kernel<TO, VPL, false><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d); \
+        }                                                                                                                          \
     } while (0)
         if (out_is_bf16) {
             if (d <= 256) IDB_LN_LAUNCH(__nv_bfloat16, 2); else if (d <= 384) IDB_LN_LAUNCH(__nv_bfloat16, 3); else IDB_LN_LAUNCH(__nv_bfloat16, 4);
