@@ -291,3 +291,44 @@ def test_split_graph_step_equals_single_graph_step():
         out.append((losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()))
     assert out[0][0] == out[1][0], (out[0][0], out[1][0])
     assert torch.equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("M,Lq,d", [(4096 + 24, 8, 384), (8192, 64, 256), (5000, 5, 384), (4104, 24, 256), (4800, 8, 320), (6144, 256, 512)])
+def test_ln_film_bulk_kernel_vs_torch(M, Lq, d):
+    """The TMA-staged LayerNorm+FiLM kernel (M >= 4096 selects it): ragged last chunk, trajectory lengths that do not divide the
+    16-row chunk (incremental phase), L < 8 (FiLM rows from global memory), widths with and without the exact-width instantiation."""
+    from interpolated_diffusion_b200.models import _engine as E
+    M = (M // Lq) * Lq
+    g = torch.Generator(device="cuda").manual_seed(M + d)
+    h = torch.randn((M, d), generator=g, device="cuda") * 3 + 1
+    w, b = torch.randn((d,), generator=g, device="cuda"), torch.randn((d,), generator=g, device="cuda")
+    gb = torch.randn((M // Lq, 2 * d), generator=g, device="cuda")
+    ref = torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)
+    ref = (ref.view(-1, Lq, d) * (1 + gb[:, None, :d]) + gb[:, None, d:]).view(M, d)
+    assert float((E.ln_film(h, w, b, gb, torch.empty_like(h), Lq) - ref).abs().max()) < 5e-5
+    ob = E.ln_film(h, w, b, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq)
+    assert ((ob.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-5).all()
+    plain = torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)
+    assert float((E.ln_film(h, w, b, None, torch.empty_like(h), Lq) - plain).abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("B,Hh,Ww,C,act", [(3, 21, 21, 128, True), (5, 9, 12, 32, False), (2, 21, 21, 8, True), (4, 7, 5, 64, True)])
+def test_im2col_scatter_form_vs_unfold(B, Hh, Ww, C, act):
+    """Patch matrix of the training conv stack (scatter form: one thread per input channel group): every entry, including the zero
+    taps of border pixels and the K padding, against torch's unfold of the activated input."""
+    from interpolated_diffusion_b200.models import _engine as E
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + C)
+    u = torch.randn((B, Hh * Ww, C), generator=g, device="cuda").to(torch.bfloat16)
+    Kpad = ((9 * C + 63) // 64) * 64
+    col = torch.full((B * Hh * Ww, Kpad), 7.0, device="cuda", dtype=torch.bfloat16)
+    E.im2col3x3(u, B, Hh, Ww, C, act, col)
+    a = u.float()
+    if act:
+        a = torch.nn.functional.silu(a).to(torch.bfloat16).float()
+    x = a.view(B, Hh, Ww, C).permute(0, 3, 1, 2)                                  # NCHW
+    pat = torch.nn.functional.unfold(x, 3, padding=1)                              # [B, C * 9, P], row = c * 9 + tap
+    pat = pat.view(B, C, 9, Hh * Ww).permute(0, 3, 2, 1).reshape(B * Hh * Ww, 9 * C)   # [(b, p), tap * C + c]
+    got = col.float()
+    assert float((got[:, :9 * C] - pat).abs().max()) <= 2.0 ** -7 * float(pat.abs().max())   # silu rounding differences only
+    assert torch.equal(got[:, :9 * C] == 0, pat == 0) or not act
+    assert float(got[:, 9 * C:].abs().max()) == 0.0 if Kpad > 9 * C else True
