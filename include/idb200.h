@@ -400,6 +400,13 @@ int idb200_silu_f32(const float* u, const float* g, int64_t n, int mode, float* 
 int idb200_ln_film_bwd(const float* da, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
                        int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb, int64_t dgb_stride,
                        float* dwb_part, float* stats_scratch, idb200_stream_t stream);
+/* Two-pass form with (i) da in fp32 or bf16 (da_is_bf16) and (ii) with_dh_sum != 0: dwb_part is [B, 3d] = [dw | db | sum_t of the
+ * UPDATED dh]: the last third, summed over the trajectories, is the bias gradient of the GEMM that accumulated into this point of the
+ * residual stream (transformer.py:39-45: out_proj / the previous layer's ff.2), which otherwise costs a full extra read of dh.
+ * stats_scratch fp32 [B*L, 4], 16-byte aligned (required). */
+int idb200_ln_film_bwd2(const void* da, int da_is_bf16, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
+                        int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb, int64_t dgb_stride,
+                        float* dwb_part, int with_dh_sum, float* stats_scratch, idb200_stream_t stream);
 /* stats_scratch: fp32 [B*L, 4] (16-byte aligned) selects the two-pass form (row scalars by a warp per token, then a thread per
  * column over the trajectory's tokens: coalesced, low register count); NULL runs the one-block-per-trajectory kernel. */
 /* Backward of the packed-QKV multi-head attention (head_dim 32, L <= 64): qkv, dqkv bf16 [B*L, 3d]; dO bf16 [B*L, d].

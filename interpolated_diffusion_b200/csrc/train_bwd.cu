@@ -323,46 +323,61 @@ __global__ void __launch_bounds__(256) ln_film_bwd_kernel(const float* __restric
 // lane (128 registers, 25 % occupancy) and ran at 1.7 TB/s.  Pass A: a warp per token reduces the four row scalars
 // (mean, rstd, mean(dxhat), mean(dxhat * xhat)) -> stats[M, 4].  Pass B: a thread per COLUMN walks the L tokens of its
 // trajectory: fully coalesced, no shuffles, ~32 registers; accumulates the column's dgamma / dbeta / dw / db and updates dh.
-template <int kPerLane>
-__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(const float* __restrict__ da, const float* __restrict__ h,
+// 4 consecutive values of the gradient w.r.t. the LayerNorm output
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// Pass A: a warp per token; lane <-> float4 column groups {lane, lane + 32, ...} (16-byte loads; the first revision used scalar
+// 4-byte loads and was request bound).  kV4 = d / 128 float4 groups per lane.
+template <int kV4, typename TDa>
+__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(const TDa* __restrict__ da, const float* __restrict__ h,
                                                            const float* __restrict__ ln_w, const float* __restrict__ gb, long long gb_stride,
                                                            int L, long long M, float4* __restrict__ stats) {
-    constexpr int d = kPerLane * 32;
+    constexpr int d = kV4 * 128;
     const int lane = threadIdx.x & 31;
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    float w[kPerLane];
+    float4 w[kV4];
 #pragma unroll
-    for (int j = 0; j < kPerLane; ++j) w[j] = ln_w[lane + 32 * j];
+    for (int j = 0; j < kV4; ++j) w[j] = load4(ln_w + 4 * (lane + 32 * j));
     for (long long m = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
         const long long b = m / L;
         const long long row = m * d;
-        float x[kPerLane], g[kPerLane];
+        float4 x[kV4], g[kV4];
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kPerLane; ++j) {
-            x[j] = h[row + lane + 32 * j];
-            g[j] = da[row + lane + 32 * j];
-            if (gb) g[j] *= 1.0f + gb[b * gb_stride + lane + 32 * j];
-            g[j] *= w[j];                                   // dxhat
-            s += x[j];
+        for (int j = 0; j < kV4; ++j) {
+            const int c = 4 * (lane + 32 * j);
+            x[j] = load4(h + row + c);
+            g[j] = load4(da + row + c);
+            if (gb) {
+                const float4 ga = load4(gb + b * gb_stride + c);
+                g[j].x *= 1.0f + ga.x; g[j].y *= 1.0f + ga.y; g[j].z *= 1.0f + ga.z; g[j].w *= 1.0f + ga.w;
+            }
+            g[j].x *= w[j].x; g[j].y *= w[j].y; g[j].z *= w[j].z; g[j].w *= w[j].w;      // dxhat
+            s += (x[j].x + x[j].y) + (x[j].z + x[j].w);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float mean = s * (1.0f / d);
         float v = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kPerLane; ++j) {
-            x[j] -= mean;
-            v += x[j] * x[j];
+        for (int j = 0; j < kV4; ++j) {
+            x[j].x -= mean; x[j].y -= mean; x[j].z -= mean; x[j].w -= mean;
+            v = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, fmaf(x[j].w, x[j].w, v))));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         const float rstd = rsqrtf(v * (1.0f / d) + 1e-5f);
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kPerLane; ++j) {
-            s1 += g[j];
-            s2 = fmaf(g[j], x[j] * rstd, s2);
+        for (int j = 0; j < kV4; ++j) {
+            s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+            s2 = fmaf(g[j].x, x[j].x * rstd, fmaf(g[j].y, x[j].y * rstd, fmaf(g[j].z, x[j].z * rstd, fmaf(g[j].w, x[j].w * rstd, s2))));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -373,41 +388,65 @@ __global__ void __launch_bounds__(256) ln_bwd_stats_kernel(const float* __restri
     }
 }
 
-__global__ void __launch_bounds__(128) ln_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ h,
+// Pass B: a thread per group of FOUR columns walks the L tokens of its trajectory (16-byte loads / stores, coalesced across the
+// block = one trajectory's d / 4 column groups), accumulates the columns' dgamma / dbeta / dw / db and updates dh.
+// TDa: fp32 or bf16 gradient w.r.t. the LayerNorm output (the training step keeps it in bf16: the dX GEMM writes half the bytes and
+// both passes read half).  kDhSum: also emit dwb_part[b, 2d + c] = sum_t of the UPDATED dh -- the bias gradient of the GEMM that
+// accumulated into this point of the residual stream (out_proj / previous layer's ff.2), which otherwise costs a full read of dh.
+template <typename TDa, bool kDhSum>
+__global__ void __launch_bounds__(128) ln_bwd_apply_kernel(const TDa* __restrict__ da, const float* __restrict__ h,
                                                            const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                            const float* __restrict__ gb, long long gb_stride, int L, int d,
                                                            const float4* __restrict__ stats, float* __restrict__ dh,
                                                            __nv_bfloat16* __restrict__ dh16, float* __restrict__ dgb, long long dgb_stride,
                                                            float* __restrict__ dwb_part) {
     const long long b = blockIdx.x;                        // trajectories on the wide grid dimension
-    const int c = blockIdx.y * 128 + threadIdx.x;
-    if (c >= d) return;
-    const float w = ln_w[c], bb = ln_b[c];
-    const float g1 = gb ? 1.0f + gb[b * gb_stride + c] : 1.0f;
-    float a_dg = 0.0f, a_db = 0.0f, a_dw = 0.0f, a_dbb = 0.0f;
-#pragma unroll 8
+    const int c = 4 * threadIdx.x;                         // blockDim.x = d / 4
+    const float4 w = load4(ln_w + c), bb = load4(ln_b + c);
+    float4 g1 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (gb) {
+        const float4 ga = load4(gb + b * gb_stride + c);
+        g1 = make_float4(1.0f + ga.x, 1.0f + ga.y, 1.0f + ga.z, 1.0f + ga.w);
+    }
+    float4 a_dg = make_float4(0.f, 0.f, 0.f, 0.f), a_db = a_dg, a_dw = a_dg, a_dbb = a_dg, a_dh = a_dg;
+#pragma unroll 4
     for (int t = 0; t < L; ++t) {
         const long long m = b * L + t;
         const float4 st = stats[m];                         // broadcast load
         const long long o = m * d + c;
-        const float xh = (h[o] - st.x) * st.y;
-        const float g = da[o];
-        const float n = fmaf(xh, w, bb);
-        const float dn = g * g1;
-        a_dg = fmaf(g, n, a_dg);
-        a_db += g;
-        a_dw = fmaf(dn, xh, a_dw);
-        a_dbb += dn;
-        const float v2 = dh[o] + st.y * (dn * w - st.z - xh * st.w);
-        dh[o] = v2;
-        if (dh16) dh16[o] = __float2bfloat16_rn(v2);
+        const float4 hv = load4(h + o), g = load4(da + o), dv = load4(dh + o);
+        float4 v2;
+#define IDB_LN_BWD_LANE(k)                                                    \
+        {                                                                      \
+            const float xh = (hv.k - st.x) * st.y;                             \
+            const float n = fmaf(xh, w.k, bb.k);                               \
+            const float dn = g.k * g1.k;                                       \
+            a_dg.k = fmaf(g.k, n, a_dg.k);                                     \
+            a_db.k += g.k;                                                     \
+            a_dw.k = fmaf(dn, xh, a_dw.k);                                     \
+            a_dbb.k += dn;                                                     \
+            v2.k = dv.k + st.y * (dn * w.k - st.z - xh * st.w);                \
+            if (kDhSum) a_dh.k += v2.k;                                        \
+        }
+        IDB_LN_BWD_LANE(x) IDB_LN_BWD_LANE(y) IDB_LN_BWD_LANE(z) IDB_LN_BWD_LANE(w)
+#undef IDB_LN_BWD_LANE
+        *reinterpret_cast<float4*>(dh + o) = v2;
+        if (dh16) {
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v2.x, v2.y), p1 = __floats2bfloat162_rn(v2.z, v2.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned*>(&p0);
+            pk.y = *reinterpret_cast<const unsigned*>(&p1);
+            *reinterpret_cast<uint2*>(dh16 + o) = pk;
+        }
     }
     if (dgb) {
-        dgb[b * dgb_stride + c] = a_dg;
-        dgb[b * dgb_stride + d + c] = a_db;
+        *reinterpret_cast<float4*>(dgb + b * dgb_stride + c) = a_dg;
+        *reinterpret_cast<float4*>(dgb + b * dgb_stride + d + c) = a_db;
     }
-    dwb_part[b * 2 * d + c] = a_dw;
-    dwb_part[b * 2 * d + d + c] = a_dbb;
+    constexpr int kW = kDhSum ? 3 : 2;
+    *reinterpret_cast<float4*>(dwb_part + b * kW * d + c) = a_dw;
+    *reinterpret_cast<float4*>(dwb_part + b * kW * d + d + c) = a_dbb;
+    if (kDhSum) *reinterpret_cast<float4*>(dwb_part + b * kW * d + 2 * d + c) = a_dh;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1076,6 +1115,29 @@ int launch_attn_bwd(const void* qkv, const void* dO, void* dqkv, long long B, in
     return check_launch("attention_bwd_kernel");
 }
 
+template <typename TDa, bool kDhSum>
+int ln_bwd_two_pass(const TDa* da, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, long long gb_stride,
+                    long long B, int L, int d, float* dh, __nv_bfloat16* d16, float* dgb, long long dgb_stride, float* dwb_part,
+                    float4* stats, cudaStream_t st) {
+    IDB_REQUIRE(aligned(da, 16) && aligned(h, 16) && aligned(dh, 16) && aligned(ln_w, 16) && aligned(ln_b, 16) && aligned(dwb_part, 16) &&
+                    (!d16 || aligned(d16, 8)) && (!gamma_beta || (aligned(gamma_beta, 16) && gb_stride % 4 == 0)) &&
+                    (!dgb || (aligned(dgb, 16) && dgb_stride % 4 == 0)),
+                IDB200_EALIGN, "LayerNorm backward (two-pass form) needs 16-byte aligned rows");
+    const long long M = B * L;
+    const int g1 = grid_for(M * 32, 256, 8);
+    switch (d / 128) {
+        case 1: ln_bwd_stats_kernel<1, TDa><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+        case 2: ln_bwd_stats_kernel<2, TDa><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+        case 3: ln_bwd_stats_kernel<3, TDa><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+        default: ln_bwd_stats_kernel<4, TDa><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
+    }
+    int rc = check_launch("ln_bwd_stats_kernel");
+    if (rc) return rc;
+    ln_bwd_apply_kernel<TDa, kDhSum><<<static_cast<unsigned>(B), d / 4, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, d, stats, dh, d16,
+                                                                                 dgb, dgb_stride, dwb_part);
+    return check_launch("ln_bwd_apply_kernel");
+}
+
 inline int slices_for(long long M, int col_blocks) {
     long long s = (148 * 8 + col_blocks - 1) / col_blocks;
     const long long max_s = (M + 63) / 64;
@@ -1189,20 +1251,8 @@ extern "C" int idb200_ln_film_bwd(const float* da, const float* h, const float* 
     const unsigned grid = static_cast<unsigned>(B);
     if (stats_scratch) {                                    // two-pass form: stats_scratch fp32 [B*L, 4], 16-byte aligned
         IDB_REQUIRE(aligned(stats_scratch, 16), IDB200_EALIGN, "stats_scratch must be 16-byte aligned");
-        const long long M = B * L;
-        float4* stats = reinterpret_cast<float4*>(stats_scratch);
-        const int g1 = grid_for(M * 32, 256, 8);
-        switch (d / 32) {
-            case 4: tb::ln_bwd_stats_kernel<4><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
-            case 8: tb::ln_bwd_stats_kernel<8><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
-            case 12: tb::ln_bwd_stats_kernel<12><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
-            default: tb::ln_bwd_stats_kernel<16><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;
-        }
-        int rc = check_launch("ln_bwd_stats_kernel");
-        if (rc) return rc;
-        tb::ln_bwd_apply_kernel<<<dim3(grid, (d + 127) / 128), 128, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, d, stats, dh, d16, dgb,
-                                                                            dgb_stride, dwb_part);
-        return check_launch("ln_bwd_apply_kernel");
+        return tb::ln_bwd_two_pass<float, false>(da, h, ln_w, ln_b, gamma_beta, gb_stride, B, L, d, dh, d16, dgb, dgb_stride, dwb_part,
+                                                 reinterpret_cast<float4*>(stats_scratch), st);
     }
     switch (d / 32) {
         case 4: tb::ln_film_bwd_kernel<4><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;
@@ -1211,6 +1261,27 @@ extern "C" int idb200_ln_film_bwd(const float* da, const float* h, const float* 
         default: tb::ln_film_bwd_kernel<16><<<grid, 256, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part); break;
     }
     return check_launch("ln_film_bwd_kernel");
+}
+
+extern "C" int idb200_ln_film_bwd2(const void* da, int da_is_bf16, const float* h, const float* ln_w, const float* ln_b,
+                                   const float* gamma_beta, int64_t gb_stride, int64_t B, int L, int d, float* dh, void* dh_bf16, float* dgb,
+                                   int64_t dgb_stride, float* dwb_part, int with_dh_sum, float* stats_scratch, idb200_stream_t stream) {
+    IDB_REQUIRE(da && h && ln_w && ln_b && dh && dwb_part && stats_scratch, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE((gamma_beta == nullptr) == (dgb == nullptr), IDB200_EINVAL, "gamma_beta and dgb must be given together");
+    IDB_REQUIRE(B > 0 && L > 0, IDB200_EINVAL, "bad shape");
+    IDB_REQUIRE(d == 256 || d == 384 || d == 128 || d == 512, IDB200_EUNSUPPORTED, "d_model must be 128, 256, 384 or 512 (got %d)", d);
+    IDB_REQUIRE(aligned(stats_scratch, 16), IDB200_EALIGN, "stats_scratch must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* d16 = static_cast<__nv_bfloat16*>(dh_bf16);
+    float4* stats = reinterpret_cast<float4*>(stats_scratch);
+    if (da_is_bf16) {
+        const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(da);
+        return with_dh_sum ? tb::ln_bwd_two_pass<__nv_bfloat16, true>(g, h, ln_w, ln_b, gamma_beta, gb_stride, B, L, d, dh, d16, dgb, dgb_stride, dwb_part, stats, st)
+                           : tb::ln_bwd_two_pass<__nv_bfloat16, false>(g, h, ln_w, ln_b, gamma_beta, gb_stride, B, L, d, dh, d16, dgb, dgb_stride, dwb_part, stats, st);
+    }
+    const float* g = static_cast<const float*>(da);
+    return with_dh_sum ? tb::ln_bwd_two_pass<float, true>(g, h, ln_w, ln_b, gamma_beta, gb_stride, B, L, d, dh, d16, dgb, dgb_stride, dwb_part, stats, st)
+                       : tb::ln_bwd_two_pass<float, false>(g, h, ln_w, ln_b, gamma_beta, gb_stride, B, L, d, dh, d16, dgb, dgb_stride, dwb_part, stats, st);
 }
 
 extern "C" int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, int force_simt,

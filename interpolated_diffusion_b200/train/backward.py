@@ -209,46 +209,50 @@ class EncoderBackprop:
         dev = dh.device
         nl = len(W)
         sc, ws = self.sc, self.sc.ws
-        da = ws.get("da", (M, d), F32, dev)
+        da = ws.get("da16", (M, d), BF16, dev)            # gradient w.r.t. the LayerNorm outputs, bf16 (half the bytes of 3 passes)
         do16 = ws.get("do16", (M, d), BF16, dev)
-        dwb = ws.get("dwb", (B, 2 * d), F32, dev)
-        dwb_sum = ws.get("dwb_sum", (2 * d,), F32, dev)
+        dwb = ws.get("dwb", (B, 3 * d), F32, dev)
+        dwb_sum = ws.get("dwb_sum", (3 * d,), F32, dev)
         stats = ws.get("ln_stats", (M, 4), F32, dev)
         dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
         st = L.stream(dev)
 
-        def ln_bwd(h_saved, nw, nb, j, name):
+        def ln_bwd(h_saved, nw, nb, j, name, bias_below):
+            """LayerNorm + FiLM backward; also yields the column sums of the UPDATED dh = the bias gradient of the GEMM that
+            accumulated into the residual stream just below this LayerNorm (``bias_below``: a grads key or None)."""
             gb = film[:, j] if film is not None else None
             dg = dgb[:, j] if film is not None else None
-            L.call("idb200_ln_film_bwd", da.data_ptr(), h_saved.data_ptr(), nw.data_ptr(), nb.data_ptr(), L.ptr(gb),
+            L.call("idb200_ln_film_bwd2", da.data_ptr(), 1, h_saved.data_ptr(), nw.data_ptr(), nb.data_ptr(), L.ptr(gb),
                    0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), dh16.data_ptr(), L.ptr(dg),
-                   0 if dg is None else dg.stride(0), dwb.data_ptr(), stats.data_ptr(), st)
+                   0 if dg is None else dg.stride(0), dwb.data_ptr(), 1, stats.data_ptr(), st)
             sc.colsum(dwb, dwb_sum)
             grads[name + ".weight"].copy_(dwb_sum[:d])
-            grads[name + ".bias"].copy_(dwb_sum[d:])
+            grads[name + ".bias"].copy_(dwb_sum[d:2 * d])
+            if bias_below is not None:
+                grads[bias_below].copy_(dwb_sum[2 * d:])
 
         for i in range(nl - 1, -1, -1):
             w = W[i]
             p = f"{prefix}layers.{i}."
             # ---- MLP: h_out = h_mid + ff.2(silu(ff.0(a2)))
             sc.dweight(dh16, sv["f"][i], grads[p + "ff.2.weight"])
-            sc.colsum(dh, grads[p + "ff.2.bias"])
+            if i == nl - 1:
+                sc.colsum(dh, grads[p + "ff.2.bias"])           # (the other layers' come out of the LayerNorm backward above them)
             du = ws.get("du16", (M, ff), BF16, dev)
             gemm_bf16_aux(dh16, w["w2t16"], None, du, sv["u"][i], EPI_BF16_DSILU)      # du = (dh W2) * silu'(u), one launch
             sc.dweight(du, sv["a2"][i], grads[p + "ff.0.weight"])
             sc.colsum(du, grads[p + "ff.0.bias"])
-            E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_F32)                            # da2 = du W1
-            ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1, p + "norm2")
+            E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_BF16)                           # da2 = du W1
+            ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1, p + "norm2", p + "attn.out_proj.bias")
             # ---- attention: h_mid = h_in + out_proj(MHA(a1))
             sc.dweight(dh16, sv["o"][i], grads[p + "attn.out_proj.weight"])
-            sc.colsum(dh, grads[p + "attn.out_proj.bias"])
             E.gemm_bf16(dh16, w["wot16"], None, do16, E.EPI_BF16)                       # dO = dh Wo
             dqkv = ws.get("dqkv16", (M, 3 * d), BF16, dev)
             L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), 0, st)
             sc.dweight(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
             sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
-            E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_F32)                        # da1 = dqkv Wqkv
-            ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, p + "norm1")
+            E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_BF16)                       # da1 = dqkv Wqkv
+            ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, p + "norm1", f"{prefix}layers.{i - 1}.ff.2.bias" if i > 0 else None)
         self._dgb = dgb
 
     def backward_film(self, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> Optional[torch.Tensor]:

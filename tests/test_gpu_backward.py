@@ -138,6 +138,44 @@ def test_ln_film_backward_matches_autograd(dev, d, Lseq, with_film, two_pass):
         assert _rel(dgb, gb.grad) < 2e-5
 
 
+@pytest.mark.parametrize("da_bf16", [False, True])
+@pytest.mark.parametrize("d,Lseq,with_film", [(256, 64, True), (384, 64, True), (128, 8, False)])
+def test_ln_film_backward2_bf16_da_and_dh_column_sums(dev, d, Lseq, with_film, da_bf16):
+    """idb200_ln_film_bwd2: gradient w.r.t. the LayerNorm output given in bf16, and the third block of dwb_part = per-trajectory sums
+    of the UPDATED dh (the bias gradient of the GEMM below the LayerNorm) against autograd."""
+    from interpolated_diffusion_b200 import _lib as L
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B = 7
+    h = (torch.randn((B, Lseq, d), generator=g) * 1.5 + 0.3).requires_grad_()
+    w = (1.0 + 0.2 * torch.randn((d,), generator=g)).requires_grad_()
+    b = (0.1 * torch.randn((d,), generator=g)).requires_grad_()
+    gb = (0.3 * torch.randn((B, 2 * d), generator=g)).requires_grad_()
+    da = torch.randn((B, Lseq, d), generator=g)
+    if da_bf16:
+        da = da.to(torch.bfloat16).float()                  # the reference sees the same (rounded) upstream gradient
+    dh0 = torch.randn((B, Lseq, d), generator=g)
+    a = torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)
+    if with_film:
+        a = a * (1.0 + gb[:, None, :d]) + gb[:, None, d:]
+    a.backward(da)
+    dh = dh0.clone().to(dev).view(B * Lseq, d)
+    dh16 = torch.empty((B * Lseq, d), device=dev, dtype=torch.bfloat16)
+    dgb = torch.zeros((B, 2 * d), device=dev) if with_film else None
+    dwb = torch.empty((B, 3 * d), device=dev)
+    gbd = gb.detach().to(dev) if with_film else None
+    da_d = da.to(dev).to(torch.bfloat16) if da_bf16 else da.to(dev)
+    h_d, w_d, b_d = h.detach().to(dev), w.detach().to(dev), b.detach().to(dev)
+    stats = torch.empty((B * Lseq, 4), device=dev)
+    L.call("idb200_ln_film_bwd2", da_d.data_ptr(), int(da_bf16), h_d.data_ptr(), w_d.data_ptr(), b_d.data_ptr(), L.ptr(gbd), 2 * d if with_film else 0,
+           B, Lseq, d, dh.data_ptr(), dh16.data_ptr(), L.ptr(dgb), 2 * d if with_film else 0, dwb.data_ptr(), 1, stats.data_ptr(), L.stream(dev))
+    want = dh0 + h.grad
+    assert _rel(dh.view(B, Lseq, d), want) < 2e-5
+    assert _rel(dwb[:, :d].sum(0), w.grad) < 2e-5 and _rel(dwb[:, d:2 * d].sum(0), b.grad) < 2e-5
+    assert _rel(dwb[:, 2 * d:], want.sum(1)) < 2e-5
+    if with_film:
+        assert _rel(dgb, gb.grad) < 2e-5
+
+
 @pytest.mark.parametrize("Lseq,H,causal,simt", [(64, 4, False, 0), (64, 12, True, 0), (64, 4, False, 1), (64, 12, True, 1), (48, 3, True, 0),
                                                  (40, 2, False, 0), (8, 8, False, 0), (32, 4, True, 0), (16, 2, False, 0), (5, 2, False, 0)])
 def test_attention_backward_matches_autograd(dev, Lseq, H, causal, simt):
