@@ -24,5 +24,8 @@ for t in "$@"; do
     interp_T64)  prof interp_T64 nested_masks 2 ;;
     gemm_qkv384) prof gemm_qkv384 gemm_bf16_tn 2 ;;
     corrupt_adj) prof corrupt_adj corrupt_adjacent 2 ;;
+    ln_bwd)      prof ln_bwd ln_bwd_apply 2 ;;
+    im2col)      prof im2col im2col3x3_scatter 2 ;;
+    colsum)      prof colsum colsum_partial_vec 2 ;;
   esac
 done

@@ -1,6 +1,6 @@
 """One warm-up + two launches of ONE hot kernel at its bench shape, for `ncu --set full -k regex:<kernel>`:
     python tools/profile_targets.py <target>
-targets: encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
+targets: encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
 import os
 import sys
 
@@ -80,6 +80,31 @@ elif t == "corrupt_adj":
     s_idx = torch.randint(1, 4, (B,), device=dev)
     kw = dict(corrupt_mode="dist", corrupt_sigma_max=0.08, corrupt_sigma_min=0.012, corrupt_sigma_pow=0.75, corrupt_anchor_frac=0.25)
     run(lambda: tr.corrupt_adjacent_fused(x0, masks, s_idx, [64, 32, 16, 8], 8, seed=1, offset=1, **kw))
+elif t == "ln_bwd":
+    B, Lq, d = 4096, 64, 384
+    M = B * Lq
+    h = torch.randn((M, d), device=dev)
+    da = torch.randn((M, d), device=dev).bfloat16()
+    dh = torch.randn((M, d), device=dev)
+    dh16 = torch.empty((M, d), device=dev, dtype=torch.bfloat16)
+    w, b = torch.randn(d, device=dev), torch.randn(d, device=dev)
+    gb = torch.randn((B, 2 * d), device=dev)
+    dgb = torch.empty((B, 2 * d), device=dev)
+    dwb = torch.empty((B, 3 * d), device=dev)
+    stats = torch.empty((M, 4), device=dev)
+    run(lambda: L.call("idb200_ln_film_bwd2", da.data_ptr(), 1, h.data_ptr(), w.data_ptr(), b.data_ptr(), gb.data_ptr(), 2 * d, B, Lq, d,
+                       dh.data_ptr(), dh16.data_ptr(), dgb.data_ptr(), 2 * d, dwb.data_ptr(), 1, stats.data_ptr(), L.stream(torch.device(dev))))
+elif t == "im2col":
+    B, C = 4096, 128
+    u = torch.randn((B, 441, C), device=dev).bfloat16()
+    col = torch.empty((B * 441, 9 * C), device=dev, dtype=torch.bfloat16)
+    run(lambda: E.im2col3x3(u, B, 21, 21, C, True, col))
+elif t == "colsum":
+    from interpolated_diffusion_b200.train import backward as BW
+    x = torch.randn((262144, 1536), device=dev).bfloat16()
+    out = torch.empty((1536,), device=dev)
+    sc = BW._Scratch()
+    run(lambda: sc.colsum(x, out))
 else:
     raise SystemExit(f"unknown target {t}")
 print("ok", t)
