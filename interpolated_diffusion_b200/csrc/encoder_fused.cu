@@ -128,20 +128,16 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     return v;
 }
 template <bool kFilmSmem>
-__device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const float* sb, const float* spend, const float* film, int mode,
+__device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const float* sb, const float* spend, const float* film, int mode,
                                      uint64_t* film_full, uint32_t film_parity, float2* stat, uint8_t* X, int row, int part, long long* tt) {
-    __builtin_assume(__isShared(sw));
-    __builtin_assume(__isShared(sb));
-    __builtin_assume(__isShared(spend));
-    __builtin_assume(__isShared(stat));
-    __builtin_assume(__isShared(X));
-    if (kFilmSmem && film != nullptr) __builtin_assume(__isShared(film));
+    // (inlined: the pointers derive from the kernel's shared-memory base, whose address space the caller has already asserted)
     const int c0 = part * 64;
     const uint32_t t0 = tmem_row + c0;
     // ---- pass 1: x = h + pending bias (kept in registers for pass 2, written back to TMEM); statistics ----
     float xs, s1 = 0.0f, s2 = 0.0f;
     uint32_t r[2][32];
     {
+        if (tt) tt[4] = clock64();
         tmem_ld_32x32(t0, r[0]);
         tmem_ld_32x32(t0 + 32, r[1]);
         tmem_ld_wait();
@@ -233,7 +229,7 @@ __device__ __noinline__ void ln_tmem(uint32_t tmem_row, const float* sw, const f
 }
 
 // kProf (dev, IDB200_PROF=1): compute warp 0 lane 0 accumulates clock64() spans per phase into p.prof[0..15]
-enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_LNLD, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
+enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_LNLD, P_LNENTRY, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
 
 // kPair: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  Each CTA still owns one 128-token tile (its
 // rows of h in its own TMEM, its own X / scratch / parameters), but the even CTA issues ONE M=256 MMA for both tiles
@@ -596,8 +592,12 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         uint8_t* sqb = smem + kOffQkv;
         uint8_t* so = smem + kOffO;
         const int L = p.L;
-        uint32_t n_acc = 0, n_o = 0, n_h = 0, n_p = 0, n_film = 0, n_sf = 0;
-        uint32_t use1[2] = {0, 0}, useh[2] = {0, 0};
+        // Barrier phases are DERIVED, not counted: every per-layer barrier completes an even number of phases per layer (4 head groups,
+        // 2 LayerNorms, 2 h_ready commits), so its parity depends on the position inside the layer only; the chunk buffers' use
+        // counts follow from the layer counter n_p.  (Ten live counters per thread spilled around the LayerNorms: local memory goes
+        // to L2 here -- 226 KB of the SM's 256 KB are shared memory.)
+        uint32_t n_p = 0;
+        const uint32_t uses0 = static_cast<uint32_t>((nc + 1) >> 1), uses1 = static_cast<uint32_t>(nc >> 1);   // chunk uses of buffer 0 / 1 per layer
         unsigned long long pacc[P_N] = {};
         long long tprev = kProf ? clock64() : 0;
         auto stamp = [&](int what) {
@@ -724,22 +724,22 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 // ================= attention half =================
                 mbar_wait(pa_full, n_p & 1, 50);
                 stamp(P_WPA);
-                long long tt[4] = {0, 0, 0, 0};
-                if (skip) { if (film_smem) { mbar_wait(film_full, n_film++ & 1, 58); } }
-                else if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                long long tt[5] = {0, 0, 0, 0, 0};
+                if (skip) { if (film_smem) { mbar_wait(film_full, 0u, 58); } }
+                else if (film_smem) ln_tmem<true>(tmem_row, sPA, sPA + 256, sPA + 512, sfilm, p.film_mode, film_full, 0u, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 else ln_tmem<false>(tmem_row, sPA, sPA + 256, sPA + 512, gbtraj ? gbtraj + (2 * l) * p.gb_ln_stride : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) arrive_mma(x_full);
-                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; pacc[P_LNLD] += tt[3] - tprev; }
+                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; pacc[P_LNLD] += tt[3] - tprev; pacc[P_LNENTRY] += tt[4] - tprev; }
                 stamp(P_LN1);
                 const float* sbqkv = sPA + 768;
 #pragma unroll 1
                 for (int g = 0; g < 4; ++g) {
-                    mbar_wait(acc_full, n_acc & 1, 51);
+                    mbar_wait(acc_full, static_cast<uint32_t>(g & 1), 51);
                     tc_fence_after();
-                    if (g > 0) mbar_wait(stg_free, (n_sf - 1) & 1, 60);  // every warp is done reading the previous q|k|v
+                    if (g > 0) mbar_wait(stg_free, static_cast<uint32_t>((g + 1) & 1), 60);  // every warp is done reading the previous q|k|v
                     stamp(P_WACC);
                     // ---- EPI_g: acc + bias -> bf16 q|k|v rows (this thread: its row, 48 of the 192 columns) ----
                     if (!skip) {
@@ -765,7 +765,6 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) arrive_mma(acc_empty);
-                    ++n_acc;
                     named_barrier_sync(2, kCT);                          // q|k|v of the whole tile are in shared memory
                     stamp(P_EPI);
                     // ---- ATT_g: this warp's (16-row block, head) ----
@@ -785,9 +784,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(stg_free);                // this warp is done reading the staged q|k|v
-                    ++n_sf;
                     stamp(P_ATT);
-                    mbar_wait(o_empty, (n_o & 1) ^ 1, 52);               // OUT_{g-1} finished reading O
+                    mbar_wait(o_empty, static_cast<uint32_t>((g & 1) ^ 1), 52);   // OUT_{g-1} finished reading O
                     stamp(P_WO);
                     if (!skip) {
                         const int gq = lane >> 2, tq = lane & 3;
@@ -803,35 +801,34 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) arrive_mma(o_full);
-                    ++n_o;
                     stamp(P_OWR);
                 }
                 if (film_smem && ew == 0 && lane == 0) {                 // once every warp is done with the staged q|k|v: stage LN2's
-                    mbar_wait(stg_free, (n_sf - 1) & 1, 61);             // FiLM rows over them (after o_full: OUT_3 is not held up)
+                    mbar_wait(stg_free, 1u, 61);                         // FiLM rows over them (after o_full: OUT_3 is not held up)
                     stage_film(tile, l, 1);
                 }
                 if (lane == 0) mbar_arrive(pa_empty);                    // (after the __syncwarp above: the warp is done with PA)
                 // ================= MLP half =================
                 mbar_wait(pm_full, n_p & 1, 53);
-                mbar_wait(h_ready, n_h & 1, 54);                         // OUT_3 has landed in h
-                ++n_h;
+                mbar_wait(h_ready, 0u, 54);                              // OUT_3 has landed in h
                 tc_fence_after();
                 stamp(P_WH1);
-                if (skip) { if (film_smem) { mbar_wait(film_full, n_film++ & 1, 58); } }
-                else if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, p.film_mode, film_full, n_film++ & 1, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
+                if (skip) { if (film_smem) { mbar_wait(film_full, 1u, 58); } }
+                else if (film_smem) ln_tmem<true>(tmem_row, sPM, sPM + 256, sPM + 512, sfilm, p.film_mode, film_full, 1u, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 else ln_tmem<false>(tmem_row, sPM, sPM + 256, sPM + 512, gbtraj ? gbtraj + (2 * l + 1) * p.gb_ln_stride : nullptr, p.film_mode, nullptr, 0, stat, smem + kOffX, row, part, kProf ? tt : nullptr);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) arrive_mma(x_full);
-                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; pacc[P_LNLD] += tt[3] - tprev; }
+                if (kProf) { pacc[P_LNP1] += tt[0] - tprev; pacc[P_LNBAR] += tt[1] - tt[0]; pacc[P_LNFILM] += tt[2] - tt[1]; pacc[P_LNLD] += tt[3] - tprev; pacc[P_LNENTRY] += tt[4] - tprev; }
                 stamp(P_LN2);
                 const float* sb1 = sPM + 768;
 #pragma unroll 1
                 for (int c = 0; c < nc; ++c) {
                     const int b = c & 1;
-                    mbar_wait(&acc1_full[b], use1[b] & 1, 55);
-                    mbar_wait(&hb_empty[b], (useh[b] & 1) ^ 1, 56);     // FF2 of the previous use finished reading H[b]
+                    const uint32_t ub = (n_p * (b ? uses1 : uses0) + static_cast<uint32_t>(c >> 1)) & 1u;   // uses of buffer b so far
+                    mbar_wait(&acc1_full[b], ub, 55);
+                    mbar_wait(&hb_empty[b], ub ^ 1u, 56);               // FF2 of the previous use finished reading H[b]
                     tc_fence_after();
                     stamp(P_WACC1);
                     if (!skip) {
@@ -861,8 +858,6 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     __syncwarp();
                     if (skip && lane == 0) arrive_mma(&acc1_empty[b]);
                     if (lane == 0) arrive_mma(&hb_full[b]);
-                    ++use1[b];
-                    ++useh[b];
                     stamp(P_EPI1);
                 }
                 if (lane == 0) mbar_arrive(pm_empty);
@@ -870,12 +865,11 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     // H[0] is dead once FF2 of the last even chunk has completed: stage the next LayerNorm's FiLM rows there
                     const long long nxt = (l + 1 < NL) ? trip : trip + trip_stride;
                     if (nxt < trips) {
-                        mbar_wait(&hb_empty[0], (useh[0] & 1) ^ 1, 59);
+                        mbar_wait(&hb_empty[0], (((n_p + 1u) * uses0) & 1u) ^ 1u, 59);
                         stage_film(tile_of(nxt), (l + 1 < NL) ? l + 1 : 0, 0);
                     }
                 }
-                mbar_wait(h_ready, n_h & 1, 57);                         // the last FF2 has landed in h
-                ++n_h;
+                mbar_wait(h_ready, 1u, 57);                              // the last FF2 has landed in h
                 tc_fence_after();
                 stamp(P_WH2);
             }
@@ -1043,7 +1037,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         static const char* names[ef::P_N] = {"load", "ln1", "wait_acc", "epi", "att", "wait_o", "o_write", "wait_h1", "ln2", "wait_acc1", "epi1",
-                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film", "ln_tmem_ld)", "[mma: wait_slot", "wait_compute", "issue]"};
+                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film", "ln_tmem_ld", "ln_entry)", "[mma: wait_slot", "wait_compute", "issue]"};
         const double units = static_cast<double>(tiles) * n_layers;
         fprintf(stderr, "encoder_fused prof (cycles per tile-layer, L=%d, pair=%d):", L, pair ? 1 : 0);
         double tot = 0;
