@@ -272,15 +272,15 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nc = p.ff / 128;
     const int NL = p.n_layers;
-    const long long tiles = (p.M + 127) / 128;
+    const int tiles = static_cast<int>((p.M + 127) / 128);          // (the host checks M < 2^38: 32-bit tile / trip counters, fewer live registers)
     const int pm_floats = 768 + p.ff;
     const int layer_floats = kPAFloats + pm_floats;
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;          // 0 = the CTA that issues the pair's MMAs
     constexpr int kArr = kPair ? 2 * kCW : kCW;                      // arrivals on the compute -> MMA barriers
     // persistent loop: trip t handles tile t (single) or tiles 2t, 2t+1 (pair; a trailing odd tile leaves the peer a dead tile)
-    const long long trips = kPair ? (tiles + 1) / 2 : tiles;
-    const long long trip0 = kPair ? blockIdx.x / 2 : blockIdx.x;
-    const long long trip_stride = kPair ? gridDim.x / 2 : gridDim.x;
+    const int trips = kPair ? (tiles + 1) / 2 : tiles;
+    const int trip0 = static_cast<int>(kPair ? blockIdx.x / 2 : blockIdx.x);
+    const int trip_stride = static_cast<int>(kPair ? gridDim.x / 2 : gridDim.x);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_qk);
@@ -346,7 +346,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 }
                 if (++slot == kSlots) { slot = 0; sphase ^= 1; }
             };
-            for (long long trip = trip0; trip < trips; trip += trip_stride) {
+            for (int trip = trip0; trip < trips; trip += trip_stride) {
                 for (int l = 0; l < NL; ++l) {
                     auto qkv = [&](int g) {
 #pragma unroll 1
@@ -411,8 +411,10 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
             constexpr uint32_t idesc192 = umma_idesc_bf16(kM, 192);
             constexpr uint32_t idesc256 = umma_idesc_bf16(kM, 256);
             int slot = 0;
-            uint32_t sphase = 0, n_x = 0, n_acc = 0, n_o = 0;
-            uint32_t use1[2] = {0, 0}, useh[2] = {0, 0};
+            uint32_t sphase = 0, n_l = 0;                                // n_l: layers issued so far (kernel lifetime)
+            // barrier phases are derived from the position in the layer (see the compute warps): no counters, and above all no
+            // dynamically indexed use1[b] / useh[b] arrays -- those lived in local memory (L2 latency) on the issue path
+            const uint32_t uses0 = static_cast<uint32_t>((nc + 1) >> 1), uses1 = static_cast<uint32_t>(nc >> 1);
             const uint32_t sX = smem_u32(smem + kOffX), sO = smem_u32(smem + kOffO), sH = smem_u32(smem + kOffH), sR = smem_u32(smem + kOffRing);
             unsigned long long macc[3] = {0, 0, 0};
             long long mprev = kProf ? clock64() : 0;
@@ -458,7 +460,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 if (++slot == kSlots) { slot = 0; sphase ^= 1; }
             };
             auto gemm = [&](int g) {
-                wait(acc_empty, (n_acc & 1) ^ 1, 20);                    // EPI of the previous group drained the accumulator
+                wait(acc_empty, static_cast<uint32_t>((g & 1) ^ 1), 20);   // EPI of the previous group drained the accumulator
 #pragma unroll 1
                 for (int kb = 0; kb < 4; ++kb) {
                     if (kPair) {
@@ -475,10 +477,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     }
                 }
                 commit(acc_full);
-                ++n_acc;
             };
             auto outp = [&](int g) {
-                wait(o_full, n_o & 1, 23);                               // ATT_g wrote O_g
+                wait(o_full, static_cast<uint32_t>(g & 1), 23);          // ATT_g wrote O_g
                 if (kPair) {
                     const uint32_t b = slot_begin(24);
                     mma4(tmem_h, sO, b, idesc256, false);                // h += O_g . Wo[:, 64g..]^T
@@ -493,11 +494,11 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 }
                 commit(o_empty);
                 if (g == 3) commit(h_ready);
-                ++n_o;
             };
             auto ff1 = [&](int c) {
                 const int b = c & 1;
-                wait(&acc1_empty[b], (use1[b] & 1) ^ 1, 26);            // EPI1 drained acc1[b]
+                const uint32_t ub = (n_l * (b ? uses1 : uses0) + static_cast<uint32_t>(c >> 1)) & 1u;   // uses of buffer b so far
+                wait(&acc1_empty[b], ub ^ 1u, 26);                       // EPI1 drained acc1[b]
                 if (kPair) {
 #pragma unroll 1
                     for (int j = 0; j < 2; ++j) {
@@ -515,11 +516,11 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     }
                 }
                 commit(&acc1_full[b]);
-                ++use1[b];
             };
             auto ff2 = [&](int c) {
                 const int b = c & 1;
-                wait(&hb_full[b], useh[b] & 1, 28);                      // EPI1 wrote H[b]
+                const uint32_t ub = (n_l * (b ? uses1 : uses0) + static_cast<uint32_t>(c >> 1)) & 1u;
+                wait(&hb_full[b], ub, 28);                               // EPI1 wrote H[b]
                 if (kPair) {
 #pragma unroll 1
                     for (int kb = 0; kb < 2; ++kb) {
@@ -537,19 +538,16 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 }
                 commit(&hb_empty[b]);
                 if (c == nc - 1) commit(h_ready);
-                ++useh[b];
             };
-            for (long long trip = trip0; trip < trips; trip += trip_stride) {
-                for (int l = 0; l < NL; ++l) {
-                    wait(x_full, n_x & 1, 30);
-                    ++n_x;
+            for (int trip = trip0; trip < trips; trip += trip_stride) {
+                for (int l = 0; l < NL; ++l, ++n_l) {
+                    wait(x_full, 0u, 30);
 #pragma unroll 1
                     for (int i = 0; i < 8; ++i) {                        // G0 G1 O0 G2 O1 G3 O2 O3
                         if ((0x2Bu >> i) & 1u) gemm(i < 2 ? i : (i + 1) >> 1);
                         else outp(i < 7 ? (i >> 1) - 1 : 3);
                     }
-                    wait(x_full, n_x & 1, 31);
-                    ++n_x;
+                    wait(x_full, 1u, 31);
 #pragma unroll 1
                     for (int c = -2; c < nc; ++c) {                    // FF1_{c+2} first: it only needs acc1 drained (signalled early)
                         if (c + 2 < nc) ff1(c + 2);
@@ -567,7 +565,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         // ===================== per-layer parameter loader =====================
         if (lane == 0) {
             uint32_t n = 0;
-            for (long long trip = trip0; trip < trips; trip += trip_stride) {
+            for (int trip = trip0; trip < trips; trip += trip_stride) {
                 for (int l = 0; l < NL; ++l, ++n) {
                     const float* src = p.params + static_cast<long long>(l) * layer_floats;
                     mbar_wait<true>(pa_empty, (n & 1) ^ 1, 40);
@@ -612,9 +610,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         // between the last attention read and EPI1_0 / between FF2 of the last even chunk and EPI_0.
         const bool skip = kProf && p.dbg_skip;
         const bool film_smem = (p.gb != nullptr) && L >= 8;
-        auto stage_film = [&](long long tile_, int l_, int which) {
+        auto stage_film = [&](int tile_, int l_, int which) {
             if (film_smem && ew == 0 && lane == 0) {
-                const long long t0 = tile_ * 128 / L;
+                const long long t0 = static_cast<long long>(tile_) * 128 / L;
                 const long long left = p.M / L - t0;
                 const int nt = left <= 0 ? 0 : static_cast<int>(left < 128 / L ? left : 128 / L);   // 0: the pair's dead tile
                 fence_proxy_async_smem();
@@ -627,7 +625,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 }
             }
         };
-        auto tile_of = [&](long long trip) { return kPair ? 2 * trip + rank : trip; };
+        auto tile_of = [&](int trip) { return kPair ? 2 * trip + static_cast<int>(rank) : trip; };
         auto arrive_mma = [&](uint64_t* bar) { if (kPair) mbar_arrive_leader(bar); else mbar_arrive(bar); };
         if (trip0 < trips) stage_film(tile_of(trip0), 0, 0);
         // attention work unit of this warp: 16-row block rb, head hh of the group
@@ -643,9 +641,9 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     okbits |= ((((key ^ qr) >> lg) == 0) ? 1u : 0u) << (nt * 4 + c);
                 }
         }
-        for (long long trip = trip0; trip < trips; trip += trip_stride) {
-            const long long tile = tile_of(trip);
-            const long long m0 = tile * 128;
+        for (int trip = trip0; trip < trips; trip += trip_stride) {
+            const int tile = tile_of(trip);
+            const long long m0 = static_cast<long long>(tile) * 128;
             const long long m = m0 + row;
             const bool live = m < p.M;
             // ---- residual stream tile -> TMEM (this thread: its row, columns part*64 .. +63) ----
@@ -863,7 +861,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 if (lane == 0) mbar_arrive(pm_empty);
                 if (film_smem && ew == 0 && lane == 0) {
                     // H[0] is dead once FF2 of the last even chunk has completed: stage the next LayerNorm's FiLM rows there
-                    const long long nxt = (l + 1 < NL) ? trip : trip + trip_stride;
+                    const int nxt = (l + 1 < NL) ? trip : trip + trip_stride;
                     if (nxt < trips) {
                         mbar_wait(&hb_empty[0], (((n_p + 1u) * uses0) & 1u) ^ 1u, 59);
                         stage_film(tile_of(nxt), (l + 1 < NL) ? l + 1 : 0, 0);
@@ -950,6 +948,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     IDB_REQUIRE(ff % 128 == 0 && ff >= 128 && ff <= ef::kMaxFF, IDB200_EUNSUPPORTED, "fused encoder needs d_ff a multiple of 128, <= 1024 (got %d)", ff);
     IDB_REQUIRE(n_layers >= 1, IDB200_EINVAL, "n_layers must be >= 1");
     IDB_REQUIRE(M >= 0 && M % L == 0, IDB200_EINVAL, "M must be a multiple of L");
+    IDB_REQUIRE(M < (1ll << 37), IDB200_EUNSUPPORTED, "M must be below 2^37 tokens (32-bit tile counters)");
     if (M == 0) return IDB200_OK;
     IDB_REQUIRE(params && cb_total && wqkv && wo && w1 && w2, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE((h || (emb && head)), IDB200_EINVAL, "h may be NULL only when both the token assembly and the output head are fused");
