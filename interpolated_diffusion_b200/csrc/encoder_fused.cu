@@ -991,7 +991,9 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     int grid;
     if (pair) {
         const long long trips = (tiles + 1) / 2;
-        const long long pairs = trips < num_sms() / 2 ? trips : num_sms() / 2;
+        static const int max_pairs = getenv("IDB200_EF_MAXPAIRS") ? atoi(getenv("IDB200_EF_MAXPAIRS")) : 1 << 30;   // dev: L2-contention probe
+        long long pairs = trips < num_sms() / 2 ? trips : num_sms() / 2;
+        if (pairs > max_pairs) pairs = max_pairs;
         grid = static_cast<int>(2 * pairs);
     } else {
         grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
