@@ -287,6 +287,15 @@ int idb200_mlp_block(float* h, const float* ln_w, const float* ln_b, const float
                      const void* W1, const float* b1, const void* W2, const float* b2, int64_t M, int L, int d, int ff,
                      idb200_stream_t stream);
 
+/* K3g  in_proj + multi-head self attention of one block in ONE kernel (nn.MultiheadAttention inside src/models/transformer.py:11,39
+ * without the out_proj): o[M, d] = MHA(a), a = the LayerNorm + FiLM output (bf16).  The packed projections q|k|v never leave the SM
+ * (accumulator -> bf16 staging tile -> in-tile attention core); for the models the whole-encoder kernel does not take
+ * (d_model = 384 / 12 heads, the trainer defaults of src/train/train_interp_levels.py:57-62; also d_model = 256).
+ *   wqkv_packed bf16 [3d, d], bqkv_packed fp32 [3d]: head-group-major (group g of two heads = rows [Wq[64g..]; Wk[64g..]; Wv[64g..]],
+ *   as for idb200_attn_block); L | 128, M % L == 0, head_dim 32; o may alias a (a tile's rows are read before they are written). */
+int idb200_qkv_attention(const void* a, const void* wqkv_packed, const float* bqkv_packed, void* o, int64_t M, int L, int d, int H,
+                         int causal, idb200_stream_t stream);
+
 /* K3f  the whole TransformerEncoder (every layer of src/models/transformer.py:73-82) in ONE persistent tcgen05 kernel,
  * d_model = 256, 8 heads, d_ff % 128 == 0 (<= 1024), L | 128, M % L == 0.  A CTA (pair) carries a 128-token tile through
  * all layers with the fp32 residual stream resident in tensor memory; h is read and written once.

@@ -118,6 +118,13 @@ def denoiser_fused(pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causa
     return y
 
 
+def qkv_attention(a: torch.Tensor, wqkv_g: torch.Tensor, bqkv_g: torch.Tensor, out: torch.Tensor, Lseq: int, H: int, causal: bool) -> torch.Tensor:
+    """out[M, d] = MHA(a) without the out_proj: in_proj + attention in one kernel (idb200_qkv_attention); out may alias a."""
+    M, d = a.shape
+    L.call("idb200_qkv_attention", a.data_ptr(), wqkv_g.data_ptr(), bqkv_g.data_ptr(), out.data_ptr(), M, Lseq, d, H, int(causal), L.stream(a.device))
+    return out
+
+
 def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((rows, dim), device=device, dtype=torch.float32)
     L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))
@@ -184,6 +191,7 @@ class PackedEncoder:
         self.fuse_mlp = True            # d_model == 256: FF1 + SiLU + FF2 + residual in one kernel
         self.fuse_blocks = True         # d_model == 256, 8 heads, L | 128: two kernels per layer (attn_block, mlp_block)
         self.fuse_encoder = True        # ... and d_ff <= 1024: ONE kernel for all layers (encoder_fused)
+        self.fuse_qkv_attn = True       # per-op path, d_model 256 / 384, L | 128: in_proj + attention in one kernel (qkv never in HBM)
 
     def _pack(self):
         layers = self.enc.layers
@@ -310,9 +318,11 @@ class PackedEncoder:
             if fused and self.fuse_encoder and self.fused is not None:
                 return encoder_fused(h, self, film, Lseq, causal)
             film = None if film is None else film.t
+            qkv_attn = (not fused and self.fuse_qkv_attn and d in (256, 384) and H * 32 == d and 128 % Lseq == 0 and M % Lseq == 0
+                        and "wqkv_g" in self.layers[0])
             if not fused:
                 a = self.ws.get("a", (M, d), torch.bfloat16, dev)
-                qkv = self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
+                qkv = None if qkv_attn else self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
             f = None if fuse_mlp else self.ws.get("f", (M, ff), torch.bfloat16, dev)
             for i, e in enumerate(self.layers):
                 g1 = film[:, 2 * i] if film is not None else None
@@ -322,8 +332,11 @@ class PackedEncoder:
                     mlp_block(h, e["n2w"], e["n2b"], g2, e["w1"], e["b1"], e["w2"], e["b2"], Lseq)
                     continue
                 ln_film(h, e["n1w"], e["n1b"], g1, a, Lseq)
-                gemm_bf16(a, e["wqkv"], e["bqkv"], qkv, EPI_BF16)
-                attention(qkv, a, B, Lseq, H, causal)                    # `a` is free again: reuse as attention output
+                if qkv_attn:
+                    qkv_attention(a, e["wqkv_g"], e["bqkv_g"], a, Lseq, H, causal)   # in place: a tile's rows are read before they are written
+                else:
+                    gemm_bf16(a, e["wqkv"], e["bqkv"], qkv, EPI_BF16)
+                    attention(qkv, a, B, Lseq, H, causal)                # `a` is free again: reuse as attention output
                 gemm_bf16(a, e["wo"], e["bo"], h, EPI_RESID_F32)
                 ln_film(h, e["n2w"], e["n2b"], g2, a, Lseq)
                 if fuse_mlp:

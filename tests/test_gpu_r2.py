@@ -332,3 +332,31 @@ def test_im2col_scatter_form_vs_unfold(B, Hh, Ww, C, act):
     assert float((got[:, :9 * C] - pat).abs().max()) <= 2.0 ** -7 * float(pat.abs().max())   # silu rounding differences only
     assert torch.equal(got[:, :9 * C] == 0, pat == 0) or not act
     assert float(got[:, 9 * C:].abs().max()) == 0.0 if Kpad > 9 * C else True
+
+
+def _pack_groups(w, b, d):
+    order = torch.cat([torch.arange(64) + part * d + g * 64 for g in range(d // 64) for part in range(3)]).to(w.device)
+    return w[order].contiguous(), b[order].contiguous()
+
+
+@pytest.mark.parametrize("B,Lq,d,causal", [(40, 8, 384, False), (33, 64, 384, False), (16, 64, 256, True), (24, 16, 384, True), (7, 128, 384, False),
+                                           (1, 8, 384, False), (129, 4, 256, False), (50, 32, 384, True)])
+def test_qkv_attention_fused_vs_torch(B, Lq, d, causal):
+    """idb200_qkv_attention (in_proj + attention in one kernel, qkv never in HBM) against fp32 torch on the same bf16 inputs: odd tile
+    counts (the pair's dead tile), a ragged last tile, L = 4 .. 128, causal, both widths; and in place (o aliases a)."""
+    from interpolated_diffusion_b200.models import _engine as E
+    H, M = d // 32, B * Lq
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Lq)
+    a = torch.randn((M, d), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((3 * d, d), generator=g, device="cuda") / d ** 0.5).to(torch.bfloat16)
+    b = torch.randn((3 * d,), generator=g, device="cuda") * 0.1
+    qkv = (a.float() @ w.float().t() + b).to(torch.bfloat16).float()            # the per-op path rounds the projections to bf16 too
+    q, k, v = (t.view(B, Lq, H, 32).transpose(1, 2) for t in qkv.split(d, dim=-1))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(M, d)
+    wg, bg = _pack_groups(w, b, d)
+    out = E.qkv_attention(a, wg, bg, torch.empty_like(a), Lq, H, causal)
+    tol = 2e-2 * max(1.0, float(ref.abs().max()))
+    assert float((out.float() - ref).abs().max()) <= tol
+    inplace = a.clone()
+    E.qkv_attention(inplace, wg, bg, inplace, Lq, H, causal)
+    assert torch.equal(inplace, out)
