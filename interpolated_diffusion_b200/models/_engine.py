@@ -125,6 +125,23 @@ def qkv_attention(a: torch.Tensor, wqkv_g: torch.Tensor, bqkv_g: torch.Tensor, o
     return out
 
 
+def mlp_pair_w2_order(d: int, device) -> torch.Tensor:
+    """Row order of ff.2.weight for idb200_mlp_pair (each CTA of a pair holds the rows its half of the pair MMAs produces)."""
+    buf = (ctypes.c_int * d)()
+    rc = L.lib().idb200_mlp_pair_w2_order(d, buf)
+    if rc:
+        raise RuntimeError(f"idb200_mlp_pair_w2_order failed ({rc})")
+    return torch.tensor(list(buf), dtype=torch.long, device=device)
+
+
+def mlp_pair(a: torch.Tensor, W1: torch.Tensor, b1: torch.Tensor, W2_packed: torch.Tensor, b2: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """h += ff.2(SiLU(ff.0(a))) in one pair-mode kernel (d_model 384 / 256); W2_packed = ff.2.weight[mlp_pair_w2_order]."""
+    M, d = a.shape
+    L.call("idb200_mlp_pair", a.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2_packed.data_ptr(), b2.data_ptr(), h.data_ptr(), M, d, W1.shape[0],
+           L.stream(a.device))
+    return h
+
+
 def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((rows, dim), device=device, dtype=torch.float32)
     L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))
@@ -192,6 +209,7 @@ class PackedEncoder:
         self.fuse_blocks = True         # d_model == 256, 8 heads, L | 128: two kernels per layer (attn_block, mlp_block)
         self.fuse_encoder = True        # ... and d_ff <= 1024: ONE kernel for all layers (encoder_fused)
         self.fuse_qkv_attn = True       # per-op path, d_model 256 / 384, L | 128: in_proj + attention in one kernel (qkv never in HBM)
+        self.fuse_mlp_pair = True       # per-op path, d_model 384: FF1 + SiLU + FF2 + residual in one pair-mode kernel (idb200_mlp_pair)
 
     def _pack(self):
         layers = self.enc.layers
@@ -217,6 +235,8 @@ class PackedEncoder:
             }
             for k in ("wqkv", "wo", "w1", "w2"):
                 e[k] = e[k + "32"].to(torch.bfloat16).contiguous()
+            if d == 384 and e["w1"].shape[0] % 64 == 0 and 128 <= e["w1"].shape[0] <= 2048:
+                e["w2p"] = e["w2"][mlp_pair_w2_order(d, e["w2"].device)].contiguous()      # ff.2 rows as idb200_mlp_pair stages them
             if d % 64 == 0:
                 # head-group-major in_proj for the fused attention block: group g = [Wq[64g:64g+64]; Wk[..]; Wv[..]]
                 order = torch.cat([torch.arange(64) + part * d + g * 64 for g in range(d // 64) for part in range(3)]).to(e["wqkv"].device)
@@ -323,7 +343,8 @@ class PackedEncoder:
             if not fused:
                 a = self.ws.get("a", (M, d), torch.bfloat16, dev)
                 qkv = None if qkv_attn else self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
-            f = None if fuse_mlp else self.ws.get("f", (M, ff), torch.bfloat16, dev)
+            mlp_pair_ok = (not fuse_mlp) and self.fuse_mlp_pair and "w2p" in self.layers[0]
+            f = None if (fuse_mlp or mlp_pair_ok) else self.ws.get("f", (M, ff), torch.bfloat16, dev)
             for i, e in enumerate(self.layers):
                 g1 = film[:, 2 * i] if film is not None else None
                 g2 = film[:, 2 * i + 1] if film is not None else None
@@ -341,6 +362,8 @@ class PackedEncoder:
                 ln_film(h, e["n2w"], e["n2b"], g2, a, Lseq)
                 if fuse_mlp:
                     mlp_fused(a, e["w1"], e["b1"], e["w2"], e["b2"], h)
+                elif mlp_pair_ok:
+                    mlp_pair(a, e["w1"], e["b1"], e["w2p"], e["b2"], h)
                 else:
                     gemm_bf16(a, e["w1"], e["b1"], f, EPI_SILU_BF16)
                     gemm_bf16(f, e["w2"], e["b2"], h, EPI_RESID_F32)

@@ -360,3 +360,23 @@ def test_qkv_attention_fused_vs_torch(B, Lq, d, causal):
     inplace = a.clone()
     E.qkv_attention(inplace, wg, bg, inplace, Lq, H, causal)
     assert torch.equal(inplace, out)
+
+
+@pytest.mark.parametrize("M,d,ff", [(640, 384, 1536), (128, 384, 128), (1000, 384, 192), (4096 + 64, 256, 1024), (300, 384, 2048), (129, 256, 448)])
+def test_mlp_pair_vs_torch(M, d, ff):
+    """idb200_mlp_pair (FF1 + SiLU + FF2 + residual in one pair-mode kernel, hidden activation never in HBM) against fp32 torch on the
+    same bf16 operands (hidden activation rounded to bf16 like the kernel's MMA operand): odd tile counts (the pair's dead tile),
+    ragged last tiles, odd and even chunk counts, both widths."""
+    from interpolated_diffusion_b200.models import _engine as E
+    g = torch.Generator(device="cuda").manual_seed(M + ff)
+    a = torch.randn((M, d), generator=g, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn((ff, d), generator=g, device="cuda") / d ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn((ff,), generator=g, device="cuda") * 0.1
+    w2 = (torch.randn((d, ff), generator=g, device="cuda") / ff ** 0.5).to(torch.bfloat16)
+    b2 = torch.randn((d,), generator=g, device="cuda") * 0.1
+    h0 = torch.randn((M, d), generator=g, device="cuda")
+    hid = torch.nn.functional.silu(a.float() @ w1.float().t() + b1).to(torch.bfloat16).float()
+    ref = h0 + hid @ w2.float().t() + b2
+    h = h0.clone()
+    E.mlp_pair(a, w1, b1, w2[E.mlp_pair_w2_order(d, "cuda")].contiguous(), b2, h)
+    assert float((h - ref).abs().max()) <= 2e-2 * max(1.0, float((ref - h0).abs().max()))
