@@ -295,6 +295,11 @@ int idb200_mlp_block(float* h, const float* ln_w, const float* ln_b, const float
  *   as for idb200_attn_block); L | 128, M % L == 0, head_dim 32; o may alias a (a tile's rows are read before they are written). */
 int idb200_qkv_attention(const void* a, const void* wqkv_packed, const float* bqkv_packed, void* o, int64_t M, int L, int d, int H,
                          int causal, idb200_stream_t stream);
+/* ... with the LayerNorm + FiLM prologue of transformer.py:35-41 computed in shared memory from the fp32 residual stream h (read only):
+ * o[M, d] = MHA(LayerNorm(h) * (1 + gamma) + beta); gamma_beta: raw rows [gamma | beta] per trajectory (row m / L), or NULL. */
+int idb200_ln_qkv_attention(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                            const void* wqkv_packed, const float* bqkv_packed, void* o, int64_t M, int L, int d, int H, int causal,
+                            idb200_stream_t stream);
 
 /* K3h  the MLP of one block in ONE pair-mode kernel for d_model = 384 (and 256), src/models/transformer.py:43-45:
  *   h[M, d] += W2 . SiLU(W1 . a + b1) + b2,  a = the LayerNorm + FiLM output (bf16); the hidden activation [M, d_ff] never leaves the SM.

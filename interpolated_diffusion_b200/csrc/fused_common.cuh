@@ -117,6 +117,71 @@ __device__ __forceinline__ void ln_film_tile(const float* __restrict__ h, long l
     }
 }
 
+// Generic-width form of ln_film_tile for the pair-mode kernels (qkv_attn.cu, mlp_pair.cu): d = VPL * 128 (256 / 384), called by
+// kWarps compute warps (ew = 0 .. kWarps - 1, 128 / kWarps rows each), a warp owns a row: lane <-> float4 column groups
+// {lane + 32 i}; batches of 4 rows with the next batch's loads in flight.  X: VPL * 2 k-blocks of [128 x 64] bf16 SWIZZLE_128B.
+// gb: raw FiLM rows [gamma (d) | beta (d)] per trajectory (row m / L) or nullptr.  Same arithmetic as ln_film_kernel.
+template <int VPL, int kWarps>
+__device__ __forceinline__ void ln_film_rows(const float* __restrict__ h, long long m0, long long M, int L, const float* __restrict__ gb,
+                                             long long gb_stride, const float* s_lnw, const float* s_lnb, uint8_t* X, int ew, int lane) {
+    constexpr int d = VPL * 128;
+    constexpr int kRows = 128 / kWarps;
+    constexpr int kB = 2;                                  // rows per batch (two batches of loads in flight: 2 * kB * VPL float4 registers)
+    static_assert(kRows % kB == 0, "rows per warp in whole batches");
+    const int colin = 4 * (lane & 15);
+    float4 va[2][kB][VPL];
+    auto issue = [&](int batch, int buf) {
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            const long long m = m0 + ew * kRows + batch * kB + i;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                va[buf][i][v] = (m < M) ? reinterpret_cast<const float4*>(h + m * d)[lane + 32 * v] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    issue(0, 0);
+#pragma unroll
+    for (int batch = 0; batch < kRows / kB; ++batch) {
+        const int buf = batch & 1;
+        if (batch + 1 < kRows / kB) issue(batch + 1, buf ^ 1);
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            const int r = ew * kRows + batch * kB + i;
+            const long long m = m0 + r;
+            float sum = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) sum += (va[buf][i][v].x + va[buf][i][v].y) + (va[buf][i][v].z + va[buf][i][v].w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / static_cast<float>(d);
+            float sq = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const float a0 = va[buf][i][v].x - mean, a1 = va[buf][i][v].y - mean, a2 = va[buf][i][v].z - mean, a3 = va[buf][i][v].w - mean;
+                sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = rsqrtf(sq / static_cast<float>(d) + 1e-5f);
+            const float* g = (gb != nullptr && m < M) ? gb + (m / L) * gb_stride : nullptr;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c4 = lane + 32 * v;
+                const float4 w4 = reinterpret_cast<const float4*>(s_lnw)[c4], b4 = reinterpret_cast<const float4*>(s_lnb)[c4];
+                float y0 = (va[buf][i][v].x - mean) * rstd * w4.x + b4.x, y1 = (va[buf][i][v].y - mean) * rstd * w4.y + b4.y;
+                float y2 = (va[buf][i][v].z - mean) * rstd * w4.z + b4.z, y3 = (va[buf][i][v].w - mean) * rstd * w4.w + b4.w;
+                if (g != nullptr) {
+                    const float4 ga = __ldg(reinterpret_cast<const float4*>(g) + c4), be = __ldg(reinterpret_cast<const float4*>(g + d) + c4);
+                    y0 = y0 * (1.0f + ga.x) + be.x; y1 = y1 * (1.0f + ga.y) + be.y; y2 = y2 * (1.0f + ga.z) + be.z; y3 = y3 * (1.0f + ga.w) + be.w;
+                }
+                if (m >= M) { y0 = y1 = y2 = y3 = 0.0f; }
+                // column 4 c4 .. 4 c4 + 3 lives in k-block c4 / 16 = 2 v + (lane >> 4), at column 4 (lane & 15) of it
+                *reinterpret_cast<uint2*>(X + (2 * v + (lane >> 4)) * kTile + sw128_offset(r, colin)) = pack4_bf16(y0, y1, y2, y3);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // legacy tensor-core helpers (mma.sync m16n8k16 + ldmatrix) for the in-tile attention core
 // ------------------------------------------------------------------------------------------------

@@ -38,8 +38,8 @@ struct Cfg {
     static constexpr int kOffO = kOffQkv + 128 * kPitch * 2;        // [128 x 64] bf16 SWIZZLE_128B (TMA store source)
     static constexpr int kOffRing = kOffO + kTile;
     static constexpr int kOffBar = kOffRing + kSlots * kSlotBytes;
-    static constexpr int kOffBias = kOffBar + 256;                  // bqkv (head-group-major) 3 d floats
-    static constexpr int kSmem = kOffBias + NG * 192 * 4 + 1024;
+    static constexpr int kOffBias = kOffBar + 256;                  // bqkv (head-group-major) 3 d floats | ln_w d | ln_b d (kLN kernels)
+    static constexpr int kSmem = kOffBias + (NG * 192 + 2 * NG * 64) * 4 + 1024;
     static_assert(kOffO % 1024 == 0 && kOffRing % 1024 == 0 && kSlotBytes % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
     static_assert(kSmem <= 232448, "shared memory budget");
 };
@@ -48,9 +48,15 @@ struct Params {
     const float* bqkv;          // [3 d] head-group-major
     long long M;
     int L, causal;
+    // kLN kernels: A = LayerNorm(h) * (1 + gamma) + beta is produced in shared memory by the compute warps (no [M, d] operand in HBM)
+    const float* h;             // [M, d] fp32 residual stream (read only)
+    const float* lnw;
+    const float* lnb;
+    const float* gb;            // FiLM rows [gamma | beta] per trajectory, or nullptr
+    long long gb_stride;
 };
 
-template <int NG>
+template <int NG, bool kLN>
 __global__ void __launch_bounds__(kThreads, 1)
 qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_o,
                 const Params p) {
@@ -67,6 +73,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint64_t* acc_empty = acc_full + 2;             // [2] compute -> MMA (leader, 2 * kCW arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* sbias = reinterpret_cast<float*>(smem + C::kOffBias);
+    float* slnw = sbias + NG * 192;
+    float* slnb = slnw + NG * 64;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -80,7 +88,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         tma_prefetch_desc(&tm_o);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(x_full, 1);
+        mbar_init(x_full, kLN ? 2 * kCW : 1);
         mbar_init(x_empty, 1);
         for (int i = 0; i < kSlots; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kCW); }
@@ -88,6 +96,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
     for (int i = threadIdx.x; i < NG * 192; i += kThreads) sbias[i] = p.bqkv[i];
+    if (kLN)
+        for (int i = threadIdx.x; i < NG * 64; i += kThreads) { slnw[i] = p.lnw[i]; slnb[i] = p.lnb[i]; }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -114,8 +124,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
             }
         } else if (warp == 3) {
-            // ===================== A-tile loader =====================
-            if (lane == 0) {
+            // ===================== A-tile loader (kLN: the compute warps produce A) =====================
+            if (!kLN && lane == 0) {
                 uint32_t n = 0;
                 for (int trip = trip0; trip < trips; trip += trip_stride, ++n) {
                     const int tile = 2 * trip + static_cast<int>(rank);
@@ -188,6 +198,16 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
         }
         uint32_t n = 0;
+        // kLN: LayerNorm + FiLM of a tile's rows -> A (bf16 SWIZZLE_128B k-blocks); the tile after the current one is normalised right
+        // after the last group's EPI (its GEMMs then run under that group's attention), the first one before the loop
+        auto ln_tile = [&](int tile_, uint32_t n_) {
+            mbar_wait(x_empty, (n_ & 1) ^ 1, 33);                        // every GEMM of the previous tile has read A
+            ln_film_rows<NG / 2, kCW>(p.h, static_cast<long long>(tile_) * 128, p.M, p.L, p.gb, p.gb_stride, slnw, slnb, smem + C::kOffX, ew, lane);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(x_full);
+        };
+        if (kLN && trip0 < trips) ln_tile(2 * trip0 + static_cast<int>(rank), 0u);
         for (int trip = trip0; trip < trips; trip += trip_stride, ++n) {
             const int tile = 2 * trip + static_cast<int>(rank);
 #pragma unroll 1
@@ -222,6 +242,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     }
                 }
                 named_barrier_sync(1, kCT);                              // q|k|v of the whole tile are staged
+                if (kLN && g == NG - 1 && trip + trip_stride < trips) ln_tile(2 * (trip + trip_stride) + static_cast<int>(rank), n + 1);
                 // ---- ATT_g: this warp's (16-row block, head) ----
                 float o[4][4];
                 {
@@ -269,12 +290,12 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
 }
 
-template <int NG>
+template <int NG, bool kLN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const Params& p, long long tiles, cudaStream_t st) {
     using C = Cfg<NG>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(qkv_attn_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(qkv_attn_kernel<NG, kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(qkv_attn, smem=%d): %s", C::kSmem, cudaGetErrorString(e));
         attr = true;
     }
@@ -292,7 +313,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, qkv_attn_kernel<NG>, ta, tw, to, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qkv_attn_kernel<NG, kLN>, ta, tw, to, p);
     if (e != cudaSuccess) return fail(IDB200_ECUDA, "qkv_attn_kernel: %s", cudaGetErrorString(e));
     return check_launch("qkv_attn_kernel");
 }
@@ -302,24 +323,48 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, 
 
 using namespace idb200;
 
-extern "C" int idb200_qkv_attention(const void* a, const void* wqkv_packed, const float* bqkv_packed, void* o, int64_t M, int L, int d, int H,
-                                    int causal, idb200_stream_t stream) {
+static int qkv_attention_impl(const void* a, const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, long long gb_stride,
+                              const void* wqkv_packed, const float* bqkv_packed, void* o, long long M, int L, int d, int H, int causal,
+                              cudaStream_t st) {
+    const bool ln = (a == nullptr);
     IDB_REQUIRE(d == 256 || d == 384, IDB200_EUNSUPPORTED, "fused in_proj + attention supports d_model 256 or 384 (got %d)", d);
     IDB_REQUIRE(H * 32 == d, IDB200_EUNSUPPORTED, "head_dim must be 32 (d = %d, H = %d)", d, H);
     IDB_REQUIRE(L >= 1 && L <= 128 && (128 % L) == 0, IDB200_EUNSUPPORTED, "fused in_proj + attention needs L | 128 (got %d)", L);
     IDB_REQUIRE(M >= 0 && M % L == 0 && M < (1ll << 37), IDB200_EINVAL, "M must be a multiple of L (and below 2^37)");
     if (M == 0) return IDB200_OK;
-    IDB_REQUIRE(a && wqkv_packed && bqkv_packed && o, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE((a || h) && wqkv_packed && bqkv_packed && o, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(aligned(bqkv_packed, 16), IDB200_EALIGN, "bias must be 16-byte aligned");
+    if (ln) {
+        IDB_REQUIRE(ln_w && ln_b, IDB200_EINVAL, "NULL LayerNorm parameters");
+        IDB_REQUIRE(aligned(h, 16) && (!gamma_beta || (aligned(gamma_beta, 16) && gb_stride % 4 == 0)), IDB200_EALIGN,
+                    "h / gamma_beta must be 16-byte aligned");
+    }
     CUtensorMap ta, tw, to;
-    int rc = make_tmap_bf16_2d(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(d), 128, 64);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tw, wqkv_packed, static_cast<uint64_t>(3 * d), static_cast<uint64_t>(d), 96, 64);
+    int rc = make_tmap_bf16_2d(&tw, wqkv_packed, static_cast<uint64_t>(3 * d), static_cast<uint64_t>(d), 96, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&to, o, static_cast<uint64_t>(M), static_cast<uint64_t>(d), 128, 64);
     if (rc) return rc;
-    qa::Params p{bqkv_packed, M, L, causal};
+    if (ln) ta = to;                                                     // unused by the kLN kernels
+    else {
+        rc = make_tmap_bf16_2d(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(d), 128, 64);
+        if (rc) return rc;
+    }
+    qa::Params p{bqkv_packed, M, L, causal, h, ln_w, ln_b, gamma_beta, gb_stride};
     const long long tiles = (M + 127) / 128;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return d == 256 ? qa::launch<4>(ta, tw, to, p, tiles, st) : qa::launch<6>(ta, tw, to, p, tiles, st);
+    if (ln) return d == 256 ? qa::launch<4, true>(ta, tw, to, p, tiles, st) : qa::launch<6, true>(ta, tw, to, p, tiles, st);
+    return d == 256 ? qa::launch<4, false>(ta, tw, to, p, tiles, st) : qa::launch<6, false>(ta, tw, to, p, tiles, st);
+}
+
+extern "C" int idb200_qkv_attention(const void* a, const void* wqkv_packed, const float* bqkv_packed, void* o, int64_t M, int L, int d, int H,
+                                    int causal, idb200_stream_t stream) {
+    IDB_REQUIRE(a != nullptr, IDB200_EINVAL, "NULL pointer");
+    return qkv_attention_impl(a, nullptr, nullptr, nullptr, nullptr, 0, wqkv_packed, bqkv_packed, o, M, L, d, H, causal, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int idb200_ln_qkv_attention(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                                       const void* wqkv_packed, const float* bqkv_packed, void* o, int64_t M, int L, int d, int H, int causal,
+                                       idb200_stream_t stream) {
+    IDB_REQUIRE(h != nullptr, IDB200_EINVAL, "NULL pointer");
+    return qkv_attention_impl(nullptr, h, ln_w, ln_b, gamma_beta, gb_stride, wqkv_packed, bqkv_packed, o, M, L, d, H, causal,
+                              static_cast<cudaStream_t>(stream));
 }

@@ -125,6 +125,16 @@ def qkv_attention(a: torch.Tensor, wqkv_g: torch.Tensor, bqkv_g: torch.Tensor, o
     return out
 
 
+def ln_qkv_attention(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], wqkv_g: torch.Tensor, bqkv_g: torch.Tensor, out: torch.Tensor,
+                     Lseq: int, H: int, causal: bool) -> torch.Tensor:
+    """out[M, d] = MHA(LayerNorm(h) * (1 + gamma) + beta) without the out_proj, one kernel (idb200_ln_qkv_attention); gb: raw FiLM rows
+    [B, 2d] (any row stride that is a multiple of 4 floats) or None."""
+    M, d = h.shape
+    L.call("idb200_ln_qkv_attention", h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), L.ptr(gb), 0 if gb is None else gb.stride(0),
+           wqkv_g.data_ptr(), bqkv_g.data_ptr(), out.data_ptr(), M, Lseq, d, H, int(causal), L.stream(h.device))
+    return out
+
+
 def mlp_pair_w2_order(d: int, device) -> torch.Tensor:
     """Row order of ff.2.weight for idb200_mlp_pair (each CTA of a pair holds the rows its half of the pair MMAs produces)."""
     buf = (ctypes.c_int * d)()
@@ -210,6 +220,9 @@ class PackedEncoder:
         self.fuse_encoder = True        # ... and d_ff <= 1024: ONE kernel for all layers (encoder_fused)
         self.fuse_qkv_attn = True       # per-op path, d_model 256 / 384, L | 128: in_proj + attention in one kernel (qkv never in HBM)
         self.fuse_mlp_pair = True       # per-op path, d_model 384: FF1 + SiLU + FF2 + residual in one pair-mode kernel (idb200_mlp_pair)
+        self.fuse_ln = False            # ... with the LayerNorm + FiLM prologue computed in the kernel (idb200_ln_qkv_attention).  Correct, but
+        #                                 measured slower: the kernel is bound by its compute warps and the prologue lands on their critical
+        #                                 path (large-model generation: 75.5 ms against 48.1 + 22.6 ms for the two launches)
 
     def _pack(self):
         layers = self.enc.layers
@@ -352,10 +365,13 @@ class PackedEncoder:
                     attn_block(h, e["n1w"], e["n1b"], g1, e["wqkv_g"], e["bqkv_g"], e["wo"], e["bo"], Lseq, H, causal)
                     mlp_block(h, e["n2w"], e["n2b"], g2, e["w1"], e["b1"], e["w2"], e["b2"], Lseq)
                     continue
-                ln_film(h, e["n1w"], e["n1b"], g1, a, Lseq)
-                if qkv_attn:
+                if qkv_attn and self.fuse_ln:
+                    ln_qkv_attention(h, e["n1w"], e["n1b"], g1, e["wqkv_g"], e["bqkv_g"], a, Lseq, H, causal)   # LN + FiLM + in_proj + attention
+                elif qkv_attn:
+                    ln_film(h, e["n1w"], e["n1b"], g1, a, Lseq)
                     qkv_attention(a, e["wqkv_g"], e["bqkv_g"], a, Lseq, H, causal)   # in place: a tile's rows are read before they are written
                 else:
+                    ln_film(h, e["n1w"], e["n1b"], g1, a, Lseq)
                     gemm_bf16(a, e["wqkv"], e["bqkv"], qkv, EPI_BF16)
                     attention(qkv, a, B, Lseq, H, causal)                # `a` is free again: reuse as attention output
                 gemm_bf16(a, e["wo"], e["bo"], h, EPI_RESID_F32)

@@ -380,3 +380,24 @@ def test_mlp_pair_vs_torch(M, d, ff):
     h = h0.clone()
     E.mlp_pair(a, w1, b1, w2[E.mlp_pair_w2_order(d, "cuda")].contiguous(), b2, h)
     assert float((h - ref).abs().max()) <= 2e-2 * max(1.0, float((ref - h0).abs().max()))
+
+
+@pytest.mark.parametrize("B,Lq,d,causal,film", [(40, 8, 384, False, True), (33, 64, 384, False, True), (16, 64, 256, True, False), (129, 4, 256, False, True),
+                                                (1, 8, 384, False, True), (50, 32, 384, True, True)])
+def test_ln_qkv_attention_equals_ln_film_then_qkv_attention(B, Lq, d, causal, film):
+    """idb200_ln_qkv_attention (LayerNorm + FiLM prologue in the kernel) against idb200_ln_film followed by idb200_qkv_attention
+    (the prologue sums a row in a different order: the bf16 operand may differ by one rounding)."""
+    from interpolated_diffusion_b200.models import _engine as E
+    H, M = d // 32, B * Lq
+    g = torch.Generator(device="cuda").manual_seed(B * 77 + Lq)
+    h = torch.randn((M, d), generator=g, device="cuda") * 2 + 0.5
+    lw, lb = torch.randn((d,), generator=g, device="cuda"), torch.randn((d,), generator=g, device="cuda")
+    big = torch.randn((B, 6, 2 * d), generator=g, device="cuda") * 0.3
+    gb = big[:, 3] if film else None                                      # a strided view, as the encoder passes it
+    w = (torch.randn((3 * d, d), generator=g, device="cuda") / d ** 0.5).to(torch.bfloat16)
+    b = torch.randn((3 * d,), generator=g, device="cuda") * 0.1
+    wg, bg = _pack_groups(w, b, d)
+    a = E.ln_film(h, lw, lb, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq)
+    ref = E.qkv_attention(a, wg, bg, torch.empty_like(a), Lq, H, causal)
+    out = E.ln_qkv_attention(h, lw, lb, gb, wg, bg, torch.empty_like(a), Lq, H, causal)
+    assert float((out.float() - ref.float()).abs().max()) <= 2e-2 * max(1.0, float(ref.float().abs().max()))
