@@ -309,6 +309,10 @@ int idb200_ln_qkv_attention(const float* h, const float* ln_w, const float* ln_b
 int idb200_mlp_pair_w2_order(int d, int* order);
 int idb200_mlp_pair(const void* a, const void* W1, const float* b1, const void* W2_packed, const float* b2, float* h, int64_t M, int d, int ff,
                     idb200_stream_t stream);
+/* ... with the LayerNorm + FiLM prologue of transformer.py:42-43 computed in shared memory from h itself:
+ * h += W2 . SiLU(W1 . (LayerNorm(h) * (1 + gamma) + beta) + b1) + b2; gamma_beta: raw rows [gamma | beta] per trajectory (row m / L) or NULL. */
+int idb200_ln_mlp_pair(float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride, int L, const void* W1,
+                       const float* b1, const void* W2_packed, const float* b2, int64_t M, int d, int ff, idb200_stream_t stream);
 
 /* K3f  the whole TransformerEncoder (every layer of src/models/transformer.py:73-82) in ONE persistent tcgen05 kernel,
  * d_model = 256, 8 heads, d_ff % 128 == 0 (<= 1024), L | 128, M % L == 0.  A CTA (pair) carries a 128-token tile through

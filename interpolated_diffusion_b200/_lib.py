@@ -48,6 +48,7 @@ _SIGS = {
     "idb200_attn_block": [c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p],
     "idb200_mlp_block": [c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
     "idb200_mlp_pair_w2_order": [c_i, ctypes.POINTER(c_i)],
+    "idb200_ln_mlp_pair": [c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_p],
     "idb200_mlp_pair": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_p],
     "idb200_ln_qkv_attention": [c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p],
     "idb200_qkv_attention": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p],

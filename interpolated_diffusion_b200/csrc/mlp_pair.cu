@@ -43,8 +43,8 @@ struct Cfg {
     static constexpr int kOffH = NK * kTile;                         // 2 x [128 x 64] bf16 | 2 x [128 x 32] fp32 (final epilogue)
     static constexpr int kOffRing = kOffH + 2 * kTile;
     static constexpr int kOffBar = kOffRing + kSlots * kSlotBytes;
-    static constexpr int kOffBias = kOffBar + 256;                   // b1 (kMaxFF) | b2 (kD)
-    static constexpr int kSmem = kOffBias + (kMaxFF + kD) * 4 + 1024;
+    static constexpr int kOffBias = kOffBar + 256;                   // b1 (kMaxFF) | b2 (kD) | ln_w (kD) | ln_b (kD) (kLN kernels)
+    static constexpr int kSmem = kOffBias + (kMaxFF + 3 * kD) * 4 + 1024;
     static constexpr int kN1 = kD < 256 ? kD : 256;                  // FF2: first MMA's N, second's (0 or 128)
     static constexpr int kN2 = kD - kN1;
     static_assert(kD == 256 || kD == 384, "d_model 256 or 384");
@@ -57,6 +57,13 @@ struct Params {
     const float* b2;            // [d]
     long long M;
     int ff;
+    // kLN kernels: A = LayerNorm(h) * (1 + gamma) + beta is produced in shared memory by the compute warps (no [M, d] operand in HBM)
+    const float* h;             // [M, d] fp32 residual stream (LayerNorm input; also updated through tm_h)
+    const float* lnw;
+    const float* lnb;
+    const float* gb;            // FiLM rows [gamma | beta] per trajectory, or nullptr
+    long long gb_stride;
+    int L;
 };
 
 __device__ __forceinline__ float silu_t(float x) {
@@ -66,7 +73,7 @@ __device__ __forceinline__ float silu_t(float x) {
     return fmaf(hx, t, hx);
 }
 
-template <int NK>
+template <int NK, bool kLN>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
                 const __grid_constant__ CUtensorMap tm_h, const Params p) {
@@ -88,6 +95,8 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
     float* sb1 = reinterpret_cast<float*>(smem + C::kOffBias);
     float* sb2 = sb1 + kMaxFF;
+    float* slnw = sb2 + C::kD;
+    float* slnb = slnw + C::kD;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -102,7 +111,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         tma_prefetch_desc(&tm_w2);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(x_full, 1);
+        mbar_init(x_full, kLN ? 2 * kCW : 1);
         mbar_init(x_empty, 1);
         for (int i = 0; i < kSlots; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
@@ -118,6 +127,8 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
     for (int i = threadIdx.x; i < p.ff; i += kThreads) sb1[i] = p.b1[i];
     for (int i = threadIdx.x; i < C::kD; i += kThreads) sb2[i] = p.b2[i];
+    if (kLN)
+        for (int i = threadIdx.x; i < C::kD; i += kThreads) { slnw[i] = p.lnw[i]; slnb[i] = p.lnb[i]; }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -157,8 +168,8 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
             }
         } else if (warp == 3) {
-            // ===================== A-tile loader =====================
-            if (lane == 0) {
+            // ===================== A-tile loader (kLN: the compute warps produce A) =====================
+            if (!kLN && lane == 0) {
                 uint32_t n = 0;
                 for (int trip = trip0; trip < trips; trip += trip_stride, ++n) {
                     const int tile = 2 * trip + static_cast<int>(rank);
@@ -241,6 +252,16 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t uses0 = static_cast<uint32_t>((nc + 1) >> 1), uses1 = static_cast<uint32_t>(nc >> 1);
         uint32_t n = 0;
+        // kLN: LayerNorm + FiLM of a tile's rows -> A.  The next tile is normalised between the last EPI1 and the final epilogue of
+        // the current one (A is free once the last FF1 has run), so its first FF1s run under that epilogue.
+        auto ln_tile = [&](int tile_, uint32_t n_) {
+            mbar_wait(x_empty, (n_ & 1) ^ 1, 33);
+            ln_film_rows<NK / 2, kCW>(p.h, static_cast<long long>(tile_) * 128, p.M, p.L, p.gb, p.gb_stride, slnw, slnb, smem + C::kOffX, ew, lane);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(x_full);
+        };
+        if (kLN && trip0 < trips) ln_tile(2 * trip0 + static_cast<int>(rank), 0u);
         for (int trip = trip0; trip < trips; trip += trip_stride, ++n) {
             const int tile = 2 * trip + static_cast<int>(rank);
 #pragma unroll 1
@@ -273,6 +294,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&hb_full[b]);
             }
+            if (kLN && trip + trip_stride < trips) ln_tile(2 * (trip + trip_stride) + static_cast<int>(rank), n + 1);
             // ---- final epilogue: h += acc2 + b2, rounds of 32 columns through two fp32 [128 x 32] boxes in the (idle) H buffers, TMA
             // reduce-add into the residual stream.  (red.global.add.v4.f32 straight from registers -- no staging, no barriers -- was
             // tried: 24 us per tile instead of 7, the L2 reduction units do not keep up with 16-byte requests from 512 threads.) ----
@@ -318,13 +340,13 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
 }
 
-template <int NK>
+template <int NK, bool kLN>
 int launch(const CUtensorMap& ta, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& th, const Params& p, long long tiles,
            cudaStream_t st) {
     using C = Cfg<NK>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_pair_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(mlp_pair_kernel<NK, kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
         if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(mlp_pair, smem=%d): %s", C::kSmem, cudaGetErrorString(e));
         attr = true;
     }
@@ -342,7 +364,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& t1, const CUtensorMap& t2, 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_pair_kernel<NK>, ta, t1, t2, th, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_pair_kernel<NK, kLN>, ta, t1, t2, th, p);
     if (e != cudaSuccess) return fail(IDB200_ECUDA, "mlp_pair_kernel: %s", cudaGetErrorString(e));
     return check_launch("mlp_pair_kernel");
 }
@@ -364,25 +386,44 @@ extern "C" int idb200_mlp_pair_w2_order(int d, int* order) {
     return IDB200_OK;
 }
 
-extern "C" int idb200_mlp_pair(const void* a, const void* W1, const float* b1, const void* W2_packed, const float* b2, float* h, int64_t M, int d,
-                               int ff, idb200_stream_t stream) {
+static int mlp_pair_impl(const void* a, const float* ln_w, const float* ln_b, const float* gamma_beta, long long gb_stride, int L, const void* W1,
+                         const float* b1, const void* W2_packed, const float* b2, float* h, long long M, int d, int ff, cudaStream_t st) {
+    const bool ln = (a == nullptr);
     IDB_REQUIRE(d == 256 || d == 384, IDB200_EUNSUPPORTED, "pair-mode fused MLP supports d_model 256 or 384 (got %d)", d);
     IDB_REQUIRE(ff % 64 == 0 && ff >= 128 && ff <= mp::kMaxFF, IDB200_EUNSUPPORTED, "d_ff must be a multiple of 64 in [128, 2048] (got %d)", ff);
     IDB_REQUIRE(M >= 0 && M < (1ll << 37), IDB200_EINVAL, "bad shape");
     if (M == 0) return IDB200_OK;
-    IDB_REQUIRE(a && W1 && b1 && W2_packed && b2 && h, IDB200_EINVAL, "NULL pointer");
-    IDB_REQUIRE(aligned(h, 16) && aligned(b1, 16), IDB200_EALIGN, "h and b1 must be 16-byte aligned");
+    IDB_REQUIRE(W1 && b1 && W2_packed && b2 && h, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(aligned(h, 16), IDB200_EALIGN, "h must be 16-byte aligned");
+    if (ln) {
+        IDB_REQUIRE(ln_w && ln_b && L >= 1 && M % L == 0, IDB200_EINVAL, "LayerNorm parameters / M must be a multiple of L");
+        IDB_REQUIRE(!gamma_beta || (aligned(gamma_beta, 16) && gb_stride % 4 == 0), IDB200_EALIGN, "gamma_beta must be 16-byte aligned");
+    }
     CUtensorMap ta, t1, t2, th;
-    int rc = make_tmap_bf16_2d(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(d), 128, 64);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&t1, W1, static_cast<uint64_t>(ff), static_cast<uint64_t>(d), 32, 64);
+    int rc = make_tmap_bf16_2d(&t1, W1, static_cast<uint64_t>(ff), static_cast<uint64_t>(d), 32, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&t2, W2_packed, static_cast<uint64_t>(d), static_cast<uint64_t>(ff), static_cast<uint32_t>(d / 2), 64);
     if (rc) return rc;
     rc = make_tmap_2d(&th, h, 4, static_cast<uint64_t>(M), static_cast<uint64_t>(d), 128, 32);
     if (rc) return rc;
-    mp::Params p{b1, b2, M, ff};
+    if (ln) ta = t1;                                                     // unused by the kLN kernels
+    else {
+        rc = make_tmap_bf16_2d(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(d), 128, 64);
+        if (rc) return rc;
+    }
+    mp::Params p{b1, b2, M, ff, h, ln_w, ln_b, gamma_beta, gb_stride, L};
     const long long tiles = (M + 127) / 128;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return d == 256 ? mp::launch<4>(ta, t1, t2, th, p, tiles, st) : mp::launch<6>(ta, t1, t2, th, p, tiles, st);
+    if (ln) return d == 256 ? mp::launch<4, true>(ta, t1, t2, th, p, tiles, st) : mp::launch<6, true>(ta, t1, t2, th, p, tiles, st);
+    return d == 256 ? mp::launch<4, false>(ta, t1, t2, th, p, tiles, st) : mp::launch<6, false>(ta, t1, t2, th, p, tiles, st);
+}
+
+extern "C" int idb200_mlp_pair(const void* a, const void* W1, const float* b1, const void* W2_packed, const float* b2, float* h, int64_t M, int d,
+                               int ff, idb200_stream_t stream) {
+    IDB_REQUIRE(a != nullptr, IDB200_EINVAL, "NULL pointer");
+    return mlp_pair_impl(a, nullptr, nullptr, nullptr, 0, 1, W1, b1, W2_packed, b2, h, M, d, ff, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int idb200_ln_mlp_pair(float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride, int L, const void* W1,
+                                  const float* b1, const void* W2_packed, const float* b2, int64_t M, int d, int ff, idb200_stream_t stream) {
+    return mlp_pair_impl(nullptr, ln_w, ln_b, gamma_beta, gb_stride, L, W1, b1, W2_packed, b2, h, M, d, ff, static_cast<cudaStream_t>(stream));
 }

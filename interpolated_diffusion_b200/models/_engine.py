@@ -152,6 +152,14 @@ def mlp_pair(a: torch.Tensor, W1: torch.Tensor, b1: torch.Tensor, W2_packed: tor
     return h
 
 
+def ln_mlp_pair(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], W1, b1, W2_packed, b2, Lseq: int) -> torch.Tensor:
+    """h += ff.2(SiLU(ff.0(LayerNorm(h) * (1 + gamma) + beta))) in one pair-mode kernel (idb200_ln_mlp_pair)."""
+    M, d = h.shape
+    L.call("idb200_ln_mlp_pair", h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), L.ptr(gb), 0 if gb is None else gb.stride(0), Lseq,
+           W1.data_ptr(), b1.data_ptr(), W2_packed.data_ptr(), b2.data_ptr(), M, d, W1.shape[0], L.stream(h.device))
+    return h
+
+
 def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((rows, dim), device=device, dtype=torch.float32)
     L.call("idb200_sinusoid", L.ptr(args), rows, dim, 0 if args is None else 1, out.data_ptr(), L.stream(out.device))
@@ -220,6 +228,7 @@ class PackedEncoder:
         self.fuse_encoder = True        # ... and d_ff <= 1024: ONE kernel for all layers (encoder_fused)
         self.fuse_qkv_attn = True       # per-op path, d_model 256 / 384, L | 128: in_proj + attention in one kernel (qkv never in HBM)
         self.fuse_mlp_pair = True       # per-op path, d_model 384: FF1 + SiLU + FF2 + residual in one pair-mode kernel (idb200_mlp_pair)
+        self.fuse_ln_mlp = True         # idb200_ln_mlp_pair: the MLP kernel with its LayerNorm + FiLM prologue computed in the kernel
         self.fuse_ln = False            # ... with the LayerNorm + FiLM prologue computed in the kernel (idb200_ln_qkv_attention).  Correct, but
         #                                 measured slower: the kernel is bound by its compute warps and the prologue lands on their critical
         #                                 path (large-model generation: 75.5 ms against 48.1 + 22.6 ms for the two launches)
@@ -375,6 +384,9 @@ class PackedEncoder:
                     gemm_bf16(a, e["wqkv"], e["bqkv"], qkv, EPI_BF16)
                     attention(qkv, a, B, Lseq, H, causal)                # `a` is free again: reuse as attention output
                 gemm_bf16(a, e["wo"], e["bo"], h, EPI_RESID_F32)
+                if mlp_pair_ok and self.fuse_ln_mlp and M % Lseq == 0:
+                    ln_mlp_pair(h, e["n2w"], e["n2b"], g2, e["w1"], e["b1"], e["w2p"], e["b2"], Lseq)      # LN + FiLM + FF1 + SiLU + FF2 + residual
+                    continue
                 ln_film(h, e["n2w"], e["n2b"], g2, a, Lseq)
                 if fuse_mlp:
                     mlp_fused(a, e["w1"], e["b1"], e["w2"], e["b2"], h)

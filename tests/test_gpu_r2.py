@@ -401,3 +401,25 @@ def test_ln_qkv_attention_equals_ln_film_then_qkv_attention(B, Lq, d, causal, fi
     ref = E.qkv_attention(a, wg, bg, torch.empty_like(a), Lq, H, causal)
     out = E.ln_qkv_attention(h, lw, lb, gb, wg, bg, torch.empty_like(a), Lq, H, causal)
     assert float((out.float() - ref.float()).abs().max()) <= 2e-2 * max(1.0, float(ref.float().abs().max()))
+
+
+@pytest.mark.parametrize("B,Lq,d,ff,film", [(40, 8, 384, 1536, True), (33, 64, 384, 1536, True), (65, 64, 256, 1024, False), (1, 8, 384, 128, True), (50, 32, 384, 192, True)])
+def test_ln_mlp_pair_vs_ln_film_then_mlp_pair(B, Lq, d, ff, film):
+    """idb200_ln_mlp_pair (LayerNorm + FiLM prologue in the kernel, h both normalised and updated) against idb200_ln_film followed by
+    idb200_mlp_pair (the prologue sums a row in a different order: the bf16 operand may differ by one rounding)."""
+    from interpolated_diffusion_b200.models import _engine as E
+    M = B * Lq
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + ff)
+    h0 = torch.randn((M, d), generator=g, device="cuda") * 2 + 0.5
+    lw, lb = torch.randn((d,), generator=g, device="cuda"), torch.randn((d,), generator=g, device="cuda")
+    big = torch.randn((B, 4, 2 * d), generator=g, device="cuda") * 0.3
+    gb = big[:, 1] if film else None
+    w1 = (torch.randn((ff, d), generator=g, device="cuda") / d ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn((ff,), generator=g, device="cuda") * 0.1
+    w2 = (torch.randn((d, ff), generator=g, device="cuda") / ff ** 0.5).to(torch.bfloat16)
+    b2 = torch.randn((d,), generator=g, device="cuda") * 0.1
+    w2p = w2[E.mlp_pair_w2_order(d, "cuda")].contiguous()
+    a = E.ln_film(h0, lw, lb, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq)
+    ref = E.mlp_pair(a, w1, b1, w2p, b2, h0.clone())
+    out = E.ln_mlp_pair(h0.clone(), lw, lb, gb, w1, b1, w2p, b2, Lq)
+    assert float((out - ref).abs().max()) <= 2e-2 * max(1.0, float((ref - h0).abs().max()))
