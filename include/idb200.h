@@ -305,7 +305,7 @@ int idb200_ln_qkv_attention(const float* h, const float* ln_w, const float* ln_b
  *   h[M, d] += W2 . SiLU(W1 . a + b1) + b2,  a = the LayerNorm + FiLM output (bf16); the hidden activation [M, d_ff] never leaves the SM.
  *   W1 bf16 [ff, d] (nn.Linear layout), W2_packed bf16 [d, ff] = ff.2.weight with its ROWS permuted by idb200_mlp_pair_w2_order
  *   (order[i] = source row of packed row i: each CTA of a pair holds the rows its half of the cta_group::2 MMAs produces);
- *   d_ff % 64 == 0, 128 <= d_ff <= 2048; h fp32, 16-byte aligned (updated by TMA reduce-add). */
+ *   d_ff % 128 == 0, 128 <= d_ff <= 2048; h fp32, 16-byte aligned (updated by TMA reduce-add). */
 int idb200_mlp_pair_w2_order(int d, int* order);
 int idb200_mlp_pair(const void* a, const void* W1, const float* b1, const void* W2_packed, const float* b2, float* h, int64_t M, int d, int ff,
                     idb200_stream_t stream);

@@ -9,16 +9,20 @@
 // stream (2.4 MB per tile), so this kernel runs as CTA pairs (tcgen05 cta_group::2: one M = 256 MMA per k-step for the pair's two
 // tiles, each CTA stages half of every weight tile) like the MLP half of encoder_fused.cu.
 //
-// Tensor memory (512 columns): acc2 = d columns (the FF2 accumulator of the whole tile), acc1 = 2 x 64 columns (FF1 chunk, double
-// buffered).  The hidden dimension is processed in chunks of 64:
-//   FF1_c   acc1[c&1]  = A[128 x d] . W1[64c.., :]^T                      d/64 x 4 tcgen05.mma N = 64
-//   EPI1_c  acc1 + b1 -> SiLU -> bf16 H[c&1] (SWIZZLE_128B A operand, 16 KB)  16 compute warps, thread <-> row x 16 columns
-//   FF2_c   acc2      += H[c&1] . W2[:, 64c..]^T                          4 x (N = 256 [+ N = 128 at d = 384])
-//   final   h += acc2 + b2: fp32 [128 x 32] boxes staged in the idle H buffers, TMA reduce-add into the residual stream
-// FF1_{c+2} is issued before FF2_c (it only needs acc1 drained, which EPI1 signals right after its TMEM load).  Shared memory: A
-// 96 KB, H 2 x 16 KB, weight ring 4 x 24 KB (a slot = the d/64 k-blocks of a W1 chunk, 4 KB each, or one k-block of W2 = this CTA's
-// d/2 output rows), biases.  (Four slots with b1 read from global memory were not faster.)  W2 is row-permuted on the host (idb200_mlp_pair_w2_order) so that each CTA's rows are one TMA box:
-// a pair MMA takes the first N/2 rows of its B operand from the even CTA and the rest from the odd one.
+// Tensor memory (512 columns): acc2 = d columns (the FF2 accumulator of the whole tile), acc1 = 128 columns (one FF1 chunk).  The
+// hidden dimension is processed in chunks of 128:
+//   FF1_c   acc1  = A[128 x d] . W1[128c.., :]^T                          d/64 x 4 tcgen05.mma N = 128
+//   EPI1_c  acc1 + b1 -> SiLU -> bf16 H (SWIZZLE_128B A operand, 2 k-blocks, 32 KB)   16 compute warps, thread <-> row x 32 columns
+//   FF2_c   acc2 += H . W2[:, 128c..]^T                                   2 k-blocks x 4 x (N = 256 [+ N = 128 at d = 384])
+//   final   h += acc2 + b2: fp32 [128 x 32] boxes staged in the idle H tile, TMA reduce-add into the residual stream
+// acc1 and H are SINGLE buffers (TMEM: 384 + 128 = 512; shared memory: A 96 KB + H 32 KB + a 3 x 24 KB weight ring), and the tensor
+// pipe still runs back to back: issue order FF1_{c+1}, FF2_c; EPI1 releases acc1 right after its TMEM load (so FF1_{c+1} runs under
+// the SiLU math), computes the chunk into registers, and only then waits for FF2_{c-1} to have released H.  (The first revision used
+// 64-column chunks with double-buffered acc1 / H: an N = 64 pair MMA costs the same ~64 cycles as N = 128 -- 2.3 k cycles per 64
+// hidden columns with the SiLU and the weight loads ablated, against 1.5 k nominal.)  A ring slot = half of the d/64 k-blocks of a
+// W1 chunk (this CTA's 64 rows, 8 KB each) or one k-block of W2 (this CTA's d/2 permuted output rows).  W2 is row-permuted on the
+// host (idb200_mlp_pair_w2_order) so that each CTA's rows are one TMA box: a pair MMA takes the first N/2 rows of its B operand from
+// the even CTA and the rest from the odd one.
 #include <cstdlib>
 
 #include "fused_common.cuh"
@@ -40,7 +44,7 @@ template <int NK>
 struct Cfg {
     static constexpr int kD = NK * 64;
     static constexpr int kOffX = 0;                                  // NK x [128 x 64] bf16 SWIZZLE_128B
-    static constexpr int kOffH = NK * kTile;                         // 2 x [128 x 64] bf16 | 2 x [128 x 32] fp32 (final epilogue)
+    static constexpr int kOffH = NK * kTile;                         // 2 k-blocks [128 x 64] bf16 | 2 x [128 x 32] fp32 (final epilogue)
     static constexpr int kOffRing = kOffH + 2 * kTile;
     static constexpr int kOffBar = kOffRing + kSlots * kSlotBytes;
     static constexpr int kOffBias = kOffBar + 256;                   // b1 (kMaxFF) | b2 (kD) | ln_w (kD) | ln_b (kD) (kLN kernels)
@@ -64,6 +68,7 @@ struct Params {
     const float* gb;            // FiLM rows [gamma | beta] per trajectory, or nullptr
     long long gb_stride;
     int L;
+    int dbg;                    // dev (IDB200_MLP_DBG): 1 = EPI1 without the SiLU math, 2 = the weight producer signals slots without loading
 };
 
 __device__ __forceinline__ float silu_t(float x) {
@@ -86,11 +91,11 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint64_t* x_empty = bars + 1;                   // MMA -> TMA: the last FF1 of the tile has read A (multicast commit)
     uint64_t* slot_full = bars + 2;                 // [kSlots] (leader)
     uint64_t* slot_empty = slot_full + kSlots;      // [kSlots] (multicast commit)
-    uint64_t* acc1_full = slot_empty + kSlots;      // [2] MMA -> compute
-    uint64_t* acc1_empty = acc1_full + 2;           // [2] compute -> MMA (leader, 2 * kCW)
-    uint64_t* hb_full = acc1_empty + 2;             // [2] compute -> MMA (leader, 2 * kCW)
-    uint64_t* hb_empty = hb_full + 2;               // [2] MMA -> compute
-    uint64_t* acc2_full = hb_empty + 2;             // MMA -> compute
+    uint64_t* acc1_full = slot_empty + kSlots;      // MMA -> compute
+    uint64_t* acc1_empty = acc1_full + 1;           // compute -> MMA (leader, 2 * kCW)
+    uint64_t* hb_full = acc1_empty + 1;             // compute -> MMA (leader, 2 * kCW)
+    uint64_t* hb_empty = hb_full + 1;               // MMA -> compute
+    uint64_t* acc2_full = hb_empty + 1;             // MMA -> compute
     uint64_t* acc2_empty = acc2_full + 1;           // compute -> MMA (leader, 2 * kCW)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
     float* sb1 = reinterpret_cast<float*>(smem + C::kOffBias);
@@ -100,7 +105,7 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int nc = p.ff / 64;
+    const int nc = p.ff / 128;
     const int tiles = static_cast<int>((p.M + 127) / 128);
     const int trips = (tiles + 1) / 2;
     const int trip0 = static_cast<int>(blockIdx.x / 2), trip_stride = static_cast<int>(gridDim.x / 2);
@@ -114,12 +119,10 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         mbar_init(x_full, kLN ? 2 * kCW : 1);
         mbar_init(x_empty, 1);
         for (int i = 0; i < kSlots; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc1_full[i], 1);
-            mbar_init(&acc1_empty[i], 2 * kCW);
-            mbar_init(&hb_full[i], 2 * kCW);
-            mbar_init(&hb_empty[i], 1);
-        }
+        mbar_init(acc1_full, 1);
+        mbar_init(acc1_empty, 2 * kCW);
+        mbar_init(hb_full, 2 * kCW);
+        mbar_init(hb_empty, 1);
         mbar_init(acc2_full, 1);
         mbar_init(acc2_empty, 2 * kCW);
         fence_mbar_init();
@@ -142,27 +145,35 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (lane == 0) {
                 int slot = 0;
                 uint32_t sphase = 0;
+                const bool noload = (p.dbg & 2) != 0;
                 auto begin = [&](uint32_t bytes) -> uint8_t* {
                     mbar_wait(&slot_empty[slot], sphase ^ 1, 10);
-                    if (rank == 0) mbar_arrive_expect_tx(&slot_full[slot], 2 * bytes);
+                    if (rank == 0) { if (noload) mbar_arrive(&slot_full[slot]); else mbar_arrive_expect_tx(&slot_full[slot], 2 * bytes); }
                     return smem + C::kOffRing + slot * kSlotBytes;
                 };
                 auto end = [&]() { if (++slot == kSlots) { slot = 0; sphase ^= 1; } };
-                auto ff1 = [&](int c) {                                  // this CTA's 32 rows of the chunk, NK k-blocks of 4 KB
-                    uint8_t* dst = begin(NK * 4096);
+                auto ff1 = [&](int c) {                                  // this CTA's 64 rows of the chunk: 2 slots x NK/2 k-blocks of 8 KB
 #pragma unroll 1
-                    for (int kb = 0; kb < NK; ++kb) tma_load_2d_2sm(dst + kb * 4096, &tm_w1, &slot_full[slot], kb * 64, c * 64 + static_cast<int>(rank) * 32);
-                    end();
+                    for (int half = 0; half < 2; ++half) {
+                        uint8_t* dst = begin((NK / 2) * 8192);
+                        if (!noload)
+                            for (int i = 0; i < NK / 2; ++i)
+                                tma_load_2d_2sm(dst + i * 8192, &tm_w1, &slot_full[slot], (half * (NK / 2) + i) * 64, c * 128 + static_cast<int>(rank) * 64);
+                        end();
+                    }
                 };
-                auto ff2 = [&](int c) {                                  // this CTA's d/2 (permuted) output rows, one k-block
-                    uint8_t* dst = begin((C::kD / 2) * 128);
-                    tma_load_2d_2sm(dst, &tm_w2, &slot_full[slot], c * 64, static_cast<int>(rank) * (C::kD / 2));
-                    end();
+                auto ff2 = [&](int c) {                                  // this CTA's d/2 (permuted) output rows, 2 k-blocks = 2 slots
+#pragma unroll 1
+                    for (int kb = 0; kb < 2; ++kb) {
+                        uint8_t* dst = begin((C::kD / 2) * 128);
+                        if (!noload) tma_load_2d_2sm(dst, &tm_w2, &slot_full[slot], c * 128 + kb * 64, static_cast<int>(rank) * (C::kD / 2));
+                        end();
+                    }
                 };
                 for (int trip = trip0; trip < trips; trip += trip_stride) {
 #pragma unroll 1
-                    for (int c = -2; c < nc; ++c) {
-                        if (c + 2 < nc) ff1(c + 2);
+                    for (int c = -1; c < nc; ++c) {
+                        if (c + 1 < nc) ff1(c + 1);
                         if (c >= 0) ff2(c);
                     }
                 }
@@ -182,13 +193,12 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         } else if (warp == 1) {
             // ===================== MMA issuer (the even CTA of the pair) =====================
             if (rank == 0) {
-                constexpr uint32_t idesc64 = umma_idesc_bf16(256, 64);
+                constexpr uint32_t idesc128 = umma_idesc_bf16(256, 128);
                 constexpr uint32_t idescN1 = umma_idesc_bf16(256, C::kN1);
                 constexpr uint32_t idescN2 = umma_idesc_bf16(256, C::kN2 > 0 ? C::kN2 : 64);
                 int slot = 0;
                 uint32_t sphase = 0, n = 0;
                 const uint32_t sX = smem_u32(smem + C::kOffX), sH = smem_u32(smem + C::kOffH), sR = smem_u32(smem + C::kOffRing);
-                const uint32_t uses0 = static_cast<uint32_t>((nc + 1) >> 1), uses1 = static_cast<uint32_t>(nc >> 1);   // chunk uses of buffer 0 / 1 per tile
                 auto wait = [&](uint64_t* bar, uint32_t parity, int tag) {
                     mbar_wait(bar, parity, tag);
                     tc_fence_after();
@@ -207,36 +217,40 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     __syncwarp();
                 };
                 auto ff1 = [&](int c) {
-                    const int b = c & 1;
-                    const uint32_t ub = (n * (b ? uses1 : uses0) + static_cast<uint32_t>(c >> 1)) & 1u;
-                    wait(&acc1_empty[b], ub ^ 1u, 20);                   // EPI1 drained acc1[b]
-                    wait(&slot_full[slot], sphase, 21);
-                    const uint32_t bs = sR + slot * kSlotBytes;
+                    const uint32_t u = (n * static_cast<uint32_t>(nc) + static_cast<uint32_t>(c)) & 1u;      // chunks so far
+                    wait(acc1_empty, u ^ 1u, 20);                        // EPI1 of the previous chunk has the accumulator in registers
 #pragma unroll 1
-                    for (int kb = 0; kb < NK; ++kb) mma4(tmem_acc1 + b * 64, sX + kb * kTile, bs + kb * 4096, idesc64, kb == 0);
-                    commit(&slot_empty[slot]);
-                    if (++slot == kSlots) { slot = 0; sphase ^= 1; }
-                    commit(&acc1_full[b]);
+                    for (int half = 0; half < 2; ++half) {
+                        wait(&slot_full[slot], sphase, 21);
+                        const uint32_t bs = sR + slot * kSlotBytes;
+#pragma unroll 1
+                        for (int i = 0; i < NK / 2; ++i) mma4(tmem_acc1, sX + (half * (NK / 2) + i) * kTile, bs + i * 8192, idesc128, half == 0 && i == 0);
+                        commit(&slot_empty[slot]);
+                        if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+                    }
+                    commit(acc1_full);
                     if (c == nc - 1) commit(x_empty);                    // A no longer needed: the next tile's load may start
                 };
                 auto ff2 = [&](int c) {
-                    const int b = c & 1;
-                    const uint32_t ub = (n * (b ? uses1 : uses0) + static_cast<uint32_t>(c >> 1)) & 1u;
-                    wait(&hb_full[b], ub, 22);                           // EPI1 wrote H[b]
-                    wait(&slot_full[slot], sphase, 23);
-                    const uint32_t bs = sR + slot * kSlotBytes;
-                    mma4(tmem_base, sH + b * kTile, bs, idescN1, c == 0);
-                    if (C::kN2 > 0) mma4(tmem_base + C::kN1, sH + b * kTile, bs + (C::kN1 / 2) * 128, idescN2, c == 0);
-                    commit(&slot_empty[slot]);
-                    if (++slot == kSlots) { slot = 0; sphase ^= 1; }
-                    commit(&hb_empty[b]);
+                    const uint32_t u = (n * static_cast<uint32_t>(nc) + static_cast<uint32_t>(c)) & 1u;
+                    wait(hb_full, u, 22);                                // EPI1 wrote H
+#pragma unroll 1
+                    for (int kb = 0; kb < 2; ++kb) {
+                        wait(&slot_full[slot], sphase, 23);
+                        const uint32_t bs = sR + slot * kSlotBytes;
+                        mma4(tmem_base, sH + kb * kTile, bs, idescN1, c == 0 && kb == 0);
+                        if (C::kN2 > 0) mma4(tmem_base + C::kN1, sH + kb * kTile, bs + (C::kN1 / 2) * 128, idescN2, c == 0 && kb == 0);
+                        commit(&slot_empty[slot]);
+                        if (++slot == kSlots) { slot = 0; sphase ^= 1; }
+                    }
+                    commit(hb_empty);
                     if (c == nc - 1) commit(acc2_full);
                 };
                 for (int trip = trip0; trip < trips; trip += trip_stride, ++n) {
                     wait(x_full, n & 1, 24);
 #pragma unroll 1
-                    for (int c = -2; c < nc; ++c) {
-                        if (c + 2 < nc) ff1(c + 2);
+                    for (int c = -1; c < nc; ++c) {
+                        if (c + 1 < nc) ff1(c + 1);
                         if (c == 0) wait(acc2_empty, (n & 1) ^ 1, 25);   // the previous tile's final epilogue drained acc2
                         if (c >= 0) ff2(c);
                     }
@@ -250,7 +264,6 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int q = ew & 3, part = ew >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t uses0 = static_cast<uint32_t>((nc + 1) >> 1), uses1 = static_cast<uint32_t>(nc >> 1);
         uint32_t n = 0;
         // kLN: LayerNorm + FiLM of a tile's rows -> A.  The next tile is normalised between the last EPI1 and the final epilogue of
         // the current one (A is free once the last FF1 has run), so its first FF1s run under that epilogue.
@@ -266,33 +279,34 @@ mlp_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const int tile = 2 * trip + static_cast<int>(rank);
 #pragma unroll 1
             for (int c = 0; c < nc; ++c) {
-                const int b = c & 1;
-                const uint32_t ub = (n * (b ? uses1 : uses0) + static_cast<uint32_t>(c >> 1)) & 1u;
-                mbar_wait(&acc1_full[b], ub, 30);
-                mbar_wait(&hb_empty[b], ub ^ 1u, 31);                   // FF2 of the previous use finished reading H[b]
+                const uint32_t u = (n * static_cast<uint32_t>(nc) + static_cast<uint32_t>(c)) & 1u;
+                mbar_wait(acc1_full, u, 30);
                 tc_fence_after();
-                uint32_t r[16];
-                tmem_ld_32x16(tmem_acc1 + lane_base + b * 64 + part * 16, r);
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_acc1 + lane_base + part * 32, r);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_leader(&acc1_empty[b]);       // in registers: FF1_{c+2} may overwrite the accumulator
-                const float* bb = sb1 + c * 64 + part * 16;
-                uint8_t* hb = smem + C::kOffH + b * kTile;
+                if (lane == 0) mbar_arrive_leader(acc1_empty);           // in registers: FF1_{c+1} may overwrite the accumulator
+                const float* bb = sb1 + c * 128 + part * 32;
+                uint4 pk[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < 4; ++j) {                            // 8 columns -> one 16-byte swizzle chunk
                     const float4 b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
                     const float4 b1v = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
-                    uint4 pk;
-                    pk.x = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 0]) + b0.x), silu_t(__uint_as_float(r[8 * j + 1]) + b0.y));
-                    pk.y = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 2]) + b0.z), silu_t(__uint_as_float(r[8 * j + 3]) + b0.w));
-                    pk.z = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 4]) + b1v.x), silu_t(__uint_as_float(r[8 * j + 5]) + b1v.y));
-                    pk.w = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 6]) + b1v.z), silu_t(__uint_as_float(r[8 * j + 7]) + b1v.w));
-                    *reinterpret_cast<uint4*>(hb + sw128_offset(row, part * 16 + j * 8)) = pk;
+                    if (p.dbg & 1) { pk[j] = make_uint4(r[8 * j], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3]); continue; }
+                    pk[j].x = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 0]) + b0.x), silu_t(__uint_as_float(r[8 * j + 1]) + b0.y));
+                    pk[j].y = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 2]) + b0.z), silu_t(__uint_as_float(r[8 * j + 3]) + b0.w));
+                    pk[j].z = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 4]) + b1v.x), silu_t(__uint_as_float(r[8 * j + 5]) + b1v.y));
+                    pk[j].w = pack2_bf16(silu_t(__uint_as_float(r[8 * j + 6]) + b1v.z), silu_t(__uint_as_float(r[8 * j + 7]) + b1v.w));
                 }
+                mbar_wait(hb_empty, u ^ 1u, 31);                         // FF2 of the previous chunk finished reading H (the math is done: only
+                uint8_t* hb = smem + C::kOffH + (part >> 1) * kTile;     // the stores wait)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(hb + sw128_offset(row, (part & 1) * 32 + j * 8)) = pk[j];
                 fence_proxy_async_smem();                                // H writes -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) mbar_arrive_leader(&hb_full[b]);
+                if (lane == 0) mbar_arrive_leader(hb_full);
             }
             if (kLN && trip + trip_stride < trips) ln_tile(2 * (trip + trip_stride) + static_cast<int>(rank), n + 1);
             // ---- final epilogue: h += acc2 + b2, rounds of 32 columns through two fp32 [128 x 32] boxes in the (idle) H buffers, TMA
@@ -390,7 +404,7 @@ static int mlp_pair_impl(const void* a, const float* ln_w, const float* ln_b, co
                          const float* b1, const void* W2_packed, const float* b2, float* h, long long M, int d, int ff, cudaStream_t st) {
     const bool ln = (a == nullptr);
     IDB_REQUIRE(d == 256 || d == 384, IDB200_EUNSUPPORTED, "pair-mode fused MLP supports d_model 256 or 384 (got %d)", d);
-    IDB_REQUIRE(ff % 64 == 0 && ff >= 128 && ff <= mp::kMaxFF, IDB200_EUNSUPPORTED, "d_ff must be a multiple of 64 in [128, 2048] (got %d)", ff);
+    IDB_REQUIRE(ff % 128 == 0 && ff >= 128 && ff <= mp::kMaxFF, IDB200_EUNSUPPORTED, "d_ff must be a multiple of 128 in [128, 2048] (got %d)", ff);
     IDB_REQUIRE(M >= 0 && M < (1ll << 37), IDB200_EINVAL, "bad shape");
     if (M == 0) return IDB200_OK;
     IDB_REQUIRE(W1 && b1 && W2_packed && b2 && h, IDB200_EINVAL, "NULL pointer");
@@ -400,7 +414,7 @@ static int mlp_pair_impl(const void* a, const float* ln_w, const float* ln_b, co
         IDB_REQUIRE(!gamma_beta || (aligned(gamma_beta, 16) && gb_stride % 4 == 0), IDB200_EALIGN, "gamma_beta must be 16-byte aligned");
     }
     CUtensorMap ta, t1, t2, th;
-    int rc = make_tmap_bf16_2d(&t1, W1, static_cast<uint64_t>(ff), static_cast<uint64_t>(d), 32, 64);
+    int rc = make_tmap_bf16_2d(&t1, W1, static_cast<uint64_t>(ff), static_cast<uint64_t>(d), 64, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&t2, W2_packed, static_cast<uint64_t>(d), static_cast<uint64_t>(ff), static_cast<uint32_t>(d / 2), 64);
     if (rc) return rc;
@@ -411,7 +425,8 @@ static int mlp_pair_impl(const void* a, const float* ln_w, const float* ln_b, co
         rc = make_tmap_bf16_2d(&ta, a, static_cast<uint64_t>(M), static_cast<uint64_t>(d), 128, 64);
         if (rc) return rc;
     }
-    mp::Params p{b1, b2, M, ff, h, ln_w, ln_b, gamma_beta, gb_stride, L};
+    static const int dbg = getenv("IDB200_MLP_DBG") ? atoi(getenv("IDB200_MLP_DBG")) : 0;
+    mp::Params p{b1, b2, M, ff, h, ln_w, ln_b, gamma_beta, gb_stride, L, dbg};
     const long long tiles = (M + 127) / 128;
     if (ln) return d == 256 ? mp::launch<4, true>(ta, t1, t2, th, p, tiles, st) : mp::launch<6, true>(ta, t1, t2, th, p, tiles, st);
     return d == 256 ? mp::launch<4, false>(ta, t1, t2, th, p, tiles, st) : mp::launch<6, false>(ta, t1, t2, th, p, tiles, st);

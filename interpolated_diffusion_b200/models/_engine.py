@@ -257,8 +257,9 @@ class PackedEncoder:
             }
             for k in ("wqkv", "wo", "w1", "w2"):
                 e[k] = e[k + "32"].to(torch.bfloat16).contiguous()
-            if d == 384 and e["w1"].shape[0] % 64 == 0 and 128 <= e["w1"].shape[0] <= 2048:
-                e["w2p"] = e["w2"][mlp_pair_w2_order(d, e["w2"].device)].contiguous()      # ff.2 rows as idb200_mlp_pair stages them
+            if d in (256, 384) and e["w1"].shape[0] % 128 == 0 and 128 <= e["w1"].shape[0] <= 2048:
+                # ff.2 rows as idb200_mlp_pair stages them (the identity at d = 256)
+                e["w2p"] = e["w2"] if d == 256 else e["w2"][mlp_pair_w2_order(d, e["w2"].device)].contiguous()
             if d % 64 == 0:
                 # head-group-major in_proj for the fused attention block: group g = [Wq[64g:64g+64]; Wk[..]; Wv[..]]
                 order = torch.cat([torch.arange(64) + part * d + g * 64 for g in range(d // 64) for part in range(3)]).to(e["wqkv"].device)
@@ -365,7 +366,7 @@ class PackedEncoder:
             if not fused:
                 a = self.ws.get("a", (M, d), torch.bfloat16, dev)
                 qkv = None if qkv_attn else self.ws.get("qkv", (M, 3 * d), torch.bfloat16, dev)
-            mlp_pair_ok = (not fuse_mlp) and self.fuse_mlp_pair and "w2p" in self.layers[0]
+            mlp_pair_ok = self.fuse_mlp_pair and "w2p" in self.layers[0]      # (preferred over the single-CTA mlp_fused at d = 256: 0.62 vs 0.83 ms at M = 512 k)
             f = None if (fuse_mlp or mlp_pair_ok) else self.ws.get("f", (M, ff), torch.bfloat16, dev)
             for i, e in enumerate(self.layers):
                 g1 = film[:, 2 * i] if film is not None else None
@@ -388,10 +389,10 @@ class PackedEncoder:
                     ln_mlp_pair(h, e["n2w"], e["n2b"], g2, e["w1"], e["b1"], e["w2p"], e["b2"], Lseq)      # LN + FiLM + FF1 + SiLU + FF2 + residual
                     continue
                 ln_film(h, e["n2w"], e["n2b"], g2, a, Lseq)
-                if fuse_mlp:
-                    mlp_fused(a, e["w1"], e["b1"], e["w2"], e["b2"], h)
-                elif mlp_pair_ok:
+                if mlp_pair_ok:
                     mlp_pair(a, e["w1"], e["b1"], e["w2p"], e["b2"], h)
+                elif fuse_mlp:
+                    mlp_fused(a, e["w1"], e["b1"], e["w2"], e["b2"], h)
                 else:
                     gemm_bf16(a, e["w1"], e["b1"], f, EPI_SILU_BF16)
                     gemm_bf16(f, e["w2"], e["b2"], h, EPI_RESID_F32)

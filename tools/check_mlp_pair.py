@@ -6,7 +6,7 @@ from interpolated_diffusion_b200.models import _engine as E
 
 torch.manual_seed(0)
 dev = "cuda"
-for (M, d, ff) in [(640, 384, 1536), (128, 384, 128), (1000, 384, 192), (4096 + 64, 256, 1024), (131072, 384, 1536), (1048576, 384, 1536), (524288, 256, 1024)]:
+for (M, d, ff) in [(640, 384, 1536), (128, 384, 128), (1000, 384, 384), (4096 + 64, 256, 1024), (131072, 384, 1536), (1048576, 384, 1536), (524288, 256, 1024)]:
     a = torch.randn((M, d), device=dev).bfloat16()
     w1 = (torch.randn((ff, d), device=dev) / d ** 0.5).bfloat16()
     b1 = torch.randn((ff,), device=dev) * 0.1
