@@ -25,6 +25,8 @@ for t in "$@"; do
     gemm_qkv384) prof gemm_qkv384 gemm_bf16_tn 2 ;;
     corrupt_adj) prof corrupt_adj corrupt_adjacent 2 ;;
     ln_bwd)      prof ln_bwd ln_bwd_apply 2 ;;
+    qkv_attn)    prof qkv_attn qkv_attn_kernel 2 ;;
+    mlp_pair)    prof mlp_pair mlp_pair_kernel 2 ;;
     im2col)      prof im2col im2col3x3_scatter 2 ;;
     colsum)      prof colsum colsum_partial_vec 2 ;;
   esac

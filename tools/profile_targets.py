@@ -1,6 +1,6 @@
 """One warm-up + two launches of ONE hot kernel at its bench shape, for `ncu --set full -k regex:<kernel>`:
     python tools/profile_targets.py <target>
-targets: encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
+targets: qkv_attn mlp_pair encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
 import os
 import sys
 
@@ -80,6 +80,26 @@ elif t == "corrupt_adj":
     s_idx = torch.randint(1, 4, (B,), device=dev)
     kw = dict(corrupt_mode="dist", corrupt_sigma_max=0.08, corrupt_sigma_min=0.012, corrupt_sigma_pow=0.75, corrupt_anchor_frac=0.25)
     run(lambda: tr.corrupt_adjacent_fused(x0, masks, s_idx, [64, 32, 16, 8], 8, seed=1, offset=1, **kw))
+elif t == "qkv_attn":
+    B, Lq, d = 16384, 8, 384
+    M = B * Lq
+    a = torch.randn((M, d), device=dev).bfloat16()
+    w = (torch.randn((3 * d, d), device=dev) / d ** 0.5).bfloat16()
+    b = torch.randn((3 * d,), device=dev) * 0.1
+    order = torch.cat([torch.arange(64) + part * d + g * 64 for g in range(d // 64) for part in range(3)]).to(dev)
+    wg, bg = w[order].contiguous(), b[order].contiguous()
+    out = torch.empty_like(a)
+    run(lambda: E.qkv_attention(a, wg, bg, out, Lq, d // 32, False))
+elif t == "mlp_pair":
+    M, d, ff = 16384 * 8, 384, 1536
+    a = torch.randn((M, d), device=dev).bfloat16()
+    w1 = (torch.randn((ff, d), device=dev) / d ** 0.5).bfloat16()
+    b1 = torch.randn((ff,), device=dev) * 0.1
+    w2 = (torch.randn((d, ff), device=dev) / ff ** 0.5).bfloat16()
+    b2 = torch.randn((d,), device=dev) * 0.1
+    h = torch.randn((M, d), device=dev)
+    w2p = w2[E.mlp_pair_w2_order(d, dev)].contiguous()
+    run(lambda: E.mlp_pair(a, w1, b1, w2p, b2, h))
 elif t == "ln_bwd":
     B, Lq, d = 4096, 64, 384
     M = B * Lq
