@@ -826,7 +826,6 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                     const int b = c & 1;
                     const uint32_t ub = (n_p * (b ? uses1 : uses0) + static_cast<uint32_t>(c >> 1)) & 1u;   // uses of buffer b so far
                     mbar_wait(&acc1_full[b], ub, 55);
-                    mbar_wait(&hb_empty[b], ub ^ 1u, 56);               // FF2 of the previous use finished reading H[b]
                     tc_fence_after();
                     stamp(P_WACC1);
                     if (!skip) {
@@ -839,17 +838,21 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                         __syncwarp();                                    // FF1_{c+2} runs under the SiLU / store work of this chunk
                         if (lane == 0) arrive_mma(&acc1_empty[b]);
                         const float* bb = sb1 + c * 128 + part * 32;    // 0.5 * b1 (pre-halved on the host)
+                        uint4 pk[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {                    // 8 columns -> one 16-byte swizzle chunk
                             const float4 b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
                             const float4 b1v = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
-                            uint4 pk;
-                            pk.x = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 0]), b0.x), silu_half(__uint_as_float(r[8 * j + 1]), b0.y));
-                            pk.y = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 2]), b0.z), silu_half(__uint_as_float(r[8 * j + 3]), b0.w));
-                            pk.z = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 4]), b1v.x), silu_half(__uint_as_float(r[8 * j + 5]), b1v.y));
-                            pk.w = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 6]), b1v.z), silu_half(__uint_as_float(r[8 * j + 7]), b1v.w));
-                            *reinterpret_cast<uint4*>(hb + sw128_offset(row, (part & 1) * 32 + j * 8)) = pk;
+                            pk[j].x = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 0]), b0.x), silu_half(__uint_as_float(r[8 * j + 1]), b0.y));
+                            pk[j].y = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 2]), b0.z), silu_half(__uint_as_float(r[8 * j + 3]), b0.w));
+                            pk[j].z = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 4]), b1v.x), silu_half(__uint_as_float(r[8 * j + 5]), b1v.y));
+                            pk[j].w = pack2_bf16(silu_half(__uint_as_float(r[8 * j + 6]), b1v.z), silu_half(__uint_as_float(r[8 * j + 7]), b1v.w));
                         }
+                        mbar_wait(&hb_empty[b], ub ^ 1u, 56);           // FF2 of the previous use finished reading H[b] (only the stores wait)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(hb + sw128_offset(row, (part & 1) * 32 + j * 8)) = pk[j];
+                    } else {
+                        mbar_wait(&hb_empty[b], ub ^ 1u, 56);
                     }
                     tc_fence_before();
                     fence_proxy_async_smem();                            // H writes -> visible to the tensor core
