@@ -8,8 +8,10 @@ from interpolated_diffusion_b200.sample.sample_generate import GenerationConfig,
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384 + 333
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 torch.manual_seed(0)
-kp = KeypointDenoiser(data_dim=2).cuda()
-il = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=2).cuda()
+large = len(sys.argv) > 3 and sys.argv[3] == "large"       # trainer-default models: the pair-mode block kernels (qkv_attention, ln_mlp_pair)
+kw = dict(d_model=384, n_layers=12, n_heads=12, d_ff=1536, maze_channels=(32, 64, 128, 128)) if large else {}
+kp = KeypointDenoiser(data_dim=2, **kw).cuda()
+il = InterpLevelDenoiser(data_dim=2, max_levels=3, mask_channels=2, **kw).cuda()
 cfg = GenerationConfig()
 gen = torch.Generator().manual_seed(1)
 cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float().cuda(), "start_goal": torch.rand((B, 4), generator=gen).cuda()}
