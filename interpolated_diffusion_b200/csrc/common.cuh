@@ -40,6 +40,27 @@ inline int grid_for(int64_t work, int per_cta, int ctas_per_sm) {
     return static_cast<int>(need < cap ? need : cap);
 }
 
+#ifdef __CUDACC__
+// SiLU / SiLU' on the bf16 token tensors of the training step (ff.0 pre-activation u; transformer.py:23-26) with ONE MUFU op:
+// sigmoid(x) = 1/2 + 1/2 tanh(x/2) (tanh.approx: relative error ~2^-11, below the bf16 rounding of what is stored).  Shared by the
+// stand-alone passes (train_bwd.cu) and the GEMM epilogues that fold them in (gemm.cu) so both forms round identically; explicit
+// _rn intrinsics keep ptxas from contracting differently at the two sites.
+__device__ __forceinline__ float tanh_approx(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
+__device__ __forceinline__ float silu16_fwd(float x) {
+    const float h = __fmul_rn(0.5f, x);
+    return __fmaf_rn(h, tanh_approx(h), h);
+}
+__device__ __forceinline__ float silu16_grad(float x) {      // s + x s (1 - s), s = sigmoid(x); 4 s (1 - s) = 1 - tanh^2(x/2)
+    const float h = __fmul_rn(0.5f, x);
+    const float t = tanh_approx(h);
+    return __fmaf_rn(__fmul_rn(0.5f, h), __fmaf_rn(-t, t, 1.0f), __fmaf_rn(0.5f, t, 0.5f));
+}
+#endif
+
 }  // namespace idb200
 
 #define IDB_REQUIRE(cond, code, ...)                          \

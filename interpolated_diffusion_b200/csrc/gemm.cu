@@ -84,7 +84,7 @@ constexpr int kBiasFloats = 2048;       // bias vector staged in shared memory (
 // 4 / 5: training forms with a second bf16 [M,N] tensor `aux` (idb200_gemm_bf16_aux):
 //   EPI_BF16_SILU_DUAL  out = bf16(acc + bias) (the pre-activation u, kept for the backward), aux = bf16(SiLU(out)) -- ff.0 forward
 //   EPI_BF16_DSILU      out = bf16(bf16(acc) * SiLU'(aux)), aux = u read through TMA -- dU = (dY W2) . SiLU'(u) of the backward
-// Both reproduce the separate SiLU kernels of csrc/train_bwd.cu bit for bit (same roundings, x * sigmoid(x) with __expf).
+// Both reproduce the separate SiLU kernels of csrc/train_bwd.cu bit for bit (same roundings, the one-MUFU silu16_* of common.cuh).
 enum { EPI_BF16 = 0, EPI_SILU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3, EPI_BF16_SILU_DUAL = 4, EPI_BF16_DSILU = 5 };
 constexpr int kConvMaxKB = 36;         // k-blocks of the implicit conv: 9 taps x C / 64 (C <= 256)
 
@@ -129,7 +129,6 @@ __device__ __forceinline__ float silu_f(float x) {
     return fmaf(h, t, h);
 }
 
-__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // kMN = false: A [M,K], W [N,K] row-major (K-major operands): out = A W^T.
@@ -151,7 +150,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* acc_full = bars + 2 * Cfg::kStages;           // [kAccStages] MMA -> epilogue
     uint64_t* acc_empty = acc_full + Cfg::kAccStages;       // [kAccStages] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::kAccStages);
-    uint64_t* aux_bar = acc_empty + Cfg::kAccStages + 1;   // [2] EPI_BF16_DSILU: the u slab of an epilogue half has landed
+    uint64_t* aux_bar = acc_empty + Cfg::kAccStages + 1;   // [2 halves x 2 buffers] EPI_BF16_DSILU: a u slab has landed
     float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
     uint8_t* staging = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem + Cfg::kStages * Cfg::kStageBytes + 256 + kBiasFloats * 4) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -177,8 +176,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPair ? 16 : 8); }
-        mbar_init(&aux_bar[0], 1);
-        mbar_init(&aux_bar[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&aux_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -286,7 +284,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t slab_it = 0;
-        uint32_t aux_phase = 0;
+        const bool leader = q == 0 && lane == 0;               // issues this half's TMA stores / aux loads
+        // EPI_BF16_DSILU: the u slab of (tile t, slab sl) of this half lands in staging buffer (it & 1) of the half
+        auto aux_issue = [&](long long t, int sl, uint32_t it) {
+            const long long mn_ = t % mn_tiles;
+            const int m0_ = static_cast<int>(mn_ / n_tiles) * kMRows + static_cast<int>(rank) * kBM;
+            const int n0_ = static_cast<int>(mn_ % n_tiles) * BN;
+            uint64_t* bar = &aux_bar[half * 2 + (it & 1)];
+            mbar_arrive_expect_tx(bar, 16384);
+            tma_load_2d(staging + half * 2 * 16384 + (it & 1) * 16384, &tmap_aux, bar, n0_ + sl * 64, m0_);
+        };
+        if (p.epilogue == EPI_BF16_DSILU && leader && tile0 < tiles && half < BN / 64) aux_issue(tile0, half, 0);
         for (long long tile = tile0; tile < tiles; tile += tile_stride) {
             const long long mn = tile % mn_tiles;
             const long long m0 = (mn / n_tiles) * kMRows + static_cast<long long>(rank) * kBM;
@@ -301,32 +309,119 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int y = pos / p.conv_PW, x = pos - y * p.conv_PW;
                 border = y == 0 || y == p.conv_PH - 1 || x == 0 || x == p.conv_PW - 1;
             }
-            if (p.tma_out) {
+            if (p.tma_out && p.epilogue >= EPI_BF16_SILU_DUAL) {
+                // Training forms with the MLP's SiLU pass folded in (one TMEM read per element, one-MUFU SiLU / SiLU').  First
+                // revision: two staging passes per slab with exp + IEEE division and, for SiLU', a TMA load of the u slab issued
+                // and awaited inside the slab: the step got 10 % SLOWER than with the separate HBM-bound passes (ALU-issue bound
+                // epilogue + one exposed HBM round trip per slab).  Now:
+                //   4: both outputs of a slab are staged at once (u -> buffer 0, SiLU(u) -> buffer 1 of the half), two TMA stores;
+                //   5: the u slab of the NEXT slab (possibly of the next tile) is requested half a slab ahead into the other
+                //      buffer, SiLU' is applied in place over the landed u slab.
+                // The buffers are released by cp.async.bulk.wait_group.read after the first half of a slab's math, when the
+                // previous slab's stores have long read them.
+                const int n_slabs = BN / 64;
+                const int r_in = q * 32 + lane;
+                uint8_t* stage_h = staging + half * 2 * 16384;
+                for (int sl = half; sl < n_slabs; sl += 2) {
+                    const bool dual = p.epilogue == EPI_BF16_SILU_DUAL;
+                    uint8_t* buf0 = dual ? stage_h : stage_h + (slab_it & 1) * 16384;
+                    uint8_t* buf1 = stage_h + 16384;                      // dual only: SiLU(u)
+                    if (!dual) mbar_wait(&aux_bar[half * 2 + (slab_it & 1)], (slab_it >> 1) & 1, 6);
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = sl * 64 + cc * 32;
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + c, r);
+                        tmem_ld_wait();
+                        uint4 pk0[4], pk1[4];
+                        if (dual) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float v[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[8 * j + k]);
+                                if (bias_smem) {
+                                    const float4 b0 = *reinterpret_cast<const float4*>(&sbias[n0 + c + 8 * j]);
+                                    const float4 b1 = *reinterpret_cast<const float4*>(&sbias[n0 + c + 8 * j + 4]);
+                                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                                } else if (p.bias) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) v[k] += __ldg(p.bias + n0 + c + 8 * j + k);
+                                }
+                                uint32_t* w0 = reinterpret_cast<uint32_t*>(&pk0[j]);
+                                uint32_t* w1 = reinterpret_cast<uint32_t*>(&pk1[j]);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 u2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                                    const float2 uf = __bfloat1622float2(u2);
+                                    const __nv_bfloat162 f2 = __floats2bfloat162_rn(silu16_fwd(uf.x), silu16_fwd(uf.y));
+                                    w0[k] = *reinterpret_cast<const uint32_t*>(&u2);
+                                    w1[k] = *reinterpret_cast<const uint32_t*>(&f2);
+                                }
+                            }
+                            if (cc == 0) {
+                                if (leader) tma_store_wait_read<0>();           // the previous slab's two stores are done with the buffers
+                                named_barrier_sync(1 + half, 128);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int off = r_in * 128 + (((cc * 4 + j) ^ (r_in & 7)) << 4);
+                                *reinterpret_cast<uint4*>(buf0 + off) = pk0[j];
+                                *reinterpret_cast<uint4*>(buf1 + off) = pk1[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int off = r_in * 128 + (((cc * 4 + j) ^ (r_in & 7)) << 4);
+                                const uint4 uu = *reinterpret_cast<const uint4*>(buf0 + off);
+                                const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&uu);
+                                uint32_t* w0 = reinterpret_cast<uint32_t*>(&pk0[j]);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float2 uf = __bfloat1622float2(u2[k]);
+                                    const float g0 = bf16_round(__uint_as_float(r[8 * j + 2 * k]));
+                                    const float g1 = bf16_round(__uint_as_float(r[8 * j + 2 * k + 1]));
+                                    const __nv_bfloat162 o2 = __floats2bfloat162_rn(__fmul_rn(g0, silu16_grad(uf.x)), __fmul_rn(g1, silu16_grad(uf.y)));
+                                    w0[k] = *reinterpret_cast<const uint32_t*>(&o2);
+                                }
+                                *reinterpret_cast<uint4*>(buf0 + off) = pk0[j];
+                            }
+                            if (cc == 0 && leader) {                            // request the next slab's u into the other buffer
+                                int nsl = sl + 2;
+                                long long nt = tile;
+                                if (nsl >= n_slabs) { nsl = half; nt = tile + tile_stride; }
+                                if (nt < tiles) {
+                                    tma_store_wait_read<0>();                   // the previous slab's store is done reading it
+                                    aux_issue(nt, nsl, slab_it + 1);
+                                }
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_barrier_sync(3 + half, 128);
+                    if (leader) {
+                        tma_store_2d(&tmap_out, buf0, n0 + sl * 64, static_cast<int>(m0));
+                        if (dual) tma_store_2d(&tmap_aux, buf1, n0 + sl * 64, static_cast<int>(m0));
+                        tma_store_commit();
+                    }
+                    ++slab_it;
+                }
+            } else if (p.tma_out) {
                 // Coalesced epilogue.  A thread owns one ROW of the accumulator (tcgen05.ld 32x32b), so direct stores touch 32
                 // different lines per instruction: measured, they (not the MMAs) bounded the kernel at ~45 % of its store-less
                 // speed.  Instead each half (4 warps = 128 rows) fills a 16 KB slab (64 bf16 / 32 fp32 columns, SWIZZLE_128B
                 // rows) in shared memory and one thread hands it to TMA (store, or reduce-add for the residual epilogue); two
                 // slabs per half ping-pong so the conversion of slab i+1 overlaps the store of slab i.
-                const bool out16 = p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16 || p.epilogue >= EPI_BF16_SILU_DUAL;
+                const bool out16 = p.epilogue == EPI_BF16 || p.epilogue == EPI_SILU_BF16;
                 const int slab_cols = out16 ? 64 : 32;
                 const int n_slabs = BN / slab_cols;
                 const int r_in = q * 32 + lane;
                 uint8_t* stage_h = staging + half * 2 * 16384;
-                const int passes = p.epilogue == EPI_BF16_SILU_DUAL ? 2 : 1;
-                // dual-output form: each slab is staged twice (pass 0: pre-activation -> out, pass 1: SiLU -> aux)
-                for (int sl = half; sl < n_slabs; sl += 2)
-                for (int pass = 0; pass < passes; ++pass) {
+                for (int sl = half; sl < n_slabs; sl += 2) {
                     uint8_t* buf = stage_h + (slab_it & 1) * 16384;
                     if (q == 0 && lane == 0) tma_store_wait_read<1>();          // the store that last read `buf` is done with it
                     named_barrier_sync(1 + half, 128);
-                    if (p.epilogue == EPI_BF16_DSILU) {                        // bring the u slab in (same box as the output slab)
-                        if (q == 0 && lane == 0) {
-                            mbar_arrive_expect_tx(&aux_bar[half], 16384);
-                            tma_load_2d(buf, &tmap_aux, &aux_bar[half], n0 + sl * slab_cols, static_cast<int>(m0));
-                        }
-                        mbar_wait(&aux_bar[half], aux_phase, 6);
-                        aux_phase ^= 1;
-                    }
                     const int nch = out16 ? 2 : 1;
                     for (int cc = 0; cc < nch; ++cc) {
                         const int c = sl * slab_cols + cc * 32;
@@ -350,23 +445,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             if (p.epilogue == EPI_SILU_BF16) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-                            } else if (p.epilogue == EPI_BF16_SILU_DUAL && pass == 1) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) { const float u = bf16_round(v[j]); v[j] = u * sigmoid_exact(u); }
-                            } else if (p.epilogue == EPI_BF16_DSILU) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int piece = cc * 4 + j;
-                                    const uint4 uu = *reinterpret_cast<const uint4*>(buf + r_in * 128 + ((piece ^ (r_in & 7)) << 4));
-                                    const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&uu);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const float2 uf = __bfloat1622float2(u2[k]);
-                                        const float s0 = sigmoid_exact(uf.x), s1 = sigmoid_exact(uf.y);
-                                        v[8 * j + 2 * k] = bf16_round(v[8 * j + 2 * k]) * (s0 * (1.0f + uf.x * (1.0f - s0)));
-                                        v[8 * j + 2 * k + 1] = bf16_round(v[8 * j + 2 * k + 1]) * (s1 * (1.0f + uf.y * (1.0f - s1)));
-                                    }
-                                }
                             }
                             if (border) {
 #pragma unroll
@@ -397,7 +475,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     named_barrier_sync(3 + half, 128);
                     if (q == 0 && lane == 0) {
                         if (p.epilogue == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, buf, n0 + sl * slab_cols, static_cast<int>(m0));
-                        else if (pass == 1) tma_store_2d(&tmap_aux, buf, n0 + sl * slab_cols, static_cast<int>(m0));
                         else tma_store_2d(&tmap_out, buf, n0 + sl * slab_cols, static_cast<int>(m0));
                         tma_store_commit();
                     }

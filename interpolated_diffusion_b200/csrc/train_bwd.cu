@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// SiLU forward / backward on bf16 pairs.  mode 0: y = silu(u);  mode 1: y = g * silu'(u).
+// SiLU forward / backward on bf16 pairs.  mode 0: y = silu(u);  mode 1: y = g * silu'(u).  One-MUFU forms of common.cuh (the GEMM
+// epilogues of gemm.cu that fold these passes in use the same functions: bit-identical results either way).
 __global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat162* __restrict__ u, const __nv_bfloat162* g, long long n2,
                                                    int mode, __nv_bfloat162* y) {   // y may alias g
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -183,10 +184,10 @@ __global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat162* __restr
         const float2 uv = __bfloat1622float2(u[i]);
         float2 o;
         if (mode == 0) {
-            o = make_float2(silu_fwd(uv.x), silu_fwd(uv.y));
+            o = make_float2(silu16_fwd(uv.x), silu16_fwd(uv.y));
         } else {
             const float2 gv = __bfloat1622float2(g[i]);
-            o = make_float2(gv.x * silu_grad(uv.x), gv.y * silu_grad(uv.y));
+            o = make_float2(__fmul_rn(gv.x, silu16_grad(uv.x)), __fmul_rn(gv.y, silu16_grad(uv.y)));
         }
         y[i] = __floats2bfloat162_rn(o.x, o.y);
     }
@@ -205,10 +206,10 @@ __global__ void __launch_bounds__(256) silu_vec_kernel(const uint4* __restrict__
             const float2 a = __bfloat1622float2(u2[j]);
             float2 o;
             if (mode == 0) {
-                o = make_float2(silu_fwd(a.x), silu_fwd(a.y));
+                o = make_float2(silu16_fwd(a.x), silu16_fwd(a.y));
             } else {
                 const float2 b = __bfloat1622float2(g2[j]);
-                o = make_float2(b.x * silu_grad(a.x), b.y * silu_grad(a.y));
+                o = make_float2(__fmul_rn(b.x, silu16_grad(a.x)), __fmul_rn(b.y, silu16_grad(a.y)));
             }
             u2[j] = __floats2bfloat162_rn(o.x, o.y);
         }

@@ -38,14 +38,17 @@ EPI_BF16_SILU_DUAL, EPI_BF16_DSILU = 4, 5
 
 
 def gemm_bf16_aux(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, aux: torch.Tensor, epilogue: int,
-                  fused: bool = False) -> torch.Tensor:
-    """The token GEMM + the MLP's SiLU pass (4: out = u, aux = SiLU(u); 5: out = (A W^T) * SiLU'(aux)).
-    ``fused=True`` (or IDB200_TRAIN_FUSED_SILU=1) folds the SiLU pass into the GEMM epilogue (idb200_gemm_bf16_aux), bit-identical
-    to the two-launch form.  MEASURED AND REJECTED as the default: the tcgen05 GEMM is bound by its epilogue, and the
-    extra MUFU work / second staging pass there costs more than the separate HBM-bound pass saves -- cfg-4 step 17.1 ms with the
-    two launches, 19.2 ms fused (B = 512 per GPU)."""
+                  fused: Optional[bool] = None) -> torch.Tensor:
+    """The token GEMM + the MLP's SiLU pass (4: out = u, aux = SiLU(u); 5: out = (A W^T) * SiLU'(aux)) as ONE launch
+    (idb200_gemm_bf16_aux), bit-identical to the two-launch form (``fused=False`` or IDB200_TRAIN_FUSED_SILU=0: token GEMM, then
+    idb200_silu_bf16 -- kept as the cross-check).  History: the first fused epilogue (exp + IEEE division, two staging passes, the
+    u slab fetched and awaited inside each slab) made the cfg-4 step 10 % SLOWER than the separate HBM-bound passes; with one-MUFU
+    SiLU / SiLU', both outputs staged from one TMEM read and the u slab requested half a slab ahead, the fused GEMMs take 0.41 /
+    0.44 ms at M = 262 144 (plain GEMM 0.29 + pass 0.34) and the B = 4096 step went 94.2 -> 90.4 ms."""
     M, K = A.shape
-    if not (fused or os.environ.get("IDB200_TRAIN_FUSED_SILU")):
+    if fused is None:
+        fused = os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0"
+    if not fused:
         E.gemm_bf16(A, W, bias, out, E.EPI_BF16)
         return silu_bf16(out, aux) if epilogue == EPI_BF16_SILU_DUAL else silu_bf16(aux, out, g=out)
     L.call("idb200_gemm_bf16_aux", A.data_ptr(), W.data_ptr(), L.ptr(bias), out.data_ptr(), aux.data_ptr(), M, W.shape[0], K, epilogue,

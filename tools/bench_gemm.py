@@ -13,9 +13,14 @@ for (M, N, K, epi) in SHAPES:
     A = torch.randn((M, K), device="cuda").bfloat16()
     W = torch.randn((N, K), device="cuda").bfloat16()
     bias = torch.randn((N,), device="cuda")
-    out = torch.zeros((M, N), device="cuda", dtype=torch.float32 if epi >= 2 else torch.bfloat16)
+    out = torch.zeros((M, N), device="cuda", dtype=torch.float32 if epi in (2, 3) else torch.bfloat16)
+    aux = torch.randn((M, N), device="cuda").bfloat16() if epi >= 4 else None      # epilogues 4 / 5: the training forms with SiLU folded in
     def run():
-        L.call("idb200_gemm_bf16", A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, epi, L.stream(A.device))
+        if aux is not None:
+            L.call("idb200_gemm_bf16_aux", A.data_ptr(), W.data_ptr(), bias.data_ptr() if epi == 4 else None, out.data_ptr(), aux.data_ptr(), M, N, K, epi,
+                   L.stream(A.device))
+        else:
+            L.call("idb200_gemm_bf16", A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, epi, L.stream(A.device))
     for _ in range(3): run()
     torch.cuda.synchronize()
     it = 10
@@ -25,7 +30,7 @@ for (M, N, K, epi) in SHAPES:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / it
     flops = 2.0 * M * N * K
-    byts = M * K * 2 + N * K * 2 + M * N * (2 if epi < 2 else (8 if epi == 2 else 4))
+    byts = M * K * 2 + N * K * 2 + M * N * {0: 2, 1: 2, 2: 8, 3: 4, 4: 4, 5: 4}[epi]
     # torch reference (cuBLAS) for context
     for _ in range(2): torch.matmul(A, W.t())
     torch.cuda.synchronize(); e0.record()
@@ -33,5 +38,5 @@ for (M, N, K, epi) in SHAPES:
     e1.record(); torch.cuda.synchronize()
     ms_t = e0.elapsed_time(e1) / it
     res[f"{M}x{N}x{K}/epi{epi}"] = {"ms": ms, "TFLOPs": flops / ms / 1e9, "GBps": byts / ms / 1e6, "cublas_ms": ms_t, "cublas_TFLOPs": flops / ms_t / 1e9}
-    del A, W, out
+    del A, W, out, aux
 print(json.dumps(res, indent=1))
