@@ -248,6 +248,10 @@ int idb200_embed_tokens(const float* src0, int n0, const float* src1, int n1, co
  * gamma_beta row b = [gamma (d) | beta (d)] at stride gb_stride (NULL: no FiLM); out bf16 or fp32 [M,d]. */
 int idb200_ln_film(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
                    void* out, int out_is_bf16, int64_t M, int L, int d, idb200_stream_t stream);
+/* Training-forward form: the same, and the residual rows it read are also written to h_copy [M,d] fp32 (16-byte aligned, != h) --
+ * what loss.backward() keeps of the LayerNorm input (train_interp_levels.py:1142-1161) without a second read of h. */
+int idb200_ln_film_save(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                        void* out, int out_is_bf16, float* h_copy, int64_t M, int L, int d, idb200_stream_t stream);
 
 /* output head y[M,D] = h[M,d] . W[D,d]^T + bias (D <= 4; the `out` Linear of both denoisers). */
 int idb200_out_head(const float* h, const float* W, const float* bias, float* y, int64_t M, int d, int D,

@@ -42,6 +42,7 @@ _SIGS = {
     "idb200_sinusoid": [c_p, c_i, c_i, c_i, c_p, c_p],
     "idb200_embed_tokens": [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_p],
     "idb200_ln_film": [c_p, c_p, c_p, c_p, c_l, c_p, c_i, c_l, c_i, c_i, c_p],
+    "idb200_ln_film_save": [c_p, c_p, c_p, c_p, c_l, c_p, c_i, c_p, c_l, c_i, c_i, c_p],
     "idb200_out_head": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_p],
     "idb200_attention": [c_p, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_p],
     "idb200_mlp_fused": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_p],

@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(256, 3) embed_traj_kernel(const EmbedParams p)
 template <typename TO, int VPL>
 __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ h, const float* __restrict__ lnw,
                                                       const float* __restrict__ lnb, const float* __restrict__ gb,
-                                                      long long gb_stride, TO* __restrict__ out, long long M, int L, int d) {
+                                                      long long gb_stride, TO* __restrict__ out, long long M, int L, int d,
+                                                      float* __restrict__ hcopy = nullptr) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(256) ln_film_kernel(const float* __restrict__ 
             const int c4 = lane + 32 * i;
             if (c4 * 4 < d) {
                 v[i] = row[c4];
+                if (hcopy) reinterpret_cast<float4*>(hcopy + m * d)[c4] = v[i];
                 sum += v[i].x + v[i].y + v[i].z + v[i].w;
             }
         }
@@ -435,7 +437,11 @@ __device__ __forceinline__ void ln_mbar_wait(uint64_t* bar, uint32_t parity) {
 template <typename TO, int VPL, bool kExact>
 __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float* __restrict__ h, const float* __restrict__ lnw,
                                                                   const float* __restrict__ lnb, const float* __restrict__ gb,
-                                                                  long long gb_stride, TO* __restrict__ out, long long M, int L, int d) {
+                                                                  long long gb_stride, TO* __restrict__ out, long long M, int L, int d,
+                                                                  float* __restrict__ hcopy) {
+    // hcopy != nullptr (training forward): the staged residual rows also go back out as a copy (the backward's saved h), one
+    // cp.async.bulk shared -> global per chunk issued by the thread that fills the ring: no registers, no LSU instructions, and
+    // the separate device-to-device copy (a second read of h) is gone.
     extern __shared__ __align__(128) unsigned char ln_smem[];
     const size_t stage_floats = static_cast<size_t>(kLnRows) * d + static_cast<size_t>(kLnFilmRows) * 2 * d;
     float* ring = reinterpret_cast<float*>(ln_smem);
@@ -484,6 +490,14 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float
         const int stage = static_cast<int>(it % kLnStages);
         ln_mbar_wait(&full[stage], static_cast<uint32_t>((it / kLnStages) & 1));
         const float* tile = ring + stage * stage_floats;
+        if (hcopy != nullptr && threadIdx.x == 0) {
+            const long long r0 = chunk * kLnRows;
+            const long long rows = (M - r0 < kLnRows) ? (M - r0) : kLnRows;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(hcopy + r0 * d)),
+                         "r"(static_cast<uint32_t>(__cvta_generic_to_shared(tile))), "r"(static_cast<uint32_t>(rows * d * 4))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         const float* film = tile + static_cast<size_t>(kLnRows) * d;
         const int r = warp;
         const long long m = chunk * kLnRows + r;
@@ -555,10 +569,14 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_film_bulk_kernel(const float
         }
         __syncthreads();                                         // every warp is done reading this stage
         const long long nxt = chunk + static_cast<long long>(kLnStages) * gridDim.x;
-        if (threadIdx.x == 0 && nxt < chunks) issue(nxt, stage);
+        if (threadIdx.x == 0) {
+            if (hcopy != nullptr) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the copy-out has read this stage
+            if (nxt < chunks) issue(nxt, stage);
+        }
         rem += step_rem;
         if (rem >= L) rem -= L;
     }
+    if (hcopy != nullptr && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -691,11 +709,12 @@ extern "C" int idb200_embed_tokens(const float* src0, int n0, const float* src1,
     return check_launch("embed_kernel");
 }
 
-extern "C" int idb200_ln_film(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
-                              int64_t gb_stride, void* out, int out_is_bf16, int64_t M, int L, int d, idb200_stream_t stream) {
+static int ln_film_impl(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride, void* out,
+                        int out_is_bf16, int64_t M, int L, int d, float* h_copy, idb200_stream_t stream) {
     IDB_REQUIRE(M >= 0 && L >= 1 && d >= 4 && d % 4 == 0 && d <= 512, IDB200_EUNSUPPORTED, "d must be a multiple of 4, <= 512");
     if (M == 0) return IDB200_OK;
     IDB_REQUIRE(h && ln_w && ln_b && out, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(!h_copy || (aligned(h_copy, 16) && h_copy != h), IDB200_EALIGN, "h_copy must be 16-byte aligned and distinct from h");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool bulk_env = !(getenv("IDB200_LN_BULK") && atoi(getenv("IDB200_LN_BULK")) == 0);
     if (bulk_env && d % 4 == 0 && aligned(h, 16) && (!gamma_beta || aligned(gamma_beta, 16)) && M >= 4096) {
@@ -714,11 +733,11 @@ extern "C" int idb200_ln_film(const float* h, const float* ln_w, const float* ln
         if (d == VPL * 128) {                                                                                                      \
             int rc_ = run(ln_film_bulk_kernel<TO, VPL, true>);                                                                     \
             if (rc_) return rc_;                                                                                                   \
-            ln_film_bulk_kernel<TO, VPL, true><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d); \
+            ln_film_bulk_kernel<TO, VPL, true><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d, h_copy); \
         } else {                                                                                                                   \
             int rc_ = run(ln_film_bulk_kernel<TO, VPL, false>);                                                                    \
             if (rc_) return rc_;                                                                                                   \
-            ln_film_bulk_kernel<TO, VPL, false><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d); \
+            ln_film_bulk_kernel<TO, VPL, false><<<grid_b, kLnThreads, smem, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<TO*>(out), M, L, d, h_copy); \
         }                                                                                                                          \
     } while (0)
         if (out_is_bf16) {
@@ -730,9 +749,20 @@ extern "C" int idb200_ln_film(const float* h, const float* ln_w, const float* ln
         return check_launch("ln_film_bulk_kernel");
     }
     const int grid = warp_grid(M);
-    if (out_is_bf16) ln_film_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<__nv_bfloat16*>(out), M, L, d);
-    else ln_film_kernel<float, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<float*>(out), M, L, d);
+    if (out_is_bf16) ln_film_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<__nv_bfloat16*>(out), M, L, d, h_copy);
+    else ln_film_kernel<float, 4><<<grid, 256, 0, st>>>(h, ln_w, ln_b, gamma_beta, gb_stride, static_cast<float*>(out), M, L, d, h_copy);
     return check_launch("ln_film_kernel");
+}
+
+extern "C" int idb200_ln_film(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta,
+                              int64_t gb_stride, void* out, int out_is_bf16, int64_t M, int L, int d, idb200_stream_t stream) {
+    return ln_film_impl(h, ln_w, ln_b, gamma_beta, gb_stride, out, out_is_bf16, M, L, d, nullptr, stream);
+}
+
+extern "C" int idb200_ln_film_save(const float* h, const float* ln_w, const float* ln_b, const float* gamma_beta, int64_t gb_stride,
+                                   void* out, int out_is_bf16, float* h_copy, int64_t M, int L, int d, idb200_stream_t stream) {
+    IDB_REQUIRE(h_copy != nullptr, IDB200_EINVAL, "h_copy is NULL (use idb200_ln_film)");
+    return ln_film_impl(h, ln_w, ln_b, gamma_beta, gb_stride, out, out_is_bf16, M, L, d, h_copy, stream);
 }
 
 extern "C" int idb200_out_head(const float* h, const float* W, const float* bias, float* y, int64_t M, int d, int D,

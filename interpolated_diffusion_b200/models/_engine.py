@@ -166,8 +166,13 @@ def sinusoid(rows: int, dim: int, device, args: Optional[torch.Tensor] = None) -
     return out
 
 
-def ln_film(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], out: torch.Tensor, Lseq: int) -> torch.Tensor:
+def ln_film(h: torch.Tensor, ln_w, ln_b, gb: Optional[torch.Tensor], out: torch.Tensor, Lseq: int, h_copy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = LN(h) * (1 + gamma) + beta; ``h_copy`` (fp32 [M, d]) also receives the rows of h that were read (training forward)."""
     M, d = h.shape
+    if h_copy is not None:
+        L.call("idb200_ln_film_save", h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), L.ptr(gb), 0 if gb is None else gb.stride(0),
+               out.data_ptr(), int(out.dtype == torch.bfloat16), h_copy.data_ptr(), M, Lseq, d, L.stream(h.device))
+        return out
     L.call("idb200_ln_film", h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), L.ptr(gb), 0 if gb is None else gb.stride(0),
            out.data_ptr(), int(out.dtype == torch.bfloat16), M, Lseq, d, L.stream(h.device))
     return out
@@ -456,7 +461,7 @@ def conv_stack_gemm(x: torch.Tensor, weights: List[torch.Tensor], biases: List[t
                     chunk: int = 4096):
     """MazeEncoder conv stack (encoders.py:15-24) of any depth as im2col + tcgen05 GEMM on NHWC bf16 PRE-activations (SiLU is
     applied when the next layer gathers its patches / by the pooling kernel).  x fp32 [B, C0, H, W] -> pooled fp32 [B, C_last].
-    keep=True also returns (x0 NHWC bf16, [u_l]) for the backward (training batches fit one chunk); otherwise the batch is
+    keep=True also returns (x0 NHWC bf16, [u_l], weight matrices, [patch matrix of layer l]) for the backward (training batches fit one chunk); otherwise the batch is
     processed in chunks so the patch matrix stays bounded (4096 trajectories x 441 x 9 C x 2 B)."""
     B, C0, Hh, Ww = x.shape
     dev = x.device
@@ -468,13 +473,18 @@ def conv_stack_gemm(x: torch.Tensor, weights: List[torch.Tensor], biases: List[t
     if keep:
         chunk = B
     us_all = []
+    cols = []
     for lo in range(0, B, chunk):
         n = min(chunk, B - lo)
         src, C = x0[lo:lo + n], C0
         us = []
         for li, (wm, b) in enumerate(zip(wms, biases)):
-            col = ws.get("col", (n * P, wm.shape[1]), torch.bfloat16, dev)
+            # keep: one patch matrix per layer, handed to the backward (its weight-gradient GEMM reads the same patches: 4 of the
+            # 11 im2col launches of a training step were rebuilding them)
+            col = ws.get(f"col_keep{li}" if keep else "col", (n * P, wm.shape[1]), torch.bfloat16, dev)
             im2col3x3(src, n, Hh, Ww, C, li > 0, col)
+            if keep:
+                cols.append(col)
             co = wm.shape[0]
             u = torch.empty((n * P, co), device=dev, dtype=torch.bfloat16) if keep else ws.get(f"u{li % 2}", (n * P, co), torch.bfloat16, dev)
             gemm_bf16(col, wm, b, u, EPI_BF16)
@@ -483,7 +493,7 @@ def conv_stack_gemm(x: torch.Tensor, weights: List[torch.Tensor], biases: List[t
         L.call("idb200_pool_silu", src.data_ptr(), n, P, C, pooled[lo:lo + n].data_ptr(), L.stream(dev))
         us_all = us
     if keep:
-        return pooled, x0, us_all, wms
+        return pooled, x0, us_all, wms, cols
     return pooled
 
 

@@ -101,7 +101,7 @@ class KeypointSelector(nn.Module):
             feats.append(m)
         x = torch.cat(feats, dim=1)
         convs = [c for c in self.spatial_conv if isinstance(c, nn.Conv2d)]
-        _, _, us, _ = E.conv_stack_gemm(x, [c.weight for c in convs], [f(c.bias) for c in convs], self._ws, keep=True)
+        _, _, us, _, _ = E.conv_stack_gemm(x, [c.weight for c in convs], [f(c.bias) for c in convs], self._ws, keep=True)
         P = Hh * Ww
         act = torch.empty_like(us[-1])                                   # SiLU of the last conv layer: the spatial features [B*P, C]
         L.call("idb200_silu_bf16", us[-1].data_ptr(), None, act.numel(), 0, act.data_ptr(), L.stream(dev))

@@ -47,7 +47,7 @@ def gemm_bf16_aux(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]
     0.44 ms at M = 262 144 (plain GEMM 0.29 + pass 0.34) and the B = 4096 step went 94.2 -> 90.4 ms."""
     M, K = A.shape
     if fused is None:
-        fused = os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0"
+        fused = os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0" and W.shape[0] % 64 == 0      # the aux epilogues stage 64-column slabs
     if not fused:
         E.gemm_bf16(A, W, bias, out, E.EPI_BF16)
         return silu_bf16(out, aux) if epilogue == EPI_BF16_SILU_DUAL else silu_bf16(aux, out, g=out)
@@ -183,13 +183,11 @@ class EncoderBackprop:
         for i, w in enumerate(W):
             g1 = film[:, 2 * i] if film is not None else None
             g2 = film[:, 2 * i + 1] if film is not None else None
-            sv["h_in"][i].copy_(h)
-            E.ln_film(h, w["n1w"], w["n1b"], g1, sv["a1"][i], Lseq)
+            E.ln_film(h, w["n1w"], w["n1b"], g1, sv["a1"][i], Lseq, h_copy=sv["h_in"][i])      # also saves the rows it read
             E.gemm_bf16(sv["a1"][i], w["wqkv16"], w["bqkv"], sv["qkv"][i], E.EPI_BF16)
             E.attention(sv["qkv"][i], sv["o"][i], B, Lseq, H, causal)
             E.gemm_bf16(sv["o"][i], w["wo16"], w["bo"], h, E.EPI_RESID_F32)
-            sv["h_mid"][i].copy_(h)
-            E.ln_film(h, w["n2w"], w["n2b"], g2, sv["a2"][i], Lseq)
+            E.ln_film(h, w["n2w"], w["n2b"], g2, sv["a2"][i], Lseq, h_copy=sv["h_mid"][i])
             # ff.0 with both outputs from one epilogue: u (pre-activation, for the backward) and f = SiLU(u)
             gemm_bf16_aux(sv["a2"][i], w["w116"], w["b1"], sv["u"][i], sv["f"][i], EPI_BF16_SILU_DUAL)
             E.gemm_bf16(sv["f"][i], w["w216"], w["b2"], h, E.EPI_RESID_F32)
@@ -352,7 +350,7 @@ class CondEncoderBackprop:
         B, _, Hh, Ww = x.shape
         convs = [c for c in m.maze.convs if isinstance(c, torch.nn.Conv2d)]
         self.dims = (B, Hh, Ww)
-        self.pooled, self.x0, self.us, self.wmats = E.conv_stack_gemm(
+        self.pooled, self.x0, self.us, self.wmats, self.cols = E.conv_stack_gemm(
             x, [c.weight for c in convs], [c.bias.detach().float().contiguous() for c in convs], self.sc.ws, keep=True)
         emb = E.sgemm(self.pooled, m.maze.fc.weight.detach().float().contiguous(), m.maze.fc.bias.detach().float().contiguous())
         if m.use_start_goal:
@@ -382,8 +380,7 @@ class CondEncoderBackprop:
         for li in range(n - 1, -1, -1):
             seq_idx, c = convs[li]
             co, ci = c.weight.shape[0], c.weight.shape[1]
-            src = self.x0 if li == 0 else self.us[li - 1]
-            col = self._col(src, B, Hh, Ww, ci, li > 0, "col")
+            col = self.cols[li]                                 # the forward's patch matrix of this layer
             kpad = col.shape[1]
             dwm = ws.get("dwm", (co, kpad), F32, dev)
             sc.dweight(du, col, dwm)
