@@ -445,6 +445,10 @@ int idb200_ln_film_bwd2(const void* da, int da_is_bf16, const float* h, const fl
  * force_simt != 0 selects the fp32 shared-memory kernel that serves L <= 32. */
 int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, int force_simt,
                          idb200_stream_t stream);
+/* The same (tensor-core kernel, 32 < L <= 64) + traj_colsum [B, 3d] fp32: per-trajectory sums over the tokens of the bf16 dqkv rows.
+ * Their sum over B is the in_proj bias gradient (nn.MultiheadAttention inside transformer.py:39) without re-reading dqkv. */
+int idb200_attention_bwd_sums(const void* qkv, const void* dO, void* dqkv, float* traj_colsum, int64_t B, int L, int H, int causal,
+                              idb200_stream_t stream);
 /* dh[M,d] = dy[M,D] * W[D,d] (out head backward, D <= 8), plus an optional bf16 copy. */
 int idb200_head_bwd(const float* dy, const float* W, int64_t M, int d, int D, float* dh, void* dh_bf16, idb200_stream_t stream);
 /* out[n,K] (+)= A[M,n]^T * X[M,K], n <= 8 (out-head / in_proj weight gradients); scratch: ..._scratch_floats(M, n, K). */

@@ -73,6 +73,7 @@ _SIGS = {
     "idb200_ln_film_bwd": [c_p, c_p, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_p, c_p, c_p, c_l, c_p, c_p, c_p],
     "idb200_ln_film_bwd2": [c_p, c_i, c_p, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_p, c_p, c_p, c_l, c_p, c_i, c_p, c_p],
     "idb200_attention_bwd": [c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p],
+    "idb200_attention_bwd_sums": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
     "idb200_head_bwd": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "idb200_narrow_outer_scratch_floats": [c_l, c_i, c_i],
     "idb200_narrow_outer": [c_p, c_i, c_p, c_l, c_i, c_p, c_i, c_p, c_p],

@@ -685,11 +685,17 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<unsigned*>(&v);
 }
 
+//   Output: the three [64 x 32] gradient tiles are staged in shared memory (dQ over the K tile, dV over the V tile -- both dead after
+//   phase 1 --, dK in its own tile) and leave as 16-byte vectors, 64 contiguous bytes per row and part (the first revision stored
+//   4-byte fragments straight from the accumulators: 16-byte pieces per row and instruction).  colsum != nullptr: the staged tiles
+//   also yield colsum[b, part * d + head * 32 + c] = sum over the trajectory's tokens of the bf16-rounded gradient -- summed over
+//   b this is the in_proj bias gradient, which otherwise costs a full read of dqkv.
 __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dO,
-                                                                __nv_bfloat16* __restrict__ dqkv, int L, int H, int causal) {
+                                                                __nv_bfloat16* __restrict__ dqkv, int L, int H, int causal,
+                                                                float* __restrict__ colsum) {
     constexpr int PQ = 40;                  // bf16 pitch of the [64][32] operand tiles (80 B rows: conflict-free ldmatrix)
     constexpr int PP = 72;                  // bf16 pitch of the [64][64] P / dS tiles (144 B rows)
-    __shared__ __align__(16) __nv_bfloat16 sQ[64 * PQ], sK[64 * PQ], sV[64 * PQ], sG[64 * PQ], sP[64 * PP], sS[64 * PP];
+    __shared__ __align__(16) __nv_bfloat16 sQ[64 * PQ], sK[64 * PQ], sV[64 * PQ], sG[64 * PQ], sP[64 * PP], sS[64 * PP], sO[64 * PQ];
     const int d = H * 32;
     const long long b = blockIdx.x / H;
     const int hh = blockIdx.x % H;
@@ -715,6 +721,7 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const __nv_bfloa
     const int g8 = lane >> 2, tq = lane & 3;
     constexpr float kScale = 0.17677669529663687f;
     constexpr float kScaleLog2 = kScale * 1.4426950408889634f;
+    unsigned dq_pk[4][2];                     // this warp's dQ fragments (bf16 pairs), staged after the barrier
     {   // ---- phase 1: query block w
         unsigned qa[2][4], ga[2][4];
         const int arow = w * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -807,12 +814,19 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const __nv_bfloa
             }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            const int col = hh * 32 + nt * 8 + tq * 2;
-            if (i0 < L) *reinterpret_cast<unsigned*>(&dqkv[(b * L + i0) * 3 * d + col]) = pack_bf16x2(o[nt][0], o[nt][1]);
-            if (i1 < L) *reinterpret_cast<unsigned*>(&dqkv[(b * L + i1) * 3 * d + col]) = pack_bf16x2(o[nt][2], o[nt][3]);
+            dq_pk[nt][0] = pack_bf16x2(o[nt][0], o[nt][1]);
+            dq_pk[nt][1] = pack_bf16x2(o[nt][2], o[nt][3]);
         }
     }
     __syncthreads();
+    {   // the K tile is dead (phase 2 reads P, dS, dO and Q): stage dQ over it
+        const int i0 = w * 16 + g8, i1 = i0 + 8;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<unsigned*>(&sK[i0 * PQ + nt * 8 + tq * 2]) = dq_pk[nt][0];
+            *reinterpret_cast<unsigned*>(&sK[i1 * PQ + nt * 8 + tq * 2]) = dq_pk[nt][1];
+        }
+    }
     {   // ---- phase 2: key block w
         float dv[4][4], dk[4][4];
 #pragma unroll
@@ -840,16 +854,28 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const __nv_bfloa
         const int j0 = w * 16 + g8, j1 = j0 + 8;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            const int col = hh * 32 + nt * 8 + tq * 2;
-            if (j0 < L) {
-                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j0) * 3 * d + d + col]) = pack_bf16x2(dk[nt][0], dk[nt][1]);
-                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j0) * 3 * d + 2 * d + col]) = pack_bf16x2(dv[nt][0], dv[nt][1]);
-            }
-            if (j1 < L) {
-                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j1) * 3 * d + d + col]) = pack_bf16x2(dk[nt][2], dk[nt][3]);
-                *reinterpret_cast<unsigned*>(&dqkv[(b * L + j1) * 3 * d + 2 * d + col]) = pack_bf16x2(dv[nt][2], dv[nt][3]);
-            }
+            const int col = nt * 8 + tq * 2;
+            *reinterpret_cast<unsigned*>(&sO[j0 * PQ + col]) = pack_bf16x2(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<unsigned*>(&sO[j1 * PQ + col]) = pack_bf16x2(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<unsigned*>(&sV[j0 * PQ + col]) = pack_bf16x2(dv[nt][0], dv[nt][1]);     // the V tile died with phase 1
+            *reinterpret_cast<unsigned*>(&sV[j1 * PQ + col]) = pack_bf16x2(dv[nt][2], dv[nt][3]);
         }
+    }
+    __syncthreads();
+    // write-out: 64 rows x 3 parts (dQ | dK | dV) x 4 pieces of 16 bytes; 4 consecutive lanes cover one row's 64 bytes of a part
+    for (int e = t; e < 64 * 12; e += 128) {
+        const int part = e >> 8, r = (e >> 2) & 63, ch = e & 3;
+        if (r < L) {
+            const __nv_bfloat16* src = (part == 0 ? sK : part == 1 ? sO : sV) + r * PQ + ch * 8;
+            *reinterpret_cast<uint4*>(&dqkv[(b * L + r) * 3 * d + part * d + hh * 32 + ch * 8]) = *reinterpret_cast<const uint4*>(src);
+        }
+    }
+    if (colsum != nullptr && t < 96) {
+        const int part = t >> 5, c = t & 31;
+        const __nv_bfloat16* src = (part == 0 ? sK : part == 1 ? sO : sV) + c;
+        float acc = 0.0f;
+        for (int r = 0; r < L; ++r) acc += __bfloat162float(src[r * PQ]);
+        colsum[b * 3 * d + part * d + hh * 32 + c] = acc;
     }
 }
 
@@ -1285,12 +1311,14 @@ extern "C" int idb200_ln_film_bwd2(const void* da, int da_is_bf16, const float* 
                        : tb::ln_bwd_two_pass<float, false>(g, h, ln_w, ln_b, gamma_beta, gb_stride, B, L, d, dh, d16, dgb, dgb_stride, dwb_part, stats, st);
 }
 
-extern "C" int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, int force_simt,
-                                    idb200_stream_t stream) {
+static int attention_bwd_impl(const void* qkv, const void* dO, void* dqkv, float* traj_colsum, int64_t B, int L, int H, int causal,
+                              int force_simt, idb200_stream_t stream) {
     IDB_REQUIRE(qkv && dO && dqkv, IDB200_EINVAL, "NULL pointer");
+    IDB_REQUIRE(!traj_colsum || (L > 32 && !force_simt), IDB200_EUNSUPPORTED,
+                "per-trajectory column sums come from the tensor-core kernel only (32 < L <= 64; got L = %d)", L);
     IDB_REQUIRE(B > 0 && H > 0, IDB200_EINVAL, "bad shape");
     IDB_REQUIRE(L >= 1 && L <= 64, IDB200_EUNSUPPORTED, "attention backward supports L <= 64 (got %d)", L);
-    IDB_REQUIRE(aligned(qkv, 16) && aligned(dO, 16) && aligned(dqkv, 4), IDB200_EALIGN, "qkv / dO must be 16-byte aligned");
+    IDB_REQUIRE(aligned(qkv, 16) && aligned(dO, 16) && aligned(dqkv, 16), IDB200_EALIGN, "qkv / dO / dqkv must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (L <= 8) return tb::launch_attn_bwd<8, 1>(qkv, dO, dqkv, B, L, H, causal, st);
     if (L <= 16) return tb::launch_attn_bwd<16, 1>(qkv, dO, dqkv, B, L, H, causal, st);
@@ -1298,8 +1326,19 @@ extern "C" int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv,
     if (force_simt) return tb::launch_attn_bwd<64, 4>(qkv, dO, dqkv, B, L, H, causal, st);
     tb::attention_bwd_mma_kernel<<<static_cast<unsigned>(B * H), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                                                static_cast<const __nv_bfloat16*>(dO),
-                                                                               static_cast<__nv_bfloat16*>(dqkv), L, H, causal);
+                                                                               static_cast<__nv_bfloat16*>(dqkv), L, H, causal, traj_colsum);
     return check_launch("attention_bwd_mma_kernel");
+}
+
+extern "C" int idb200_attention_bwd(const void* qkv, const void* dO, void* dqkv, int64_t B, int L, int H, int causal, int force_simt,
+                                    idb200_stream_t stream) {
+    return attention_bwd_impl(qkv, dO, dqkv, nullptr, B, L, H, causal, force_simt, stream);
+}
+
+extern "C" int idb200_attention_bwd_sums(const void* qkv, const void* dO, void* dqkv, float* traj_colsum, int64_t B, int L, int H, int causal,
+                                         idb200_stream_t stream) {
+    IDB_REQUIRE(traj_colsum != nullptr, IDB200_EINVAL, "traj_colsum is NULL (use idb200_attention_bwd)");
+    return attention_bwd_impl(qkv, dO, dqkv, traj_colsum, B, L, H, causal, 0, stream);
 }
 
 extern "C" int idb200_head_bwd(const float* dy, const float* W, int64_t M, int d, int D, float* dh, void* dh_bf16, idb200_stream_t stream) {

@@ -249,9 +249,15 @@ class EncoderBackprop:
             sc.dweight(dh16, sv["o"][i], grads[p + "attn.out_proj.weight"])
             E.gemm_bf16(dh16, w["wot16"], None, do16, E.EPI_BF16)                       # dO = dh Wo
             dqkv = ws.get("dqkv16", (M, 3 * d), BF16, dev)
-            L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), 0, st)
+            if 32 < Lseq <= 64:        # tensor-core kernel: also emits the per-trajectory column sums (= the in_proj bias gradient)
+                dqkv_sum = ws.get("dqkv_sum", (B, 3 * d), F32, dev)
+                L.call("idb200_attention_bwd_sums", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), dqkv_sum.data_ptr(), B, Lseq, H,
+                       int(causal), st)
+                sc.colsum(dqkv_sum, grads[p + "attn.in_proj_bias"])
+            else:
+                L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), 0, st)
+                sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
             sc.dweight(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
-            sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
             E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_BF16)                       # da1 = dqkv Wqkv
             ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, p + "norm1", f"{prefix}layers.{i - 1}.ff.2.bias" if i > 0 else None)
         self._dgb = dgb

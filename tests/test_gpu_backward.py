@@ -197,6 +197,14 @@ def test_attention_backward_matches_autograd(dev, Lseq, H, causal, simt):
     L.call("idb200_attention_bwd", qkv_d.data_ptr(), dO_d.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), simt, L.stream(dev))
     # fp32 kernel: bf16 rounding of the output only; tensor-core kernel (L > 32): P and dS are bf16 operands as well
     assert _rel(dqkv.view(B, Lseq, 3 * d), x.grad) < (6e-3 if (simt or Lseq <= 32) else 1e-2)
+    if Lseq > 32 and not simt:
+        # the form the training step uses: the same gradient + per-trajectory column sums of the bf16 rows (in_proj bias gradient)
+        dqkv2 = torch.full_like(dqkv, float("nan"))
+        sums = torch.full((B, 3 * d), float("nan"), device=dev)
+        L.call("idb200_attention_bwd_sums", qkv_d.data_ptr(), dO_d.data_ptr(), dqkv2.data_ptr(), sums.data_ptr(), B, Lseq, H, int(causal), L.stream(dev))
+        assert torch.equal(dqkv2, dqkv)
+        want = dqkv.float().view(B, Lseq, 3 * d).sum(1)
+        assert (sums - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
 
 
 def _make_model(dev, d, nl, H, ff, maze_channels, C, causal=False):
