@@ -931,24 +931,50 @@ __global__ void __launch_bounds__(128) token_sum_kernel(const float* __restrict_
 
 // out[i, j] (+)= sum_k A[i * sa0 + k * sa1] * B[j * sb0 + k * sb1]: strided fp32 GEMM for the per-trajectory linears'
 // backward (level_proj, cond_proj, maze.fc, sg.mlp, t_embed: M = batch, all dims <= 512)
+// 32 x 32 output tile per block, 2 x 2 outputs per thread, k-steps of 32; the tile loads walk whichever index is contiguous in memory
+// (sa1 == 1: k, else the row index), so both the plain and the transposed operand forms are coalesced.  (The first revision -- 16 x 16
+// tiles, one output per thread, k always on the fast thread index -- read transposed operands with a stride of a whole row: 0.3-0.4 ms
+// per call at B = 4096 for 1.2 GFLOP.)  Per-thread accumulation order over k is fixed: deterministic.
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, long long sa0, long long sa1, const float* __restrict__ B,
                                                             long long sb0, long long sb1, float* __restrict__ out, long long ldo, int M, int N,
                                                             int K, int accumulate) {
-    __shared__ float As[16][17], Bs[16][17];
+    __shared__ float As[32][34], Bs[32][34];                // [k][row]
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
-    float acc = 0.0f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        const int ia = blockIdx.y * 16 + ty, ka = k0 + tx;
-        As[ty][tx] = (ia < M && ka < K) ? A[ia * sa0 + ka * sa1] : 0.0f;
-        const int jb = blockIdx.x * 16 + ty;
-        Bs[ty][tx] = (jb < N && ka < K) ? B[jb * sb0 + ka * sb1] : 0.0f;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    float acc[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+            {
+                const int r = (sa1 == 1) ? (e >> 5) : (e & 31), k = (sa1 == 1) ? (e & 31) : (e >> 5);
+                const int ia = i0 + r, ka = k0 + k;
+                As[k][r] = (ia < M && ka < K) ? A[ia * sa0 + ka * sa1] : 0.0f;
+            }
+            {
+                const int r = (sb1 == 1) ? (e >> 5) : (e & 31), k = (sb1 == 1) ? (e & 31) : (e >> 5);
+                const int jb = j0 + r, kb = k0 + k;
+                Bs[k][r] = (jb < N && kb < K) ? B[jb * sb0 + kb * sb1] : 0.0f;
+            }
+        }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc = fmaf(As[ty][k], Bs[tx][k], acc);
+        for (int k = 0; k < 32; ++k) {
+            const float2 a = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+            const float2 b = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
+            acc[0][0] = fmaf(a.x, b.x, acc[0][0]);
+            acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+            acc[1][0] = fmaf(a.y, b.x, acc[1][0]);
+            acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+        }
         __syncthreads();
     }
-    if (i < M && j < N) out[i * ldo + j] = accumulate ? out[i * ldo + j] + acc : acc;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj) {
+            const int i = i0 + ty * 2 + di, j = j0 + tx * 2 + dj;
+            if (i < M && j < N) out[i * ldo + j] = accumulate ? out[i * ldo + j] + acc[di][dj] : acc[di][dj];
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1380,7 +1406,7 @@ extern "C" int idb200_sgemm_strided(const float* A, int64_t sa0, int64_t sa1, co
                                     int64_t ldo, int M, int N, int K, int accumulate, idb200_stream_t stream) {
     IDB_REQUIRE(A && Bm && out, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE(M > 0 && N > 0 && K > 0, IDB200_EINVAL, "bad shape");
-    tb::sgemm_strided_kernel<<<dim3((N + 15) / 16, (M + 15) / 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sa0, sa1, Bm, sb0, sb1, out,
+    tb::sgemm_strided_kernel<<<dim3((N + 31) / 32, (M + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sa0, sa1, Bm, sb0, sb1, out,
                                                                                                                ldo, M, N, K, accumulate);
     return check_launch("sgemm_strided_kernel");
 }
