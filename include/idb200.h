@@ -421,6 +421,10 @@ int idb200_transpose_bf16(const void* src, int src_is_f32, int64_t M, int N, voi
 int idb200_colsum_scratch_floats(int64_t M, int N);
 int idb200_colsum(const void* src, int src_kind, int64_t M, int N, float* scratch, float scale, int accumulate, float* out,
                   idb200_stream_t stream);
+/* The same for `segs` stacked matrices: src [segs, M, N] -> out [segs, N] in two launches (the per-LayerNorm [B, 3d] partials of a
+ * whole backward pass are reduced at once); scratch: segs * idb200_colsum_scratch_floats(M, N) floats. */
+int idb200_colsum_segments(const void* src, int src_kind, int segs, int64_t M, int N, float* scratch, float scale, int accumulate,
+                           float* out, idb200_stream_t stream);
 /* out[W] (+)= scale * sum_r partial[r, W] (fixed order). */
 int idb200_reduce_rows(const float* partial, int R, int64_t W, float scale, int accumulate, float* out, idb200_stream_t stream);
 /* bf16 elementwise, n even: mode 0 y = silu(u); mode 1 y = g * silu'(u). */

@@ -93,6 +93,15 @@ class _Scratch:
                out.data_ptr(), L.stream(src.device))
         return out
 
+    def colsum_segments(self, src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """out[s, :] = column sums of src[s] for src [segs, M, N] (two launches for all segments)."""
+        segs, M, N = src.shape
+        n = L.lib().idb200_colsum_scratch_floats(M, N) * segs
+        sc = self.ws.get("colsum_seg", (n,), F32, src.device)
+        L.call("idb200_colsum_segments", src.data_ptr(), int(src.dtype == BF16), segs, M, N, sc.data_ptr(), 1.0, 0, out.data_ptr(),
+               L.stream(src.device))
+        return out
+
     def narrow_outer(self, A: torch.Tensor, X: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         """out[n, K] = A[M, n]^T X[M, K] (n <= 8)."""
         M, n = A.shape
@@ -212,25 +221,23 @@ class EncoderBackprop:
         sc, ws = self.sc, self.sc.ws
         da = ws.get("da16", (M, d), BF16, dev)            # gradient w.r.t. the LayerNorm outputs, bf16 (half the bytes of 3 passes)
         do16 = ws.get("do16", (M, d), BF16, dev)
-        dwb = ws.get("dwb", (B, 3 * d), F32, dev)
-        dwb_sum = ws.get("dwb_sum", (3 * d,), F32, dev)
+        # per-trajectory partials of every LayerNorm ([dw | db | sum_t dh]) and of every in_proj bias: reduced over the batch by
+        # ONE segmented column sum each at the end (was two launches per LayerNorm / layer: 0.4 ms of a 14.6 ms step at B = 512)
+        dwb_all = ws.get("dwb_all", (2 * nl, B, 3 * d), F32, dev)
+        dqkv_sum_all = ws.get("dqkv_sum_all", (nl, B, 3 * d), F32, dev)
+        fused_qkv_sums = 32 < Lseq <= 64            # the tensor-core attention backward emits the per-trajectory sums
         stats = ws.get("ln_stats", (M, 4), F32, dev)
         dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
         st = L.stream(dev)
 
-        def ln_bwd(h_saved, nw, nb, j, name, bias_below):
-            """LayerNorm + FiLM backward; also yields the column sums of the UPDATED dh = the bias gradient of the GEMM that
-            accumulated into the residual stream just below this LayerNorm (``bias_below``: a grads key or None)."""
+        def ln_bwd(h_saved, nw, nb, j):
+            """LayerNorm + FiLM backward of LayerNorm slot j; its partials (incl. the column sums of the UPDATED dh = the bias gradient
+            of the GEMM that accumulated into the residual stream just below this LayerNorm) land in dwb_all[j]."""
             gb = film[:, j] if film is not None else None
             dg = dgb[:, j] if film is not None else None
             L.call("idb200_ln_film_bwd2", da.data_ptr(), 1, h_saved.data_ptr(), nw.data_ptr(), nb.data_ptr(), L.ptr(gb),
                    0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), dh16.data_ptr(), L.ptr(dg),
-                   0 if dg is None else dg.stride(0), dwb.data_ptr(), 1, stats.data_ptr(), st)
-            sc.colsum(dwb, dwb_sum)
-            grads[name + ".weight"].copy_(dwb_sum[:d])
-            grads[name + ".bias"].copy_(dwb_sum[d:2 * d])
-            if bias_below is not None:
-                grads[bias_below].copy_(dwb_sum[2 * d:])
+                   0 if dg is None else dg.stride(0), dwb_all[j].data_ptr(), 1, stats.data_ptr(), st)
 
         for i in range(nl - 1, -1, -1):
             w = W[i]
@@ -244,22 +251,34 @@ class EncoderBackprop:
             sc.dweight(du, sv["a2"][i], grads[p + "ff.0.weight"])
             sc.colsum(du, grads[p + "ff.0.bias"])
             E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_BF16)                           # da2 = du W1
-            ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1, p + "norm2", p + "attn.out_proj.bias")
+            ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1)
             # ---- attention: h_mid = h_in + out_proj(MHA(a1))
             sc.dweight(dh16, sv["o"][i], grads[p + "attn.out_proj.weight"])
             E.gemm_bf16(dh16, w["wot16"], None, do16, E.EPI_BF16)                       # dO = dh Wo
             dqkv = ws.get("dqkv16", (M, 3 * d), BF16, dev)
-            if 32 < Lseq <= 64:        # tensor-core kernel: also emits the per-trajectory column sums (= the in_proj bias gradient)
-                dqkv_sum = ws.get("dqkv_sum", (B, 3 * d), F32, dev)
-                L.call("idb200_attention_bwd_sums", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), dqkv_sum.data_ptr(), B, Lseq, H,
-                       int(causal), st)
-                sc.colsum(dqkv_sum, grads[p + "attn.in_proj_bias"])
+            if fused_qkv_sums:         # tensor-core kernel: also emits the per-trajectory column sums (= the in_proj bias gradient)
+                L.call("idb200_attention_bwd_sums", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), dqkv_sum_all[i].data_ptr(), B, Lseq,
+                       H, int(causal), st)
             else:
                 L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), 0, st)
                 sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
             sc.dweight(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
             E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_BF16)                       # da1 = dqkv Wqkv
-            ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, p + "norm1", f"{prefix}layers.{i - 1}.ff.2.bias" if i > 0 else None)
+            ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i)
+        sums = self.sc.colsum_segments(dwb_all, ws.get("dwb_sums", (2 * nl, 3 * d), F32, dev))
+        for i in range(nl):
+            p = f"{prefix}layers.{i}."
+            grads[p + "norm1.weight"].copy_(sums[2 * i, :d])
+            grads[p + "norm1.bias"].copy_(sums[2 * i, d:2 * d])
+            grads[p + "norm2.weight"].copy_(sums[2 * i + 1, :d])
+            grads[p + "norm2.bias"].copy_(sums[2 * i + 1, d:2 * d])
+            grads[p + "attn.out_proj.bias"].copy_(sums[2 * i + 1, 2 * d:])
+            if i > 0:
+                grads[f"{prefix}layers.{i - 1}.ff.2.bias"].copy_(sums[2 * i, 2 * d:])
+        if fused_qkv_sums:
+            qs = self.sc.colsum_segments(dqkv_sum_all, ws.get("dqkv_sums", (nl, 3 * d), F32, dev))
+            for i in range(nl):
+                grads[f"{prefix}layers.{i}.attn.in_proj_bias"].copy_(qs[i])
         self._dgb = dgb
 
     def backward_film(self, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> Optional[torch.Tensor]:
