@@ -455,6 +455,130 @@ __global__ void __launch_bounds__(128) ln_bwd_apply_kernel(const TDa* __restrict
     if (kDhSum) *reinterpret_cast<float4*>(dwb_part + b * kW * d + 2 * d + c) = a_dh;
 }
 
+// One-launch form of the two passes: a block per trajectory runs pass A (a warp per token -> the four row scalars, kept in shared
+// memory) and then pass B (a thread per group of four columns; the two halves of the block walk the two halves of the trajectory's
+// tokens and are merged in a fixed order).  Pass B's second read of da / h (147 KB per trajectory at d = 384, L = 64) comes out of
+// L2 instead of HBM: DRAM traffic 22 -> 16 bytes per element.  Same per-element arithmetic as the two kernels above.
+template <int kV4, typename TDa, bool kDhSum>
+__global__ void __launch_bounds__(64 * kV4) ln_bwd_fused_kernel(const TDa* __restrict__ da, const float* __restrict__ h,
+                                                                const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                                const float* __restrict__ gb, long long gb_stride, int L,
+                                                                float* __restrict__ dh, __nv_bfloat16* __restrict__ dh16,
+                                                                float* __restrict__ dgb, long long dgb_stride, float* __restrict__ dwb_part) {
+    constexpr int d = kV4 * 128, kThreads = 64 * kV4, kWarps = kThreads / 32, kCg = d / 4;
+    extern __shared__ __align__(16) float4 ln_bwd_sm[];
+    float4* sstats = ln_bwd_sm;                            // [L]
+    float4* smerge = ln_bwd_sm + L;                        // [5][kCg]: the upper half's column accumulators
+    const long long b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {   // ---- pass A
+        float4 w[kV4];
+#pragma unroll
+        for (int j = 0; j < kV4; ++j) w[j] = load4(ln_w + 4 * (lane + 32 * j));
+        for (int t = warp; t < L; t += kWarps) {
+            const long long row = (b * L + t) * d;
+            float4 x[kV4], g[kV4];
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kV4; ++j) {
+                const int c = 4 * (lane + 32 * j);
+                x[j] = load4(h + row + c);
+                g[j] = load4(da + row + c);
+                if (gb) {
+                    const float4 ga = load4(gb + b * gb_stride + c);
+                    g[j].x *= 1.0f + ga.x; g[j].y *= 1.0f + ga.y; g[j].z *= 1.0f + ga.z; g[j].w *= 1.0f + ga.w;
+                }
+                g[j].x *= w[j].x; g[j].y *= w[j].y; g[j].z *= w[j].z; g[j].w *= w[j].w;      // dxhat
+                s += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * (1.0f / d);
+            float v = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kV4; ++j) {
+                x[j].x -= mean; x[j].y -= mean; x[j].z -= mean; x[j].w -= mean;
+                v = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, fmaf(x[j].w, x[j].w, v))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const float rstd = rsqrtf(v * (1.0f / d) + 1e-5f);
+            float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kV4; ++j) {
+                s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+                s2 = fmaf(g[j].x, x[j].x * rstd, fmaf(g[j].y, x[j].y * rstd, fmaf(g[j].z, x[j].z * rstd, fmaf(g[j].w, x[j].w * rstd, s2))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == 0) sstats[t] = make_float4(mean, rstd, s1 * (1.0f / d), s2 * (1.0f / d));
+        }
+    }
+    __syncthreads();
+    // ---- pass B
+    const int cg = threadIdx.x % kCg, rh = threadIdx.x / kCg;
+    const int c = 4 * cg;
+    const int half = (L + 1) / 2;
+    const int t0 = rh * half, t1 = rh ? L : half;
+    const float4 w = load4(ln_w + c), bb = load4(ln_b + c);
+    float4 g1 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (gb) {
+        const float4 ga = load4(gb + b * gb_stride + c);
+        g1 = make_float4(1.0f + ga.x, 1.0f + ga.y, 1.0f + ga.z, 1.0f + ga.w);
+    }
+    float4 a_dg = make_float4(0.f, 0.f, 0.f, 0.f), a_db = a_dg, a_dw = a_dg, a_dbb = a_dg, a_dh = a_dg;
+#pragma unroll 4
+    for (int t = t0; t < t1; ++t) {
+        const float4 st = sstats[t];
+        const long long o = (b * L + t) * d + c;
+        const float4 hv = load4(h + o), g = load4(da + o), dv = load4(dh + o);
+        float4 v2;
+#define IDB_LN_BWD_LANE(k)                                                    \
+        {                                                                      \
+            const float xh = (hv.k - st.x) * st.y;                             \
+            const float n = fmaf(xh, w.k, bb.k);                               \
+            const float dn = g.k * g1.k;                                       \
+            a_dg.k = fmaf(g.k, n, a_dg.k);                                     \
+            a_db.k += g.k;                                                     \
+            a_dw.k = fmaf(dn, xh, a_dw.k);                                     \
+            a_dbb.k += dn;                                                     \
+            v2.k = dv.k + st.y * (dn * w.k - st.z - xh * st.w);                \
+            if (kDhSum) a_dh.k += v2.k;                                        \
+        }
+        IDB_LN_BWD_LANE(x) IDB_LN_BWD_LANE(y) IDB_LN_BWD_LANE(z) IDB_LN_BWD_LANE(w)
+#undef IDB_LN_BWD_LANE
+        *reinterpret_cast<float4*>(dh + o) = v2;
+        if (dh16) {
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v2.x, v2.y), p1 = __floats2bfloat162_rn(v2.z, v2.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned*>(&p0);
+            pk.y = *reinterpret_cast<const unsigned*>(&p1);
+            *reinterpret_cast<uint2*>(dh16 + o) = pk;
+        }
+    }
+    if (rh == 1) {
+        smerge[0 * kCg + cg] = a_dg; smerge[1 * kCg + cg] = a_db; smerge[2 * kCg + cg] = a_dw; smerge[3 * kCg + cg] = a_dbb;
+        smerge[4 * kCg + cg] = a_dh;
+    }
+    __syncthreads();
+    if (rh == 0) {
+        auto add4 = [](float4& a, const float4& o) { a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; };
+        add4(a_dg, smerge[0 * kCg + cg]); add4(a_db, smerge[1 * kCg + cg]); add4(a_dw, smerge[2 * kCg + cg]); add4(a_dbb, smerge[3 * kCg + cg]);
+        add4(a_dh, smerge[4 * kCg + cg]);
+        if (dgb) {
+            *reinterpret_cast<float4*>(dgb + b * dgb_stride + c) = a_dg;
+            *reinterpret_cast<float4*>(dgb + b * dgb_stride + d + c) = a_db;
+        }
+        constexpr int kW = kDhSum ? 3 : 2;
+        *reinterpret_cast<float4*>(dwb_part + b * kW * d + c) = a_dw;
+        *reinterpret_cast<float4*>(dwb_part + b * kW * d + d + c) = a_dbb;
+        if (kDhSum) *reinterpret_cast<float4*>(dwb_part + b * kW * d + 2 * d + c) = a_dh;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Backward of softmax(q k^T / sqrt(32)) v for one (trajectory, head) per block (nn.MultiheadAttention inside
 // transformer.py:39, head_dim 32, L <= 64): recompute P, then dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(P o dP)),
@@ -875,12 +999,16 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const __nv_bfloa
             *reinterpret_cast<uint4*>(&dqkv[(b * L + r) * 3 * d + part * d + hh * 32 + ch * 8]) = *reinterpret_cast<const uint4*>(src);
         }
     }
-    if (colsum != nullptr && t < 96) {
-        const int part = t >> 5, c = t & 31;
+    if (colsum != nullptr && t < 48) {                     // a thread sums a PAIR of columns (the kernel is LSU-wavefront bound: ncu 80 %)
+        const int part = t >> 4, c = (t & 15) * 2;
         const __nv_bfloat16* src = (part == 0 ? sK : part == 1 ? sO : sV) + c;
-        float acc = 0.0f;
-        for (int r = 0; r < L; ++r) acc += __bfloat162float(src[r * PQ]);
-        colsum[b * 3 * d + part * d + hh * 32 + c] = acc;
+        float a0 = 0.0f, a1 = 0.0f;
+        for (int r = 0; r < L; ++r) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + r * PQ));
+            a0 += f.x;
+            a1 += f.y;
+        }
+        *reinterpret_cast<float2*>(&colsum[b * 3 * d + part * d + hh * 32 + c]) = make_float2(a0, a1);
     }
 }
 
@@ -1191,6 +1319,26 @@ int ln_bwd_two_pass(const TDa* da, const float* h, const float* ln_w, const floa
                     (!dgb || (aligned(dgb, 16) && dgb_stride % 4 == 0)),
                 IDB200_EALIGN, "LayerNorm backward (two-pass form) needs 16-byte aligned rows");
     const long long M = B * L;
+    static const int fused_env = getenv("IDB200_LN_BWD_FUSED") ? atoi(getenv("IDB200_LN_BWD_FUSED")) : 1;
+    if (fused_env && L >= 2 && L <= 1024) {
+        // pad_kb (dev knob) caps the resident blocks per SM: the re-read of pass B has to find the trajectory's rows in L2
+        static const int pad_kb = getenv("IDB200_LN_BWD_PAD_KB") ? atoi(getenv("IDB200_LN_BWD_PAD_KB")) : 0;
+        const size_t smem = (static_cast<size_t>(L) + 5 * (d / 4)) * sizeof(float4) + static_cast<size_t>(pad_kb) * 1024;
+        auto go = [&](auto kern, int threads) -> int {
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                if (e != cudaSuccess) return fail(IDB200_ECUDA, "cudaFuncSetAttribute(ln_bwd_fused): %s", cudaGetErrorString(e));
+            }
+            kern<<<static_cast<unsigned>(B), threads, smem, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, dh, d16, dgb, dgb_stride, dwb_part);
+            return check_launch("ln_bwd_fused_kernel");
+        };
+        switch (d / 128) {
+            case 1: return go(ln_bwd_fused_kernel<1, TDa, kDhSum>, 64);
+            case 2: return go(ln_bwd_fused_kernel<2, TDa, kDhSum>, 128);
+            case 3: return go(ln_bwd_fused_kernel<3, TDa, kDhSum>, 192);
+            default: return go(ln_bwd_fused_kernel<4, TDa, kDhSum>, 256);
+        }
+    }
     const int g1 = grid_for(M * 32, 256, 8);
     switch (d / 128) {
         case 1: ln_bwd_stats_kernel<1, TDa><<<g1, 256, 0, st>>>(da, h, ln_w, gamma_beta, gb_stride, L, M, stats); break;

@@ -1,6 +1,6 @@
 """One warm-up + two launches of ONE hot kernel at its bench shape, for `ncu --set full -k regex:<kernel>`:
     python tools/profile_targets.py <target>
-targets: qkv_attn mlp_pair encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
+targets: qkv_attn mlp_pair encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd attn_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
 import os
 import sys
 
@@ -114,6 +114,14 @@ elif t == "ln_bwd":
     stats = torch.empty((M, 4), device=dev)
     run(lambda: L.call("idb200_ln_film_bwd2", da.data_ptr(), 1, h.data_ptr(), w.data_ptr(), b.data_ptr(), gb.data_ptr(), 2 * d, B, Lq, d,
                        dh.data_ptr(), dh16.data_ptr(), dgb.data_ptr(), 2 * d, dwb.data_ptr(), 1, stats.data_ptr(), L.stream(torch.device(dev))))
+elif t == "attn_bwd":
+    B, Lq, H = 4096, 64, 12
+    d = 32 * H
+    qkv = torch.randn((B * Lq, 3 * d), device=dev).bfloat16()
+    dO = torch.randn((B * Lq, d), device=dev).bfloat16()
+    dqkv = torch.empty_like(qkv)
+    sums = torch.empty((B, 3 * d), device=dev)
+    run(lambda: L.call("idb200_attention_bwd_sums", qkv.data_ptr(), dO.data_ptr(), dqkv.data_ptr(), sums.data_ptr(), B, Lq, H, 0, L.stream(torch.device(dev))))
 elif t == "im2col":
     B, C = 4096, 128
     u = torch.randn((B, 441, C), device=dev).bfloat16()
