@@ -37,6 +37,7 @@ _SIGS = {
     "idb200_conv3x3_gemm": [c_p, c_i, c_p, c_p, c_p, c_i, c_l, c_i, c_i, c_i, c_p],
     "idb200_pool_bordered": [c_p, c_l, c_i, c_i, c_i, c_p, c_p],
     "idb200_gemm_bf16_aux": [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p],
+    "idb200_gemm_bf16_dsilu_sums": [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_p],
     "idb200_sgemm": [c_p, c_i, c_l, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_i, c_i, c_p],
     "idb200_conv_encoder": [c_p, c_p, c_l, c_i, c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_p), ctypes.POINTER(c_p), c_p, c_p, c_p],
     "idb200_sinusoid": [c_p, c_i, c_i, c_i, c_p, c_p],

@@ -118,6 +118,10 @@ struct GemmParams {
     int conv_P2, conv_PW, conv_PH;
     int conv_shift[kConvMaxKB];
     int conv_col[kConvMaxKB];
+    // EPI_BF16_DSILU only (nullptr otherwise): colpart [4 * ceil(M / 128), N] fp32 receives, per 128-row block and epilogue warp, the
+    // column sums of the bf16-rounded output over the warp's 32 rows -- summed over its rows this is the bias gradient of ff.0
+    // (column sums of dU), which otherwise costs a full extra read of dU.
+    float* colpart;
 };
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU (tanh.approx, rel. error ~2^-11, below the bf16
@@ -398,6 +402,36 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                         }
                     }
+                    if (!dual && p.colpart != nullptr) {
+                        // column sums of the warp's OWN 32 rows of the staged slab (only __syncwarp needed: no other warp's rows are
+                        // read, and the buffer is not handed to TMA yet): lane <-> (16-byte piece = 8 columns, row group of 4);
+                        // 8 conflict-free LDS.128 per thread, then two shuffle steps over the 4 row groups
+                        __syncwarp();
+                        const int piece = lane & 7, rg = q * 32 + (lane >> 3);
+                        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = rg + 4 * i;
+                            const uint4 v = *reinterpret_cast<const uint4*>(buf0 + r * 128 + ((piece ^ (r & 7)) << 4));
+                            const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f = __bfloat1622float2(v2[k]);
+                                cs[2 * k] += f.x;
+                                cs[2 * k + 1] += f.y;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+                            cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+                        }
+                        if (lane < 8) {
+                            float* dst = p.colpart + ((m0 / kBM) * 4 + q) * p.N + n0 + sl * 64 + piece * 8;
+                            *reinterpret_cast<float4*>(dst) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+                            *reinterpret_cast<float4*>(dst + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+                        }
+                    }
                     fence_proxy_async_smem();
                     named_barrier_sync(3 + half, 128);
                     if (leader) {
@@ -652,7 +686,8 @@ int gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, long long 
 }
 
 int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, long long M, int N, int K, int epilogue,
-                 cudaStream_t st, int splits, void* aux = nullptr) {
+                 cudaStream_t st, int splits, void* aux = nullptr, float* colpart = nullptr) {
+    IDB_REQUIRE(!colpart || (epilogue == EPI_BF16_DSILU && aligned(colpart, 16)), IDB200_EINVAL, "colpart goes with epilogue 5 (16-byte aligned)");
     IDB_REQUIRE(A && W && out, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE((epilogue >= EPI_BF16_SILU_DUAL) == (aux != nullptr), IDB200_EINVAL, "epilogues 4 / 5 need the aux tensor (and only they take one)");
     IDB_REQUIRE(M >= 0 && N > 0 && K > 0, IDB200_EINVAL, "bad shape");
@@ -691,6 +726,7 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
         }
     }
     GemmParams p{bias, out, M, N, K, epilogue, splits, use_tma};
+    p.colpart = colpart;
     const CUtensorMap* px = aux ? &tx : nullptr;
     switch (BN) {
         case 256: return launch_gemm<256>(ta, tw, tw_half, to, p, st, px);
@@ -769,6 +805,12 @@ extern "C" int idb200_gemm_bf16(const void* A, const void* W, const float* bias,
 extern "C" int idb200_gemm_bf16_aux(const void* A, const void* W, const float* bias, void* out, void* aux, int64_t M, int N, int K,
                                     int epilogue, idb200_stream_t stream) {
     return idb200::gemm_bf16_tn(A, W, bias, out, M, N, K, epilogue, static_cast<cudaStream_t>(stream), 1, aux);
+}
+
+extern "C" int idb200_gemm_bf16_dsilu_sums(const void* A, const void* W, void* out, void* aux, float* colpart, int64_t M, int N, int K,
+                                           idb200_stream_t stream) {
+    IDB_REQUIRE(colpart != nullptr, IDB200_EINVAL, "colpart is NULL (use idb200_gemm_bf16_aux)");
+    return idb200::gemm_bf16_tn(A, W, nullptr, out, M, N, K, idb200::EPI_BF16_DSILU, static_cast<cudaStream_t>(stream), 1, aux, colpart);
 }
 
 extern "C" int idb200_gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, int64_t M, int N, int64_t K, int splits,

@@ -226,6 +226,8 @@ class EncoderBackprop:
         dwb_all = ws.get("dwb_all", (2 * nl, B, 3 * d), F32, dev)
         dqkv_sum_all = ws.get("dqkv_sum_all", (nl, B, 3 * d), F32, dev)
         fused_qkv_sums = 32 < Lseq <= 64            # the tensor-core attention backward emits the per-trajectory sums
+        fused_du_sums = ff % 64 == 0 and d % 64 == 0 and os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0"
+        du_part = ws.get("du_part", (4 * ((M + 127) // 128), ff), F32, dev) if fused_du_sums else None
         stats = ws.get("ln_stats", (M, 4), F32, dev)
         dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
         st = L.stream(dev)
@@ -247,9 +249,14 @@ class EncoderBackprop:
             if i == nl - 1:
                 sc.colsum(dh, grads[p + "ff.2.bias"])           # (the other layers' come out of the LayerNorm backward above them)
             du = ws.get("du16", (M, ff), BF16, dev)
-            gemm_bf16_aux(dh16, w["w2t16"], None, du, sv["u"][i], EPI_BF16_DSILU)      # du = (dh W2) * silu'(u), one launch
+            if fused_du_sums:          # du = (dh W2) * silu'(u) and its per-warp column sums (-> ff.0 bias gradient) in one launch
+                L.call("idb200_gemm_bf16_dsilu_sums", dh16.data_ptr(), w["w2t16"].data_ptr(), du.data_ptr(), sv["u"][i].data_ptr(),
+                       du_part.data_ptr(), M, ff, d, st)
+                sc.colsum(du_part, grads[p + "ff.0.bias"])
+            else:
+                gemm_bf16_aux(dh16, w["w2t16"], None, du, sv["u"][i], EPI_BF16_DSILU)  # du = (dh W2) * silu'(u)
+                sc.colsum(du, grads[p + "ff.0.bias"])
             sc.dweight(du, sv["a2"][i], grads[p + "ff.0.weight"])
-            sc.colsum(du, grads[p + "ff.0.bias"])
             E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_BF16)                           # da2 = du W1
             ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1)
             # ---- attention: h_mid = h_in + out_proj(MHA(a1))

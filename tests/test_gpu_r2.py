@@ -257,6 +257,14 @@ def test_gemm_silu_epilogues_equal_the_separate_passes(M, N, K):
     E.gemm_bf16(A, W, None, dF, E.EPI_BF16)
     du_ref = bw.silu_bf16(u, dF, g=dF)
     assert torch.equal(du, du_ref)
+    # the form the training step uses: the same dU + per-warp column sums (column sums of colpart = the ff.0 bias gradient)
+    from interpolated_diffusion_b200 import _lib as L
+    du2 = torch.full_like(du, float("nan"))
+    part = torch.full((4 * ((M + 127) // 128), N), float("nan"), device="cuda")
+    L.call("idb200_gemm_bf16_dsilu_sums", A.data_ptr(), W.data_ptr(), du2.data_ptr(), u.data_ptr(), part.data_ptr(), M, N, K, L.stream(A.device))
+    assert torch.equal(du2, du)
+    want_cs = du.double().sum(0)
+    assert (part.double().sum(0) - want_cs).abs().max().item() <= 1e-4 * max(1.0, want_cs.abs().max().item())
     x = u.float()
     s = torch.sigmoid(x)
     want = (A.float() @ W.float().t()).bfloat16().float() * (s * (1 + x * (1 - s)))
