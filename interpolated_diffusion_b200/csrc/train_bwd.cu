@@ -1319,7 +1319,10 @@ int ln_bwd_two_pass(const TDa* da, const float* h, const float* ln_w, const floa
                     (!dgb || (aligned(dgb, 16) && dgb_stride % 4 == 0)),
                 IDB200_EALIGN, "LayerNorm backward (two-pass form) needs 16-byte aligned rows");
     const long long M = B * L;
-    static const int fused_env = getenv("IDB200_LN_BWD_FUSED") ? atoi(getenv("IDB200_LN_BWD_FUSED")) : 1;
+    // MEASURED AND REJECTED as the default (tools/bench_ln_bwd.py, d = 384, L = 64): the one-launch form takes 0.430 ms at B = 4096 and
+    // 0.0795 ms at B = 512 against 0.409 / 0.0753 ms of the two passes -- those already stream their 22 bytes per element at 5.4 TB/s
+    // (82 % of the measured copy bandwidth); the block-per-trajectory form moves 16 but is latency bound.  IDB200_LN_BWD_FUSED=1 opts in.
+    static const int fused_env = getenv("IDB200_LN_BWD_FUSED") ? atoi(getenv("IDB200_LN_BWD_FUSED")) : 0;
     if (fused_env && L >= 2 && L <= 1024) {
         // pad_kb (dev knob) caps the resident blocks per SM: the re-read of pass B has to find the trajectory's rows in L2
         static const int pad_kb = getenv("IDB200_LN_BWD_PAD_KB") ? atoi(getenv("IDB200_LN_BWD_PAD_KB")) : 0;
