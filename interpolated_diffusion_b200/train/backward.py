@@ -221,6 +221,39 @@ class EncoderBackprop:
         sc, ws = self.sc, self.sc.ws
         da = ws.get("da16", (M, d), BF16, dev)            # gradient w.r.t. the LayerNorm outputs, bf16 (half the bytes of 3 passes)
         do16 = ws.get("do16", (M, d), BF16, dev)
+        # ---- weight-gradient GEMMs on a side stream.  The dX chain (dU GEMM -> da GEMM -> LayerNorm backward -> dO GEMM -> attention
+        # backward -> da GEMM -> LayerNorm backward) is the critical path; the four dW GEMMs of a layer only feed the optimiser.  On
+        # their own stream they fill the SMs while the main stream runs its HBM-bound passes (LayerNorm / attention backward, column
+        # sums), and the tail of one GEMM overlaps the head of the next.  What they read (dh16, dU, dqkv) is double-buffered so the
+        # main stream runs up to one LayerNorm interval ahead; `readers` holds, per buffer, the side-stream event after its last
+        # reader there, awaited before the main stream overwrites the buffer.  Same kernels, same arithmetic order: bit-identical
+        # gradients (IDB200_TRAIN_DW_STREAM=0: everything on one stream).
+        main = torch.cuda.current_stream(dev)
+        side = None
+        if os.environ.get("IDB200_TRAIN_DW_STREAM", "1") != "0":
+            if getattr(self, "_dw_stream", None) is None:
+                self._dw_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("IDB200_TRAIN_DW_PRIO", "0")))
+            side = self._dw_stream
+        readers: Dict[int, "torch.cuda.Event"] = {}
+
+        def dw_async(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> None:
+            if side is None:
+                sc.dweight(dy, x, out)
+                return
+            side.wait_stream(main)                         # after everything enqueued on the main stream so far (dy is final)
+            with torch.cuda.stream(side):
+                sc.dweight(dy, x, out)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            readers[dy.data_ptr()] = ev
+
+        def before_write(buf: torch.Tensor) -> None:
+            ev = readers.pop(buf.data_ptr(), None)
+            if ev is not None:
+                main.wait_event(ev)
+
+        dh16_bufs = [dh16, ws.get("dh16_alt", (M, d), BF16, dev)]      # LayerNorm backward k writes buffer (k + 1) % 2: 2 nl calls end in dh16
+        cur16 = [0]
         # per-trajectory partials of every LayerNorm ([dw | db | sum_t dh]) and of every in_proj bias: reduced over the batch by
         # ONE segmented column sum each at the end (was two launches per LayerNorm / layer: 0.4 ms of a 14.6 ms step at B = 512)
         dwb_all = ws.get("dwb_all", (2 * nl, B, 3 * d), F32, dev)
@@ -237,41 +270,52 @@ class EncoderBackprop:
             of the GEMM that accumulated into the residual stream just below this LayerNorm) land in dwb_all[j]."""
             gb = film[:, j] if film is not None else None
             dg = dgb[:, j] if film is not None else None
+            nxt = dh16_bufs[1 - cur16[0]] if side is not None else dh16
+            before_write(nxt)
             L.call("idb200_ln_film_bwd2", da.data_ptr(), 1, h_saved.data_ptr(), nw.data_ptr(), nb.data_ptr(), L.ptr(gb),
-                   0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), dh16.data_ptr(), L.ptr(dg),
+                   0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), nxt.data_ptr(), L.ptr(dg),
                    0 if dg is None else dg.stride(0), dwb_all[j].data_ptr(), 1, stats.data_ptr(), st)
+            if side is not None:
+                cur16[0] = 1 - cur16[0]
 
         for i in range(nl - 1, -1, -1):
             w = W[i]
             p = f"{prefix}layers.{i}."
+            g16 = dh16_bufs[cur16[0]]                        # bf16 copy of the residual-stream gradient at this point
             # ---- MLP: h_out = h_mid + ff.2(silu(ff.0(a2)))
-            sc.dweight(dh16, sv["f"][i], grads[p + "ff.2.weight"])
+            dw_async(g16, sv["f"][i], grads[p + "ff.2.weight"])
             if i == nl - 1:
                 sc.colsum(dh, grads[p + "ff.2.bias"])           # (the other layers' come out of the LayerNorm backward above them)
-            du = ws.get("du16", (M, ff), BF16, dev)
+            du = ws.get(f"du16_{i & 1}" if side is not None else "du16", (M, ff), BF16, dev)
+            before_write(du)
             if fused_du_sums:          # du = (dh W2) * silu'(u) and its per-warp column sums (-> ff.0 bias gradient) in one launch
-                L.call("idb200_gemm_bf16_dsilu_sums", dh16.data_ptr(), w["w2t16"].data_ptr(), du.data_ptr(), sv["u"][i].data_ptr(),
+                L.call("idb200_gemm_bf16_dsilu_sums", g16.data_ptr(), w["w2t16"].data_ptr(), du.data_ptr(), sv["u"][i].data_ptr(),
                        du_part.data_ptr(), M, ff, d, st)
                 sc.colsum(du_part, grads[p + "ff.0.bias"])
             else:
-                gemm_bf16_aux(dh16, w["w2t16"], None, du, sv["u"][i], EPI_BF16_DSILU)  # du = (dh W2) * silu'(u)
+                gemm_bf16_aux(g16, w["w2t16"], None, du, sv["u"][i], EPI_BF16_DSILU)   # du = (dh W2) * silu'(u)
                 sc.colsum(du, grads[p + "ff.0.bias"])
-            sc.dweight(du, sv["a2"][i], grads[p + "ff.0.weight"])
+            dw_async(du, sv["a2"][i], grads[p + "ff.0.weight"])
             E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_BF16)                           # da2 = du W1
             ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1)
+            g16 = dh16_bufs[cur16[0]]
             # ---- attention: h_mid = h_in + out_proj(MHA(a1))
-            sc.dweight(dh16, sv["o"][i], grads[p + "attn.out_proj.weight"])
-            E.gemm_bf16(dh16, w["wot16"], None, do16, E.EPI_BF16)                       # dO = dh Wo
-            dqkv = ws.get("dqkv16", (M, 3 * d), BF16, dev)
+            dw_async(g16, sv["o"][i], grads[p + "attn.out_proj.weight"])
+            E.gemm_bf16(g16, w["wot16"], None, do16, E.EPI_BF16)                        # dO = dh Wo
+            dqkv = ws.get(f"dqkv16_{i & 1}" if side is not None else "dqkv16", (M, 3 * d), BF16, dev)
+            before_write(dqkv)
             if fused_qkv_sums:         # tensor-core kernel: also emits the per-trajectory column sums (= the in_proj bias gradient)
                 L.call("idb200_attention_bwd_sums", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), dqkv_sum_all[i].data_ptr(), B, Lseq,
                        H, int(causal), st)
             else:
                 L.call("idb200_attention_bwd", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), B, Lseq, H, int(causal), 0, st)
                 sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
-            sc.dweight(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
+            dw_async(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
             E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_BF16)                       # da1 = dqkv Wqkv
             ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i)
+        if side is not None:
+            main.wait_stream(side)                           # every weight gradient is final (and the capture's fork is joined)
+            assert cur16[0] == 0                             # 2 nl LayerNorm backward calls: the last one wrote the caller's dh16
         sums = self.sc.colsum_segments(dwb_all, ws.get("dwb_sums", (2 * nl, 3 * d), F32, dev))
         for i in range(nl):
             p = f"{prefix}layers.{i}."

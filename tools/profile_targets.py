@@ -1,6 +1,6 @@
 """One warm-up + two launches of ONE hot kernel at its bench shape, for `ncu --set full -k regex:<kernel>`:
     python tools/profile_targets.py <target>
-targets: qkv_attn mlp_pair encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd attn_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 corrupt_adj"""
+targets: qkv_attn mlp_pair encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd attn_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 gemm_silu_dual gemm_dsilu corrupt_adj"""
 import os
 import sys
 
@@ -71,6 +71,20 @@ elif t == "gemm_qkv384":
     bias = torch.randn((1152,), device=dev)
     out = torch.empty((M, 1152), device=dev, dtype=torch.bfloat16)
     run(lambda: E.gemm_bf16(A, W, bias, out, E.EPI_BF16))
+elif t in ("gemm_silu_dual", "gemm_dsilu"):
+    # the training step's ff.0 forward (u and SiLU(u) from one launch) / dU = (dY W2) . SiLU'(u) with per-warp column sums
+    M, N, K = 4096 * 64, 1536, 384
+    A = torch.randn((M, K), device=dev).bfloat16()
+    W = (torch.randn((N, K), device=dev) / K ** 0.5).bfloat16()
+    bias = torch.randn((N,), device=dev)
+    u = torch.randn((M, N), device=dev).bfloat16()
+    out = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+    part = torch.empty((4 * (M // 128), N), device=dev)
+    st = L.stream(torch.device(dev))
+    if t == "gemm_silu_dual":
+        run(lambda: L.call("idb200_gemm_bf16_aux", A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), u.data_ptr(), M, N, K, 4, st))
+    else:
+        run(lambda: L.call("idb200_gemm_bf16_dsilu_sums", A.data_ptr(), W.data_ptr(), out.data_ptr(), u.data_ptr(), part.data_ptr(), M, N, K, st))
 elif t == "corrupt_adj":
     from interpolated_diffusion_b200.corruptions import keyframes as kf
     from interpolated_diffusion_b200.train import train_interp_levels as tr
