@@ -318,6 +318,40 @@ def test_ln_film_bulk_kernel_vs_torch(M, Lq, d):
     assert ((ob.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-5).all()
     plain = torch.nn.functional.layer_norm(h, (d,), w, b, 1e-5)
     assert float((E.ln_film(h, w, b, None, torch.empty_like(h), Lq) - plain).abs().max()) < 5e-5
+    # training-forward form (idb200_ln_film_save): same output bit for bit + an exact copy of the rows it read
+    hc = torch.full_like(h, float("nan"))
+    ob2 = E.ln_film(h, w, b, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq, h_copy=hc)
+    assert torch.equal(ob2, ob) and torch.equal(hc, h)
+
+
+@pytest.mark.parametrize("M,Lq,d", [(512, 8, 256), (1000, 5, 384)])
+def test_ln_film_save_small_batches(M, Lq, d):
+    """idb200_ln_film_save below the TMA-staged kernel's threshold (the register kernel writes the copy)."""
+    from interpolated_diffusion_b200.models import _engine as E
+    g = torch.Generator(device="cuda").manual_seed(3)
+    h = torch.randn((M, d), generator=g, device="cuda")
+    w, b = torch.randn((d,), generator=g, device="cuda"), torch.randn((d,), generator=g, device="cuda")
+    gb = torch.randn((M // Lq, 2 * d), generator=g, device="cuda")
+    want = E.ln_film(h, w, b, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq)
+    hc = torch.full_like(h, float("nan"))
+    got = E.ln_film(h, w, b, gb, torch.empty((M, d), device="cuda", dtype=torch.bfloat16), Lq, h_copy=hc)
+    assert torch.equal(got, want) and torch.equal(hc, h)
+
+
+@pytest.mark.parametrize("segs,M,N,dt", [(24, 512, 1152, torch.float32), (3, 777, 100, torch.float32), (5, 4096, 768, torch.bfloat16), (1, 64, 33, torch.bfloat16)])
+def test_colsum_segments_vs_torch(segs, M, N, dt):
+    """idb200_colsum_segments: column sums of `segs` stacked [M, N] matrices in two launches (vector and scalar paths, ragged slices)."""
+    from interpolated_diffusion_b200.train import backward as bw
+    g = torch.Generator(device="cuda").manual_seed(segs * 131 + N)
+    src = torch.randn((segs, M, N), generator=g, device="cuda").to(dt)
+    out = torch.full((segs, N), float("nan"), device="cuda")
+    bw._Scratch().colsum_segments(src, out)
+    want = src.double().sum(1)
+    assert (out.double() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()) * (8 if dt == torch.float32 else 1)
+    one = torch.empty((N,), device="cuda")
+    sc = bw._Scratch()
+    for k in (0, segs - 1):                                     # the segmented form equals the plain call on each slice, bit for bit
+        assert torch.equal(sc.colsum(src[k], one), out[k])
 
 
 @pytest.mark.parametrize("B,Hh,Ww,C,act", [(3, 21, 21, 128, True), (5, 9, 12, 32, False), (2, 21, 21, 8, True), (4, 7, 5, 64, True)])
