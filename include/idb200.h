@@ -430,6 +430,13 @@ int idb200_colsum(const void* src, int src_kind, int64_t M, int N, float* scratc
 int idb200_colsum_segments(const void* src, int src_kind, int segs, int64_t M, int N, float* scratch, float scale, int accumulate,
                            float* out, idb200_stream_t stream);
 /* out[W] (+)= scale * sum_r partial[r, W] (fixed order). */
+/* Batched small operations of a training step (pointer tables are HOST arrays, passed on as kernel parameters: graph capturable):
+ * n contiguous fp32 copies dsts[i][0..counts[i]) = srcs[i][...] in one launch per 96 segments (gradient slices into the flat arena); */
+int idb200_multi_copy_f32(const float* const* srcs, float* const* dsts, const int64_t* counts, int n, idb200_stream_t stream);
+/* and, for n fp32 matrices [rows[i], cols[i]]: dsts[i] = bf16 copy, dsts_t[i] = bf16 transpose [cols, rows] (either may be NULL) -- the
+ * per-step operand copies of the token GEMMs' weights (autocast's bf16 casts, train_interp_levels.py:1142-1161). */
+int idb200_cast_weights_bf16(const float* const* srcs, void* const* dsts, void* const* dsts_t, const int* rows, const int* cols, int n,
+                             idb200_stream_t stream);
 int idb200_reduce_rows(const float* partial, int R, int64_t W, float scale, int accumulate, float* out, idb200_stream_t stream);
 /* bf16 elementwise, n even: mode 0 y = silu(u); mode 1 y = g * silu'(u). */
 int idb200_silu_bf16(const void* u, const void* g, int64_t n, int mode, void* y, idb200_stream_t stream);

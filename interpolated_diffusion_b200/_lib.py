@@ -68,6 +68,8 @@ _SIGS = {
     "idb200_colsum_scratch_floats": [c_l, c_i],
     "idb200_tail_scratch_doubles": [],
     "idb200_colsum": [c_p, c_i, c_l, c_i, c_p, c_f, c_i, c_p, c_p],
+    "idb200_multi_copy_f32": [ctypes.POINTER(c_p), ctypes.POINTER(c_p), ctypes.POINTER(c_l), c_i, c_p],
+    "idb200_cast_weights_bf16": [ctypes.POINTER(c_p), ctypes.POINTER(c_p), ctypes.POINTER(c_p), ctypes.POINTER(c_i), ctypes.POINTER(c_i), c_i, c_p],
     "idb200_colsum_segments": [c_p, c_i, c_i, c_l, c_i, c_p, c_f, c_i, c_p, c_p],
     "idb200_reduce_rows": [c_p, c_i, c_l, c_f, c_i, c_p, c_p],
     "idb200_silu_bf16": [c_p, c_p, c_l, c_i, c_p, c_p],

@@ -80,6 +80,60 @@ __global__ void __launch_bounds__(256) transpose_bf16_vec_kernel(const __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Batched small operations of a training step, one launch each instead of one per parameter (at B = 512 per GPU a step had ~130
+// device-to-device copies of gradient slices and ~150 weight casts / transposes of 2-3 us each).  The pointer tables travel as
+// kernel parameters (by value), so the launches are CUDA-graph capturable and need no host-to-device copy.
+constexpr int kMaxCopy = 96;
+struct CopyBatch {
+    const float* src[kMaxCopy];
+    float* dst[kMaxCopy];
+    int n[kMaxCopy];
+};
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ CopyBatch b) {
+    const int seg = blockIdx.y;
+    const float* __restrict__ src = b.src[seg];
+    float* __restrict__ dst = b.dst[seg];
+    const int n = b.n[seg];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// dst[m] = bf16(src[m]) [rows, cols] and dst_t[m] = bf16(src[m]^T) [cols, rows] for a list of fp32 matrices (the per-step bf16 operand
+// copies of the token GEMMs' weights: W for the forward, W^T as the weight operand of dX = dY W); 64 x 64 tiles through shared memory.
+constexpr int kMaxCast = 64;
+struct CastBatch {
+    const float* src[kMaxCast];
+    __nv_bfloat16* dst[kMaxCast];
+    __nv_bfloat16* dst_t[kMaxCast];
+    int rows[kMaxCast], cols[kMaxCast];
+};
+__global__ void __launch_bounds__(256) cast_weights_kernel(const __grid_constant__ CastBatch b) {
+    __shared__ float tile[64][65];
+    const int m = blockIdx.z;
+    const int R = b.rows[m], C = b.cols[m];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    if (r0 >= R || c0 >= C) return;
+    const float* __restrict__ src = b.src[m];
+    __nv_bfloat16* __restrict__ dst = b.dst[m];
+    __nv_bfloat16* __restrict__ dst_t = b.dst_t[m];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int r = ty; r < 64; r += 4) {
+        const int rr = r0 + r, cc = c0 + tx;
+        float v = 0.0f;
+        if (rr < R && cc < C) {
+            v = src[static_cast<long long>(rr) * C + cc];
+            if (dst) dst[static_cast<long long>(rr) * C + cc] = __float2bfloat16_rn(v);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    if (dst_t)
+        for (int c = ty; c < 64; c += 4) {
+            const int cc = c0 + c, rr = r0 + tx;
+            if (cc < C && rr < R) dst_t[static_cast<long long>(cc) * R + rr] = __float2bfloat16_rn(tile[tx][c]);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Column sums of src[M, N] (bias gradients; LayerNorm affine gradients from per-trajectory partials).
 // Stage 1: block (32 columns, one row slice) -> partial[slice, N]; stage 2: reduce_rows.
 template <typename TIn>
@@ -1435,6 +1489,53 @@ extern "C" int idb200_colsum(const void* src, int src_kind, int64_t M, int N, fl
 extern "C" int idb200_colsum_segments(const void* src, int src_kind, int segs, int64_t M, int N, float* scratch, float scale, int accumulate,
                                       float* out, idb200_stream_t stream) {
     return colsum_impl(src, src_kind, segs, M, N, scratch, scale, accumulate, out, stream);
+}
+
+extern "C" int idb200_multi_copy_f32(const float* const* srcs, float* const* dsts, const int64_t* counts, int n, idb200_stream_t stream) {
+    IDB_REQUIRE(n >= 0 && (n == 0 || (srcs && dsts && counts)), IDB200_EINVAL, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i0 = 0; i0 < n; i0 += tb::kMaxCopy) {
+        tb::CopyBatch b{};
+        const int m = n - i0 < tb::kMaxCopy ? n - i0 : tb::kMaxCopy;
+        int64_t mx = 1;
+        for (int i = 0; i < m; ++i) {
+            IDB_REQUIRE(srcs[i0 + i] && dsts[i0 + i] && counts[i0 + i] >= 0 && counts[i0 + i] < (1ll << 31), IDB200_EINVAL, "bad segment %d", i0 + i);
+            b.src[i] = srcs[i0 + i];
+            b.dst[i] = dsts[i0 + i];
+            b.n[i] = static_cast<int>(counts[i0 + i]);
+            if (counts[i0 + i] > mx) mx = counts[i0 + i];
+        }
+        const int gx = static_cast<int>((mx + 1023) / 1024 < 64 ? (mx + 1023) / 1024 : 64);
+        tb::multi_copy_kernel<<<dim3(gx, m), 256, 0, st>>>(b);
+        int rc = check_launch("multi_copy_kernel");
+        if (rc) return rc;
+    }
+    return IDB200_OK;
+}
+
+extern "C" int idb200_cast_weights_bf16(const float* const* srcs, void* const* dsts, void* const* dsts_t, const int* rows, const int* cols, int n,
+                                        idb200_stream_t stream) {
+    IDB_REQUIRE(n >= 0 && (n == 0 || (srcs && dsts && dsts_t && rows && cols)), IDB200_EINVAL, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i0 = 0; i0 < n; i0 += tb::kMaxCast) {
+        tb::CastBatch b{};
+        const int m = n - i0 < tb::kMaxCast ? n - i0 : tb::kMaxCast;
+        int mr = 1, mc = 1;
+        for (int i = 0; i < m; ++i) {
+            IDB_REQUIRE(srcs[i0 + i] && rows[i0 + i] > 0 && cols[i0 + i] > 0 && (dsts[i0 + i] || dsts_t[i0 + i]), IDB200_EINVAL, "bad matrix %d", i0 + i);
+            b.src[i] = srcs[i0 + i];
+            b.dst[i] = static_cast<__nv_bfloat16*>(dsts[i0 + i]);
+            b.dst_t[i] = static_cast<__nv_bfloat16*>(dsts_t[i0 + i]);
+            b.rows[i] = rows[i0 + i];
+            b.cols[i] = cols[i0 + i];
+            if (rows[i0 + i] > mr) mr = rows[i0 + i];
+            if (cols[i0 + i] > mc) mc = cols[i0 + i];
+        }
+        tb::cast_weights_kernel<<<dim3((mc + 63) / 64, (mr + 63) / 64, m), 256, 0, st>>>(b);
+        int rc = check_launch("cast_weights_kernel");
+        if (rc) return rc;
+    }
+    return IDB200_OK;
 }
 
 extern "C" int idb200_reduce_rows(const float* partial, int R, int64_t W, float scale, int accumulate, float* out, idb200_stream_t stream) {

@@ -79,6 +79,27 @@ def sgemm_strided(A: torch.Tensor, a_t: bool, Bm: torch.Tensor, b_t: bool, out: 
     return out
 
 
+def multi_copy(pairs) -> None:
+    """dst.copy_(src) for a list of (dst, src) fp32 tensor pairs in ONE launch per 96 pairs (idb200_multi_copy_f32): the gradient
+    slices a backward pass scatters into the flat arena were ~130 separate 2-3 us copy kernels per step.  Pairs that are not
+    contiguous fp32 of equal size fall back to ``copy_``."""
+    import ctypes
+    fast = []
+    for dst, src in pairs:
+        if (dst.dtype == F32 and src.dtype == F32 and dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
+                and dst.device == src.device and dst.is_cuda):
+            fast.append((dst, src))
+        else:
+            dst.copy_(src)
+    if not fast:
+        return
+    n = len(fast)
+    srcs = (ctypes.c_void_p * n)(*[s.data_ptr() for _, s in fast])
+    dsts = (ctypes.c_void_p * n)(*[d.data_ptr() for d, _ in fast])
+    cnts = (ctypes.c_int64 * n)(*[d.numel() for d, _ in fast])
+    L.call("idb200_multi_copy_f32", srcs, dsts, cnts, n, L.stream(fast[0][0].device))
+
+
 class _Scratch:
     """Workspaces shared by the backward helpers."""
 
@@ -156,16 +177,37 @@ class EncoderBackprop:
         self.saved = None
 
     def _weights(self):
-        out = []
-        for l in self.enc.layers:
+        """Per layer: fp32 views of the parameters + the bf16 operand copies of the four token-GEMM weights (W for the forward, W^T as
+        the weight operand of dX = dY W).  The 8 n_layers casts / transposes are ONE launch (idb200_cast_weights_bf16) into buffers
+        that persist across steps (stable addresses: CUDA-graph friendly)."""
+        import ctypes
+        out, mats = [], []
+        cache = getattr(self, "_w16", None)
+        if cache is None:
+            cache = self._w16 = {}
+        for li, l in enumerate(self.enc.layers):
             f = lambda t: t.detach().float().contiguous()
             w = {"wqkv": f(l.attn.in_proj_weight), "bqkv": f(l.attn.in_proj_bias), "wo": f(l.attn.out_proj.weight), "bo": f(l.attn.out_proj.bias),
                  "w1": f(l.ff[0].weight), "b1": f(l.ff[0].bias), "w2": f(l.ff[2].weight), "b2": f(l.ff[2].bias),
                  "n1w": f(l.norm1.weight), "n1b": f(l.norm1.bias), "n2w": f(l.norm2.weight), "n2b": f(l.norm2.bias)}
             for k in ("wqkv", "wo", "w1", "w2"):
-                w[k + "16"] = w[k].to(BF16)
-                w[k + "t16"] = w[k].t().contiguous().to(BF16)
+                src = w[k]
+                key = (li, k, tuple(src.shape), src.device)
+                bufs = cache.get(key)
+                if bufs is None:
+                    bufs = cache[key] = (torch.empty(src.shape, device=src.device, dtype=BF16),
+                                         torch.empty((src.shape[1], src.shape[0]), device=src.device, dtype=BF16))
+                w[k + "16"], w[k + "t16"] = bufs
+                mats.append((src, bufs[0], bufs[1]))
             out.append(w)
+        n = len(mats)
+        if n:
+            srcs = (ctypes.c_void_p * n)(*[m[0].data_ptr() for m in mats])
+            dsts = (ctypes.c_void_p * n)(*[m[1].data_ptr() for m in mats])
+            dsts_t = (ctypes.c_void_p * n)(*[m[2].data_ptr() for m in mats])
+            rows = (ctypes.c_int * n)(*[m[0].shape[0] for m in mats])
+            cols = (ctypes.c_int * n)(*[m[0].shape[1] for m in mats])
+            L.call("idb200_cast_weights_bf16", srcs, dsts, dsts_t, rows, cols, n, L.stream(mats[0][0].device))
         return out
 
     def forward(self, h: torch.Tensor, B: int, Lseq: int, cond_vec: Optional[torch.Tensor]) -> torch.Tensor:
@@ -317,19 +359,18 @@ class EncoderBackprop:
             main.wait_stream(side)                           # every weight gradient is final (and the capture's fork is joined)
             assert cur16[0] == 0                             # 2 nl LayerNorm backward calls: the last one wrote the caller's dh16
         sums = self.sc.colsum_segments(dwb_all, ws.get("dwb_sums", (2 * nl, 3 * d), F32, dev))
+        pairs = []
         for i in range(nl):
             p = f"{prefix}layers.{i}."
-            grads[p + "norm1.weight"].copy_(sums[2 * i, :d])
-            grads[p + "norm1.bias"].copy_(sums[2 * i, d:2 * d])
-            grads[p + "norm2.weight"].copy_(sums[2 * i + 1, :d])
-            grads[p + "norm2.bias"].copy_(sums[2 * i + 1, d:2 * d])
-            grads[p + "attn.out_proj.bias"].copy_(sums[2 * i + 1, 2 * d:])
+            pairs += [(grads[p + "norm1.weight"], sums[2 * i, :d]), (grads[p + "norm1.bias"], sums[2 * i, d:2 * d]),
+                      (grads[p + "norm2.weight"], sums[2 * i + 1, :d]), (grads[p + "norm2.bias"], sums[2 * i + 1, d:2 * d]),
+                      (grads[p + "attn.out_proj.bias"], sums[2 * i + 1, 2 * d:])]
             if i > 0:
-                grads[f"{prefix}layers.{i - 1}.ff.2.bias"].copy_(sums[2 * i, 2 * d:])
+                pairs.append((grads[f"{prefix}layers.{i - 1}.ff.2.bias"], sums[2 * i, 2 * d:]))
         if fused_qkv_sums:
             qs = self.sc.colsum_segments(dqkv_sum_all, ws.get("dqkv_sums", (nl, 3 * d), F32, dev))
-            for i in range(nl):
-                grads[f"{prefix}layers.{i}.attn.in_proj_bias"].copy_(qs[i])
+            pairs += [(grads[f"{prefix}layers.{i}.attn.in_proj_bias"], qs[i]) for i in range(nl)]
+        multi_copy(pairs)                                    # one launch instead of 7 n_layers copy kernels
         self._dgb = dgb
 
     def backward_film(self, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> Optional[torch.Tensor]:
@@ -360,11 +401,13 @@ class EncoderBackprop:
             sgemm_strided(dgb2, True, cond_vec, True, dW_all)
             sgemm_strided(dgb2, False, film_w, True, dcond)
         two_d = 2 * d
+        pairs = []
         for i in range(nl):
             for k, nm in enumerate(("film1", "film2")):
                 r0 = (2 * i + k) * two_d
-                grads[f"{prefix}layers.{i}.{nm}.weight"].copy_(dW_all[r0:r0 + two_d])
-                grads[f"{prefix}layers.{i}.{nm}.bias"].copy_(db_all[r0:r0 + two_d])
+                pairs.append((grads[f"{prefix}layers.{i}.{nm}.weight"], dW_all[r0:r0 + two_d]))
+                pairs.append((grads[f"{prefix}layers.{i}.{nm}.bias"], db_all[r0:r0 + two_d]))
+        multi_copy(pairs)
         return dcond
 
 
