@@ -254,6 +254,17 @@ class EncoderBackprop:
         return self.backward_film(grads, prefix)
 
     def backward_layers(self, dh: torch.Tensor, dh16: torch.Tensor, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> None:
+        """Every per-layer gradient except the FiLM linears.
+
+        The dX chain (dU GEMM -> da GEMM -> LayerNorm backward -> dO GEMM -> attention backward -> da GEMM -> LayerNorm backward) runs
+        layer by layer.  The weight gradients dW = dY^T X are NOT computed per layer: every layer's dY (bf16 dh before the MLP and
+        before the attention, dU, dqkv) is kept in a buffer stacked over the layers, like the saved activations X already are, and
+        each of the four weight kinds is ONE launch of the split-K GEMM over the stacked token axis [n_layers * M] with splits =
+        n_layers: "split" s then covers exactly layer s and its partial product IS that layer's gradient -- no partial sums, no
+        reduce_rows, 4 GEMM launches instead of 48 + 48, reduction loops of M tokens instead of M / 16 (which is what made the
+        per-layer form inefficient at the cfg-4 per-GPU shape: 32 k-blocks per work unit, 3.2 waves of quantisation per launch).
+        ``IDB200_TRAIN_DW_GROUPED=0`` selects the per-layer form (on a side stream with double-buffered operands; kept as the
+        cross-check)."""
         S = self.saved
         sv, W, film = S["sv"], S["W"], S["film"]
         B, Lseq, H, ff, causal = S["B"], S["L"], S["H"], S["ff"], S["causal"]
@@ -261,28 +272,46 @@ class EncoderBackprop:
         dev = dh.device
         nl = len(W)
         sc, ws = self.sc, self.sc.ws
+        st = L.stream(dev)
+        grouped = os.environ.get("IDB200_TRAIN_DW_GROUPED", "1") != "0" and M % 64 == 0 and d % 64 == 0 and ff % 64 == 0
         da = ws.get("da16", (M, d), BF16, dev)            # gradient w.r.t. the LayerNorm outputs, bf16 (half the bytes of 3 passes)
         do16 = ws.get("do16", (M, d), BF16, dev)
-        # ---- weight-gradient GEMMs on a side stream.  The dX chain (dU GEMM -> da GEMM -> LayerNorm backward -> dO GEMM -> attention
-        # backward -> da GEMM -> LayerNorm backward) is the critical path; the four dW GEMMs of a layer only feed the optimiser.  On
-        # their own stream they fill the SMs while the main stream runs its HBM-bound passes (LayerNorm / attention backward, column
-        # sums), and the tail of one GEMM overlaps the head of the next.  What they read (dh16, dU, dqkv) is double-buffered so the
-        # main stream runs up to one LayerNorm interval ahead; `readers` holds, per buffer, the side-stream event after its last
-        # reader there, awaited before the main stream overwrites the buffer.  Same kernels, same arithmetic order: bit-identical
-        # gradients (IDB200_TRAIN_DW_STREAM=0: everything on one stream).
+        # per-trajectory partials of every LayerNorm ([dw | db | sum_t dh]) and of every in_proj bias: reduced over the batch by
+        # ONE segmented column sum each at the end (was two launches per LayerNorm / layer: 0.4 ms of a 14.6 ms step at B = 512)
+        dwb_all = ws.get("dwb_all", (2 * nl, B, 3 * d), F32, dev)
+        dqkv_sum_all = ws.get("dqkv_sum_all", (nl, B, 3 * d), F32, dev)
+        fused_qkv_sums = 32 < Lseq <= 64            # the tensor-core attention backward emits the per-trajectory sums
+        fused_du_sums = ff % 64 == 0 and d % 64 == 0 and os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0"
+        du_part = ws.get("du_part", (4 * ((M + 127) // 128), ff), F32, dev) if fused_du_sums else None
+        stats = ws.get("ln_stats", (M, 4), F32, dev)
+        dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
+
+        # ---- where each dY lives
         main = torch.cuda.current_stream(dev)
         side = None
-        if os.environ.get("IDB200_TRAIN_DW_STREAM", "1") != "0":
-            if getattr(self, "_dw_stream", None) is None:
-                self._dw_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("IDB200_TRAIN_DW_PRIO", "0")))
-            side = self._dw_stream
         readers: Dict[int, "torch.cuda.Event"] = {}
+        if grouped:
+            g_mlp = ws.get("g16_mlp", (nl, M, d), BF16, dev)        # bf16 dh entering layer i's MLP backward   (dY of ff.2)
+            g_att = ws.get("g16_att", (nl, M, d), BF16, dev)        # bf16 dh entering layer i's attention backward (dY of out_proj)
+            du_all = ws.get("du16_all", (nl, M, ff), BF16, dev)     # dY of ff.0
+            dqkv_all = ws.get("dqkv16_all", (nl, M, 3 * d), BF16, dev)
+            g_mlp[nl - 1].copy_(dh16)
+        else:
+            if os.environ.get("IDB200_TRAIN_DW_STREAM", "1") != "0":
+                if getattr(self, "_dw_stream", None) is None:
+                    self._dw_stream = torch.cuda.Stream(device=dev)
+                side = self._dw_stream
+            dh16_bufs = [dh16, ws.get("dh16_alt", (M, d), BF16, dev)]      # LayerNorm backward k writes buffer (k + 1) % 2: 2 nl calls end in dh16
+        cur16 = [0]
 
         def dw_async(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> None:
+            """Per-layer form: the weight-gradient GEMM on the side stream, ordered after everything enqueued on the main stream."""
+            if grouped:
+                return
             if side is None:
                 sc.dweight(dy, x, out)
                 return
-            side.wait_stream(main)                         # after everything enqueued on the main stream so far (dy is final)
+            side.wait_stream(main)
             with torch.cuda.stream(side):
                 sc.dweight(dy, x, out)
                 ev = torch.cuda.Event()
@@ -294,41 +323,33 @@ class EncoderBackprop:
             if ev is not None:
                 main.wait_event(ev)
 
-        dh16_bufs = [dh16, ws.get("dh16_alt", (M, d), BF16, dev)]      # LayerNorm backward k writes buffer (k + 1) % 2: 2 nl calls end in dh16
-        cur16 = [0]
-        # per-trajectory partials of every LayerNorm ([dw | db | sum_t dh]) and of every in_proj bias: reduced over the batch by
-        # ONE segmented column sum each at the end (was two launches per LayerNorm / layer: 0.4 ms of a 14.6 ms step at B = 512)
-        dwb_all = ws.get("dwb_all", (2 * nl, B, 3 * d), F32, dev)
-        dqkv_sum_all = ws.get("dqkv_sum_all", (nl, B, 3 * d), F32, dev)
-        fused_qkv_sums = 32 < Lseq <= 64            # the tensor-core attention backward emits the per-trajectory sums
-        fused_du_sums = ff % 64 == 0 and d % 64 == 0 and os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0"
-        du_part = ws.get("du_part", (4 * ((M + 127) // 128), ff), F32, dev) if fused_du_sums else None
-        stats = ws.get("ln_stats", (M, 4), F32, dev)
-        dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
-        st = L.stream(dev)
-
-        def ln_bwd(h_saved, nw, nb, j):
+        def ln_bwd(h_saved, nw, nb, j, out16):
             """LayerNorm + FiLM backward of LayerNorm slot j; its partials (incl. the column sums of the UPDATED dh = the bias gradient
-            of the GEMM that accumulated into the residual stream just below this LayerNorm) land in dwb_all[j]."""
+            of the GEMM that accumulated into the residual stream just below this LayerNorm) land in dwb_all[j]; the bf16 copy of the
+            updated dh goes to ``out16``."""
             gb = film[:, j] if film is not None else None
             dg = dgb[:, j] if film is not None else None
-            nxt = dh16_bufs[1 - cur16[0]] if side is not None else dh16
-            before_write(nxt)
+            before_write(out16)
             L.call("idb200_ln_film_bwd2", da.data_ptr(), 1, h_saved.data_ptr(), nw.data_ptr(), nb.data_ptr(), L.ptr(gb),
-                   0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), nxt.data_ptr(), L.ptr(dg),
+                   0 if gb is None else gb.stride(0), B, Lseq, d, dh.data_ptr(), out16.data_ptr(), L.ptr(dg),
                    0 if dg is None else dg.stride(0), dwb_all[j].data_ptr(), 1, stats.data_ptr(), st)
-            if side is not None:
-                cur16[0] = 1 - cur16[0]
 
+        def next16():
+            """Per-layer form: the buffer the next LayerNorm backward writes (ping-pong, or dh16 itself without the side stream)."""
+            if side is None:
+                return dh16
+            cur16[0] = 1 - cur16[0]
+            return dh16_bufs[cur16[0]]
+
+        g16 = g_mlp[nl - 1] if grouped else dh16
         for i in range(nl - 1, -1, -1):
             w = W[i]
             p = f"{prefix}layers.{i}."
-            g16 = dh16_bufs[cur16[0]]                        # bf16 copy of the residual-stream gradient at this point
             # ---- MLP: h_out = h_mid + ff.2(silu(ff.0(a2)))
             dw_async(g16, sv["f"][i], grads[p + "ff.2.weight"])
             if i == nl - 1:
                 sc.colsum(dh, grads[p + "ff.2.bias"])           # (the other layers' come out of the LayerNorm backward above them)
-            du = ws.get(f"du16_{i & 1}" if side is not None else "du16", (M, ff), BF16, dev)
+            du = du_all[i] if grouped else ws.get(f"du16_{i & 1}" if side is not None else "du16", (M, ff), BF16, dev)
             before_write(du)
             if fused_du_sums:          # du = (dh W2) * silu'(u) and its per-warp column sums (-> ff.0 bias gradient) in one launch
                 L.call("idb200_gemm_bf16_dsilu_sums", g16.data_ptr(), w["w2t16"].data_ptr(), du.data_ptr(), sv["u"][i].data_ptr(),
@@ -339,12 +360,12 @@ class EncoderBackprop:
                 sc.colsum(du, grads[p + "ff.0.bias"])
             dw_async(du, sv["a2"][i], grads[p + "ff.0.weight"])
             E.gemm_bf16(du, w["w1t16"], None, da, E.EPI_BF16)                           # da2 = du W1
-            ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1)
-            g16 = dh16_bufs[cur16[0]]
+            g16 = g_att[i] if grouped else next16()
+            ln_bwd(sv["h_mid"][i], w["n2w"], w["n2b"], 2 * i + 1, g16)
             # ---- attention: h_mid = h_in + out_proj(MHA(a1))
             dw_async(g16, sv["o"][i], grads[p + "attn.out_proj.weight"])
             E.gemm_bf16(g16, w["wot16"], None, do16, E.EPI_BF16)                        # dO = dh Wo
-            dqkv = ws.get(f"dqkv16_{i & 1}" if side is not None else "dqkv16", (M, 3 * d), BF16, dev)
+            dqkv = dqkv_all[i] if grouped else ws.get(f"dqkv16_{i & 1}" if side is not None else "dqkv16", (M, 3 * d), BF16, dev)
             before_write(dqkv)
             if fused_qkv_sums:         # tensor-core kernel: also emits the per-trajectory column sums (= the in_proj bias gradient)
                 L.call("idb200_attention_bwd_sums", sv["qkv"][i].data_ptr(), do16.data_ptr(), dqkv.data_ptr(), dqkv_sum_all[i].data_ptr(), B, Lseq,
@@ -354,12 +375,24 @@ class EncoderBackprop:
                 sc.colsum(dqkv, grads[p + "attn.in_proj_bias"])
             dw_async(dqkv, sv["a1"][i], grads[p + "attn.in_proj_weight"])
             E.gemm_bf16(dqkv, w["wqkvt16"], None, da, E.EPI_BF16)                       # da1 = dqkv Wqkv
-            ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i)
+            if grouped:
+                g16 = g_mlp[i - 1] if i > 0 else dh16                                   # the last one lands in the caller's dh16
+            else:
+                g16 = next16()
+            ln_bwd(sv["h_in"][i], w["n1w"], w["n1b"], 2 * i, g16)
         if side is not None:
             main.wait_stream(side)                           # every weight gradient is final (and the capture's fork is joined)
             assert cur16[0] == 0                             # 2 nl LayerNorm backward calls: the last one wrote the caller's dh16
-        sums = self.sc.colsum_segments(dwb_all, ws.get("dwb_sums", (2 * nl, 3 * d), F32, dev))
         pairs = []
+        if grouped:
+            # the four weight kinds, all layers at once: split s of the stacked token axis = layer s
+            for key, dy_all, x_all, n_out, k_in in (("ff.2.weight", g_mlp, sv["f"], d, ff), ("ff.0.weight", du_all, sv["a2"], ff, d),
+                                                    ("attn.out_proj.weight", g_att, sv["o"], d, d),
+                                                    ("attn.in_proj_weight", dqkv_all, sv["a1"], 3 * d, d)):
+                part = ws.get("dw_" + key, (nl, n_out, k_in), F32, dev)
+                L.call("idb200_gemm_bf16_nn_splitk", dy_all.data_ptr(), x_all.data_ptr(), part.data_ptr(), n_out, k_in, nl * M, nl, st)
+                pairs += [(grads[f"{prefix}layers.{i}.{key}"], part[i]) for i in range(nl)]
+        sums = self.sc.colsum_segments(dwb_all, ws.get("dwb_sums", (2 * nl, 3 * d), F32, dev))
         for i in range(nl):
             p = f"{prefix}layers.{i}."
             pairs += [(grads[p + "norm1.weight"], sums[2 * i, :d]), (grads[p + "norm1.bias"], sums[2 * i, d:2 * d]),
@@ -370,7 +403,7 @@ class EncoderBackprop:
         if fused_qkv_sums:
             qs = self.sc.colsum_segments(dqkv_sum_all, ws.get("dqkv_sums", (nl, 3 * d), F32, dev))
             pairs += [(grads[f"{prefix}layers.{i}.attn.in_proj_bias"], qs[i]) for i in range(nl)]
-        multi_copy(pairs)                                    # one launch instead of 7 n_layers copy kernels
+        multi_copy(pairs)                                    # one launch per 96 slices instead of a copy kernel each
         self._dgb = dgb
 
     def backward_film(self, grads: Dict[str, torch.Tensor], prefix: str = "transformer.") -> Optional[torch.Tensor]:
