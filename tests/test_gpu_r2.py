@@ -465,3 +465,63 @@ def test_ln_mlp_pair_vs_ln_film_then_mlp_pair(B, Lq, d, ff, film):
     ref = E.mlp_pair(a, w1, b1, w2p, b2, h0.clone())
     out = E.ln_mlp_pair(h0.clone(), lw, lb, gb, w1, b1, w2p, b2, Lq)
     assert float((out - ref).abs().max()) <= 2e-2 * max(1.0, float((ref - h0).abs().max()))
+
+
+def test_multi_copy_and_cast_weights_batches():
+    """idb200_multi_copy_f32 (more segments than one launch takes, ragged sizes, a non-contiguous pair through the fallback) and
+    idb200_cast_weights_bf16 (ragged matrices: bf16 copy and bf16 transpose == torch's casts, bit for bit)."""
+    import ctypes
+    from interpolated_diffusion_b200 import _lib as L
+    from interpolated_diffusion_b200.train import backward as bw
+    g = torch.Generator(device="cuda").manual_seed(9)
+    sizes = [1, 7, 384, 1000, 147456] + [33 + 5 * i for i in range(120)]
+    srcs = [torch.randn((n,), generator=g, device="cuda") for n in sizes]
+    dsts = [torch.full((n,), float("nan"), device="cuda") for n in sizes]
+    strided_src = torch.randn((16, 8), generator=g, device="cuda")[:, ::2]
+    strided_dst = torch.full((16, 4), float("nan"), device="cuda")
+    bw.multi_copy(list(zip(dsts, srcs)) + [(strided_dst, strided_src)])
+    assert all(torch.equal(d, s) for d, s in zip(dsts, srcs)) and torch.equal(strided_dst, strided_src)
+    shapes = [(1152, 384), (384, 1536), (70, 130), (1, 64), (65, 1)]
+    mats = [torch.randn(s, generator=g, device="cuda") for s in shapes]
+    d0 = [torch.empty(s, device="cuda", dtype=torch.bfloat16) for s in shapes]
+    d1 = [torch.empty((s[1], s[0]), device="cuda", dtype=torch.bfloat16) for s in shapes]
+    n = len(mats)
+    L.call("idb200_cast_weights_bf16", (ctypes.c_void_p * n)(*[m.data_ptr() for m in mats]), (ctypes.c_void_p * n)(*[t.data_ptr() for t in d0]),
+           (ctypes.c_void_p * n)(*[t.data_ptr() for t in d1]), (ctypes.c_int * n)(*[s[0] for s in shapes]), (ctypes.c_int * n)(*[s[1] for s in shapes]),
+           n, L.stream(mats[0].device))
+    for m, a, b in zip(mats, d0, d1):
+        assert torch.equal(a, m.bfloat16()) and torch.equal(b, m.t().contiguous().bfloat16())
+
+
+def test_grouped_weight_gradients_equal_the_per_layer_form(monkeypatch):
+    """EncoderBackprop.backward_layers: one split-K GEMM per weight kind over the stacked layers (default) against the per-layer
+    form (IDB200_TRAIN_DW_GROUPED=0): same gradients up to the fp32 summation order of the token reduction; every other gradient
+    (LayerNorm, biases, dh) is bit-identical."""
+    from interpolated_diffusion_b200.models.transformer import TransformerEncoder
+    from interpolated_diffusion_b200.train import backward as bw
+    torch.manual_seed(5)
+    B, Lq, d, nl = 64, 64, 128, 3
+    enc = TransformerEncoder(d_model=d, n_layers=nl, n_heads=4, d_ff=256, cond_dim=64).cuda()
+    h0 = torch.randn((B * Lq, d), device="cuda")
+    cond = torch.randn((B, 64), device="cuda")
+    dh0 = torch.randn((B * Lq, d), device="cuda") * 0.1
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("IDB200_TRAIN_DW_GROUPED", mode)
+        bp = bw.EncoderBackprop(enc)
+        bp.forward(h0.clone(), B, Lq, cond)
+        grads = {"transformer." + n: torch.zeros_like(p) for n, p in enc.named_parameters()}
+        dh, dh16 = dh0.clone(), dh0.bfloat16()
+        bp.backward_layers(dh, dh16, grads)
+        torch.cuda.synchronize()
+        out[mode] = (grads, dh, dh16)
+    ga, gb = out["1"][0], out["0"][0]
+    assert torch.equal(out["1"][1], out["0"][1]) and torch.equal(out["1"][2], out["0"][2])
+    for k in ga:
+        if ".film" in k:
+            continue
+        if k.endswith(("ff.0.weight", "ff.2.weight", "in_proj_weight", "out_proj.weight")):
+            den = max(1e-12, float(gb[k].norm()))
+            assert float((ga[k] - gb[k]).norm()) / den < 1e-5, k
+        else:
+            assert torch.equal(ga[k], gb[k]), k
