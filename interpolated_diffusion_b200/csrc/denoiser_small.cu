@@ -82,6 +82,56 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const TA* __restrict__ A,
     }
 }
 
+// Small-problem form of the same product (fewer than one 64 x 64 tile per SM, e.g. the per-trajectory linears of a 512-trajectory
+// training batch: [512 x 384] . [384 x 384]^T is 48 tiles on 148 SMs, one latency-bound CTA per SM: 63 us for 0.15 GFLOP):
+// 32 x 32 tiles, 2 x 2 outputs per thread, k-steps of 32.  Every output is still ONE fmaf chain over ascending k: bit-identical
+// to sgemm_tn_kernel.
+template <typename TA>
+__global__ void __launch_bounds__(256) sgemm_tn_small_kernel(const TA* __restrict__ A, long long lda, const float* __restrict__ W,
+                                                             const float* __restrict__ bias, float* __restrict__ out, long long ldo,
+                                                             long long M, int N, int K, int act, int accumulate) {
+    __shared__ float As[32][34], Ws[32][34];                // [k][row]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long m0 = static_cast<long long>(blockIdx.y) * 32;
+    const int n0 = blockIdx.x * 32;
+    float acc[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+            const int r = e >> 5, c = e & 31;
+            const long long m = m0 + r;
+            const int k = k0 + c, nn = n0 + r;
+            As[c][r] = (m < M && k < K) ? to_f32<TA>(A[m * lda + k]) : 0.0f;
+            Ws[c][r] = (nn < N && k < K) ? W[static_cast<long long>(nn) * K + k] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float2 a = *reinterpret_cast<const float2*>(&As[c][ty * 2]);
+            const float2 w = *reinterpret_cast<const float2*>(&Ws[c][tx * 2]);
+            acc[0][0] = fmaf(a.x, w.x, acc[0][0]);
+            acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
+            acc[1][0] = fmaf(a.y, w.x, acc[1][0]);
+            acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const long long m = m0 + ty * 2 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int nn = n0 + tx * 2 + j;
+            if (nn >= N) continue;
+            float v = acc[i][j] + (bias ? bias[nn] : 0.0f);
+            if (act == 1) v = silu_exact(v);
+            if (accumulate) v += out[m * ldo + nn];
+            out[m * ldo + nn] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // conv encoder: one launch per 3x3 pad-1 conv layer (+ SiLU).  A CTA owns (trajectory, block of 32 output
 // channels); input planes stream through shared memory in chunks of <= 32 channels ([23 x 23] zero-bordered
@@ -621,6 +671,14 @@ extern "C" int idb200_sgemm(const void* A, int a_is_bf16, int64_t lda, const flo
     if (M == 0) return IDB200_OK;
     IDB_REQUIRE((M + 63) / 64 <= 65535 * 32LL, IDB200_EUNSUPPORTED, "M too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (((N + 63) / 64) * ((M + 63) / 64) < num_sms()) {   // fewer 64 x 64 tiles than SMs: the small-tile form (same results)
+        dim3 grid((N + 31) / 32, static_cast<unsigned>((M + 31) / 32));
+        if (a_is_bf16)
+            sgemm_tn_small_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(A), lda, W, bias, out, ldo, M, N, K, act, accumulate);
+        else
+            sgemm_tn_small_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(A), lda, W, bias, out, ldo, M, N, K, act, accumulate);
+        return check_launch("sgemm_tn_small_kernel");
+    }
     // grid.y is limited to 65535: loop over row chunks
     const long long chunk = 65535LL * 64;
     for (long long m0 = 0; m0 < M; m0 += chunk) {

@@ -282,7 +282,7 @@ class EncoderBackprop:
         dqkv_sum_all = ws.get("dqkv_sum_all", (nl, B, 3 * d), F32, dev)
         fused_qkv_sums = 32 < Lseq <= 64            # the tensor-core attention backward emits the per-trajectory sums
         fused_du_sums = ff % 64 == 0 and d % 64 == 0 and os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0"
-        du_part = ws.get("du_part", (4 * ((M + 127) // 128), ff), F32, dev) if fused_du_sums else None
+        du_part_all = ws.get("du_part", (nl, 4 * ((M + 127) // 128), ff), F32, dev) if fused_du_sums else None   # per-warp column sums of dU
         stats = ws.get("ln_stats", (M, 4), F32, dev)
         dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
 
@@ -353,8 +353,7 @@ class EncoderBackprop:
             before_write(du)
             if fused_du_sums:          # du = (dh W2) * silu'(u) and its per-warp column sums (-> ff.0 bias gradient) in one launch
                 L.call("idb200_gemm_bf16_dsilu_sums", g16.data_ptr(), w["w2t16"].data_ptr(), du.data_ptr(), sv["u"][i].data_ptr(),
-                       du_part.data_ptr(), M, ff, d, st)
-                sc.colsum(du_part, grads[p + "ff.0.bias"])
+                       du_part_all[i].data_ptr(), M, ff, d, st)                          # (reduced for all layers at the end)
             else:
                 gemm_bf16_aux(g16, w["w2t16"], None, du, sv["u"][i], EPI_BF16_DSILU)   # du = (dh W2) * silu'(u)
                 sc.colsum(du, grads[p + "ff.0.bias"])
@@ -403,6 +402,9 @@ class EncoderBackprop:
         if fused_qkv_sums:
             qs = self.sc.colsum_segments(dqkv_sum_all, ws.get("dqkv_sums", (nl, 3 * d), F32, dev))
             pairs += [(grads[f"{prefix}layers.{i}.attn.in_proj_bias"], qs[i]) for i in range(nl)]
+        if fused_du_sums:
+            us = self.sc.colsum_segments(du_part_all, ws.get("du_sums", (nl, ff), F32, dev))
+            pairs += [(grads[f"{prefix}layers.{i}.ff.0.bias"], us[i]) for i in range(nl)]
         multi_copy(pairs)                                    # one launch per 96 slices instead of a copy kernel each
         self._dgb = dgb
 
