@@ -509,6 +509,82 @@ __global__ void __launch_bounds__(128) ln_bwd_apply_kernel(const TDa* __restrict
     if (kDhSum) *reinterpret_cast<float4*>(dwb_part + b * kW * d + 2 * d + c) = a_dh;
 }
 
+// Pass B for SMALL batches (B below ~8 blocks per SM: at the cfg-4 per-GPU shape B = 512 the form above runs 3.5 blocks of 3 warps
+// per SM and is latency bound: 0.050 ms against 0.033 ms of HBM time).  kG row groups of d / 4 threads walk interleaved tokens
+// (t = g, g + kG, ...) of the trajectory; the groups' column accumulators are merged through shared memory in a fixed order
+// (group 0 + 1 + 2 + 3): deterministic, but a different summation order than the one-group form.
+template <typename TDa, bool kDhSum, int kG>
+__global__ void __launch_bounds__(512) ln_bwd_apply_groups_kernel(const TDa* __restrict__ da, const float* __restrict__ h,
+                                                                  const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                                  const float* __restrict__ gb, long long gb_stride, int L, int d,
+                                                                  const float4* __restrict__ stats, float* __restrict__ dh,
+                                                                  __nv_bfloat16* __restrict__ dh16, float* __restrict__ dgb, long long dgb_stride,
+                                                                  float* __restrict__ dwb_part) {
+    extern __shared__ __align__(16) float4 ln_apply_sm[];      // [kG - 1][5][d / 4]
+    const long long b = blockIdx.x;
+    const int kCg = d >> 2;
+    const int cg = threadIdx.x % kCg, g = threadIdx.x / kCg;
+    const int c = 4 * cg;
+    const float4 w = load4(ln_w + c), bb = load4(ln_b + c);
+    float4 g1 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (gb) {
+        const float4 ga = load4(gb + b * gb_stride + c);
+        g1 = make_float4(1.0f + ga.x, 1.0f + ga.y, 1.0f + ga.z, 1.0f + ga.w);
+    }
+    float4 a_dg = make_float4(0.f, 0.f, 0.f, 0.f), a_db = a_dg, a_dw = a_dg, a_dbb = a_dg, a_dh = a_dg;
+#pragma unroll 2
+    for (int t = g; t < L; t += kG) {
+        const long long m = b * L + t;
+        const float4 st = stats[m];
+        const long long o = m * d + c;
+        const float4 hv = load4(h + o), gg = load4(da + o), dv = load4(dh + o);
+        float4 v2;
+#define IDB_LN_BWD_LANE(k)                                                    \
+        {                                                                      \
+            const float xh = (hv.k - st.x) * st.y;                             \
+            const float n = fmaf(xh, w.k, bb.k);                               \
+            const float dn = gg.k * g1.k;                                      \
+            a_dg.k = fmaf(gg.k, n, a_dg.k);                                    \
+            a_db.k += gg.k;                                                    \
+            a_dw.k = fmaf(dn, xh, a_dw.k);                                     \
+            a_dbb.k += dn;                                                     \
+            v2.k = dv.k + st.y * (dn * w.k - st.z - xh * st.w);                \
+            if (kDhSum) a_dh.k += v2.k;                                        \
+        }
+        IDB_LN_BWD_LANE(x) IDB_LN_BWD_LANE(y) IDB_LN_BWD_LANE(z) IDB_LN_BWD_LANE(w)
+#undef IDB_LN_BWD_LANE
+        *reinterpret_cast<float4*>(dh + o) = v2;
+        if (dh16) {
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v2.x, v2.y), p1 = __floats2bfloat162_rn(v2.z, v2.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned*>(&p0);
+            pk.y = *reinterpret_cast<const unsigned*>(&p1);
+            *reinterpret_cast<uint2*>(dh16 + o) = pk;
+        }
+    }
+    if (g > 0) {
+        float4* dst = ln_apply_sm + static_cast<size_t>(g - 1) * 5 * kCg + cg;
+        dst[0] = a_dg; dst[kCg] = a_db; dst[2 * kCg] = a_dw; dst[3 * kCg] = a_dbb; dst[4 * kCg] = a_dh;
+    }
+    __syncthreads();
+    if (g == 0) {
+        auto add4 = [](float4& a, const float4& o) { a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; };
+#pragma unroll
+        for (int q = 0; q < kG - 1; ++q) {
+            const float4* src = ln_apply_sm + static_cast<size_t>(q) * 5 * kCg + cg;
+            add4(a_dg, src[0]); add4(a_db, src[kCg]); add4(a_dw, src[2 * kCg]); add4(a_dbb, src[3 * kCg]); add4(a_dh, src[4 * kCg]);
+        }
+        if (dgb) {
+            *reinterpret_cast<float4*>(dgb + b * dgb_stride + c) = a_dg;
+            *reinterpret_cast<float4*>(dgb + b * dgb_stride + d + c) = a_db;
+        }
+        constexpr int kW = kDhSum ? 3 : 2;
+        *reinterpret_cast<float4*>(dwb_part + b * kW * d + c) = a_dw;
+        *reinterpret_cast<float4*>(dwb_part + b * kW * d + d + c) = a_dbb;
+        if (kDhSum) *reinterpret_cast<float4*>(dwb_part + b * kW * d + 2 * d + c) = a_dh;
+    }
+}
+
 // One-launch form of the two passes: a block per trajectory runs pass A (a warp per token -> the four row scalars, kept in shared
 // memory) and then pass B (a thread per group of four columns; the two halves of the block walk the two halves of the trajectory's
 // tokens and are merged in a fixed order).  Pass B's second read of da / h (147 KB per trajectory at d = 384, L = 64) comes out of
@@ -1405,6 +1481,14 @@ int ln_bwd_two_pass(const TDa* da, const float* h, const float* ln_w, const floa
     }
     int rc = check_launch("ln_bwd_stats_kernel");
     if (rc) return rc;
+    static const int groups_env = getenv("IDB200_LN_BWD_GROUPS") ? atoi(getenv("IDB200_LN_BWD_GROUPS")) : -1;
+    const bool small = groups_env >= 0 ? groups_env == 4 : (B < 8ll * num_sms() && L >= 8);
+    if (small && d <= 512) {                               // 4 row groups x d / 4 threads (<= 512 threads)
+        const size_t smem = static_cast<size_t>(3) * 5 * (d / 4) * sizeof(float4);
+        ln_bwd_apply_groups_kernel<TDa, kDhSum, 4><<<static_cast<unsigned>(B), d, smem, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, d, stats,
+                                                                                           dh, d16, dgb, dgb_stride, dwb_part);
+        return check_launch("ln_bwd_apply_groups_kernel");
+    }
     ln_bwd_apply_kernel<TDa, kDhSum><<<static_cast<unsigned>(B), d / 4, 0, st>>>(da, h, ln_w, ln_b, gamma_beta, gb_stride, L, d, stats, dh, d16,
                                                                                  dgb, dgb_stride, dwb_part);
     return check_launch("ln_bwd_apply_kernel");
