@@ -5,13 +5,15 @@
 Forward keeps what the backward needs (per layer: the residual stream before each LayerNorm in fp32; LN+FiLM outputs, packed
 qkv, attention output, MLP pre-activation and activation in bf16).  Backward walks the layers in reverse:
 
-* dense contractions on the tcgen05 GEMM: ``dX = dY W`` (transposed weight as the weight operand), ``dW = dY^T X`` (split-K over
-  the tokens on bf16 transposes, partials reduced in a fixed order);
-* everything else in ``csrc/train_bwd.cu``: LayerNorm+FiLM backward (one block per trajectory), attention backward (one block
-  per trajectory x head), SiLU', bias / LayerNorm-affine column sums, out-head and in_proj gradients, the conv stack as
-  im2col + GEMM (dgrad = the same conv with flipped weights).
+* dense contractions on the tcgen05 GEMM: ``dX = dY W`` (transposed weight as the weight operand; the MLP's SiLU / SiLU' passes ride
+  in the ff.0 / dU GEMM epilogues), ``dW = dY^T X`` read in place as MN-major operands -- for the encoder ONE split-K launch per
+  weight kind over the token axis stacked across the layers (split s = layer s: no partial sums to reduce);
+* everything else in ``csrc/train_bwd.cu``: LayerNorm+FiLM backward (two passes: row scalars, then a thread per column group),
+  attention backward (one block per trajectory x head, also the in_proj bias gradient), bias / LayerNorm-affine column sums
+  (per-trajectory partials of all layers reduced once per pass), out-head and in_proj gradients, the conv stack as im2col + GEMM
+  (dgrad = the same conv with flipped weights).
 
-PyTorch owns memory and reshapes (weight transposes / packing, one-hot level rows); no arithmetic of the step runs in torch.
+PyTorch owns memory and reshapes (one-hot level rows, conv weight packing); no arithmetic of the step runs in torch.
 Gradients are written into caller-provided fp32 tensors keyed by the reference's parameter names (``grads[name]``)."""
 from __future__ import annotations
 
