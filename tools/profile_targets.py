@@ -1,6 +1,6 @@
 """One warm-up + two launches of ONE hot kernel at its bench shape, for `ncu --set full -k regex:<kernel>`:
     python tools/profile_targets.py <target>
-targets: qkv_attn mlp_pair encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd attn_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 gemm_silu_dual gemm_dsilu corrupt_adj"""
+targets: qkv_attn mlp_pair encoder_L8 encoder_L64 attn_L8 attn_L64 attn_L256 conv_tap ln_film ln_bwd attn_bwd im2col colsum embed sgemm interp_T256 interp_T64 gemm_qkv384 gemm_silu_dual gemm_dsilu dw_grouped corrupt_adj"""
 import os
 import sys
 
@@ -85,6 +85,13 @@ elif t in ("gemm_silu_dual", "gemm_dsilu"):
         run(lambda: L.call("idb200_gemm_bf16_aux", A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), u.data_ptr(), M, N, K, 4, st))
     else:
         run(lambda: L.call("idb200_gemm_bf16_dsilu_sums", A.data_ptr(), W.data_ptr(), out.data_ptr(), u.data_ptr(), part.data_ptr(), M, N, K, st))
+elif t == "dw_grouped":
+    # weight gradients of all 12 layers as one split-K launch over the stacked token axis (cfg-4 per-GPU shape: M = 32 768 per layer)
+    nl, M, n_out, k_in = 12, 32768, 384, 1536
+    dy = torch.randn((nl, M, n_out), device=dev).bfloat16()
+    x = torch.randn((nl, M, k_in), device=dev).bfloat16()
+    part = torch.empty((nl, n_out, k_in), device=dev)
+    run(lambda: L.call("idb200_gemm_bf16_nn_splitk", dy.data_ptr(), x.data_ptr(), part.data_ptr(), n_out, k_in, nl * M, nl, L.stream(torch.device(dev))))
 elif t == "corrupt_adj":
     from interpolated_diffusion_b200.corruptions import keyframes as kf
     from interpolated_diffusion_b200.train import train_interp_levels as tr
