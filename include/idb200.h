@@ -196,8 +196,9 @@ int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out,
 #define IDB200_EPI_BF16_DSILU 5
 int idb200_gemm_bf16_aux(const void* A, const void* W, const float* bias, void* out, void* aux, int64_t M, int N, int K, int epilogue,
                          idb200_stream_t stream);
-/* Epilogue 5 that also leaves colpart [4 * ceil(M / 128), N] fp32: per 128-row block and epilogue warp, the column sums of the
- * bf16-rounded dU rows of that warp.  Column sums of colpart = column sums of dU = the ff.0 bias gradient (transformer.py:23). */
+/* Epilogue 5 that also leaves colpart [8 * ceil(M / 256), N] fp32 (4 rows per 128-row block, blocks rounded up to whole CTA pairs; every
+ * row is written): per 128-row block and epilogue warp, the column sums of the bf16-rounded dU rows of that warp (zeros for rows >= M).
+ * Column sums of colpart = column sums of dU = the ff.0 bias gradient (transformer.py:23). */
 int idb200_gemm_bf16_dsilu_sums(const void* A, const void* W, void* out, void* aux, float* colpart, int64_t M, int N, int K,
                                 idb200_stream_t stream);
 

@@ -118,7 +118,7 @@ struct GemmParams {
     int conv_P2, conv_PW, conv_PH;
     int conv_shift[kConvMaxKB];
     int conv_col[kConvMaxKB];
-    // EPI_BF16_DSILU only (nullptr otherwise): colpart [4 * ceil(M / 128), N] fp32 receives, per 128-row block and epilogue warp, the
+    // EPI_BF16_DSILU only (nullptr otherwise): colpart [8 * ceil(M / 256), N] fp32 receives, per 128-row block and epilogue warp, the
     // column sums of the bf16-rounded output over the warp's 32 rows -- summed over its rows this is the bias gradient of ff.0
     // (column sums of dU), which otherwise costs a full extra read of dU.
     float* colpart;

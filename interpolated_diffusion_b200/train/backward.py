@@ -284,7 +284,7 @@ class EncoderBackprop:
         dqkv_sum_all = ws.get("dqkv_sum_all", (nl, B, 3 * d), F32, dev)
         fused_qkv_sums = 32 < Lseq <= 64            # the tensor-core attention backward emits the per-trajectory sums
         fused_du_sums = ff % 64 == 0 and d % 64 == 0 and os.environ.get("IDB200_TRAIN_FUSED_SILU", "1") != "0"
-        du_part_all = ws.get("du_part", (nl, 4 * ((M + 127) // 128), ff), F32, dev) if fused_du_sums else None   # per-warp column sums of dU
+        du_part_all = ws.get("du_part", (nl, 8 * ((M + 255) // 256), ff), F32, dev) if fused_du_sums else None   # per-warp column sums of dU
         stats = ws.get("ln_stats", (M, 4), F32, dev)
         dgb = torch.zeros((B, 2 * nl, 2 * d), device=dev, dtype=F32) if film is not None else None
 

@@ -260,7 +260,7 @@ def test_gemm_silu_epilogues_equal_the_separate_passes(M, N, K):
     # the form the training step uses: the same dU + per-warp column sums (column sums of colpart = the ff.0 bias gradient)
     from interpolated_diffusion_b200 import _lib as L
     du2 = torch.full_like(du, float("nan"))
-    part = torch.full((4 * ((M + 127) // 128), N), float("nan"), device="cuda")
+    part = torch.full((8 * ((M + 255) // 256), N), float("nan"), device="cuda")          # 4 rows per 128-row block, blocks rounded up to CTA pairs
     L.call("idb200_gemm_bf16_dsilu_sums", A.data_ptr(), W.data_ptr(), du2.data_ptr(), u.data_ptr(), part.data_ptr(), M, N, K, L.stream(A.device))
     assert torch.equal(du2, du)
     want_cs = du.double().sum(0)

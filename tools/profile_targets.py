@@ -79,7 +79,7 @@ elif t in ("gemm_silu_dual", "gemm_dsilu"):
     bias = torch.randn((N,), device=dev)
     u = torch.randn((M, N), device=dev).bfloat16()
     out = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
-    part = torch.empty((4 * (M // 128), N), device=dev)
+    part = torch.empty((8 * ((M + 255) // 256), N), device=dev)
     st = L.stream(torch.device(dev))
     if t == "gemm_silu_dual":
         run(lambda: L.call("idb200_gemm_bf16_aux", A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), u.data_ptr(), M, N, K, 4, st))
