@@ -356,6 +356,9 @@ typedef struct {
     const int64_t* tab_idx;                       /* [M] row of tab per token, or NULL: the token's position in its trajectory */
     const float* row_a; int64_t row_a_stride;     /* [B or 1, 256] fp32 (stride 0 broadcasts one row) */
     const float* row_b;                           /* [B, 256] fp32 */
+    int tab_rows;                                 /* rows of tab; 1..64 (and n0 + n1 + n2 <= 8) selects the staged-table prologue
+                                                     (the table is copied into shared memory by TMA once per tile and gathered
+                                                     there); 0 = unknown: rows are gathered from global memory */
 } idb200_embed_t;
 typedef struct {
     const float* W;                               /* [D, 256] fp32 */

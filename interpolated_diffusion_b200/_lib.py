@@ -103,7 +103,7 @@ PARAM_EPOCH = 0
 class EmbedDesc(ctypes.Structure):
     """idb200_embed_t (include/idb200.h)."""
     _fields_ = [("src0", c_p), ("n0", c_i), ("src1", c_p), ("n1", c_i), ("src2", c_p), ("n2", c_i), ("Wf", c_p), ("tab", c_p),
-                ("tab_idx", c_p), ("row_a", c_p), ("row_a_stride", c_l), ("row_b", c_p)]
+                ("tab_idx", c_p), ("row_a", c_p), ("row_a_stride", c_l), ("row_b", c_p), ("tab_rows", c_i)]
 
 
 class HeadDesc(ctypes.Structure):

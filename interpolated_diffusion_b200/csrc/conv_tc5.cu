@@ -13,6 +13,10 @@
 // K-major layout; the nine weight taps [64 x 32] stay resident in the same layout.  Per maze: 4 tiles x 9 taps x 2
 // tcgen05.mma (M=128, N=64, K=16), accumulators double-buffered in TMEM (2 x 4 x 64 columns) so the epilogue of maze
 // i (bias + SiLU + masked column sums -> mean) overlaps the first conv and the MMAs of maze i+1.
+// The single activation buffer is handed over PER TILE: the first conv walks the pixels in order, signals tile t as soon
+// as every activation row that tile reads is written (act_full[t]) and overwrites a band of rows as soon as the last MMA
+// tile of the previous maze that reads it has completed (tile_done[t]) -- so the first conv of maze i+1 runs under the
+// MMAs of maze i instead of after them (a per-maze hand-over serialised the two: 15.3 k cycles per maze).
 // Warps: 0..3 epilogue (TMEM lane quadrants), 4 MMA issuer + TMEM allocator, 5..12 first conv (CUDA cores).
 // One persistent CTA per SM.  Requires C1 = 32, C2 = 64, H * PW <= 512 (other shapes: idb200_conv_encoder_tc).
 #include <cuda_bf16.h>
@@ -73,11 +77,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
     float* b1s = b0s + kC1;
     float* red = b1s + kC2;                                           // [4][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * kC2);
-    uint64_t* act_full = bars + 0;                                    // conv warps -> MMA           (8 arrivals)
-    uint64_t* act_empty = bars + 1;                                   // MMA commit -> conv warps
-    uint64_t* acc_full = bars + 2;                                    // [2] MMA commit -> epilogue
-    uint64_t* acc_empty = bars + 4;                                   // [2] epilogue -> MMA         (4 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* act_full = bars + 0;                                    // [4] conv warps -> MMA: the rows tile t reads are written (8 arrivals)
+    uint64_t* tile_done = bars + 4;                                   // [4] MMA commit -> conv warps: tile t has read its rows
+    uint64_t* acc_full = bars + 8;                                    // [2] MMA commit -> epilogue
+    uint64_t* acc_empty = bars + 10;                                  // [2] epilogue -> MMA         (4 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = p.H * p.W, PWi = p.W + 2, PP = (p.H + 2) * PWi;
@@ -97,8 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
         *reinterpret_cast<uint4*>(wB + tap * 4096 + sw64_offset(n, ch)) = v;
     }
     if (warp == 4 && lane == 0) {
-        mbar_init(act_full, 8);
-        mbar_init(act_empty, 1);
+        for (int i = 0; i < kTiles; ++i) { mbar_init(&act_full[i], 8); mbar_init(&tile_done[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_mbar_init();
     }
@@ -124,6 +127,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        const int o = ct & 3;                                            // this thread's channel octet (256 % 4 == 0: fixed)
+        const int n_items = HW * 4, n_iters = (n_items + 255) >> 8;       // a pass = 64 consecutive pixels x 4 octets
+        // last pass that writes a row MMA tile t reads (tile t reads padded positions t * 128 .. t * 128 + 129 + 2 PW)
+        int last_i[kTiles];
+#pragma unroll
+        for (int t = 0; t < kTiles; ++t) {
+            const int ylast = min(p.H - 1, (t * 128 + 128 + 2 * p.PW) / p.PW - 1);
+            last_i[t] = ylast < 0 ? 0 : (ylast * p.W + p.W - 1) >> 6;
+        }
+        // cin == 1 (no SDF channel): this thread's 9 x 8 first-layer weights live in registers (18 of the 27 shared-memory loads per item)
+        const bool kRegW = p.cin == 1;
+        float wr[9][8];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wr[tap][j] = kRegW ? w0s[tap * kC1 + o * 8 + j] : 0.0f;
+        auto signal_tiles = [&](int iter, uint32_t prev) {
+#pragma unroll
+            for (int t = 0; t < kTiles; ++t) {
+                if (last_i[t] == iter) {                                 // (warp-uniform)
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_wait(&tile_done[t], prev, 74);              // the MMA warp has consumed this barrier's previous phase
+                        mbar_arrive(&act_full[t]);
+                    }
+                }
+            }
+        };
         long long it = 0;
         if (static_cast<long long>(blockIdx.x) < p.B) load_plane(blockIdx.x, 0);
         for (long long b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
@@ -131,24 +163,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
             asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's part of this maze's plane has landed
             named_barrier_sync(1, 256);                                 // ... and everybody's; every warp is done reading the other buffer
             if (b + gridDim.x < p.B) load_plane(b + gridDim.x, buf ^ 1);  // prefetch the next maze while this one is computed
-            mbar_wait(act_empty, (it & 1) ^ 1, 70);                     // the MMAs of the previous maze have read the activations
             const float* pl = plane + buf * kMaxPlane;
+            const uint32_t prev = static_cast<uint32_t>((it & 1) ^ 1);    // parity of the previous maze's phases
             // item = (pixel, channel octet): 8 channels of one pixel -> one 16-byte chunk, written to the 3 shifted copies
-            for (int item = ct; item < HW * 4; item += 256) {
-                const int pix = item >> 2, o = item & 3;
+            for (int iter = 0; iter < n_iters; ++iter) {
+                const int item = ct + (iter << 8);
+                // the rows this pass writes (positions up to the end of its last pixel row) are read by MMA tiles <= tneed of the
+                // previous maze (tiles complete in order)
+                {
+                    const int pmax = min(iter * 64 + 63, HW - 1);
+                    const int tneed = min(kTiles - 1, ((pmax / p.W + 1) * p.PW + p.W) >> 7);
+                    mbar_wait(&tile_done[tneed], prev, 70);
+                }
+                if (item < n_items) {
+                const int pix = item >> 2;
                 const int y = pix / p.W, x = pix - y * p.W;
                 float a[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a[j] = b0s[o * 8 + j];
-                for (int c = 0; c < p.cin; ++c) {
-                    const float* ip = pl + c * PP + y * PWi + x;
+                if (kRegW) {
+                    const float* ip = pl + y * PWi + x;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const float iv = ip[(tap / 3) * PWi + (tap % 3)];
-                        const float4 wa = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8);
-                        const float4 wb = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8 + 4);
-                        a[0] = fmaf(iv, wa.x, a[0]); a[1] = fmaf(iv, wa.y, a[1]); a[2] = fmaf(iv, wa.z, a[2]); a[3] = fmaf(iv, wa.w, a[3]);
-                        a[4] = fmaf(iv, wb.x, a[4]); a[5] = fmaf(iv, wb.y, a[5]); a[6] = fmaf(iv, wb.z, a[6]); a[7] = fmaf(iv, wb.w, a[7]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) a[j] = fmaf(iv, wr[tap][j], a[j]);
+                    }
+                } else {
+                    for (int c = 0; c < p.cin; ++c) {
+                        const float* ip = pl + c * PP + y * PWi + x;
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const float iv = ip[(tap / 3) * PWi + (tap % 3)];
+                            const float4 wa = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8);
+                            const float4 wb = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8 + 4);
+                            a[0] = fmaf(iv, wa.x, a[0]); a[1] = fmaf(iv, wa.y, a[1]); a[2] = fmaf(iv, wa.z, a[2]); a[3] = fmaf(iv, wa.w, a[3]);
+                            a[4] = fmaf(iv, wb.x, a[4]); a[5] = fmaf(iv, wb.y, a[5]); a[6] = fmaf(iv, wb.z, a[6]); a[7] = fmaf(iv, wb.w, a[7]);
+                        }
                     }
                 }
                 uint4 pk;
@@ -159,10 +210,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
                 const int q = (y + 1) * p.PW + (x + 1);                 // padded linear position of this pixel
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) *reinterpret_cast<uint4*>(act + kx * act_bytes + sw64_offset(q - kx, o)) = pk;
+                }
+                signal_tiles(iter, prev);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(act_full);
         }
     } else if (warp == 4) {
         // ===================== MMA issuer: warp-uniform schedule, one elected lane issues =====================
@@ -173,10 +223,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
             for (long long b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
                 const int buf = static_cast<int>(it & 1);
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 71);    // the epilogue drained this accumulator buffer
-                mbar_wait(act_full, it & 1, 72);
-                tc_fence_after();
 #pragma unroll 1
                 for (int t = 0; t < kTiles; ++t) {
+                    mbar_wait(&act_full[t], it & 1, 72);                 // the rows this tile reads are written
+                    tc_fence_after();
                     const uint32_t d = tmem_base + buf * (kTiles * kC2) + t * kC2;
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
@@ -189,11 +239,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
                         }
                         __syncwarp();
                     }
+                    if (elect_one_sync()) umma_commit(&tile_done[t]);
+                    __syncwarp();
                 }
-                if (elect_one_sync()) {
-                    umma_commit(act_empty);
-                    umma_commit(&acc_full[buf]);
-                }
+                if (elect_one_sync()) umma_commit(&acc_full[buf]);
                 __syncwarp();
             }
         }
@@ -278,7 +327,7 @@ extern "C" int idb200_conv_encoder_tc5(const float* occ, const float* sdf, int64
     IDB_REQUIRE(aligned(w1_packed_bf16, 16), IDB200_EALIGN, "packed weights must be 16-byte aligned");
     const int act_rows = conv5::kTiles * 128 + 2 * PW + 8;              // last tile + largest tap shift (a multiple of 8)
     const size_t smem = 3 * static_cast<size_t>(act_rows) * 64 + 9 * 4096 +
-                        (2 * conv5::kMaxPlane + 2 * 9 * conv5::kC1 + conv5::kC1 + conv5::kC2 + 4 * conv5::kC2) * 4 + 64 + 1024;
+                        (2 * conv5::kMaxPlane + 2 * 9 * conv5::kC1 + conv5::kC1 + conv5::kC2 + 4 * conv5::kC2) * 4 + 128 + 1024;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(conv5::conv2l_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -93,6 +93,7 @@ struct Params {
     const float* e_row_a;       // [B or 1, 256]
     long long e_row_a_stride;
     const float* e_row_b;       // [B, 256]
+    int e_stage;                // 1: tab has <= 64 rows and F <= 8 -> the table is staged in the (idle) X region by TMA, swizzled
     // optional fused output head (replaces the write of h): y[M, D] = (h + bias_last) . W^T + b
     const float* o_w;           // [D, 256] or nullptr: write h
     const float* o_b;           // [D]
@@ -241,7 +242,7 @@ template <bool kProf, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
                      const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_w1,
-                     const __grid_constant__ CUtensorMap tm_w2, const Params p) {
+                     const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_tab, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     __builtin_assume(__isShared(smem));             // the integer round trip hides the address space: keep LDS / STS, not generic LD / ST
@@ -264,7 +265,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
     uint64_t* pm_empty = pm_full + 1;
     uint64_t* film_full = pm_empty + 1;             // FiLM rows of the next LayerNorm staged in the scratch region (tx bytes)
     uint64_t* stg_free = film_full + 1;             // every compute warp has read what it needs of the staged q|k|v (kCW arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 1);
+    uint64_t* tab_full = stg_free + 1;              // token-assembly table staged in the X region (tx bytes), one phase per tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_full + 1);
     float2* stat = reinterpret_cast<float2*>(smem + kOffStat);
     float* sPA = reinterpret_cast<float*>(smem + kOffPA);
     float* sPM = reinterpret_cast<float*>(smem + kOffPM);
@@ -288,6 +290,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         tma_prefetch_desc(&tm_wo);
         tma_prefetch_desc(&tm_w1);
         tma_prefetch_desc(&tm_w2);
+        if (p.e_stage) tma_prefetch_desc(&tm_tab);
     }
     if (warp == 1 && lane == 0) {
         mbar_init(x_full, kArr);
@@ -309,6 +312,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         mbar_init(pm_empty, kCW);
         mbar_init(film_full, 1);
         mbar_init(stg_free, kCW);
+        mbar_init(tab_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -628,6 +632,23 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         auto tile_of = [&](int trip) { return kPair ? 2 * trip + static_cast<int>(rank) : trip; };
         auto arrive_mma = [&](uint64_t* bar) { if (kPair) mbar_arrive_leader(bar); else mbar_arrive(bar); };
         if (trip0 < trips) stage_film(tile_of(trip0), 0, 0);
+        // Token-assembly table (p.e_stage: <= 64 rows of 256 floats): eight [64 x 32] fp32 SWIZZLE_128B boxes into the X region,
+        // which is idle from the last FF1 of a tile to the first LayerNorm of the next.  The tile's rows gather their table row
+        // with one conflict-free LDS.128 per 4 columns (a row-per-thread gather from global memory costs 32 L1 wavefronts per
+        // load instruction: ~8 k cycles per tile, like the row-per-thread read of h it replaces).  The table is the same for every
+        // tile; it is re-staged per tile because X is the LayerNorm output in between.
+        // tab_full completes TWO phases per tile (the copy, then a plain arrive just before the next copy is issued), so the prologue
+        // always waits for parity 0 and no per-tile counter stays live across the layers.
+        auto stage_tab = [&](bool first) {
+            if (p.e_stage && ew == 1 && lane == 0) {
+                if (!first) mbar_arrive(tab_full);
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(tab_full, 65536u);
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) tma_load_2d(smem + kOffX + c * 8192, &tm_tab, tab_full, c * 32, 0);
+            }
+        };
+        if (trip0 < trips) stage_tab(true);
         // attention work unit of this warp: 16-row block rb, head hh of the group
         const int rb = ew & 7, hh = ew >> 3;
         uint32_t okbits = 0;                             // L < 16: block-diagonal mask of the 16 x 16 score block (per thread, fixed)
@@ -659,6 +680,61 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                         r[4 * j + 1] = __float_as_uint(v.y);
                         r[4 * j + 2] = __float_as_uint(v.z);
                         r[4 * j + 3] = __float_as_uint(v.w);
+                    }
+                    tmem_st_32x32(tmem_row + part * 64 + cc * 32, r);
+                }
+                tmem_st_wait();
+            } else if (p.e_stage) {
+                // fused token assembly + in_proj with the table staged in shared memory (idb200_embed_tokens; same fp32 operation
+                // order: fma chain over the features, + tab + row_a + row_b)
+                const int F = p.e_n0 + p.e_n1 + p.e_n2;
+                float f[8];
+                long long bb = 0;
+                int trow = 0;
+                if (live) {
+                    bb = m / L;
+                    trow = p.e_tab_idx ? static_cast<int>(p.e_tab_idx[m]) : static_cast<int>(m - bb * L);
+                    trow = min(max(trow, 0), 63);                        // (an out-of-range index must not leave the staged boxes)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v = 0.0f;
+                        if (j < p.e_n0) v = p.e_src0[m * p.e_n0 + j];
+                        else if (j < p.e_n0 + p.e_n1) v = p.e_src1[m * p.e_n1 + (j - p.e_n0)];
+                        else if (j < F) v = p.e_src2[m * p.e_n2 + (j - p.e_n0 - p.e_n1)] ? 1.0f : 0.0f;
+                        f[j] = v;
+                    }
+                }
+                const float4* ra4 = reinterpret_cast<const float4*>(p.e_row_a + bb * p.e_row_a_stride) + part * 16;
+                const float4* rb4 = reinterpret_cast<const float4*>(p.e_row_b + bb * kD) + part * 16;
+                const float4* wf4 = reinterpret_cast<const float4*>(p.e_wf) + part * 16;
+                const uint32_t tab_s = smem_u32(smem + kOffX) + static_cast<uint32_t>(part * 2) * 8192u + static_cast<uint32_t>(trow) * 128u;
+                const uint32_t tsw = static_cast<uint32_t>(trow & 7);
+                mbar_wait(tab_full, 0u, 62);
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (j < F) {
+                                    const float4 w = __ldg(wf4 + j * (kD / 4) + cc * 8 + j4);
+                                    acc.x = fmaf(f[j], w.x, acc.x);
+                                    acc.y = fmaf(f[j], w.y, acc.y);
+                                    acc.z = fmaf(f[j], w.z, acc.z);
+                                    acc.w = fmaf(f[j], w.w, acc.w);
+                                }
+                            }
+                            const float4 tb = lds128(tab_s + static_cast<uint32_t>(cc) * 8192u + ((static_cast<uint32_t>(j4) ^ tsw) << 4));
+                            const float4 a = __ldg(ra4 + cc * 8 + j4), b = __ldg(rb4 + cc * 8 + j4);
+                            acc = make_float4(acc.x + tb.x + a.x + b.x, acc.y + tb.y + a.y + b.y, acc.z + tb.z + a.z + b.z, acc.w + tb.w + a.w + b.w);
+                        }
+                        r[4 * j4 + 0] = __float_as_uint(acc.x);
+                        r[4 * j4 + 1] = __float_as_uint(acc.y);
+                        r[4 * j4 + 2] = __float_as_uint(acc.z);
+                        r[4 * j4 + 3] = __float_as_uint(acc.w);
                     }
                     tmem_st_32x32(tmem_row + part * 64 + cc * 32, r);
                 }
@@ -873,6 +949,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 mbar_wait(h_ready, 1u, 57);                              // the last FF2 has landed in h
                 tc_fence_after();
                 stamp(P_WH2);
+                if (l == NL - 1 && trip + trip_stride < trips) stage_tab(false);   // every MMA reading X has completed: the next tile's table
             }
             // ---- TMEM -> residual stream (+ the pending bias), or straight through the output head ----
             if (p.o_w != nullptr) {
@@ -1005,7 +1082,14 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     p.h = h; p.params = params; p.cb_total = cb_total; p.gb = gb; p.gb_stride = gb_stride; p.gb_ln_stride = gb_ln_stride; p.M = M; p.L = L; p.causal = causal;
     p.ff = ff; p.n_layers = n_layers; p.film_mode = gb ? (film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone; p.prof = nullptr;
     p.dbg_skip = getenv("IDB200_DBG_SKIP") ? atoi(getenv("IDB200_DBG_SKIP")) : 0;
+    CUtensorMap ttab = tqk;                                                // (unused unless the table is staged)
     if (emb) {
+        const int F = emb->n0 + emb->n1 + emb->n2;
+        if (emb->tab_rows >= 1 && emb->tab_rows <= 64 && F <= 8) {
+            rc = make_tmap_2d(&ttab, emb->tab, 4, static_cast<uint64_t>(emb->tab_rows), 256, 64, 32);
+            if (rc) return rc;
+            p.e_stage = 1;
+        }
         p.e_src0 = emb->src0; p.e_src1 = emb->src1; p.e_src2 = emb->src2; p.e_n0 = emb->n0; p.e_n1 = emb->n1; p.e_n2 = emb->n2;
         p.e_wf = emb->Wf; p.e_tab = emb->tab; p.e_tab_idx = reinterpret_cast<const long long*>(emb->tab_idx);
         p.e_row_a = emb->row_a; p.e_row_a_stride = emb->row_a_stride; p.e_row_b = emb->row_b;
@@ -1025,10 +1109,10 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     cfg.attrs = at;
     cfg.numAttrs = 1;
     auto launch = [&](bool profiled) -> cudaError_t {
-        if (pair) return profiled ? cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<true, true>, tqk, tv, two, t1, t2, p)
-                                  : cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<false, true>, tqk, tv, two, t1, t2, p);
-        return profiled ? cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<true, false>, tqk, tv, two, t1, t2, p)
-                        : cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<false, false>, tqk, tv, two, t1, t2, p);
+        if (pair) return profiled ? cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<true, true>, tqk, tv, two, t1, t2, ttab, p)
+                                  : cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<false, true>, tqk, tv, two, t1, t2, ttab, p);
+        return profiled ? cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<true, false>, tqk, tv, two, t1, t2, ttab, p)
+                        : cudaLaunchKernelEx(&cfg, ef::encoder_fused_kernel<false, false>, tqk, tv, two, t1, t2, ttab, p);
     };
     if (prof) {                                                           // dev only: synchronous, prints the phase breakdown
         static unsigned long long* dprof = nullptr;

@@ -110,7 +110,7 @@ def denoiser_fused(pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causa
     ft, fts, ftl = (None, 0, 0) if film is None else film.strides()
     emb = L.EmbedDesc(src0.data_ptr(), src0.shape[-1], L.ptr(src1), 0 if src1 is None else src1.shape[-1], L.ptr(src2),
                       0 if src2 is None else src2.shape[-1], Wf.data_ptr(), tab.data_ptr(), L.ptr(tab_idx), row_a.data_ptr(),
-                      0 if row_a.shape[0] == 1 else row_a.stride(0), row_b.data_ptr())
+                      0 if row_a.shape[0] == 1 else row_a.stride(0), row_b.data_ptr(), int(tab.shape[0]))
     head = L.HeadDesc(W_out.data_ptr(), b_out.data_ptr(), y.data_ptr(), W_out.shape[0])
     L.call("idb200_denoiser_fused", ctypes.byref(emb), ctypes.byref(head), None, f["params"].data_ptr(), f["bias_last"].data_ptr(),
            L.ptr(ft), fts, ftl, int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),

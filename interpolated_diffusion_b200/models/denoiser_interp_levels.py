@@ -2,6 +2,8 @@
 ``denoiser_interp_levels_causal.py``): same constructor, parameter tree and ``forward(x_s, s, mask, cond)``."""
 from typing import Dict, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -37,7 +39,7 @@ class InterpLevelDenoiser(nn.Module):
         # token assembly + out head inside the fused-encoder launch (idb200_denoiser_fused): h never exists in HBM (saves the
         # [M, 256] fp32 buffer, 4.3 GB at B = 65536, T = 64).  Off by default: the thread-per-row prologue is 2 % slower per
         # generation than the dedicated embed / head kernels (measured, round 1).
-        self.fuse_io = False
+        self.fuse_io = os.environ.get("IDB200_FUSE_IO", "1") != "0"
         self.fuse_head = True            # the out head as the tile epilogue of the fused-encoder launch (h is not written back)
         self.pad_causal = True           # causal models: right-pad T < 128 to a divisor of 128 so the whole-encoder kernel applies
         self._cache = {}

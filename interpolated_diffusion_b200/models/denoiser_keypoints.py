@@ -2,6 +2,8 @@
 ``forward(z_t, t, idx, known_mask, cond, T)``; executed by libidb200 (CUDA only, inference / no autograd)."""
 from typing import Dict, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -56,7 +58,7 @@ class KeypointDenoiser(nn.Module):
         # token assembly + out head inside the fused-encoder launch (idb200_denoiser_fused): h never exists in HBM (saves the
         # [M, 256] fp32 buffer, 4.3 GB at B = 65536, T = 64).  Off by default: the thread-per-row prologue is 2 % slower per
         # generation than the dedicated embed / head kernels (measured, round 1).
-        self.fuse_io = False
+        self.fuse_io = os.environ.get("IDB200_FUSE_IO", "1") != "0"
         self.fuse_head = True            # the out head as the tile epilogue of the fused-encoder launch (h is not written back)
         self._cache = {}
         self._ws = E.Workspace()
