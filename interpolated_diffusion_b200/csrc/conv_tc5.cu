@@ -23,6 +23,10 @@
 
 #include "tc_common.cuh"
 
+#ifndef IDB200_CONV_IPT
+#define IDB200_CONV_IPT 2
+#endif
+
 namespace idb200 {
 using namespace tc;
 
@@ -128,34 +132,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         const int o = ct & 3;                                            // this thread's channel octet (256 % 4 == 0: fixed)
-        const int n_items = HW * 4, n_iters = (n_items + 255) >> 8;       // a pass = 64 consecutive pixels x 4 octets
-        // last pass that writes a row MMA tile t reads (tile t reads padded positions t * 128 .. t * 128 + 129 + 2 PW)
-        int last_i[kTiles];
+        constexpr int kIPT = IDB200_CONV_IPT;                                          // items per thread and pass: two independent FMA / SiLU chains in flight
+        constexpr int kPassPix = 64 * kIPT;                              // a pass = kPassPix consecutive pixels x 4 octets
+        const int n_items = HW * 4, n_iters = (n_items + 256 * kIPT - 1) / (256 * kIPT);     // <= 5 (H * W <= 576)
+        // Per pass, packed 4 bits each: low 2 bits = the last MMA tile of the PREVIOUS maze that reads a row this pass writes (tiles
+        // complete in order; tile t reads padded positions t * 128 .. t * 128 + 129 + 2 PW), and one nibble of tile bits = the tiles
+        // whose rows are complete after this pass.
+        uint32_t need_bits = 0, sig_bits = 0;
+        for (int i = 0; i < n_iters; ++i) {
+            const int pmax = min(i * kPassPix + kPassPix - 1, HW - 1);
+            need_bits |= static_cast<uint32_t>(min(kTiles - 1, ((pmax / p.W + 1) * p.PW + p.W) >> 7)) << (4 * i);
+        }
 #pragma unroll
         for (int t = 0; t < kTiles; ++t) {
             const int ylast = min(p.H - 1, (t * 128 + 128 + 2 * p.PW) / p.PW - 1);
-            last_i[t] = ylast < 0 ? 0 : (ylast * p.W + p.W - 1) >> 6;
+            const int last_i = ylast < 0 ? 0 : (ylast * p.W + p.W - 1) / kPassPix;
+            sig_bits |= 1u << (4 * last_i + t);
         }
+        const float inv_w = 1.0f / static_cast<float>(p.W);             // pix / W for pix < 1024: (pix + 0.5) * (1 / W) truncates exactly
         // cin == 1 (no SDF channel): this thread's 9 x 8 first-layer weights live in registers (18 of the 27 shared-memory loads per item)
         const bool kRegW = p.cin == 1;
-        float wr[9][8];
+        float wr[9][8], br[8];
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
             for (int j = 0; j < 8; ++j) wr[tap][j] = kRegW ? w0s[tap * kC1 + o * 8 + j] : 0.0f;
-        auto signal_tiles = [&](int iter, uint32_t prev) {
 #pragma unroll
-            for (int t = 0; t < kTiles; ++t) {
-                if (last_i[t] == iter) {                                 // (warp-uniform)
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_wait(&tile_done[t], prev, 74);              // the MMA warp has consumed this barrier's previous phase
-                        mbar_arrive(&act_full[t]);
-                    }
-                }
-            }
-        };
+        for (int j = 0; j < 8; ++j) br[j] = b0s[o * 8 + j];
         long long it = 0;
         if (static_cast<long long>(blockIdx.x) < p.B) load_plane(blockIdx.x, 0);
         for (long long b = blockIdx.x; b < p.B; b += gridDim.x, ++it) {
@@ -166,52 +169,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv2l_tc5_kernel(const Params p)
             const float* pl = plane + buf * kMaxPlane;
             const uint32_t prev = static_cast<uint32_t>((it & 1) ^ 1);    // parity of the previous maze's phases
             // item = (pixel, channel octet): 8 channels of one pixel -> one 16-byte chunk, written to the 3 shifted copies
+#pragma unroll 1
             for (int iter = 0; iter < n_iters; ++iter) {
-                const int item = ct + (iter << 8);
-                // the rows this pass writes (positions up to the end of its last pixel row) are read by MMA tiles <= tneed of the
-                // previous maze (tiles complete in order)
-                {
-                    const int pmax = min(iter * 64 + 63, HW - 1);
-                    const int tneed = min(kTiles - 1, ((pmax / p.W + 1) * p.PW + p.W) >> 7);
-                    mbar_wait(&tile_done[tneed], prev, 70);
-                }
-                if (item < n_items) {
-                const int pix = item >> 2;
-                const int y = pix / p.W, x = pix - y * p.W;
-                float a[8];
+                mbar_wait(&tile_done[(need_bits >> (4 * iter)) & 3u], prev, 70);
+                float a[kIPT][8];
+                int q[kIPT];
+                bool valid[kIPT];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = b0s[o * 8 + j];
-                if (kRegW) {
-                    const float* ip = pl + y * PWi + x;
+                for (int u = 0; u < kIPT; ++u) {
+                    const int item = ct + ((iter * kIPT + u) << 8);
+                    valid[u] = item < n_items;
+                    const int pix = min(item >> 2, HW - 1);
+                    const int y = static_cast<int>((static_cast<float>(pix) + 0.5f) * inv_w), x = pix - y * p.W;
+                    q[u] = (y + 1) * p.PW + (x + 1);                    // padded linear position of this pixel
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const float iv = ip[(tap / 3) * PWi + (tap % 3)];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) a[j] = fmaf(iv, wr[tap][j], a[j]);
-                    }
-                } else {
-                    for (int c = 0; c < p.cin; ++c) {
-                        const float* ip = pl + c * PP + y * PWi + x;
+                    for (int j = 0; j < 8; ++j) a[u][j] = br[j];
+                    if (kRegW) {
+                        const float* ip = pl + y * PWi + x;
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const float iv = ip[(tap / 3) * PWi + (tap % 3)];
-                            const float4 wa = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8);
-                            const float4 wb = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8 + 4);
-                            a[0] = fmaf(iv, wa.x, a[0]); a[1] = fmaf(iv, wa.y, a[1]); a[2] = fmaf(iv, wa.z, a[2]); a[3] = fmaf(iv, wa.w, a[3]);
-                            a[4] = fmaf(iv, wb.x, a[4]); a[5] = fmaf(iv, wb.y, a[5]); a[6] = fmaf(iv, wb.z, a[6]); a[7] = fmaf(iv, wb.w, a[7]);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a[u][j] = fmaf(iv, wr[tap][j], a[u][j]);
+                        }
+                    } else {
+                        for (int c = 0; c < p.cin; ++c) {
+                            const float* ip = pl + c * PP + y * PWi + x;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const float iv = ip[(tap / 3) * PWi + (tap % 3)];
+                                const float4 wa = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8);
+                                const float4 wb = *reinterpret_cast<const float4*>(w0s + (c * 9 + tap) * kC1 + o * 8 + 4);
+                                a[u][0] = fmaf(iv, wa.x, a[u][0]); a[u][1] = fmaf(iv, wa.y, a[u][1]); a[u][2] = fmaf(iv, wa.z, a[u][2]); a[u][3] = fmaf(iv, wa.w, a[u][3]);
+                                a[u][4] = fmaf(iv, wb.x, a[u][4]); a[u][5] = fmaf(iv, wb.y, a[u][5]); a[u][6] = fmaf(iv, wb.z, a[u][6]); a[u][7] = fmaf(iv, wb.w, a[u][7]);
+                            }
                         }
                     }
                 }
-                uint4 pk;
-                pk.x = pack2(silu_t(a[0]), silu_t(a[1]));
-                pk.y = pack2(silu_t(a[2]), silu_t(a[3]));
-                pk.z = pack2(silu_t(a[4]), silu_t(a[5]));
-                pk.w = pack2(silu_t(a[6]), silu_t(a[7]));
-                const int q = (y + 1) * p.PW + (x + 1);                 // padded linear position of this pixel
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) *reinterpret_cast<uint4*>(act + kx * act_bytes + sw64_offset(q - kx, o)) = pk;
+                for (int u = 0; u < kIPT; ++u) {
+                    uint4 pk;
+                    pk.x = pack2(silu_t(a[u][0]), silu_t(a[u][1]));
+                    pk.y = pack2(silu_t(a[u][2]), silu_t(a[u][3]));
+                    pk.z = pack2(silu_t(a[u][4]), silu_t(a[u][5]));
+                    pk.w = pack2(silu_t(a[u][6]), silu_t(a[u][7]));
+                    if (valid[u]) {
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) *reinterpret_cast<uint4*>(act + kx * act_bytes + sw64_offset(q[u] - kx, o)) = pk;
+                    }
                 }
-                signal_tiles(iter, prev);
+                const uint32_t sig = (sig_bits >> (4 * iter)) & 15u;     // (warp-uniform)
+                if (sig) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int t = 0; t < kTiles; ++t) {
+                            if ((sig >> t) & 1u) {
+                                mbar_wait(&tile_done[t], prev, 74);      // the MMA warp has consumed this barrier's previous phase
+                                mbar_arrive(&act_full[t]);
+                            }
+                        }
+                    }
+                }
             }
         }
     } else if (warp == 4) {

@@ -31,6 +31,7 @@
 // GEMM_{g+1} overlaps ATT_g, FF1_{c+2} overlaps EPI1_c; the shared-memory scratch (q|k|v staging + O, or H) and the
 // TMEM scratch columns [256,512) are time-shared by the two phases (ordered by the x_full / h_ready barriers).
 #include <cstdlib>
+#include <type_traits>
 
 #include "fused_common.cuh"
 
@@ -59,6 +60,10 @@ constexpr int kOffRing = kOffO + kTile;
 constexpr int kOffBar = kOffRing + kSlots * kSlotBytes;
 constexpr int kOffStat = kOffO + 12288;             // float2 [4][128] LayerNorm partial statistics: the tail of the O tile, idle
                                                     // while a LayerNorm runs (every MMA reading O / H has completed: h_ready)
+constexpr int kOffERb = kOffS + 32768;              // staged prologue operands (p.e_stage; H[1], dead between the last FF2 and EPI1_1):
+constexpr int kOffEWf = kOffERb + 16384;            //   row_b rows of the tile's trajectories (<= 16 KB) | Wf (<= 8 KB) | row_a (1 KB)
+constexpr int kOffERa = kOffEWf + 8192;
+static_assert(kOffERa + 1024 <= kOffO + 8192, "staged prologue operands stay clear of the head's partial sums and the LayerNorm statistics");
 constexpr int kOffPA = kOffBar + 256;             // ln1_w 256 | ln1_b 256 | cb1 256 | bqkv 768
 constexpr int kPAFloats = 1536;
 constexpr int kOffPM = kOffPA + kPAFloats * 4;      // ln2_w 256 | ln2_b 256 | cb2 256 | b1 ff
@@ -230,7 +235,7 @@ __device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, cons
 }
 
 // kProf (dev, IDB200_PROF=1): compute warp 0 lane 0 accumulates clock64() spans per phase into p.prof[0..15]
-enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_LNLD, P_LNENTRY, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
+enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_LNLD, P_LNENTRY, P_LDWAIT, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
 
 // kPair: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  Each CTA still owns one 128-token tile (its
 // rows of h in its own TMEM, its own X / scratch / parameters), but the even CTA issues ONE M=256 MMA for both tiles
@@ -639,16 +644,27 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         // tile; it is re-staged per tile because X is the LayerNorm output in between.
         // tab_full completes TWO phases per tile (the copy, then a plain arrive just before the next copy is issued), so the prologue
         // always waits for parity 0 and no per-tile counter stays live across the layers.
-        auto stage_tab = [&](bool first) {
+        // Next to it, in the part of the scratch region that is dead at that time (H[1]): the tile's row_b rows (contiguous: one row
+        // per trajectory), the feature weights Wf and (when batch-constant) row_a -- every operand of the prologue is then read
+        // with shared-memory latency, and its loops have no global-memory round trips.
+        auto stage_tab = [&](int tile_, bool first) {
             if (p.e_stage && ew == 1 && lane == 0) {
+                const long long t0 = static_cast<long long>(tile_) * 128 / L;
+                const long long left = p.M / L - t0;
+                const uint32_t nt = left <= 0 ? 0u : static_cast<uint32_t>(left < 128 / L ? left : 128 / L);   // 0: the pair's dead tile
+                const uint32_t wf_bytes = static_cast<uint32_t>(p.e_n0 + p.e_n1 + p.e_n2) * 1024u;
+                const uint32_t ra_bytes = p.e_row_a_stride == 0 ? 1024u : 0u;
                 if (!first) mbar_arrive(tab_full);
                 fence_proxy_async_smem();
-                mbar_arrive_expect_tx(tab_full, 65536u);
+                mbar_arrive_expect_tx(tab_full, 65536u + nt * 1024u + wf_bytes + ra_bytes);
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) tma_load_2d(smem + kOffX + c * 8192, &tm_tab, tab_full, c * 32, 0);
+                if (nt) bulk_load_1d(smem + kOffERb, p.e_row_b + t0 * kD, nt * 1024u, tab_full);
+                bulk_load_1d(smem + kOffEWf, p.e_wf, wf_bytes, tab_full);
+                if (ra_bytes) bulk_load_1d(smem + kOffERa, p.e_row_a, 1024u, tab_full);
             }
         };
-        if (trip0 < trips) stage_tab(true);
+        if (trip0 < trips) stage_tab(tile_of(trip0), true);
         // attention work unit of this warp: 16-row block rb, head hh of the group
         const int rb = ew & 7, hh = ew >> 3;
         uint32_t okbits = 0;                             // L < 16: block-diagonal mask of the 16 x 16 score block (per thread, fixed)
@@ -685,59 +701,62 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 }
                 tmem_st_wait();
             } else if (p.e_stage) {
-                // fused token assembly + in_proj with the table staged in shared memory (idb200_embed_tokens; same fp32 operation
-                // order: fma chain over the features, + tab + row_a + row_b)
+                // fused token assembly + in_proj with every operand staged in shared memory (idb200_embed_tokens; same fp32 operation
+                // order: fma chain over the features, + tab + row_a + row_b).  Dead rows compute on slot 0 and are zeroed at the end.
                 const int F = p.e_n0 + p.e_n1 + p.e_n2;
                 float f[8];
-                long long bb = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.0f;
                 int trow = 0;
                 if (live) {
-                    bb = m / L;
-                    trow = p.e_tab_idx ? static_cast<int>(p.e_tab_idx[m]) : static_cast<int>(m - bb * L);
+                    trow = p.e_tab_idx ? static_cast<int>(p.e_tab_idx[m]) : (row % L);
                     trow = min(max(trow, 0), 63);                        // (an out-of-range index must not leave the staged boxes)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float v = 0.0f;
-                        if (j < p.e_n0) v = p.e_src0[m * p.e_n0 + j];
-                        else if (j < p.e_n0 + p.e_n1) v = p.e_src1[m * p.e_n1 + (j - p.e_n0)];
-                        else if (j < F) v = p.e_src2[m * p.e_n2 + (j - p.e_n0 - p.e_n1)] ? 1.0f : 0.0f;
-                        f[j] = v;
+                        if (j < p.e_n0) f[j] = p.e_src0[m * p.e_n0 + j];
+                        else if (j < p.e_n0 + p.e_n1) f[j] = p.e_src1[m * p.e_n1 + (j - p.e_n0)];
+                        else if (j < F) f[j] = p.e_src2[m * p.e_n2 + (j - p.e_n0 - p.e_n1)] ? 1.0f : 0.0f;
                     }
                 }
-                const float4* ra4 = reinterpret_cast<const float4*>(p.e_row_a + bb * p.e_row_a_stride) + part * 16;
-                const float4* rb4 = reinterpret_cast<const float4*>(p.e_row_b + bb * kD) + part * 16;
-                const float4* wf4 = reinterpret_cast<const float4*>(p.e_wf) + part * 16;
+                const bool ra_s = p.e_row_a_stride == 0;
+                const float4* ra4 = reinterpret_cast<const float4*>(p.e_row_a + (live ? m / L : 0) * p.e_row_a_stride) + part * 16;
+                const uint32_t col_s = static_cast<uint32_t>(part) * 256u;                                  // this thread's 64 columns, bytes
                 const uint32_t tab_s = smem_u32(smem + kOffX) + static_cast<uint32_t>(part * 2) * 8192u + static_cast<uint32_t>(trow) * 128u;
                 const uint32_t tsw = static_cast<uint32_t>(trow & 7);
+                const uint32_t rb_s = smem_u32(smem + kOffERb) + static_cast<uint32_t>(live ? row / L : 0) * 1024u + col_s;
+                const uint32_t wf_s = smem_u32(smem + kOffEWf) + col_s, ras = smem_u32(smem + kOffERa) + col_s;
                 mbar_wait(tab_full, 0u, 62);
+                stamp(P_LDWAIT);                                         // (dev: tile turnaround up to the staged operands' arrival)
+                auto body = [&](auto kFtag) {
+                    constexpr int kF = decltype(kFtag)::value;
 #pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    uint32_t r[32];
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t r[32];
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live) {
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const uint32_t co = static_cast<uint32_t>(cc * 8 + j4) * 16u;
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (j < F) {
-                                    const float4 w = __ldg(wf4 + j * (kD / 4) + cc * 8 + j4);
-                                    acc.x = fmaf(f[j], w.x, acc.x);
-                                    acc.y = fmaf(f[j], w.y, acc.y);
-                                    acc.z = fmaf(f[j], w.z, acc.z);
-                                    acc.w = fmaf(f[j], w.w, acc.w);
-                                }
+                            for (int j = 0; j < kF; ++j) {
+                                if (j >= F) break;                       // (rows >= F of the staged Wf are not written)
+                                const float4 w = lds128(wf_s + static_cast<uint32_t>(j) * 1024u + co);
+                                acc.x = fmaf(f[j], w.x, acc.x);
+                                acc.y = fmaf(f[j], w.y, acc.y);
+                                acc.z = fmaf(f[j], w.z, acc.z);
+                                acc.w = fmaf(f[j], w.w, acc.w);
                             }
                             const float4 tb = lds128(tab_s + static_cast<uint32_t>(cc) * 8192u + ((static_cast<uint32_t>(j4) ^ tsw) << 4));
-                            const float4 a = __ldg(ra4 + cc * 8 + j4), b = __ldg(rb4 + cc * 8 + j4);
-                            acc = make_float4(acc.x + tb.x + a.x + b.x, acc.y + tb.y + a.y + b.y, acc.z + tb.z + a.z + b.z, acc.w + tb.w + a.w + b.w);
+                            const float4 a = ra_s ? lds128(ras + co) : __ldg(ra4 + cc * 8 + j4);
+                            const float4 b = lds128(rb_s + co);
+                            r[4 * j4 + 0] = live ? __float_as_uint(acc.x + tb.x + a.x + b.x) : 0u;
+                            r[4 * j4 + 1] = live ? __float_as_uint(acc.y + tb.y + a.y + b.y) : 0u;
+                            r[4 * j4 + 2] = live ? __float_as_uint(acc.z + tb.z + a.z + b.z) : 0u;
+                            r[4 * j4 + 3] = live ? __float_as_uint(acc.w + tb.w + a.w + b.w) : 0u;
                         }
-                        r[4 * j4 + 0] = __float_as_uint(acc.x);
-                        r[4 * j4 + 1] = __float_as_uint(acc.y);
-                        r[4 * j4 + 2] = __float_as_uint(acc.z);
-                        r[4 * j4 + 3] = __float_as_uint(acc.w);
+                        tmem_st_32x32(tmem_row + part * 64 + cc * 32, r);
                     }
-                    tmem_st_32x32(tmem_row + part * 64 + cc * 32, r);
-                }
+                };
+                if (F <= 4) body(std::integral_constant<int, 4>{}); else body(std::integral_constant<int, 8>{});
                 tmem_st_wait();
             } else {
                 // fused token assembly + in_proj (idb200_embed_tokens; same fp32 operation order):
@@ -949,7 +968,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 mbar_wait(h_ready, 1u, 57);                              // the last FF2 has landed in h
                 tc_fence_after();
                 stamp(P_WH2);
-                if (l == NL - 1 && trip + trip_stride < trips) stage_tab(false);   // every MMA reading X has completed: the next tile's table
+                if (l == NL - 1 && trip + trip_stride < trips) stage_tab(tile_of(trip + trip_stride), false);   // every MMA reading X / H has completed
             }
             // ---- TMEM -> residual stream (+ the pending bias), or straight through the output head ----
             if (p.o_w != nullptr) {
@@ -1085,7 +1104,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     CUtensorMap ttab = tqk;                                                // (unused unless the table is staged)
     if (emb) {
         const int F = emb->n0 + emb->n1 + emb->n2;
-        if (emb->tab_rows >= 1 && emb->tab_rows <= 64 && F <= 8) {
+        if (emb->tab_rows >= 1 && emb->tab_rows <= 64 && F <= 8 && L >= 8) {
             rc = make_tmap_2d(&ttab, emb->tab, 4, static_cast<uint64_t>(emb->tab_rows), 256, 64, 32);
             if (rc) return rc;
             p.e_stage = 1;
@@ -1125,7 +1144,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         static const char* names[ef::P_N] = {"load", "ln1", "wait_acc", "epi", "att", "wait_o", "o_write", "wait_h1", "ln2", "wait_acc1", "epi1",
-                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film", "ln_tmem_ld", "ln_entry)", "[mma: wait_slot", "wait_compute", "issue]"};
+                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film", "ln_tmem_ld", "ln_entry)", "(load_until_staged)", "[mma: wait_slot", "wait_compute", "issue]"};
         const double units = static_cast<double>(tiles) * n_layers;
         fprintf(stderr, "encoder_fused prof (cycles per tile-layer, L=%d, pair=%d):", L, pair ? 1 : 0);
         double tot = 0;
