@@ -126,7 +126,7 @@ __device__ __forceinline__ float silu_half(float acc, float hb) {
 //   kFilmFolded  [scale | shift] with the LayerNorm affine already folded in: y = n * scale + shift
 //   kFilmRaw     [gamma | beta]: y = (n * w + b) * (1 + gamma) + beta        kFilmNone  y = n * w + b
 // kFilmSmem: the row is in shared memory (staged by bulk copies; wait on film_full first), else in global memory.
-enum { kFilmNone = 0, kFilmRaw = 1, kFilmFolded = 2 };
+enum { kFilmNone = 0, kFilmRaw = 1, kFilmFolded = 2, kFilmFolded16 = 3 };   // Folded16: [scale | shift] as bf16 (rows of 512 bf16, staged in shared memory only)
 // explicit shared-space 16-byte load (pointer selects hide the address space from the compiler: generic LD is ~3x slower here)
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
@@ -187,17 +187,32 @@ __device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, cons
     uint8_t* xt = X + part * kTile;
     // scale / shift: the folded FiLM row (staged in shared memory, or in global memory when L < 8) or the LayerNorm affine
     const bool folded = (mode == kFilmFolded) && film != nullptr;
+    const bool folded16 = kFilmSmem && (mode == kFilmFolded16) && film != nullptr;
     const bool raw = (mode == kFilmRaw) && film != nullptr;
     const bool gfold = !kFilmSmem && folded;
     const uint32_t scs = smem_u32((kFilmSmem && folded) ? film : sw) + c0 * 4;
     const uint32_t shs = smem_u32((kFilmSmem && folded) ? film + 256 : sb) + c0 * 4;
     const uint32_t fls = (kFilmSmem && raw) ? smem_u32(film) + c0 * 4 : 0u;
+    const uint32_t f16s = smem_u32(film) + c0 * 2;                       // bf16 table: scale at [0, 256), shift at [256, 512) bf16
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
         const int col = c0 + cc * 32;
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {                                 // 8 columns -> one 16-byte swizzle chunk
             float y[8];
+            if (folded16) {
+                // half the shared-memory bytes per column: the LayerNorm is bound by the LSU return path (a warp-wide LDS.128
+                // delivers 512 B in 4 cycles whether or not it is a broadcast), not by issue slots
+                const float4 s16 = lds128(f16s + (cc * 4 + j2) * 16), h16 = lds128(f16s + 512 + (cc * 4 + j2) * 16);
+                const uint32_t sv[4] = {__float_as_uint(s16.x), __float_as_uint(s16.y), __float_as_uint(s16.z), __float_as_uint(s16.w)};
+                const uint32_t hv[4] = {__float_as_uint(h16.x), __float_as_uint(h16.y), __float_as_uint(h16.z), __float_as_uint(h16.w)};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j2 * 8 + 2 * u;                        // column offset inside the 32-column half
+                    y[2 * u + 0] = fmaf(fmaf(__uint_as_float(r[cc][j + 0]), rstd, shift), __uint_as_float(sv[u] << 16), __uint_as_float(hv[u] << 16));
+                    y[2 * u + 1] = fmaf(fmaf(__uint_as_float(r[cc][j + 1]), rstd, shift), __uint_as_float(sv[u] & 0xffff0000u), __uint_as_float(hv[u] & 0xffff0000u));
+                }
+            } else {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int j = j2 * 2 + u;
@@ -222,6 +237,7 @@ __device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, cons
                     y[4 * u + 2] = fmaf(y[4 * u + 2], 1.0f + g.z, t.z);
                     y[4 * u + 3] = fmaf(y[4 * u + 3], 1.0f + g.w, t.w);
                 }
+            }
             }
             uint4 pk;
             pk.x = pack2_bf16(y[0], y[1]);
@@ -619,18 +635,20 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
         // between the last attention read and EPI1_0 / between FF2 of the last even chunk and EPI_0.
         const bool skip = kProf && p.dbg_skip;
         const bool film_smem = (p.gb != nullptr) && L >= 8;
+        const int film_elem = p.film_mode == kFilmFolded16 ? 2 : 4;      // bytes per table element; a trajectory's row is 512 elements
+        const uint32_t film_row_bytes = 512u * static_cast<uint32_t>(film_elem);
         auto stage_film = [&](int tile_, int l_, int which) {
             if (film_smem && ew == 0 && lane == 0) {
                 const long long t0 = static_cast<long long>(tile_) * 128 / L;
                 const long long left = p.M / L - t0;
                 const int nt = left <= 0 ? 0 : static_cast<int>(left < 128 / L ? left : 128 / L);   // 0: the pair's dead tile
                 fence_proxy_async_smem();
-                mbar_arrive_expect_tx(film_full, static_cast<uint32_t>(nt) * 2048u);
-                const float* src = p.gb + t0 * p.gb_stride + (2 * l_ + which) * p.gb_ln_stride;
+                mbar_arrive_expect_tx(film_full, static_cast<uint32_t>(nt) * film_row_bytes);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.gb) + (t0 * p.gb_stride + (2 * l_ + which) * p.gb_ln_stride) * film_elem;
                 if (p.gb_stride == 512) {                                // LayerNorm-major table: the tile's rows are contiguous
-                    if (nt > 0) bulk_load_1d(smem + kOffS, src, static_cast<uint32_t>(nt) * 2048u, film_full);
+                    if (nt > 0) bulk_load_1d(smem + kOffS, src, static_cast<uint32_t>(nt) * film_row_bytes, film_full);
                 } else {
-                    for (int t = 0; t < nt; ++t) bulk_load_1d(smem + kOffS + t * 2048, src + t * p.gb_stride, 2048, film_full);
+                    for (int t = 0; t < nt; ++t) bulk_load_1d(smem + kOffS + t * film_row_bytes, src + t * p.gb_stride * film_elem, film_row_bytes, film_full);
                 }
             }
         };
@@ -812,7 +830,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
             stamp(P_LOAD);
             // FiLM row of this thread's trajectory: global (L < 8) or staged in the scratch region (L >= 8, slot = row / L)
             const float* gbtraj = (p.gb != nullptr && live) ? p.gb + (m / L) * p.gb_stride : nullptr;
-            const float* sfilm = (p.gb != nullptr && live) ? reinterpret_cast<const float*>(smem + kOffS) + (row / L) * 512 : nullptr;
+            const float* sfilm = (p.gb != nullptr && live) ? reinterpret_cast<const float*>(smem + kOffS + (row / L) * film_row_bytes) : nullptr;
             for (int l = 0; l < NL; ++l, ++n_p) {
                 // ================= attention half =================
                 mbar_wait(pa_full, n_p & 1, 50);
@@ -1062,6 +1080,8 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         IDB_REQUIRE(head->W && head->bias && head->y && head->D >= 1 && head->D <= 4, IDB200_EUNSUPPORTED, "output head needs 1 <= D <= 4");
         IDB_REQUIRE(aligned(head->W, 16), IDB200_EALIGN, "head weights must be 16-byte aligned");
     }
+    IDB_REQUIRE(film_folded != 2 || !gb || L >= 8, IDB200_EUNSUPPORTED, "the bf16 [scale | shift] table is staged in shared memory: needs L >= 8");
+    IDB_REQUIRE(film_folded != 2 || !gb || (gb_stride % 8 == 0 && gb_ln_stride % 8 == 0), IDB200_EALIGN, "bf16 FiLM rows must be 16-byte aligned");
     IDB_REQUIRE((!h || aligned(h, 16)) && aligned(params, 16) && aligned(cb_total, 16) && (!gb || (aligned(gb, 16) && gb_stride % 4 == 0 && gb_ln_stride % 4 == 0)),
                 IDB200_EALIGN, "h / params / gamma_beta must be 16-byte aligned");
     static const bool pair_env = !(getenv("IDB200_ENCODER_PAIR") && atoi(getenv("IDB200_ENCODER_PAIR")) == 0);
@@ -1099,7 +1119,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
     }
     ef::Params p{};
     p.h = h; p.params = params; p.cb_total = cb_total; p.gb = gb; p.gb_stride = gb_stride; p.gb_ln_stride = gb_ln_stride; p.M = M; p.L = L; p.causal = causal;
-    p.ff = ff; p.n_layers = n_layers; p.film_mode = gb ? (film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone; p.prof = nullptr;
+    p.ff = ff; p.n_layers = n_layers; p.film_mode = gb ? (film_folded == 2 ? ef::kFilmFolded16 : film_folded ? ef::kFilmFolded : ef::kFilmRaw) : ef::kFilmNone; p.prof = nullptr;
     p.dbg_skip = getenv("IDB200_DBG_SKIP") ? atoi(getenv("IDB200_DBG_SKIP")) : 0;
     CUtensorMap ttab = tqk;                                                // (unused unless the table is staged)
     if (emb) {

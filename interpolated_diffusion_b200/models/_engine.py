@@ -4,6 +4,7 @@ SIMT attention, fused LN+FiLM, fp32 SIMT linears for the per-trajectory terms); 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -11,6 +12,7 @@ import torch
 from .. import _lib as L
 
 EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2, 3
+FILM_BF16 = os.environ.get("IDB200_FILM_BF16", "1") != "0"      # dev: A/B of the bf16 [scale | shift] table
 
 
 def _sig(params) -> Tuple:
@@ -69,6 +71,10 @@ class Film:
     def __init__(self, t: torch.Tensor, folded: bool, ln_major: bool = False):
         self.t, self.folded, self.ln_major = t, folded, ln_major        # ln_major: t is [2 * n_layers, B, 2d]
 
+    def code(self) -> int:
+        """film_folded argument of idb200_encoder_fused: 0 raw, 1 folded fp32, 2 folded bf16."""
+        return 0 if not self.folded else (2 if self.t.dtype == torch.bfloat16 else 1)
+
     def strides(self):
         """(table, floats between trajectories, floats between LayerNorm slots) as idb200_encoder_fused takes them."""
         t = self.t
@@ -83,7 +89,7 @@ def encoder_fused(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Film"], 
     f = pk.fused
     ft, fts, ftl = (None, 0, 0) if film is None else film.strides()
     L.call("idb200_encoder_fused", h.data_ptr(), f["params"].data_ptr(), f["bias_last"].data_ptr(), L.ptr(ft),
-           fts, ftl, int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           fts, ftl, 0 if film is None else film.code(), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
            f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(h.device))
     return h
 
@@ -96,7 +102,7 @@ def encoder_fused_head(h: torch.Tensor, pk: "PackedEncoder", film: Optional["Fil
     ft, fts, ftl = (None, 0, 0) if film is None else film.strides()
     head = L.HeadDesc(W_out.data_ptr(), b_out.data_ptr(), y.data_ptr(), W_out.shape[0])
     L.call("idb200_denoiser_fused", None, ctypes.byref(head), h.data_ptr(), f["params"].data_ptr(), f["bias_last"].data_ptr(),
-           L.ptr(ft), fts, ftl, int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           L.ptr(ft), fts, ftl, 0 if film is None else film.code(), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
            f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(y.device))
     return y
 
@@ -113,7 +119,7 @@ def denoiser_fused(pk: "PackedEncoder", film: Optional["Film"], Lseq: int, causa
                       0 if row_a.shape[0] == 1 else row_a.stride(0), row_b.data_ptr(), int(tab.shape[0]))
     head = L.HeadDesc(W_out.data_ptr(), b_out.data_ptr(), y.data_ptr(), W_out.shape[0])
     L.call("idb200_denoiser_fused", ctypes.byref(emb), ctypes.byref(head), None, f["params"].data_ptr(), f["bias_last"].data_ptr(),
-           L.ptr(ft), fts, ftl, int(film is not None and film.folded), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
+           L.ptr(ft), fts, ftl, 0 if film is None else film.code(), f["wqkv"].data_ptr(), f["wo"].data_ptr(),
            f["w1"].data_ptr(), f["w2"].data_ptr(), M, Lseq, d, pk.n_heads, pk.ff, len(pk.layers), int(causal), L.stream(y.device))
     return y
 
@@ -332,11 +338,15 @@ class PackedEncoder:
         tc = precision == "bf16" and cond_vec.shape[1] % 64 == 0
         if folded:
             # LayerNorm-major table [2 * n_layers, B, 2d]: the rows of a 128-token tile are contiguous for every LayerNorm
-            out = torch.empty((nln, B, d2), device=cond_vec.device, dtype=torch.float32)
+            # bf16 table (tensor-core mode, trajectories of >= 8 tokens: the kernel stages the rows in shared memory): the LayerNorm
+            # of the whole-encoder kernel is bound by shared-memory return bandwidth, and half the bytes per column is ~1 k cycles
+            # per LayerNorm; the table's values already carry the bf16 rounding of the GEMM's operands
+            t16 = tc and Lseq >= 8 and FILM_BF16
+            out = torch.empty((nln, B, d2), device=cond_vec.device, dtype=torch.bfloat16 if t16 else torch.float32)
             a16 = cond_vec.to(torch.bfloat16).contiguous() if tc else None
             for j in range(nln):
                 if tc:
-                    gemm_bf16(a16, self.film_w_folded16[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j], EPI_F32)
+                    gemm_bf16(a16, self.film_w_folded16[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j], EPI_BF16 if t16 else EPI_F32)
                 else:
                     sgemm(cond_vec, self.film_w_folded[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j])
             return Film(out, True, ln_major=True)
