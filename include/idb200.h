@@ -330,6 +330,9 @@ int idb200_ln_mlp_pair(float* h, const float* ln_w, const float* ln_b, const flo
  *     0.5 * b1 (ff)].  pend1 / pend2 = the bias of the GEMM that accumulated into h just before that LayerNorm (ff.2 bias of
  *     the previous layer, zero for layer 0 / out_proj bias of this layer): the accumulating GEMMs never add their own bias,
  *     the LayerNorm that follows does.  bias_last [256] = ff.2 bias of the last layer (added when h is written back).
+ *     Of bqkv_packed (per head group [bq 64 | bk 64 | bv 64]) the kernel adds ONLY the q part: a k bias shifts every score of a
+ *     query equally (softmax-invariant: dropped) and a v bias passes through the attention unchanged (rows of softmax sum to 1),
+ *     so the caller folds it into pend2 = out_proj.bias + out_proj.weight . bv (transformer.py:39 semantics are unchanged).
  *   film: FiLM table or NULL: the row (512 floats) of trajectory b = m / L for LayerNorm slot j (2l = film1 of layer l,
  *     2l+1 = film2) is at film + b * film_stride + j * film_ln_stride.  [B][2 * n_layers][512] is (8192-ish, 512);
  *     the LayerNorm-major form [2 * n_layers][B][512] (film_stride = 512, film_ln_stride = B * 512) makes the rows of a

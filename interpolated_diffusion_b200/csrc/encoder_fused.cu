@@ -860,11 +860,18 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                         tmem_ld_wait();
                         const float* bb = sbqkv + g * 192 + part * 48;
                         uint8_t* dst = sqb + row * (kPitch * 2) + part * 96;
+                        // Only the q columns (the first 64 of the group's 192) get their in_proj bias here: a k bias shifts every score
+                        // of a query by the same amount (softmax-invariant) and a v bias passes through the attention unchanged
+                        // (rows of P sum to 1), so the host drops the former and folds the latter into the pending out_proj bias.
+                        // This epilogue is bound by shared-memory return bandwidth (12 of its 18 128-bit accesses were bias loads).
 #pragma unroll
                         for (int j = 0; j < 6; ++j) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
                             const uint32_t* v = (j < 4) ? &ra[8 * j] : &rc[8 * (j - 4)];
+                            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                            if (part * 48 + 8 * j < 64) {                    // (warp-uniform)
+                                b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
+                                b1 = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
+                            }
                             uint4 pk;
                             pk.x = pack2_bf16(__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y);
                             pk.y = pack2_bf16(__uint_as_float(v[2]) + b0.z, __uint_as_float(v[3]) + b0.w);

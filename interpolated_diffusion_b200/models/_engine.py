@@ -307,8 +307,12 @@ class PackedEncoder:
             # stacked weights + per-layer parameter blobs of idb200_encoder_fused (layout: include/idb200.h)
             pend = torch.zeros(self.d, device=self.layers[0]["bo"].device, dtype=torch.float32)
             blobs = []
+            d_ = self.d
             for e in self.layers:
-                blobs += [e["n1w"], e["n1b"], pend, e["bqkv_g"], e["n2w"], e["n2b"], e["bo"], 0.5 * e["b1"]]
+                # the kernel adds the in_proj bias to q only (include/idb200.h): the k bias is softmax-invariant, the v bias passes
+                # through the attention (rows of P sum to 1) and is folded, through out_proj, into the pending bias LayerNorm 2 adds
+                bo_eff = e["bo"] + e["wo32"] @ e["bqkv"][2 * d_:]
+                blobs += [e["n1w"], e["n1b"], pend, e["bqkv_g"], e["n2w"], e["n2b"], bo_eff, 0.5 * e["b1"]]
                 pend = e["b2"]
             self.fused = {
                 "params": torch.cat(blobs).contiguous(), "bias_last": pend.contiguous(),
