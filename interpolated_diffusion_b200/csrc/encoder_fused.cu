@@ -897,6 +897,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                         } else {
                             const int kbeg = (rb * 16 / L) * L, kend = kbeg + L;
                             if (L == 16) attn_unit_fast<2, 0>(qh, qh + 64, qh + 128, rb, kbeg, kend, 0u, lane, o);
+                            else if (L == 64) attn_unit_fast<8, 0>(qh, qh + 64, qh + 128, rb, kbeg, kend, 0u, lane, o);   // all 64 keys in one pass: no online rescale
                             else attn_unit_fast<4, 0>(qh, qh + 64, qh + 128, rb, kbeg, kend, 0u, lane, o);
                         }
                     }
