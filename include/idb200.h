@@ -339,8 +339,9 @@ int idb200_ln_mlp_pair(float* h, const float* ln_w, const float* ln_b, const flo
  *     tile contiguous, which the kernel stages with ONE bulk copy per LayerNorm (16 separate copies cost 3 k cycles).  film_folded == 0: rows are [gamma | beta] (a = LN(h) * (1 + gamma) + beta); != 0: rows are
  *     [scale | shift] with the LayerNorm affine folded in, scale = ln_w * (1 + gamma), shift = ln_b * (1 + gamma) + beta
  *     (a = n * scale + shift, n = the normalised row) -- both are linear in cond_vec, so the host folds them into the FiLM GEMM.
- *     film_folded == 2: the same [scale | shift] rows stored as bf16 (`film` points at bf16 data, both strides count bf16
- *     elements and must be multiples of 8; needs L >= 8): halves the shared-memory bytes the LayerNorm reads per column.
+ *     film_folded == 2: rows [scale - 1 | shift] stored as bf16 (`film` points at bf16 data, both strides count bf16
+ *     elements and must be multiples of 8; needs L >= 8): halves the shared-memory bytes the LayerNorm reads per column;
+ *     a = n + n * (scale - 1) + shift (the offset keeps the bf16 rounding error of the scale a fraction of 2^-9).
  *   wqkv_packed bf16 [n_layers*768, 256] (per layer head-group-major, see idb200_attn_block), wo bf16 [n_layers*256, 256],
  *   w1 bf16 [n_layers*ff, 256], w2 bf16 [n_layers*256, ff]. */
 int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_last, const float* film, int64_t film_stride,

@@ -126,7 +126,7 @@ __device__ __forceinline__ float silu_half(float acc, float hb) {
 //   kFilmFolded  [scale | shift] with the LayerNorm affine already folded in: y = n * scale + shift
 //   kFilmRaw     [gamma | beta]: y = (n * w + b) * (1 + gamma) + beta        kFilmNone  y = n * w + b
 // kFilmSmem: the row is in shared memory (staged by bulk copies; wait on film_full first), else in global memory.
-enum { kFilmNone = 0, kFilmRaw = 1, kFilmFolded = 2, kFilmFolded16 = 3 };   // Folded16: [scale | shift] as bf16 (rows of 512 bf16, staged in shared memory only)
+enum { kFilmNone = 0, kFilmRaw = 1, kFilmFolded = 2, kFilmFolded16 = 3 };   // Folded16: [scale - 1 | shift] as bf16 (rows of 512 bf16, staged in shared memory only)
 // explicit shared-space 16-byte load (pointer selects hide the address space from the compiler: generic LD is ~3x slower here)
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
@@ -209,8 +209,11 @@ __device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, cons
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j2 * 8 + 2 * u;                        // column offset inside the 32-column half
-                    y[2 * u + 0] = fmaf(fmaf(__uint_as_float(r[cc][j + 0]), rstd, shift), __uint_as_float(sv[u] << 16), __uint_as_float(hv[u] << 16));
-                    y[2 * u + 1] = fmaf(fmaf(__uint_as_float(r[cc][j + 1]), rstd, shift), __uint_as_float(sv[u] & 0xffff0000u), __uint_as_float(hv[u] & 0xffff0000u));
+                    // the table holds scale - 1 (|scale - 1| is a fraction of |scale| for LayerNorm weights near 1 and moderate FiLM
+                    // gains, so its bf16 rounding error is too): y = n + n (scale - 1) + shift
+                    const float n0 = fmaf(__uint_as_float(r[cc][j + 0]), rstd, shift), n1 = fmaf(__uint_as_float(r[cc][j + 1]), rstd, shift);
+                    y[2 * u + 0] = fmaf(n0, __uint_as_float(sv[u] << 16), n0 + __uint_as_float(hv[u] << 16));
+                    y[2 * u + 1] = fmaf(n1, __uint_as_float(sv[u] & 0xffff0000u), n1 + __uint_as_float(hv[u] & 0xffff0000u));
                 }
             } else {
 #pragma unroll

@@ -297,6 +297,9 @@ class PackedEncoder:
                     fb += [nw * (1.0 + bg), nb * (1.0 + bg) + bb]
             self.film_w_folded = torch.cat(fw, dim=0).contiguous()
             self.film_b_folded = torch.cat(fb, dim=0).contiguous()
+            m1 = self.film_b_folded.view(-1, 2, d_).clone()
+            m1[:, 0] -= 1.0                                             # bias of the [scale - 1 | shift] form (bf16 table)
+            self.film_b_folded_m1 = m1.view(-1).contiguous()
             self.film_w16 = self.film_w.to(torch.bfloat16).contiguous()
             self.film_w_folded16 = self.film_w_folded.to(torch.bfloat16).contiguous()
         self.d = layers[0].norm1.weight.shape[0]
@@ -350,7 +353,9 @@ class PackedEncoder:
             a16 = cond_vec.to(torch.bfloat16).contiguous() if tc else None
             for j in range(nln):
                 if tc:
-                    gemm_bf16(a16, self.film_w_folded16[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j], EPI_BF16 if t16 else EPI_F32)
+                    # (bf16 table: rows are [scale - 1 | shift] -- the offset rides on the GEMM's bias)
+                    gemm_bf16(a16, self.film_w_folded16[j * d2:(j + 1) * d2], (self.film_b_folded_m1 if t16 else self.film_b_folded)[j * d2:(j + 1) * d2],
+                              out[j], EPI_BF16 if t16 else EPI_F32)
                 else:
                     sgemm(cond_vec, self.film_w_folded[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j])
             return Film(out, True, ln_major=True)

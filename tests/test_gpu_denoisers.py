@@ -97,7 +97,9 @@ def test_small_kernels_vs_torch():
             got_tc = E.conv_encoder_tc(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if chans[0] == 2 else None, ws[0], bs[0], w1p, bs[1])
             assert _maxabs(got_tc, ref) < 3e-3, (chans, _maxabs(got_tc, ref))
     # tcgen05 conv encoder (maze_channels (32, 64)): several mazes per CTA (persistent loop, both accumulator buffers), sdf channel
-    for cin, B, H, W in [(1, 5, 21, 21), (1, 148 * 3 + 7, 21, 21), (2, 301, 21, 21), (1, 9, 12, 9)]:
+    # (the activation buffer is handed over per MMA tile: shapes with one pass / junk tiles / the widest padded row / two channels)
+    for cin, B, H, W in [(1, 5, 21, 21), (1, 148 * 3 + 7, 21, 21), (2, 301, 21, 21), (1, 9, 12, 9), (1, 300, 21, 22), (1, 311, 5, 7),
+                         (2, 200, 16, 14), (1, 151, 3, 30), (1, 1, 21, 21)]:
         x = torch.rand((B, cin, H, W), generator=g, device="cuda")
         x[:, 0] = (x[:, 0] < 0.3).float()
         ws = [torch.randn((32, cin, 3, 3), generator=g, device="cuda") * (cin * 9) ** -0.5, torch.randn((64, 32, 3, 3), generator=g, device="cuda") * (32 * 9) ** -0.5]
@@ -328,6 +330,61 @@ def test_denoiser_fused_io_matches_separate_kernels(which):
     assert _maxabs(fused, separate) < tol, _maxabs(fused, separate)
     assert _maxabs(head_only, separate) < tol, _maxabs(head_only, separate)
     assert torch.equal(head_only, fused)     # same kernel, bit-identical residual stream
+
+
+@pytest.mark.parametrize("B,T,K,kp_feat_dim,per_sample_t", [(37, 64, 8, 0, True), (300, 32, 16, 3, False), (5, 64, 32, 0, False), (129, 48, 8, 4, True)])
+def test_staged_prologue_shapes(B, T, K, kp_feat_dim, per_sample_t):
+    """Token assembly as the whole-encoder kernel's tile prologue with TMA-staged operands (table <= 64 rows, <= 8 features, K >= 8)
+    against the separate idb200_embed_tokens kernel on the same weights: bit-identical residual stream, so identical eps.  Covers
+    7-8 features (the predicated feature loop), tables shorter than 64 rows (zero-filled boxes), row_a per sample (global) and
+    batch-constant (staged), dead rows / dead pair tiles, and a single tile."""
+    from interpolated_diffusion_b200.models.denoiser_keypoints import KeypointDenoiser
+    torch.manual_seed(21)
+    gen = torch.Generator().manual_seed(22)
+    D = 2
+    m = KeypointDenoiser(data_dim=D, kp_feat_dim=kp_feat_dim).cuda()
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float().cuda(), "start_goal": torch.rand((B, 4), generator=gen).cuda()}
+    if kp_feat_dim:
+        cond["kp_feat"] = torch.randn((B, K, kp_feat_dim), generator=gen).cuda()
+    idx = torch.sort(torch.stack([torch.randperm(T, generator=gen)[:K] for _ in range(B)]), dim=1).values.cuda()
+    z = torch.randn((B, K, D), generator=gen).cuda()
+    km = (torch.rand((B, K, D), generator=gen) < 0.3).cuda()
+    t = torch.randint(0, 1000, (B,), generator=gen).cuda() if per_sample_t else torch.full((B,), 123, dtype=torch.long).cuda()
+    kw = {} if per_sample_t else {"t_vec": m.timestep_vector(t[:1])}
+    m.fuse_io = True
+    fused = m(z, t, idx, km, cond, T, **kw)
+    m.fuse_io = False
+    separate = m(z, t, idx, km, cond, T, **kw)
+    assert torch.isfinite(fused).all()
+    assert torch.equal(fused, separate)
+
+
+def test_bf16_film_table_as_accurate_as_fp32_table(monkeypatch):
+    """The folded FiLM table of the whole-encoder kernel stored as bf16 [scale - 1 | shift] (default) against the fp32 [scale | shift]
+    table, both measured against the fp32 check mode: the bf16 table does not add error (the offset keeps the rounding error of the
+    scale a fraction of 2^-9; a plain bf16 scale measured 1.2e-2 between the two tables)."""
+    from interpolated_diffusion_b200.models import _engine as E
+    from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
+    torch.manual_seed(31)
+    gen = torch.Generator().manual_seed(32)
+    B, T, D = 40, 64, 2
+    m = InterpLevelDenoiser(data_dim=D, max_levels=3, mask_channels=2).cuda()
+    cond = {"occ": (torch.rand((B, 1, 21, 21), generator=gen) < 0.2).float().cuda(), "start_goal": torch.rand((B, 4), generator=gen).cuda()}
+    args = (torch.rand((B, T, D), generator=gen).cuda(), torch.full((B,), 1, dtype=torch.long).cuda(), torch.rand((B, T, 2), generator=gen).cuda(), cond)
+    m.precision = "fp32"
+    ref = m(*args).clone()
+    m.precision = "bf16"
+    assert E.FILM_BF16
+    y16 = m(*args).clone()
+    film = m.transformer.packed().film_params(m.encode_cond(cond), T, m.precision)
+    assert film.t.dtype == torch.bfloat16 and film.code() == 2
+    monkeypatch.setattr(E, "FILM_BF16", False)
+    y32 = m(*args).clone()
+    assert m.transformer.packed().film_params(m.encode_cond(cond), T, m.precision).code() == 1
+    e16, e32 = _maxabs(y16, ref), _maxabs(y32, ref)
+    scale = max(1.0, ref.abs().max().item())
+    assert e32 < 2e-2 * scale and e16 < 2e-2 * scale, (e16, e32)
+    assert e16 < e32 + 3e-3 * scale, (e16, e32)
 
 
 @pytest.mark.parametrize("chan,use_sdf,B", [((32, 64, 128, 128), False, 37), ((32, 64, 64), True, 5), ((64,), False, 4100),
