@@ -179,12 +179,14 @@ int idb200_anchor_conf(const uint8_t* mask_s, const uint8_t* student, const uint
  *      and the in/out projections of the two denoisers (nn.Linear weight layout [out, in] = [N, K]).
  *   A, W: bf16 row-major, 16-byte aligned; K % 64 == 0, N % 32 == 0; M arbitrary.
  *   epilogue: 0 bf16 store, 1 SiLU then bf16 store (ff.0), 2 fp32 residual accumulate
- *             out[M,N] += acc + bias (out_proj / ff.2 into the residual stream), 3 fp32 store.
+ *             out[M,N] += acc + bias (out_proj / ff.2 into the residual stream), 3 fp32 store;
+ *             0 | IDB200_EPI_OUT_F16: the 16-bit store is IEEE half instead of bf16 (the FiLM table of idb200_encoder_fused).
  * ---------------------------------------------------------------------------------------------- */
 #define IDB200_EPI_BF16 0
 #define IDB200_EPI_SILU_BF16 1
 #define IDB200_EPI_RESID_F32 2
 #define IDB200_EPI_F32 3
+#define IDB200_EPI_OUT_F16 0x100
 
 int idb200_gemm_bf16(const void* A, const void* W, const float* bias, void* out, int64_t M, int N, int K, int epilogue,
                      idb200_stream_t stream);
@@ -339,9 +341,8 @@ int idb200_ln_mlp_pair(float* h, const float* ln_w, const float* ln_b, const flo
  *     tile contiguous, which the kernel stages with ONE bulk copy per LayerNorm (16 separate copies cost 3 k cycles).  film_folded == 0: rows are [gamma | beta] (a = LN(h) * (1 + gamma) + beta); != 0: rows are
  *     [scale | shift] with the LayerNorm affine folded in, scale = ln_w * (1 + gamma), shift = ln_b * (1 + gamma) + beta
  *     (a = n * scale + shift, n = the normalised row) -- both are linear in cond_vec, so the host folds them into the FiLM GEMM.
- *     film_folded == 2: rows [scale - 1 | shift] stored as bf16 (`film` points at bf16 data, both strides count bf16
- *     elements and must be multiples of 8; needs L >= 8): halves the shared-memory bytes the LayerNorm reads per column;
- *     a = n + n * (scale - 1) + shift (the offset keeps the bf16 rounding error of the scale a fraction of 2^-9).
+ *     film_folded == 2: the same [scale | shift] rows stored as IEEE half (`film` points at fp16 data, both strides count
+ *     16-bit elements and must be multiples of 8; needs L >= 8): halves the shared-memory bytes the LayerNorm reads per column.
  *   wqkv_packed bf16 [n_layers*768, 256] (per layer head-group-major, see idb200_attn_block), wo bf16 [n_layers*256, 256],
  *   w1 bf16 [n_layers*ff, 256], w2 bf16 [n_layers*256, ff]. */
 int idb200_encoder_fused(float* h, const float* layer_params, const float* bias_last, const float* film, int64_t film_stride,

@@ -30,6 +30,7 @@
 //     FF2_c   h += H[c&1] . W2[:, 128c..]^T
 // GEMM_{g+1} overlaps ATT_g, FF1_{c+2} overlaps EPI1_c; the shared-memory scratch (q|k|v staging + O, or H) and the
 // TMEM scratch columns [256,512) are time-shared by the two phases (ordered by the x_full / h_ready barriers).
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <type_traits>
 
@@ -126,7 +127,7 @@ __device__ __forceinline__ float silu_half(float acc, float hb) {
 //   kFilmFolded  [scale | shift] with the LayerNorm affine already folded in: y = n * scale + shift
 //   kFilmRaw     [gamma | beta]: y = (n * w + b) * (1 + gamma) + beta        kFilmNone  y = n * w + b
 // kFilmSmem: the row is in shared memory (staged by bulk copies; wait on film_full first), else in global memory.
-enum { kFilmNone = 0, kFilmRaw = 1, kFilmFolded = 2, kFilmFolded16 = 3 };   // Folded16: [scale - 1 | shift] as bf16 (rows of 512 bf16, staged in shared memory only)
+enum { kFilmNone = 0, kFilmRaw = 1, kFilmFolded = 2, kFilmFolded16 = 3 };   // Folded16: [scale | shift] as IEEE half (rows of 512 halves, staged in shared memory only)
 // explicit shared-space 16-byte load (pointer selects hide the address space from the compiler: generic LD is ~3x slower here)
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
@@ -193,7 +194,7 @@ __device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, cons
     const uint32_t scs = smem_u32((kFilmSmem && folded) ? film : sw) + c0 * 4;
     const uint32_t shs = smem_u32((kFilmSmem && folded) ? film + 256 : sb) + c0 * 4;
     const uint32_t fls = (kFilmSmem && raw) ? smem_u32(film) + c0 * 4 : 0u;
-    const uint32_t f16s = smem_u32(film) + c0 * 2;                       // bf16 table: scale at [0, 256), shift at [256, 512) bf16
+    const uint32_t f16s = smem_u32(film) + c0 * 2;                       // half table: scale at [0, 256), shift at [256, 512)
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
         const int col = c0 + cc * 32;
@@ -209,11 +210,10 @@ __device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, cons
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j2 * 8 + 2 * u;                        // column offset inside the 32-column half
-                    // the table holds scale - 1 (|scale - 1| is a fraction of |scale| for LayerNorm weights near 1 and moderate FiLM
-                    // gains, so its bf16 rounding error is too): y = n + n (scale - 1) + shift
-                    const float n0 = fmaf(__uint_as_float(r[cc][j + 0]), rstd, shift), n1 = fmaf(__uint_as_float(r[cc][j + 1]), rstd, shift);
-                    y[2 * u + 0] = fmaf(n0, __uint_as_float(sv[u] << 16), n0 + __uint_as_float(hv[u] << 16));
-                    y[2 * u + 1] = fmaf(n1, __uint_as_float(sv[u] & 0xffff0000u), n1 + __uint_as_float(hv[u] & 0xffff0000u));
+                    const float2 sc2 = __half22float2(*reinterpret_cast<const __half2*>(&sv[u]));
+                    const float2 sh2 = __half22float2(*reinterpret_cast<const __half2*>(&hv[u]));
+                    y[2 * u + 0] = fmaf(fmaf(__uint_as_float(r[cc][j + 0]), rstd, shift), sc2.x, sh2.x);
+                    y[2 * u + 1] = fmaf(fmaf(__uint_as_float(r[cc][j + 1]), rstd, shift), sc2.y, sh2.y);
                 }
             } else {
 #pragma unroll

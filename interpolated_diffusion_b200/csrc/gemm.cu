@@ -13,6 +13,7 @@
 //   warps 4..11 epilogue: tcgen05.ld (thread <-> output row), bias / SiLU / residual, global stores;
 //               overlaps the next tile's MMAs through the second accumulator stage
 // M is arbitrary (TMA zero-fills out-of-range rows, stores are row-guarded); N % BN == 0; K % 64 == 0.
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace idb200 {
@@ -122,7 +123,24 @@ struct GemmParams {
     // column sums of the bf16-rounded output over the warp's 32 rows -- summed over its rows this is the bias gradient of ff.0
     // (column sums of dU), which otherwise costs a full extra read of dU.
     float* colpart;
+    int out_f16;            // EPI_BF16 only: the 16-bit output is IEEE half instead of bf16 (epilogue | 0x100 at the entry point)
 };
+
+
+// eight fp32 -> one 16-byte chunk of bf16 (or IEEE half) pairs
+__device__ __forceinline__ uint4 pack8_16(const float* v, bool f16) {
+    uint4 pk;
+    if (f16) {
+        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    } else {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]), h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    return pk;
+}
 
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU (tanh.approx, rel. error ~2^-11, below the bf16
 // rounding of the stored result) instead of ex2 + rcp.
@@ -486,15 +504,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                uint4 pk;
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-                                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                const uint4 pk = pack8_16(&v[8 * j], p.out_f16 != 0);
                                 const int piece = cc * 4 + j;
                                 *reinterpret_cast<uint4*>(buf + r_in * 128 + ((piece ^ (r_in & 7)) << 4)) = pk;
                             }
@@ -547,16 +557,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            dst[j] = pk;
+                            dst[j] = pack8_16(&v[8 * j], p.out_f16 != 0);
                         }
                     } else {
                         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
@@ -687,6 +688,9 @@ int gemm_bf16_nn_splitk(const void* A, const void* W, float* partial, long long 
 
 int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, long long M, int N, int K, int epilogue,
                  cudaStream_t st, int splits, void* aux = nullptr, float* colpart = nullptr) {
+    const int out_f16 = (epilogue & 0x100) ? 1 : 0;                     // epilogue 0 | 0x100: IEEE half output
+    epilogue &= 0xff;
+    IDB_REQUIRE(!out_f16 || epilogue == EPI_BF16, IDB200_EINVAL, "the half-precision output flag goes with epilogue 0");
     IDB_REQUIRE(!colpart || (epilogue == EPI_BF16_DSILU && aligned(colpart, 16)), IDB200_EINVAL, "colpart goes with epilogue 5 (16-byte aligned)");
     IDB_REQUIRE(A && W && out, IDB200_EINVAL, "NULL pointer");
     IDB_REQUIRE((epilogue >= EPI_BF16_SILU_DUAL) == (aux != nullptr), IDB200_EINVAL, "epilogues 4 / 5 need the aux tensor (and only they take one)");
@@ -727,6 +731,7 @@ int gemm_bf16_tn(const void* A, const void* W, const float* bias, void* out, lon
     }
     GemmParams p{bias, out, M, N, K, epilogue, splits, use_tma};
     p.colpart = colpart;
+    p.out_f16 = out_f16;
     const CUtensorMap* px = aux ? &tx : nullptr;
     switch (BN) {
         case 256: return launch_gemm<256>(ta, tw, tw_half, to, p, st, px);

@@ -12,7 +12,8 @@ import torch
 from .. import _lib as L
 
 EPI_BF16, EPI_SILU_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2, 3
-FILM_BF16 = os.environ.get("IDB200_FILM_BF16", "1") != "0"      # dev: A/B of the bf16 [scale | shift] table
+EPI_OUT_F16 = 0x100                                            # with EPI_BF16: the 16-bit output is IEEE half
+FILM_F16 = os.environ.get("IDB200_FILM_F16", "1") != "0"        # dev: A/B of the half-precision [scale | shift] table
 
 
 def _sig(params) -> Tuple:
@@ -72,8 +73,8 @@ class Film:
         self.t, self.folded, self.ln_major = t, folded, ln_major        # ln_major: t is [2 * n_layers, B, 2d]
 
     def code(self) -> int:
-        """film_folded argument of idb200_encoder_fused: 0 raw, 1 folded fp32, 2 folded bf16."""
-        return 0 if not self.folded else (2 if self.t.dtype == torch.bfloat16 else 1)
+        """film_folded argument of idb200_encoder_fused: 0 raw, 1 folded fp32, 2 folded IEEE half."""
+        return 0 if not self.folded else (2 if self.t.dtype == torch.float16 else 1)
 
     def strides(self):
         """(table, floats between trajectories, floats between LayerNorm slots) as idb200_encoder_fused takes them."""
@@ -297,9 +298,6 @@ class PackedEncoder:
                     fb += [nw * (1.0 + bg), nb * (1.0 + bg) + bb]
             self.film_w_folded = torch.cat(fw, dim=0).contiguous()
             self.film_b_folded = torch.cat(fb, dim=0).contiguous()
-            m1 = self.film_b_folded.view(-1, 2, d_).clone()
-            m1[:, 0] -= 1.0                                             # bias of the [scale - 1 | shift] form (bf16 table)
-            self.film_b_folded_m1 = m1.view(-1).contiguous()
             self.film_w16 = self.film_w.to(torch.bfloat16).contiguous()
             self.film_w_folded16 = self.film_w_folded.to(torch.bfloat16).contiguous()
         self.d = layers[0].norm1.weight.shape[0]
@@ -345,17 +343,17 @@ class PackedEncoder:
         tc = precision == "bf16" and cond_vec.shape[1] % 64 == 0
         if folded:
             # LayerNorm-major table [2 * n_layers, B, 2d]: the rows of a 128-token tile are contiguous for every LayerNorm
-            # bf16 table (tensor-core mode, trajectories of >= 8 tokens: the kernel stages the rows in shared memory): the LayerNorm
-            # of the whole-encoder kernel is bound by shared-memory return bandwidth, and half the bytes per column is ~1 k cycles
-            # per LayerNorm; the table's values already carry the bf16 rounding of the GEMM's operands
-            t16 = tc and Lseq >= 8 and FILM_BF16
-            out = torch.empty((nln, B, d2), device=cond_vec.device, dtype=torch.bfloat16 if t16 else torch.float32)
+            # half-precision table (tensor-core mode, trajectories of >= 8 tokens: the kernel stages the rows in shared memory): the
+            # LayerNorm of the whole-encoder kernel is bound by shared-memory return bandwidth, and half the bytes per column is ~1 k
+            # cycles per LayerNorm.  IEEE half, not bf16: its 2^-12 rounding of a scale near 1 is invisible next to the bf16 rounding
+            # of the LayerNorm output (a bf16 table moved the outputs by up to 1.2e-2)
+            t16 = tc and Lseq >= 8 and FILM_F16
+            out = torch.empty((nln, B, d2), device=cond_vec.device, dtype=torch.float16 if t16 else torch.float32)
             a16 = cond_vec.to(torch.bfloat16).contiguous() if tc else None
             for j in range(nln):
                 if tc:
-                    # (bf16 table: rows are [scale - 1 | shift] -- the offset rides on the GEMM's bias)
-                    gemm_bf16(a16, self.film_w_folded16[j * d2:(j + 1) * d2], (self.film_b_folded_m1 if t16 else self.film_b_folded)[j * d2:(j + 1) * d2],
-                              out[j], EPI_BF16 if t16 else EPI_F32)
+                    gemm_bf16(a16, self.film_w_folded16[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j],
+                              (EPI_BF16 | EPI_OUT_F16) if t16 else EPI_F32)
                 else:
                     sgemm(cond_vec, self.film_w_folded[j * d2:(j + 1) * d2], self.film_b_folded[j * d2:(j + 1) * d2], out[j])
             return Film(out, True, ln_major=True)

@@ -359,10 +359,10 @@ def test_staged_prologue_shapes(B, T, K, kp_feat_dim, per_sample_t):
     assert torch.equal(fused, separate)
 
 
-def test_bf16_film_table_as_accurate_as_fp32_table(monkeypatch):
-    """The folded FiLM table of the whole-encoder kernel stored as bf16 [scale - 1 | shift] (default) against the fp32 [scale | shift]
-    table, both measured against the fp32 check mode: the bf16 table does not add error (the offset keeps the rounding error of the
-    scale a fraction of 2^-9; a plain bf16 scale measured 1.2e-2 between the two tables)."""
+def test_half_film_table_as_accurate_as_fp32_table(monkeypatch):
+    """The folded FiLM table of the whole-encoder kernel stored as IEEE half [scale | shift] (default) against the fp32 table, both
+    measured against the fp32 check mode: the half table does not add error (2^-12 rounding of the scale; a bf16 table measured
+    1.2e-2 between the two tables)."""
     from interpolated_diffusion_b200.models import _engine as E
     from interpolated_diffusion_b200.models.denoiser_interp_levels import InterpLevelDenoiser
     torch.manual_seed(31)
@@ -374,17 +374,17 @@ def test_bf16_film_table_as_accurate_as_fp32_table(monkeypatch):
     m.precision = "fp32"
     ref = m(*args).clone()
     m.precision = "bf16"
-    assert E.FILM_BF16
+    assert E.FILM_F16
     y16 = m(*args).clone()
     film = m.transformer.packed().film_params(m.encode_cond(cond), T, m.precision)
-    assert film.t.dtype == torch.bfloat16 and film.code() == 2
-    monkeypatch.setattr(E, "FILM_BF16", False)
+    assert film.t.dtype == torch.float16 and film.code() == 2
+    monkeypatch.setattr(E, "FILM_F16", False)
     y32 = m(*args).clone()
     assert m.transformer.packed().film_params(m.encode_cond(cond), T, m.precision).code() == 1
     e16, e32 = _maxabs(y16, ref), _maxabs(y32, ref)
     scale = max(1.0, ref.abs().max().item())
     assert e32 < 2e-2 * scale and e16 < 2e-2 * scale, (e16, e32)
-    assert e16 < e32 + 3e-3 * scale, (e16, e32)
+    assert e16 < e32 + 2e-3 * scale, (e16, e32)
 
 
 @pytest.mark.parametrize("chan,use_sdf,B", [((32, 64, 128, 128), False, 37), ((32, 64, 64), True, 5), ((64,), False, 4100),

@@ -1,4 +1,4 @@
-"""Dev: error of the bf16-mode denoiser outputs against the fp32 check mode, with the folded FiLM table as bf16 [scale - 1 | shift] and as fp32."""
+"""Dev: error of the bf16-mode denoiser outputs against the fp32 check mode, with the folded FiLM table as IEEE half [scale | shift] and as fp32."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,7 +17,7 @@ for seed in (1, 2, 3):
     a_kp = (torch.randn((B, K, D), generator=gen).cuda(), torch.full((B,), 500, dtype=torch.long).cuda(), idx, (torch.rand((B, K, D), generator=gen) < 0.3).cuda(), cond, T)
     for name, m, a in (("interp", il, a_il), ("keypoints", kp, a_kp)):
         m.precision = "fp32"; ref = m(*a).clone(); m.precision = "bf16"
-        E.FILM_BF16 = True; y16 = m(*a).clone()
-        E.FILM_BF16 = False; y32 = m(*a).clone()
-        E.FILM_BF16 = True
-        print(f"seed {seed} {name}: |ref| max {ref.abs().max():.3f}  err bf16-table {(y16-ref).abs().max():.5f}  err fp32-table {(y32-ref).abs().max():.5f}  table diff {(y16-y32).abs().max():.5f}", flush=True)
+        E.FILM_F16 = True; y16 = m(*a).clone()
+        E.FILM_F16 = False; y32 = m(*a).clone()
+        E.FILM_F16 = True
+        print(f"seed {seed} {name}: |ref| max {ref.abs().max():.3f}  err half-table {(y16-ref).abs().max():.5f}  err fp32-table {(y32-ref).abs().max():.5f}  table diff {(y16-y32).abs().max():.5f}", flush=True)
