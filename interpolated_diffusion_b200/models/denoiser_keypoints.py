@@ -56,8 +56,9 @@ class KeypointDenoiser(nn.Module):
         self.out = nn.Linear(d_model, data_dim)
         self.precision = "bf16"          # "fp32" = check mode (SIMT fp32 GEMMs / attention)
         # token assembly + out head inside the fused-encoder launch (idb200_denoiser_fused): h never exists in HBM (saves the
-        # [M, 256] fp32 buffer, 4.3 GB at B = 65536, T = 64).  Off by default: the thread-per-row prologue is 2 % slower per
-        # generation than the dedicated embed / head kernels (measured, round 1).
+        # [M, 256] fp32 buffer, 4.3 GB at B = 65536, T = 64).  On by default since round 2: the prologue's operands are staged in
+        # shared memory by TMA (<= 64 table rows, <= 8 features, >= 8 tokens per trajectory; other shapes gather from global memory,
+        # which round 1 measured 2 % slower than the dedicated embed kernel).  IDB200_FUSE_IO=0 selects the separate kernels.
         self.fuse_io = os.environ.get("IDB200_FUSE_IO", "1") != "0"
         self.fuse_head = True            # the out head as the tile epilogue of the fused-encoder launch (h is not written back)
         self._cache = {}
