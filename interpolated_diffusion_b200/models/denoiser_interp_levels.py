@@ -149,7 +149,10 @@ class InterpLevelDenoiser(nn.Module):
         if out is None:
             out = torch.empty((B, T, D), device=dev, dtype=torch.float32)
         W_out, b_out = self.out.weight.detach().float().contiguous(), self.out.bias.detach().float().contiguous()
-        if self.fuse_io and pk.fused_path(T, self.precision) and W_out.shape[0] <= 4 and (film is None or isinstance(film, E.Film)):
+        # (the staged prologue needs <= 64 table rows, <= 8 features, T >= 8; other shapes are faster through the separate embed kernel
+        # unless fuse_io == "always")
+        staged = der["tab"].shape[0] <= 64 and der["Wf"].shape[0] <= 8 and T >= 8
+        if self.fuse_io and (staged or self.fuse_io == "always") and pk.fused_path(T, self.precision) and W_out.shape[0] <= 4 and (film is None or isinstance(film, E.Film)):
             # token assembly, all encoder layers and the out head in one launch: h never exists in HBM
             E.denoiser_fused(pk, film, T, bool(self.transformer.causal), M, L.f32c(x_s).view(M, D), src1, src2, der["Wf"], der["tab"], None,
                              level_vec, row_b, W_out, b_out, out.view(M, D))

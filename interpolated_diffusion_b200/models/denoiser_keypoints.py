@@ -142,7 +142,10 @@ class KeypointDenoiser(nn.Module):
             out = torch.empty((B, K, D), device=dev, dtype=torch.float32)
         W_out, b_out = self.out.weight.detach().float().contiguous(), self.out.bias.detach().float().contiguous()
         src1 = None if kp_feat is None else kp_feat.view(M, -1)
-        if self.fuse_io and pk.fused_path(K, self.precision) and W_out.shape[0] <= 4 and (film is None or isinstance(film, E.Film)):
+        # (the staged prologue needs <= 64 table rows, <= 8 features, K >= 8; other shapes are faster through the separate embed kernel
+        # unless fuse_io == "always")
+        staged = der["tab"].shape[0] <= 64 and der["Wf"].shape[0] <= 8 and K >= 8
+        if self.fuse_io and (staged or self.fuse_io == "always") and pk.fused_path(K, self.precision) and W_out.shape[0] <= 4 and (film is None or isinstance(film, E.Film)):
             # token assembly, all encoder layers and the out head in one launch: h never exists in HBM
             E.denoiser_fused(pk, film, K, bool(self.transformer.causal), M, z.view(M, D), src1, km.view(M, D), der["Wf"], der["tab"],
                              L.i64c(idx).view(M), t_vec, row_b, W_out, b_out, out.view(M, D))
