@@ -254,7 +254,7 @@ __device__ __forceinline__ void ln_tmem(uint32_t tmem_row, const float* sw, cons
 }
 
 // kProf (dev, IDB200_PROF=1): compute warp 0 lane 0 accumulates clock64() spans per phase into p.prof[0..15]
-enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_LNLD, P_LNENTRY, P_LDWAIT, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
+enum { P_LOAD, P_LN1, P_WACC, P_EPI, P_ATT, P_WO, P_OWR, P_WH1, P_LN2, P_WACC1, P_EPI1, P_WH2, P_STORE, P_WPA, P_LNP1, P_LNBAR, P_LNFILM, P_LNLD, P_LNENTRY, P_LDPRE, P_LDWAIT, P_MSLOT, P_MCOMP, P_MISSUE, P_N };
 
 // kPair: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  Each CTA still owns one 128-token tile (its
 // rows of h in its own TMEM, its own X / scratch / parameters), but the even CTA issues ONE M=256 MMA for both tiles
@@ -746,6 +746,7 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_con
                 const uint32_t tsw = static_cast<uint32_t>(trow & 7);
                 const uint32_t rb_s = smem_u32(smem + kOffERb) + static_cast<uint32_t>(live ? row / L : 0) * 1024u + col_s;
                 const uint32_t wf_s = smem_u32(smem + kOffEWf) + col_s, ras = smem_u32(smem + kOffERa) + col_s;
+                stamp(P_LDPRE);                                          // (dev: tile turnaround up to here; P_LDWAIT = the wait for the staged operands)
                 mbar_wait(tab_full, 0u, 62);
                 stamp(P_LDWAIT);                                         // (dev: tile turnaround up to the staged operands' arrival)
                 auto body = [&](auto kFtag) {
@@ -1175,7 +1176,7 @@ int encoder_fused(float* h, const float* params, const float* cb_total, const fl
         cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         static const char* names[ef::P_N] = {"load", "ln1", "wait_acc", "epi", "att", "wait_o", "o_write", "wait_h1", "ln2", "wait_acc1", "epi1",
-                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film", "ln_tmem_ld", "ln_entry)", "(load_until_staged)", "[mma: wait_slot", "wait_compute", "issue]"};
+                                             "wait_h2", "store", "wait_pa", "(ln_pass1", "ln_bar", "ln_film", "ln_tmem_ld", "ln_entry)", "(load_turnaround", "load_wait_staged)", "[mma: wait_slot", "wait_compute", "issue]"};
         const double units = static_cast<double>(tiles) * n_layers;
         fprintf(stderr, "encoder_fused prof (cycles per tile-layer, L=%d, pair=%d):", L, pair ? 1 : 0);
         double tot = 0;
