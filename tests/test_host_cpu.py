@@ -178,3 +178,27 @@ def test_causal_chunk_plan_host_logic():
     left, goal = torch.tensor([[0.0, 0.0]]), torch.tensor([[1.0, 2.0]])
     assert torch.allclose(_heuristic_right(left, goal, 16, 64), torch.tensor([[0.25, 0.5]]))
     assert torch.allclose(_heuristic_right(left, goal, 16, 8), goal)
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The argument structs of idb200_denoiser_fused as the Python binding lays them out (ctypes) against the C compiler's layout of
+    include/idb200.h: sizes and the offsets of the fields added last (an ABI drift here would be silent garbage on the device)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "idb200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(idb200_embed_t), offsetof(idb200_embed_t, tab_rows), offsetof(idb200_embed_t, row_b),\n'
+        "         offsetof(idb200_embed_t, row_a_stride), sizeof(idb200_head_t), offsetof(idb200_head_t, D));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([gcc, "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(L.EmbedDesc), L.EmbedDesc.tab_rows.offset, L.EmbedDesc.row_b.offset, L.EmbedDesc.row_a_stride.offset,
+            ctypes.sizeof(L.HeadDesc), L.HeadDesc.D.offset]
+    assert got == want, (got, want)
